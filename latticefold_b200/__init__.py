@@ -1,0 +1,6 @@
+"""latticefold_b200: Blackwell-native LatticeFold prover hot path.
+
+Importing the package does not load CUDA; `latticefold_b200.lib()` loads the C-ABI shared library
+(latticefold_b200/_lib/liblf_b200.so) and raises if it is missing -- there is no CPU fallback.
+"""
+from . import synth  # noqa: F401

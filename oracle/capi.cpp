@@ -1,0 +1,228 @@
+// TEST INFRASTRUCTURE ONLY (see ring.hpp header).  C entry points over the CPU oracle so that tests/, smoke()
+// and bench.py's cpu_baseline / --impl reference legs can drive it through ctypes.  Never linked into the product.
+//
+// All ring elements cross this boundary as d canonical u64 limbs (NTT form: slot-major; coefficient form:
+// power of X), vectors as contiguous arrays of such elements -- the same host format the product C-ABI uses.
+#include "protocol.hpp"
+#include <map>
+#include <memory>
+#include <chrono>
+#include <omp.h>
+
+using namespace lfo;
+
+namespace {
+const RingParams& ring(int id) {
+    static std::map<int, std::unique_ptr<RingParams>> cache;
+    #pragma omp critical(lfo_ring_cache)
+    { if (!cache.count(id)) cache[id].reset(new RingParams(make_ring(id))); }
+    return *cache[id];
+}
+thread_local std::string g_err;
+template <class F> int guard(F&& f) {
+    try { f(); return 0; }
+    catch (const LfError& e) { g_err = e.what(); return e.code; }
+    catch (const std::exception& e) { g_err = e.what(); return -100; }
+}
+Vec vec_of(const u64* p, size_t n_elems, int d) { return p ? Vec(p, p + n_elems * d) : Vec(); }
+}  // namespace
+
+extern "C" {
+
+const char* lfo_last_error() { return g_err.c_str(); }
+int lfo_num_threads() { return omp_get_max_threads(); }
+void lfo_set_num_threads(int n) { omp_set_num_threads(n); }
+
+// out[0..7] = p, d, S, tau, g, nu, trinomial, cs_bytes
+int lfo_ring_info(int id, u64* out) {
+    return guard([&] { const RingParams& R = ring(id); out[0] = R.F.p; out[1] = R.d; out[2] = R.S; out[3] = R.tau; out[4] = R.g; out[5] = R.nu; out[6] = R.trinomial; out[7] = R.cs_bytes; });
+}
+int lfo_crt(int id, const u64* in, u64* out, size_t n) {
+    return guard([&] { const RingParams& R = ring(id); Vec o = elementwise_crt(R, vec_of(in, n, R.d)); memcpy(out, o.data(), 8 * o.size()); });
+}
+int lfo_icrt(int id, const u64* in, u64* out, size_t n) {
+    return guard([&] { const RingParams& R = ring(id); Vec o = elementwise_icrt(R, vec_of(in, n, R.d)); memcpy(out, o.data(), 8 * o.size()); });
+}
+int lfo_coeff_mul(int id, const u64* a, const u64* b, u64* out) { return guard([&] { coeff_mul(ring(id), out, a, b); }); }
+int lfo_ntt_mul(int id, const u64* a, const u64* b, u64* out, size_t n) {
+    return guard([&] { const RingParams& R = ring(id); for (size_t i = 0; i < n; ++i) ntt_mul(R, out + i * R.d, a + i * R.d, b + i * R.d); });
+}
+int lfo_gadget_decompose(int id, const u64* in, size_t n, u64 B_lo, u64 B_hi, int L, u64* out) {
+    return guard([&] { const RingParams& R = ring(id); Vec o = gadget_decompose(R, vec_of(in, n, R.d), ((u128)B_hi << 64) | B_lo, L); memcpy(out, o.data(), 8 * o.size()); });
+}
+int lfo_gadget_recompose(int id, const u64* in, size_t n_in, u64 B_lo, u64 B_hi, int L, u64* out) {
+    return guard([&] { const RingParams& R = ring(id); Vec o = gadget_recompose(R, vec_of(in, n_in, R.d), ((u128)B_hi << 64) | B_lo, L); memcpy(out, o.data(), 8 * o.size()); });
+}
+// out: K x n x d (piece-major)
+int lfo_decompose_to_vec(int id, const u64* in, size_t n, u64 b, int K, u64* out) {
+    return guard([&] { const RingParams& R = ring(id); auto ps = decompose_to_k_vecs(R, vec_of(in, n, R.d), b, K);
+                       for (int k = 0; k < K; ++k) memcpy(out + (size_t)k * n * R.d, ps[k].data(), 8 * n * R.d); });
+}
+// out: tau x n x d (zero padded), lens[tau] = effective (truncated) lengths
+int lfo_fhat(int id, const u64* f_coeff, size_t n, u64* out, u64* lens) {
+    return guard([&] { const RingParams& R = ring(id); auto fh = get_fhat(R, vec_of(f_coeff, n, R.d));
+                       memset(out, 0, 8 * (size_t)R.tau * n * R.d);
+                       for (int j = 0; j < R.tau; ++j) { memcpy(out + (size_t)j * n * R.d, fh[j].ev.data(), 8 * fh[j].ev.size()); lens[j] = fh[j].len(); } });
+}
+int lfo_commit(int id, const u64* A, size_t kappa, size_t n, const u64* f, size_t nf, u64* out) {
+    return guard([&] { const RingParams& R = ring(id); Ajtai S; S.kappa = kappa; S.n = n; S.A = vec_of(A, kappa * n, R.d);
+                       Vec cm = ajtai_commit(R, S, vec_of(f, nf, R.d)); memcpy(out, cm.data(), 8 * cm.size()); });
+}
+int lfo_spmv(int id, size_t nrows, size_t ncols, const u64* row_ptr, const u64* col, const u64* val, const u64* z, size_t nz, u64* out) {
+    return guard([&] { const RingParams& R = ring(id); SparseMatrix M; M.nrows = nrows; M.ncols = ncols; M.row_ptr.assign(row_ptr, row_ptr + nrows + 1);
+                       M.col.assign(col, col + row_ptr[nrows]); M.val = vec_of(val, row_ptr[nrows], R.d);
+                       Vec o = mat_vec_mul(R, M, vec_of(z, nz, R.d)); memcpy(out, o.data(), 8 * o.size()); });
+}
+int lfo_eq_table(int id, const u64* r, int s, u64* out) {
+    return guard([&] { const RingParams& R = ring(id); Mle m = build_eq_x_r(R, r, s); memcpy(out, m.ev.data(), 8 * m.ev.size()); });
+}
+int lfo_eq_eval(int id, const u64* x, const u64* y, int n, u64* out) { return guard([&] { eq_eval(ring(id), x, y, n, out); }); }
+// mles: count x len x d ; all with num_vars nv; point: np ring elements
+int lfo_evaluate_mles(int id, const u64* mles, int count, size_t len, int nv, const u64* point, int np, u64* out) {
+    return guard([&] { const RingParams& R = ring(id); std::vector<Mle> ms;
+                       for (int k = 0; k < count; ++k) ms.push_back(mle_from(R, nv, mles + (size_t)k * len * R.d, len));
+                       Vec o = evaluate_mles(R, ms, vec_of(point, np, R.d)); memcpy(out, o.data(), 8 * o.size()); });
+}
+int lfo_rot_lin_combination(int id, const u64* rho_coeff, const u64* theta, int count, u64* out) {
+    return guard([&] { const RingParams& R = ring(id); std::vector<Vec> rho, th;
+                       for (int i = 0; i < count; ++i) { rho.push_back(vec_of(rho_coeff + (size_t)i * R.d, 1, R.d)); th.push_back(vec_of(theta + (size_t)i * R.tau * R.d, R.tau, R.d)); }
+                       Vec o = rot_lin_combination(R, rho, th); memcpy(out, o.data(), 8 * o.size()); });
+}
+int lfo_short_challenge_from_bytes(int id, const uint8_t* bs, u64* coeffs) { return guard([&] { short_challenge_from_bytes(ring(id), bs, coeffs); }); }
+
+// ------------------------------------------------------------------ transcript handles
+void* lfo_tr_new(int id) { try { return new Transcript(ring(id)); } catch (...) { return nullptr; } }
+void* lfo_tr_clone(void* h) { return new Transcript(*(Transcript*)h); }
+void lfo_tr_free(void* h) { delete (Transcript*)h; }
+void lfo_tr_absorb(void* h, const u64* els, size_t n) { ((Transcript*)h)->absorb_slice(els, n); }
+void lfo_tr_absorb_base(void* h, const u64* limbs, size_t n) { ((Transcript*)h)->sp.absorb(limbs, n); }   // raw sponge absorb (KATs)
+void lfo_tr_absorb_tag(void* h, const char* tag) { ((Transcript*)h)->absorb_tag(tag); }
+void lfo_tr_absorb_u64(void* h, u64 x) { ((Transcript*)h)->absorb_u64(x); }
+void lfo_tr_squeeze_base(void* h, u64* out, size_t n) { ((Transcript*)h)->sp.squeeze(out, n); }
+void lfo_tr_get_challenge(void* h, u64* sf) { ((Transcript*)h)->get_challenge(sf); }
+void lfo_tr_get_short_challenge(void* h, u64* coeffs) { ((Transcript*)h)->get_short_challenge(coeffs); }
+void lfo_tr_state(void* h, u64* out24) { memcpy(out24, ((Transcript*)h)->sp.st, sizeof(((Transcript*)h)->sp.st)); }
+
+// ------------------------------------------------------------------ stand-alone sumcheck
+// comb_kind: 0 = PRODUCTS (sum_i coef_i * prod_{j in idx_i} v_j), 1 = LIN, 2 = FOLD.
+// For 0/1: nterms, coef (nterms x d), idx_flat + idx_len[nterms].  For 2: n_mu, b, mu (n_mu x d).
+// mles: M x len x d, effective lengths lens[M] (<= len).  Outputs: msgs nv x (deg+1) x d; point nv x tau.
+int lfo_sumcheck_prove(int id, void* tr, const u64* mles, int M, size_t len, const u64* lens, int nv, int degree, int comb_kind,
+                       int nterms, const u64* coef, const int* idx_flat, const int* idx_len, int n_mu, int b, const u64* mu,
+                       u64* msgs, u64* point, u64* final_vals /* M x d after applying the last challenge, may be null */) {
+    return guard([&] {
+        const RingParams& R = ring(id); Comb C; C.kind = comb_kind;
+        if (comb_kind != COMB_FOLD) { int o = 0; for (int i = 0; i < nterms; ++i) { C.coef.push_back(vec_of(coef + (size_t)i * R.d, 1, R.d)); C.idx.emplace_back(idx_flat + o, idx_flat + o + idx_len[i]); o += idx_len[i]; } }
+        else { C.n_mu = n_mu; C.tau = R.tau; C.b = b; C.mu = vec_of(mu, n_mu, R.d); }
+        std::vector<Mle> ms; for (int k = 0; k < M; ++k) ms.push_back(mle_from(R, nv, mles + (size_t)k * len * R.d, lens ? lens[k] : len));
+        std::vector<std::vector<u64>> pt; ProverState st;
+        SumcheckProof pf = prove_as_subprotocol(R, *(Transcript*)tr, std::move(ms), nv, degree, C, pt, &st);
+        memcpy(msgs, pf.msgs.data(), 8 * pf.msgs.size());
+        for (int i = 0; i < nv; ++i) memcpy(point + (size_t)i * R.tau, pt[i].data(), 8 * R.tau);
+        if (final_vals) { Vec r(R.d); ntt_from_sf(R, r.data(), pt[nv - 1].data());
+                          for (int k = 0; k < M; ++k) { Mle m = st.mles[k]; mle_fix_low(R, m, r.data()); mle_get(R, m, 0, final_vals + (size_t)k * R.d); } }
+    });
+}
+// claimed_sum: d limbs.  returns 0 and fills expected (d limbs) + point on accept, ERR_SUMCHECK_FAILED otherwise
+int lfo_sumcheck_verify(int id, void* tr, int nv, int degree, const u64* claimed_sum, const u64* msgs, u64* expected, u64* point) {
+    return guard([&] {
+        const RingParams& R = ring(id); SumcheckProof pf; pf.nvars = nv; pf.degree = degree; pf.msgs.assign(msgs, msgs + (size_t)nv * (degree + 1) * R.d);
+        SubClaim sc = verify_as_subprotocol(R, *(Transcript*)tr, nv, degree, claimed_sum, pf);
+        if (!sc.ok) throw LfError(ERR_SUMCHECK_FAILED, "SumCheckFailed");
+        memcpy(expected, sc.expected.data(), 8 * R.d);
+        for (int i = 0; i < nv; ++i) memcpy(point + (size_t)i * R.tau, sc.point[i].data(), 8 * R.tau);
+    });
+}
+
+// ------------------------------------------------------------------ the full prover step on flat inputs
+struct lfo_csr { u64 nrows, ncols; const u64* row_ptr; const u64* col; const u64* val; };
+struct lfo_problem {
+    int ring; int L, K; u64 B_lo, B_hi, b;
+    u64 kappa, n; const u64* A;                              // Ajtai matrix kappa x n x d (NTT form)
+    u64 m, n_ccs, l, t, q, d, s;                             // CCS shape (arith.rs:51-74)
+    const lfo_csr* M; const int* S_flat; const int* S_len; const u64* c;   // t matrices; q multisets; q ring elements
+    const u64 *acc_r, *acc_v, *acc_cm, *acc_u, *acc_x_w, *acc_h;           // running LCCCS
+    const u64* w_acc_f;                                      // accumulator witness, NTT form, n x d  (Witness::from_f)
+    const u64 *cm_i_cm, *cm_i_x_ccs;                         // incoming CCCS
+    const u64* w_i_f;                                        // incoming witness f (NTT form, n x d)
+};
+static void load_problem(const lfo_problem& P, const RingParams& R, DecompParams& dp, CCS& ccs, Ajtai& sch, LCCCS& acc, CCCS& cmi) {
+    dp.B = ((u128)P.B_hi << 64) | P.B_lo; dp.L = P.L; dp.b = P.b; dp.K = P.K;
+    ccs.m = P.m; ccs.n = P.n_ccs; ccs.l = P.l; ccs.t = P.t; ccs.q = P.q; ccs.d = P.d; ccs.s = P.s;
+    int o = 0;
+    for (u64 i = 0; i < P.q; ++i) { ccs.S.emplace_back(P.S_flat + o, P.S_flat + o + P.S_len[i]); o += P.S_len[i]; }
+    ccs.c = vec_of(P.c, P.q, R.d);
+    for (u64 j = 0; j < P.t; ++j) { SparseMatrix M; M.nrows = P.M[j].nrows; M.ncols = P.M[j].ncols; M.row_ptr.assign(P.M[j].row_ptr, P.M[j].row_ptr + M.nrows + 1);
+                                    u64 nnz = M.row_ptr[M.nrows]; M.col.assign(P.M[j].col, P.M[j].col + nnz); M.val = vec_of(P.M[j].val, nnz, R.d); ccs.M.push_back(std::move(M)); }
+    if (P.A) { sch.kappa = P.kappa; sch.n = P.n; sch.A = vec_of(P.A, P.kappa * P.n, R.d); }
+    if (P.acc_r) { acc.r = vec_of(P.acc_r, P.s, R.d); acc.v = vec_of(P.acc_v, R.tau, R.d); acc.cm = vec_of(P.acc_cm, P.kappa, R.d); acc.u = vec_of(P.acc_u, P.t, R.d);
+                   acc.x_w = vec_of(P.acc_x_w, P.l, R.d); acc.h = vec_of(P.acc_h, 1, R.d); }
+    cmi.cm = vec_of(P.cm_i_cm, P.kappa, R.d); cmi.x_ccs = vec_of(P.cm_i_x_ccs, P.l, R.d);
+}
+static void put(u64*& p, const Vec& v) { memcpy(p, v.data(), 8 * v.size()); p += v.size(); }
+static void get(const u64*& p, Vec& v, size_t n) { v.assign(p, p + n); p += n; }
+static size_t lcccs_words(const lfo_problem& P, const RingParams& R) { return (P.s + R.tau + P.kappa + P.t + P.l + 1) * R.d; }
+static void put_lcccs(u64*& p, const LCCCS& L) { put(p, L.r); put(p, L.v); put(p, L.cm); put(p, L.u); put(p, L.x_w); put(p, L.h); }
+
+// number of u64 words of the serialized proof for this problem shape
+u64 lfo_proof_words(const lfo_problem* P) {
+    const RingParams& R = ring(P->ring); u64 d = R.d, tau = R.tau;
+    u64 lin = P->s * (P->d + 2) * d + tau * d + P->t * d;
+    u64 dec = (u64)P->K * ((P->l + 1) + P->kappa + P->t + tau) * d;
+    u64 fold = P->s * (2 * P->b + 1) * d + 2 * (u64)P->K * (tau + P->t) * d;
+    return lin + 2 * dec + fold;
+}
+u64 lfo_lcccs_words(const lfo_problem* P) { return lcccs_words(*P, ring(P->ring)); }
+static void put_proof(u64*& p, const LFProof& pf) {
+    put(p, pf.lin.sumcheck.msgs); put(p, pf.lin.v); put(p, pf.lin.u);
+    for (const DecompositionProof* dp : {&pf.dl, &pf.dr}) for (size_t k = 0; k < dp->x_s.size(); ++k) { put(p, dp->x_s[k]); put(p, dp->y_s[k]); put(p, dp->u_s[k]); put(p, dp->v_s[k]); }
+    put(p, pf.fold.sumcheck.msgs); for (auto& v : pf.fold.theta_s) put(p, v); for (auto& v : pf.fold.eta_s) put(p, v);
+}
+static void get_proof(const u64*& p, LFProof& pf, const lfo_problem& P, const RingParams& R) {
+    size_t d = R.d, tau = R.tau;
+    pf.lin.sumcheck.nvars = (int)P.s; pf.lin.sumcheck.degree = (int)P.d + 1; get(p, pf.lin.sumcheck.msgs, P.s * (P.d + 2) * d); get(p, pf.lin.v, tau * d); get(p, pf.lin.u, P.t * d);
+    for (DecompositionProof* dp : {&pf.dl, &pf.dr}) { dp->x_s.resize(P.K); dp->y_s.resize(P.K); dp->u_s.resize(P.K); dp->v_s.resize(P.K);
+        for (int k = 0; k < P.K; ++k) { get(p, dp->x_s[k], (P.l + 1) * d); get(p, dp->y_s[k], P.kappa * d); get(p, dp->u_s[k], P.t * d); get(p, dp->v_s[k], tau * d); } }
+    pf.fold.sumcheck.nvars = (int)P.s; pf.fold.sumcheck.degree = 2 * (int)P.b; get(p, pf.fold.sumcheck.msgs, P.s * (2 * P.b + 1) * d);
+    pf.fold.theta_s.resize(2 * P.K); pf.fold.eta_s.resize(2 * P.K);
+    for (auto& v : pf.fold.theta_s) get(p, v, tau * d); for (auto& v : pf.fold.eta_s) get(p, v, P.t * d);
+}
+
+// Witness::commit (arith.rs:357-362) for a witness given by f
+// LFLinearizationProver::prove on (cm_i, w_i): fills out_lcccs (lcccs_words) and lin proof part (msgs, v, u).
+int lfo_linearize(const lfo_problem* P, void* tr, u64* out_lcccs, u64* out_proof /* s*(d+2)*dd + tau*dd + t*dd */) {
+    return guard([&] {
+        const RingParams& R = ring(P->ring); DecompParams dp; CCS ccs; Ajtai sch; LCCCS acc; CCCS cmi; load_problem(*P, R, dp, ccs, sch, acc, cmi);
+        Witness wi = witness_from_f(R, dp, vec_of(P->w_i_f, P->n, R.d));
+        LCCCS out; LinearizationProof pf; linearization_prove(R, cmi, wi, *(Transcript*)tr, ccs, out, pf);
+        u64* p = out_lcccs; put_lcccs(p, out);
+        if (out_proof) { p = out_proof; put(p, pf.sumcheck.msgs); put(p, pf.v); put(p, pf.u); }
+    });
+}
+// NIFSProver::prove (nifs.rs:48-103).  out_proof: lfo_proof_words; out_lcccs: lfo_lcccs_words; out_f: n x d (folded witness, NTT form)
+// timing_ms (optional, 4 doubles): linearization, decomposition x2, folding, total
+int lfo_nifs_prove(const lfo_problem* P, void* tr, u64* out_proof, u64* out_lcccs, u64* out_f, double* timing_ms) {
+    return guard([&] {
+        const RingParams& R = ring(P->ring); DecompParams dp; CCS ccs; Ajtai sch; LCCCS acc; CCCS cmi; load_problem(*P, R, dp, ccs, sch, acc, cmi);
+        Witness wa = witness_from_f(R, dp, vec_of(P->w_acc_f, P->n, R.d)), wi = witness_from_f(R, dp, vec_of(P->w_i_f, P->n, R.d));
+        LCCCS out; Witness wo; LFProof pf;
+        auto t0 = std::chrono::steady_clock::now();
+        nifs_prove(R, dp, acc, wa, cmi, wi, *(Transcript*)tr, ccs, sch, out, wo, pf);
+        auto t1 = std::chrono::steady_clock::now();
+        if (timing_ms) timing_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        u64* p = out_proof; put_proof(p, pf);
+        p = out_lcccs; put_lcccs(p, out);
+        if (out_f) memcpy(out_f, wo.f.data(), 8 * wo.f.size());
+    });
+}
+// NIFSVerifier::verify (nifs.rs:117-162): returns 0 when the proof is accepted and fills out_lcccs
+int lfo_nifs_verify(const lfo_problem* P, void* tr, const u64* proof, u64* out_lcccs) {
+    return guard([&] {
+        const RingParams& R = ring(P->ring); DecompParams dp; CCS ccs; Ajtai sch; LCCCS acc; CCCS cmi; load_problem(*P, R, dp, ccs, sch, acc, cmi);
+        LFProof pf; const u64* p = proof; get_proof(p, pf, *P, R);
+        LCCCS out; nifs_verify(R, dp, acc, cmi, pf, *(Transcript*)tr, ccs, out);
+        if (out_lcccs) { u64* q = out_lcccs; put_lcccs(q, out); }
+    });
+}
+
+}  // extern "C"

@@ -31,10 +31,12 @@ inline void mle_get(const RingParams& R, const Mle& m, size_t i, u64* out) {
 // fix the lowest variable to the ring element r: new[b] = old[2b] + r*(old[2b+1]-old[2b])
 inline void mle_fix_low(const RingParams& R, Mle& m, const u64* r) {
     size_t half = (size_t)1 << (m.nv - 1); size_t nl = std::min(half, (m.len() + 1) / 2);
-    std::vector<u64> out(nl * R.d); std::vector<u64> a(R.d), b(R.d), t(R.d);
-    for (size_t i = 0; i < nl; ++i) {
-        mle_get(R, m, 2 * i, a.data()); mle_get(R, m, 2 * i + 1, b.data());
-        el_sub(R, t.data(), b.data(), a.data()); ntt_mul(R, t.data(), t.data(), r); el_add(R, out.data() + i * R.d, a.data(), t.data());
+    std::vector<u64> out(nl * R.d);
+    #pragma omp parallel for schedule(static) if (nl > 256)
+    for (long i = 0; i < (long)nl; ++i) {
+        u64 a[128], b[128], t[128];
+        mle_get(R, m, 2 * (size_t)i, a); mle_get(R, m, 2 * (size_t)i + 1, b);
+        el_sub(R, t, b, a); ntt_mul(R, t, t, r); el_add(R, out.data() + (size_t)i * R.d, a, t);
     }
     m.ev.swap(out); m.nv -= 1;
 }
@@ -85,44 +87,44 @@ struct Comb {
     int n_mu = 0, tau = 0, b = 0; std::vector<u64> mu;  // n_mu ring elements
 };
 inline void comb_eval(const RingParams& R, const Comb& C, const u64* vals /* M x d */, int M, u64* out) {
-    const int d = R.d; std::vector<u64> res(d, 0), term(d), t(d);
+    const int d = R.d; u64 res[128], term[128], t[128]; memset(res, 0, 8 * d);
     if (C.kind == COMB_PRODUCTS || C.kind == COMB_LIN) {
         for (size_t i = 0; i < C.coef.size(); ++i) {
             if (C.kind == COMB_LIN && el_is_zero(R, C.coef[i].data())) continue;
-            term = C.coef[i]; bool skip = false;
+            memcpy(term, C.coef[i].data(), 8 * d); bool skip = false;
             for (int j : C.idx[i]) {
                 if (C.kind == COMB_LIN && el_is_zero(R, vals + (size_t)j * d)) { skip = true; break; }
-                ntt_mul(R, term.data(), term.data(), vals + (size_t)j * d);
+                ntt_mul(R, term, term, vals + (size_t)j * d);
             }
-            if (!skip) el_add(R, res.data(), res.data(), term.data());
+            if (!skip) el_add(R, res, res, term);
         }
-        if (C.kind == COMB_LIN) ntt_mul(R, res.data(), res.data(), vals + (size_t)(M - 1) * d);  // eq() is the last MLE
-        memcpy(out, res.data(), 8 * d); return;
+        if (C.kind == COMB_LIN) ntt_mul(R, res, res, vals + (size_t)(M - 1) * d);  // eq() is the last MLE
+        memcpy(out, res, 8 * d); return;
     }
     // FOLD: v0*v1 + v2*v3 + sum_k mu-Horner over d of v4 * f * prod_{j=1}^{b-1}(f^2 - j^2)
-    std::vector<u64> inter(d), ev(d), f2(d), mult(d), jj(d);
-    ntt_mul(R, res.data(), vals, vals + d);
-    ntt_mul(R, t.data(), vals + 2 * (size_t)d, vals + 3 * (size_t)d); el_add(R, res.data(), res.data(), t.data());
+    u64 inter[128], ev[128], f2[128], mult[128], jj[128];
+    ntt_mul(R, res, vals, vals + d);
+    ntt_mul(R, t, vals + 2 * (size_t)d, vals + 3 * (size_t)d); el_add(R, res, res, t);
     for (int k = 0; k < C.n_mu; ++k) {
         const u64* mu = C.mu.data() + (size_t)k * d;
-        std::fill(inter.begin(), inter.end(), 0);
+        memset(inter, 0, 8 * d);
         for (int dd = C.tau - 1; dd >= 0; --dd) {
             const u64* f = vals + (size_t)(5 + k * C.tau + dd) * d;
-            if (el_is_zero(R, f)) { if (!el_is_zero(R, inter.data())) ntt_mul(R, inter.data(), inter.data(), mu); continue; }
-            memcpy(ev.data(), vals + 4 * (size_t)d, 8 * d);
-            ntt_mul(R, f2.data(), f, f);
+            if (el_is_zero(R, f)) { if (!el_is_zero(R, inter)) ntt_mul(R, inter, inter, mu); continue; }
+            memcpy(ev, vals + 4 * (size_t)d, 8 * d);
+            ntt_mul(R, f2, f, f);
             for (int j = 1; j < C.b; ++j) {
-                ntt_from_u64(R, jj.data(), (u64)j * j); el_sub(R, mult.data(), f2.data(), jj.data());
-                if (el_is_zero(R, mult.data())) { std::fill(ev.begin(), ev.end(), 0); break; }
-                ntt_mul(R, ev.data(), ev.data(), mult.data());
+                ntt_from_u64(R, jj, (u64)j * j); el_sub(R, mult, f2, jj);
+                if (el_is_zero(R, mult)) { memset(ev, 0, 8 * d); break; }
+                ntt_mul(R, ev, ev, mult);
             }
-            ntt_mul(R, ev.data(), ev.data(), f);
-            el_add(R, inter.data(), inter.data(), ev.data());
-            ntt_mul(R, inter.data(), inter.data(), mu);
+            ntt_mul(R, ev, ev, f);
+            el_add(R, inter, inter, ev);
+            ntt_mul(R, inter, inter, mu);
         }
-        el_add(R, res.data(), res.data(), inter.data());
+        el_add(R, res, res, inter);
     }
-    memcpy(out, res.data(), 8 * d);
+    memcpy(out, res, 8 * d);
 }
 
 // ---------------------------------------------------------------- prover
@@ -141,17 +143,24 @@ inline void prove_round(const RingParams& R, ProverState& st, const u64* prev, c
     st.round += 1;
     if (st.round > st.nv) throw std::runtime_error("Prover is not active");
     const int M = (int)st.mles.size(), deg = st.deg; const size_t nb = (size_t)1 << (st.nv - st.round);
-    std::vector<u64> evals((deg + 1) * d, 0), v0(M * d), v1(M * d), steps(M * d), vals(M * d), lev(d);
-    for (size_t b = 0; b < nb; ++b) {
-        for (int k = 0; k < M; ++k) { mle_get(R, st.mles[k], 2 * b, v0.data() + (size_t)k * d); mle_get(R, st.mles[k], 2 * b + 1, v1.data() + (size_t)k * d); }
-        comb_eval(R, C, v0.data(), M, lev.data()); el_add(R, evals.data(), evals.data(), lev.data());
-        comb_eval(R, C, v1.data(), M, lev.data()); el_add(R, evals.data() + d, evals.data() + d, lev.data());
-        for (int k = 0; k < M; ++k) { el_sub(R, steps.data() + (size_t)k * d, v1.data() + (size_t)k * d, v0.data() + (size_t)k * d); }
-        vals = v1;
-        for (int e = 2; e <= deg; ++e) {
-            for (int k = 0; k < M; ++k) el_add(R, vals.data() + (size_t)k * d, vals.data() + (size_t)k * d, steps.data() + (size_t)k * d);
-            comb_eval(R, C, vals.data(), M, lev.data()); el_add(R, evals.data() + (size_t)e * d, evals.data() + (size_t)e * d, lev.data());
+    std::vector<u64> evals((deg + 1) * d, 0);
+    #pragma omp parallel if (nb > 16)
+    {   // rayon fold over b (prover.rs:111-143) then reduce (prover.rs:145-161)
+        std::vector<u64> le((deg + 1) * d, 0), v0(M * d), v1(M * d), steps(M * d), vals(M * d), lev(d);
+        #pragma omp for schedule(static) nowait
+        for (long b = 0; b < (long)nb; ++b) {
+            for (int k = 0; k < M; ++k) { mle_get(R, st.mles[k], 2 * (size_t)b, v0.data() + (size_t)k * d); mle_get(R, st.mles[k], 2 * (size_t)b + 1, v1.data() + (size_t)k * d); }
+            comb_eval(R, C, v0.data(), M, lev.data()); el_add(R, le.data(), le.data(), lev.data());
+            comb_eval(R, C, v1.data(), M, lev.data()); el_add(R, le.data() + d, le.data() + d, lev.data());
+            for (int k = 0; k < M; ++k) { el_sub(R, steps.data() + (size_t)k * d, v1.data() + (size_t)k * d, v0.data() + (size_t)k * d); }
+            vals = v1;
+            for (int e = 2; e <= deg; ++e) {
+                for (int k = 0; k < M; ++k) el_add(R, vals.data() + (size_t)k * d, vals.data() + (size_t)k * d, steps.data() + (size_t)k * d);
+                comb_eval(R, C, vals.data(), M, lev.data()); el_add(R, le.data() + (size_t)e * d, le.data() + (size_t)e * d, lev.data());
+            }
         }
+        #pragma omp critical
+        for (int e = 0; e <= deg; ++e) el_add(R, evals.data() + (size_t)e * d, evals.data() + (size_t)e * d, le.data() + (size_t)e * d);
     }
     memcpy(evals_out, evals.data(), 8 * (size_t)(deg + 1) * d);
 }
