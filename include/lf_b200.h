@@ -1,0 +1,205 @@
+/* lf_b200.h -- C ABI of liblf_b200.so, the B200 (sm_100a) implementation of the LatticeFold prover hot path.
+ *
+ * The reference (NethermindEth/latticefold, Rust) has no FFI or plugin registry: the hot path sits behind generic
+ * Rust functions.  Each entry point below replaces one of those call sites; the Rust-side binding a
+ * maintainer would add (a `lf-b200-sys` crate + wrapper types) is shown in INTEGRATION.md.  File:line citations are
+ * relative to the reference tree.
+ *
+ * Conventions
+ *   - Ring element on the host side: D consecutive little-endian u64 limbs, canonical (value in [0,p)).
+ *       NTT form:          limb index = slot * TAU + l          (what `RqNTT` holds; transcript/poseidon.rs:40-47)
+ *       coefficient form:  limb index = power of X              (what `RqPoly` holds)
+ *     Host vectors are contiguous arrays of such elements (the memory image of `Vec<R>` after `into_bigint()`).
+ *   - Device vectors are opaque (`lf_vec`): limb-plane ("SoA") layout, see DESIGN.md.
+ *   - Every function returns an `lf_status`; 0 is success, negative values mirror the reference's error enums.
+ *     Nothing aborts; `lf_last_error(ctx)` gives the message of the last failure on that context.
+ *   - One context = one (GPU, ring).  Calls on one context must be serialised by the caller; different contexts
+ *     are independent (the reference calls `commit` from rayon workers: give each worker its own stream context
+ *     or batch with lf_commit_batch).
+ *   - There is no CPU fallback: without a CUDA device lf_ctx_create fails with LF_ERR_CUDA.
+ */
+#ifndef LF_B200_H
+#define LF_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t lf_status;
+enum {
+    LF_OK = 0,
+    LF_ERR_WRONG_WITNESS_LEN = -1, /* CommitmentError::WrongWitnessLength      commitment.rs:14-26            */
+    LF_ERR_LENGTHS_NOT_EQUAL = -2, /* CSError::LengthsNotEqual                 arith/error.rs:8-29            */
+    LF_ERR_MLE_LEN = -3,           /* MleEvaluationError::IncorrectLength      utils/mle_helpers.rs:21-63     */
+    LF_ERR_INVALID_SIZE_BOUNDS = -4, /* LatticefoldError / sanity_check        nifs.rs:165-173                */
+    LF_ERR_INCORRECT_LENGTH = -5,  /* *Error::IncorrectLength                  nifs/error.rs:13-66            */
+    LF_ERR_SUMCHECK_MISUSE = -6,   /* the panics of sumcheck/prover.rs:41,63,74,80 reported as a status       */
+    LF_ERR_UNSUPPORTED = -8,       /* ring / parameter outside what this build implements                     */
+    LF_ERR_DOES_NOT_FIT = -9,      /* a coefficient needs more digits than requested                          */
+    LF_ERR_CUDA = -20,
+    LF_ERR_INVALID_ARG = -21
+};
+
+enum { LF_RING_GOLDILOCKS = 0, LF_RING_BABYBEAR = 1, LF_RING_FROG = 2 };  /* cyclotomic-rings/src/rings/{goldilocks,babybear,frog}.rs:9-20 */
+enum { LF_FORM_NTT = 0, LF_FORM_COEFF = 1 };
+
+typedef struct lf_ctx lf_ctx;
+typedef struct lf_vec lf_vec;           /* device vector of ring elements                                         */
+typedef struct lf_ajtai lf_ajtai;       /* AjtaiCommitmentScheme<R>{matrix}         commitment_scheme.rs:17-35    */
+typedef struct lf_sparse lf_sparse;     /* SparseMatrix<R> as CSR                   arith/r1cs.rs:188-223         */
+typedef struct lf_sumcheck lf_sumcheck; /* IPForMLSumcheck ProverState              sumcheck/prover.rs:19-31      */
+typedef struct lf_transcript lf_transcript; /* PoseidonTranscript<R, CS> (host)     transcript/poseidon.rs:18-27  */
+
+typedef struct { uint64_t p; int32_t d, n_slots, tau; uint64_t nu; } lf_ring_info;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+lf_status lf_ring_describe(int32_t ring_id, lf_ring_info* out);
+lf_status lf_ctx_create(int32_t ring_id, int32_t device, lf_ctx** out);
+void lf_ctx_destroy(lf_ctx* ctx);
+const char* lf_last_error(const lf_ctx* ctx);            /* ctx may be NULL: last creation error               */
+lf_status lf_ctx_sync(lf_ctx* ctx);
+void* lf_ctx_stream(lf_ctx* ctx);                        /* the cudaStream_t every call of this context uses   */
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t lf_ctx_launches(const lf_ctx* ctx);
+/* measurement aid: with profiling on, every kernel launch is bracketed by CUDA events on the context's stream;
+ * the report is one line "kernel_name launches total_ms" per kernel.  Off by default (it adds two event records per launch). */
+lf_status lf_ctx_profile(lf_ctx* ctx, int32_t enable);
+lf_status lf_ctx_profile_report(lf_ctx* ctx, char* buf, size_t buf_len);
+
+/* ---- vectors: Vec<R> <-> device ------------------------------------------------------------------------------- */
+lf_status lf_vec_upload(lf_ctx* ctx, const uint64_t* host, size_t n, int32_t form, lf_vec** out);
+lf_status lf_vec_download(lf_ctx* ctx, const lf_vec* v, uint64_t* host);
+size_t lf_vec_len(const lf_vec* v);
+int32_t lf_vec_form(const lf_vec* v);
+void lf_vec_free(lf_ctx* ctx, lf_vec* v);
+
+/* ---- a2/a3: CRT::elementwise_crt / ICRT::elementwise_icrt (arith.rs:232,238,300,327; commitment_scheme.rs:85,110) */
+lf_status lf_crt(lf_ctx* ctx, const lf_vec* in_coeff, lf_vec** out_ntt);
+lf_status lf_icrt(lf_ctx* ctx, const lf_vec* in_ntt, lf_vec** out_coeff);
+
+/* ---- a4: balanced decompositions (arith.rs:235,305,330; decomposition/utils.rs:23-49)                           */
+/* gadget_decompose(B, L): element i -> elements [i*L, (i+1)*L), digit l has weight B^l                            */
+lf_status lf_gadget_decompose(lf_ctx* ctx, const lf_vec* in_coeff, uint64_t B, int32_t L, lf_vec** out_coeff);
+/* gadget_recompose(B, L): out[i] = sum_l in[i*L+l] * B^l (either form)                                            */
+lf_status lf_gadget_recompose(lf_ctx* ctx, const lf_vec* in, uint64_t B, int32_t L, lf_vec** out);
+/* decompose_to_vec(b, K).transpose(): K vectors, piece k has weight b^k (decomposition.rs:162-167,288-292)        */
+lf_status lf_decompose_to_vec(lf_ctx* ctx, const lf_vec* in_coeff, uint64_t b, int32_t K, lf_vec** out_coeff_k);
+
+/* ---- a5: Witness::get_fhat (arith.rs:273-297): tau NTT-form MLE tables from one coefficient-form vector         */
+lf_status lf_fhat(lf_ctx* ctx, const lf_vec* in_coeff, lf_vec** out_tau);
+
+/* ---- a1/a12: AjtaiCommitmentScheme (commitment_scheme.rs:17-114)                                                */
+lf_status lf_ajtai_create(lf_ctx* ctx, size_t kappa, size_t n, const uint64_t* host_matrix_ntt, lf_ajtai** out);
+void lf_ajtai_free(lf_ctx* ctx, lf_ajtai* a);
+size_t lf_ajtai_kappa(const lf_ajtai* a);
+size_t lf_ajtai_width(const lf_ajtai* a);
+/* commit / commit_ntt: out_host = kappa ring elements.  Length mismatch -> LF_ERR_WRONG_WITNESS_LEN               */
+lf_status lf_commit(lf_ctx* ctx, const lf_ajtai* a, const lf_vec* f_ntt, uint64_t* out_host);
+/* the K-1 commits of one decomposition in a single pass over the matrix (decomposition.rs:178-201)                */
+lf_status lf_commit_batch(lf_ctx* ctx, const lf_ajtai* a, const lf_vec* const* f_ntt, int32_t count, uint64_t* out_host);
+
+/* ---- a6: mat_vec_mul / calculate_Mz_mles (arith/utils.rs:52-65; mle_helpers.rs:137-146)                          */
+lf_status lf_sparse_create(lf_ctx* ctx, size_t nrows, size_t ncols, const uint64_t* row_ptr, const uint64_t* col,
+                           const uint64_t* val_host_ntt, lf_sparse** out);
+void lf_sparse_free(lf_ctx* ctx, lf_sparse* m);
+lf_status lf_spmv(lf_ctx* ctx, const lf_sparse* m, const lf_vec* z_ntt, lf_vec** out_ntt);
+
+/* ---- a7: build_eq_x_r (sumcheck/utils.rs:100-170): r = s ring elements on the host, r[0] on bit 0               */
+lf_status lf_eq_table(lf_ctx* ctx, const uint64_t* r_host, int32_t s, lf_vec** out_ntt);
+
+/* ---- a9: evaluate_mles (mle_helpers.rs:65-88).  MLEs shorter than 2^s have an implicit zero tail; a vector longer
+ *      than 2^s or a point of the wrong length gives LF_ERR_MLE_LEN                                               */
+lf_status lf_mle_eval_batch(lf_ctx* ctx, const lf_vec* const* mles, int32_t count, int32_t num_vars,
+                            const uint64_t* point_host, int32_t point_len, uint64_t* out_host);
+
+/* ---- a11: compute_f_0 and the Horner MLE combinations (folding.rs:208-226,258-268) as one primitive              */
+lf_status lf_lincomb(lf_ctx* ctx, const uint64_t* coeffs_host_ntt, const lf_vec* const* vecs, int32_t count, lf_vec** out);
+
+/* ---- a8: MLSumcheck (utils/sumcheck.rs:53-80, sumcheck/prover.rs:56-162)
+ * A Rust closure cannot cross the ABI, so the combination functions the reference uses are enumerated:            */
+enum {
+    LF_COMB_PRODUCTS = 0, /* sum_i coef_i * prod_{j in idx_i} v_j                    sumcheck/utils.rs:60-73       */
+    LF_COMB_LIN = 1,      /* (sum_i c_i prod_{j in S_i} v_j) * v_last                linearization/utils.rs:90-107 */
+    LF_COMB_FOLD = 2      /* v0 v1 + v2 v3 + v4 * sum_k sum_d mu_k^{d+1} f(f^2-1)..(f^2-(b-1)^2)  folding/utils.rs:273-325 */
+};
+typedef struct {
+    int32_t kind;
+    int32_t n_terms;            /* PRODUCTS / LIN                                                                 */
+    const uint64_t* coef_host;  /* n_terms ring elements (NTT form)                                               */
+    const int32_t* idx;         /* concatenated MLE indices                                                       */
+    const int32_t* idx_len;     /* per-term count                                                                 */
+    int32_t n_mu, b;            /* FOLD: 2K challenges mu (ring elements, slot-constant), small base b             */
+    const uint64_t* mu_host;
+} lf_comb;
+/* takes ownership of the MLE vectors (they are folded in place and freed by lf_sumcheck_free), like the reference's
+ * `Vec<DenseMultilinearExtension<R>>` argument.  All MLEs have num_vars variables; shorter vectors are zero-padded. */
+lf_status lf_sumcheck_begin(lf_ctx* ctx, lf_vec** mles, int32_t n_mles, int32_t num_vars, int32_t degree,
+                            const lf_comb* comb, lf_sumcheck** out);
+/* one prove_round: prev_challenge = TAU limbs of the verifier message (NULL in round 1);
+ * out_evals_host = (degree+1) ring elements                                                                      */
+lf_status lf_sumcheck_round(lf_sumcheck* sc, const uint64_t* prev_challenge_sf, uint64_t* out_evals_host);
+/* applies the last challenge and returns mle_k(r) for every MLE (what the caller would otherwise recompute with
+ * evaluate_mles at the sumcheck point)                                                                           */
+lf_status lf_sumcheck_finish(lf_sumcheck* sc, const uint64_t* last_challenge_sf, uint64_t* out_final_host);
+void lf_sumcheck_free(lf_sumcheck* sc);
+
+/* ---- a14: host transcript (the reference keeps Fiat-Shamir on the CPU; transcript/poseidon.rs:29-75)             */
+lf_status lf_transcript_create(int32_t ring_id, lf_transcript** out);
+lf_status lf_transcript_clone(const lf_transcript* t, lf_transcript** out);
+void lf_transcript_free(lf_transcript* t);
+void lf_transcript_absorb(lf_transcript* t, const uint64_t* ring_elems, size_t count);
+void lf_transcript_absorb_base(lf_transcript* t, const uint64_t* limbs, size_t count);
+void lf_transcript_absorb_tag(lf_transcript* t, const char* tag);
+void lf_transcript_get_challenge(lf_transcript* t, uint64_t* out_sf);               /* TAU limbs                  */
+void lf_transcript_get_short_challenge(lf_transcript* t, uint64_t* out_coeffs);     /* D coefficients             */
+uint64_t lf_transcript_permutations(const lf_transcript* t);
+
+/* ---- a13: rot_lin_combination (cyclotomic-rings/src/rotation.rs:45-104), host                                    */
+lf_status lf_rot_lin_combination(int32_t ring_id, const uint64_t* rho_coeff, const uint64_t* theta_ntt, int32_t count, uint64_t* out);
+
+/* ---- the prover step: NIFSProver::prove (nifs.rs:48-103) = linearization + 2 x decomposition + folding            */
+typedef struct { uint64_t nrows, ncols; const uint64_t* row_ptr; const uint64_t* col; const uint64_t* val; } lf_csr;
+/* flat, host-side description of one step.  Pointers may be NULL where noted.                                      */
+typedef struct {
+    int32_t ring; int32_t L, K; uint64_t B_lo, B_hi, b;       /* DecompositionParams  decomposition_parameters.rs:11-20 */
+    uint64_t kappa, n; const uint64_t* A;                     /* Ajtai matrix (host, NTT form) or NULL when a prepared lf_ajtai is passed */
+    uint64_t m, n_ccs, l, t, q, d, s;                         /* CCS shape            arith.rs:51-74                */
+    const lf_csr* M; const int32_t* S_flat; const int32_t* S_len; const uint64_t* c;
+    const uint64_t *acc_r, *acc_v, *acc_cm, *acc_u, *acc_x_w, *acc_h;   /* LCCCS accumulator  arith.rs:193-206      */
+    const uint64_t* w_acc_f;                                  /* accumulator witness f (NTT form, n elements)       */
+    const uint64_t *cm_i_cm, *cm_i_x_ccs;                     /* incoming CCCS        arith.rs:180-185              */
+    const uint64_t* w_i_f;                                    /* incoming witness f (NTT form, n elements)          */
+} lf_problem;
+
+typedef struct lf_prover lf_prover;   /* device-resident static state: Ajtai matrix + CCS matrices + workspaces     */
+/* uploads the static inputs (matrix, CCS).  The reference builds those outside the timed closure as well
+ * (benches/utils.rs:640-660).                                                                                      */
+lf_status lf_prover_create(lf_ctx* ctx, const lf_problem* shape, lf_prover** out);
+void lf_prover_free(lf_prover* p);
+uint64_t lf_proof_words(const lf_problem* shape);     /* u64 words of the serialised LFProof                        */
+uint64_t lf_lcccs_words(const lf_problem* shape);     /* u64 words of a serialised LCCCS: r, v, cm, u, x_w, h        */
+/* Witness::from_w_ccs on the device (arith.rs:230-248): returns f (NTT form) = CRT(gadget_decompose(ICRT(w_ccs)))   */
+lf_status lf_witness_f_from_w_ccs(lf_ctx* ctx, const uint64_t* w_ccs_host, size_t W, uint64_t B, int32_t L, uint64_t* f_host);
+/* LFLinearizationProver::prove (linearization.rs:145-189) on (cm_i, w_i): LCCCS + its proof part                    */
+lf_status lf_linearize(lf_prover* p, const lf_problem* in, lf_transcript* t, uint64_t* out_lcccs, uint64_t* out_lin_proof);
+/* one full step from HOST inputs: uploads w_acc_f / w_i_f, proves, downloads proof, folded LCCCS and (if out_f is
+ * not NULL) the folded witness f_0.  Proof layout: lin{msgs,v,u} | dec_acc{x,y,u,v per piece} | dec_new | fold{msgs,theta,eta} */
+lf_status lf_nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, uint64_t* out_f);
+/* the same step with both witnesses already resident in HBM (bench.py's `value`): witnesses are handles made by
+ * lf_prover_upload_witness; the folded witness stays on the device and is returned as a new handle                 */
+typedef struct lf_witness lf_witness;
+lf_status lf_prover_upload_witness(lf_prover* p, const uint64_t* f_host_ntt, lf_witness** out);
+void lf_witness_free(lf_prover* p, lf_witness* w);
+lf_status lf_witness_download_f(lf_prover* p, const lf_witness* w, uint64_t* f_host);
+lf_status lf_nifs_prove_resident(lf_prover* p, const lf_problem* in, const lf_witness* w_acc, const lf_witness* w_i,
+                                 lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, lf_witness** out_w);
+/* per-phase device/host timings of the last step in milliseconds: [0] linearization [1] decomposition x2 [2] folding
+ * [3] host transcript [4] total wall                                                                               */
+lf_status lf_prover_last_timings(const lf_prover* p, double* out5);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LF_B200_H */

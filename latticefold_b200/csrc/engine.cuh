@@ -1,0 +1,197 @@
+// Host-side engine: device memory, launches and the per-op drivers behind the C ABI (include/lf_b200.h).
+#pragma once
+#include "kernels.cuh"
+#include "transcript_host.hpp"
+#include "../../include/lf_b200.h"
+#include <vector>
+#include <string>
+#include <memory>
+#include <chrono>
+
+namespace lf {
+
+#define LF_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) throw LfException(LF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); } while (0)
+
+typedef std::vector<u64> HV;   // host vector of ring elements, D limbs each
+
+inline size_t pitch_of(size_t n) { return ((n ? n : 1) + 31) / 32 * 32; }   // planes start 256-byte aligned
+inline int ceil_log2(size_t x) { int l = 0; while (((size_t)1 << l) < x) ++l; return l; }
+
+}  // namespace lf
+
+struct lf_ctx {
+    int ring = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // ring tables on the device: [0] CRT, [1] ICRT
+    int* d_tab_idx[2] = {nullptr, nullptr}; lf::u64* d_tab_val[2] = {nullptr, nullptr};
+    void* tables = nullptr;        // RingTables<Rg>*
+    lf::u64* h_pinned = nullptr; size_t h_pinned_words = 0;       // D2H landing zone / H2D staging
+    lf::u64* d_small = nullptr; size_t d_small_words = 0;          // small device results / parameters
+    lf::u64* d_partial = nullptr; size_t d_partial_words = 0;      // block partial sums
+    int* d_err = nullptr;
+    bool profiling = false;
+    struct ProfRec { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+};
+struct lf_vec { lf::u64* p = nullptr; size_t n = 0, pitch = 0; int form = 0; };
+struct lf_ajtai { lf::u64* p = nullptr; size_t kappa = 0, n = 0, pitch = 0; };
+struct lf_sparse { lf::u32 *row_ptr = nullptr, *col = nullptr; lf::u64* val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0, val_pitch = 0, eff_rows = 0; };
+
+namespace lf {
+
+template <class Rg> struct Engine {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef HostRing<Rg> HR; typedef typename HR::El El;
+    static constexpr int D = Rg::D, S = Rg::S, TAU = Rg::TAU;
+    lf_ctx* c;
+    explicit Engine(lf_ctx* ctx) : c(ctx) {}
+    const RingTables<Rg>& tab() const { return *(const RingTables<Rg>*)c->tables; }
+    cudaStream_t st() const { return c->stream; }
+
+    // ---------------------------------------------------------------- memory
+    template <class T> T* dalloc(size_t count) { void* p = nullptr; LF_CUDA(cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), st())); return (T*)p; }
+    void dfree(void* p) { if (p) cudaFreeAsync(p, st()); }
+    lf_vec* vec_alloc(size_t n, int form) { lf_vec* v = new lf_vec; v->n = n; v->pitch = pitch_of(n); v->form = form; v->p = dalloc<u64>(v->pitch * D); return v; }
+    void vec_free(lf_vec* v) { if (v) { dfree(v->p); delete v; } }
+    u64* pinned(size_t words) {
+        if (c->h_pinned_words < words) { if (c->h_pinned) { LF_CUDA(cudaStreamSynchronize(st())); cudaFreeHost(c->h_pinned); } size_t w = std::max(words, (size_t)1 << 16); LF_CUDA(cudaMallocHost(&c->h_pinned, w * 8)); c->h_pinned_words = w; }
+        return c->h_pinned;
+    }
+    u64* small_dev(size_t words) {
+        if (c->d_small_words < words) { if (c->d_small) { LF_CUDA(cudaStreamSynchronize(st())); cudaFree(c->d_small); } size_t w = std::max(words, (size_t)1 << 16); LF_CUDA(cudaMalloc(&c->d_small, w * 8)); c->d_small_words = w; }
+        return c->d_small;
+    }
+    u64* partial_dev(size_t words) {
+        if (c->d_partial_words < words) { if (c->d_partial) { LF_CUDA(cudaStreamSynchronize(st())); cudaFree(c->d_partial); } size_t w = std::max(words, (size_t)1 << 20); LF_CUDA(cudaMalloc(&c->d_partial, w * 8)); c->d_partial_words = w; }
+        return c->d_partial;
+    }
+    void sync() { LF_CUDA(cudaStreamSynchronize(st())); }
+    // every kernel launch goes through here: counts launches (bench.py's gpu_launches) and, in profiling mode, brackets
+    // the launch with CUDA events on the context's stream so bench.py can attribute device time per kernel.
+    template <class Fn> void launch(const char* name, Fn&& fn) {
+        if (c->profiling) {
+            cudaEvent_t a, b; LF_CUDA(cudaEventCreate(&a)); LF_CUDA(cudaEventCreate(&b));
+            LF_CUDA(cudaEventRecord(a, st())); fn(); LF_CUDA(cudaEventRecord(b, st()));
+            c->prof.push_back({name, a, b});
+        } else fn();
+        ++c->launches; LF_CUDA(cudaGetLastError());
+    }
+    void check_err_flag(int code, const char* msg) {
+        int h = 0; LF_CUDA(cudaMemcpyAsync(&h, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st())); sync();
+        if (h) { LF_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), st())); throw LfException(code, msg); }
+    }
+    // host elements -> small SoA device vector (synchronous staging through pageable memory is fine: a few elements)
+    void upload_small(const u64* host, size_t n, u64* dev, size_t pitch) {
+        std::vector<u64> soa(pitch * D, 0);
+        for (size_t i = 0; i < n; ++i) for (int l = 0; l < D; ++l) soa[(size_t)l * pitch + i] = host[i * D + l];
+        LF_CUDA(cudaMemcpyAsync(dev, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice, st())); sync();
+    }
+    // download `words` u64 from the device into a host vector (through the pinned landing zone)
+    void download_words(const u64* dev, size_t words, u64* host) {
+        u64* pz = pinned(words);
+        LF_CUDA(cudaMemcpyAsync(pz, dev, words * 8, cudaMemcpyDeviceToHost, st())); sync();
+        std::memcpy(host, pz, words * 8);
+    }
+
+    // ---------------------------------------------------------------- layout
+    void upload_planes(const u64* host, size_t n, u64* dev, size_t pitch) {   // host AoS -> device planes
+        if (!n) return;
+        u64* stage = dalloc<u64>(n * D);
+        LF_CUDA(cudaMemcpyAsync(stage, host, n * D * 8, cudaMemcpyHostToDevice, st()));
+        launch("k_aos_to_soa", [&] { k_aos_to_soa<D><<<(unsigned)((n + 63) / 64), 256, 0, st()>>>(stage, dev, n, pitch); });
+        dfree(stage);
+    }
+    void download_planes(const u64* dev, size_t pitch, size_t n, u64* host) {
+        if (!n) return;
+        u64* stage = dalloc<u64>(n * D);
+        launch("k_soa_to_aos", [&] { k_soa_to_aos<D><<<(unsigned)((n + 63) / 64), 256, 0, st()>>>(dev, stage, n, pitch); });
+        LF_CUDA(cudaMemcpyAsync(host, stage, n * D * 8, cudaMemcpyDeviceToHost, st())); sync();
+        dfree(stage);
+    }
+
+    // ---------------------------------------------------------------- elementwise ops
+    void crt(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, bool inverse) {
+        if (!n) return;
+        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, u64><<<(unsigned)((n + 127) / 128), 128, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[inverse], c->d_tab_val[inverse]); });
+    }
+    void crt_digits(const int8_t* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n) {
+        if (!n) return;
+        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, int8_t><<<(unsigned)((n + 127) / 128), 128, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[0], c->d_tab_val[0]); });
+    }
+    static unsigned blocks_for(size_t work, int bs = 256) { return (unsigned)((work + bs - 1) / bs); }
+    void gadget_decompose(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, u64 B, int L) {
+        if (B < 2 || B >= ((u64)1 << 62) || L < 1 || L > 64) throw LfException(LF_ERR_UNSUPPORTED, "gadget_decompose: need 2 <= B < 2^62, 1 <= L <= 64");
+        if (!n) return;
+        launch("k_gadget_decompose", [&] { k_gadget_decompose<Rg><<<blocks_for(n * D), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n, (int64_t)B, L, c->d_err); });
+    }
+    void gadget_recompose(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n_out, u64 B, int L) {
+        if (!n_out) return;
+        launch("k_gadget_recompose", [&] { k_gadget_recompose<Rg><<<blocks_for(n_out * D), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n_out, B % F::P, L); });
+    }
+    void digit_split(const u64* in, size_t in_pitch, int8_t* out, size_t out_pitch, size_t n, u64 b, int K) {
+        if (b < 2 || b > 254 || K < 1 || K > 64) throw LfException(LF_ERR_UNSUPPORTED, "decompose_to_vec: need 2 <= b <= 254 (int8 digits), 1 <= K <= 64");
+        if (!n) return;
+        launch("k_digit_split", [&] { k_digit_split<Rg><<<blocks_for(n * D), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n, (int64_t)b, K, c->d_err); });
+    }
+
+    // ---------------------------------------------------------------- batched dot products (commit, MLE evaluation)
+    // result: nrows x ncols x D limbs on the device (d_out)
+    void dot(const u64* X, size_t x_row_stride, size_t x_pitch, int nrows, const size_t* x_len_dev,
+             const PtrList& Y, size_t y_pitch, int ncols, size_t n, u64* d_out) {
+        if (nrows == 0 || ncols == 0) return;
+        if (ncols > MAX_LIST) throw LfException(LF_ERR_INVALID_ARG, "dot: too many columns in one launch");
+        DotArgs a; a.X = X; a.x_row_stride = x_row_stride; a.x_pitch = x_pitch; a.nrows = nrows; a.Y = Y; a.y_pitch = y_pitch; a.ncols = ncols;
+        a.x_len = x_len_dev; a.n = n; a.x_per_block = 128 * 8;
+        const unsigned xt = (unsigned)std::max<size_t>(1, (n + a.x_per_block - 1) / a.x_per_block);
+        const size_t nout = (size_t)nrows * ncols * D;
+        a.partial = partial_dev((size_t)xt * nout);
+        launch("k_dot", [&] {
+            if (ncols >= 3) { constexpr int RT = 1, CT = 4; dim3 g((unsigned)(((nrows + RT - 1) / RT) * ((ncols + CT - 1) / CT)), xt, S); k_dot<Rg, RT, CT><<<g, 128, 0, st()>>>(a); }
+            else if (ncols == 2) { constexpr int RT = 2, CT = 2; dim3 g((unsigned)(((nrows + RT - 1) / RT) * ((ncols + CT - 1) / CT)), xt, S); k_dot<Rg, RT, CT><<<g, 128, 0, st()>>>(a); }
+            else { constexpr int RT = 4, CT = 1; dim3 g((unsigned)((nrows + RT - 1) / RT), xt, S); k_dot<Rg, RT, CT><<<g, 128, 0, st()>>>(a); }
+        });
+        launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(a.partial, (int)xt, (int)nout, d_out); });
+    }
+    // f-hat evaluation from coefficient planes; result nvec x TAU x D limbs on the device
+    template <class TIn> void coeff_eval(const TIn* coeff, size_t c_pitch, size_t c_vec_stride, int nvec, const u64* eq, size_t eq_pitch, size_t n, u64* d_out) {
+        if (!nvec) return;
+        const int xpb = 128 * 8; const unsigned xt = (unsigned)std::max<size_t>(1, (n + xpb - 1) / xpb);
+        const size_t nout = (size_t)nvec * TAU * D;
+        u64* partial = partial_dev((size_t)xt * nout);
+        launch("k_coeff_eval", [&] { k_coeff_eval<Rg, TIn><<<dim3(xt, S, nvec), 128, 0, st()>>>(coeff, c_pitch, c_vec_stride, eq, eq_pitch, n, xpb, nvec, partial); });
+        launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(partial, (int)xt, (int)nout, d_out); });
+    }
+    void spmv(const lf_sparse* M, const u64* head, size_t head_len, size_t head_pitch, const u64* tail, size_t tail_pitch, u64* out, size_t out_pitch, size_t nrows) {
+        if (!nrows) return;
+        launch("k_spmv", [&] { k_spmv<Rg><<<dim3(blocks_for(nrows, 128), S), 128, 0, st()>>>(M->row_ptr, M->col, M->val, M->val_pitch, head, head_len, head_pitch, tail, tail_pitch, out, out_pitch, nrows); });
+    }
+    // eq(., r) for r given as s ring elements on the host
+    void eq_table(const u64* r_host, int s, u64* out, size_t out_pitch) {
+        if (s < 1 || s > 40) throw LfException(LF_ERR_INVALID_ARG, "eq_table: r length is 0 or too large");
+        std::vector<u64> pair((size_t)s * 2 * D);
+        El one = HR::from_u64(1);
+        for (int i = 0; i < s; ++i) { El r = HR::load(r_host + (size_t)i * D), m = HR::sub(one, r); std::memcpy(&pair[((size_t)i * 2) * D], m.data(), 8 * D); std::memcpy(&pair[((size_t)i * 2 + 1) * D], r.data(), 8 * D); }
+        u64* d_pair = dalloc<u64>(pair.size());
+        LF_CUDA(cudaMemcpyAsync(d_pair, pair.data(), pair.size() * 8, cudaMemcpyHostToDevice, st())); sync();
+        const size_t n = (size_t)1 << s;
+        launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(n, 128), S), 128, (size_t)s * 2 * TAU * 8, st()>>>(d_pair, s, out, out_pitch, n); });
+        dfree(d_pair);
+    }
+    // out (+)= sum_i coef_i (.) vecs_i ; coef on the host (count x D)
+    void lincomb(const PtrList& vecs, size_t v_pitch, int count, const u64* coef_host, u64* out, size_t out_pitch, size_t n, bool accumulate) {
+        int done = 0;
+        while (done < count || (count == 0 && !accumulate && done == 0)) {
+            const int chunk = std::min(MAX_LIST, count - done);
+            PtrList pl; for (int i = 0; i < chunk; ++i) { pl.p[i] = vecs.p[done + i]; pl.len[i] = vecs.len[done + i]; }
+            u64* d_coef = dalloc<u64>((size_t)std::max(chunk, 1) * D);
+            if (chunk) LF_CUDA(cudaMemcpyAsync(d_coef, coef_host + (size_t)done * D, (size_t)chunk * D * 8, cudaMemcpyHostToDevice, st()));
+            sync();
+            launch("k_lincomb", [&] { k_lincomb<Rg><<<dim3(blocks_for(n, 128), S), 128, 0, st()>>>(pl, v_pitch, chunk, d_coef, out, out_pitch, n, (accumulate || done > 0) ? 1 : 0); });
+            dfree(d_coef);
+            done += chunk; if (count == 0) break;
+        }
+    }
+};
+
+}  // namespace lf

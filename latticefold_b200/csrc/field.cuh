@@ -1,0 +1,135 @@
+// Base-field and slot-field arithmetic for the LatticeFold rings, usable from host and device code.
+//
+// Goldilocks  p = 2^64 - 2^32 + 1, ring Z_p[X]/(X^24 - X^12 + 1) = 8 slots of Fq3 = Fq[Y]/(Y^3 - nu), nu = 2^40
+//   (reference type aliases: crates/cyclotomic-rings/src/rings/goldilocks.rs:9-20; the arithmetic itself is the
+//    un-vendored stark-rings crate -- see DESIGN.md "Conventions" for what is and is not pinned).
+// Elements are canonical (value in [0, p)), never Montgomery: 2^64 = 2^32 - 1 (mod p) makes the reduction of a
+// 128-bit product a handful of 32/64-bit adds, cheaper on the GPU's 32-bit integer pipes than a Montgomery REDC.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define LF_HD __host__ __device__ __forceinline__
+#define LF_D __device__ __forceinline__
+#else
+#define LF_HD inline
+#define LF_D inline
+#endif
+
+namespace lf {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+typedef unsigned __int128 u128;
+
+// 64 x 64 -> 128
+LF_HD void mul_wide(u64 a, u64 b, u64& lo, u64& hi) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b; hi = __umul64hi(a, b);
+#else
+    u128 x = (u128)a * b; lo = (u64)x; hi = (u64)(x >> 64);
+#endif
+}
+
+// 192-bit accumulator for lazily reduced sums of 128-bit products (up to 2^64 terms)
+struct Acc192 {
+    u64 w0, w1, w2;
+    LF_HD void clear() { w0 = w1 = w2 = 0; }
+    LF_HD void mac(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+        asm("mad.lo.cc.u64 %0, %3, %4, %0;\n\t"
+            "madc.hi.cc.u64 %1, %3, %4, %1;\n\t"
+            "addc.u64 %2, %2, 0;"
+            : "+l"(w0), "+l"(w1), "+l"(w2) : "l"(a), "l"(b));
+#else
+        u128 x = (u128)a * b; u128 s = (u128)w0 + (u64)x; w0 = (u64)s;
+        s = (u128)w1 + (u64)(x >> 64) + (u64)(s >> 64); w1 = (u64)s; w2 += (u64)(s >> 64);
+#endif
+    }
+    LF_HD void add(u64 a) {   // += a (64-bit)
+#if defined(__CUDA_ARCH__)
+        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, 0;\n\taddc.u64 %2, %2, 0;" : "+l"(w0), "+l"(w1), "+l"(w2) : "l"(a));
+#else
+        u128 s = (u128)w0 + a; w0 = (u64)s; s = (u128)w1 + (u64)(s >> 64); w1 = (u64)s; w2 += (u64)(s >> 64);
+#endif
+    }
+};
+
+struct Goldilocks {
+    static constexpr u64 P = 0xFFFFFFFF00000001ULL;
+    static constexpr u64 EPS = 0xFFFFFFFFULL;  // 2^64 mod p
+    static constexpr int NU_SHIFT = 40;        // nu = 2^40 (a primitive 24th root of unity)
+
+    static LF_HD u64 add(u64 a, u64 b) { u64 s = a + b; if (s < a || s >= P) s -= P; return s; }
+    static LF_HD u64 sub(u64 a, u64 b) { u64 d = a - b; if (a < b) d += P; return d; }
+    static LF_HD u64 neg(u64 a) { return a ? P - a : 0; }
+    // (hi:lo) mod p, canonical.  2^64 = EPS, 2^96 = -1.
+    static LF_HD u64 reduce128(u64 lo, u64 hi) {
+        u64 hh = hi >> 32, hl = hi & EPS;
+        u64 t0 = lo - hh; if (lo < hh) t0 -= EPS;      // wrapped by 2^64 = EPS too much
+        u64 t1 = (hl << 32) - hl;                      // hl * EPS < 2^64
+        u64 r = t0 + t1; if (r < t1) r += EPS;         // wrapped: add 2^64 mod p
+        if (r >= P) r -= P;
+        return r;
+    }
+    static LF_HD u64 mul(u64 a, u64 b) { u64 lo, hi; mul_wide(a, b, lo, hi); return reduce128(lo, hi); }
+    static LF_HD u64 sqr(u64 a) { return mul(a, a); }
+    // (w2:w1:w0) mod p; 2^128 = -2^32
+    static LF_HD u64 reduce192(const Acc192& a) {
+        u64 r = reduce128(a.w0, a.w1);
+        u64 t = reduce128(a.w2 << 32, a.w2 >> 32);
+        return sub(r, t);
+    }
+    static LF_HD u64 mul_nu(u64 a) { return reduce128(a << NU_SHIFT, a >> (64 - NU_SHIFT)); }
+    static LF_HD u64 from_i64(int64_t v) { return v >= 0 ? (u64)v : P - (u64)(-v); }   // |v| < p
+    static LF_HD int64_t to_signed(u64 a) { return a <= (P - 1) / 2 ? (int64_t)a : -(int64_t)(P - a); }
+    static inline u64 pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = mul(r, a); a = mul(a, a); e >>= 1; } return r; }
+    static inline u64 inv(u64 a) { return pow(a, P - 2); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ring descriptor: slot field Fq[Y]/(Y^TAU - nu).  Rg::F is the base field.
+struct GoldilocksRing {
+    typedef Goldilocks F;
+    static constexpr int ID = 0, D = 24, S = 8, TAU = 3, G = 24;
+    static constexpr bool TRINOMIAL = true;   // X^24 = X^12 - 1
+    static constexpr int CS_BYTES = 18;
+};
+
+// c = a * b in the slot field (fully reduced operands and result).  TAU = 3 specialisation keeps everything in
+// registers; products of one output limb are summed in a 192-bit accumulator and reduced once.
+template <class Rg> struct SlotField;
+
+template <> struct SlotField<GoldilocksRing> {
+    typedef Goldilocks F;
+    static constexpr int TAU = 3;
+    static LF_HD void mul(u64* c, const u64* a, const u64* b) {
+        u64 b1n = F::mul_nu(b[1]), b2n = F::mul_nu(b[2]);
+        Acc192 x; u64 c0, c1, c2;
+        x.clear(); x.mac(a[0], b[0]); x.mac(a[1], b2n);  x.mac(a[2], b1n);  c0 = F::reduce192(x);
+        x.clear(); x.mac(a[0], b[1]); x.mac(a[1], b[0]); x.mac(a[2], b2n);  c1 = F::reduce192(x);
+        x.clear(); x.mac(a[0], b[2]); x.mac(a[1], b[1]); x.mac(a[2], b[0]); c2 = F::reduce192(x);
+        c[0] = c0; c[1] = c1; c[2] = c2;
+    }
+    static LF_HD void sqr(u64* c, const u64* a) {
+        u64 a1n = F::mul_nu(a[1]), a2n = F::mul_nu(a[2]);
+        u64 d1 = F::add(a[1], a[1]), d2 = F::add(a[2], a[2]);
+        Acc192 x; u64 c0, c1, c2;
+        x.clear(); x.mac(a[0], a[0]); x.mac(d1, a2n);                      c0 = F::reduce192(x);
+        x.clear(); x.mac(a[0], d1);   x.mac(a[2], a2n);                    c1 = F::reduce192(x);
+        x.clear(); x.mac(a[0], d2);   x.mac(a[1], a[1]);                   c2 = F::reduce192(x);
+        c[0] = c0; c[1] = c1; c[2] = c2;
+    }
+    // lazy multiply-accumulate: acc[l] += (a*b)[l] with bn = (b0, nu*b1, nu*b2 precomputed by prep())
+    struct Prepped { u64 b0, b1, b2, b1n, b2n; };
+    static LF_HD Prepped prep(const u64* b) { Prepped p; p.b0 = b[0]; p.b1 = b[1]; p.b2 = b[2]; p.b1n = F::mul_nu(b[1]); p.b2n = F::mul_nu(b[2]); return p; }
+    static LF_HD void mac(Acc192* acc, const u64* a, const Prepped& p) {
+        acc[0].mac(a[0], p.b0); acc[0].mac(a[1], p.b2n); acc[0].mac(a[2], p.b1n);
+        acc[1].mac(a[0], p.b1); acc[1].mac(a[1], p.b0);  acc[1].mac(a[2], p.b2n);
+        acc[2].mac(a[0], p.b2); acc[2].mac(a[1], p.b1);  acc[2].mac(a[2], p.b0);
+    }
+    static LF_HD void add(u64* c, const u64* a, const u64* b) { for (int i = 0; i < 3; ++i) c[i] = F::add(a[i], b[i]); }
+    static LF_HD void sub(u64* c, const u64* a, const u64* b) { for (int i = 0; i < 3; ++i) c[i] = F::sub(a[i], b[i]); }
+};
+
+}  // namespace lf

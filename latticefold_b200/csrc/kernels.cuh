@@ -1,0 +1,635 @@
+// sm_100a kernels of the LatticeFold prover hot path.  All of them are integer modular arithmetic over limb planes:
+// a device vector of n ring elements is D planes of n u64 (plane = limb index, pitch-aligned), so that a warp reading
+// one limb of 32 consecutive elements issues one fully coalesced request and a thread that owns (element, slot) has a
+// whole slot-field element in registers.  Tensor cores are not used (nothing here is a dense FP contraction).
+// Each kernel cites the reference loop it replaces; byte counts per unit are in DESIGN.md.
+#pragma once
+#include "field.cuh"
+#include "ring_host.hpp"
+#include <cuda_runtime.h>
+
+namespace lf {
+
+constexpr int MAX_LIST = 32;          // pointer-list capacity of one launch (pieces, MLEs, ...)
+constexpr int MAX_MU = 128;           // 2K * tau
+constexpr int SC_MAX_MLES = 8, SC_MAX_TERMS = 4, SC_MAX_FACTORS = 4, SC_MAX_DEG = 7;
+
+struct PtrList { const u64* p[MAX_LIST]; size_t len[MAX_LIST]; };
+struct PtrList8 { const int8_t* p[MAX_LIST]; };
+
+// ------------------------------------------------------------------------------------------------ reductions
+// sum over the block of NV field elements per thread; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
+template <class F, int NV> __device__ __forceinline__ void block_reduce_add(u64* v, u64* smem /* NV * 32 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        u64 x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x = F::add(x, __shfl_down_sync(0xffffffffu, x, o));
+        v[i] = x;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) smem[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            u64 x = lane < nw ? smem[i * 32 + lane] : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x = F::add(x, __shfl_down_sync(0xffffffffu, x, o));
+            v[i] = x;
+        }
+    }
+    __syncthreads();
+}
+
+// out[j] = sum_b partial[b * nout + j]
+template <class F> __global__ void k_reduce_partials(const u64* __restrict__ partial, int nblk, int nout, u64* __restrict__ out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nout) return;
+    u64 acc = 0;
+    for (int b = 0; b < nblk; ++b) acc = F::add(acc, partial[(size_t)b * nout + j]);
+    out[j] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ layout changes
+// host "Vec<R>" image (element-major) <-> limb planes.  64 elements per block through shared memory so both sides coalesce.
+template <int D> __global__ void k_aos_to_soa(const u64* __restrict__ aos, u64* __restrict__ soa, size_t n, size_t pitch) {
+    __shared__ u64 tile[64][D + 1];
+    size_t base = (size_t)blockIdx.x * 64; int cnt = (int)min((size_t)64, n - base);
+    for (int i = threadIdx.x; i < cnt * D; i += blockDim.x) tile[i / D][i % D] = aos[base * D + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * D; i += blockDim.x) { int l = i / 64, e = i % 64; if (e < cnt) soa[(size_t)l * pitch + base + e] = tile[e][l]; }
+}
+template <int D> __global__ void k_soa_to_aos(const u64* __restrict__ soa, u64* __restrict__ aos, size_t n, size_t pitch) {
+    __shared__ u64 tile[64][D + 1];
+    size_t base = (size_t)blockIdx.x * 64; int cnt = (int)min((size_t)64, n - base);
+    for (int i = threadIdx.x; i < 64 * D; i += blockDim.x) { int l = i / 64, e = i % 64; if (e < cnt) tile[e][l] = soa[(size_t)l * pitch + base + e]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * D; i += blockDim.x) aos[base * D + i] = tile[i / D][i % D];
+}
+
+// ------------------------------------------------------------------------------------------------ K2/K3 CRT / ICRT
+// CRT::elementwise_crt / ICRT::elementwise_icrt (reference call sites arith.rs:232,238,300,327).  One thread per element;
+// the D input limbs are staged in shared memory ([limb][thread], conflict free) because the sparse table indexes them
+// dynamically.  tab_idx/tab_val: D rows x NNZ entries.  TIn = u64 (field elements) or int8_t (balanced digits).
+template <class Rg, class TIn> __global__ void __launch_bounds__(128)
+k_matrix_apply(const TIn* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t n,
+               const int* __restrict__ tab_idx, const u64* __restrict__ tab_val) {
+    typedef typename Rg::F F; constexpr int D = Rg::D, NNZ = Rg::S;
+    __shared__ u64 s_in[D][128];
+    __shared__ int s_idx[D * NNZ]; __shared__ u64 s_val[D * NNZ];
+    for (int i = threadIdx.x; i < D * NNZ; i += blockDim.x) { s_idx[i] = tab_idx[i]; s_val[i] = tab_val[i]; }
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) {
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+            if (sizeof(TIn) == 1) s_in[l][threadIdx.x] = F::from_i64((int64_t)(int8_t)in[(size_t)l * in_pitch + e]);
+            else s_in[l][threadIdx.x] = (u64)in[(size_t)l * in_pitch + e];
+        }
+    }
+    __syncthreads();
+    if (e >= n) return;
+#pragma unroll 4
+    for (int r = 0; r < D; ++r) {
+        Acc192 a; a.clear();
+#pragma unroll
+        for (int c = 0; c < NNZ; ++c) a.mac(s_val[r * NNZ + c], s_in[s_idx[r * NNZ + c]][threadIdx.x]);
+        out[(size_t)r * out_pitch + e] = F::reduce192(a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4/K5 digits
+// gadget_decompose(B, L) (arith.rs:235): coefficient c of element i -> digits l = 0..L-1 at element i*L + l.
+template <class Rg> __global__ void k_gadget_decompose(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch,
+                                                       size_t n, int64_t B, int L, int* __restrict__ err) {
+    typedef typename Rg::F F;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * Rg::D) return;
+    size_t i = t % n; int c = (int)(t / n);
+    int64_t dg[64];
+    if (!balanced_digits(F::to_signed(in[(size_t)c * in_pitch + i]), B, L, dg)) atomicExch(err, 1);
+    for (int l = 0; l < L; ++l) out[(size_t)c * out_pitch + i * L + l] = F::from_i64(dg[l]);
+}
+// decompose_to_vec(b, K).transpose() (decomposition/utils.rs:45-49) into K int8 digit planes sets: out[k][c][i]
+template <class Rg> __global__ void k_digit_split(const u64* __restrict__ in, size_t in_pitch, int8_t* __restrict__ out, size_t out_pitch,
+                                                  size_t n, int64_t b, int K, int* __restrict__ err) {
+    typedef typename Rg::F F;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * Rg::D) return;
+    size_t i = t % n; int c = (int)(t / n);
+    int64_t dg[64];
+    if (!balanced_digits(F::to_signed(in[(size_t)c * in_pitch + i]), b, K, dg)) atomicExch(err, 1);
+    for (int k = 0; k < K; ++k) out[((size_t)k * Rg::D + c) * out_pitch + i] = (int8_t)dg[k];
+}
+template <class Rg> __global__ void k_digits_to_field(const int8_t* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t n) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * Rg::D) return;
+    size_t i = t % n; int c = (int)(t / n);
+    out[(size_t)c * out_pitch + i] = Rg::F::from_i64((int64_t)in[(size_t)c * in_pitch + i]);
+}
+// gadget_recompose(B, L): out[i] = sum_l in[i*L + l] * B^l, limb-wise (B is an integer scalar; arith.rs:305,330)
+template <class Rg> __global__ void k_gadget_recompose(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch,
+                                                       size_t n_out, u64 Bmod, int L) {
+    typedef typename Rg::F F;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_out * Rg::D) return;
+    size_t i = t % n_out; int c = (int)(t / n_out);
+    u64 acc = 0, pw = 1;
+    for (int l = 0; l < L; ++l) { acc = F::add(acc, F::mul(in[(size_t)c * in_pitch + i * L + l], pw)); pw = F::mul(pw, Bmod); }
+    out[(size_t)c * out_pitch + i] = acc;
+}
+// get_fhat (arith.rs:273-297): MLE j, slot k, limb 0 = coefficient j*S + k; other limbs 0.  `in` points at plane j*S.
+template <class Rg> __global__ void k_fhat(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t n) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * Rg::S) return;
+    size_t i = t % n; int k = (int)(t / n);
+    out[(size_t)(k * Rg::TAU) * out_pitch + i] = in[(size_t)k * in_pitch + i];
+    for (int l = 1; l < Rg::TAU; ++l) out[(size_t)(k * Rg::TAU + l) * out_pitch + i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 / K10 batched dot products
+// out[r][c] = sum_x X_r[x] (.) Y_c[x]   (slot-wise product), the shape of both
+//   AjtaiCommitmentScheme::commit  (rows X_r = matrix rows, Y_c = the K-1 witness pieces; commitment_scheme.rs:45-51), and
+//   evaluate_mles                  (rows X_r = MLE tables, Y_0 = eq(., r) table; mle_helpers.rs:65-88).
+// grid = (row tiles * col tiles  [fastest: concurrent blocks share the same x tile in L2], x tiles, slots).
+// A thread owns one x per iteration, RT x CT slot-field accumulators kept as lazily reduced 192-bit sums.
+struct DotArgs {
+    const u64* X; size_t x_row_stride, x_pitch; int nrows;    // rows: X + r * x_row_stride
+    PtrList Y; size_t y_pitch; int ncols;                     // columns: separate vectors, len[] = effective length
+    const size_t* x_len;                                      // optional per-row effective length (device), else n
+    size_t n; int x_per_block;
+    u64* partial;                                             // [x tile][row][col][D]
+};
+template <class Rg, int RT, int CT> __global__ void __launch_bounds__(128)
+k_dot(const DotArgs a) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+    __shared__ u64 red[RT * CT * TAU * 32];
+    const int col_tiles = (a.ncols + CT - 1) / CT;
+    const int rt = blockIdx.x / col_tiles, ct = blockIdx.x % col_tiles, slot = blockIdx.z;
+    const int r0 = rt * RT, c0 = ct * CT;
+    Acc192 acc[RT][CT][TAU];
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < CT; ++j)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) acc[i][j][l].clear();
+    const size_t x_begin = (size_t)blockIdx.y * a.x_per_block, x_end = min(a.n, x_begin + a.x_per_block);
+    size_t rlen[RT];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) rlen[i] = (r0 + i < a.nrows) ? (a.x_len ? a.x_len[r0 + i] : a.n) : 0;
+    for (size_t x = x_begin + threadIdx.x; x < x_end; x += blockDim.x) {
+        typename SF::Prepped xp[RT]; bool xv[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            xv[i] = x < rlen[i];
+            u64 v[TAU];
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) v[l] = xv[i] ? a.X[(size_t)(r0 + i) * a.x_row_stride + (size_t)(slot * TAU + l) * a.x_pitch + x] : 0;
+            xp[i] = SF::prep(v);
+        }
+#pragma unroll
+        for (int j = 0; j < CT; ++j) {
+            if (c0 + j >= a.ncols || x >= a.Y.len[c0 + j]) continue;
+            u64 y[TAU];
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) y[l] = a.Y.p[c0 + j][(size_t)(slot * TAU + l) * a.y_pitch + x];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) if (xv[i]) SF::mac(acc[i][j], y, xp[i]);
+        }
+    }
+    u64 v[RT * CT * TAU];
+#pragma unroll
+    for (int i = 0; i < RT; ++i)
+#pragma unroll
+        for (int j = 0; j < CT; ++j)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) v[(i * CT + j) * TAU + l] = F::reduce192(acc[i][j][l]);
+    block_reduce_add<F, RT * CT * TAU>(v, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < RT; ++i)
+#pragma unroll
+            for (int j = 0; j < CT; ++j) {
+                if (r0 + i >= a.nrows || c0 + j >= a.ncols) continue;
+                u64* o = a.partial + (((size_t)blockIdx.y * a.nrows + (r0 + i)) * a.ncols + (c0 + j)) * Rg::D + slot * TAU;
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) o[l] = v[(i * CT + j) * TAU + l];
+            }
+    }
+}
+
+// evaluate f-hat MLEs straight from coefficient planes: out[v][j][slot][l] = sum_x eq[x][slot][l] * coeff_v[x][j*S + slot]
+// (compute_v_s, decomposition.rs:204-211; linearization.rs:126-131).  TIn = int8_t (digit pieces) or u64 (field coefficients).
+// grid = (x tiles, slots, vectors); partial: [x tile][vector][tau_j][D]
+template <class Rg, class TIn> __global__ void __launch_bounds__(128)
+k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride, const u64* __restrict__ eq, size_t eq_pitch,
+             size_t n, int x_per_block, int nvec, u64* __restrict__ partial) {
+    typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
+    __shared__ u64 red[TAU * TAU * 32];
+    const int slot = blockIdx.y, vec = blockIdx.z;
+    const TIn* cv = coeff + (size_t)vec * c_vec_stride;
+    Acc192 acc[TAU][TAU];
+#pragma unroll
+    for (int j = 0; j < TAU; ++j)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) acc[j][l].clear();
+    const size_t x_begin = (size_t)blockIdx.x * x_per_block, x_end = min(n, x_begin + x_per_block);
+    for (size_t x = x_begin + threadIdx.x; x < x_end; x += blockDim.x) {
+        u64 e[TAU];
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) e[l] = eq[(size_t)(slot * TAU + l) * eq_pitch + x];
+#pragma unroll
+        for (int j = 0; j < TAU; ++j) {
+            u64 c;
+            if (sizeof(TIn) == 1) c = F::from_i64((int64_t)(int8_t)cv[(size_t)(j * S + slot) * c_pitch + x]);
+            else c = (u64)cv[(size_t)(j * S + slot) * c_pitch + x];
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) acc[j][l].mac(c, e[l]);
+        }
+    }
+    u64 v[TAU * TAU];
+#pragma unroll
+    for (int j = 0; j < TAU; ++j)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) v[j * TAU + l] = F::reduce192(acc[j][l]);
+    block_reduce_add<F, TAU * TAU>(v, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < TAU; ++j)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) partial[(((size_t)blockIdx.x * nvec + vec) * TAU + j) * Rg::D + slot * TAU + l] = v[j * TAU + l];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K7 sparse mat-vec
+// mat_vec_mul (arith/utils.rs:52-65): out[row] = sum (val, col) val (.) z[col].  thread = (row, slot).  z may be the
+// concatenation z = head || tail (x_s[k] || w_ccs_k, decomposition.rs:238-246) without materialising it.
+template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, const u32* __restrict__ col, const u64* __restrict__ val, size_t val_pitch,
+                                           const u64* __restrict__ z_head, size_t head_len, size_t head_pitch,
+                                           const u64* __restrict__ z_tail, size_t tail_pitch,
+                                           u64* __restrict__ out, size_t out_pitch, size_t nrows) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
+    if (row >= nrows) return;
+    Acc192 acc[TAU];
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) acc[l].clear();
+    for (u32 e = row_ptr[row]; e < row_ptr[row + 1]; ++e) {
+        u64 v[TAU], z[TAU]; const size_t c = col[e];
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) {
+            v[l] = val[(size_t)(slot * TAU + l) * val_pitch + e];
+            z[l] = c < head_len ? z_head[(size_t)(slot * TAU + l) * head_pitch + c] : z_tail[(size_t)(slot * TAU + l) * tail_pitch + (c - head_len)];
+        }
+        SF::mac(acc, v, SF::prep(z));
+    }
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + row] = F::reduce192(acc[l]);
+}
+
+// ------------------------------------------------------------------------------------------------ K8 eq table
+// build_eq_x_r (sumcheck/utils.rs:100-170): eq[x] = prod_i (x_i r_i + (1 - x_i)(1 - r_i)), r[0] on bit 0.
+// r_pair: s x 2 x D limbs on the device = (1 - r_i, r_i) per variable.  thread = (x, slot).
+// The table is built as lo(x mod 2^h) * hi(x div 2^h) from two half tables held in shared memory would save multiplies;
+// at s <= 24 the direct product is s-1 slot-field multiplies per entry and is not on the critical path.
+template <class Rg> __global__ void k_eq_table(const u64* __restrict__ r_pair, int s, u64* __restrict__ out, size_t out_pitch, size_t n) {
+    typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU, D = Rg::D;
+    extern __shared__ u64 s_r[];   // s * 2 * TAU for this slot
+    const int slot = blockIdx.y;
+    for (int i = threadIdx.x; i < s * 2 * TAU; i += blockDim.x) { int v = i / (2 * TAU), w = (i / TAU) & 1, l = i % TAU; s_r[i] = r_pair[((size_t)v * 2 + w) * D + slot * TAU + l]; }
+    __syncthreads();
+    size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    u64 acc[TAU];
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) acc[l] = s_r[((x & 1) ? TAU : 0) + l];
+    for (int v = 1; v < s; ++v) SF::mul(acc, acc, &s_r[(v * 2 + ((x >> v) & 1)) * TAU]);
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = acc[l];
+}
+
+// ------------------------------------------------------------------------------------------------ K11 linear combinations
+// out[x] (+)= sum_i c_i (.) v_i[x]   (compute_f_0 folding.rs:258-268; zeta-Horner combination of Mz MLEs folding.rs:208-226)
+// coef: count x D limbs on the device.  thread = (x, slot).
+template <class Rg> __global__ void k_lincomb(const PtrList vecs, size_t v_pitch, int count, const u64* __restrict__ coef,
+                                              u64* __restrict__ out, size_t out_pitch, size_t n, int accumulate) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU, D = Rg::D;
+    __shared__ typename SF::Prepped s_c[MAX_LIST];
+    const int slot = blockIdx.y;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s_c[i] = SF::prep(coef + (size_t)i * D + slot * TAU);
+    __syncthreads();
+    size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    Acc192 acc[TAU];
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) { acc[l].clear(); if (accumulate) acc[l].add(out[(size_t)(slot * TAU + l) * out_pitch + x]); }
+    for (int i = 0; i < count; ++i) {
+        if (x >= vecs.len[i]) continue;
+        u64 v[TAU];
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) v[l] = vecs.p[i][(size_t)(slot * TAU + l) * v_pitch + x];
+        SF::mac(acc, v, s_c[i]);
+    }
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = F::reduce192(acc[l]);
+}
+// out[x][slot] (+)= sum_k sum_j w[k][j] * digit_k[x][j*S + slot]     (prepare_g1_and_3_k_mles_list, folding/utils.rs:524-546:
+// the alpha-Horner combination of the f-hat MLEs, computed from the int8 digits).  w: K x TAU slot-field elements.
+template <class Rg> __global__ void k_digit_lincomb(const int8_t* __restrict__ dig, size_t d_pitch, size_t d_vec_stride, int K,
+                                                    const u64* __restrict__ w, u64* __restrict__ out, size_t out_pitch, size_t n, int accumulate) {
+    typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
+    __shared__ u64 s_w[MAX_MU * TAU];
+    for (int i = threadIdx.x; i < K * TAU * TAU; i += blockDim.x) s_w[i] = w[i];
+    __syncthreads();
+    size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
+    if (x >= n) return;
+    Acc192 acc[TAU];
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) { acc[l].clear(); if (accumulate) acc[l].add(out[(size_t)(slot * TAU + l) * out_pitch + x]); }
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < TAU; ++j) {
+            u64 c = F::from_i64((int64_t)dig[(size_t)k * d_vec_stride + (size_t)(j * S + slot) * d_pitch + x]);
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) acc[l].mac(c, s_w[(k * TAU + j) * TAU + l]);
+        }
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = F::reduce192(acc[l]);
+}
+
+// ------------------------------------------------------------------------------------------------ K9 sumcheck
+// fix_variables on a list of tables (sumcheck/prover.rs:61-72): new[b] = old[2b] + r (old[2b+1] - old[2b]).
+// in/out may alias only through separate buffers (ping-pong).  r_sf: TAU limbs (slot-constant challenge).
+// grid = (b tiles, slots, tables)
+struct FoldArgs { const u64* in; u64* out; size_t in_pitch, out_pitch, in_stride, out_stride; size_t n_out; u64 r[8]; };
+template <class Rg> __global__ void k_fold(const FoldArgs a) {
+    typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
+    if (b >= a.n_out) return;
+    const u64* in = a.in + (size_t)blockIdx.z * a.in_stride; u64* out = a.out + (size_t)blockIdx.z * a.out_stride;
+    u64 f0[TAU], f1[TAU], t[TAU];
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) { const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(in + (size_t)(slot * TAU + l) * a.in_pitch + 2 * b); f0[l] = p.x; f1[l] = p.y; }
+    SF::sub(t, f1, f0); SF::mul(t, t, a.r); SF::add(t, t, f0);
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * a.out_pitch + b] = t[l];
+}
+
+// generic round evaluation for PRODUCTS / LIN combination functions (prove_round, sumcheck/prover.rs:111-143):
+// evals[e] = sum_b comb(v_k(2b) + e (v_k(2b+1) - v_k(2b))), e = 0..deg.   thread = (b, slot); partial: [b tile][deg+1][D]
+struct ScGenericArgs {
+    const u64* mle[SC_MAX_MLES]; size_t pitch; int n_mles, deg, n_terms, lin;
+    int term_len[SC_MAX_TERMS]; int term_idx[SC_MAX_TERMS][SC_MAX_FACTORS];
+    const u64* coef;           // n_terms x D on the device
+    size_t n_pairs; u64* partial;
+};
+template <class Rg, int NM> __global__ void __launch_bounds__(128)
+k_sc_generic(const ScGenericArgs a) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+    __shared__ u64 red[(SC_MAX_DEG + 1) * TAU * 32];
+    const int slot = blockIdx.y;
+    u64 ev[SC_MAX_DEG + 1][TAU];
+#pragma unroll
+    for (int e = 0; e <= SC_MAX_DEG; ++e)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) ev[e][l] = 0;
+    u64 cf[SC_MAX_TERMS][TAU];
+#pragma unroll
+    for (int t = 0; t < SC_MAX_TERMS; ++t)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) cf[t][l] = t < a.n_terms ? a.coef[(size_t)t * Rg::D + slot * TAU + l] : 0;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < a.n_pairs; b += (size_t)gridDim.x * blockDim.x) {
+        u64 val[NM][TAU], step[NM][TAU];
+#pragma unroll
+        for (int k = 0; k < NM; ++k)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) {
+                const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(a.mle[k] + (size_t)(slot * TAU + l) * a.pitch + 2 * b);
+                val[k][l] = p.x; step[k][l] = F::sub(p.y, p.x);
+            }
+#pragma unroll
+        for (int e = 0; e <= SC_MAX_DEG; ++e) {
+            if (e > a.deg) break;
+            u64 res[TAU] = {0};
+#pragma unroll
+            for (int t = 0; t < SC_MAX_TERMS; ++t) {
+                if (t >= a.n_terms) break;
+                u64 term[TAU];
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) term[l] = cf[t][l];
+#pragma unroll
+                for (int f = 0; f < SC_MAX_FACTORS; ++f) {
+                    if (f >= a.term_len[t]) break;
+                    const int idx = a.term_idx[t][f];
+                    u64 fac[TAU];
+#pragma unroll
+                    for (int k = 0; k < NM; ++k) if (k == idx) {
+#pragma unroll
+                        for (int l = 0; l < TAU; ++l) fac[l] = val[k][l];
+                    }
+                    SF::mul(term, term, fac);
+                }
+                SF::add(res, res, term);
+            }
+            if (a.lin) {
+                u64 last[TAU];
+#pragma unroll
+                for (int k = 0; k < NM; ++k) if (k == a.n_mles - 1) {
+#pragma unroll
+                    for (int l = 0; l < TAU; ++l) last[l] = val[k][l];
+                }
+                SF::mul(res, res, last);
+            }
+            SF::add(ev[e], ev[e], res);
+#pragma unroll
+            for (int k = 0; k < NM; ++k) SF::add(val[k], val[k], step[k]);
+        }
+    }
+    u64 v[(SC_MAX_DEG + 1) * TAU];
+#pragma unroll
+    for (int e = 0; e <= SC_MAX_DEG; ++e)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) v[e * TAU + l] = ev[e][l];
+    block_reduce_add<F, (SC_MAX_DEG + 1) * TAU>(v, red);
+    if (threadIdx.x == 0)
+        for (int e = 0; e <= a.deg; ++e)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) a.partial[((size_t)blockIdx.x * (a.deg + 1) + e) * Rg::D + slot * TAU + l] = v[e * TAU + l];
+}
+
+// ---- FOLD combination function, b = 2 (folding/utils.rs:273-325):
+//   g(x) = v0 v1 + v2 v3 + v4 * h(x),   h = sum_{k<2K} sum_{d<tau} mu_k^{d+1} (f_{k,d}^3 - f_{k,d})
+// h is a cubic along the line through a pair, so 4 points determine it; the degree-4 message needs 5 points of g.
+// "dense" = the five tables [eq(r_acc), G_acc, eq(r_new), G_new, eq(beta)].
+struct FoldScArgs {
+    const u64* dense; size_t dense_pitch, dense_stride;     // 5 tables
+    const u64* mu_pow;                                      // n_f x TAU limbs: mu_k^{d+1} (slot-constant)
+    int n_f;                                                // 2K * tau
+    size_t n_pairs; u64* partial;                           // [b tile][5][D]
+    // round 1: int8 digits, piece k at dig + k * dig_stride, coefficient plane c at c * dig_pitch
+    const int8_t* dig; size_t dig_pitch, dig_stride;
+    // rounds >= 2: slot-field tables, f-hat (k,d) at fh + (k*tau+d) * fh_stride
+    const u64* fh; size_t fh_pitch, fh_stride;
+};
+template <class Rg> __device__ __forceinline__ void fold_sc_tail(const FoldScArgs& a, size_t b, bool active, int slot, const u64 (*h)[Rg::TAU] /* h(0..4) */, u64* red) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+    u64 ev[5][TAU];
+#pragma unroll
+    for (int e = 0; e < 5; ++e)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) ev[e][l] = 0;
+    if (active) {
+        u64 val[5][TAU], step[5][TAU];
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) {
+                const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(a.dense + (size_t)k * a.dense_stride + (size_t)(slot * TAU + l) * a.dense_pitch + 2 * b);
+                val[k][l] = p.x; step[k][l] = F::sub(p.y, p.x);
+            }
+#pragma unroll
+        for (int e = 0; e < 5; ++e) {
+            u64 t0[TAU], t1[TAU];
+            SF::mul(t0, val[0], val[1]); SF::mul(t1, val[2], val[3]); SF::add(t0, t0, t1);
+            SF::mul(t1, val[4], h[e]); SF::add(ev[e], t0, t1);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) SF::add(val[k], val[k], step[k]);
+        }
+    }
+    u64 v[5 * TAU];
+#pragma unroll
+    for (int e = 0; e < 5; ++e)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) v[e * TAU + l] = ev[e][l];
+    block_reduce_add<F, 5 * TAU>(v, red);
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int e = 0; e < 5; ++e)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) a.partial[((size_t)blockIdx.x * 5 + e) * Rg::D + slot * TAU + l] = v[e * TAU + l];
+}
+// round 1: every f-hat entry is a balanced digit in {-1,0,1} embedded in the base field (arith.rs:283-289), so
+// f^3 - f vanishes at X = 0, 1 and is a small integer at X = 2, 3; h(4) follows from the cubic's finite differences.
+template <class Rg> __global__ void __launch_bounds__(128)
+k_fold_sc_round1(const FoldScArgs a) {
+    typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
+    __shared__ u64 red[5 * TAU * 32];
+    __shared__ u64 s_mu[MAX_MU * TAU];
+    for (int i = threadIdx.x; i < a.n_f * TAU; i += blockDim.x) s_mu[i] = a.mu_pow[i];
+    __syncthreads();
+    const int slot = blockIdx.y;
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const bool active = b < a.n_pairs;
+    u64 h[5][TAU];
+#pragma unroll
+    for (int e = 0; e < 5; ++e)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) h[e][l] = 0;
+    if (active) {
+        Acc192 p2[TAU], n2[TAU], p3[TAU], n3[TAU];   // positive / negative parts of h(2), h(3)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) { p2[l].clear(); n2[l].clear(); p3[l].clear(); n3[l].clear(); }
+        const int K2 = a.n_f / TAU;
+        for (int k = 0; k < K2; ++k)
+#pragma unroll
+            for (int d = 0; d < TAU; ++d) {
+                const char2 dd = *reinterpret_cast<const char2*>(a.dig + (size_t)k * a.dig_stride + (size_t)(d * S + slot) * a.dig_pitch + 2 * b);
+                const int f2 = 2 * dd.y - dd.x, f3 = 3 * dd.y - 2 * dd.x;
+                const int g2 = f2 * f2 * f2 - f2, g3 = f3 * f3 * f3 - f3;
+                const u64* mu = &s_mu[(k * TAU + d) * TAU];
+                if (g2 > 0) { for (int l = 0; l < TAU; ++l) p2[l].mac((u64)g2, mu[l]); } else if (g2 < 0) { for (int l = 0; l < TAU; ++l) n2[l].mac((u64)(-g2), mu[l]); }
+                if (g3 > 0) { for (int l = 0; l < TAU; ++l) p3[l].mac((u64)g3, mu[l]); } else if (g3 < 0) { for (int l = 0; l < TAU; ++l) n3[l].mac((u64)(-g3), mu[l]); }
+            }
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) {
+            const u64 h2 = F::sub(F::reduce192(p2[l]), F::reduce192(n2[l])), h3 = F::sub(F::reduce192(p3[l]), F::reduce192(n3[l]));
+            h[2][l] = h2; h[3][l] = h3;
+            // h(0) = h(1) = 0 and third differences constant: h(4) = 4 h(3) - 6 h(2)
+            const u64 h3x2 = F::add(h3, h3), h3x4 = F::add(h3x2, h3x2), h2x2 = F::add(h2, h2), h2x6 = F::add(F::add(h2x2, h2x2), h2x2);
+            h[4][l] = F::sub(h3x4, h2x6);
+        }
+    }
+    fold_sc_tail<Rg>(a, b, active, slot, h, red);
+}
+// after the first challenge r: f-hat tables become slot-field valued: new[b] = d0 + r (d1 - d0)
+template <class Rg> __global__ void k_fold_digits(const int8_t* __restrict__ dig, size_t dig_pitch, size_t dig_stride, int n_f,
+                                                  u64* __restrict__ out, size_t out_pitch, size_t out_stride, size_t n_out, const FoldArgs r) {
+    typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y, kd = blockIdx.z;
+    if (b >= n_out) return;
+    const int k = kd / TAU, d = kd % TAU;
+    const char2 dd = *reinterpret_cast<const char2*>(dig + (size_t)k * dig_stride + (size_t)(d * S + slot) * dig_pitch + 2 * b);
+    const u64 st = F::from_i64((int64_t)dd.y - dd.x), d0 = F::from_i64((int64_t)dd.x);
+    u64* o = out + (size_t)kd * out_stride;
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) { u64 v = F::mul(st, r.r[l]); if (l == 0) v = F::add(v, d0); o[(size_t)(slot * TAU + l) * out_pitch + b] = v; }
+}
+// rounds >= 2
+template <class Rg> __global__ void __launch_bounds__(128)
+k_fold_sc_round(const FoldScArgs a) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+    __shared__ u64 red[5 * TAU * 32];
+    __shared__ typename SF::Prepped s_mu[MAX_MU];
+    for (int i = threadIdx.x; i < a.n_f; i += blockDim.x) s_mu[i] = SF::prep(a.mu_pow + (size_t)i * TAU);
+    __syncthreads();
+    const int slot = blockIdx.y;
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const bool active = b < a.n_pairs;
+    u64 h[5][TAU];
+#pragma unroll
+    for (int e = 0; e < 5; ++e)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) h[e][l] = 0;
+    if (active) {
+        Acc192 acc[4][TAU];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) acc[e][l].clear();
+        for (int kd = 0; kd < a.n_f; ++kd) {
+            u64 u[TAU], s[TAU];
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) {
+                const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(a.fh + (size_t)kd * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b);
+                u[l] = p.x; s[l] = F::sub(p.y, p.x);
+            }
+            // (u + e s)^3 - (u + e s) for e = 0..3 from u^2, s^2, u^3, s^3, u^2 s, u s^2
+            u64 uu[TAU], ss[TAU], u3[TAU], s3[TAU], uus[TAU], uss[TAU];
+            SF::sqr(uu, u); SF::sqr(ss, s); SF::mul(u3, uu, u); SF::mul(s3, ss, s); SF::mul(uus, uu, s); SF::mul(uss, ss, u);
+            u64 g[TAU], a3[TAU], b3[TAU], t[TAU];
+            SF::add(a3, uus, uus); SF::add(a3, a3, uus);       // 3 u^2 s
+            SF::add(b3, uss, uss); SF::add(b3, b3, uss);       // 3 u s^2
+            // e = 0: u^3 - u
+            SF::sub(g, u3, u); SF::mac(acc[0], g, s_mu[kd]);
+            // e = 1: u^3 + 3u^2 s + 3 u s^2 + s^3 - u - s
+            SF::add(g, g, a3); SF::add(g, g, b3); SF::add(g, g, s3); SF::sub(g, g, s); SF::mac(acc[1], g, s_mu[kd]);
+            // e = 2: u^3 + 6 u^2 s + 12 u s^2 + 8 s^3 - u - 2s  = g1 + 3u^2 s + 9 u s^2 + 7 s^3 - s
+            SF::add(g, g, a3); SF::add(t, b3, b3); SF::add(t, t, b3); SF::add(g, g, t);                // + 3u^2 s + 9 u s^2
+            u64 s3x2[TAU], s3x4[TAU], s3x7[TAU];
+            SF::add(s3x2, s3, s3); SF::add(s3x4, s3x2, s3x2); SF::add(s3x7, s3x4, s3x2); SF::add(s3x7, s3x7, s3);
+            SF::add(g, g, s3x7); SF::sub(g, g, s); SF::mac(acc[2], g, s_mu[kd]);
+            // e = 3: g2 + 3 u^2 s + 15 u s^2 + 19 s^3 - s
+            SF::add(g, g, a3); SF::add(t, t, b3); SF::add(t, t, b3); SF::add(g, g, t);                 // + 3u^2 s + 15 u s^2
+            u64 s3x16[TAU], s3x19[TAU];
+            SF::add(s3x16, s3x4, s3x4); SF::add(s3x16, s3x16, s3x16); SF::add(s3x19, s3x16, s3x2); SF::add(s3x19, s3x19, s3);
+            SF::add(g, g, s3x19); SF::sub(g, g, s); SF::mac(acc[3], g, s_mu[kd]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) h[e][l] = F::reduce192(acc[e][l]);
+        // cubic: h(4) = 4 h(3) - 6 h(2) + 4 h(1) - h(0)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) {
+            const u64 a4 = F::add(F::add(h[3][l], h[3][l]), F::add(h[3][l], h[3][l]));
+            const u64 c2 = F::add(h[2][l], h[2][l]), c6 = F::add(F::add(c2, c2), c2);
+            const u64 b4 = F::add(F::add(h[1][l], h[1][l]), F::add(h[1][l], h[1][l]));
+            h[4][l] = F::sub(F::add(F::sub(a4, c6), b4), h[0][l]);
+        }
+    }
+    fold_sc_tail<Rg>(a, b, active, slot, h, red);
+}
+
+}  // namespace lf

@@ -1,0 +1,374 @@
+// One LatticeFold folding step on the device: the host side of NIFSProver::prove
+//   crates/latticefold/src/nifs.rs:48-103   = linearization (nifs/linearization.rs:145-189)
+//                                            + 2 x decomposition (nifs/decomposition.rs:33-88)
+//                                            + folding (nifs/folding.rs:42-130)
+// written above the kernels.  What the reference does on small vectors between transcript calls (x_s, y_0 Horner,
+// RotSum, cm_0/u_0/x_0) stays on the CPU here as well; everything witness-sized runs on the GPU and stays in HBM.
+// Algebraic regrouping relative to the reference (results are identical field elements because the arithmetic is exact):
+//   * f-hat MLEs are never materialised: MLE j slot k of a witness IS coefficient plane j*S+k (arith.rs:282-291);
+//     decomposed pieces are held as int8 balanced digits;
+//   * theta (folding.rs:236-246) is read off the sumcheck's final fold instead of a second evaluate_mles pass;
+//   * eq(r,.) tables are built once per point and shared by decomposition and folding.
+#pragma once
+#include "sumcheck.cuh"
+
+struct lf_witness { lf::u64 *f = nullptr, *f_coeff = nullptr, *w_ccs = nullptr; size_t n = 0, pitch = 0, W = 0, w_pitch = 0; };
+
+struct lf_prover {
+    lf_ctx* ctx = nullptr;
+    int ring = 0, L = 0, K = 0; uint64_t B = 0, b = 0;
+    size_t kappa = 0, n = 0;
+    size_t m = 0, n_ccs = 0, l = 0, t = 0, q = 0, d = 0, s = 0;
+    std::vector<std::vector<int>> S; lf::HV c;
+    lf_ajtai* A = nullptr; bool own_A = true;
+    std::vector<lf_sparse*> M;
+    double timings[5] = {0, 0, 0, 0, 0};
+};
+
+namespace lf {
+
+struct LCCCS { HV r, v, cm, u, x_w, h; };
+
+template <class Rg> struct Prover {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef HostRing<Rg> HR; typedef typename HR::El El;
+    static constexpr int D = Rg::D, S = Rg::S, TAU = Rg::TAU;
+    lf_prover* P; Engine<Rg> E; HR H;
+    explicit Prover(lf_prover* p) : P(p), E(p->ctx), H(E.tab()) {}
+
+    static HV sf_to_ring(const std::vector<u64>& sf) { size_t n = sf.size() / TAU; HV o(n * D); for (size_t i = 0; i < n; ++i) { El e = HR::from_sf(&sf[i * TAU]); std::memcpy(&o[i * D], e.data(), 8 * D); } return o; }
+    static std::vector<u64> squeeze(Transcript<Rg>& T, const char* tag, int n) { T.absorb_tag(tag); std::vector<u64> o((size_t)n * TAU); for (int i = 0; i < n; ++i) T.get_challenge(&o[(size_t)i * TAU]); return o; }
+    static size_t cnt(const HV& v) { return v.size() / D; }
+
+    void sanity_check() const {   // nifs.rs:165-173
+        size_t want = std::max((P->n_ccs - P->l - 1) * (size_t)P->L, P->m), p2 = 1; while (p2 < want) p2 <<= 1;
+        if (P->m != p2 || ((size_t)1 << P->s) != P->m) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "InvalidSizeBounds");
+        if (P->n > P->m) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "witness longer than 2^s");
+    }
+
+    // ------------------------------------------------------------------ witnesses (arith.rs:299-313, Witness::from_f)
+    lf_witness* witness_from_f_device(u64* f_dev /* takes ownership, pitch = pitch_of(n) */) {
+        lf_witness* w = new lf_witness; w->n = P->n; w->pitch = pitch_of(P->n); w->f = f_dev;
+        if (P->n % P->L) throw LfException(LF_ERR_INCORRECT_LENGTH, "witness length is not a multiple of L");
+        w->W = P->n / P->L; w->w_pitch = pitch_of(w->W);
+        w->f_coeff = E.template dalloc<u64>(w->pitch * D); E.crt(w->f, w->pitch, w->f_coeff, w->pitch, w->n, true);
+        w->w_ccs = E.template dalloc<u64>(w->w_pitch * D); E.gadget_recompose(w->f, w->pitch, w->w_ccs, w->w_pitch, w->W, P->B, P->L);
+        return w;
+    }
+    lf_witness* upload_witness(const u64* f_host) {
+        u64* f = E.template dalloc<u64>(pitch_of(P->n) * D); E.upload_planes(f_host, P->n, f, pitch_of(P->n));
+        return witness_from_f_device(f);
+    }
+    void free_witness(lf_witness* w) { if (!w) return; E.dfree(w->f); E.dfree(w->f_coeff); E.dfree(w->w_ccs); delete w; }
+
+    // ------------------------------------------------------------------ shared device helpers
+    struct DevVec { u64* p = nullptr; size_t n = 0, pitch = 0; };
+    DevVec eq_table(const HV& r) { DevVec v; v.n = (size_t)1 << cnt(r); v.pitch = pitch_of(v.n); v.p = E.template dalloc<u64>(v.pitch * D); E.eq_table(r.data(), (int)cnt(r), v.p, v.pitch); return v; }
+    // Mz tables for a list of z = head_k || tail_k; out: [count * t] rows of pitch mz_pitch, effective length eff[j]
+    struct MzSet { u64* p = nullptr; size_t pitch = 0, stride = 0; int rows = 0; size_t* d_len = nullptr; std::vector<size_t> len; };
+    MzSet alloc_mz(int count) {
+        MzSet z; z.rows = count * (int)P->t; size_t mx = 1; for (auto* M : P->M) mx = std::max(mx, M->eff_rows);
+        z.pitch = pitch_of(mx); z.stride = z.pitch * D; z.p = E.template dalloc<u64>((size_t)z.rows * z.stride);
+        z.len.resize(z.rows); for (int i = 0; i < z.rows; ++i) z.len[i] = P->M[i % P->t]->eff_rows;
+        z.d_len = E.template dalloc<size_t>(z.rows);
+        LF_CUDA(cudaMemcpyAsync(z.d_len, z.len.data(), z.rows * sizeof(size_t), cudaMemcpyHostToDevice, E.st())); E.sync();
+        return z;
+    }
+    void free_mz(MzSet& z) { E.dfree(z.p); E.dfree(z.d_len); z.p = nullptr; }
+    void compute_mz(MzSet& z, int k, const HV& head, const u64* tail, size_t tail_pitch, size_t tail_len) {   // mat_vec_mul x t (arith/utils.rs:52-65)
+        const size_t hl = cnt(head), hp = pitch_of(hl);
+        u64* d_head = E.template dalloc<u64>(hp * D); E.upload_small(head.data(), hl, d_head, hp);
+        for (size_t j = 0; j < P->t; ++j) {
+            if (P->M[j]->ncols != hl + tail_len) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "LengthsNotEqual(M, z)");
+            E.spmv(P->M[j], d_head, hl, hp, tail, tail_pitch, z.p + ((size_t)k * P->t + j) * z.stride, z.pitch, P->M[j]->eff_rows);
+        }
+        E.dfree(d_head);
+    }
+    // evaluate every Mz row at the point whose eq table is given -> rows x D limbs (host)
+    HV eval_mz(const MzSet& z, int row0, int rows, const DevVec& eq) {
+        PtrList Y; Y.p[0] = eq.p; Y.len[0] = eq.n;
+        u64* d_out = E.small_dev((size_t)rows * D);
+        E.dot(z.p + (size_t)row0 * z.stride, z.stride, z.pitch, rows, z.d_len + row0, Y, eq.pitch, 1, z.pitch, d_out);
+        HV o((size_t)rows * D); E.download_words(d_out, o.size(), o.data()); return o;
+    }
+
+    // ------------------------------------------------------------------ linearization (linearization.rs:145-189)
+    struct LinOut { LCCCS lc; HV msgs; DevVec eq_r; };
+    LinOut linearize(const HV& cm_i_cm, const HV& x_ccs, const lf_witness* w, Transcript<Rg>& T) {
+        LinOut o; const int s = (int)P->s; const size_t m = P->m;
+        HV head = x_ccs; { El one = HR::from_u64(1); head.insert(head.end(), one.begin(), one.end()); }      // z = x || 1 || w  (arith.rs:399-409)
+        HV beta = sf_to_ring(squeeze(T, "beta_s", s));                                                       // linearization/utils.rs:113-124
+        MzSet mz = alloc_mz(1); compute_mz(mz, 0, head, w->w_ccs, w->w_pitch, w->W);
+        // sumcheck list: for each term with c_i != 0, the Mz named by S_i; eq(beta,.) last (linearization/utils.rs:63-88)
+        std::vector<int> list; for (size_t i = 0; i < P->q; ++i) { bool z = true; for (int l = 0; l < D; ++l) z = z && P->c[i * D + l] == 0; if (z) continue; for (int j : P->S[i]) list.push_back(j); }
+        const int Mn = (int)list.size() + 1;
+        if (Mn > SC_MAX_MLES || (int)P->q > SC_MAX_TERMS) throw LfException(LF_ERR_UNSUPPORTED, "CCS shape exceeds SC_MAX_MLES / SC_MAX_TERMS");
+        lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = (int)P->d + 1; sc.kind = LF_COMB_LIN; sc.len = m;
+        SumcheckDriver<Rg> drv(P->ctx, &sc);
+        SumcheckDriver<Rg>::alloc_group(E, sc.dense, Mn, m);
+        LF_CUDA(cudaMemsetAsync(sc.dense.cur, 0, (size_t)Mn * sc.dense.stride * 8, E.st()));
+        for (int k = 0; k + 1 < Mn; ++k) { const int j = list[k];
+            LF_CUDA(cudaMemcpy2DAsync(sc.dense.cur + (size_t)k * sc.dense.stride, sc.dense.pitch * 8, mz.p + (size_t)j * mz.stride, mz.pitch * 8, mz.len[j] * 8, D, cudaMemcpyDeviceToDevice, E.st())); }
+        E.eq_table(beta.data(), s, sc.dense.cur + (size_t)(Mn - 1) * sc.dense.stride, sc.dense.pitch);
+        // LIN comb (linearization/utils.rs:90-107): vals[] is indexed by the CCS matrix index j.  The list position of
+        // matrix j coincides with j for R1CS and the degree-3 CCS; reproduce the reference literally and refuse anything else.
+        sc.gen.n_mles = Mn; sc.gen.deg = sc.deg; sc.gen.lin = 1; sc.gen.n_terms = (int)P->q;
+        for (size_t i = 0; i < P->q; ++i) { if (P->S[i].size() > SC_MAX_FACTORS) throw LfException(LF_ERR_UNSUPPORTED, "CCS multiset too large"); sc.gen.term_len[i] = (int)P->S[i].size();
+            for (size_t f = 0; f < P->S[i].size(); ++f) { int j = P->S[i][f]; if (j < 0 || j >= Mn) throw LfException(LF_ERR_INCORRECT_LENGTH, "comb index outside MLE list"); sc.gen.term_idx[i][f] = j; } }
+        sc.d_coef = E.template dalloc<u64>(P->q * D);
+        LF_CUDA(cudaMemcpyAsync(sc.d_coef, P->c.data(), P->q * D * 8, cudaMemcpyHostToDevice, E.st())); E.sync();
+        std::vector<u64> point; o.msgs = run_sumcheck(drv, T, point);
+        drv.free_all();
+        o.lc.r = sf_to_ring(point);
+        o.eq_r = eq_table(o.lc.r);
+        // v = f-hat(r) (linearization.rs:126-131), u = Mz(r) (:133-139)
+        u64* d_v = E.small_dev((size_t)TAU * D);
+        E.template coeff_eval<u64>(w->f_coeff, w->pitch, 0, 1, o.eq_r.p, o.eq_r.pitch, w->n, d_v);
+        o.lc.v.resize((size_t)TAU * D); E.download_words(d_v, o.lc.v.size(), o.lc.v.data());
+        o.lc.u = eval_mz(mz, 0, (int)P->t, o.eq_r);
+        free_mz(mz);
+        T.absorb_slice(o.lc.v.data(), cnt(o.lc.v)); T.absorb_slice(o.lc.u.data(), cnt(o.lc.u));
+        o.lc.cm = cm_i_cm; o.lc.x_w = x_ccs; { El one = HR::from_u64(1); o.lc.h.assign(one.begin(), one.end()); }
+        return o;
+    }
+    // MLSumcheck::prove_as_subprotocol (sumcheck.rs:53-80); returns nv x (deg+1) x D message limbs, point = nv x TAU
+    HV run_sumcheck(SumcheckDriver<Rg>& drv, Transcript<Rg>& T, std::vector<u64>& point, HV* final_vals = nullptr) {
+        lf_sumcheck* sc = drv.sc; const int ne = sc->deg + 1;
+        if (sc->nv == 0) throw LfException(LF_ERR_SUMCHECK_MISUSE, "Attempt to prove a constant.");
+        T.absorb_u64((u64)sc->nv); T.absorb_u64((u64)sc->deg);
+        HV msgs((size_t)sc->nv * ne * D); point.assign((size_t)sc->nv * TAU, 0);
+        for (int i = 0; i < sc->nv; ++i) {
+            if (i > 0) drv.apply_challenge(&point[(size_t)(i - 1) * TAU]);
+            u64* msg = &msgs[(size_t)i * ne * D];
+            drv.evaluate(msg);
+            auto t0 = std::chrono::steady_clock::now();
+            T.absorb_slice(msg, ne); T.get_challenge(&point[(size_t)i * TAU]); T.absorb_sf(&point[(size_t)i * TAU]);
+            P->timings[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+        if (final_vals) { drv.apply_challenge(&point[(size_t)(sc->nv - 1) * TAU]); final_vals->resize((size_t)(sc->dense.count + sc->n_f) * D); drv.final_values(final_vals->data()); }
+        return msgs;
+    }
+
+    // ------------------------------------------------------------------ decomposition (decomposition.rs:33-88)
+    struct StepBuffers {    // witness-sized state shared by the two decompositions and the folding
+        int8_t* dig = nullptr; size_t dig_pitch = 0, dig_stride = 0;     // [2K][D][pitch]
+        u64* pieces = nullptr; size_t pc_pitch = 0, pc_stride = 0;       // NTT form of every piece, [2K][D][pitch]
+        u64* wccs = nullptr; size_t wc_pitch = 0, wc_stride = 0;         // gadget_recompose of every piece, [2K][D][pitch]
+        MzSet mz;                                                        // [2K * t]
+    };
+    struct DecOut { std::vector<HV> x_s, y_s, u_s, v_s; std::vector<LCCCS> lc; };
+    // decompose_big_vec_into_k_vec_and_compose_back (decomposition/utils.rs:12-42) on l+1 elements: host
+    std::vector<HV> compute_x_s(const LCCCS& cm) {
+        HV xs = cm.x_w; xs.insert(xs.end(), cm.h.begin(), cm.h.end());
+        const size_t ne = cnt(xs); const int L = P->L, K = P->K;
+        std::vector<HV> out(K, HV(ne * D, 0));
+        std::vector<int64_t> dB(L), db(K);
+        for (size_t e = 0; e < ne; ++e) {
+            El co = H.icrt(HR::load(&xs[e * D]));
+            // piece k, chunk digit l, coefficient c  ->  recompose over l with base B
+            std::vector<El> acc(K, HR::zero());
+            for (int c = 0; c < D; ++c) {
+                if (!balanced_digits(F::to_signed(co[c]), (int64_t)P->B, L, dB.data())) throw LfException(LF_ERR_DOES_NOT_FIT, "x_s: coefficient does not fit L digits of base B");
+                u64 pw = 1;
+                for (int l = 0; l < L; ++l) {
+                    if (!balanced_digits(dB[l], (int64_t)P->b, K, db.data())) throw LfException(LF_ERR_DOES_NOT_FIT, "x_s: digit does not fit K digits of base b");
+                    for (int k = 0; k < K; ++k) acc[k][c] = F::add(acc[k][c], F::mul(F::from_i64(db[k]), pw));
+                    pw = F::mul(pw, P->B % F::P);
+                }
+            }
+            for (int k = 0; k < K; ++k) { El nt = H.crt(acc[k]); std::memcpy(&out[k][e * D], nt.data(), 8 * D); }
+        }
+        return out;
+    }
+    DecOut decompose(const LCCCS& cm, const lf_witness* w, const DevVec& eq_r, StepBuffers& sb, int half, Transcript<Rg>& T) {
+        DecOut o; const int K = P->K; const size_t n = P->n, kappa = P->kappa;
+        int8_t* dig = sb.dig + (size_t)half * K * sb.dig_stride;
+        u64* pieces = sb.pieces + (size_t)half * K * sb.pc_stride;
+        u64* wccs = sb.wccs + (size_t)half * K * sb.wc_stride;
+        // decompose_witness: f_coeff.decompose_to_vec(b, K).transpose() (decomposition.rs:162-167), then CRT and recompose per piece (arith.rs:324-338)
+        E.digit_split(w->f_coeff, w->pitch, dig, sb.dig_pitch, n, P->b, K);
+        for (int k = 0; k < K; ++k) {
+            E.crt_digits(dig + (size_t)k * sb.dig_stride, sb.dig_pitch, pieces + (size_t)k * sb.pc_stride, sb.pc_pitch, n);
+            E.gadget_recompose(pieces + (size_t)k * sb.pc_stride, sb.pc_pitch, wccs + (size_t)k * sb.wc_stride, sb.wc_pitch, w->W, P->B, P->L);
+        }
+        E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_witness: a coefficient does not fit K digits of base b");
+        o.x_s = compute_x_s(cm);
+        // commit_witnesses (decomposition.rs:178-201): K-1 commits in one pass over A, y_0 = cm - b (y_1 + b (y_2 + ...))
+        o.y_s.assign(K, HV(kappa * D, 0));
+        if (cnt(cm.cm) != kappa) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongCommitmentLength");
+        if (K > 1) {
+            PtrList Y; for (int k = 1; k < K; ++k) { Y.p[k - 1] = pieces + (size_t)k * sb.pc_stride; Y.len[k - 1] = n; }
+            u64* d_y = E.small_dev(kappa * (K - 1) * D);
+            E.dot(P->A->p, P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y);
+            HV all(kappa * (K - 1) * D); E.download_words(d_y, all.size(), all.data());
+            for (int k = 1; k < K; ++k) for (size_t i = 0; i < kappa; ++i) std::memcpy(&o.y_s[k][i * D], &all[(i * (K - 1) + (k - 1)) * D], 8 * D);
+        }
+        { HV bsum(kappa * D, 0); const u64 bm = P->b % F::P;
+          for (int k = K - 1; k >= 1; --k) for (size_t i = 0; i < kappa * D; ++i) bsum[i] = F::mul(F::add(bsum[i], o.y_s[k][i]), bm);
+          for (size_t i = 0; i < kappa * D; ++i) o.y_s[0][i] = F::sub(cm.cm[i], bsum[i]); }
+        // compute_v_s (decomposition.rs:204-211): f-hat of piece k evaluated at r, straight from the digits
+        { u64* d_v = E.small_dev((size_t)K * TAU * D);
+          E.template coeff_eval<int8_t>(dig, sb.dig_pitch, sb.dig_stride, K, eq_r.p, eq_r.pitch, n, d_v);
+          HV all((size_t)K * TAU * D); E.download_words(d_v, all.size(), all.data());
+          for (int k = 0; k < K; ++k) o.v_s.emplace_back(all.begin() + (size_t)k * TAU * D, all.begin() + (size_t)(k + 1) * TAU * D); }
+        // compute_mz_mles / compute_u_s (decomposition.rs:214-256): z_k = x_s[k] || w_ccs_k
+        for (int k = 0; k < K; ++k) compute_mz(sb.mz, half * K + k, o.x_s[k], wccs + (size_t)k * sb.wc_stride, sb.wc_pitch, w->W);
+        { HV all = eval_mz(sb.mz, half * K * (int)P->t, K * (int)P->t, eq_r);
+          for (int k = 0; k < K; ++k) o.u_s.emplace_back(all.begin() + (size_t)k * P->t * D, all.begin() + (size_t)(k + 1) * P->t * D); }
+        auto t0 = std::chrono::steady_clock::now();
+        for (int k = 0; k < K; ++k) {
+            const HV& x = o.x_s[k];
+            T.absorb_slice(x.data(), cnt(x)); T.absorb_slice(o.y_s[k].data(), kappa); T.absorb_slice(o.u_s[k].data(), cnt(o.u_s[k])); T.absorb_slice(o.v_s[k].data(), cnt(o.v_s[k]));
+            if (x.empty()) throw LfException(LF_ERR_INCORRECT_LENGTH, "IncorrectLength");
+            LCCCS L; L.r = cm.r; L.v = o.v_s[k]; L.cm = o.y_s[k]; L.u = o.u_s[k]; L.x_w.assign(x.begin(), x.end() - D); L.h.assign(x.end() - D, x.end());
+            o.lc.push_back(std::move(L));
+        }
+        P->timings[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return o;
+    }
+
+    // ------------------------------------------------------------------ folding (folding.rs:42-130)
+    struct FoldOut { HV msgs; std::vector<HV> theta, eta; LCCCS lc; u64* f0 = nullptr; };
+    // rot_lin_combination (cyclotomic-rings/src/rotation.rs:45-104), host: d^2 base-by-slot-field products per term
+    static HV rot_lin_combination(const std::vector<El>& rho_coeff, const std::vector<HV>& theta) {
+        HV acc((size_t)D * TAU, 0);
+        for (size_t i = 0; i < rho_coeff.size(); ++i) {
+            if (theta[i].size() != (size_t)TAU * D) throw LfException(LF_ERR_INCORRECT_LENGTH, "rot_sum: b.len() != dimension");
+            El a = rho_coeff[i];
+            for (int bi = 0; bi < D; ++bi) {          // flatten_to_coeffs: element-major, slot-minor == memory order
+                const u64* Bv = &theta[i][(size_t)bi * TAU];
+                for (int j = 0; j < D; ++j) for (int l = 0; l < TAU; ++l) acc[(size_t)j * TAU + l] = F::add(acc[(size_t)j * TAU + l], F::mul(a[j], Bv[l]));
+                HR::mul_x(a);
+            }
+        }
+        return acc;
+    }
+    FoldOut fold(const std::vector<LCCCS>& lcs, StepBuffers& sb, const DevVec& eq_acc, const DevVec& eq_new, Transcript<Rg>& T) {
+        FoldOut o; const int K = P->K, s = (int)P->s; const size_t n = P->n, m = P->m, t = P->t;
+        if ((int)lcs.size() != 2 * K) throw LfException(LF_ERR_INCORRECT_LENGTH, "IncorrectLength");
+        if (P->b != 2) throw LfException(LF_ERR_UNSUPPORTED, "folding sumcheck kernels are specialised for b = 2 (every reference parameter set but Stark)");
+        // squeeze_alpha_beta_zeta_mu (folding/utils.rs:51-96)
+        std::vector<u64> alpha = squeeze(T, "alpha_s", 2 * K), zeta = squeeze(T, "zeta_s", 2 * K), mu = squeeze(T, "mu_s", 2 * K - 1);
+        { u64 one[TAU] = {0}; one[0] = 1; mu.insert(mu.end(), one, one + TAU); }
+        HV beta = sf_to_ring(squeeze(T, "beta_s", s));
+        // dense tables [eq(r_acc), G_acc, eq(r_new), G_new, eq(beta)]  (create_sumcheck_polynomial, folding/utils.rs:200-259)
+        lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = 2 * (int)P->b; sc.kind = LF_COMB_FOLD; sc.len = m;
+        SumcheckDriver<Rg> drv(P->ctx, &sc);
+        SumcheckDriver<Rg>::alloc_group(E, sc.dense, 5, m);
+        auto tbl = [&](int i) { return sc.dense.cur + (size_t)i * sc.dense.stride; };
+        LF_CUDA(cudaMemcpy2DAsync(tbl(0), sc.dense.pitch * 8, eq_acc.p, eq_acc.pitch * 8, m * 8, D, cudaMemcpyDeviceToDevice, E.st()));
+        LF_CUDA(cudaMemcpy2DAsync(tbl(2), sc.dense.pitch * 8, eq_new.p, eq_new.pitch * 8, m * 8, D, cudaMemcpyDeviceToDevice, E.st()));
+        E.eq_table(beta.data(), s, tbl(4), sc.dense.pitch);
+        for (int half = 0; half < 2; ++half) {
+            u64* G = tbl(1 + 2 * half);
+            LF_CUDA(cudaMemsetAsync(G, 0, sc.dense.stride * 8, E.st()));
+            // sum_i Horner_{alpha_i}(f-hat_i[tau-1..0]) = sum_i sum_d alpha_i^{d+1} f-hat_{i,d}   (folding/utils.rs:524-546)
+            std::vector<u64> wts((size_t)K * TAU * TAU);
+            for (int i = 0; i < K; ++i) { const u64* a = &alpha[(size_t)(half * K + i) * TAU]; u64 pw[TAU]; std::memcpy(pw, a, 8 * TAU);
+                for (int dd = 0; dd < TAU; ++dd) { std::memcpy(&wts[((size_t)i * TAU + dd) * TAU], pw, 8 * TAU); SF::mul(pw, pw, a); } }
+            u64* d_w = E.template dalloc<u64>(wts.size());
+            LF_CUDA(cudaMemcpyAsync(d_w, wts.data(), wts.size() * 8, cudaMemcpyHostToDevice, E.st())); E.sync();
+            E.launch("k_digit_lincomb", [&] { k_digit_lincomb<Rg><<<dim3(Engine<Rg>::blocks_for(n, 128), S), 128, 0, E.st()>>>(sb.dig + (size_t)half * K * sb.dig_stride, sb.dig_pitch, sb.dig_stride, K, d_w, G, sc.dense.pitch, n, 0); });
+            E.dfree(d_w);
+            // + sum_i Horner_{zeta_i}(Mz_i[t-1..0])   (calculate_challenged_mz_mle, folding.rs:208-226)
+            HV coef((size_t)K * t * D); PtrList pl; std::vector<const u64*> ptrs; std::vector<size_t> lens;
+            for (int i = 0; i < K; ++i) { const u64* z = &zeta[(size_t)(half * K + i) * TAU]; u64 pw[TAU]; std::memcpy(pw, z, 8 * TAU);
+                for (size_t j = 0; j < t; ++j) { El e = HR::from_sf(pw); std::memcpy(&coef[((size_t)i * t + j) * D], e.data(), 8 * D); SF::mul(pw, pw, z);
+                    ptrs.push_back(sb.mz.p + ((size_t)(half * K + i) * t + j) * sb.mz.stride); lens.push_back(sb.mz.len[(size_t)(half * K + i) * t + j]); } }
+            for (size_t done = 0; done < ptrs.size(); done += MAX_LIST) {
+                const int chunk = (int)std::min<size_t>(MAX_LIST, ptrs.size() - done);
+                for (int i = 0; i < chunk; ++i) { pl.p[i] = ptrs[done + i]; pl.len[i] = lens[done + i]; }
+                if (sb.mz.pitch > sc.dense.pitch) throw LfException(LF_ERR_MLE_LEN, "IncorrectLength");
+                E.lincomb(pl, sb.mz.pitch, chunk, &coef[done * D], G, sc.dense.pitch, sb.mz.pitch, true);
+            }
+        }
+        sc.dig = sb.dig; sc.dig_pitch = sb.dig_pitch; sc.dig_stride = sb.dig_stride;
+        { HV mu_ring = sf_to_ring(mu); drv.set_mu(mu_ring.data(), 2 * K); }
+        std::vector<u64> point; HV finals;
+        o.msgs = run_sumcheck(drv, T, point, &finals);
+        drv.free_all();
+        HV r0 = sf_to_ring(point);
+        // theta_i = f-hat_i(r_0): the sumcheck's fully folded f-hat tables (get_thetas, folding.rs:236-246)
+        for (int i = 0; i < 2 * K; ++i) o.theta.emplace_back(finals.begin() + (size_t)(5 + i * TAU) * D, finals.begin() + (size_t)(5 + (i + 1) * TAU) * D);
+        // eta_i = Mz_i(r_0) (get_etas, folding.rs:248-256)
+        { DevVec eq0 = eq_table(r0); HV all = eval_mz(sb.mz, 0, 2 * K * (int)t, eq0); E.dfree(eq0.p);
+          for (int i = 0; i < 2 * K; ++i) o.eta.emplace_back(all.begin() + (size_t)i * t * D, all.begin() + (size_t)(i + 1) * t * D); }
+        auto t0 = std::chrono::steady_clock::now();
+        for (auto& th : o.theta) T.absorb_slice(th.data(), cnt(th));
+        for (auto& et : o.eta) T.absorb_slice(et.data(), cnt(et));
+        // get_rhos (folding/utils.rs:116-131)
+        T.absorb_tag("rho_s");
+        std::vector<El> rho_coeff; HV rho((size_t)2 * K * D);
+        for (int i = 0; i < 2 * K - 1; ++i) { El cfs; T.get_short_challenge(cfs.data()); rho_coeff.push_back(cfs); }
+        { El one = HR::zero(); one[0] = 1; rho_coeff.push_back(one); }
+        for (int i = 0; i < 2 * K; ++i) { El r = H.crt(rho_coeff[i]); std::memcpy(&rho[(size_t)i * D], r.data(), 8 * D); }
+        P->timings[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        // compute_f_0 = sum_i rho_i f_i (folding.rs:258-268)
+        o.f0 = E.template dalloc<u64>(pitch_of(n) * D);
+        { PtrList pl; for (int i = 0; i < 2 * K; ++i) { pl.p[i] = sb.pieces + (size_t)i * sb.pc_stride; pl.len[i] = n; }
+          if (2 * K > MAX_LIST) throw LfException(LF_ERR_UNSUPPORTED, "2K exceeds MAX_LIST");
+          E.lincomb(pl, sb.pc_pitch, 2 * K, rho.data(), o.f0, pitch_of(n), n, false); }
+        // compute_v0_u0_x0_cm_0 (folding/utils.rs:460-521): host
+        o.lc.r = r0; o.lc.v = rot_lin_combination(rho_coeff, o.theta);
+        const size_t kappa = cnt(lcs[0].cm);
+        o.lc.cm.assign(kappa * D, 0); o.lc.u.assign(t * D, 0); HV x0((P->l + 1) * D, 0);
+        auto axpy = [&](HV& acc, size_t e, const u64* v, const El& r) { El p = HR::mul(HR::load(v), r); for (int l = 0; l < D; ++l) acc[e * D + l] = F::add(acc[e * D + l], p[l]); };
+        for (int i = 0; i < 2 * K; ++i) {
+            El r = HR::load(&rho[(size_t)i * D]);
+            for (size_t e = 0; e < kappa && e < cnt(lcs[i].cm); ++e) axpy(o.lc.cm, e, &lcs[i].cm[e * D], r);
+            for (size_t e = 0; e < t && e < cnt(o.eta[i]); ++e) axpy(o.lc.u, e, &o.eta[i][e * D], r);
+            HV xh = lcs[i].x_w; xh.insert(xh.end(), lcs[i].h.begin(), lcs[i].h.end());
+            for (size_t e = 0; e < P->l + 1 && e < cnt(xh); ++e) axpy(x0, e, &xh[e * D], r);
+        }
+        o.lc.h.assign(x0.end() - D, x0.end()); o.lc.x_w.assign(x0.begin(), x0.end() - D);
+        return o;
+    }
+
+    // ------------------------------------------------------------------ NIFSProver::prove (nifs.rs:48-103)
+    static void put(u64*& p, const HV& v) { std::memcpy(p, v.data(), 8 * v.size()); p += v.size(); }
+    static void put_lcccs(u64* p, const LCCCS& L) { put(p, L.r); put(p, L.v); put(p, L.cm); put(p, L.u); put(p, L.x_w); put(p, L.h); }
+    static LCCCS load_acc(const lf_problem& in, const lf_prover* P) {
+        LCCCS a; auto ld = [&](const u64* p, size_t n) { if (!p && n) throw LfException(LF_ERR_INVALID_ARG, "accumulator field is NULL"); return HV(p, p + n * D); };
+        a.r = ld(in.acc_r, P->s); a.v = ld(in.acc_v, TAU); a.cm = ld(in.acc_cm, P->kappa); a.u = ld(in.acc_u, P->t); a.x_w = ld(in.acc_x_w, P->l); a.h = ld(in.acc_h, 1); return a;
+    }
+    lf_witness* prove(const lf_problem& in, const lf_witness* w_acc, const lf_witness* w_i, Transcript<Rg>& T, u64* out_proof, u64* out_lcccs) {
+        using clk = std::chrono::steady_clock; auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        for (double& x : P->timings) x = 0;
+        auto t_begin = clk::now();
+        sanity_check();
+        const int K = P->K; const size_t n = P->n;
+        LCCCS acc = load_acc(in, P);
+        HV cm_i_cm(in.cm_i_cm, in.cm_i_cm + P->kappa * D), x_ccs(in.cm_i_x_ccs, in.cm_i_x_ccs + P->l * D);
+        // absorb_public_input (nifs.rs:175-197)
+        T.absorb_tag("acc");
+        T.absorb_slice(acc.r.data(), cnt(acc.r)); T.absorb_slice(acc.v.data(), cnt(acc.v)); T.absorb_slice(acc.cm.data(), cnt(acc.cm));
+        T.absorb_slice(acc.u.data(), cnt(acc.u)); T.absorb_slice(acc.x_w.data(), cnt(acc.x_w)); T.absorb(acc.h.data());
+        T.absorb_tag("cm_i"); T.absorb_slice(cm_i_cm.data(), cnt(cm_i_cm)); T.absorb_slice(x_ccs.data(), cnt(x_ccs));
+        auto t0 = clk::now();
+        LinOut lin = linearize(cm_i_cm, x_ccs, w_i, T);
+        E.sync(); auto t1 = clk::now(); P->timings[0] = ms(t0, t1);
+        StepBuffers sb;
+        sb.dig_pitch = (n + 255) / 256 * 256; sb.dig_stride = sb.dig_pitch * D; sb.dig = E.template dalloc<int8_t>((size_t)2 * K * sb.dig_stride);
+        sb.pc_pitch = pitch_of(n); sb.pc_stride = sb.pc_pitch * D; sb.pieces = E.template dalloc<u64>((size_t)2 * K * sb.pc_stride);
+        sb.wc_pitch = pitch_of(w_i->W); sb.wc_stride = sb.wc_pitch * D; sb.wccs = E.template dalloc<u64>((size_t)2 * K * sb.wc_stride);
+        sb.mz = alloc_mz(2 * K);
+        DevVec eq_acc = eq_table(acc.r);
+        DecOut dl = decompose(acc, w_acc, eq_acc, sb, 0, T);
+        DecOut dr = decompose(lin.lc, w_i, lin.eq_r, sb, 1, T);
+        E.sync(); auto t2 = clk::now(); P->timings[1] = ms(t1, t2);
+        std::vector<LCCCS> lcs = dl.lc; lcs.insert(lcs.end(), dr.lc.begin(), dr.lc.end());
+        FoldOut fo = fold(lcs, sb, eq_acc, lin.eq_r, T);
+        lf_witness* w_out = witness_from_f_device(fo.f0);
+        E.dfree(sb.dig); E.dfree(sb.pieces); E.dfree(sb.wccs); free_mz(sb.mz); E.dfree(eq_acc.p); E.dfree(lin.eq_r.p);
+        E.sync(); auto t3 = clk::now(); P->timings[2] = ms(t2, t3);
+        // serialise: lin{msgs,v,u} | dec_acc | dec_new | fold{msgs,theta,eta}
+        u64* p = out_proof;
+        put(p, lin.msgs); put(p, lin.lc.v); put(p, lin.lc.u);
+        for (const DecOut* dd : {&dl, &dr}) for (int k = 0; k < K; ++k) { put(p, dd->x_s[k]); put(p, dd->y_s[k]); put(p, dd->u_s[k]); put(p, dd->v_s[k]); }
+        put(p, fo.msgs); for (auto& v : fo.theta) put(p, v); for (auto& v : fo.eta) put(p, v);
+        put_lcccs(out_lcccs, fo.lc);
+        P->timings[4] = ms(t_begin, clk::now());
+        return w_out;
+    }
+};
+
+}  // namespace lf

@@ -1,0 +1,124 @@
+// Device-resident ring sumcheck prover state: MLSumcheck / IPForMLSumcheck of the reference
+// (crates/latticefold/src/utils/sumcheck.rs:53-80, utils/sumcheck/prover.rs:19-162).  The Fiat-Shamir transcript stays on
+// the host: one round = evaluate on the device -> (deg+1) ring elements to the host -> caller hashes -> challenge comes
+// back and is applied (fix_variables) before the next evaluation.
+#pragma once
+#include "engine.cuh"
+
+struct lf_sumcheck {
+    lf_ctx* ctx = nullptr;
+    int nv = 0, deg = 0, round = 0, kind = 0;
+    // table groups, each [count][D planes][pitch]; ping-pong buffers (cur -> nxt on every applied challenge)
+    struct Group { lf::u64 *cur = nullptr, *nxt = nullptr; size_t pitch = 0, stride = 0, nxt_pitch = 0, nxt_stride = 0; int count = 0; bool cur_owned = true; };
+    Group dense;          // PRODUCTS/LIN: all MLEs.  FOLD: the first five
+    Group fh;             // FOLD: the 2K*tau f-hat tables (slot-field valued); empty while still in digit form
+    const int8_t* dig = nullptr; size_t dig_pitch = 0, dig_stride = 0;   // FOLD round 1 in the prover: borrowed int8 digits
+    int n_f = 0;
+    lf::u64* d_mu_pow = nullptr;      // n_f x TAU
+    lf::u64* d_coef = nullptr;        // PRODUCTS/LIN term coefficients, n_terms x D
+    lf::ScGenericArgs gen;            // term structure
+    size_t len = 0;                   // current table length (2^(nv - applied challenges))
+    int applied = 0;
+};
+
+namespace lf {
+
+template <class Rg> struct SumcheckDriver {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef HostRing<Rg> HR;
+    static constexpr int D = Rg::D, S = Rg::S, TAU = Rg::TAU;
+    Engine<Rg> E; lf_sumcheck* sc;
+    SumcheckDriver(lf_ctx* c, lf_sumcheck* s) : E(c), sc(s) {}
+
+    static void alloc_group(Engine<Rg>& E, lf_sumcheck::Group& g, int count, size_t len) {
+        g.count = count; g.pitch = pitch_of(len); g.stride = g.pitch * D; g.cur = E.template dalloc<u64>((size_t)count * g.stride); g.cur_owned = true;
+    }
+    void free_all() {
+        for (lf_sumcheck::Group* g : {&sc->dense, &sc->fh}) { if (g->cur_owned) E.dfree(g->cur); E.dfree(g->nxt); g->cur = g->nxt = nullptr; }
+        E.dfree(sc->d_mu_pow); E.dfree(sc->d_coef); sc->d_mu_pow = sc->d_coef = nullptr;
+    }
+    // mu (n_mu ring elements, slot-constant) -> mu_k^{d+1} for d < tau as slot-field elements (folding/utils.rs:293-322)
+    void set_mu(const u64* mu_host, int n_mu) {
+        sc->n_f = n_mu * TAU; if (sc->n_f > MAX_MU) throw LfException(LF_ERR_UNSUPPORTED, "FOLD: 2K*tau exceeds MAX_MU");
+        std::vector<u64> pw((size_t)sc->n_f * TAU);
+        for (int k = 0; k < n_mu; ++k) {
+            const u64* m = mu_host + (size_t)k * D;     // slot 0 of a slot-constant element
+            for (int s = 1; s < S; ++s) if (std::memcmp(m, m + s * TAU, 8 * TAU) != 0) throw LfException(LF_ERR_UNSUPPORTED, "FOLD: mu must be slot-constant (a sumcheck challenge)");
+            u64 acc[TAU]; std::memcpy(acc, m, 8 * TAU);
+            for (int d = 0; d < TAU; ++d) { std::memcpy(&pw[((size_t)k * TAU + d) * TAU], acc, 8 * TAU); SF::mul(acc, acc, m); }
+        }
+        sc->d_mu_pow = E.template dalloc<u64>(pw.size());
+        LF_CUDA(cudaMemcpyAsync(sc->d_mu_pow, pw.data(), pw.size() * 8, cudaMemcpyHostToDevice, E.st())); E.sync();
+    }
+
+    // prove_round's evaluation half: out_host = (deg+1) x D limbs
+    void evaluate(u64* out_host) {
+        if (sc->applied != sc->round) throw LfException(LF_ERR_SUMCHECK_MISUSE, "verifier message is empty");
+        if (sc->round >= sc->nv) throw LfException(LF_ERR_SUMCHECK_MISUSE, "Prover is not active");
+        const size_t n_pairs = sc->len / 2; const int ne = sc->deg + 1;
+        unsigned nblk; u64* partial;
+        if (sc->kind == LF_COMB_FOLD) {
+            nblk = (unsigned)((n_pairs + 127) / 128); partial = E.partial_dev((size_t)nblk * 5 * D);
+            FoldScArgs a; a.dense = sc->dense.cur; a.dense_pitch = sc->dense.pitch; a.dense_stride = sc->dense.stride; a.mu_pow = sc->d_mu_pow; a.n_f = sc->n_f;
+            a.n_pairs = n_pairs; a.partial = partial; a.dig = sc->dig; a.dig_pitch = sc->dig_pitch; a.dig_stride = sc->dig_stride;
+            a.fh = sc->fh.cur; a.fh_pitch = sc->fh.pitch; a.fh_stride = sc->fh.stride;
+            if (sc->dig && sc->applied == 0) E.launch("k_fold_sc_round1", [&] { k_fold_sc_round1<Rg><<<dim3(nblk, S), 128, 0, E.st()>>>(a); });
+            else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(nblk, S), 128, 0, E.st()>>>(a); });
+        } else {
+            nblk = (unsigned)std::min<size_t>((n_pairs + 127) / 128, 148 * 8); partial = E.partial_dev((size_t)nblk * ne * D);
+            ScGenericArgs a = sc->gen; a.pitch = sc->dense.pitch; a.n_pairs = n_pairs; a.partial = partial; a.coef = sc->d_coef;
+            for (int k = 0; k < a.n_mles; ++k) a.mle[k] = sc->dense.cur + (size_t)k * sc->dense.stride;
+            dim3 g(nblk, S);
+            for (int k = a.n_mles; k < SC_MAX_MLES; ++k) a.mle[k] = a.mle[0];   // padding tables are loaded but never referenced by a term
+            E.launch("k_sc_generic", [&] {
+                if (a.n_mles <= 2) k_sc_generic<Rg, 2><<<g, 128, 0, E.st()>>>(a);
+                else if (a.n_mles <= 4) k_sc_generic<Rg, 4><<<g, 128, 0, E.st()>>>(a);
+                else k_sc_generic<Rg, 8><<<g, 128, 0, E.st()>>>(a);
+            });
+        }
+        u64* d_out = E.small_dev((size_t)ne * D);
+        E.launch("k_reduce_partials", [&] { k_reduce_partials<F><<<Engine<Rg>::blocks_for((size_t)ne * D, 128), 128, 0, E.st()>>>(partial, (int)nblk, ne * D, d_out); });
+        E.download_words(d_out, (size_t)ne * D, out_host);
+        sc->round += 1;
+    }
+    void fold_group(lf_sumcheck::Group& g, const u64* r_sf, size_t n_out) {
+        if (!g.count || !g.cur) return;
+        const size_t np = pitch_of(n_out);
+        u64* out = E.template dalloc<u64>((size_t)g.count * np * D);
+        FoldArgs a; a.in = g.cur; a.out = out; a.in_pitch = g.pitch; a.out_pitch = np; a.in_stride = g.stride; a.out_stride = np * D; a.n_out = n_out;
+        for (int l = 0; l < TAU; ++l) a.r[l] = r_sf[l];
+        E.launch("k_fold", [&] { k_fold<Rg><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, g.count), 128, 0, E.st()>>>(a); });
+        if (g.cur_owned) E.dfree(g.cur);
+        g.cur = out; g.cur_owned = true; g.pitch = np; g.stride = np * D;
+    }
+    // fix_variables with the verifier's challenge (prover.rs:61-72)
+    void apply_challenge(const u64* r_sf) {
+        if (sc->applied >= sc->round) throw LfException(LF_ERR_SUMCHECK_MISUSE, "first round should be prover first.");
+        const size_t n_out = sc->len / 2;
+        fold_group(sc->dense, r_sf, n_out);
+        if (sc->kind == LF_COMB_FOLD) {
+            if (sc->dig && sc->applied == 0) {
+                alloc_group(E, sc->fh, sc->n_f, n_out);
+                FoldArgs a; for (int l = 0; l < TAU; ++l) a.r[l] = r_sf[l];
+                E.launch("k_fold_digits", [&] { k_fold_digits<Rg><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, sc->n_f), 128, 0, E.st()>>>(sc->dig, sc->dig_pitch, sc->dig_stride, sc->n_f, sc->fh.cur, sc->fh.pitch, sc->fh.stride, n_out, a); });
+            } else fold_group(sc->fh, r_sf, n_out);
+        }
+        sc->len = n_out; sc->applied += 1;
+    }
+    // after the last challenge every table has one entry: mle_k(r).  out: (dense.count + n_f) x D limbs on the host
+    void final_values(u64* out_host) {
+        if (sc->len != 1) throw LfException(LF_ERR_SUMCHECK_MISUSE, "sumcheck not finished");
+        const int total = sc->dense.count + (sc->kind == LF_COMB_FOLD ? sc->n_f : 0);
+        std::vector<u64> tmp;
+        auto grab = [&](const lf_sumcheck::Group& g, u64* dst) {
+            if (!g.count) return;
+            tmp.resize((size_t)g.count * g.stride);
+            E.download_words(g.cur, tmp.size(), tmp.data());
+            for (int k = 0; k < g.count; ++k) for (int l = 0; l < D; ++l) dst[(size_t)k * D + l] = tmp[(size_t)k * g.stride + (size_t)l * g.pitch];
+        };
+        grab(sc->dense, out_host);
+        if (sc->kind == LF_COMB_FOLD) grab(sc->fh, out_host + (size_t)sc->dense.count * D);
+        (void)total;
+    }
+};
+
+}  // namespace lf
