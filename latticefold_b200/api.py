@@ -233,7 +233,7 @@ class DeviceVec:
 
     def __del__(self):
         try:
-            if self.h:
+            if self.h and self.ctx.h:
                 self.ctx.L.lf_vec_free(self.ctx.h, self.h)
         except Exception:
             pass
@@ -361,7 +361,8 @@ class AjtaiCommitmentScheme:
 
     def __del__(self):
         try:
-            self.ctx.L.lf_ajtai_free(self.ctx.h, self.h)
+            if self.ctx.h:
+                self.ctx.L.lf_ajtai_free(self.ctx.h, self.h)
         except Exception:
             pass
 
@@ -376,7 +377,8 @@ class SparseMatrix:
 
     def __del__(self):
         try:
-            self.ctx.L.lf_sparse_free(self.ctx.h, self.h)
+            if self.ctx.h:
+                self.ctx.L.lf_sparse_free(self.ctx.h, self.h)
         except Exception:
             pass
 

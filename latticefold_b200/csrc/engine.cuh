@@ -138,7 +138,7 @@ template <class Rg> struct Engine {
     // ---------------------------------------------------------------- batched dot products (commit, MLE evaluation)
     // result: nrows x ncols x D limbs on the device (d_out)
     void dot(const u64* X, size_t x_row_stride, size_t x_pitch, int nrows, const size_t* x_len_dev,
-             const PtrList& Y, size_t y_pitch, int ncols, size_t n, u64* d_out) {
+             const PtrList& Y, size_t y_pitch, int ncols, size_t n, u64* d_out, const char* name = "k_dot") {
         if (nrows == 0 || ncols == 0) return;
         if (ncols > MAX_LIST) throw LfException(LF_ERR_INVALID_ARG, "dot: too many columns in one launch");
         DotArgs a; a.X = X; a.x_row_stride = x_row_stride; a.x_pitch = x_pitch; a.nrows = nrows; a.Y = Y; a.y_pitch = y_pitch; a.ncols = ncols;
@@ -146,7 +146,7 @@ template <class Rg> struct Engine {
         const unsigned xt = (unsigned)std::max<size_t>(1, (n + a.x_per_block - 1) / a.x_per_block);
         const size_t nout = (size_t)nrows * ncols * D;
         a.partial = partial_dev((size_t)xt * nout);
-        launch("k_dot", [&] {
+        launch(name, [&] {
             if (ncols >= 3) { constexpr int RT = 1, CT = 4; dim3 g((unsigned)(((nrows + RT - 1) / RT) * ((ncols + CT - 1) / CT)), xt, S); k_dot<Rg, RT, CT><<<g, 128, 0, st()>>>(a); }
             else if (ncols == 2) { constexpr int RT = 2, CT = 2; dim3 g((unsigned)(((nrows + RT - 1) / RT) * ((ncols + CT - 1) / CT)), xt, S); k_dot<Rg, RT, CT><<<g, 128, 0, st()>>>(a); }
             else { constexpr int RT = 4, CT = 1; dim3 g((unsigned)((nrows + RT - 1) / RT), xt, S); k_dot<Rg, RT, CT><<<g, 128, 0, st()>>>(a); }

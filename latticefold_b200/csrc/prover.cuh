@@ -87,7 +87,7 @@ template <class Rg> struct Prover {
     HV eval_mz(const MzSet& z, int row0, int rows, const DevVec& eq) {
         PtrList Y; Y.p[0] = eq.p; Y.len[0] = eq.n;
         u64* d_out = E.small_dev((size_t)rows * D);
-        E.dot(z.p + (size_t)row0 * z.stride, z.stride, z.pitch, rows, z.d_len + row0, Y, eq.pitch, 1, z.pitch, d_out);
+        E.dot(z.p + (size_t)row0 * z.stride, z.stride, z.pitch, rows, z.d_len + row0, Y, eq.pitch, 1, z.pitch, d_out, "k_dot_eval");
         HV o((size_t)rows * D); E.download_words(d_out, o.size(), o.data()); return o;
     }
 
@@ -198,7 +198,7 @@ template <class Rg> struct Prover {
         if (K > 1) {
             PtrList Y; for (int k = 1; k < K; ++k) { Y.p[k - 1] = pieces + (size_t)k * sb.pc_stride; Y.len[k - 1] = n; }
             u64* d_y = E.small_dev(kappa * (K - 1) * D);
-            E.dot(P->A->p, P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y);
+            E.dot(P->A->p, P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y, "k_dot_commit");
             HV all(kappa * (K - 1) * D); E.download_words(d_y, all.size(), all.data());
             for (int k = 1; k < K; ++k) for (size_t i = 0; i < kappa; ++i) std::memcpy(&o.y_s[k][i * D], &all[(i * (K - 1) + (k - 1)) * D], 8 * D);
         }
@@ -347,7 +347,9 @@ template <class Rg> struct Prover {
         LinOut lin = linearize(cm_i_cm, x_ccs, w_i, T);
         E.sync(); auto t1 = clk::now(); P->timings[0] = ms(t0, t1);
         StepBuffers sb;
-        sb.dig_pitch = (n + 255) / 256 * 256; sb.dig_stride = sb.dig_pitch * D; sb.dig = E.template dalloc<int8_t>((size_t)2 * K * sb.dig_stride);
+        sb.dig_pitch = (std::max(n, P->m) + 255) / 256 * 256;   // the sumcheck walks all 2^s entries
+        sb.dig_stride = sb.dig_pitch * D; sb.dig = E.template dalloc<int8_t>((size_t)2 * K * sb.dig_stride);
+        LF_CUDA(cudaMemsetAsync(sb.dig, 0, (size_t)2 * K * sb.dig_stride, E.st()));   // f-hat tables are zero on [n, 2^s)
         sb.pc_pitch = pitch_of(n); sb.pc_stride = sb.pc_pitch * D; sb.pieces = E.template dalloc<u64>((size_t)2 * K * sb.pc_stride);
         sb.wc_pitch = pitch_of(w_i->W); sb.wc_stride = sb.wc_pitch * D; sb.wccs = E.template dalloc<u64>((size_t)2 * K * sb.wc_stride);
         sb.mz = alloc_mz(2 * K);
