@@ -198,6 +198,8 @@ lf_status lf_nifs_prove_resident(lf_prover* p, const lf_problem* in, const lf_wi
 /* per-phase device/host timings of the last step in milliseconds: [0] linearization [1] decomposition x2 [2] folding
  * [3] host transcript [4] total wall                                                                               */
 lf_status lf_prover_last_timings(const lf_prover* p, double* out5);
+/* diagnostic: with LF_TIMING_DETAIL=1 in the environment the step synchronises at phase marks; one line "mark ms" each */
+lf_status lf_prover_timing_detail(const lf_prover* p, char* buf, size_t buf_len);
 
 #ifdef __cplusplus
 }

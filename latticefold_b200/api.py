@@ -30,7 +30,7 @@ lf_sumcheck_finish lf_sumcheck_free lf_transcript_create lf_transcript_clone lf_
 lf_transcript_absorb_base lf_transcript_absorb_tag lf_transcript_get_challenge lf_transcript_get_short_challenge
 lf_transcript_permutations lf_rot_lin_combination lf_prover_create lf_prover_free lf_proof_words lf_lcccs_words
 lf_witness_f_from_w_ccs lf_linearize lf_nifs_prove lf_prover_upload_witness lf_witness_free lf_witness_download_f
-lf_nifs_prove_resident lf_prover_last_timings""".split()
+lf_nifs_prove_resident lf_prover_last_timings lf_prover_timing_detail""".split()
 
 
 class LfError(RuntimeError):
@@ -163,6 +163,7 @@ def lib():
     L.lf_witness_download_f.argtypes = [vp, vp, u64p]
     L.lf_nifs_prove_resident.argtypes = [vp, C.POINTER(Problem), vp, vp, vp, u64p, u64p, C.POINTER(vp)]
     L.lf_prover_last_timings.argtypes = [vp, C.POINTER(C.c_double)]
+    L.lf_prover_timing_detail.argtypes = [vp, C.c_char_p, C.c_size_t]
     _lib = L
     return L
 
@@ -465,6 +466,10 @@ class NIFSProver:
         proof = np.empty(self.proof_words, dtype=np.uint64); lc = np.empty(self.lcccs_words, dtype=np.uint64); w = vp()
         self.ctx.check(self.ctx.L.lf_nifs_prove_resident(self.h, C.byref(P), w_acc, w_i, transcript.h, ptr(proof), ptr(lc), C.byref(w) if keep_witness else None))
         return (proof, lc, w) if keep_witness else (proof, lc)
+
+    def timing_detail(self):
+        buf = C.create_string_buffer(1 << 14); self.ctx.L.lf_prover_timing_detail(self.h, buf, len(buf))
+        return [(l.split()[0], float(l.split()[1])) for l in buf.value.decode().splitlines()]
 
     def timings(self):
         t = (C.c_double * 5)(); self.ctx.L.lf_prover_last_timings(self.h, t)

@@ -7,6 +7,7 @@
 #include <string>
 #include <memory>
 #include <chrono>
+#include <cstdlib>
 
 namespace lf {
 
@@ -142,14 +143,23 @@ template <class Rg> struct Engine {
         if (nrows == 0 || ncols == 0) return;
         if (ncols > MAX_LIST) throw LfException(LF_ERR_INVALID_ARG, "dot: too many columns in one launch");
         DotArgs a; a.X = X; a.x_row_stride = x_row_stride; a.x_pitch = x_pitch; a.nrows = nrows; a.Y = Y; a.y_pitch = y_pitch; a.ncols = ncols;
-        a.x_len = x_len_dev; a.n = n; a.x_per_block = 128 * 8;
-        const unsigned xt = (unsigned)std::max<size_t>(1, (n + a.x_per_block - 1) / a.x_per_block);
+        a.x_len = x_len_dev; a.n = n;
+        // x tile: long enough to amortise the per-warp reduction, short enough to fill 148 SMs
+        const int ct = ncols >= 3 ? 4 : ncols;
+        const int units = nrows * ((ncols + ct - 1) / ct);
+        int wpb = 1; { int best = 1 << 30; for (int w = 16; w >= 4; --w) { int waste = (units + w - 1) / w * w - units; if (waste < best) { best = waste; wpb = w; } } if (units < 4) wpb = units; }
+        const int groups = (units + wpb - 1) / wpb;
+        size_t xpb = 128 * 32;
+        while (xpb > 256 && (size_t)groups * S * ((n + xpb - 1) / xpb) < 148 * 4) xpb /= 2;
+        a.x_per_block = (int)xpb;
+        const unsigned xt = (unsigned)std::max<size_t>(1, (n + xpb - 1) / xpb);
         const size_t nout = (size_t)nrows * ncols * D;
         a.partial = partial_dev((size_t)xt * nout);
         launch(name, [&] {
-            if (ncols >= 3) { constexpr int RT = 1, CT = 4; dim3 g((unsigned)(((nrows + RT - 1) / RT) * ((ncols + CT - 1) / CT)), xt, S); k_dot<Rg, RT, CT><<<g, 128, 0, st()>>>(a); }
-            else if (ncols == 2) { constexpr int RT = 2, CT = 2; dim3 g((unsigned)(((nrows + RT - 1) / RT) * ((ncols + CT - 1) / CT)), xt, S); k_dot<Rg, RT, CT><<<g, 128, 0, st()>>>(a); }
-            else { constexpr int RT = 4, CT = 1; dim3 g((unsigned)((nrows + RT - 1) / RT), xt, S); k_dot<Rg, RT, CT><<<g, 128, 0, st()>>>(a); }
+            dim3 g((unsigned)groups, xt, S);
+            if (ct == 4) k_dot<Rg, 4><<<g, wpb * 32, 0, st()>>>(a);
+            else if (ct == 2) k_dot<Rg, 2><<<g, wpb * 32, 0, st()>>>(a);
+            else k_dot<Rg, 1><<<g, wpb * 32, 0, st()>>>(a);
         });
         launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(a.partial, (int)xt, (int)nout, d_out); });
     }

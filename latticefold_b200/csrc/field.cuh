@@ -22,37 +22,74 @@ typedef uint64_t u64;
 typedef uint32_t u32;
 typedef unsigned __int128 u128;
 
-// 64 x 64 -> 128
+// 64 x 64 -> 128.  On the device the product is written on 32-bit halves with explicit carry chains: ptxas fuses each
+// mad.lo.cc / madc.hi.cc pair into one IMAD.WIDE.U32 with a carry predicate (4 IMAD.WIDE + 2 IADD3.X in SASS), whereas
+// `a * b` and `__umul64hi(a, b)` are lowered separately and recompute the partial products (~2x the instructions).
 LF_HD void mul_wide(u64 a, u64 b, u64& lo, u64& hi) {
 #if defined(__CUDA_ARCH__)
-    lo = a * b; hi = __umul64hi(a, b);
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), r0, r1, r2, r3;
+    asm("mul.lo.u32 %0, %4, %6;\n\t"
+        "mul.hi.u32 %1, %4, %6;\n\t"
+        "mul.lo.u32 %2, %5, %7;\n\t"
+        "mul.hi.u32 %3, %5, %7;\n\t"
+        "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
+        "madc.hi.cc.u32 %2, %4, %7, %2;\n\t"
+        "addc.u32 %3, %3, 0;\n\t"
+        "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
+        "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
+        "addc.u32 %3, %3, 0;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    lo = ((u64)r1 << 32) | r0; hi = ((u64)r3 << 32) | r2;
 #else
     u128 x = (u128)a * b; lo = (u64)x; hi = (u64)(x >> 64);
 #endif
 }
 
-// 192-bit accumulator for lazily reduced sums of 128-bit products (up to 2^64 terms)
+// Accumulator for lazily reduced sums of 128-bit products.  Device layout: the even-aligned partial products
+// (a0 b0 at bit 0, a1 b1 at bit 64) and the odd-aligned ones (a0 b1 + a1 b0 at bit 32) are summed in separate word
+// chains, so one 64 x 64 multiply-accumulate is 4 IMAD.WIDE.U32 + 2-3 carry adds and no chain depends on another.
+// Capacity: 2^31 products.  words() returns the 192-bit value (w2 < 2^32).
 struct Acc192 {
-    u64 w0, w1, w2;
-    LF_HD void clear() { w0 = w1 = w2 = 0; }
+#if defined(__CUDA_ARCH__)
+    u32 e0, e1, e2, e3, e4, o1, o2, o3;
+    LF_HD void clear() { e0 = e1 = e2 = e3 = e4 = o1 = o2 = o3 = 0; }
     LF_HD void mac(u64 a, u64 b) {
-#if defined(__CUDA_ARCH__)
-        asm("mad.lo.cc.u64 %0, %3, %4, %0;\n\t"
-            "madc.hi.cc.u64 %1, %3, %4, %1;\n\t"
-            "addc.u64 %2, %2, 0;"
-            : "+l"(w0), "+l"(w1), "+l"(w2) : "l"(a), "l"(b));
-#else
-        u128 x = (u128)a * b; u128 s = (u128)w0 + (u64)x; w0 = (u64)s;
-        s = (u128)w1 + (u64)(x >> 64) + (u64)(s >> 64); w1 = (u64)s; w2 += (u64)(s >> 64);
-#endif
+        u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+        asm("mad.lo.cc.u32 %0, %8, %10, %0;\n\t"
+            "madc.hi.cc.u32 %1, %8, %10, %1;\n\t"
+            "madc.lo.cc.u32 %2, %9, %11, %2;\n\t"
+            "madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+            "addc.u32 %4, %4, 0;\n\t"
+            "mad.lo.cc.u32 %5, %8, %11, %5;\n\t"
+            "madc.hi.cc.u32 %6, %8, %11, %6;\n\t"
+            "addc.u32 %7, %7, 0;\n\t"
+            "mad.lo.cc.u32 %5, %9, %10, %5;\n\t"
+            "madc.hi.cc.u32 %6, %9, %10, %6;\n\t"
+            "addc.u32 %7, %7, 0;"
+            : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(o1), "+r"(o2), "+r"(o3)
+            : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     }
-    LF_HD void add(u64 a) {   // += a (64-bit)
-#if defined(__CUDA_ARCH__)
-        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, 0;\n\taddc.u64 %2, %2, 0;" : "+l"(w0), "+l"(w1), "+l"(w2) : "l"(a));
-#else
-        u128 s = (u128)w0 + a; w0 = (u64)s; s = (u128)w1 + (u64)(s >> 64); w1 = (u64)s; w2 += (u64)(s >> 64);
-#endif
+    LF_HD void add(u64 a) {
+        u32 a0 = (u32)a, a1 = (u32)(a >> 32);
+        asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\taddc.u32 %4, %4, 0;"
+            : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4) : "r"(a0), "r"(a1));
     }
+    LF_HD void words(u64& w0, u64& w1, u32& w2) const {
+        u32 r0 = e0, r1, r2, r3, r4;
+        asm("add.cc.u32 %0, %4, %8;\n\taddc.cc.u32 %1, %5, %9;\n\taddc.cc.u32 %2, %6, %10;\n\taddc.u32 %3, %7, 0;"
+            : "=&r"(r1), "=&r"(r2), "=&r"(r3), "=&r"(r4) : "r"(e1), "r"(e2), "r"(e3), "r"(e4), "r"(o1), "r"(o2), "r"(o3));
+        w0 = ((u64)r1 << 32) | r0; w1 = ((u64)r3 << 32) | r2; w2 = r4;
+    }
+#else
+    u64 h0, h1, h2;
+    LF_HD void clear() { h0 = h1 = h2 = 0; }
+    LF_HD void mac(u64 a, u64 b) {
+        u128 x = (u128)a * b; u128 s = (u128)h0 + (u64)x; h0 = (u64)s;
+        s = (u128)h1 + (u64)(x >> 64) + (u64)(s >> 64); h1 = (u64)s; h2 += (u64)(s >> 64);
+    }
+    LF_HD void add(u64 a) { u128 s = (u128)h0 + a; h0 = (u64)s; s = (u128)h1 + (u64)(s >> 64); h1 = (u64)s; h2 += (u64)(s >> 64); }
+    LF_HD void words(u64& w0, u64& w1, u32& w2) const { w0 = h0; w1 = h1; w2 = (u32)h2; }
+#endif
 };
 
 struct Goldilocks {
@@ -60,25 +97,48 @@ struct Goldilocks {
     static constexpr u64 EPS = 0xFFFFFFFFULL;  // 2^64 mod p
     static constexpr int NU_SHIFT = 40;        // nu = 2^40 (a primitive 24th root of unity)
 
-    static LF_HD u64 add(u64 a, u64 b) { u64 s = a + b; if (s < a || s >= P) s -= P; return s; }
-    static LF_HD u64 sub(u64 a, u64 b) { u64 d = a - b; if (a < b) d += P; return d; }
+    // host builds use mask arithmetic: the comparisons are data dependent coin flips and a mispredicted branch costs more
+    // than the whole reduction (the Poseidon transcript runs ~10^7 of these per prover step)
+    static LF_HD u64 add(u64 a, u64 b) {
+        u64 s = a + b;
+#if defined(__CUDA_ARCH__)
+        if (s < a || s >= P) s -= P;
+#else
+        s -= (0 - (u64)((s < a) | (s >= P))) & P;
+#endif
+        return s;
+    }
+    static LF_HD u64 sub(u64 a, u64 b) {
+        u64 d = a - b;
+#if defined(__CUDA_ARCH__)
+        if (a < b) d += P;
+#else
+        d += (0 - (u64)(a < b)) & P;
+#endif
+        return d;
+    }
     static LF_HD u64 neg(u64 a) { return a ? P - a : 0; }
     // (hi:lo) mod p, canonical.  2^64 = EPS, 2^96 = -1.
     static LF_HD u64 reduce128(u64 lo, u64 hi) {
         u64 hh = hi >> 32, hl = hi & EPS;
-        u64 t0 = lo - hh; if (lo < hh) t0 -= EPS;      // wrapped by 2^64 = EPS too much
         u64 t1 = (hl << 32) - hl;                      // hl * EPS < 2^64
+#if defined(__CUDA_ARCH__)
+        u64 t0 = lo - hh; if (lo < hh) t0 -= EPS;      // wrapped by 2^64 = EPS too much
         u64 r = t0 + t1; if (r < t1) r += EPS;         // wrapped: add 2^64 mod p
         if (r >= P) r -= P;
+#else
+        u64 t0 = lo - hh; t0 -= (0 - (u64)(lo < hh)) & EPS;
+        u64 r = t0 + t1; r += (0 - (u64)(r < t1)) & EPS;
+        r -= (0 - (u64)(r >= P)) & P;
+#endif
         return r;
     }
     static LF_HD u64 mul(u64 a, u64 b) { u64 lo, hi; mul_wide(a, b, lo, hi); return reduce128(lo, hi); }
     static LF_HD u64 sqr(u64 a) { return mul(a, a); }
-    // (w2:w1:w0) mod p; 2^128 = -2^32
+    // (w2:w1:w0) mod p with w2 < 2^32; 2^128 = -2^32 and w2 * 2^32 < p is already canonical
     static LF_HD u64 reduce192(const Acc192& a) {
-        u64 r = reduce128(a.w0, a.w1);
-        u64 t = reduce128(a.w2 << 32, a.w2 >> 32);
-        return sub(r, t);
+        u64 w0, w1; u32 w2; a.words(w0, w1, w2);
+        return sub(reduce128(w0, w1), (u64)w2 << 32);
     }
     static LF_HD u64 mul_nu(u64 a) { return reduce128(a << NU_SHIFT, a >> (64 - NU_SHIFT)); }
     static LF_HD u64 from_i64(int64_t v) { return v >= 0 ? (u64)v : P - (u64)(-v); }   // |v| < p

@@ -154,8 +154,12 @@ template <class Rg> __global__ void k_fhat(const u64* __restrict__ in, size_t in
 // out[r][c] = sum_x X_r[x] (.) Y_c[x]   (slot-wise product), the shape of both
 //   AjtaiCommitmentScheme::commit  (rows X_r = matrix rows, Y_c = the K-1 witness pieces; commitment_scheme.rs:45-51), and
 //   evaluate_mles                  (rows X_r = MLE tables, Y_0 = eq(., r) table; mle_helpers.rs:65-88).
-// grid = (row tiles * col tiles  [fastest: concurrent blocks share the same x tile in L2], x tiles, slots).
-// A thread owns one x per iteration, RT x CT slot-field accumulators kept as lazily reduced 192-bit sums.
+// Work unit = (row r, tile of CT columns); one WARP per unit, lanes over x.  The warps of a block take consecutive units
+// (column tile fastest) over the SAME x range, so a row is fetched from L2 once per block and re-served from L1 to the
+// warps that share it, and likewise for the column vectors.  grid = (unit groups, x tiles, slots); blocks that share an
+// x tile are adjacent in launch order, which keeps HBM traffic at one pass over X and Y (ncu: 2.1 GB for the 2.06 GB
+// algorithmic at kappa=26, n=2^18, 15 pieces).  Accumulators are lazily reduced (Acc192): the inner loop is
+// 9 * CT 64-bit multiply-accumulates per x with no modular reduction and no branch.
 struct DotArgs {
     const u64* X; size_t x_row_stride, x_pitch; int nrows;    // rows: X + r * x_row_stride
     PtrList Y; size_t y_pitch; int ncols;                     // columns: separate vectors, len[] = effective length
@@ -163,63 +167,67 @@ struct DotArgs {
     size_t n; int x_per_block;
     u64* partial;                                             // [x tile][row][col][D]
 };
-template <class Rg, int RT, int CT> __global__ void __launch_bounds__(128)
+template <class Rg, int CT> __global__ void __launch_bounds__(512)
 k_dot(const DotArgs a) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
-    __shared__ u64 red[RT * CT * TAU * 32];
-    const int col_tiles = (a.ncols + CT - 1) / CT;
-    const int rt = blockIdx.x / col_tiles, ct = blockIdx.x % col_tiles, slot = blockIdx.z;
-    const int r0 = rt * RT, c0 = ct * CT;
-    Acc192 acc[RT][CT][TAU];
+    const int col_tiles = (a.ncols + CT - 1) / CT, n_units = a.nrows * col_tiles;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int unit = blockIdx.x * wpb + warp, slot = blockIdx.z;
+    if (unit >= n_units) return;
+    const int row = unit / col_tiles, c0 = (unit % col_tiles) * CT;
+    const size_t x_begin = (size_t)blockIdx.y * a.x_per_block, x_stop = min(a.n, x_begin + a.x_per_block);
+    const size_t rlen = a.x_len ? a.x_len[row] : a.n;
+    const u64* xp = a.X + (size_t)row * a.x_row_stride + (size_t)(slot * TAU) * a.x_pitch;
+    const u64* yp[CT]; size_t ylen[CT];
 #pragma unroll
-    for (int i = 0; i < RT; ++i)
+    for (int j = 0; j < CT; ++j) { const int c = min(c0 + j, a.ncols - 1); yp[j] = a.Y.p[c] + (size_t)(slot * TAU) * a.y_pitch; ylen[j] = (c0 + j < a.ncols) ? a.Y.len[c] : 0; }
+    Acc192 acc[CT][TAU];
+#pragma unroll
+    for (int j = 0; j < CT; ++j)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) acc[j][l].clear();
+    // everything below min(lengths) needs no per-element bounds test
+    size_t safe = min(x_stop, rlen);
+#pragma unroll
+    for (int j = 0; j < CT; ++j) if (c0 + j < a.ncols) safe = min(safe, ylen[j]);
+    size_t x = x_begin + lane;
+#pragma unroll 2
+    for (; x < safe; x += 32) {
+        u64 xv[TAU], yv[CT][TAU];
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) xv[l] = __ldg(xp + (size_t)l * a.x_pitch + x);
 #pragma unroll
         for (int j = 0; j < CT; ++j)
 #pragma unroll
-            for (int l = 0; l < TAU; ++l) acc[i][j][l].clear();
-    const size_t x_begin = (size_t)blockIdx.y * a.x_per_block, x_end = min(a.n, x_begin + a.x_per_block);
-    size_t rlen[RT];
+            for (int l = 0; l < TAU; ++l) yv[j][l] = __ldg(yp[j] + (size_t)l * a.y_pitch + x);
+        const typename SF::Prepped pr = SF::prep(xv);
 #pragma unroll
-    for (int i = 0; i < RT; ++i) rlen[i] = (r0 + i < a.nrows) ? (a.x_len ? a.x_len[r0 + i] : a.n) : 0;
-    for (size_t x = x_begin + threadIdx.x; x < x_end; x += blockDim.x) {
-        typename SF::Prepped xp[RT]; bool xv[RT];
+        for (int j = 0; j < CT; ++j) SF::mac(acc[j], yv[j], pr);
+    }
+    for (; x < x_stop; x += 32) {            // ragged tail: operands past their effective length are zero
+        if (x >= rlen) break;
+        u64 xv[TAU];
 #pragma unroll
-        for (int i = 0; i < RT; ++i) {
-            xv[i] = x < rlen[i];
-            u64 v[TAU];
-#pragma unroll
-            for (int l = 0; l < TAU; ++l) v[l] = xv[i] ? a.X[(size_t)(r0 + i) * a.x_row_stride + (size_t)(slot * TAU + l) * a.x_pitch + x] : 0;
-            xp[i] = SF::prep(v);
-        }
+        for (int l = 0; l < TAU; ++l) xv[l] = xp[(size_t)l * a.x_pitch + x];
+        const typename SF::Prepped pr = SF::prep(xv);
 #pragma unroll
         for (int j = 0; j < CT; ++j) {
-            if (c0 + j >= a.ncols || x >= a.Y.len[c0 + j]) continue;
-            u64 y[TAU];
+            if (x >= ylen[j]) continue;
+            u64 yv[TAU];
 #pragma unroll
-            for (int l = 0; l < TAU; ++l) y[l] = a.Y.p[c0 + j][(size_t)(slot * TAU + l) * a.y_pitch + x];
-#pragma unroll
-            for (int i = 0; i < RT; ++i) if (xv[i]) SF::mac(acc[i][j], y, xp[i]);
+            for (int l = 0; l < TAU; ++l) yv[l] = yp[j][(size_t)l * a.y_pitch + x];
+            SF::mac(acc[j], yv, pr);
         }
     }
-    u64 v[RT * CT * TAU];
 #pragma unroll
-    for (int i = 0; i < RT; ++i)
+    for (int j = 0; j < CT; ++j)
 #pragma unroll
-        for (int j = 0; j < CT; ++j)
+        for (int l = 0; l < TAU; ++l) {
+            u64 v = F::reduce192(acc[j][l]);
 #pragma unroll
-            for (int l = 0; l < TAU; ++l) v[(i * CT + j) * TAU + l] = F::reduce192(acc[i][j][l]);
-    block_reduce_add<F, RT * CT * TAU>(v, red);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < RT; ++i)
-#pragma unroll
-            for (int j = 0; j < CT; ++j) {
-                if (r0 + i >= a.nrows || c0 + j >= a.ncols) continue;
-                u64* o = a.partial + (((size_t)blockIdx.y * a.nrows + (r0 + i)) * a.ncols + (c0 + j)) * Rg::D + slot * TAU;
-#pragma unroll
-                for (int l = 0; l < TAU; ++l) o[l] = v[(i * CT + j) * TAU + l];
-            }
-    }
+            for (int o = 16; o > 0; o >>= 1) v = F::add(v, __shfl_down_sync(0xffffffffu, v, o));
+            if (lane == 0 && c0 + j < a.ncols) a.partial[(((size_t)blockIdx.y * a.nrows + row) * a.ncols + (c0 + j)) * Rg::D + slot * TAU + l] = v;
+        }
 }
 
 // evaluate f-hat MLEs straight from coefficient planes: out[v][j][slot][l] = sum_x eq[x][slot][l] * coeff_v[x][j*S + slot]
@@ -583,50 +591,36 @@ k_fold_sc_round(const FoldScArgs a) {
 #pragma unroll
         for (int l = 0; l < TAU; ++l) h[e][l] = 0;
     if (active) {
-        Acc192 acc[4][TAU];
+        // along the pair's line f(X) = u + X s:  f^3 - f = (u^3 - u) + 3X u^2 s + 3X^2 u s^2 + X^3 (s^3 - s) + (X^3 - X) s,
+        // so h(X) = A + 3X B + 3X^2 C + X^3 Dd + (X^3 - X) Es with five mu-weighted sums that stay lazily reduced over all tables
+        Acc192 sA[TAU], sB[TAU], sC[TAU], sD[TAU], sE[TAU];
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int l = 0; l < TAU; ++l) acc[e][l].clear();
+        for (int l = 0; l < TAU; ++l) { sA[l].clear(); sB[l].clear(); sC[l].clear(); sD[l].clear(); sE[l].clear(); }
         for (int kd = 0; kd < a.n_f; ++kd) {
             u64 u[TAU], s[TAU];
 #pragma unroll
             for (int l = 0; l < TAU; ++l) {
-                const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(a.fh + (size_t)kd * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b);
+                const ulonglong2 p = __ldg(reinterpret_cast<const ulonglong2*>(a.fh + (size_t)kd * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b));
                 u[l] = p.x; s[l] = F::sub(p.y, p.x);
             }
-            // (u + e s)^3 - (u + e s) for e = 0..3 from u^2, s^2, u^3, s^3, u^2 s, u s^2
-            u64 uu[TAU], ss[TAU], u3[TAU], s3[TAU], uus[TAU], uss[TAU];
-            SF::sqr(uu, u); SF::sqr(ss, s); SF::mul(u3, uu, u); SF::mul(s3, ss, s); SF::mul(uus, uu, s); SF::mul(uss, ss, u);
-            u64 g[TAU], a3[TAU], b3[TAU], t[TAU];
-            SF::add(a3, uus, uus); SF::add(a3, a3, uus);       // 3 u^2 s
-            SF::add(b3, uss, uss); SF::add(b3, b3, uss);       // 3 u s^2
-            // e = 0: u^3 - u
-            SF::sub(g, u3, u); SF::mac(acc[0], g, s_mu[kd]);
-            // e = 1: u^3 + 3u^2 s + 3 u s^2 + s^3 - u - s
-            SF::add(g, g, a3); SF::add(g, g, b3); SF::add(g, g, s3); SF::sub(g, g, s); SF::mac(acc[1], g, s_mu[kd]);
-            // e = 2: u^3 + 6 u^2 s + 12 u s^2 + 8 s^3 - u - 2s  = g1 + 3u^2 s + 9 u s^2 + 7 s^3 - s
-            SF::add(g, g, a3); SF::add(t, b3, b3); SF::add(t, t, b3); SF::add(g, g, t);                // + 3u^2 s + 9 u s^2
-            u64 s3x2[TAU], s3x4[TAU], s3x7[TAU];
-            SF::add(s3x2, s3, s3); SF::add(s3x4, s3x2, s3x2); SF::add(s3x7, s3x4, s3x2); SF::add(s3x7, s3x7, s3);
-            SF::add(g, g, s3x7); SF::sub(g, g, s); SF::mac(acc[2], g, s_mu[kd]);
-            // e = 3: g2 + 3 u^2 s + 15 u s^2 + 19 s^3 - s
-            SF::add(g, g, a3); SF::add(t, t, b3); SF::add(t, t, b3); SF::add(g, g, t);                 // + 3u^2 s + 15 u s^2
-            u64 s3x16[TAU], s3x19[TAU];
-            SF::add(s3x16, s3x4, s3x4); SF::add(s3x16, s3x16, s3x16); SF::add(s3x19, s3x16, s3x2); SF::add(s3x19, s3x19, s3);
-            SF::add(g, g, s3x19); SF::sub(g, g, s); SF::mac(acc[3], g, s_mu[kd]);
+            u64 uu[TAU], ss[TAU], t[TAU];
+            const typename SF::Prepped mu = s_mu[kd];
+            SF::sqr(uu, u); SF::sqr(ss, s);
+            SF::mul(t, uu, u); SF::sub(t, t, u); SF::mac(sA, t, mu);      // u^3 - u
+            SF::mul(t, uu, s); SF::mac(sB, t, mu);                        // u^2 s
+            SF::mul(t, ss, u); SF::mac(sC, t, mu);                        // u s^2
+            SF::mul(t, ss, s); SF::sub(t, t, s); SF::mac(sD, t, mu);      // s^3 - s
+            SF::mac(sE, s, mu);
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int l = 0; l < TAU; ++l) h[e][l] = F::reduce192(acc[e][l]);
-        // cubic: h(4) = 4 h(3) - 6 h(2) + 4 h(1) - h(0)
-#pragma unroll
         for (int l = 0; l < TAU; ++l) {
-            const u64 a4 = F::add(F::add(h[3][l], h[3][l]), F::add(h[3][l], h[3][l]));
-            const u64 c2 = F::add(h[2][l], h[2][l]), c6 = F::add(F::add(c2, c2), c2);
-            const u64 b4 = F::add(F::add(h[1][l], h[1][l]), F::add(h[1][l], h[1][l]));
-            h[4][l] = F::sub(F::add(F::sub(a4, c6), b4), h[0][l]);
+            const u64 A = F::reduce192(sA[l]), B = F::reduce192(sB[l]), C = F::reduce192(sC[l]), Dd = F::reduce192(sD[l]), Es = F::reduce192(sE[l]);
+            auto mulc = [](u64 v, u64 c) { return F::mul(v, c); };
+            h[0][l] = A;
+            h[1][l] = F::add(F::add(A, mulc(B, 3)), F::add(mulc(C, 3), Dd));
+            h[2][l] = F::add(F::add(F::add(A, mulc(B, 6)), F::add(mulc(C, 12), mulc(Dd, 8))), mulc(Es, 6));
+            h[3][l] = F::add(F::add(F::add(A, mulc(B, 9)), F::add(mulc(C, 27), mulc(Dd, 27))), mulc(Es, 24));
+            h[4][l] = F::add(F::add(F::add(A, mulc(B, 12)), F::add(mulc(C, 48), mulc(Dd, 64))), mulc(Es, 60));
         }
     }
     fold_sc_tail<Rg>(a, b, active, slot, h, red);

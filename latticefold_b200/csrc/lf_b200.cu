@@ -324,6 +324,11 @@ lf_status lf_nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, ui
         if (out_f) pr.E.download_planes(w->f, w->pitch, w->n, out_f);
         pr.free_witness(w); pr.free_witness(wa); pr.free_witness(wi); pr.E.sync(); });
 }
+lf_status lf_prover_timing_detail(const lf_prover* p, char* buf, size_t buf_len) {
+    std::string out; for (auto& m : p->marks) out += m.first + " " + std::to_string(m.second) + "\n";
+    if (out.size() + 1 > buf_len) return LF_ERR_INVALID_ARG;
+    std::memcpy(buf, out.c_str(), out.size() + 1); return LF_OK;
+}
 lf_status lf_prover_last_timings(const lf_prover* p, double* out5) { for (int i = 0; i < 5; ++i) out5[i] = p->timings[i]; return LF_OK; }
 
 }  // extern "C"

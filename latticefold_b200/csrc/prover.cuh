@@ -23,6 +23,7 @@ struct lf_prover {
     lf_ajtai* A = nullptr; bool own_A = true;
     std::vector<lf_sparse*> M;
     double timings[5] = {0, 0, 0, 0, 0};
+    bool detail = false; std::vector<std::pair<std::string, double>> marks; std::chrono::steady_clock::time_point last_mark;
 };
 
 namespace lf {
@@ -34,6 +35,8 @@ template <class Rg> struct Prover {
     static constexpr int D = Rg::D, S = Rg::S, TAU = Rg::TAU;
     lf_prover* P; Engine<Rg> E; HR H;
     explicit Prover(lf_prover* p) : P(p), E(p->ctx), H(E.tab()) {}
+    // diagnostic phase marks (LF_TIMING_DETAIL=1): synchronise and record the time since the previous mark
+    void mark(const char* name) { if (!P->detail) return; E.sync(); auto now = std::chrono::steady_clock::now(); P->marks.push_back({name, std::chrono::duration<double, std::milli>(now - P->last_mark).count()}); P->last_mark = now; }
 
     static HV sf_to_ring(const std::vector<u64>& sf) { size_t n = sf.size() / TAU; HV o(n * D); for (size_t i = 0; i < n; ++i) { El e = HR::from_sf(&sf[i * TAU]); std::memcpy(&o[i * D], e.data(), 8 * D); } return o; }
     static std::vector<u64> squeeze(Transcript<Rg>& T, const char* tag, int n) { T.absorb_tag(tag); std::vector<u64> o((size_t)n * TAU); for (int i = 0; i < n; ++i) T.get_challenge(&o[(size_t)i * TAU]); return o; }
@@ -191,7 +194,9 @@ template <class Rg> struct Prover {
             E.gadget_recompose(pieces + (size_t)k * sb.pc_stride, sb.pc_pitch, wccs + (size_t)k * sb.wc_stride, sb.wc_pitch, w->W, P->B, P->L);
         }
         E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_witness: a coefficient does not fit K digits of base b");
+        mark("dec.split_crt");
         o.x_s = compute_x_s(cm);
+        mark("dec.x_s");
         // commit_witnesses (decomposition.rs:178-201): K-1 commits in one pass over A, y_0 = cm - b (y_1 + b (y_2 + ...))
         o.y_s.assign(K, HV(kappa * D, 0));
         if (cnt(cm.cm) != kappa) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongCommitmentLength");
@@ -205,15 +210,18 @@ template <class Rg> struct Prover {
         { HV bsum(kappa * D, 0); const u64 bm = P->b % F::P;
           for (int k = K - 1; k >= 1; --k) for (size_t i = 0; i < kappa * D; ++i) bsum[i] = F::mul(F::add(bsum[i], o.y_s[k][i]), bm);
           for (size_t i = 0; i < kappa * D; ++i) o.y_s[0][i] = F::sub(cm.cm[i], bsum[i]); }
+        mark("dec.commit");
         // compute_v_s (decomposition.rs:204-211): f-hat of piece k evaluated at r, straight from the digits
         { u64* d_v = E.small_dev((size_t)K * TAU * D);
           E.template coeff_eval<int8_t>(dig, sb.dig_pitch, sb.dig_stride, K, eq_r.p, eq_r.pitch, n, d_v);
           HV all((size_t)K * TAU * D); E.download_words(d_v, all.size(), all.data());
           for (int k = 0; k < K; ++k) o.v_s.emplace_back(all.begin() + (size_t)k * TAU * D, all.begin() + (size_t)(k + 1) * TAU * D); }
+        mark("dec.v_s");
         // compute_mz_mles / compute_u_s (decomposition.rs:214-256): z_k = x_s[k] || w_ccs_k
         for (int k = 0; k < K; ++k) compute_mz(sb.mz, half * K + k, o.x_s[k], wccs + (size_t)k * sb.wc_stride, sb.wc_pitch, w->W);
         { HV all = eval_mz(sb.mz, half * K * (int)P->t, K * (int)P->t, eq_r);
           for (int k = 0; k < K; ++k) o.u_s.emplace_back(all.begin() + (size_t)k * P->t * D, all.begin() + (size_t)(k + 1) * P->t * D); }
+        mark("dec.mz_u_s");
         auto t0 = std::chrono::steady_clock::now();
         for (int k = 0; k < K; ++k) {
             const HV& x = o.x_s[k];
@@ -223,6 +231,7 @@ template <class Rg> struct Prover {
             o.lc.push_back(std::move(L));
         }
         P->timings[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        mark("dec.absorb");
         return o;
     }
 
@@ -250,6 +259,7 @@ template <class Rg> struct Prover {
         std::vector<u64> alpha = squeeze(T, "alpha_s", 2 * K), zeta = squeeze(T, "zeta_s", 2 * K), mu = squeeze(T, "mu_s", 2 * K - 1);
         { u64 one[TAU] = {0}; one[0] = 1; mu.insert(mu.end(), one, one + TAU); }
         HV beta = sf_to_ring(squeeze(T, "beta_s", s));
+        mark("fold.challenges");
         // dense tables [eq(r_acc), G_acc, eq(r_new), G_new, eq(beta)]  (create_sumcheck_polynomial, folding/utils.rs:200-259)
         lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = 2 * (int)P->b; sc.kind = LF_COMB_FOLD; sc.len = m;
         SumcheckDriver<Rg> drv(P->ctx, &sc);
@@ -281,17 +291,20 @@ template <class Rg> struct Prover {
                 E.lincomb(pl, sb.mz.pitch, chunk, &coef[done * D], G, sc.dense.pitch, sb.mz.pitch, true);
             }
         }
+        mark("fold.tables");
         sc.dig = sb.dig; sc.dig_pitch = sb.dig_pitch; sc.dig_stride = sb.dig_stride;
         { HV mu_ring = sf_to_ring(mu); drv.set_mu(mu_ring.data(), 2 * K); }
         std::vector<u64> point; HV finals;
         o.msgs = run_sumcheck(drv, T, point, &finals);
         drv.free_all();
+        mark("fold.sumcheck");
         HV r0 = sf_to_ring(point);
         // theta_i = f-hat_i(r_0): the sumcheck's fully folded f-hat tables (get_thetas, folding.rs:236-246)
         for (int i = 0; i < 2 * K; ++i) o.theta.emplace_back(finals.begin() + (size_t)(5 + i * TAU) * D, finals.begin() + (size_t)(5 + (i + 1) * TAU) * D);
         // eta_i = Mz_i(r_0) (get_etas, folding.rs:248-256)
         { DevVec eq0 = eq_table(r0); HV all = eval_mz(sb.mz, 0, 2 * K * (int)t, eq0); E.dfree(eq0.p);
           for (int i = 0; i < 2 * K; ++i) o.eta.emplace_back(all.begin() + (size_t)i * t * D, all.begin() + (size_t)(i + 1) * t * D); }
+        mark("fold.eta");
         auto t0 = std::chrono::steady_clock::now();
         for (auto& th : o.theta) T.absorb_slice(th.data(), cnt(th));
         for (auto& et : o.eta) T.absorb_slice(et.data(), cnt(et));
@@ -302,11 +315,13 @@ template <class Rg> struct Prover {
         { El one = HR::zero(); one[0] = 1; rho_coeff.push_back(one); }
         for (int i = 0; i < 2 * K; ++i) { El r = H.crt(rho_coeff[i]); std::memcpy(&rho[(size_t)i * D], r.data(), 8 * D); }
         P->timings[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        mark("fold.absorb_rho");
         // compute_f_0 = sum_i rho_i f_i (folding.rs:258-268)
         o.f0 = E.template dalloc<u64>(pitch_of(n) * D);
         { PtrList pl; for (int i = 0; i < 2 * K; ++i) { pl.p[i] = sb.pieces + (size_t)i * sb.pc_stride; pl.len[i] = n; }
           if (2 * K > MAX_LIST) throw LfException(LF_ERR_UNSUPPORTED, "2K exceeds MAX_LIST");
           E.lincomb(pl, sb.pc_pitch, 2 * K, rho.data(), o.f0, pitch_of(n), n, false); }
+        mark("fold.f0");
         // compute_v0_u0_x0_cm_0 (folding/utils.rs:460-521): host
         o.lc.r = r0; o.lc.v = rot_lin_combination(rho_coeff, o.theta);
         const size_t kappa = cnt(lcs[0].cm);
@@ -333,6 +348,7 @@ template <class Rg> struct Prover {
     lf_witness* prove(const lf_problem& in, const lf_witness* w_acc, const lf_witness* w_i, Transcript<Rg>& T, u64* out_proof, u64* out_lcccs) {
         using clk = std::chrono::steady_clock; auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         for (double& x : P->timings) x = 0;
+        P->detail = std::getenv("LF_TIMING_DETAIL") != nullptr; P->marks.clear(); P->last_mark = clk::now();
         auto t_begin = clk::now();
         sanity_check();
         const int K = P->K; const size_t n = P->n;
@@ -344,7 +360,9 @@ template <class Rg> struct Prover {
         T.absorb_slice(acc.u.data(), cnt(acc.u)); T.absorb_slice(acc.x_w.data(), cnt(acc.x_w)); T.absorb(acc.h.data());
         T.absorb_tag("cm_i"); T.absorb_slice(cm_i_cm.data(), cnt(cm_i_cm)); T.absorb_slice(x_ccs.data(), cnt(x_ccs));
         auto t0 = clk::now();
+        mark("absorb_public_input");
         LinOut lin = linearize(cm_i_cm, x_ccs, w_i, T);
+        mark("linearize");
         E.sync(); auto t1 = clk::now(); P->timings[0] = ms(t0, t1);
         StepBuffers sb;
         sb.dig_pitch = (std::max(n, P->m) + 255) / 256 * 256;   // the sumcheck walks all 2^s entries
@@ -354,14 +372,19 @@ template <class Rg> struct Prover {
         sb.wc_pitch = pitch_of(w_i->W); sb.wc_stride = sb.wc_pitch * D; sb.wccs = E.template dalloc<u64>((size_t)2 * K * sb.wc_stride);
         sb.mz = alloc_mz(2 * K);
         DevVec eq_acc = eq_table(acc.r);
+        mark("alloc");
         DecOut dl = decompose(acc, w_acc, eq_acc, sb, 0, T);
+        mark("decompose_acc");
         DecOut dr = decompose(lin.lc, w_i, lin.eq_r, sb, 1, T);
+        mark("decompose_new");
         E.sync(); auto t2 = clk::now(); P->timings[1] = ms(t1, t2);
         std::vector<LCCCS> lcs = dl.lc; lcs.insert(lcs.end(), dr.lc.begin(), dr.lc.end());
         FoldOut fo = fold(lcs, sb, eq_acc, lin.eq_r, T);
+        mark("fold.host_tail");
         lf_witness* w_out = witness_from_f_device(fo.f0);
         E.dfree(sb.dig); E.dfree(sb.pieces); E.dfree(sb.wccs); free_mz(sb.mz); E.dfree(eq_acc.p); E.dfree(lin.eq_r.p);
         E.sync(); auto t3 = clk::now(); P->timings[2] = ms(t2, t3);
+        mark("witness_out_free");
         // serialise: lin{msgs,v,u} | dec_acc | dec_new | fold{msgs,theta,eta}
         u64* p = out_proof;
         put(p, lin.msgs); put(p, lin.lc.v); put(p, lin.lc.u);

@@ -15,7 +15,52 @@ template <class Rg> class Transcript {
     typedef typename Rg::F F;
     static constexpr int W = POSEIDON_W24_WIDTH, RATE = POSEIDON_W24_RATE, CAP = POSEIDON_W24_CAP;
     static constexpr int RF = POSEIDON_W24_FULL, RP = POSEIDON_W24_PARTIAL;
-    struct Tables { u64 ark[(RF + RP) * W]; u64 mds[W * W]; Tables() { for (int i = 0; i < (RF + RP) * W; ++i) ark[i] = POSEIDON_W24_ARK[i] % F::P; for (int i = 0; i < W * W; ++i) mds[i] = POSEIDON_W24_MDS[i] % F::P; } };
+    // Partial rounds use the standard sparse factorisation of the MDS matrix (Poseidon paper, appendix B): with
+    // M = Ms * Md, Ms = [[m00, v^T Mh^-1], [w, I]], Md = diag(1, Mh), the block-diagonal factor commutes with the
+    // single S-box and is pushed into the previous round, so a partial round costs 2W-1 multiplications instead of W^2.
+    // The permutation computed is identical (checked against the dense form in tests and by the reference KATs).
+    struct Tables {
+        u64 ark[(RF + RP) * W];       // round constants; partial rounds hold Md_r * c_r
+        u64 mds[W * W];               // dense MDS (full rounds)
+        u64 pre[W * W];               // replaces MDS in the last full round before the partial rounds
+        u64 sp_row0[RP][W];           // Ms_r first row
+        u64 sp_col0[RP][W];           // Ms_r first column (entry 0 unused)
+        static void matmul(u64* o, const u64* a, const u64* b) {   // o = a * b (W x W)
+            for (int i = 0; i < W; ++i) for (int j = 0; j < W; ++j) { u64 acc = 0; for (int k = 0; k < W; ++k) acc = F::add(acc, F::mul(a[i * W + k], b[k * W + j])); o[i * W + j] = acc; }
+        }
+        static void invert(u64* inv, const u64* m, int n) {         // Gauss-Jordan over Fq, n x n row-major
+            std::vector<u64> a(m, m + n * n); for (int i = 0; i < n * n; ++i) inv[i] = 0; for (int i = 0; i < n; ++i) inv[i * n + i] = 1;
+            for (int c = 0; c < n; ++c) {
+                int piv = -1; for (int r = c; r < n; ++r) if (a[r * n + c]) { piv = r; break; }
+                if (piv < 0) throw std::logic_error("Poseidon: singular MDS sub-matrix");
+                if (piv != c) for (int k = 0; k < n; ++k) { std::swap(a[piv * n + k], a[c * n + k]); std::swap(inv[piv * n + k], inv[c * n + k]); }
+                u64 iv = F::inv(a[c * n + c]);
+                for (int k = 0; k < n; ++k) { a[c * n + k] = F::mul(a[c * n + k], iv); inv[c * n + k] = F::mul(inv[c * n + k], iv); }
+                for (int r = 0; r < n; ++r) if (r != c && a[r * n + c]) { u64 f = a[r * n + c];
+                    for (int k = 0; k < n; ++k) { a[r * n + k] = F::sub(a[r * n + k], F::mul(f, a[c * n + k])); inv[r * n + k] = F::sub(inv[r * n + k], F::mul(f, inv[c * n + k])); } }
+            }
+        }
+        Tables() {
+            for (int i = 0; i < (RF + RP) * W; ++i) ark[i] = POSEIDON_W24_ARK[i] % F::P;
+            for (int i = 0; i < W * W; ++i) mds[i] = POSEIDON_W24_MDS[i] % F::P;
+            std::vector<u64> cur(mds, mds + W * W), md(W * W), nxt(W * W), hat((W - 1) * (W - 1)), hinv((W - 1) * (W - 1));
+            for (int r = RP - 1; r >= 0; --r) {
+                for (int i = 1; i < W; ++i) for (int j = 1; j < W; ++j) hat[(i - 1) * (W - 1) + (j - 1)] = cur[i * W + j];
+                invert(hinv.data(), hat.data(), W - 1);
+                sp_row0[r][0] = cur[0];
+                for (int j = 1; j < W; ++j) { u64 acc = 0; for (int k = 1; k < W; ++k) acc = F::add(acc, F::mul(cur[k], hinv[(k - 1) * (W - 1) + (j - 1)])); sp_row0[r][j] = acc; }   // v^T Mh^-1
+                sp_col0[r][0] = 0; for (int i = 1; i < W; ++i) sp_col0[r][i] = cur[i * W];
+                std::fill(md.begin(), md.end(), 0); md[0] = 1;
+                for (int i = 1; i < W; ++i) for (int j = 1; j < W; ++j) md[i * W + j] = cur[i * W + j];
+                // constants of this partial round move through Md
+                u64* c = ark + (RF / 2 + r) * W; u64 nc[W];
+                for (int i = 0; i < W; ++i) { u64 acc = 0; for (int k = 0; k < W; ++k) acc = F::add(acc, F::mul(md[i * W + k], c[k])); nc[i] = acc; }
+                std::memcpy(c, nc, sizeof nc);
+                matmul(nxt.data(), md.data(), mds); cur = nxt;   // matrix the previous round has to apply
+            }
+            std::memcpy(pre, cur.data(), sizeof pre);
+        }
+    };
     static const Tables& tables() { static const Tables t; return t; }
     u64 st_[W];
     int cursor_;        // next rate lane to absorb into / squeeze from
@@ -23,14 +68,32 @@ template <class Rg> class Transcript {
     unsigned long long permutations_ = 0;
 
     static u64 pow7(u64 x) { u64 x2 = F::mul(x, x), x3 = F::mul(x2, x), x6 = F::mul(x3, x3); return F::mul(x6, x); }
+    // dot product of two W-vectors mod p with two independent carry chains (low / high product halves)
+    static u64 dot(const u64* a, const u64* b) {
+        u128 lo = 0, hi = 0;
+        for (int j = 0; j < W; ++j) { u128 x = (u128)a[j] * b[j]; lo += (u64)x; hi += (u64)(x >> 64); }
+        u128 t = hi + (u64)(lo >> 64);                     // value = (u64)lo + t * 2^64, t < 2^70
+        u64 r = F::reduce128((u64)lo, (u64)t);
+        return F::sub(r, (u64)(t >> 64) << 32);            // 2^128 = -2^32 (mod p)
+    }
+    void dense_layer(const u64* m) { u64 nx[W]; for (int i = 0; i < W; ++i) nx[i] = dot(m + i * W, st_); std::memcpy(st_, nx, sizeof st_); }
     void permute() {
         const Tables& t = tables(); ++permutations_;
-        for (int r = 0; r < RF + RP; ++r) {
+        int r = 0;
+        for (; r < RF / 2; ++r) {
+            for (int i = 0; i < W; ++i) st_[i] = pow7(F::add(st_[i], t.ark[r * W + i]));
+            dense_layer(r == RF / 2 - 1 ? t.pre : t.mds);
+        }
+        for (int pr = 0; pr < RP; ++pr, ++r) {
             for (int i = 0; i < W; ++i) st_[i] = F::add(st_[i], t.ark[r * W + i]);
-            if (r < RF / 2 || r >= RF / 2 + RP) { for (int i = 0; i < W; ++i) st_[i] = pow7(st_[i]); } else st_[0] = pow7(st_[0]);
-            u64 nx[W];
-            for (int i = 0; i < W; ++i) { Acc192 a; a.clear(); const u64* row = t.mds + i * W; for (int j = 0; j < W; ++j) a.mac(row[j], st_[j]); nx[i] = F::reduce192(a); }
-            std::memcpy(st_, nx, sizeof st_);
+            st_[0] = pow7(st_[0]);
+            const u64 x0 = st_[0]; const u64 n0 = dot(t.sp_row0[pr], st_);
+            for (int i = 1; i < W; ++i) { u128 x = (u128)t.sp_col0[pr][i] * x0 + st_[i]; st_[i] = F::reduce128((u64)x, (u64)(x >> 64)); }
+            st_[0] = n0;
+        }
+        for (; r < RF + RP; ++r) {
+            for (int i = 0; i < W; ++i) st_[i] = pow7(F::add(st_[i], t.ark[r * W + i]));
+            dense_layer(t.mds);
         }
     }
 public:
