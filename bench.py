@@ -91,7 +91,8 @@ def run_reference(args, rank, world):
     orc = Oracle()
     cores = os.cpu_count() or 1
     orc.set_threads(cores)
-    wl = workload(args.log_w)
+    import math
+    wl = workload(args.log_w + int(math.log2(max(args.gpus, 1))))
     sample_log_w = min(args.log_w, args.cpu_sample_log_w)
     swl = dict(wl, W=1 << sample_log_w)
     prob = synth.make_instance(RING, swl["W"], swl["B"], swl["L"], swl["b"], swl["K"], swl["kappa"], kind=swl["kind"], config_id=2, ops=OracleOps(orc))
@@ -100,7 +101,7 @@ def run_reference(args, rank, world):
     t = [cpu_step(orc, prob, cores) for _ in range(args.steps)]
     ms = float(np.mean(t))
     value = prob["constraints"] / (ms / 1e3)
-    sample = f"W=2^{sample_log_w} slice of the W=2^{args.log_w} workload (same ring, DP, kappa={wl['kappa']}); constraints/s = (W+2)/step time"
+    sample = f"W=2^{sample_log_w} slice of the W={wl['W']} workload (same ring, DP, kappa={wl['kappa']}); constraints/s = (W+2)/step time"
     line = dict(metric="prover constraints/sec (commit+decomp+sumcheck)", value=value, unit="constraints/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64 (mod 2^64-2^32+1)", data="synthetic", impl="reference",
                 config=config_of(wl, args, "cpu"), cpu_baseline=dict(value=value, unit="constraints/s", cores=cores, kind="port", sample=sample),
@@ -109,9 +110,10 @@ def run_reference(args, rank, world):
 
 
 def config_of(wl, args, where):
-    return dict(workload=f"Goldilocks ring X^24-X^12+1, dummy R1CS ({wl['kind']} witness) with 2^{args.log_w}+2 constraints, one NIFSProver::prove step "
-                         f"(BASELINE.json configs[1])", W=wl["W"], B=wl["B"], L=wl["L"], b=wl["b"], K=wl["K"], kappa=wl["kappa"], n=wl["W"] * wl["L"],
-                parallelism=("cpu threads" if where == "cpu" else ("1 GPU" if args.gpus == 1 else f"{args.gpus} independent replicas (one step per GPU, no collective)")),
+    return dict(workload=f"Goldilocks ring X^24-X^12+1, dummy R1CS ({wl['kind']} witness) with {wl['W']}+2 constraints, one NIFSProver::prove step "
+                         f"(BASELINE.json configs[1]; weak-scaled to W = gpus * 2^{args.log_w} when gpus > 1, as configs[3])", W=wl["W"], B=wl["B"], L=wl["L"], b=wl["b"], K=wl["K"], kappa=wl["kappa"], n=wl["W"] * wl["L"],
+                parallelism=("cpu threads" if where == "cpu" else ("1 GPU" if args.gpus == 1 else
+                             f"{args.gpus} GPUs: witness columns / hypercube sharded, one all-reduce per commit batch, sumcheck round and evaluation")),
                 l2="inputs larger than L2: Ajtai matrix 1.3 GB + 2K witness pieces 1.6 GB per step vs 126 MB L2")
 
 
@@ -144,13 +146,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    wl = workload(args.log_w)
+    # Weak scaling: N GPUs prove ONE instance of N * 2^log_w constraints, witness columns / hypercube sharded over the
+    # ranks with one small all-reduce per commit batch, sumcheck round and evaluation (BASELINE configs[3]).
+    import math
+    wl = workload(args.log_w + int(math.log2(world)))
+    assert world & (world - 1) == 0, "rank count must be a power of two"
     ctx = lf.Context(RING, local)
+    if world > 1:
+        ctx.set_shard(rank, world)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    # every rank proves its own instance (config_id = rank): weak scaling by independent steps
-    prob = synth.make_instance(RING, wl["W"], wl["B"], wl["L"], wl["b"], wl["K"], wl["kappa"], kind=wl["kind"], config_id=100 + rank, ops=None)
-    pr = lf.NIFSProver(ctx, prob)                 # static inputs (Ajtai matrix, CCS) go to HBM once, outside the timed region
-    f = ctx.witness_f_from_w_ccs(RING, prob["w_ccs"], wl["B"], wl["L"])
+    prob = make_sharded_instance(wl, rank, world)
+    pr = lf.NIFSProver(ctx, prob)                 # static inputs (Ajtai matrix slice, CCS) go to HBM once, outside the timed region
+    W_loc = wl["W"] // world
+    f = ctx.witness_f_from_w_ccs(RING, prob["w_ccs"][rank * W_loc:(rank + 1) * W_loc], wl["B"], wl["L"])     # elementwise: local slice
     # pinned host copies of the per-step inputs / outputs for the end-to-end leg
     def pinned_like(a):
         t_ = torch.empty(a.shape, dtype=torch.int64, pin_memory=True)
@@ -188,17 +196,18 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
-    l0 = ctx.launches()
+    l0, c0 = ctx.launches(), ctx.collectives()
     with ClockSampler(local) as clk:
         ms_res = timed(step_resident, args.steps)
     launches = (ctx.launches() - l0) // max(args.steps, 1)
+    collectives = (ctx.collectives() - c0) // max(args.steps, 1)
     phases = pr.timings()
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     constraints = prob["constraints"]
-    value = world * constraints / (ms_res / 1e3)
-    e2e_value = world * constraints / (ms_e2e / 1e3)
+    value = constraints / (ms_res / 1e3)          # one sharded instance: its constraints are the whole job's
+    e2e_value = constraints / (ms_e2e / 1e3)
 
     # per-kernel device time of one extra step (events around every launch; not part of the timed region above)
     ctx.profile(True)
@@ -209,13 +218,13 @@ def main():
     top = max(prof.items(), key=lambda kv: kv[1][1])
     hbm, peak_src = peaks()
     s, t = ccs["s"], ccs["t"]
-    n, K, kappa = wl["W"] * wl["L"], wl["K"], wl["kappa"]
+    n, K, kappa = wl["W"] * wl["L"] // world, wl["K"], wl["kappa"]          # per rank
     M_fold = 5 + 2 * K * 3
     alg = {
         # SURVEY 8(d) per-unit figures in the reference layout (E = 192 B), summed over that kernel's launches in one step
         "k_dot_commit": 2 * (kappa * n + (K - 1) * n + (K - 1) * kappa) * E_BYTES,
-        "k_fold_sc_round": M_fold * ((1 << s) - 2) * E_BYTES,              # rounds 2..s read M tables of length 2^(s-r+1)
-        "k_fold_sc_round1": M_fold * (1 << s) * E_BYTES,
+        "k_fold_sc_round": M_fold * (((1 << s) // world) - 2 + 2 * max(world - 1, 0)) * E_BYTES,              # rounds 2..s read M tables of length 2^(s-r+1)
+        "k_fold_sc_round1": M_fold * ((1 << s) // world) * E_BYTES,
         "k_fold": None, "k_matrix_apply": 2 * (2 * K + 3) * n * E_BYTES,
     }
     top_name, (top_cnt, top_ms) = top
@@ -227,7 +236,7 @@ def main():
                     note="integer-ALU bound kernel (64-bit modular multiplies on 32-bit pipes); see DESIGN.md for the op count")
     line = dict(metric="prover constraints/sec (commit+decomp+sumcheck)", value=value, unit="constraints/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_res, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64 (mod 2^64-2^32+1)", data="synthetic",
-                config=config_of(wl, args, "gpu"), clocks=clk.summary(), gpu_launches=int(launches),
+                config=config_of(wl, args, "gpu"), clocks=clk.summary(), gpu_launches=int(launches), collectives_per_step=collectives,
                 e2e=dict(value=e2e_value, unit="constraints/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(2 * f_pin.nbytes),
                          d2h_bytes_per_step=int(out_proof.nbytes + out_lc.nbytes + out_f.nbytes)),
                 roofline=roofline, phases_ms=phases,
@@ -248,8 +257,21 @@ def main():
         dist.destroy_process_group()
 
 
+def make_sharded_instance(wl, rank, world):
+    """Synthetic inputs of one step, holding only this rank's column slice of the Ajtai matrix (kappa x n/world independent
+    uniform ring elements, SplitMix64 seeded per rank) -- the full 8-GPU matrix would be 10.5 GB per process."""
+    R = synth.RINGS[RING]
+    seed = (synth.SEED_BASE + 100) & synth.MASK
+    n = wl["W"] * wl["L"]
+    w_ccs = synth.make_witness(RING, wl["W"], wl["kind"], seed)
+    ccs = synth.make_ccs(RING, wl["W"], wl["L"], wl["kind"], w_ccs, 1)
+    A = synth.uniform_field(R["p"], wl["kappa"] * (n // world) * R["d"], seed + 7919 * (rank + 1)).reshape(wl["kappa"], n // world, R["d"])
+    return dict(ring=RING, B=wl["B"], L=wl["L"], b=wl["b"], K=wl["K"], kappa=wl["kappa"], n=n, W=wl["W"], A=A, ccs=ccs, w_ccs=w_ccs,
+                cm_i_x_ccs=synth.one(RING, 1), constraints=1 + wl["W"] + 1, kind=wl["kind"])
+
+
 def _commit_with_prover(ctx, pr, lf, prob, f):
-    """cm_i.cm = A f using a temporary scheme object (setup only)."""
+    """cm_i.cm = A f using a temporary scheme object (setup only; all-reduced over the ranks when sharded)."""
     sch = lf.AjtaiCommitmentScheme(ctx, prob["A"])
     cm = sch.commit(ctx.upload(f))
     del sch

@@ -68,6 +68,16 @@ uint64_t lf_ctx_launches(const lf_ctx* ctx);
 lf_status lf_ctx_profile(lf_ctx* ctx, int32_t enable);
 lf_status lf_ctx_profile_report(lf_ctx* ctx, char* buf, size_t buf_len);
 
+/* ---- multi-GPU: one context per rank; the witness-column axis (Ajtai commit) and the hypercube's high bits (sumcheck,
+ * MLE evaluation) are sharded across the ranks, each followed by one small all-reduce.  The collective is
+ * supplied by the host side (torch.distributed over NCCL in bench.py): op 0 = in-place sum of `words` u64 lanes,
+ * op 1 = in-place all-gather (buffer of world * words, this rank's part at rank * words).  Returns 0 on success.
+ * After this call lf_commit / lf_commit_batch / lf_mle_eval_batch treat their vectors as this rank's slice and return the
+ * all-reduced result, and an lf_prover created on the context shards the whole step.                                   */
+typedef int32_t (*lf_collective_fn)(void* user, int32_t op, void* device_ptr, size_t words);
+lf_status lf_ctx_set_shard(lf_ctx* ctx, int32_t rank, int32_t world, lf_collective_fn fn, void* user);
+uint64_t lf_ctx_collectives(const lf_ctx* ctx);
+
 /* ---- vectors: Vec<R> <-> device ------------------------------------------------------------------------------- */
 lf_status lf_vec_upload(lf_ctx* ctx, const uint64_t* host, size_t n, int32_t form, lf_vec** out);
 lf_status lf_vec_download(lf_ctx* ctx, const lf_vec* v, uint64_t* host);

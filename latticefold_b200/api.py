@@ -18,11 +18,12 @@ u64p = C.POINTER(C.c_uint64)
 i32p = C.POINTER(C.c_int32)
 vp = C.c_void_p
 
+COLLECTIVE_FN = C.CFUNCTYPE(C.c_int32, vp, C.c_int32, vp, C.c_size_t)   # lf_collective_fn
 LF_COMB_PRODUCTS, LF_COMB_LIN, LF_COMB_FOLD = 0, 1, 2
 FORM_NTT, FORM_COEFF = 0, 1
 
 # every symbol include/lf_b200.h declares (tests check that the built library exports all of them)
-SYMBOLS = """lf_ring_describe lf_ctx_create lf_ctx_destroy lf_last_error lf_ctx_sync lf_ctx_stream lf_ctx_launches lf_ctx_profile lf_ctx_profile_report
+SYMBOLS = """lf_ring_describe lf_ctx_create lf_ctx_destroy lf_last_error lf_ctx_sync lf_ctx_stream lf_ctx_launches lf_ctx_profile lf_ctx_profile_report lf_ctx_set_shard lf_ctx_collectives
 lf_vec_upload lf_vec_download lf_vec_len lf_vec_form lf_vec_free lf_crt lf_icrt lf_gadget_decompose lf_gadget_recompose
 lf_decompose_to_vec lf_fhat lf_ajtai_create lf_ajtai_free lf_ajtai_kappa lf_ajtai_width lf_commit lf_commit_batch
 lf_sparse_create lf_sparse_free lf_spmv lf_eq_table lf_mle_eval_batch lf_lincomb lf_sumcheck_begin lf_sumcheck_round
@@ -114,6 +115,9 @@ def lib():
     L.lf_ctx_stream.argtypes = [vp]
     L.lf_ctx_launches.restype = C.c_uint64
     L.lf_ctx_launches.argtypes = [vp]
+    L.lf_ctx_set_shard.argtypes = [vp, C.c_int32, C.c_int32, COLLECTIVE_FN, vp]
+    L.lf_ctx_collectives.restype = C.c_uint64
+    L.lf_ctx_collectives.argtypes = [vp]
     L.lf_ctx_profile.argtypes = [vp, C.c_int32]
     L.lf_ctx_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.lf_vec_upload.argtypes = [vp, u64p, C.c_size_t, C.c_int32, C.POINTER(vp)]
@@ -248,6 +252,7 @@ class Context:
         self.ring = ring
         R = synth.RINGS[ring]
         self.d, self.tau, self.S, self.p = R["d"], R["tau"], R["S"], R["p"]
+        self.device, self.rank, self.world = device, 0, 1
         h = vp()
         rc = self.L.lf_ctx_create(ring, device, C.byref(h))
         if rc:
@@ -270,6 +275,17 @@ class Context:
 
     def stream(self):
         return self.L.lf_ctx_stream(self.h)
+
+    def set_shard(self, rank, world, group=None):
+        """Shard the witness-column / hypercube axis over `world` ranks (one Context per rank).  Collectives go through
+        torch.distributed on `group` (NCCL between GPUs; gloo works too, staged through host memory)."""
+        from . import parallel
+        self._coll = parallel.make_collective(self, group)      # keep the ctypes callback alive
+        self.check(self.L.lf_ctx_set_shard(self.h, rank, world, self._coll, None))
+        self.rank, self.world = rank, world
+
+    def collectives(self):
+        return int(self.L.lf_ctx_collectives(self.h))
 
     def profile(self, enable):
         self.check(self.L.lf_ctx_profile(self.h, 1 if enable else 0))
@@ -433,7 +449,7 @@ class NIFSProver:
         P, keep = make_problem(prob)
         h = vp(); ctx.check(ctx.L.lf_prover_create(ctx.h, C.byref(P), C.byref(h))); self.h = h
         self.proof_words = int(ctx.L.lf_proof_words(C.byref(P))); self.lcccs_words = int(ctx.L.lf_lcccs_words(C.byref(P)))
-        self.n = prob["n"]
+        self.n = prob["n"] // ctx.world      # witness elements held by this rank
 
     def close(self):
         if self.h:

@@ -32,6 +32,10 @@ struct lf_ctx {
     lf::u64* d_small = nullptr; size_t d_small_words = 0;          // small device results / parameters
     lf::u64* d_partial = nullptr; size_t d_partial_words = 0;      // block partial sums
     int* d_err = nullptr;
+    // column / hypercube sharding across the GPUs of one box: rank, world and the collective the host side
+    // provides (torch.distributed over NCCL in bench.py).  op 0: in-place sum of u64 lanes; op 1: in-place all-gather
+    // (buffer = world x words, this rank's part at rank * words).  The pointer is device memory on this context's device.
+    int rank = 0, world = 1; lf_collective_fn coll = nullptr; void* coll_user = nullptr; uint64_t collectives = 0;
     bool profiling = false;
     struct ProfRec { const char* name; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
@@ -93,6 +97,23 @@ template <class Rg> struct Engine {
         u64* pz = pinned(words);
         LF_CUDA(cudaMemcpyAsync(pz, dev, words * 8, cudaMemcpyDeviceToHost, st())); sync();
         std::memcpy(host, pz, words * 8);
+    }
+
+    // ---------------------------------------------------------------- collectives
+    bool sharded() const { return c->world > 1; }
+    void collective(int op, u64* dev, size_t words) {
+        if (!c->coll) throw LfException(LF_ERR_INVALID_ARG, "sharded context without a collective callback");
+        sync(); ++c->collectives;
+        if (c->coll(c->coll_user, op, dev, words) != 0) throw LfException(LF_ERR_CUDA, "collective callback failed");
+    }
+    // sum mod p across ranks of `words` field elements at dev (in place)
+    void allreduce_field(u64* dev, size_t words) {
+        if (!sharded() || !words) return;
+        u64* tmp = dalloc<u64>(2 * words);
+        launch("k_split_limbs", [&] { k_split_limbs<<<blocks_for(words), 256, 0, st()>>>(dev, tmp, words); });
+        collective(0, tmp, 2 * words);
+        launch("k_combine_limbs", [&] { k_combine_limbs<F><<<blocks_for(words), 256, 0, st()>>>(tmp, dev, words); });
+        dfree(tmp);
     }
 
     // ---------------------------------------------------------------- layout
@@ -162,6 +183,7 @@ template <class Rg> struct Engine {
             else k_dot<Rg, 1><<<g, wpb * 32, 0, st()>>>(a);
         });
         launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(a.partial, (int)xt, (int)nout, d_out); });
+        allreduce_field(d_out, nout);      // x axis sharded across ranks: one small all-reduce per batched dot
     }
     // f-hat evaluation from coefficient planes; result nvec x TAU x D limbs on the device
     template <class TIn> void coeff_eval(const TIn* coeff, size_t c_pitch, size_t c_vec_stride, int nvec, const u64* eq, size_t eq_pitch, size_t n, u64* d_out) {
@@ -171,21 +193,24 @@ template <class Rg> struct Engine {
         u64* partial = partial_dev((size_t)xt * nout);
         launch("k_coeff_eval", [&] { k_coeff_eval<Rg, TIn><<<dim3(xt, S, nvec), 128, 0, st()>>>(coeff, c_pitch, c_vec_stride, eq, eq_pitch, n, xpb, nvec, partial); });
         launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(partial, (int)xt, (int)nout, d_out); });
+        allreduce_field(d_out, nout);
     }
-    void spmv(const lf_sparse* M, const u64* head, size_t head_len, size_t head_pitch, const u64* tail, size_t tail_pitch, u64* out, size_t out_pitch, size_t nrows) {
+    void spmv(const lf_sparse* M, const u64* head, size_t head_len, size_t head_pitch, const u64* tail, size_t tail_pitch, u64* out, size_t out_pitch, size_t nrows,
+              size_t tail_chunk = ~(size_t)0, size_t tail_chunk_stride = 0) {
         if (!nrows) return;
-        launch("k_spmv", [&] { k_spmv<Rg><<<dim3(blocks_for(nrows, 128), S), 128, 0, st()>>>(M->row_ptr, M->col, M->val, M->val_pitch, head, head_len, head_pitch, tail, tail_pitch, out, out_pitch, nrows); });
+        launch("k_spmv", [&] { k_spmv<Rg><<<dim3(blocks_for(nrows, 128), S), 128, 0, st()>>>(M->row_ptr, M->col, M->val, M->val_pitch, head, head_len, head_pitch, tail, tail_pitch, tail_chunk, tail_chunk_stride, out, out_pitch, nrows); });
     }
     // eq(., r) for r given as s ring elements on the host
-    void eq_table(const u64* r_host, int s, u64* out, size_t out_pitch) {
+    // x_offset / n_local: the slab [x_offset, x_offset + n_local) of the table (hypercube sharding); default = whole table
+    void eq_table(const u64* r_host, int s, u64* out, size_t out_pitch, size_t x_offset = 0, size_t n_local = 0) {
         if (s < 1 || s > 40) throw LfException(LF_ERR_INVALID_ARG, "eq_table: r length is 0 or too large");
         std::vector<u64> pair((size_t)s * 2 * D);
         El one = HR::from_u64(1);
         for (int i = 0; i < s; ++i) { El r = HR::load(r_host + (size_t)i * D), m = HR::sub(one, r); std::memcpy(&pair[((size_t)i * 2) * D], m.data(), 8 * D); std::memcpy(&pair[((size_t)i * 2 + 1) * D], r.data(), 8 * D); }
         u64* d_pair = dalloc<u64>(pair.size());
         LF_CUDA(cudaMemcpyAsync(d_pair, pair.data(), pair.size() * 8, cudaMemcpyHostToDevice, st())); sync();
-        const size_t n = (size_t)1 << s;
-        launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(n, 128), S), 128, (size_t)s * 2 * TAU * 8, st()>>>(d_pair, s, out, out_pitch, n); });
+        const size_t n = n_local ? n_local : (size_t)1 << s;
+        launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(n, 128), S), 128, (size_t)s * 2 * TAU * 8, st()>>>(d_pair, s, out, out_pitch, n, x_offset); });
         dfree(d_pair);
     }
     // out (+)= sum_i coef_i (.) vecs_i ; coef on the host (count x D)

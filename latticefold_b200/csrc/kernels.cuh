@@ -54,6 +54,24 @@ template <class F> __global__ void k_reduce_partials(const u64* __restrict__ par
     out[j] = acc;
 }
 
+// ------------------------------------------------------------------------------------------------ multi-GPU helpers
+// NCCL has no "sum mod p": a field element is sent as two 32-bit halves in u64 lanes, summed with ncclSum (world * 2^32
+// cannot wrap) and folded back mod p.  Bit-exact because integer addition is associative.
+__global__ void k_split_limbs(const u64* __restrict__ in, u64* __restrict__ out, size_t words) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < words) { const u64 v = in[i]; out[2 * i] = v & 0xFFFFFFFFULL; out[2 * i + 1] = v >> 32; }
+}
+template <class F> __global__ void k_combine_limbs(const u64* __restrict__ in, u64* __restrict__ out, size_t words) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < words) { const u64 lo = in[2 * i], hi = in[2 * i + 1];        // each < world * 2^32
+        out[i] = F::add(F::reduce128(lo, 0), F::reduce128(hi << 32, hi >> 32)); }
+}
+// entry 0 of every (table, plane) -> column `rank` of a zeroed [rows][pitch_out] buffer (all-gather by summation)
+__global__ void k_scatter_entry(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t rows, int rank) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) out[i * out_pitch + rank] = in[i * in_pitch];
+}
+
 // ------------------------------------------------------------------------------------------------ layout changes
 // host "Vec<R>" image (element-major) <-> limb planes.  64 elements per block through shared memory so both sides coalesce.
 template <int D> __global__ void k_aos_to_soa(const u64* __restrict__ aos, u64* __restrict__ soa, size_t n, size_t pitch) {
@@ -278,7 +296,7 @@ k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride,
 // concatenation z = head || tail (x_s[k] || w_ccs_k, decomposition.rs:238-246) without materialising it.
 template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, const u32* __restrict__ col, const u64* __restrict__ val, size_t val_pitch,
                                            const u64* __restrict__ z_head, size_t head_len, size_t head_pitch,
-                                           const u64* __restrict__ z_tail, size_t tail_pitch,
+                                           const u64* __restrict__ z_tail, size_t tail_pitch, size_t tail_chunk, size_t tail_chunk_stride,
                                            u64* __restrict__ out, size_t out_pitch, size_t nrows) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
@@ -291,7 +309,10 @@ template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, cons
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
             v[l] = val[(size_t)(slot * TAU + l) * val_pitch + e];
-            z[l] = c < head_len ? z_head[(size_t)(slot * TAU + l) * head_pitch + c] : z_tail[(size_t)(slot * TAU + l) * tail_pitch + (c - head_len)];
+            // the tail may be the all-gathered concatenation of per-rank slabs: chunk r lives at z_tail + r * tail_chunk_stride
+            const size_t tc = c - head_len;
+            z[l] = c < head_len ? z_head[(size_t)(slot * TAU + l) * head_pitch + c]
+                                : z_tail[(tc / tail_chunk) * tail_chunk_stride + (size_t)(slot * TAU + l) * tail_pitch + (tc % tail_chunk)];
         }
         SF::mac(acc, v, SF::prep(z));
     }
@@ -304,20 +325,21 @@ template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, cons
 // r_pair: s x 2 x D limbs on the device = (1 - r_i, r_i) per variable.  thread = (x, slot).
 // The table is built as lo(x mod 2^h) * hi(x div 2^h) from two half tables held in shared memory would save multiplies;
 // at s <= 24 the direct product is s-1 slot-field multiplies per entry and is not on the critical path.
-template <class Rg> __global__ void k_eq_table(const u64* __restrict__ r_pair, int s, u64* __restrict__ out, size_t out_pitch, size_t n) {
+template <class Rg> __global__ void k_eq_table(const u64* __restrict__ r_pair, int s, u64* __restrict__ out, size_t out_pitch, size_t n, size_t x_offset) {
     typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU, D = Rg::D;
     extern __shared__ u64 s_r[];   // s * 2 * TAU for this slot
     const int slot = blockIdx.y;
     for (int i = threadIdx.x; i < s * 2 * TAU; i += blockDim.x) { int v = i / (2 * TAU), w = (i / TAU) & 1, l = i % TAU; s_r[i] = r_pair[((size_t)v * 2 + w) * D + slot * TAU + l]; }
     __syncthreads();
-    size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n) return;
+    const size_t xl = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // local index; x = global hypercube index
+    if (xl >= n) return;
+    const size_t x = xl + x_offset;
     u64 acc[TAU];
 #pragma unroll
     for (int l = 0; l < TAU; ++l) acc[l] = s_r[((x & 1) ? TAU : 0) + l];
     for (int v = 1; v < s; ++v) SF::mul(acc, acc, &s_r[(v * 2 + ((x >> v) & 1)) * TAU]);
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = acc[l];
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + xl] = acc[l];
 }
 
 // ------------------------------------------------------------------------------------------------ K11 linear combinations

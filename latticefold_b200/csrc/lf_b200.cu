@@ -60,6 +60,11 @@ void lf_ctx_destroy(lf_ctx* c) {
 lf_status lf_ctx_sync(lf_ctx* c) { return guard(c, [&] { LF_CUDA(cudaStreamSynchronize(c->stream)); }); }
 void* lf_ctx_stream(lf_ctx* c) { return (void*)c->stream; }
 uint64_t lf_ctx_launches(const lf_ctx* c) { return c->launches; }
+lf_status lf_ctx_set_shard(lf_ctx* c, int32_t rank, int32_t world, lf_collective_fn fn, void* user) {
+    return guard(c, [&] { if (world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) throw LfException(LF_ERR_INVALID_ARG, "bad rank / world / collective");
+                          c->rank = rank; c->world = world; c->coll = fn; c->coll_user = user; });
+}
+uint64_t lf_ctx_collectives(const lf_ctx* c) { return c->collectives; }
 lf_status lf_ctx_profile(lf_ctx* c, int32_t enable) {
     return guard(c, [&] { LF_CUDA(cudaStreamSynchronize(c->stream)); for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } c->prof.clear(); c->profiling = enable != 0; });
 }
@@ -289,9 +294,17 @@ lf_status lf_prover_create(lf_ctx* c, const lf_problem* sh, lf_prover** out) {
         int o = 0; for (u64 i = 0; i < sh->q; ++i) { p->S.emplace_back(sh->S_flat + o, sh->S_flat + o + sh->S_len[i]); o += sh->S_len[i]; }
         p->c.assign(sh->c, sh->c + sh->q * D);
         if (!sh->A) throw LfException(LF_ERR_INVALID_ARG, "Ajtai matrix is NULL");
-        lf_status rc = lf_ajtai_create(c, sh->kappa, sh->n, sh->A, &p->A); if (rc) throw LfException(rc, c->err);
-        for (u64 j = 0; j < sh->t; ++j) { lf_sparse* m = nullptr; rc = lf_sparse_create(c, sh->M[j].nrows, sh->M[j].ncols, sh->M[j].row_ptr, sh->M[j].col, sh->M[j].val, &m);
-            if (rc) throw LfException(rc, c->err); if (m->nrows != sh->m) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "CCS matrix rows != m"); p->M.push_back(m); }
+        // sharded context: the caller passes this rank's column slice of A (kappa x n/world); CCS matrices are given whole
+        // and cut to this rank's row slab here
+        const size_t G = (size_t)c->world, n_loc = sh->n / G, m_loc = sh->m / G;
+        if (sh->n % G || sh->m % G) throw LfException(LF_ERR_UNSUPPORTED, "n and m must be multiples of the rank count");
+        lf_status rc = lf_ajtai_create(c, sh->kappa, n_loc, sh->A, &p->A); if (rc) throw LfException(rc, c->err);
+        for (u64 j = 0; j < sh->t; ++j) {
+            const lf_csr& M = sh->M[j]; if (M.nrows != sh->m) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "CCS matrix rows != m");
+            const size_t r0 = (size_t)c->rank * m_loc; const u64 e0 = M.row_ptr[r0];
+            std::vector<u64> rp(m_loc + 1); for (size_t i = 0; i <= m_loc; ++i) rp[i] = M.row_ptr[r0 + i] - e0;
+            lf_sparse* m = nullptr; rc = lf_sparse_create(c, m_loc, M.ncols, rp.data(), M.col + e0, M.val + e0 * D, &m);
+            if (rc) throw LfException(rc, c->err); p->M.push_back(m); }
         *out = p.release();
     });
 }

@@ -41,31 +41,43 @@ template <class Rg> struct Prover {
     static HV sf_to_ring(const std::vector<u64>& sf) { size_t n = sf.size() / TAU; HV o(n * D); for (size_t i = 0; i < n; ++i) { El e = HR::from_sf(&sf[i * TAU]); std::memcpy(&o[i * D], e.data(), 8 * D); } return o; }
     static std::vector<u64> squeeze(Transcript<Rg>& T, const char* tag, int n) { T.absorb_tag(tag); std::vector<u64> o((size_t)n * TAU); for (int i = 0; i < n; ++i) T.get_challenge(&o[(size_t)i * TAU]); return o; }
     static size_t cnt(const HV& v) { return v.size() / D; }
+    // sharding: rank g owns witness elements / hypercube indices [g * n/G, (g+1) * n/G)
+    int world() const { return P->ctx->world; }
+    int rank() const { return P->ctx->rank; }
+    size_t nl() const { return P->n / world(); }        // local witness length
+    size_t ml() const { return P->m / world(); }        // local hypercube slab
+    size_t Wl() const { return nl() / P->L; }
 
     void sanity_check() const {   // nifs.rs:165-173
         size_t want = std::max((P->n_ccs - P->l - 1) * (size_t)P->L, P->m), p2 = 1; while (p2 < want) p2 <<= 1;
         if (P->m != p2 || ((size_t)1 << P->s) != P->m) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "InvalidSizeBounds");
         if (P->n > P->m) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "witness longer than 2^s");
+        const size_t G = (size_t)world();
+        if (G > 1 && ((G & (G - 1)) || P->n != P->m || P->n % (G * P->L) || ml() < 2))
+            throw LfException(LF_ERR_UNSUPPORTED, "sharding needs a power-of-two rank count, n == 2^s, ranks | W and at least two hypercube entries per rank");
     }
 
     // ------------------------------------------------------------------ witnesses (arith.rs:299-313, Witness::from_f)
     lf_witness* witness_from_f_device(u64* f_dev /* takes ownership, pitch = pitch_of(n) */) {
-        lf_witness* w = new lf_witness; w->n = P->n; w->pitch = pitch_of(P->n); w->f = f_dev;
-        if (P->n % P->L) throw LfException(LF_ERR_INCORRECT_LENGTH, "witness length is not a multiple of L");
-        w->W = P->n / P->L; w->w_pitch = pitch_of(w->W);
+        lf_witness* w = new lf_witness; w->n = nl(); w->pitch = pitch_of(nl()); w->f = f_dev;
+        if (P->n % (P->L * (size_t)world())) throw LfException(LF_ERR_INCORRECT_LENGTH, "witness length is not a multiple of L (times the rank count)");
+        w->W = Wl(); w->w_pitch = pitch_of(w->W);
         w->f_coeff = E.template dalloc<u64>(w->pitch * D); E.crt(w->f, w->pitch, w->f_coeff, w->pitch, w->n, true);
         w->w_ccs = E.template dalloc<u64>(w->w_pitch * D); E.gadget_recompose(w->f, w->pitch, w->w_ccs, w->w_pitch, w->W, P->B, P->L);
         return w;
     }
     lf_witness* upload_witness(const u64* f_host) {
-        u64* f = E.template dalloc<u64>(pitch_of(P->n) * D); E.upload_planes(f_host, P->n, f, pitch_of(P->n));
+        u64* f = E.template dalloc<u64>(pitch_of(nl()) * D); E.upload_planes(f_host, nl(), f, pitch_of(nl()));   // this rank's slice
         return witness_from_f_device(f);
     }
     void free_witness(lf_witness* w) { if (!w) return; E.dfree(w->f); E.dfree(w->f_coeff); E.dfree(w->w_ccs); delete w; }
 
     // ------------------------------------------------------------------ shared device helpers
     struct DevVec { u64* p = nullptr; size_t n = 0, pitch = 0; };
-    DevVec eq_table(const HV& r) { DevVec v; v.n = (size_t)1 << cnt(r); v.pitch = pitch_of(v.n); v.p = E.template dalloc<u64>(v.pitch * D); E.eq_table(r.data(), (int)cnt(r), v.p, v.pitch); return v; }
+    DevVec eq_table(const HV& r) {      // this rank's slab of eq(., r)
+        DevVec v; v.n = ((size_t)1 << cnt(r)) / world(); v.pitch = pitch_of(v.n); v.p = E.template dalloc<u64>(v.pitch * D);
+        E.eq_table(r.data(), (int)cnt(r), v.p, v.pitch, (size_t)rank() * v.n, v.n); return v;
+    }
     // Mz tables for a list of z = head_k || tail_k; out: [count * t] rows of pitch mz_pitch, effective length eff[j]
     struct MzSet { u64* p = nullptr; size_t pitch = 0, stride = 0; int rows = 0; size_t* d_len = nullptr; std::vector<size_t> len; };
     MzSet alloc_mz(int count) {
@@ -77,14 +89,24 @@ template <class Rg> struct Prover {
         return z;
     }
     void free_mz(MzSet& z) { E.dfree(z.p); E.dfree(z.d_len); z.p = nullptr; }
-    void compute_mz(MzSet& z, int k, const HV& head, const u64* tail, size_t tail_pitch, size_t tail_len) {   // mat_vec_mul x t (arith/utils.rs:52-65)
+    // z = head || tail where the tail (w_ccs) is, when sharded, the all-gathered concatenation of the ranks' slabs:
+    // chunk r (tail_chunk elements) at tail + r * tail_chunk_stride.  Rows of M are this rank's slab.
+    void compute_mz(MzSet& z, int k, const HV& head, const u64* tail, size_t tail_pitch, size_t tail_len, size_t tail_chunk = ~(size_t)0, size_t tail_chunk_stride = 0) {   // mat_vec_mul x t (arith/utils.rs:52-65)
         const size_t hl = cnt(head), hp = pitch_of(hl);
         u64* d_head = E.template dalloc<u64>(hp * D); E.upload_small(head.data(), hl, d_head, hp);
         for (size_t j = 0; j < P->t; ++j) {
             if (P->M[j]->ncols != hl + tail_len) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "LengthsNotEqual(M, z)");
-            E.spmv(P->M[j], d_head, hl, hp, tail, tail_pitch, z.p + ((size_t)k * P->t + j) * z.stride, z.pitch, P->M[j]->eff_rows);
+            E.spmv(P->M[j], d_head, hl, hp, tail, tail_pitch, z.p + ((size_t)k * P->t + j) * z.stride, z.pitch, P->M[j]->eff_rows, tail_chunk, tail_chunk_stride);
         }
         E.dfree(d_head);
+    }
+    // all-gather `count` consecutive per-piece w_ccs slabs (each wc_stride words) of every rank: returns [world][count][D][pitch]
+    u64* gather_wccs(const u64* local, size_t words) {
+        if (world() == 1) return const_cast<u64*>(local);
+        u64* all = E.template dalloc<u64>(words * world());
+        LF_CUDA(cudaMemcpyAsync(all + (size_t)rank() * words, local, words * 8, cudaMemcpyDeviceToDevice, E.st()));
+        E.collective(1, all, words);
+        return all;
     }
     // evaluate every Mz row at the point whose eq table is given -> rows x D limbs (host)
     HV eval_mz(const MzSet& z, int row0, int rows, const DevVec& eq) {
@@ -97,21 +119,24 @@ template <class Rg> struct Prover {
     // ------------------------------------------------------------------ linearization (linearization.rs:145-189)
     struct LinOut { LCCCS lc; HV msgs; DevVec eq_r; };
     LinOut linearize(const HV& cm_i_cm, const HV& x_ccs, const lf_witness* w, Transcript<Rg>& T) {
-        LinOut o; const int s = (int)P->s; const size_t m = P->m;
+        LinOut o; const int s = (int)P->s; const size_t m = ml();    // tables hold this rank's slab
         HV head = x_ccs; { El one = HR::from_u64(1); head.insert(head.end(), one.begin(), one.end()); }      // z = x || 1 || w  (arith.rs:399-409)
         HV beta = sf_to_ring(squeeze(T, "beta_s", s));                                                       // linearization/utils.rs:113-124
-        MzSet mz = alloc_mz(1); compute_mz(mz, 0, head, w->w_ccs, w->w_pitch, w->W);
+        MzSet mz = alloc_mz(1);
+        { const size_t words = w->w_pitch * D; u64* tail = gather_wccs(w->w_ccs, words);
+          compute_mz(mz, 0, head, tail, w->w_pitch, w->W * world(), w->W, words);
+          if (tail != w->w_ccs) E.dfree(tail); }
         // sumcheck list: for each term with c_i != 0, the Mz named by S_i; eq(beta,.) last (linearization/utils.rs:63-88)
         std::vector<int> list; for (size_t i = 0; i < P->q; ++i) { bool z = true; for (int l = 0; l < D; ++l) z = z && P->c[i * D + l] == 0; if (z) continue; for (int j : P->S[i]) list.push_back(j); }
         const int Mn = (int)list.size() + 1;
         if (Mn > SC_MAX_MLES || (int)P->q > SC_MAX_TERMS) throw LfException(LF_ERR_UNSUPPORTED, "CCS shape exceeds SC_MAX_MLES / SC_MAX_TERMS");
-        lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = (int)P->d + 1; sc.kind = LF_COMB_LIN; sc.len = m;
+        lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = (int)P->d + 1; sc.kind = LF_COMB_LIN; sc.len = m; sc.sharded = world() > 1;
         SumcheckDriver<Rg> drv(P->ctx, &sc);
         SumcheckDriver<Rg>::alloc_group(E, sc.dense, Mn, m);
         LF_CUDA(cudaMemsetAsync(sc.dense.cur, 0, (size_t)Mn * sc.dense.stride * 8, E.st()));
         for (int k = 0; k + 1 < Mn; ++k) { const int j = list[k];
             LF_CUDA(cudaMemcpy2DAsync(sc.dense.cur + (size_t)k * sc.dense.stride, sc.dense.pitch * 8, mz.p + (size_t)j * mz.stride, mz.pitch * 8, mz.len[j] * 8, D, cudaMemcpyDeviceToDevice, E.st())); }
-        E.eq_table(beta.data(), s, sc.dense.cur + (size_t)(Mn - 1) * sc.dense.stride, sc.dense.pitch);
+        E.eq_table(beta.data(), s, sc.dense.cur + (size_t)(Mn - 1) * sc.dense.stride, sc.dense.pitch, (size_t)rank() * m, m);
         // LIN comb (linearization/utils.rs:90-107): vals[] is indexed by the CCS matrix index j.  The list position of
         // matrix j coincides with j for R1CS and the degree-3 CCS; reproduce the reference literally and refuse anything else.
         sc.gen.n_mles = Mn; sc.gen.deg = sc.deg; sc.gen.lin = 1; sc.gen.n_terms = (int)P->q;
@@ -183,7 +208,7 @@ template <class Rg> struct Prover {
         return out;
     }
     DecOut decompose(const LCCCS& cm, const lf_witness* w, const DevVec& eq_r, StepBuffers& sb, int half, Transcript<Rg>& T) {
-        DecOut o; const int K = P->K; const size_t n = P->n, kappa = P->kappa;
+        DecOut o; const int K = P->K; const size_t n = nl(), kappa = P->kappa;
         int8_t* dig = sb.dig + (size_t)half * K * sb.dig_stride;
         u64* pieces = sb.pieces + (size_t)half * K * sb.pc_stride;
         u64* wccs = sb.wccs + (size_t)half * K * sb.wc_stride;
@@ -218,7 +243,9 @@ template <class Rg> struct Prover {
           for (int k = 0; k < K; ++k) o.v_s.emplace_back(all.begin() + (size_t)k * TAU * D, all.begin() + (size_t)(k + 1) * TAU * D); }
         mark("dec.v_s");
         // compute_mz_mles / compute_u_s (decomposition.rs:214-256): z_k = x_s[k] || w_ccs_k
-        for (int k = 0; k < K; ++k) compute_mz(sb.mz, half * K + k, o.x_s[k], wccs + (size_t)k * sb.wc_stride, sb.wc_pitch, w->W);
+        { const size_t words = (size_t)K * sb.wc_stride; u64* all = gather_wccs(wccs, words);     // one all-gather per decomposition
+          for (int k = 0; k < K; ++k) compute_mz(sb.mz, half * K + k, o.x_s[k], all + (size_t)k * sb.wc_stride, sb.wc_pitch, w->W * world(), w->W, words);
+          if (all != wccs) E.dfree(all); }
         { HV all = eval_mz(sb.mz, half * K * (int)P->t, K * (int)P->t, eq_r);
           for (int k = 0; k < K; ++k) o.u_s.emplace_back(all.begin() + (size_t)k * P->t * D, all.begin() + (size_t)(k + 1) * P->t * D); }
         mark("dec.mz_u_s");
@@ -252,7 +279,7 @@ template <class Rg> struct Prover {
         return acc;
     }
     FoldOut fold(const std::vector<LCCCS>& lcs, StepBuffers& sb, const DevVec& eq_acc, const DevVec& eq_new, Transcript<Rg>& T) {
-        FoldOut o; const int K = P->K, s = (int)P->s; const size_t n = P->n, m = P->m, t = P->t;
+        FoldOut o; const int K = P->K, s = (int)P->s; const size_t n = nl(), m = ml(), t = P->t;
         if ((int)lcs.size() != 2 * K) throw LfException(LF_ERR_INCORRECT_LENGTH, "IncorrectLength");
         if (P->b != 2) throw LfException(LF_ERR_UNSUPPORTED, "folding sumcheck kernels are specialised for b = 2 (every reference parameter set but Stark)");
         // squeeze_alpha_beta_zeta_mu (folding/utils.rs:51-96)
@@ -261,13 +288,13 @@ template <class Rg> struct Prover {
         HV beta = sf_to_ring(squeeze(T, "beta_s", s));
         mark("fold.challenges");
         // dense tables [eq(r_acc), G_acc, eq(r_new), G_new, eq(beta)]  (create_sumcheck_polynomial, folding/utils.rs:200-259)
-        lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = 2 * (int)P->b; sc.kind = LF_COMB_FOLD; sc.len = m;
+        lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = 2 * (int)P->b; sc.kind = LF_COMB_FOLD; sc.len = m; sc.sharded = world() > 1;
         SumcheckDriver<Rg> drv(P->ctx, &sc);
         SumcheckDriver<Rg>::alloc_group(E, sc.dense, 5, m);
         auto tbl = [&](int i) { return sc.dense.cur + (size_t)i * sc.dense.stride; };
         LF_CUDA(cudaMemcpy2DAsync(tbl(0), sc.dense.pitch * 8, eq_acc.p, eq_acc.pitch * 8, m * 8, D, cudaMemcpyDeviceToDevice, E.st()));
         LF_CUDA(cudaMemcpy2DAsync(tbl(2), sc.dense.pitch * 8, eq_new.p, eq_new.pitch * 8, m * 8, D, cudaMemcpyDeviceToDevice, E.st()));
-        E.eq_table(beta.data(), s, tbl(4), sc.dense.pitch);
+        E.eq_table(beta.data(), s, tbl(4), sc.dense.pitch, (size_t)rank() * m, m);
         for (int half = 0; half < 2; ++half) {
             u64* G = tbl(1 + 2 * half);
             LF_CUDA(cudaMemsetAsync(G, 0, sc.dense.stride * 8, E.st()));
@@ -351,7 +378,7 @@ template <class Rg> struct Prover {
         P->detail = std::getenv("LF_TIMING_DETAIL") != nullptr; P->marks.clear(); P->last_mark = clk::now();
         auto t_begin = clk::now();
         sanity_check();
-        const int K = P->K; const size_t n = P->n;
+        const int K = P->K; const size_t n = nl();
         LCCCS acc = load_acc(in, P);
         HV cm_i_cm(in.cm_i_cm, in.cm_i_cm + P->kappa * D), x_ccs(in.cm_i_x_ccs, in.cm_i_x_ccs + P->l * D);
         // absorb_public_input (nifs.rs:175-197)
@@ -365,7 +392,7 @@ template <class Rg> struct Prover {
         mark("linearize");
         E.sync(); auto t1 = clk::now(); P->timings[0] = ms(t0, t1);
         StepBuffers sb;
-        sb.dig_pitch = (std::max(n, P->m) + 255) / 256 * 256;   // the sumcheck walks all 2^s entries
+        sb.dig_pitch = (std::max(n, ml()) + 255) / 256 * 256;   // the sumcheck walks all 2^s entries
         sb.dig_stride = sb.dig_pitch * D; sb.dig = E.template dalloc<int8_t>((size_t)2 * K * sb.dig_stride);
         LF_CUDA(cudaMemsetAsync(sb.dig, 0, (size_t)2 * K * sb.dig_stride, E.st()));   // f-hat tables are zero on [n, 2^s)
         sb.pc_pitch = pitch_of(n); sb.pc_stride = sb.pc_pitch * D; sb.pieces = E.template dalloc<u64>((size_t)2 * K * sb.pc_stride);

@@ -17,8 +17,9 @@ struct lf_sumcheck {
     lf::u64* d_mu_pow = nullptr;      // n_f x TAU
     lf::u64* d_coef = nullptr;        // PRODUCTS/LIN term coefficients, n_terms x D
     lf::ScGenericArgs gen;            // term structure
-    size_t len = 0;                   // current table length (2^(nv - applied challenges))
+    size_t len = 0;                   // current LOCAL table length (2^(nv - applied challenges) / ranks while sharded)
     int applied = 0;
+    bool sharded = false;             // tables hold this rank's slab of the hypercube (high bits = rank)
 };
 
 namespace lf {
@@ -54,6 +55,7 @@ template <class Rg> struct SumcheckDriver {
     void evaluate(u64* out_host) {
         if (sc->applied != sc->round) throw LfException(LF_ERR_SUMCHECK_MISUSE, "verifier message is empty");
         if (sc->round >= sc->nv) throw LfException(LF_ERR_SUMCHECK_MISUSE, "Prover is not active");
+        if (sc->sharded && sc->len == 1) gather_tables();      // last log2(world) rounds run replicated on every rank
         const size_t n_pairs = sc->len / 2; const int ne = sc->deg + 1;
         unsigned nblk; u64* partial;
         if (sc->kind == LF_COMB_FOLD) {
@@ -77,6 +79,7 @@ template <class Rg> struct SumcheckDriver {
         }
         u64* d_out = E.small_dev((size_t)ne * D);
         E.launch("k_reduce_partials", [&] { k_reduce_partials<F><<<Engine<Rg>::blocks_for((size_t)ne * D, 128), 128, 0, E.st()>>>(partial, (int)nblk, ne * D, d_out); });
+        if (sc->sharded) E.allreduce_field(d_out, (size_t)ne * D);      // one all-reduce of (deg+1) ring elements per round
         E.download_words(d_out, (size_t)ne * D, out_host);
         sc->round += 1;
     }
@@ -89,6 +92,23 @@ template <class Rg> struct SumcheckDriver {
         E.launch("k_fold", [&] { k_fold<Rg><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, g.count), 128, 0, E.st()>>>(a); });
         if (g.cur_owned) E.dfree(g.cur);
         g.cur = out; g.cur_owned = true; g.pitch = np; g.stride = np * D;
+    }
+    // every rank holds one entry per table: all-gather them (summing into a zeroed buffer) so the remaining variables,
+    // which index the ranks, can be bound on every rank redundantly
+    void gather_group(lf_sumcheck::Group& g) {
+        if (!g.count || !g.cur) return;
+        const int G = E.c->world; const size_t np = pitch_of(G), rows = (size_t)g.count * D;
+        u64* out = E.template dalloc<u64>(rows * np);
+        LF_CUDA(cudaMemsetAsync(out, 0, rows * np * 8, E.st()));
+        E.launch("k_scatter_entry", [&] { k_scatter_entry<<<Engine<Rg>::blocks_for(rows), 256, 0, E.st()>>>(g.cur, g.pitch, out, np, rows, E.c->rank); });
+        E.collective(0, out, rows * np);
+        if (g.cur_owned) E.dfree(g.cur);
+        g.cur = out; g.cur_owned = true; g.pitch = np; g.stride = np * D;
+    }
+    void gather_tables() {
+        if (sc->kind == LF_COMB_FOLD && sc->dig && sc->applied == 0) throw LfException(LF_ERR_UNSUPPORTED, "sharded FOLD sumcheck needs at least 2 local entries");
+        gather_group(sc->dense); if (sc->kind == LF_COMB_FOLD) gather_group(sc->fh);
+        sc->len = (size_t)E.c->world; sc->sharded = false;
     }
     // fix_variables with the verifier's challenge (prover.rs:61-72)
     void apply_challenge(const u64* r_sf) {
@@ -106,7 +126,7 @@ template <class Rg> struct SumcheckDriver {
     }
     // after the last challenge every table has one entry: mle_k(r).  out: (dense.count + n_f) x D limbs on the host
     void final_values(u64* out_host) {
-        if (sc->len != 1) throw LfException(LF_ERR_SUMCHECK_MISUSE, "sumcheck not finished");
+        if (sc->len != 1 || sc->sharded) throw LfException(LF_ERR_SUMCHECK_MISUSE, "sumcheck not finished");
         const int total = sc->dense.count + (sc->kind == LF_COMB_FOLD ? sc->n_f : 0);
         std::vector<u64> tmp;
         auto grab = [&](const lf_sumcheck::Group& g, u64* dst) {
