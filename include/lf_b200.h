@@ -76,6 +76,11 @@ lf_status lf_ctx_profile_report(lf_ctx* ctx, char* buf, size_t buf_len);
  * all-reduced result, and an lf_prover created on the context shards the whole step.                                   */
 typedef int32_t (*lf_collective_fn)(void* user, int32_t op, void* device_ptr, size_t words);
 lf_status lf_ctx_set_shard(lf_ctx* ctx, int32_t rank, int32_t world, lf_collective_fn fn, void* user);
+/* Preferred on real multi-GPU boxes: the library opens its own NCCL communicator (rank 0 makes the id with
+ * lf_nccl_unique_id and the host side broadcasts the 128 bytes), and every collective is enqueued on the context's stream
+ * right behind the kernel that produced its input -- no host synchronisation, no callback.                              */
+lf_status lf_nccl_unique_id(uint8_t* out128);
+lf_status lf_ctx_set_shard_nccl(lf_ctx* ctx, int32_t rank, int32_t world, const uint8_t* id128);
 uint64_t lf_ctx_collectives(const lf_ctx* ctx);
 
 /* ---- vectors: Vec<R> <-> device ------------------------------------------------------------------------------- */

@@ -23,7 +23,7 @@ LF_COMB_PRODUCTS, LF_COMB_LIN, LF_COMB_FOLD = 0, 1, 2
 FORM_NTT, FORM_COEFF = 0, 1
 
 # every symbol include/lf_b200.h declares (tests check that the built library exports all of them)
-SYMBOLS = """lf_ring_describe lf_ctx_create lf_ctx_destroy lf_last_error lf_ctx_sync lf_ctx_stream lf_ctx_launches lf_ctx_profile lf_ctx_profile_report lf_ctx_set_shard lf_ctx_collectives
+SYMBOLS = """lf_ring_describe lf_ctx_create lf_ctx_destroy lf_last_error lf_ctx_sync lf_ctx_stream lf_ctx_launches lf_ctx_profile lf_ctx_profile_report lf_ctx_set_shard lf_ctx_collectives lf_nccl_unique_id lf_ctx_set_shard_nccl
 lf_vec_upload lf_vec_download lf_vec_len lf_vec_form lf_vec_free lf_crt lf_icrt lf_gadget_decompose lf_gadget_recompose
 lf_decompose_to_vec lf_fhat lf_ajtai_create lf_ajtai_free lf_ajtai_kappa lf_ajtai_width lf_commit lf_commit_batch
 lf_sparse_create lf_sparse_free lf_spmv lf_eq_table lf_mle_eval_batch lf_lincomb lf_sumcheck_begin lf_sumcheck_round
@@ -116,6 +116,8 @@ def lib():
     L.lf_ctx_launches.restype = C.c_uint64
     L.lf_ctx_launches.argtypes = [vp]
     L.lf_ctx_set_shard.argtypes = [vp, C.c_int32, C.c_int32, COLLECTIVE_FN, vp]
+    L.lf_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    L.lf_ctx_set_shard_nccl.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
     L.lf_ctx_collectives.restype = C.c_uint64
     L.lf_ctx_collectives.argtypes = [vp]
     L.lf_ctx_profile.argtypes = [vp, C.c_int32]
@@ -267,6 +269,10 @@ class Context:
         if rc:
             raise LfError(rc, self.L.lf_last_error(self.h).decode())
 
+    def check_global(self, rc):
+        if rc:
+            raise LfError(rc, self.L.lf_last_error(None).decode())
+
     def sync(self):
         self.check(self.L.lf_ctx_sync(self.h))
 
@@ -280,8 +286,20 @@ class Context:
         """Shard the witness-column / hypercube axis over `world` ranks (one Context per rank).  Collectives go through
         torch.distributed on `group` (NCCL between GPUs; gloo works too, staged through host memory)."""
         from . import parallel
-        self._coll = parallel.make_collective(self, group)      # keep the ctypes callback alive
-        self.check(self.L.lf_ctx_set_shard(self.h, rank, world, self._coll, None))
+        import torch.distributed as dist
+        if world > 1 and dist.get_backend(group) == "nccl":
+            # the library's own communicator: collectives are enqueued on the context's stream (no host round trip)
+            import torch
+            ident = (C.c_uint8 * 128)()
+            if rank == 0:
+                self.check_global(self.L.lf_nccl_unique_id(ident))
+            t = torch.tensor(list(ident), dtype=torch.uint8, device=f"cuda:{self.device}")
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+            self.check(self.L.lf_ctx_set_shard_nccl(self.h, rank, world, ident))
+        else:
+            self._coll = parallel.make_collective(self, group)      # keep the ctypes callback alive
+            self.check(self.L.lf_ctx_set_shard(self.h, rank, world, self._coll, None))
         self.rank, self.world = rank, world
 
     def collectives(self):

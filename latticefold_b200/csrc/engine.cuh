@@ -8,6 +8,8 @@
 #include <memory>
 #include <chrono>
 #include <cstdlib>
+#include <dlfcn.h>
+#include <unordered_map>
 
 namespace lf {
 
@@ -18,6 +20,30 @@ typedef std::vector<u64> HV;   // host vector of ring elements, D limbs each
 inline size_t pitch_of(size_t n) { return ((n ? n : 1) + 31) / 32 * 32; }   // planes start 256-byte aligned
 inline int ceil_log2(size_t x) { int l = 0; while (((size_t)1 << l) < x) ++l; return l; }
 
+}  // namespace lf
+
+// NCCL is reached through dlopen (the process already holds torch's bundled libnccl.so.2; nothing links against it at build
+// time), with the handful of prototypes the sharded path needs.  ncclSum = 0, ncclUint64 = 5 (nccl.h).
+namespace lf {
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    static NcclApi& get() {
+        static NcclApi api; static bool tried = false;
+        if (!tried) { tried = true;
+            void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (h) { api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId"); api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+                     api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy"); api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+                     api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather"); api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString"); } }
+        return api;
+    }
+    bool ok() const { return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather; }
+};
 }  // namespace lf
 
 struct lf_ctx {
@@ -32,10 +58,16 @@ struct lf_ctx {
     lf::u64* d_small = nullptr; size_t d_small_words = 0;          // small device results / parameters
     lf::u64* d_partial = nullptr; size_t d_partial_words = 0;      // block partial sums
     int* d_err = nullptr;
+    // size-keyed cache of device blocks.  Every use is on this context's single stream, so a block handed back by dfree can be
+    // re-issued at once (stream order serialises the old and the new user); steady-state prover steps allocate nothing.
+    std::unordered_multimap<size_t, void*> block_cache; std::unordered_map<void*, size_t> block_size; size_t cached_bytes = 0;
+    // pinned bump arena: staging for small async H2D copies and landing zone for async D2H results; reset per prover step
+    unsigned char* h_arena = nullptr; size_t arena_size = 0, arena_off = 0;
     // column / hypercube sharding across the GPUs of one box: rank, world and the collective the host side
     // provides (torch.distributed over NCCL in bench.py).  op 0: in-place sum of u64 lanes; op 1: in-place all-gather
     // (buffer = world x words, this rank's part at rank * words).  The pointer is device memory on this context's device.
     int rank = 0, world = 1; lf_collective_fn coll = nullptr; void* coll_user = nullptr; uint64_t collectives = 0;
+    void* nccl = nullptr;          // ncclComm_t when the collectives run on this context's stream (no host round trip)
     bool profiling = false;
     struct ProfRec { const char* name; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
@@ -55,8 +87,18 @@ template <class Rg> struct Engine {
     cudaStream_t st() const { return c->stream; }
 
     // ---------------------------------------------------------------- memory
-    template <class T> T* dalloc(size_t count) { void* p = nullptr; LF_CUDA(cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), st())); return (T*)p; }
-    void dfree(void* p) { if (p) cudaFreeAsync(p, st()); }
+    template <class T> T* dalloc(size_t count) {
+        size_t bytes = ((count ? count : 1) * sizeof(T) + 511) / 512 * 512;
+        auto it = c->block_cache.find(bytes);
+        if (it != c->block_cache.end()) { void* p = it->second; c->block_cache.erase(it); c->cached_bytes -= bytes; return (T*)p; }
+        void* p = nullptr; cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {      // out of memory: drop the cache and retry once
+            cudaGetLastError(); sync(); for (auto& kv : c->block_cache) { cudaFree(kv.second); c->block_size.erase(kv.second); } c->block_cache.clear(); c->cached_bytes = 0;
+            LF_CUDA(cudaMalloc(&p, bytes));
+        }
+        c->block_size[p] = bytes; return (T*)p;
+    }
+    void dfree(void* p) { if (!p) return; auto it = c->block_size.find(p); if (it == c->block_size.end()) return; c->block_cache.emplace(it->second, p); c->cached_bytes += it->second; }
     lf_vec* vec_alloc(size_t n, int form) { lf_vec* v = new lf_vec; v->n = n; v->pitch = pitch_of(n); v->form = form; v->p = dalloc<u64>(v->pitch * D); return v; }
     void vec_free(lf_vec* v) { if (v) { dfree(v->p); delete v; } }
     u64* pinned(size_t words) {
@@ -72,6 +114,28 @@ template <class Rg> struct Engine {
         return c->d_partial;
     }
     void sync() { LF_CUDA(cudaStreamSynchronize(st())); }
+    // ---- pinned arena (no synchronisation: the staged bytes stay untouched until arena_reset at the next step)
+    void* arena_alloc(size_t bytes, bool may_wrap = true) {
+        if (!c->h_arena) { c->arena_size = (size_t)64 << 20; LF_CUDA(cudaMallocHost(&c->h_arena, c->arena_size)); c->arena_off = 0; }
+        bytes = (bytes + 63) / 64 * 64;
+        if (bytes > c->arena_size) throw LfException(LF_ERR_INVALID_ARG, "pinned arena too small for this transfer");
+        if (c->arena_off + bytes > c->arena_size) {
+            if (!may_wrap) throw LfException(LF_ERR_INVALID_ARG, "pinned arena exhausted by pending downloads");
+            sync(); c->arena_off = 0;      // wrap: every staged upload has been consumed by now
+        }
+        void* p = c->h_arena + c->arena_off; c->arena_off += bytes; return p;
+    }
+    void arena_reset() { c->arena_off = 0; }
+    void h2d(void* dev, const void* host, size_t bytes) {          // small async upload from pageable memory
+        if (!bytes) return;
+        void* stage = arena_alloc(bytes); std::memcpy(stage, host, bytes);
+        LF_CUDA(cudaMemcpyAsync(dev, stage, bytes, cudaMemcpyHostToDevice, st()));
+    }
+    const u64* d2h_async(const u64* dev, size_t words) {           // valid after the next sync / event on this stream
+        u64* land = (u64*)arena_alloc(std::max<size_t>(words, 1) * 8, false);
+        if (words) LF_CUDA(cudaMemcpyAsync(land, dev, words * 8, cudaMemcpyDeviceToHost, st()));
+        return land;
+    }
     // every kernel launch goes through here: counts launches (bench.py's gpu_launches) and, in profiling mode, brackets
     // the launch with CUDA events on the context's stream so bench.py can attribute device time per kernel.
     template <class Fn> void launch(const char* name, Fn&& fn) {
@@ -86,11 +150,11 @@ template <class Rg> struct Engine {
         int h = 0; LF_CUDA(cudaMemcpyAsync(&h, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st())); sync();
         if (h) { LF_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), st())); throw LfException(code, msg); }
     }
-    // host elements -> small SoA device vector (synchronous staging through pageable memory is fine: a few elements)
+    // host elements -> small SoA device vector, staged through the pinned arena (asynchronous)
     void upload_small(const u64* host, size_t n, u64* dev, size_t pitch) {
-        std::vector<u64> soa(pitch * D, 0);
+        u64* soa = (u64*)arena_alloc(pitch * D * 8); std::memset(soa, 0, pitch * D * 8);
         for (size_t i = 0; i < n; ++i) for (int l = 0; l < D; ++l) soa[(size_t)l * pitch + i] = host[i * D + l];
-        LF_CUDA(cudaMemcpyAsync(dev, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice, st())); sync();
+        LF_CUDA(cudaMemcpyAsync(dev, soa, pitch * D * 8, cudaMemcpyHostToDevice, st()));
     }
     // download `words` u64 from the device into a host vector (through the pinned landing zone)
     void download_words(const u64* dev, size_t words, u64* host) {
@@ -102,7 +166,13 @@ template <class Rg> struct Engine {
     // ---------------------------------------------------------------- collectives
     bool sharded() const { return c->world > 1; }
     void collective(int op, u64* dev, size_t words) {
-        if (!c->coll) throw LfException(LF_ERR_INVALID_ARG, "sharded context without a collective callback");
+        if (c->nccl) {      // enqueued on the context's stream: ordered with the producing / consuming kernels, no synchronisation
+            NcclApi& n = NcclApi::get(); ++c->collectives;
+            int rc = op == 0 ? n.AllReduce(dev, dev, words, 5, 0, c->nccl, st()) : n.AllGather(dev + (size_t)c->rank * words, dev, words, 5, c->nccl, st());
+            if (rc != 0) throw LfException(LF_ERR_CUDA, std::string("NCCL: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"));
+            return;
+        }
+        if (!c->coll) throw LfException(LF_ERR_INVALID_ARG, "sharded context without a collective");
         sync(); ++c->collectives;
         if (c->coll(c->coll_user, op, dev, words) != 0) throw LfException(LF_ERR_CUDA, "collective callback failed");
     }
@@ -166,9 +236,13 @@ template <class Rg> struct Engine {
         DotArgs a; a.X = X; a.x_row_stride = x_row_stride; a.x_pitch = x_pitch; a.nrows = nrows; a.Y = Y; a.y_pitch = y_pitch; a.ncols = ncols;
         a.x_len = x_len_dev; a.n = n;
         // x tile: long enough to amortise the per-warp reduction, short enough to fill 148 SMs
-        const int ct = ncols >= 3 ? 4 : ncols;
+        // measured on B200 (tools/dot_ab.py, kappa=26, n=2^18, 15 pieces): CT=2 with 4-8 warps per block runs at 87% of the
+        // IMAD.WIDE-bound multiply-accumulate peak (4.7 ms vs 4.1 ms); CT=4 is register-starved (7.9 ms), CT=1 reloads too much (6.6 ms)
+        int ct = ncols >= 2 ? 2 : 1;
+        if (const char* e = std::getenv("LF_DOT_CT")) { int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && v <= ncols) ct = v; }
         const int units = nrows * ((ncols + ct - 1) / ct);
-        int wpb = 1; { int best = 1 << 30; for (int w = 16; w >= 4; --w) { int waste = (units + w - 1) / w * w - units; if (waste < best) { best = waste; wpb = w; } } if (units < 4) wpb = units; }
+        int wmax = 4; if (const char* e = std::getenv("LF_DOT_WPB")) { int v = atoi(e); if (v >= 1 && v <= 16) wmax = v; }
+        int wpb = 1; { int best = 1 << 30; for (int w = wmax; w >= std::min(3, wmax); --w) { int waste = (units + w - 1) / w * w - units; if (waste < best) { best = waste; wpb = w; } } if (units < 4) wpb = std::min(units, wmax); }
         const int groups = (units + wpb - 1) / wpb;
         size_t xpb = 128 * 32;
         while (xpb > 256 && (size_t)groups * S * ((n + xpb - 1) / xpb) < 148 * 4) xpb /= 2;
@@ -178,9 +252,11 @@ template <class Rg> struct Engine {
         a.partial = partial_dev((size_t)xt * nout);
         launch(name, [&] {
             dim3 g((unsigned)groups, xt, S);
-            if (ct == 4) k_dot<Rg, 4><<<g, wpb * 32, 0, st()>>>(a);
-            else if (ct == 2) k_dot<Rg, 2><<<g, wpb * 32, 0, st()>>>(a);
-            else k_dot<Rg, 1><<<g, wpb * 32, 0, st()>>>(a);
+            if (wpb <= 8) {
+                if (ct == 4) k_dot<Rg, 4, 256><<<g, wpb * 32, 0, st()>>>(a); else if (ct == 2) k_dot<Rg, 2, 256><<<g, wpb * 32, 0, st()>>>(a); else k_dot<Rg, 1, 256><<<g, wpb * 32, 0, st()>>>(a);
+            } else {
+                if (ct == 4) k_dot<Rg, 4, 512><<<g, wpb * 32, 0, st()>>>(a); else if (ct == 2) k_dot<Rg, 2, 512><<<g, wpb * 32, 0, st()>>>(a); else k_dot<Rg, 1, 512><<<g, wpb * 32, 0, st()>>>(a);
+            }
         });
         launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(a.partial, (int)xt, (int)nout, d_out); });
         allreduce_field(d_out, nout);      // x axis sharded across ranks: one small all-reduce per batched dot
@@ -208,9 +284,18 @@ template <class Rg> struct Engine {
         El one = HR::from_u64(1);
         for (int i = 0; i < s; ++i) { El r = HR::load(r_host + (size_t)i * D), m = HR::sub(one, r); std::memcpy(&pair[((size_t)i * 2) * D], m.data(), 8 * D); std::memcpy(&pair[((size_t)i * 2 + 1) * D], r.data(), 8 * D); }
         u64* d_pair = dalloc<u64>(pair.size());
-        LF_CUDA(cudaMemcpyAsync(d_pair, pair.data(), pair.size() * 8, cudaMemcpyHostToDevice, st())); sync();
+        h2d(d_pair, pair.data(), pair.size() * 8);
         const size_t n = n_local ? n_local : (size_t)1 << s;
-        launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(n, 128), S), 128, (size_t)s * 2 * TAU * 8, st()>>>(d_pair, s, out, out_pitch, n, x_offset); });
+        if (s < 8) {
+            launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(n, 128), S), 128, (size_t)s * 2 * TAU * 8, st()>>>(d_pair, s, out, out_pitch, n, x_offset); });
+        } else {      // two half tables, then one multiply per entry
+            const int h = s / 2; const size_t nlo = (size_t)1 << h, nhi = (size_t)1 << (s - h), plo = pitch_of(nlo), phi = pitch_of(nhi);
+            u64 *lo = dalloc<u64>(plo * D), *hi = dalloc<u64>(phi * D);
+            launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(nlo, 128), S), 128, (size_t)h * 2 * TAU * 8, st()>>>(d_pair, h, lo, plo, nlo, 0); });
+            launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(nhi, 128), S), 128, (size_t)(s - h) * 2 * TAU * 8, st()>>>(d_pair + (size_t)h * 2 * D, s - h, hi, phi, nhi, 0); });
+            launch("k_eq_combine", [&] { k_eq_combine<Rg><<<dim3(blocks_for(n, 128), S), 128, 0, st()>>>(lo, plo, hi, phi, h, out, out_pitch, n, x_offset); });
+            dfree(lo); dfree(hi);
+        }
         dfree(d_pair);
     }
     // out (+)= sum_i coef_i (.) vecs_i ; coef on the host (count x D)
@@ -220,8 +305,7 @@ template <class Rg> struct Engine {
             const int chunk = std::min(MAX_LIST, count - done);
             PtrList pl; for (int i = 0; i < chunk; ++i) { pl.p[i] = vecs.p[done + i]; pl.len[i] = vecs.len[done + i]; }
             u64* d_coef = dalloc<u64>((size_t)std::max(chunk, 1) * D);
-            if (chunk) LF_CUDA(cudaMemcpyAsync(d_coef, coef_host + (size_t)done * D, (size_t)chunk * D * 8, cudaMemcpyHostToDevice, st()));
-            sync();
+            if (chunk) h2d(d_coef, coef_host + (size_t)done * D, (size_t)chunk * D * 8);
             launch("k_lincomb", [&] { k_lincomb<Rg><<<dim3(blocks_for(n, 128), S), 128, 0, st()>>>(pl, v_pitch, chunk, d_coef, out, out_pitch, n, (accumulate || done > 0) ? 1 : 0); });
             dfree(d_coef);
             done += chunk; if (count == 0) break;

@@ -185,7 +185,7 @@ struct DotArgs {
     size_t n; int x_per_block;
     u64* partial;                                             // [x tile][row][col][D]
 };
-template <class Rg, int CT> __global__ void __launch_bounds__(512)
+template <class Rg, int CT, int MAXT> __global__ void __launch_bounds__(MAXT)
 k_dot(const DotArgs a) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     const int col_tiles = (a.ncols + CT - 1) / CT, n_units = a.nrows * col_tiles;
@@ -340,6 +340,21 @@ template <class Rg> __global__ void k_eq_table(const u64* __restrict__ r_pair, i
     for (int v = 1; v < s; ++v) SF::mul(acc, acc, &s_r[(v * 2 + ((x >> v) & 1)) * TAU]);
 #pragma unroll
     for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + xl] = acc[l];
+}
+
+// eq[x] = lo[x mod 2^h] * hi[x div 2^h]: the table over s variables from two half tables (one multiply per entry instead of s-1)
+template <class Rg> __global__ void k_eq_combine(const u64* __restrict__ lo, size_t lo_pitch, const u64* __restrict__ hi, size_t hi_pitch, int h,
+                                                 u64* __restrict__ out, size_t out_pitch, size_t n, size_t x_offset) {
+    typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+    const size_t xl = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
+    if (xl >= n) return;
+    const size_t x = xl + x_offset, xlo = x & (((size_t)1 << h) - 1), xhi = x >> h;
+    u64 a[TAU], b[TAU];
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) { a[l] = __ldg(lo + (size_t)(slot * TAU + l) * lo_pitch + xlo); b[l] = __ldg(hi + (size_t)(slot * TAU + l) * hi_pitch + xhi); }
+    SF::mul(a, a, b);
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + xl] = a[l];
 }
 
 // ------------------------------------------------------------------------------------------------ K11 linear combinations
@@ -505,7 +520,7 @@ struct FoldScArgs {
     // rounds >= 2: slot-field tables, f-hat (k,d) at fh + (k*tau+d) * fh_stride
     const u64* fh; size_t fh_pitch, fh_stride;
 };
-template <class Rg> __device__ __forceinline__ void fold_sc_tail(const FoldScArgs& a, size_t b, bool active, int slot, const u64 (*h)[Rg::TAU] /* h(0..4) */, u64* red) {
+template <class Rg, bool WITH_PRODUCTS = true> __device__ __forceinline__ void fold_sc_tail(const FoldScArgs& a, size_t b, bool active, int slot, const u64 (*h)[Rg::TAU] /* h(0..4) */, u64* red, size_t partial_block = ~(size_t)0) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     u64 ev[5][TAU];
 #pragma unroll
@@ -515,19 +530,23 @@ template <class Rg> __device__ __forceinline__ void fold_sc_tail(const FoldScArg
     if (active) {
         u64 val[5][TAU], step[5][TAU];
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
+        for (int k = 0; k < 5; ++k) {
+            if (!WITH_PRODUCTS && k < 4) continue;
 #pragma unroll
             for (int l = 0; l < TAU; ++l) {
                 const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(a.dense + (size_t)k * a.dense_stride + (size_t)(slot * TAU + l) * a.dense_pitch + 2 * b);
                 val[k][l] = p.x; step[k][l] = F::sub(p.y, p.x);
             }
+        }
 #pragma unroll
         for (int e = 0; e < 5; ++e) {
             u64 t0[TAU], t1[TAU];
-            SF::mul(t0, val[0], val[1]); SF::mul(t1, val[2], val[3]); SF::add(t0, t0, t1);
-            SF::mul(t1, val[4], h[e]); SF::add(ev[e], t0, t1);
+            SF::mul(t1, val[4], h[e]);
+            if (WITH_PRODUCTS) { SF::mul(t0, val[0], val[1]); SF::add(t1, t1, t0); SF::mul(t0, val[2], val[3]); SF::add(t1, t1, t0); }
 #pragma unroll
-            for (int k = 0; k < 5; ++k) SF::add(val[k], val[k], step[k]);
+            for (int l = 0; l < TAU; ++l) ev[e][l] = t1[l];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { if (!WITH_PRODUCTS && k < 4) continue; SF::add(val[k], val[k], step[k]); }
         }
     }
     u64 v[5 * TAU];
@@ -536,11 +555,12 @@ template <class Rg> __device__ __forceinline__ void fold_sc_tail(const FoldScArg
 #pragma unroll
         for (int l = 0; l < TAU; ++l) v[e * TAU + l] = ev[e][l];
     block_reduce_add<F, 5 * TAU>(v, red);
+    const size_t pb = partial_block == ~(size_t)0 ? (size_t)blockIdx.x : partial_block;
     if (threadIdx.x == 0)
 #pragma unroll
         for (int e = 0; e < 5; ++e)
 #pragma unroll
-            for (int l = 0; l < TAU; ++l) a.partial[((size_t)blockIdx.x * 5 + e) * Rg::D + slot * TAU + l] = v[e * TAU + l];
+            for (int l = 0; l < TAU; ++l) a.partial[(pb * 5 + e) * Rg::D + slot * TAU + l] = v[e * TAU + l];
 }
 // round 1: every f-hat entry is a balanced digit in {-1,0,1} embedded in the base field (arith.rs:283-289), so
 // f^3 - f vanishes at X = 0, 1 and is a small integer at X = 2, 3; h(4) follows from the cubic's finite differences.
@@ -597,14 +617,15 @@ template <class Rg> __global__ void k_fold_digits(const int8_t* __restrict__ dig
 #pragma unroll
     for (int l = 0; l < TAU; ++l) { u64 v = F::mul(st, r.r[l]); if (l == 0) v = F::add(v, d0); o[(size_t)(slot * TAU + l) * out_pitch + b] = v; }
 }
-// rounds >= 2
-template <class Rg> __global__ void __launch_bounds__(128)
-k_fold_sc_round(const FoldScArgs a) {
+// rounds >= 2.  Along the pair's line f(X) = u + X s:
+//   f^3 - f = (u^3 - u) + 3X u^2 s + 3X^2 u s^2 + X^3 (s^3 - s) + (X^3 - X) s,
+// so h(X) = A + 3X B + 3X^2 C + X^3 Dd + (X^3 - X) Es with five mu-weighted sums that stay lazily reduced over all 2K*tau
+// tables.  The sums are split over two thread sets (blockIdx.z): PART 0 carries {A, B, Es} and the v0 v1 + v2 v3 term,
+// PART 1 carries {C, Dd}; the round message is linear in them, so the two sets simply contribute separate partial sums.
+// Halving the live accumulators per thread (15 -> 9 / 6 Acc192) is what lets enough warps be resident to cover the
+// IMAD / carry-chain latencies (ncu before the split: 211 registers, 12 % occupancy, issue slot busy 43 %).
+template <class Rg, int PART> __device__ __forceinline__ void fold_sc_round_part(const FoldScArgs& a, u64* red, const typename SlotField<Rg>::Prepped* s_mu) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
-    __shared__ u64 red[5 * TAU * 32];
-    __shared__ typename SF::Prepped s_mu[MAX_MU];
-    for (int i = threadIdx.x; i < a.n_f; i += blockDim.x) s_mu[i] = SF::prep(a.mu_pow + (size_t)i * TAU);
-    __syncthreads();
     const int slot = blockIdx.y;
     const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const bool active = b < a.n_pairs;
     u64 h[5][TAU];
@@ -613,11 +634,10 @@ k_fold_sc_round(const FoldScArgs a) {
 #pragma unroll
         for (int l = 0; l < TAU; ++l) h[e][l] = 0;
     if (active) {
-        // along the pair's line f(X) = u + X s:  f^3 - f = (u^3 - u) + 3X u^2 s + 3X^2 u s^2 + X^3 (s^3 - s) + (X^3 - X) s,
-        // so h(X) = A + 3X B + 3X^2 C + X^3 Dd + (X^3 - X) Es with five mu-weighted sums that stay lazily reduced over all tables
-        Acc192 sA[TAU], sB[TAU], sC[TAU], sD[TAU], sE[TAU];
+        Acc192 s0[TAU], s1[TAU], s2[TAU];      // PART 0: A, B, Es    PART 1: C, Dd, (unused)
 #pragma unroll
-        for (int l = 0; l < TAU; ++l) { sA[l].clear(); sB[l].clear(); sC[l].clear(); sD[l].clear(); sE[l].clear(); }
+        for (int l = 0; l < TAU; ++l) { s0[l].clear(); s1[l].clear(); s2[l].clear(); }
+#pragma unroll 2
         for (int kd = 0; kd < a.n_f; ++kd) {
             u64 u[TAU], s[TAU];
 #pragma unroll
@@ -625,27 +645,49 @@ k_fold_sc_round(const FoldScArgs a) {
                 const ulonglong2 p = __ldg(reinterpret_cast<const ulonglong2*>(a.fh + (size_t)kd * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b));
                 u[l] = p.x; s[l] = F::sub(p.y, p.x);
             }
-            u64 uu[TAU], ss[TAU], t[TAU];
+            u64 q[TAU], t[TAU];
             const typename SF::Prepped mu = s_mu[kd];
-            SF::sqr(uu, u); SF::sqr(ss, s);
-            SF::mul(t, uu, u); SF::sub(t, t, u); SF::mac(sA, t, mu);      // u^3 - u
-            SF::mul(t, uu, s); SF::mac(sB, t, mu);                        // u^2 s
-            SF::mul(t, ss, u); SF::mac(sC, t, mu);                        // u s^2
-            SF::mul(t, ss, s); SF::sub(t, t, s); SF::mac(sD, t, mu);      // s^3 - s
-            SF::mac(sE, s, mu);
+            if (PART == 0) {
+                SF::sqr(q, u);
+                SF::mul(t, q, u); SF::sub(t, t, u); SF::mac(s0, t, mu);      // u^3 - u
+                SF::mul(t, q, s); SF::mac(s1, t, mu);                        // u^2 s
+                SF::mac(s2, s, mu);                                          // s
+            } else {
+                SF::sqr(q, s);
+                SF::mul(t, q, u); SF::mac(s0, t, mu);                        // u s^2
+                SF::mul(t, q, s); SF::sub(t, t, s); SF::mac(s1, t, mu);      // s^3 - s
+            }
         }
+        auto mulc = [](u64 v, u64 c) { return F::mul(v, c); };
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
-            const u64 A = F::reduce192(sA[l]), B = F::reduce192(sB[l]), C = F::reduce192(sC[l]), Dd = F::reduce192(sD[l]), Es = F::reduce192(sE[l]);
-            auto mulc = [](u64 v, u64 c) { return F::mul(v, c); };
-            h[0][l] = A;
-            h[1][l] = F::add(F::add(A, mulc(B, 3)), F::add(mulc(C, 3), Dd));
-            h[2][l] = F::add(F::add(F::add(A, mulc(B, 6)), F::add(mulc(C, 12), mulc(Dd, 8))), mulc(Es, 6));
-            h[3][l] = F::add(F::add(F::add(A, mulc(B, 9)), F::add(mulc(C, 27), mulc(Dd, 27))), mulc(Es, 24));
-            h[4][l] = F::add(F::add(F::add(A, mulc(B, 12)), F::add(mulc(C, 48), mulc(Dd, 64))), mulc(Es, 60));
+            const u64 x0 = F::reduce192(s0[l]), x1 = F::reduce192(s1[l]);
+            if (PART == 0) {
+                const u64 Es = F::reduce192(s2[l]);
+                h[0][l] = x0;
+                h[1][l] = F::add(x0, mulc(x1, 3));
+                h[2][l] = F::add(F::add(x0, mulc(x1, 6)), mulc(Es, 6));
+                h[3][l] = F::add(F::add(x0, mulc(x1, 9)), mulc(Es, 24));
+                h[4][l] = F::add(F::add(x0, mulc(x1, 12)), mulc(Es, 60));
+            } else {
+                h[0][l] = 0;
+                h[1][l] = F::add(mulc(x0, 3), x1);
+                h[2][l] = F::add(mulc(x0, 12), mulc(x1, 8));
+                h[3][l] = F::add(mulc(x0, 27), mulc(x1, 27));
+                h[4][l] = F::add(mulc(x0, 48), mulc(x1, 64));
+            }
         }
     }
-    fold_sc_tail<Rg>(a, b, active, slot, h, red);
+    fold_sc_tail<Rg, PART == 0>(a, b, active, slot, h, red, (size_t)blockIdx.z * gridDim.x + blockIdx.x);
+}
+template <class Rg> __global__ void __launch_bounds__(128, 3)
+k_fold_sc_round(const FoldScArgs a) {
+    typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+    __shared__ u64 red[5 * TAU * 32];
+    __shared__ typename SF::Prepped s_mu[MAX_MU];
+    for (int i = threadIdx.x; i < a.n_f; i += blockDim.x) s_mu[i] = SF::prep(a.mu_pow + (size_t)i * TAU);
+    __syncthreads();
+    if (blockIdx.z == 0) fold_sc_round_part<Rg, 0>(a, red, s_mu); else fold_sc_round_part<Rg, 1>(a, red, s_mu);
 }
 
 }  // namespace lf

@@ -53,8 +53,10 @@ lf_status lf_ctx_create(int32_t ring_id, int32_t device, lf_ctx** out) {
 void lf_ctx_destroy(lf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
+    if (c->nccl) NcclApi::get().CommDestroy(c->nccl);
+    for (auto& kv : c->block_size) cudaFree(kv.first);
     for (int i = 0; i < 2; ++i) { cudaFree(c->d_tab_idx[i]); cudaFree(c->d_tab_val[i]); }
-    cudaFree(c->d_err); cudaFree(c->d_small); cudaFree(c->d_partial); if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    cudaFree(c->d_err); cudaFree(c->d_small); cudaFree(c->d_partial); if (c->h_pinned) cudaFreeHost(c->h_pinned); if (c->h_arena) cudaFreeHost(c->h_arena);
     delete (RingTables<G>*)c->tables; cudaStreamDestroy(c->stream); delete c;
 }
 lf_status lf_ctx_sync(lf_ctx* c) { return guard(c, [&] { LF_CUDA(cudaStreamSynchronize(c->stream)); }); }
@@ -65,6 +67,19 @@ lf_status lf_ctx_set_shard(lf_ctx* c, int32_t rank, int32_t world, lf_collective
                           c->rank = rank; c->world = world; c->coll = fn; c->coll_user = user; });
 }
 uint64_t lf_ctx_collectives(const lf_ctx* c) { return c->collectives; }
+lf_status lf_nccl_unique_id(uint8_t* out128) {
+    return guard(nullptr, [&] { NcclApi& n = NcclApi::get(); if (!n.ok()) throw LfException(LF_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+                                NcclApi::UniqueId id; if (n.GetUniqueId(&id) != 0) throw LfException(LF_ERR_CUDA, "ncclGetUniqueId failed"); std::memcpy(out128, id.internal, 128); });
+}
+lf_status lf_ctx_set_shard_nccl(lf_ctx* c, int32_t rank, int32_t world, const uint8_t* id128) {
+    return guard(c, [&] { if (world < 1 || rank < 0 || rank >= world) throw LfException(LF_ERR_INVALID_ARG, "bad rank / world");
+                          NcclApi& n = NcclApi::get(); if (!n.ok()) throw LfException(LF_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+                          LF_CUDA(cudaSetDevice(c->device));
+                          NcclApi::UniqueId id; std::memcpy(id.internal, id128, 128);
+                          int rc = n.CommInitRank(&c->nccl, world, id, rank);
+                          if (rc != 0) throw LfException(LF_ERR_CUDA, std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"));
+                          c->rank = rank; c->world = world; });
+}
 lf_status lf_ctx_profile(lf_ctx* c, int32_t enable) {
     return guard(c, [&] { LF_CUDA(cudaStreamSynchronize(c->stream)); for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } c->prof.clear(); c->profiling = enable != 0; });
 }

@@ -85,7 +85,7 @@ template <class Rg> struct Prover {
         z.pitch = pitch_of(mx); z.stride = z.pitch * D; z.p = E.template dalloc<u64>((size_t)z.rows * z.stride);
         z.len.resize(z.rows); for (int i = 0; i < z.rows; ++i) z.len[i] = P->M[i % P->t]->eff_rows;
         z.d_len = E.template dalloc<size_t>(z.rows);
-        LF_CUDA(cudaMemcpyAsync(z.d_len, z.len.data(), z.rows * sizeof(size_t), cudaMemcpyHostToDevice, E.st())); E.sync();
+        E.h2d(z.d_len, z.len.data(), z.rows * sizeof(size_t));
         return z;
     }
     void free_mz(MzSet& z) { E.dfree(z.p); E.dfree(z.d_len); z.p = nullptr; }
@@ -109,11 +109,14 @@ template <class Rg> struct Prover {
         return all;
     }
     // evaluate every Mz row at the point whose eq table is given -> rows x D limbs (host)
-    HV eval_mz(const MzSet& z, int row0, int rows, const DevVec& eq) {
+    const u64* eval_mz_async(const MzSet& z, int row0, int rows, const DevVec& eq) {      // pinned result, valid after the next sync / event
         PtrList Y; Y.p[0] = eq.p; Y.len[0] = eq.n;
-        u64* d_out = E.small_dev((size_t)rows * D);
+        u64* d_out = E.template dalloc<u64>((size_t)rows * D);
         E.dot(z.p + (size_t)row0 * z.stride, z.stride, z.pitch, rows, z.d_len + row0, Y, eq.pitch, 1, z.pitch, d_out, "k_dot_eval");
-        HV o((size_t)rows * D); E.download_words(d_out, o.size(), o.data()); return o;
+        const u64* land = E.d2h_async(d_out, (size_t)rows * D); E.dfree(d_out); return land;
+    }
+    HV eval_mz(const MzSet& z, int row0, int rows, const DevVec& eq) {
+        const u64* land = eval_mz_async(z, row0, rows, eq); E.sync(); return HV(land, land + (size_t)rows * D);
     }
 
     // ------------------------------------------------------------------ linearization (linearization.rs:145-189)
@@ -143,7 +146,7 @@ template <class Rg> struct Prover {
         for (size_t i = 0; i < P->q; ++i) { if (P->S[i].size() > SC_MAX_FACTORS) throw LfException(LF_ERR_UNSUPPORTED, "CCS multiset too large"); sc.gen.term_len[i] = (int)P->S[i].size();
             for (size_t f = 0; f < P->S[i].size(); ++f) { int j = P->S[i][f]; if (j < 0 || j >= Mn) throw LfException(LF_ERR_INCORRECT_LENGTH, "comb index outside MLE list"); sc.gen.term_idx[i][f] = j; } }
         sc.d_coef = E.template dalloc<u64>(P->q * D);
-        LF_CUDA(cudaMemcpyAsync(sc.d_coef, P->c.data(), P->q * D * 8, cudaMemcpyHostToDevice, E.st())); E.sync();
+        E.h2d(sc.d_coef, P->c.data(), P->q * D * 8);
         std::vector<u64> point; o.msgs = run_sumcheck(drv, T, point);
         drv.free_all();
         o.lc.r = sf_to_ring(point);
@@ -207,48 +210,57 @@ template <class Rg> struct Prover {
         }
         return out;
     }
-    DecOut decompose(const LCCCS& cm, const lf_witness* w, const DevVec& eq_r, StepBuffers& sb, int half, Transcript<Rg>& T) {
-        DecOut o; const int K = P->K; const size_t n = nl(), kappa = P->kappa;
+    // The device half of a decomposition is enqueued without any host synchronisation (results land in the pinned arena
+    // behind an event); the host half (y_0 Horner, transcript absorbs) runs later, overlapping whatever the GPU does next.
+    struct DecPending { LCCCS cm; std::vector<HV> x_s; const u64 *y_pin = nullptr, *v_pin = nullptr, *u_pin = nullptr; cudaEvent_t ev = nullptr; };
+    DecPending decompose_enqueue(const LCCCS& cm, const lf_witness* w, const DevVec& eq_r, StepBuffers& sb, int half) {
+        DecPending o; o.cm = cm; const int K = P->K; const size_t n = nl(), kappa = P->kappa;
         int8_t* dig = sb.dig + (size_t)half * K * sb.dig_stride;
         u64* pieces = sb.pieces + (size_t)half * K * sb.pc_stride;
         u64* wccs = sb.wccs + (size_t)half * K * sb.wc_stride;
+        if (cnt(cm.cm) != kappa) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongCommitmentLength");
         // decompose_witness: f_coeff.decompose_to_vec(b, K).transpose() (decomposition.rs:162-167), then CRT and recompose per piece (arith.rs:324-338)
         E.digit_split(w->f_coeff, w->pitch, dig, sb.dig_pitch, n, P->b, K);
         for (int k = 0; k < K; ++k) {
             E.crt_digits(dig + (size_t)k * sb.dig_stride, sb.dig_pitch, pieces + (size_t)k * sb.pc_stride, sb.pc_pitch, n);
             E.gadget_recompose(pieces + (size_t)k * sb.pc_stride, sb.pc_pitch, wccs + (size_t)k * sb.wc_stride, sb.wc_pitch, w->W, P->B, P->L);
         }
-        E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_witness: a coefficient does not fit K digits of base b");
         mark("dec.split_crt");
         o.x_s = compute_x_s(cm);
         mark("dec.x_s");
-        // commit_witnesses (decomposition.rs:178-201): K-1 commits in one pass over A, y_0 = cm - b (y_1 + b (y_2 + ...))
-        o.y_s.assign(K, HV(kappa * D, 0));
-        if (cnt(cm.cm) != kappa) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongCommitmentLength");
+        // commit_witnesses (decomposition.rs:178-201): K-1 commits in one pass over A
         if (K > 1) {
             PtrList Y; for (int k = 1; k < K; ++k) { Y.p[k - 1] = pieces + (size_t)k * sb.pc_stride; Y.len[k - 1] = n; }
-            u64* d_y = E.small_dev(kappa * (K - 1) * D);
+            u64* d_y = E.template dalloc<u64>(kappa * (K - 1) * D);
             E.dot(P->A->p, P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y, "k_dot_commit");
-            HV all(kappa * (K - 1) * D); E.download_words(d_y, all.size(), all.data());
-            for (int k = 1; k < K; ++k) for (size_t i = 0; i < kappa; ++i) std::memcpy(&o.y_s[k][i * D], &all[(i * (K - 1) + (k - 1)) * D], 8 * D);
+            o.y_pin = E.d2h_async(d_y, kappa * (K - 1) * D); E.dfree(d_y);
         }
-        { HV bsum(kappa * D, 0); const u64 bm = P->b % F::P;
-          for (int k = K - 1; k >= 1; --k) for (size_t i = 0; i < kappa * D; ++i) bsum[i] = F::mul(F::add(bsum[i], o.y_s[k][i]), bm);
-          for (size_t i = 0; i < kappa * D; ++i) o.y_s[0][i] = F::sub(cm.cm[i], bsum[i]); }
         mark("dec.commit");
         // compute_v_s (decomposition.rs:204-211): f-hat of piece k evaluated at r, straight from the digits
-        { u64* d_v = E.small_dev((size_t)K * TAU * D);
+        { u64* d_v = E.template dalloc<u64>((size_t)K * TAU * D);
           E.template coeff_eval<int8_t>(dig, sb.dig_pitch, sb.dig_stride, K, eq_r.p, eq_r.pitch, n, d_v);
-          HV all((size_t)K * TAU * D); E.download_words(d_v, all.size(), all.data());
-          for (int k = 0; k < K; ++k) o.v_s.emplace_back(all.begin() + (size_t)k * TAU * D, all.begin() + (size_t)(k + 1) * TAU * D); }
+          o.v_pin = E.d2h_async(d_v, (size_t)K * TAU * D); E.dfree(d_v); }
         mark("dec.v_s");
         // compute_mz_mles / compute_u_s (decomposition.rs:214-256): z_k = x_s[k] || w_ccs_k
         { const size_t words = (size_t)K * sb.wc_stride; u64* all = gather_wccs(wccs, words);     // one all-gather per decomposition
           for (int k = 0; k < K; ++k) compute_mz(sb.mz, half * K + k, o.x_s[k], all + (size_t)k * sb.wc_stride, sb.wc_pitch, w->W * world(), w->W, words);
           if (all != wccs) E.dfree(all); }
-        { HV all = eval_mz(sb.mz, half * K * (int)P->t, K * (int)P->t, eq_r);
-          for (int k = 0; k < K; ++k) o.u_s.emplace_back(all.begin() + (size_t)k * P->t * D, all.begin() + (size_t)(k + 1) * P->t * D); }
+        o.u_pin = eval_mz_async(sb.mz, half * K * (int)P->t, K * (int)P->t, eq_r);
         mark("dec.mz_u_s");
+        LF_CUDA(cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming)); LF_CUDA(cudaEventRecord(o.ev, E.st()));
+        return o;
+    }
+    DecOut decompose_finish(DecPending& pd, Transcript<Rg>& T) {
+        DecOut o; const int K = P->K; const size_t kappa = P->kappa, t = P->t; const LCCCS& cm = pd.cm;
+        LF_CUDA(cudaEventSynchronize(pd.ev)); cudaEventDestroy(pd.ev); pd.ev = nullptr;
+        o.x_s = std::move(pd.x_s);
+        o.y_s.assign(K, HV(kappa * D, 0));
+        for (int k = 1; k < K; ++k) for (size_t i = 0; i < kappa; ++i) std::memcpy(&o.y_s[k][i * D], pd.y_pin + (i * (K - 1) + (k - 1)) * D, 8 * D);
+        { HV bsum(kappa * D, 0); const u64 bm = P->b % F::P;      // y_0 = cm - b (y_1 + b (y_2 + ...))
+          for (int k = K - 1; k >= 1; --k) for (size_t i = 0; i < kappa * D; ++i) bsum[i] = F::mul(F::add(bsum[i], o.y_s[k][i]), bm);
+          for (size_t i = 0; i < kappa * D; ++i) o.y_s[0][i] = F::sub(cm.cm[i], bsum[i]); }
+        for (int k = 0; k < K; ++k) o.v_s.emplace_back(pd.v_pin + (size_t)k * TAU * D, pd.v_pin + (size_t)(k + 1) * TAU * D);
+        for (int k = 0; k < K; ++k) o.u_s.emplace_back(pd.u_pin + (size_t)k * t * D, pd.u_pin + (size_t)(k + 1) * t * D);
         auto t0 = std::chrono::steady_clock::now();
         for (int k = 0; k < K; ++k) {
             const HV& x = o.x_s[k];
@@ -258,7 +270,6 @@ template <class Rg> struct Prover {
             o.lc.push_back(std::move(L));
         }
         P->timings[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        mark("dec.absorb");
         return o;
     }
 
@@ -303,7 +314,7 @@ template <class Rg> struct Prover {
             for (int i = 0; i < K; ++i) { const u64* a = &alpha[(size_t)(half * K + i) * TAU]; u64 pw[TAU]; std::memcpy(pw, a, 8 * TAU);
                 for (int dd = 0; dd < TAU; ++dd) { std::memcpy(&wts[((size_t)i * TAU + dd) * TAU], pw, 8 * TAU); SF::mul(pw, pw, a); } }
             u64* d_w = E.template dalloc<u64>(wts.size());
-            LF_CUDA(cudaMemcpyAsync(d_w, wts.data(), wts.size() * 8, cudaMemcpyHostToDevice, E.st())); E.sync();
+            E.h2d(d_w, wts.data(), wts.size() * 8);
             E.launch("k_digit_lincomb", [&] { k_digit_lincomb<Rg><<<dim3(Engine<Rg>::blocks_for(n, 128), S), 128, 0, E.st()>>>(sb.dig + (size_t)half * K * sb.dig_stride, sb.dig_pitch, sb.dig_stride, K, d_w, G, sc.dense.pitch, n, 0); });
             E.dfree(d_w);
             // + sum_i Horner_{zeta_i}(Mz_i[t-1..0])   (calculate_challenged_mz_mle, folding.rs:208-226)
@@ -375,6 +386,7 @@ template <class Rg> struct Prover {
     lf_witness* prove(const lf_problem& in, const lf_witness* w_acc, const lf_witness* w_i, Transcript<Rg>& T, u64* out_proof, u64* out_lcccs) {
         using clk = std::chrono::steady_clock; auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         for (double& x : P->timings) x = 0;
+        E.sync(); E.arena_reset();
         P->detail = std::getenv("LF_TIMING_DETAIL") != nullptr; P->marks.clear(); P->last_mark = clk::now();
         auto t_begin = clk::now();
         sanity_check();
@@ -400,10 +412,14 @@ template <class Rg> struct Prover {
         sb.mz = alloc_mz(2 * K);
         DevVec eq_acc = eq_table(acc.r);
         mark("alloc");
-        DecOut dl = decompose(acc, w_acc, eq_acc, sb, 0, T);
+        // both device halves are queued back to back; the host absorbs the first decomposition while the GPU runs the second
+        DecPending pl = decompose_enqueue(acc, w_acc, eq_acc, sb, 0);
+        DecPending prr = decompose_enqueue(lin.lc, w_i, lin.eq_r, sb, 1);
+        DecOut dl = decompose_finish(pl, T);
         mark("decompose_acc");
-        DecOut dr = decompose(lin.lc, w_i, lin.eq_r, sb, 1, T);
+        DecOut dr = decompose_finish(prr, T);
         mark("decompose_new");
+        E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_witness: a coefficient does not fit K digits of base b");
         E.sync(); auto t2 = clk::now(); P->timings[1] = ms(t1, t2);
         std::vector<LCCCS> lcs = dl.lc; lcs.insert(lcs.end(), dr.lc.begin(), dr.lc.end());
         FoldOut fo = fold(lcs, sb, eq_acc, lin.eq_r, T);

@@ -9,7 +9,7 @@ struct lf_sumcheck {
     lf_ctx* ctx = nullptr;
     int nv = 0, deg = 0, round = 0, kind = 0;
     // table groups, each [count][D planes][pitch]; ping-pong buffers (cur -> nxt on every applied challenge)
-    struct Group { lf::u64 *cur = nullptr, *nxt = nullptr; size_t pitch = 0, stride = 0, nxt_pitch = 0, nxt_stride = 0; int count = 0; bool cur_owned = true; };
+    struct Group { lf::u64 *cur = nullptr, *nxt = nullptr, *alt = nullptr; size_t pitch = 0, stride = 0, nxt_cap = 0, alt_cap = 0; int count = 0; bool cur_owned = true; };
     Group dense;          // PRODUCTS/LIN: all MLEs.  FOLD: the first five
     Group fh;             // FOLD: the 2K*tau f-hat tables (slot-field valued); empty while still in digit form
     const int8_t* dig = nullptr; size_t dig_pitch = 0, dig_stride = 0;   // FOLD round 1 in the prover: borrowed int8 digits
@@ -34,7 +34,7 @@ template <class Rg> struct SumcheckDriver {
         g.count = count; g.pitch = pitch_of(len); g.stride = g.pitch * D; g.cur = E.template dalloc<u64>((size_t)count * g.stride); g.cur_owned = true;
     }
     void free_all() {
-        for (lf_sumcheck::Group* g : {&sc->dense, &sc->fh}) { if (g->cur_owned) E.dfree(g->cur); E.dfree(g->nxt); g->cur = g->nxt = nullptr; }
+        for (lf_sumcheck::Group* g : {&sc->dense, &sc->fh}) { if (g->cur_owned && g->cur != g->nxt && g->cur != g->alt) E.dfree(g->cur); E.dfree(g->nxt); E.dfree(g->alt); g->cur = g->nxt = g->alt = nullptr; g->nxt_cap = g->alt_cap = 0; }
         E.dfree(sc->d_mu_pow); E.dfree(sc->d_coef); sc->d_mu_pow = sc->d_coef = nullptr;
     }
     // mu (n_mu ring elements, slot-constant) -> mu_k^{d+1} for d < tau as slot-field elements (folding/utils.rs:293-322)
@@ -48,7 +48,7 @@ template <class Rg> struct SumcheckDriver {
             for (int d = 0; d < TAU; ++d) { std::memcpy(&pw[((size_t)k * TAU + d) * TAU], acc, 8 * TAU); SF::mul(acc, acc, m); }
         }
         sc->d_mu_pow = E.template dalloc<u64>(pw.size());
-        LF_CUDA(cudaMemcpyAsync(sc->d_mu_pow, pw.data(), pw.size() * 8, cudaMemcpyHostToDevice, E.st())); E.sync();
+        E.h2d(sc->d_mu_pow, pw.data(), pw.size() * 8);
     }
 
     // prove_round's evaluation half: out_host = (deg+1) x D limbs
@@ -59,12 +59,14 @@ template <class Rg> struct SumcheckDriver {
         const size_t n_pairs = sc->len / 2; const int ne = sc->deg + 1;
         unsigned nblk; u64* partial;
         if (sc->kind == LF_COMB_FOLD) {
-            nblk = (unsigned)((n_pairs + 127) / 128); partial = E.partial_dev((size_t)nblk * 5 * D);
+            const bool round1 = sc->dig && sc->applied == 0;
+            const unsigned gx = (unsigned)((n_pairs + 127) / 128); nblk = round1 ? gx : 2 * gx;     // rounds >= 2 run two thread sets (blockIdx.z)
+            partial = E.partial_dev((size_t)nblk * 5 * D);
             FoldScArgs a; a.dense = sc->dense.cur; a.dense_pitch = sc->dense.pitch; a.dense_stride = sc->dense.stride; a.mu_pow = sc->d_mu_pow; a.n_f = sc->n_f;
             a.n_pairs = n_pairs; a.partial = partial; a.dig = sc->dig; a.dig_pitch = sc->dig_pitch; a.dig_stride = sc->dig_stride;
             a.fh = sc->fh.cur; a.fh_pitch = sc->fh.pitch; a.fh_stride = sc->fh.stride;
-            if (sc->dig && sc->applied == 0) E.launch("k_fold_sc_round1", [&] { k_fold_sc_round1<Rg><<<dim3(nblk, S), 128, 0, E.st()>>>(a); });
-            else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(nblk, S), 128, 0, E.st()>>>(a); });
+            if (round1) E.launch("k_fold_sc_round1", [&] { k_fold_sc_round1<Rg><<<dim3(gx, S), 128, 0, E.st()>>>(a); });
+            else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(gx, S, 2), 128, 0, E.st()>>>(a); });
         } else {
             nblk = (unsigned)std::min<size_t>((n_pairs + 127) / 128, 148 * 8); partial = E.partial_dev((size_t)nblk * ne * D);
             ScGenericArgs a = sc->gen; a.pitch = sc->dense.pitch; a.n_pairs = n_pairs; a.partial = partial; a.coef = sc->d_coef;
@@ -83,15 +85,23 @@ template <class Rg> struct SumcheckDriver {
         E.download_words(d_out, (size_t)ne * D, out_host);
         sc->round += 1;
     }
+    // ping-pong targets are allocated once (sizes len/2 and len/4 of the first fold) and reused by all later rounds
+    u64* pingpong_target(lf_sumcheck::Group& g, size_t n_out) {
+        const size_t need = (size_t)g.count * pitch_of(n_out) * D;
+        u64*& slot = (g.cur == g.nxt) ? g.alt : g.nxt;
+        size_t& cap = (g.cur == g.nxt) ? g.alt_cap : g.nxt_cap;
+        if (cap < need) { E.dfree(slot); slot = E.template dalloc<u64>(need); cap = need; }
+        return slot;
+    }
     void fold_group(lf_sumcheck::Group& g, const u64* r_sf, size_t n_out) {
         if (!g.count || !g.cur) return;
         const size_t np = pitch_of(n_out);
-        u64* out = E.template dalloc<u64>((size_t)g.count * np * D);
+        u64* out = pingpong_target(g, n_out);
         FoldArgs a; a.in = g.cur; a.out = out; a.in_pitch = g.pitch; a.out_pitch = np; a.in_stride = g.stride; a.out_stride = np * D; a.n_out = n_out;
         for (int l = 0; l < TAU; ++l) a.r[l] = r_sf[l];
         E.launch("k_fold", [&] { k_fold<Rg><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, g.count), 128, 0, E.st()>>>(a); });
-        if (g.cur_owned) E.dfree(g.cur);
-        g.cur = out; g.cur_owned = true; g.pitch = np; g.stride = np * D;
+        if (g.cur_owned && g.cur != g.nxt && g.cur != g.alt) E.dfree(g.cur);     // the caller-provided / initial table set
+        g.cur = out; g.cur_owned = false; g.pitch = np; g.stride = np * D;
     }
     // every rank holds one entry per table: all-gather them (summing into a zeroed buffer) so the remaining variables,
     // which index the ranks, can be bound on every rank redundantly
@@ -102,7 +112,7 @@ template <class Rg> struct SumcheckDriver {
         LF_CUDA(cudaMemsetAsync(out, 0, rows * np * 8, E.st()));
         E.launch("k_scatter_entry", [&] { k_scatter_entry<<<Engine<Rg>::blocks_for(rows), 256, 0, E.st()>>>(g.cur, g.pitch, out, np, rows, E.c->rank); });
         E.collective(0, out, rows * np);
-        if (g.cur_owned) E.dfree(g.cur);
+        if (g.cur_owned && g.cur != g.nxt && g.cur != g.alt) E.dfree(g.cur);
         g.cur = out; g.cur_owned = true; g.pitch = np; g.stride = np * D;
     }
     void gather_tables() {
@@ -117,7 +127,8 @@ template <class Rg> struct SumcheckDriver {
         fold_group(sc->dense, r_sf, n_out);
         if (sc->kind == LF_COMB_FOLD) {
             if (sc->dig && sc->applied == 0) {
-                alloc_group(E, sc->fh, sc->n_f, n_out);
+                sc->fh.count = sc->n_f; sc->fh.pitch = pitch_of(n_out); sc->fh.stride = sc->fh.pitch * D; sc->fh.cur = nullptr;
+                sc->fh.cur = pingpong_target(sc->fh, n_out); sc->fh.cur_owned = false;
                 FoldArgs a; for (int l = 0; l < TAU; ++l) a.r[l] = r_sf[l];
                 E.launch("k_fold_digits", [&] { k_fold_digits<Rg><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, sc->n_f), 128, 0, E.st()>>>(sc->dig, sc->dig_pitch, sc->dig_stride, sc->n_f, sc->fh.cur, sc->fh.pitch, sc->fh.stride, n_out, a); });
             } else fold_group(sc->fh, r_sf, n_out);
