@@ -54,6 +54,7 @@ struct lf_ctx {
     // ring tables on the device: [0] CRT, [1] ICRT
     int* d_tab_idx[2] = {nullptr, nullptr}; lf::u64* d_tab_val[2] = {nullptr, nullptr};
     void* tables = nullptr;        // RingTables<Rg>*
+    bool shared_tables = false;    // auxiliary context: ring tables belong to the parent
     lf::u64* h_pinned = nullptr; size_t h_pinned_words = 0;       // D2H landing zone / H2D staging
     lf::u64* d_small = nullptr; size_t d_small_words = 0;          // small device results / parameters
     lf::u64* d_partial = nullptr; size_t d_partial_words = 0;      // block partial sums
@@ -205,11 +206,12 @@ template <class Rg> struct Engine {
     // ---------------------------------------------------------------- elementwise ops
     void crt(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, bool inverse) {
         if (!n) return;
-        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, u64><<<(unsigned)((n + 127) / 128), 128, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[inverse], c->d_tab_val[inverse]); });
+        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, u64><<<(unsigned)((n + 127) / 128), 128, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[inverse], c->d_tab_val[inverse], 0, 0); });
     }
-    void crt_digits(const int8_t* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n) {
-        if (!n) return;
-        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, int8_t><<<(unsigned)((n + 127) / 128), 128, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[0], c->d_tab_val[0]); });
+    // CRT of `batch` digit vectors (in/out strides between consecutive vectors) in one launch
+    void crt_digits(const int8_t* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, int batch = 1, size_t in_stride = 0, size_t out_stride = 0) {
+        if (!n || !batch) return;
+        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, int8_t><<<dim3((unsigned)((n + 127) / 128), batch), 128, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[0], c->d_tab_val[0], in_stride, out_stride); });
     }
     static unsigned blocks_for(size_t work, int bs = 256) { return (unsigned)((work + bs - 1) / bs); }
     void gadget_decompose(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, u64 B, int L) {
@@ -217,9 +219,9 @@ template <class Rg> struct Engine {
         if (!n) return;
         launch("k_gadget_decompose", [&] { k_gadget_decompose<Rg><<<blocks_for(n * D), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n, (int64_t)B, L, c->d_err); });
     }
-    void gadget_recompose(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n_out, u64 B, int L) {
-        if (!n_out) return;
-        launch("k_gadget_recompose", [&] { k_gadget_recompose<Rg><<<blocks_for(n_out * D), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n_out, B % F::P, L); });
+    void gadget_recompose(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n_out, u64 B, int L, int batch = 1, size_t in_stride = 0, size_t out_stride = 0) {
+        if (!n_out || !batch) return;
+        launch("k_gadget_recompose", [&] { k_gadget_recompose<Rg><<<dim3(blocks_for(n_out * D), batch), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n_out, B % F::P, L, in_stride, out_stride); });
     }
     void digit_split(const u64* in, size_t in_pitch, int8_t* out, size_t out_pitch, size_t n, u64 b, int K) {
         if (b < 2 || b > 254 || K < 1 || K > 64) throw LfException(LF_ERR_UNSUPPORTED, "decompose_to_vec: need 2 <= b <= 254 (int8 digits), 1 <= K <= 64");
@@ -272,9 +274,9 @@ template <class Rg> struct Engine {
         allreduce_field(d_out, nout);
     }
     void spmv(const lf_sparse* M, const u64* head, size_t head_len, size_t head_pitch, const u64* tail, size_t tail_pitch, u64* out, size_t out_pitch, size_t nrows,
-              size_t tail_chunk = ~(size_t)0, size_t tail_chunk_stride = 0) {
-        if (!nrows) return;
-        launch("k_spmv", [&] { k_spmv<Rg><<<dim3(blocks_for(nrows, 128), S), 128, 0, st()>>>(M->row_ptr, M->col, M->val, M->val_pitch, head, head_len, head_pitch, tail, tail_pitch, tail_chunk, tail_chunk_stride, out, out_pitch, nrows); });
+              size_t tail_chunk = ~(size_t)0, size_t tail_chunk_stride = 0, int batch = 1, size_t head_batch_stride = 0, size_t tail_batch_stride = 0, size_t out_batch_stride = 0) {
+        if (!nrows || !batch) return;
+        launch("k_spmv", [&] { k_spmv<Rg><<<dim3(blocks_for(nrows, 128), S, batch), 128, 0, st()>>>(M->row_ptr, M->col, M->val, M->val_pitch, head, head_len, head_pitch, tail, tail_pitch, tail_chunk, tail_chunk_stride, out, out_pitch, nrows, head_batch_stride, tail_batch_stride, out_batch_stride); });
     }
     // eq(., r) for r given as s ring elements on the host
     // x_offset / n_local: the slab [x_offset, x_offset + n_local) of the table (hypercube sharding); default = whole table

@@ -95,8 +95,9 @@ template <int D> __global__ void k_soa_to_aos(const u64* __restrict__ soa, u64* 
 // dynamically.  tab_idx/tab_val: D rows x NNZ entries.  TIn = u64 (field elements) or int8_t (balanced digits).
 template <class Rg, class TIn> __global__ void __launch_bounds__(128)
 k_matrix_apply(const TIn* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t n,
-               const int* __restrict__ tab_idx, const u64* __restrict__ tab_val) {
+               const int* __restrict__ tab_idx, const u64* __restrict__ tab_val, size_t in_batch_stride, size_t out_batch_stride) {
     typedef typename Rg::F F; constexpr int D = Rg::D, NNZ = Rg::S;
+    in += (size_t)blockIdx.y * in_batch_stride; out += (size_t)blockIdx.y * out_batch_stride;      // blockIdx.y = vector of a batch
     __shared__ u64 s_in[D][128];
     __shared__ int s_idx[D * NNZ]; __shared__ u64 s_val[D * NNZ];
     for (int i = threadIdx.x; i < D * NNZ; i += blockDim.x) { s_idx[i] = tab_idx[i]; s_val[i] = tab_val[i]; }
@@ -150,8 +151,9 @@ template <class Rg> __global__ void k_digits_to_field(const int8_t* __restrict__
 }
 // gadget_recompose(B, L): out[i] = sum_l in[i*L + l] * B^l, limb-wise (B is an integer scalar; arith.rs:305,330)
 template <class Rg> __global__ void k_gadget_recompose(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch,
-                                                       size_t n_out, u64 Bmod, int L) {
+                                                       size_t n_out, u64 Bmod, int L, size_t in_batch_stride, size_t out_batch_stride) {
     typedef typename Rg::F F;
+    in += (size_t)blockIdx.y * in_batch_stride; out += (size_t)blockIdx.y * out_batch_stride;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_out * Rg::D) return;
     size_t i = t % n_out; int c = (int)(t / n_out);
@@ -297,10 +299,13 @@ k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride,
 template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, const u32* __restrict__ col, const u64* __restrict__ val, size_t val_pitch,
                                            const u64* __restrict__ z_head, size_t head_len, size_t head_pitch,
                                            const u64* __restrict__ z_tail, size_t tail_pitch, size_t tail_chunk, size_t tail_chunk_stride,
-                                           u64* __restrict__ out, size_t out_pitch, size_t nrows) {
+                                           u64* __restrict__ out, size_t out_pitch, size_t nrows,
+                                           size_t head_batch_stride, size_t tail_batch_stride, size_t out_batch_stride) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
     if (row >= nrows) return;
+    // blockIdx.z = which z vector of a batch (the K pieces of one decomposition share the matrix)
+    z_head += (size_t)blockIdx.z * head_batch_stride; z_tail += (size_t)blockIdx.z * tail_batch_stride; out += (size_t)blockIdx.z * out_batch_stride;
     Acc192 acc[TAU];
 #pragma unroll
     for (int l = 0; l < TAU; ++l) acc[l].clear();

@@ -55,9 +55,10 @@ void lf_ctx_destroy(lf_ctx* c) {
     cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
     if (c->nccl) NcclApi::get().CommDestroy(c->nccl);
     for (auto& kv : c->block_size) cudaFree(kv.first);
-    for (int i = 0; i < 2; ++i) { cudaFree(c->d_tab_idx[i]); cudaFree(c->d_tab_val[i]); }
+    if (!c->shared_tables) for (int i = 0; i < 2; ++i) { cudaFree(c->d_tab_idx[i]); cudaFree(c->d_tab_val[i]); }
     cudaFree(c->d_err); cudaFree(c->d_small); cudaFree(c->d_partial); if (c->h_pinned) cudaFreeHost(c->h_pinned); if (c->h_arena) cudaFreeHost(c->h_arena);
-    delete (RingTables<G>*)c->tables; cudaStreamDestroy(c->stream); delete c;
+    if (!c->shared_tables) delete (RingTables<G>*)c->tables;
+    cudaStreamDestroy(c->stream); delete c;
 }
 lf_status lf_ctx_sync(lf_ctx* c) { return guard(c, [&] { LF_CUDA(cudaStreamSynchronize(c->stream)); }); }
 void* lf_ctx_stream(lf_ctx* c) { return (void*)c->stream; }
@@ -323,7 +324,7 @@ lf_status lf_prover_create(lf_ctx* c, const lf_problem* sh, lf_prover** out) {
         *out = p.release();
     });
 }
-void lf_prover_free(lf_prover* p) { if (!p) return; for (auto* m : p->M) lf_sparse_free(p->ctx, m); lf_ajtai_free(p->ctx, p->A); delete p; }
+void lf_prover_free(lf_prover* p) { if (!p) return; if (p->aux) lf_ctx_destroy(p->aux); for (auto* m : p->M) lf_sparse_free(p->ctx, m); lf_ajtai_free(p->ctx, p->A); delete p; }
 lf_status lf_prover_upload_witness(lf_prover* p, const uint64_t* f_host, lf_witness** out) { *out = nullptr; return guard(p->ctx, [&] { Prover<G> pr(p); *out = pr.upload_witness(f_host); }); }
 void lf_witness_free(lf_prover* p, lf_witness* w) { Prover<G> pr(p); pr.free_witness(w); }
 lf_status lf_witness_download_f(lf_prover* p, const lf_witness* w, uint64_t* f_host) { return guard(p->ctx, [&] { Eng E(p->ctx); E.download_planes(w->f, w->pitch, w->n, f_host); }); }

@@ -16,6 +16,7 @@ struct lf_witness { lf::u64 *f = nullptr, *f_coeff = nullptr, *w_ccs = nullptr; 
 
 struct lf_prover {
     lf_ctx* ctx = nullptr;
+    lf_ctx* aux = nullptr;         // second stream + scratch: the accumulator's decomposition runs beside the linearization
     int ring = 0, L = 0, K = 0; uint64_t B = 0, b = 0;
     size_t kappa = 0, n = 0;
     size_t m = 0, n_ccs = 0, l = 0, t = 0, q = 0, d = 0, s = 0;
@@ -99,6 +100,18 @@ template <class Rg> struct Prover {
             E.spmv(P->M[j], d_head, hl, hp, tail, tail_pitch, z.p + ((size_t)k * P->t + j) * z.stride, z.pitch, P->M[j]->eff_rows, tail_chunk, tail_chunk_stride);
         }
         E.dfree(d_head);
+    }
+    // the K pieces of one decomposition against every CCS matrix: t launches (blockIdx.z = piece) instead of K * t
+    void compute_mz_batch(MzSet& z, int k0, int K, const std::vector<HV>& heads, const u64* tail, size_t tail_pitch, size_t tail_piece_stride, size_t tail_len, size_t tail_chunk, size_t tail_chunk_stride) {
+        const size_t hl = cnt(heads[0]), hp = pitch_of(hl);
+        u64* d_heads = E.template dalloc<u64>((size_t)K * hp * D);
+        for (int k = 0; k < K; ++k) { if (cnt(heads[k]) != hl) throw LfException(LF_ERR_INCORRECT_LENGTH, "IncorrectLength"); E.upload_small(heads[k].data(), hl, d_heads + (size_t)k * hp * D, hp); }
+        for (size_t j = 0; j < P->t; ++j) {
+            if (P->M[j]->ncols != hl + tail_len) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "LengthsNotEqual(M, z)");
+            E.spmv(P->M[j], d_heads, hl, hp, tail, tail_pitch, z.p + ((size_t)k0 * P->t + j) * z.stride, z.pitch, P->M[j]->eff_rows, tail_chunk, tail_chunk_stride,
+                   K, hp * D, tail_piece_stride, P->t * z.stride);
+        }
+        E.dfree(d_heads);
     }
     // all-gather `count` consecutive per-piece w_ccs slabs (each wc_stride words) of every rank: returns [world][count][D][pitch]
     u64* gather_wccs(const u64* local, size_t words) {
@@ -221,10 +234,8 @@ template <class Rg> struct Prover {
         if (cnt(cm.cm) != kappa) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongCommitmentLength");
         // decompose_witness: f_coeff.decompose_to_vec(b, K).transpose() (decomposition.rs:162-167), then CRT and recompose per piece (arith.rs:324-338)
         E.digit_split(w->f_coeff, w->pitch, dig, sb.dig_pitch, n, P->b, K);
-        for (int k = 0; k < K; ++k) {
-            E.crt_digits(dig + (size_t)k * sb.dig_stride, sb.dig_pitch, pieces + (size_t)k * sb.pc_stride, sb.pc_pitch, n);
-            E.gadget_recompose(pieces + (size_t)k * sb.pc_stride, sb.pc_pitch, wccs + (size_t)k * sb.wc_stride, sb.wc_pitch, w->W, P->B, P->L);
-        }
+        E.crt_digits(dig, sb.dig_pitch, pieces, sb.pc_pitch, n, K, sb.dig_stride, sb.pc_stride);                       // all K pieces, one launch each
+        E.gadget_recompose(pieces, sb.pc_pitch, wccs, sb.wc_pitch, w->W, P->B, P->L, K, sb.pc_stride, sb.wc_stride);
         mark("dec.split_crt");
         o.x_s = compute_x_s(cm);
         mark("dec.x_s");
@@ -243,7 +254,7 @@ template <class Rg> struct Prover {
         mark("dec.v_s");
         // compute_mz_mles / compute_u_s (decomposition.rs:214-256): z_k = x_s[k] || w_ccs_k
         { const size_t words = (size_t)K * sb.wc_stride; u64* all = gather_wccs(wccs, words);     // one all-gather per decomposition
-          for (int k = 0; k < K; ++k) compute_mz(sb.mz, half * K + k, o.x_s[k], all + (size_t)k * sb.wc_stride, sb.wc_pitch, w->W * world(), w->W, words);
+          compute_mz_batch(sb.mz, half * K, K, o.x_s, all, sb.wc_pitch, sb.wc_stride, w->W * world(), w->W, words);
           if (all != wccs) E.dfree(all); }
         o.u_pin = eval_mz_async(sb.mz, half * K * (int)P->t, K * (int)P->t, eq_r);
         mark("dec.mz_u_s");
@@ -376,6 +387,15 @@ template <class Rg> struct Prover {
         return o;
     }
 
+    lf_ctx* aux_ctx() {
+        if (P->aux) return P->aux;
+        lf_ctx* m = P->ctx; std::unique_ptr<lf_ctx> a(new lf_ctx);
+        a->ring = m->ring; a->device = m->device; a->tables = m->tables; a->shared_tables = true;
+        for (int i = 0; i < 2; ++i) { a->d_tab_idx[i] = m->d_tab_idx[i]; a->d_tab_val[i] = m->d_tab_val[i]; }
+        LF_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
+        LF_CUDA(cudaMalloc(&a->d_err, sizeof(int))); LF_CUDA(cudaMemset(a->d_err, 0, sizeof(int)));
+        P->aux = a.release(); return P->aux;
+    }
     // ------------------------------------------------------------------ NIFSProver::prove (nifs.rs:48-103)
     static void put(u64*& p, const HV& v) { std::memcpy(p, v.data(), 8 * v.size()); p += v.size(); }
     static void put_lcccs(u64* p, const LCCCS& L) { put(p, L.r); put(p, L.v); put(p, L.cm); put(p, L.u); put(p, L.x_w); put(p, L.h); }
@@ -398,11 +418,8 @@ template <class Rg> struct Prover {
         T.absorb_slice(acc.r.data(), cnt(acc.r)); T.absorb_slice(acc.v.data(), cnt(acc.v)); T.absorb_slice(acc.cm.data(), cnt(acc.cm));
         T.absorb_slice(acc.u.data(), cnt(acc.u)); T.absorb_slice(acc.x_w.data(), cnt(acc.x_w)); T.absorb(acc.h.data());
         T.absorb_tag("cm_i"); T.absorb_slice(cm_i_cm.data(), cnt(cm_i_cm)); T.absorb_slice(x_ccs.data(), cnt(x_ccs));
-        auto t0 = clk::now();
-        mark("absorb_public_input");
-        LinOut lin = linearize(cm_i_cm, x_ccs, w_i, T);
-        mark("linearize");
-        E.sync(); auto t1 = clk::now(); P->timings[0] = ms(t0, t1);
+        // Schedule: the accumulator's decomposition depends on nothing the transcript produces, so its device half is
+        // queued first on the auxiliary stream and runs beside the (latency-bound, host-paced) linearization sumcheck.
         StepBuffers sb;
         sb.dig_pitch = (std::max(n, ml()) + 255) / 256 * 256;   // the sumcheck walks all 2^s entries
         sb.dig_stride = sb.dig_pitch * D; sb.dig = E.template dalloc<int8_t>((size_t)2 * K * sb.dig_stride);
@@ -410,15 +427,40 @@ template <class Rg> struct Prover {
         sb.pc_pitch = pitch_of(n); sb.pc_stride = sb.pc_pitch * D; sb.pieces = E.template dalloc<u64>((size_t)2 * K * sb.pc_stride);
         sb.wc_pitch = pitch_of(w_i->W); sb.wc_stride = sb.wc_pitch * D; sb.wccs = E.template dalloc<u64>((size_t)2 * K * sb.wc_stride);
         sb.mz = alloc_mz(2 * K);
-        DevVec eq_acc = eq_table(acc.r);
-        mark("alloc");
-        // both device halves are queued back to back; the host absorbs the first decomposition while the GPU runs the second
-        DecPending pl = decompose_enqueue(acc, w_acc, eq_acc, sb, 0);
+        DevVec eq_acc; eq_acc.n = ((size_t)1 << cnt(acc.r)) / world(); eq_acc.pitch = pitch_of(eq_acc.n); eq_acc.p = E.template dalloc<u64>(eq_acc.pitch * D);
+        const bool overlap = world() == 1 && !P->detail && !std::getenv("LF_NO_OVERLAP");
+        DecPending pl;
+        {
+            lf_ctx* main_ctx = E.c;
+            if (overlap) {
+                lf_ctx* aux = aux_ctx();
+                cudaEvent_t ready; LF_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)); LF_CUDA(cudaEventRecord(ready, main_ctx->stream));
+                LF_CUDA(cudaStreamWaitEvent(aux->stream, ready, 0)); cudaEventDestroy(ready);
+                aux->arena_off = 0; aux->profiling = main_ctx->profiling;
+                E.c = aux;
+            }
+            try {
+                E.eq_table(acc.r.data(), (int)cnt(acc.r), eq_acc.p, eq_acc.pitch, (size_t)rank() * eq_acc.n, eq_acc.n);
+                pl = decompose_enqueue(acc, w_acc, eq_acc, sb, 0);
+            } catch (...) { E.c = main_ctx; throw; }
+            E.c = main_ctx;
+        }
+        mark("alloc+dec_acc_enqueue");
+        auto t0 = clk::now();
+        LinOut lin = linearize(cm_i_cm, x_ccs, w_i, T);
+        mark("linearize");
+        E.sync(); auto t1 = clk::now(); P->timings[0] = ms(t0, t1);
         DecPending prr = decompose_enqueue(lin.lc, w_i, lin.eq_r, sb, 1);
         DecOut dl = decompose_finish(pl, T);
         mark("decompose_acc");
         DecOut dr = decompose_finish(prr, T);
         mark("decompose_new");
+        if (P->aux) {      // fold the auxiliary context's bookkeeping (launch count, event pairs, digit-overflow flag) into the main one
+            lf_ctx* m = E.c; lf_ctx* a = P->aux;
+            m->launches += a->launches; a->launches = 0;
+            for (auto& r : a->prof) m->prof.push_back(r); a->prof.clear();
+            E.c = a; try { E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_witness: a coefficient does not fit K digits of base b"); } catch (...) { E.c = m; throw; } E.c = m;
+        }
         E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_witness: a coefficient does not fit K digits of base b");
         E.sync(); auto t2 = clk::now(); P->timings[1] = ms(t1, t2);
         std::vector<LCCCS> lcs = dl.lc; lcs.insert(lcs.end(), dr.lc.begin(), dr.lc.end());
