@@ -81,7 +81,7 @@ namespace lf {
 
 template <class Rg> struct Engine {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef HostRing<Rg> HR; typedef typename HR::El El;
-    static constexpr int D = Rg::D, S = Rg::S, TAU = Rg::TAU;
+    static constexpr int D = Rg::D, S = Rg::S, TAU = Rg::TAU, TPB_MA = matrix_apply_tpb<Rg>();
     lf_ctx* c;
     explicit Engine(lf_ctx* ctx) : c(ctx) {}
     const RingTables<Rg>& tab() const { return *(const RingTables<Rg>*)c->tables; }
@@ -181,7 +181,7 @@ template <class Rg> struct Engine {
     void allreduce_field(u64* dev, size_t words) {
         if (!sharded() || !words) return;
         u64* tmp = dalloc<u64>(2 * words);
-        launch("k_split_limbs", [&] { k_split_limbs<<<blocks_for(words), 256, 0, st()>>>(dev, tmp, words); });
+        launch("k_split_limbs", [&] { k_split_limbs<0><<<blocks_for(words), 256, 0, st()>>>(dev, tmp, words); });
         collective(0, tmp, 2 * words);
         launch("k_combine_limbs", [&] { k_combine_limbs<F><<<blocks_for(words), 256, 0, st()>>>(tmp, dev, words); });
         dfree(tmp);
@@ -206,12 +206,12 @@ template <class Rg> struct Engine {
     // ---------------------------------------------------------------- elementwise ops
     void crt(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, bool inverse) {
         if (!n) return;
-        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, u64><<<(unsigned)((n + 127) / 128), 128, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[inverse], c->d_tab_val[inverse], 0, 0); });
+        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, u64><<<(unsigned)((n + TPB_MA - 1) / TPB_MA), TPB_MA, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[inverse], c->d_tab_val[inverse], 0, 0); });
     }
     // CRT of `batch` digit vectors (in/out strides between consecutive vectors) in one launch
     void crt_digits(const int8_t* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, int batch = 1, size_t in_stride = 0, size_t out_stride = 0) {
         if (!n || !batch) return;
-        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, int8_t><<<dim3((unsigned)((n + 127) / 128), batch), 128, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[0], c->d_tab_val[0], in_stride, out_stride); });
+        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, int8_t><<<dim3((unsigned)((n + TPB_MA - 1) / TPB_MA), batch), TPB_MA, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[0], c->d_tab_val[0], in_stride, out_stride); });
     }
     static unsigned blocks_for(size_t work, int bs = 256) { return (unsigned)((work + bs - 1) / bs); }
     void gadget_decompose(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, u64 B, int L) {

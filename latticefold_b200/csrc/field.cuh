@@ -11,9 +11,11 @@
 #if defined(__CUDACC__)
 #define LF_HD __host__ __device__ __forceinline__
 #define LF_D __device__ __forceinline__
+#define LF_HD_CALL __host__ __device__ __noinline__      // real calls: keeps the generic (parity-only) rings' code size and build time sane
 #else
 #define LF_HD inline
 #define LF_D inline
+#define LF_HD_CALL __attribute__((noinline))
 #endif
 
 namespace lf {
@@ -96,6 +98,8 @@ struct Goldilocks {
     static constexpr u64 P = 0xFFFFFFFF00000001ULL;
     static constexpr u64 EPS = 0xFFFFFFFFULL;  // 2^64 mod p
     static constexpr int NU_SHIFT = 40;        // nu = 2^40 (a primitive 24th root of unity)
+    static constexpr u64 NU = (u64)1 << NU_SHIFT;
+    typedef Acc192 Acc;
 
     // host builds use mask arithmetic: the comparisons are data dependent coin flips and a mispredicted branch costs more
     // than the whole reduction (the Poseidon transcript runs ~10^7 of these per prover step)
@@ -140,12 +144,43 @@ struct Goldilocks {
         u64 w0, w1; u32 w2; a.words(w0, w1, w2);
         return sub(reduce128(w0, w1), (u64)w2 << 32);
     }
+    static LF_HD u64 reduce(const Acc192& a) { return reduce192(a); }
     static LF_HD u64 mul_nu(u64 a) { return reduce128(a << NU_SHIFT, a >> (64 - NU_SHIFT)); }
+    // (lo + hi * 2^32) mod p for lo, hi < 2^40: recombination of the split-limb all-reduce
+    static LF_HD u64 from_split(u64 lo, u64 hi) { return add(reduce128(lo, 0), reduce128(hi << 32, hi >> 32)); }
+    // (lo + hi * 2^64) mod p for 128-bit lo, hi < 2^72 (host: sums of products in the Poseidon layers)
+    static inline u64 reduce_wide(u128 lo, u128 hi) { u128 t = hi + (u64)(lo >> 64); return sub(reduce128((u64)lo, (u64)t), (u64)(t >> 64) << 32); }
     static LF_HD u64 from_i64(int64_t v) { return v >= 0 ? (u64)v : P - (u64)(-v); }   // |v| < p
     static LF_HD int64_t to_signed(u64 a) { return a <= (P - 1) / 2 ? (int64_t)a : -(int64_t)(P - a); }
     static inline u64 pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = mul(r, a); a = mul(a, a); e >>= 1; } return r; }
     static inline u64 inv(u64 a) { return pow(a, P - 2); }
 };
+
+// Generic prime field for the reference's other rings (BabyBear p = 15*2^27+1, Frog p = 15912092521325583641): plain
+// `%`-based arithmetic with an eagerly reduced accumulator.  These rings are carried for parity, not tuned: the headline
+// workload is Goldilocks.  SMALL: p < 2^32, products fit in 64 bits; otherwise 128-bit intermediates.
+template <u64 P_, u64 NU_, bool SMALL> struct ModField {
+    static constexpr u64 P = P_, NU = NU_;
+    static LF_HD u64 add(u64 a, u64 b) { u64 s = a + b; if (s < a || s >= P) s -= P; return s; }
+    static LF_HD u64 sub(u64 a, u64 b) { return a >= b ? a - b : a + (P - b); }
+    static LF_HD u64 neg(u64 a) { return a ? P - a : 0; }
+    static LF_HD_CALL u64 mul(u64 a, u64 b) { if (SMALL) return (a * b) % P; return (u64)(((u128)a * b) % P); }
+    static LF_HD u64 sqr(u64 a) { return mul(a, a); }
+    static LF_HD u64 mul_nu(u64 a) { return mul(a, NU); }
+    struct Acc { u64 v; LF_HD void clear() { v = 0; } LF_HD void mac(u64 a, u64 b) { v = ModField::add(v, ModField::mul(a, b)); } LF_HD void add(u64 a) { v = ModField::add(v, a % P); } };
+    static LF_HD u64 reduce(const Acc& a) { return a.v; }
+    static LF_HD_CALL u64 reduce128(u64 lo, u64 hi) { return (u64)((((u128)hi << 64) | lo) % P); }
+    static LF_HD_CALL u64 from_split(u64 lo, u64 hi) { return (u64)((((u128)hi << 32) + lo) % P); }
+    static inline u64 reduce_wide(u128 lo, u128 hi) { u128 t = ((hi % P) * (((u128)1 << 64) % P)) % P; return (u64)((t + lo % P) % P); }
+    static LF_HD u64 from_i64(int64_t v) { return v >= 0 ? (u64)v % P : (P - ((u64)(-v) % P)) % P; }
+    static LF_HD int64_t to_signed(u64 a) { return a <= (P - 1) / 2 ? (int64_t)a : -(int64_t)(P - a); }
+    static inline u64 pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = mul(r, a); a = mul(a, a); e >>= 1; } return r; }
+    static inline u64 inv(u64 a) { return pow(a, P - 2); }
+};
+// nu = the primitive g-th root of unity h^((p-1)/g) for the smallest h of exact order g (same rule as the oracle's
+// find_nu; this convention is "unpinned"): 1398021245 for BabyBear (g = 24), 2755067726615789629 for Frog (g = 8)
+typedef ModField<2013265921ULL, 1398021245ULL, true> BabyBear;
+typedef ModField<15912092521325583641ULL, 2755067726615789629ULL, false> FrogField;
 
 // ---------------------------------------------------------------------------------------------------------------
 // Ring descriptor: slot field Fq[Y]/(Y^TAU - nu).  Rg::F is the base field.
@@ -156,9 +191,51 @@ struct GoldilocksRing {
     static constexpr int CS_BYTES = 18;
 };
 
-// c = a * b in the slot field (fully reduced operands and result).  TAU = 3 specialisation keeps everything in
-// registers; products of one output limb are summed in a 192-bit accumulator and reduced once.
-template <class Rg> struct SlotField;
+struct BabyBearRing {      // Z_p[X]/(X^72 - X^36 + 1), 8 slots of Fq9   (crates/cyclotomic-rings/src/rings/babybear.rs:9-20)
+    typedef BabyBear F;
+    static constexpr int ID = 1, D = 72, S = 8, TAU = 9, G = 24;
+    static constexpr bool TRINOMIAL = true;
+    static constexpr int CS_BYTES = 18;
+};
+struct FrogRing {          // Z_p[X]/(X^16 + 1), 4 slots of Fq4           (crates/cyclotomic-rings/src/rings/frog.rs:9-20)
+    typedef FrogField F;
+    static constexpr int ID = 2, D = 16, S = 4, TAU = 4, G = 8;
+    static constexpr bool TRINOMIAL = false;
+    static constexpr int CS_BYTES = 16;
+};
+
+// c = a * b in the slot field Fq[Y]/(Y^TAU - nu) (fully reduced operands and result).  Generic form for any TAU;
+// the Goldilocks TAU = 3 specialisation below keeps everything in registers with lazily reduced 192-bit sums.
+template <class Rg> struct SlotField {
+    typedef typename Rg::F F;
+    static constexpr int TAU = Rg::TAU;
+    struct Prepped { u64 b[Rg::TAU], bn[Rg::TAU]; };      // b and nu * b
+    static LF_HD_CALL Prepped prep(const u64* b) { Prepped p;
+#pragma unroll
+        for (int i = 0; i < TAU; ++i) { p.b[i] = b[i]; p.bn[i] = F::mul_nu(b[i]); } return p; }
+    // acc[k] += sum_{i+j=k} a_i b_j + nu sum_{i+j=k+TAU} a_i b_j
+    static LF_HD_CALL void mac(typename F::Acc* acc, const u64* a, const Prepped& p) {
+        for (int k = 0; k < TAU; ++k)
+            for (int i = 0; i < TAU; ++i) { if (i <= k) acc[k].mac(a[i], p.b[k - i]); else acc[k].mac(a[i], p.bn[k + TAU - i]); }
+    }
+    static LF_HD_CALL void mul(u64* c, const u64* a, const u64* b) {
+        const Prepped p = prep(b); typename F::Acc acc[Rg::TAU];
+#pragma unroll
+        for (int k = 0; k < TAU; ++k) acc[k].clear();
+        mac(acc, a, p);
+#pragma unroll
+        for (int k = 0; k < TAU; ++k) c[k] = F::reduce(acc[k]);
+    }
+    static LF_HD_CALL void sqr(u64* c, const u64* a) { u64 t[Rg::TAU];
+#pragma unroll
+        for (int k = 0; k < TAU; ++k) t[k] = a[k]; mul(c, a, t); }
+    static LF_HD void add(u64* c, const u64* a, const u64* b) {
+#pragma unroll
+        for (int i = 0; i < TAU; ++i) c[i] = F::add(a[i], b[i]); }
+    static LF_HD void sub(u64* c, const u64* a, const u64* b) {
+#pragma unroll
+        for (int i = 0; i < TAU; ++i) c[i] = F::sub(a[i], b[i]); }
+};
 
 template <> struct SlotField<GoldilocksRing> {
     typedef Goldilocks F;

@@ -11,7 +11,7 @@
 namespace lf {
 
 constexpr int MAX_LIST = 32;          // pointer-list capacity of one launch (pieces, MLEs, ...)
-constexpr int MAX_MU = 128;           // 2K * tau
+constexpr int MAX_MU = 320;           // 2K * tau (K = 16 on the BabyBear ring: 288)
 constexpr int SC_MAX_MLES = 8, SC_MAX_TERMS = 4, SC_MAX_FACTORS = 4, SC_MAX_DEG = 7;
 
 struct PtrList { const u64* p[MAX_LIST]; size_t len[MAX_LIST]; };
@@ -57,17 +57,17 @@ template <class F> __global__ void k_reduce_partials(const u64* __restrict__ par
 // ------------------------------------------------------------------------------------------------ multi-GPU helpers
 // NCCL has no "sum mod p": a field element is sent as two 32-bit halves in u64 lanes, summed with ncclSum (world * 2^32
 // cannot wrap) and folded back mod p.  Bit-exact because integer addition is associative.
-__global__ void k_split_limbs(const u64* __restrict__ in, u64* __restrict__ out, size_t words) {
+template <int = 0> __global__ void k_split_limbs(const u64* __restrict__ in, u64* __restrict__ out, size_t words) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < words) { const u64 v = in[i]; out[2 * i] = v & 0xFFFFFFFFULL; out[2 * i + 1] = v >> 32; }
 }
 template <class F> __global__ void k_combine_limbs(const u64* __restrict__ in, u64* __restrict__ out, size_t words) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < words) { const u64 lo = in[2 * i], hi = in[2 * i + 1];        // each < world * 2^32
-        out[i] = F::add(F::reduce128(lo, 0), F::reduce128(hi << 32, hi >> 32)); }
+        out[i] = F::from_split(lo, hi); }
 }
 // entry 0 of every (table, plane) -> column `rank` of a zeroed [rows][pitch_out] buffer (all-gather by summation)
-__global__ void k_scatter_entry(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t rows, int rank) {
+template <int = 0> __global__ void k_scatter_entry(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t rows, int rank) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows) out[i * out_pitch + rank] = in[i * in_pitch];
 }
@@ -93,12 +93,13 @@ template <int D> __global__ void k_soa_to_aos(const u64* __restrict__ soa, u64* 
 // CRT::elementwise_crt / ICRT::elementwise_icrt (reference call sites arith.rs:232,238,300,327).  One thread per element;
 // the D input limbs are staged in shared memory ([limb][thread], conflict free) because the sparse table indexes them
 // dynamically.  tab_idx/tab_val: D rows x NNZ entries.  TIn = u64 (field elements) or int8_t (balanced digits).
+template <class Rg> constexpr int matrix_apply_tpb() { return Rg::D > 32 ? 64 : 128; }      // [D][tpb] u64 staging must fit 48 KB
 template <class Rg, class TIn> __global__ void __launch_bounds__(128)
 k_matrix_apply(const TIn* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t n,
                const int* __restrict__ tab_idx, const u64* __restrict__ tab_val, size_t in_batch_stride, size_t out_batch_stride) {
     typedef typename Rg::F F; constexpr int D = Rg::D, NNZ = Rg::S;
     in += (size_t)blockIdx.y * in_batch_stride; out += (size_t)blockIdx.y * out_batch_stride;      // blockIdx.y = vector of a batch
-    __shared__ u64 s_in[D][128];
+    __shared__ u64 s_in[D][matrix_apply_tpb<Rg>()];
     __shared__ int s_idx[D * NNZ]; __shared__ u64 s_val[D * NNZ];
     for (int i = threadIdx.x; i < D * NNZ; i += blockDim.x) { s_idx[i] = tab_idx[i]; s_val[i] = tab_val[i]; }
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,10 +114,10 @@ k_matrix_apply(const TIn* __restrict__ in, size_t in_pitch, u64* __restrict__ ou
     if (e >= n) return;
 #pragma unroll 4
     for (int r = 0; r < D; ++r) {
-        Acc192 a; a.clear();
+        typename F::Acc a; a.clear();
 #pragma unroll
         for (int c = 0; c < NNZ; ++c) a.mac(s_val[r * NNZ + c], s_in[s_idx[r * NNZ + c]][threadIdx.x]);
-        out[(size_t)r * out_pitch + e] = F::reduce192(a);
+        out[(size_t)r * out_pitch + e] = F::reduce(a);
     }
 }
 
@@ -178,7 +179,7 @@ template <class Rg> __global__ void k_fhat(const u64* __restrict__ in, size_t in
 // (column tile fastest) over the SAME x range, so a row is fetched from L2 once per block and re-served from L1 to the
 // warps that share it, and likewise for the column vectors.  grid = (unit groups, x tiles, slots); blocks that share an
 // x tile are adjacent in launch order, which keeps HBM traffic at one pass over X and Y (ncu: 2.1 GB for the 2.06 GB
-// algorithmic at kappa=26, n=2^18, 15 pieces).  Accumulators are lazily reduced (Acc192): the inner loop is
+// algorithmic at kappa=26, n=2^18, 15 pieces).  Accumulators are lazily reduced (F::Acc): the inner loop is
 // 9 * CT 64-bit multiply-accumulates per x with no modular reduction and no branch.
 struct DotArgs {
     const u64* X; size_t x_row_stride, x_pitch; int nrows;    // rows: X + r * x_row_stride
@@ -201,7 +202,7 @@ k_dot(const DotArgs a) {
     const u64* yp[CT]; size_t ylen[CT];
 #pragma unroll
     for (int j = 0; j < CT; ++j) { const int c = min(c0 + j, a.ncols - 1); yp[j] = a.Y.p[c] + (size_t)(slot * TAU) * a.y_pitch; ylen[j] = (c0 + j < a.ncols) ? a.Y.len[c] : 0; }
-    Acc192 acc[CT][TAU];
+    typename F::Acc acc[CT][TAU];
 #pragma unroll
     for (int j = 0; j < CT; ++j)
 #pragma unroll
@@ -243,7 +244,7 @@ k_dot(const DotArgs a) {
     for (int j = 0; j < CT; ++j)
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
-            u64 v = F::reduce192(acc[j][l]);
+            u64 v = F::reduce(acc[j][l]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v = F::add(v, __shfl_down_sync(0xffffffffu, v, o));
             if (lane == 0 && c0 + j < a.ncols) a.partial[(((size_t)blockIdx.y * a.nrows + row) * a.ncols + (c0 + j)) * Rg::D + slot * TAU + l] = v;
@@ -260,7 +261,7 @@ k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride,
     __shared__ u64 red[TAU * TAU * 32];
     const int slot = blockIdx.y, vec = blockIdx.z;
     const TIn* cv = coeff + (size_t)vec * c_vec_stride;
-    Acc192 acc[TAU][TAU];
+    typename F::Acc acc[TAU][TAU];
 #pragma unroll
     for (int j = 0; j < TAU; ++j)
 #pragma unroll
@@ -283,7 +284,7 @@ k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride,
 #pragma unroll
     for (int j = 0; j < TAU; ++j)
 #pragma unroll
-        for (int l = 0; l < TAU; ++l) v[j * TAU + l] = F::reduce192(acc[j][l]);
+        for (int l = 0; l < TAU; ++l) v[j * TAU + l] = F::reduce(acc[j][l]);
     block_reduce_add<F, TAU * TAU>(v, red);
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -306,7 +307,7 @@ template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, cons
     if (row >= nrows) return;
     // blockIdx.z = which z vector of a batch (the K pieces of one decomposition share the matrix)
     z_head += (size_t)blockIdx.z * head_batch_stride; z_tail += (size_t)blockIdx.z * tail_batch_stride; out += (size_t)blockIdx.z * out_batch_stride;
-    Acc192 acc[TAU];
+    typename F::Acc acc[TAU];
 #pragma unroll
     for (int l = 0; l < TAU; ++l) acc[l].clear();
     for (u32 e = row_ptr[row]; e < row_ptr[row + 1]; ++e) {
@@ -322,7 +323,7 @@ template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, cons
         SF::mac(acc, v, SF::prep(z));
     }
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + row] = F::reduce192(acc[l]);
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + row] = F::reduce(acc[l]);
 }
 
 // ------------------------------------------------------------------------------------------------ K8 eq table
@@ -374,7 +375,7 @@ template <class Rg> __global__ void k_lincomb(const PtrList vecs, size_t v_pitch
     __syncthreads();
     size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n) return;
-    Acc192 acc[TAU];
+    typename F::Acc acc[TAU];
 #pragma unroll
     for (int l = 0; l < TAU; ++l) { acc[l].clear(); if (accumulate) acc[l].add(out[(size_t)(slot * TAU + l) * out_pitch + x]); }
     for (int i = 0; i < count; ++i) {
@@ -385,7 +386,7 @@ template <class Rg> __global__ void k_lincomb(const PtrList vecs, size_t v_pitch
         SF::mac(acc, v, s_c[i]);
     }
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = F::reduce192(acc[l]);
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = F::reduce(acc[l]);
 }
 // out[x][slot] (+)= sum_k sum_j w[k][j] * digit_k[x][j*S + slot]     (prepare_g1_and_3_k_mles_list, folding/utils.rs:524-546:
 // the alpha-Horner combination of the f-hat MLEs, computed from the int8 digits).  w: K x TAU slot-field elements.
@@ -397,7 +398,7 @@ template <class Rg> __global__ void k_digit_lincomb(const int8_t* __restrict__ d
     __syncthreads();
     size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
     if (x >= n) return;
-    Acc192 acc[TAU];
+    typename F::Acc acc[TAU];
 #pragma unroll
     for (int l = 0; l < TAU; ++l) { acc[l].clear(); if (accumulate) acc[l].add(out[(size_t)(slot * TAU + l) * out_pitch + x]); }
     for (int k = 0; k < K; ++k)
@@ -408,14 +409,14 @@ template <class Rg> __global__ void k_digit_lincomb(const int8_t* __restrict__ d
             for (int l = 0; l < TAU; ++l) acc[l].mac(c, s_w[(k * TAU + j) * TAU + l]);
         }
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = F::reduce192(acc[l]);
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = F::reduce(acc[l]);
 }
 
 // ------------------------------------------------------------------------------------------------ K9 sumcheck
 // fix_variables on a list of tables (sumcheck/prover.rs:61-72): new[b] = old[2b] + r (old[2b+1] - old[2b]).
 // in/out may alias only through separate buffers (ping-pong).  r_sf: TAU limbs (slot-constant challenge).
 // grid = (b tiles, slots, tables)
-struct FoldArgs { const u64* in; u64* out; size_t in_pitch, out_pitch, in_stride, out_stride; size_t n_out; u64 r[8]; };
+struct FoldArgs { const u64* in; u64* out; size_t in_pitch, out_pitch, in_stride, out_stride; size_t n_out; u64 r[16]; };      // r: TAU limbs of the challenge (TAU <= 9)
 template <class Rg> __global__ void k_fold(const FoldArgs a) {
     typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
@@ -584,7 +585,7 @@ k_fold_sc_round1(const FoldScArgs a) {
 #pragma unroll
         for (int l = 0; l < TAU; ++l) h[e][l] = 0;
     if (active) {
-        Acc192 p2[TAU], n2[TAU], p3[TAU], n3[TAU];   // positive / negative parts of h(2), h(3)
+        typename F::Acc p2[TAU], n2[TAU], p3[TAU], n3[TAU];   // positive / negative parts of h(2), h(3)
 #pragma unroll
         for (int l = 0; l < TAU; ++l) { p2[l].clear(); n2[l].clear(); p3[l].clear(); n3[l].clear(); }
         const int K2 = a.n_f / TAU;
@@ -600,7 +601,7 @@ k_fold_sc_round1(const FoldScArgs a) {
             }
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
-            const u64 h2 = F::sub(F::reduce192(p2[l]), F::reduce192(n2[l])), h3 = F::sub(F::reduce192(p3[l]), F::reduce192(n3[l]));
+            const u64 h2 = F::sub(F::reduce(p2[l]), F::reduce(n2[l])), h3 = F::sub(F::reduce(p3[l]), F::reduce(n3[l]));
             h[2][l] = h2; h[3][l] = h3;
             // h(0) = h(1) = 0 and third differences constant: h(4) = 4 h(3) - 6 h(2)
             const u64 h3x2 = F::add(h3, h3), h3x4 = F::add(h3x2, h3x2), h2x2 = F::add(h2, h2), h2x6 = F::add(F::add(h2x2, h2x2), h2x2);
@@ -627,9 +628,9 @@ template <class Rg> __global__ void k_fold_digits(const int8_t* __restrict__ dig
 // so h(X) = A + 3X B + 3X^2 C + X^3 Dd + (X^3 - X) Es with five mu-weighted sums that stay lazily reduced over all 2K*tau
 // tables.  The sums are split over two thread sets (blockIdx.z): PART 0 carries {A, B, Es} and the v0 v1 + v2 v3 term,
 // PART 1 carries {C, Dd}; the round message is linear in them, so the two sets simply contribute separate partial sums.
-// Halving the live accumulators per thread (15 -> 9 / 6 Acc192) is what lets enough warps be resident to cover the
+// Halving the live accumulators per thread (15 -> 9 / 6 accumulators) is what lets enough warps be resident to cover the
 // IMAD / carry-chain latencies (ncu before the split: 211 registers, 12 % occupancy, issue slot busy 43 %).
-template <class Rg, int PART> __device__ __forceinline__ void fold_sc_round_part(const FoldScArgs& a, u64* red, const typename SlotField<Rg>::Prepped* s_mu) {
+template <class Rg, int PART> __device__ __forceinline__ void fold_sc_round_part(const FoldScArgs& a, u64* red, const u64* s_mu /* n_f x TAU */) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     const int slot = blockIdx.y;
     const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const bool active = b < a.n_pairs;
@@ -639,7 +640,7 @@ template <class Rg, int PART> __device__ __forceinline__ void fold_sc_round_part
 #pragma unroll
         for (int l = 0; l < TAU; ++l) h[e][l] = 0;
     if (active) {
-        Acc192 s0[TAU], s1[TAU], s2[TAU];      // PART 0: A, B, Es    PART 1: C, Dd, (unused)
+        typename F::Acc s0[TAU], s1[TAU], s2[TAU];      // PART 0: A, B, Es    PART 1: C, Dd, (unused)
 #pragma unroll
         for (int l = 0; l < TAU; ++l) { s0[l].clear(); s1[l].clear(); s2[l].clear(); }
 #pragma unroll 2
@@ -651,7 +652,7 @@ template <class Rg, int PART> __device__ __forceinline__ void fold_sc_round_part
                 u[l] = p.x; s[l] = F::sub(p.y, p.x);
             }
             u64 q[TAU], t[TAU];
-            const typename SF::Prepped mu = s_mu[kd];
+            const typename SF::Prepped mu = SF::prep(s_mu + kd * TAU);
             if (PART == 0) {
                 SF::sqr(q, u);
                 SF::mul(t, q, u); SF::sub(t, t, u); SF::mac(s0, t, mu);      // u^3 - u
@@ -666,9 +667,9 @@ template <class Rg, int PART> __device__ __forceinline__ void fold_sc_round_part
         auto mulc = [](u64 v, u64 c) { return F::mul(v, c); };
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
-            const u64 x0 = F::reduce192(s0[l]), x1 = F::reduce192(s1[l]);
+            const u64 x0 = F::reduce(s0[l]), x1 = F::reduce(s1[l]);
             if (PART == 0) {
-                const u64 Es = F::reduce192(s2[l]);
+                const u64 Es = F::reduce(s2[l]);
                 h[0][l] = x0;
                 h[1][l] = F::add(x0, mulc(x1, 3));
                 h[2][l] = F::add(F::add(x0, mulc(x1, 6)), mulc(Es, 6));
@@ -689,8 +690,8 @@ template <class Rg> __global__ void __launch_bounds__(128, 3)
 k_fold_sc_round(const FoldScArgs a) {
     typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     __shared__ u64 red[5 * TAU * 32];
-    __shared__ typename SF::Prepped s_mu[MAX_MU];
-    for (int i = threadIdx.x; i < a.n_f; i += blockDim.x) s_mu[i] = SF::prep(a.mu_pow + (size_t)i * TAU);
+    __shared__ u64 s_mu[MAX_MU * TAU];
+    for (int i = threadIdx.x; i < a.n_f * TAU; i += blockDim.x) s_mu[i] = a.mu_pow[i];
     __syncthreads();
     if (blockIdx.z == 0) fold_sc_round_part<Rg, 0>(a, red, s_mu); else fold_sc_round_part<Rg, 1>(a, red, s_mu);
 }

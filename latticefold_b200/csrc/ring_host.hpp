@@ -26,7 +26,7 @@ template <class Rg> struct RingTables {
     int icrt_idx[D][NNZ]; u64 icrt_val[D][NNZ];
 
     RingTables() {
-        nu = (u64)1 << F::NU_SHIFT;
+        nu = F::NU;
         int c = 0;
         for (int x = 1; x < Rg::G; ++x) { int a = x, b = Rg::G; while (b) { int t = a % b; a = b; b = t; } if (a == 1) k[c++] = x; }
         if (c != S) throw std::logic_error("slot count");
@@ -70,8 +70,8 @@ template <class Rg> struct HostRing {
     static El mul(const El& a, const El& b) { El c; for (int s = 0; s < S; ++s) SF::mul(&c[s * TAU], &a[s * TAU], &b[s * TAU]); return c; }   // NTT form
     static El scale(const El& a, u64 k) { El c; for (int i = 0; i < D; ++i) c[i] = F::mul(a[i], k); return c; }
     static bool is_zero(const El& a) { for (u64 v : a) if (v) return false; return true; }
-    El crt(const El& a) const { El o; for (int r = 0; r < D; ++r) { Acc192 x; x.clear(); for (int c = 0; c < T.NNZ; ++c) x.mac(T.crt_val[r][c], a[T.crt_idx[r][c]]); o[r] = F::reduce192(x); } return o; }
-    El icrt(const El& a) const { El o; for (int r = 0; r < D; ++r) { Acc192 x; x.clear(); for (int c = 0; c < T.NNZ; ++c) x.mac(T.icrt_val[r][c], a[T.icrt_idx[r][c]]); o[r] = F::reduce192(x); } return o; }
+    El crt(const El& a) const { El o; for (int r = 0; r < D; ++r) { typename F::Acc x; x.clear(); for (int c = 0; c < T.NNZ; ++c) x.mac(T.crt_val[r][c], a[T.crt_idx[r][c]]); o[r] = F::reduce(x); } return o; }
+    El icrt(const El& a) const { El o; for (int r = 0; r < D; ++r) { typename F::Acc x; x.clear(); for (int c = 0; c < T.NNZ; ++c) x.mac(T.icrt_val[r][c], a[T.icrt_idx[r][c]]); o[r] = F::reduce(x); } return o; }
     // multiply a coefficient-form element by X (Cyclotomic::into_rot_iter step, cyclotomic-rings/src/rotation.rs:60)
     static void mul_x(El& a) { u64 top = a[D - 1]; for (int i = D - 1; i > 0; --i) a[i] = a[i - 1]; a[0] = F::neg(top); if (Rg::TRINOMIAL) a[D / 2] = F::add(a[D / 2], top); }
 };

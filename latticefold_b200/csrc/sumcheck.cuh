@@ -110,7 +110,7 @@ template <class Rg> struct SumcheckDriver {
         const int G = E.c->world; const size_t np = pitch_of(G), rows = (size_t)g.count * D;
         u64* out = E.template dalloc<u64>(rows * np);
         LF_CUDA(cudaMemsetAsync(out, 0, rows * np * 8, E.st()));
-        E.launch("k_scatter_entry", [&] { k_scatter_entry<<<Engine<Rg>::blocks_for(rows), 256, 0, E.st()>>>(g.cur, g.pitch, out, np, rows, E.c->rank); });
+        E.launch("k_scatter_entry", [&] { k_scatter_entry<0><<<Engine<Rg>::blocks_for(rows), 256, 0, E.st()>>>(g.cur, g.pitch, out, np, rows, E.c->rank); });
         E.collective(0, out, rows * np);
         if (g.cur_owned && g.cur != g.nxt && g.cur != g.alt) E.dfree(g.cur);
         g.cur = out; g.cur_owned = true; g.pitch = np; g.stride = np * D;

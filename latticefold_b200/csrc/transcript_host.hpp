@@ -72,9 +72,7 @@ template <class Rg> class Transcript {
     static u64 dot(const u64* a, const u64* b) {
         u128 lo = 0, hi = 0;
         for (int j = 0; j < W; ++j) { u128 x = (u128)a[j] * b[j]; lo += (u64)x; hi += (u64)(x >> 64); }
-        u128 t = hi + (u64)(lo >> 64);                     // value = (u64)lo + t * 2^64, t < 2^70
-        u64 r = F::reduce128((u64)lo, (u64)t);
-        return F::sub(r, (u64)(t >> 64) << 32);            // 2^128 = -2^32 (mod p)
+        return F::reduce_wide(lo, hi);                     // (lo + hi * 2^64) mod p
     }
     void dense_layer(const u64* m) { u64 nx[W]; for (int i = 0; i < W; ++i) nx[i] = dot(m + i * W, st_); std::memcpy(st_, nx, sizeof st_); }
     void permute() {
@@ -141,8 +139,11 @@ public:
     }
     static void short_challenge_from_bytes(const uint8_t* bs, u64* coeffs) {
         std::memset(coeffs, 0, 8 * Rg::D);
-        static_assert(Rg::CS_BYTES == 18, "only the 6-bit challenge sets are implemented");
-        for (int i = 0; i < 6; ++i) {
+        if (Rg::CS_BYTES == 16) {      // frog.rs:32-56: 16 bytes -> byte - 128
+            for (int i = 0; i < 16; ++i) coeffs[i] = F::from_i64((int64_t)bs[i] - 128);
+            return;
+        }
+        for (int i = 0; i < 6; ++i) {  // goldilocks.rs:32-68 / babybear.rs:32-68: 18 bytes -> 24 six-bit values - 32
             const uint8_t b0 = bs[3 * i], b1 = bs[3 * i + 1], b2 = bs[3 * i + 2];
             int v[4] = {b0 & 0x3F, ((b0 >> 6) & 3) | ((b1 & 0x0F) << 2), ((b1 >> 4) & 0x0F) | ((b2 & 3) << 4), (b2 >> 2) & 0x3F};
             for (int j = 0; j < 4; ++j) coeffs[4 * i + j] = F::from_i64(v[j] - 32);

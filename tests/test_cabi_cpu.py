@@ -65,6 +65,23 @@ def test_no_cpu_fallback():
 
 
 def test_unsupported_ring_is_reported():
-    with pytest.raises(lf.LfError) as e:
-        lf.Transcript(synth.RING_FROG)
-    assert e.value.code == -8
+    h = api.vp()
+    rc = lf.lib().lf_transcript_create(3, api.C.byref(h))       # the Stark ring (256-bit field) is not implemented
+    assert rc == -8
+
+
+@pytest.mark.parametrize("ring", [synth.RING_GOLDILOCKS, synth.RING_BABYBEAR, synth.RING_FROG])
+def test_product_host_side_matches_oracle_all_rings(oracle, ring):
+    """transcript (incl. the ring's short-challenge set) and RotSum of the product's host code vs the oracle"""
+    R = synth.RINGS[ring]; d, tau = R["d"], R["tau"]
+    a, b = lf.Transcript(ring), oracle.transcript(ring)
+    els = synth.uniform_field(R["p"], 9 * d, 5).reshape(9, d)
+    for step in range(3):
+        a.absorb(els[step * 3:(step + 1) * 3]); b.absorb(els[step * 3:(step + 1) * 3])
+        a.absorb_tag("rho_s"); b.absorb_tag("rho_s")
+        assert np.array_equal(a.get_challenge(), b.get_challenge())
+        assert np.array_equal(a.get_short_challenge(), b.get_short_challenge())
+    rho = synth.uniform_field(R["p"], 2 * d, 6).reshape(2, d); theta = synth.uniform_field(R["p"], 2 * tau * d, 7).reshape(2, tau, d)
+    out = np.empty((tau, d), dtype=np.uint64)
+    assert lf.lib().lf_rot_lin_combination(ring, api.ptr(rho), api.ptr(theta), 2, api.ptr(out)) == 0
+    assert np.array_equal(out, oracle.rot_lin_combination(ring, rho, theta))
