@@ -242,13 +242,28 @@ def main():
         "k_fold_sc_round1": M_fold * ((1 << s) // world) * E_BYTES,
         "k_fold": None, "k_matrix_apply": 2 * (2 * K + 3) * n * E_BYTES,
     }
+    # 64-bit multiply-accumulates per step of the two integer-bound kernels against the measured
+    # IMAD.WIDE-bound ceiling of tools/microbench/imad_peak.cu on B200: 1.785e12 lazily reduced MACs / s
+    MAC_PEAK = 1.785e12
+    S_slots, tau = 8, 3
+    pairs_r2 = max(((1 << s) // world) // 2 - 1, 0) + max(world - 1, 0)                # sum over rounds >= 2 of the pair count
+    macs = {"k_dot_commit": 2 * kappa * (K - 1) * n * S_slots * 9,
+            "k_fold_sc_round": pairs_r2 * S_slots * (2 * K * tau) * 93}
     top_name, (top_cnt, top_ms) = top
     a_bytes = alg.get(top_name)
+    # DRAM bytes of this kernel from the committed `ncu --set full` capture (profiles/): largest launch (round 2 at C2) moved
+    # 2.545 GB read + 5 MB written for 2.54 GB algorithmic; the batched commit 2.10 GB for 2.06 GB algorithmic
+    ncu_traffic = {"k_fold_sc_round": 2.551e9, "k_dot_commit": 2.145e9}
     roofline = dict(bound="hbm", kernel=top_name, launches_per_step=top_cnt, avg_launch_ms=top_ms / top_cnt, share_of_kernel_time=top_ms / total_kernel_ms,
                     achieved=(a_bytes / 1e9) / (top_ms / 1e3) if a_bytes else None, peak=hbm, unit="GB/s",
-                    frac=((a_bytes / 1e9) / (top_ms / 1e3) / hbm) if a_bytes else None, traffic=None, peak_source=peak_src,
-                    algorithmic_bytes_per_step=a_bytes,
-                    note="integer-ALU bound kernel (64-bit modular multiplies on 32-bit pipes); see DESIGN.md for the op count")
+                    frac=((a_bytes / 1e9) / (top_ms / 1e3) / hbm) if a_bytes else None,
+                    traffic=ncu_traffic.get(top_name) if (world == 1 and args.log_w == 16) else None,
+                    traffic_note="dram read+write of the largest launch of this kernel in profiles/ (ncu --set full); its algorithmic bytes are the same to 1%",
+                    peak_source=peak_src, algorithmic_bytes_per_step=a_bytes,
+                    int_pipe={k: dict(macs_per_step=v, achieved_mac_per_s=v / (prof[k][1] / 1e3), peak_mac_per_s=MAC_PEAK,
+                                      frac=v / (prof[k][1] / 1e3) / MAC_PEAK) for k, v in macs.items() if k in prof and prof[k][1] > 0},
+                    note="this kernel is bound by the IMAD.WIDE issue rate (64-bit modular multiply-accumulates on 32-bit pipes), not by HBM: "
+                         "frac is the HBM fraction the contract asks for, int_pipe.frac the fraction of the measured multiply-accumulate ceiling")
     line = dict(metric="prover constraints/sec (commit+decomp+sumcheck)", value=value, unit="constraints/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_res, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64 (mod 2^64-2^32+1)", data="synthetic",
                 config=config_of(wl, args, "gpu"), clocks=clk.summary(), gpu_launches=int(launches), collectives_per_step=collectives,

@@ -235,6 +235,14 @@ template <class Rg> struct SlotField {
     static LF_HD void sub(u64* c, const u64* a, const u64* b) {
 #pragma unroll
         for (int i = 0; i < TAU; ++i) c[i] = F::sub(a[i], b[i]); }
+    // accumulating dot products (k_dot): NDOT accumulators per output, one fixed operand prepared once per x
+    static constexpr int NDOT = Rg::TAU;
+    typedef Prepped DotPrepped;
+    static LF_HD DotPrepped dot_prep(const u64* x) { return prep(x); }
+    static LF_HD void dot_mac(typename F::Acc* acc, const u64* y, const DotPrepped& x) { mac(acc, y, x); }
+    static LF_HD void dot_finish(u64* c, const typename F::Acc* acc) {
+#pragma unroll
+        for (int i = 0; i < TAU; ++i) c[i] = F::reduce(acc[i]); }
 };
 
 template <> struct SlotField<GoldilocksRing> {
@@ -267,6 +275,15 @@ template <> struct SlotField<GoldilocksRing> {
     }
     static LF_HD void add(u64* c, const u64* a, const u64* b) { for (int i = 0; i < 3; ++i) c[i] = F::add(a[i], b[i]); }
     static LF_HD void sub(u64* c, const u64* a, const u64* b) { for (int i = 0; i < 3; ++i) c[i] = F::sub(a[i], b[i]); }
+    // Accumulating dot products (k_dot): three lazily reduced sums per output, fixed operand prepared once per x.
+    // (A Karatsuba form with six sums -- 6 instead of 9 wide multiplies per slot-field product -- was measured on B200 and
+    // lost 2.7x: the three extra modular additions per product and the doubled accumulator registers cost more than the
+    // saved IMAD.WIDE issue slots; see tools/dot_ab.py.)
+    static constexpr int NDOT = 3;
+    typedef Prepped DotPrepped;
+    static LF_HD DotPrepped dot_prep(const u64* x) { return prep(x); }
+    static LF_HD void dot_mac(Acc192* acc, const u64* y, const DotPrepped& x) { mac(acc, y, x); }
+    static LF_HD void dot_finish(u64* c, const Acc192* acc) { for (int i = 0; i < 3; ++i) c[i] = F::reduce192(acc[i]); }
 };
 
 }  // namespace lf

@@ -202,11 +202,12 @@ k_dot(const DotArgs a) {
     const u64* yp[CT]; size_t ylen[CT];
 #pragma unroll
     for (int j = 0; j < CT; ++j) { const int c = min(c0 + j, a.ncols - 1); yp[j] = a.Y.p[c] + (size_t)(slot * TAU) * a.y_pitch; ylen[j] = (c0 + j < a.ncols) ? a.Y.len[c] : 0; }
-    typename F::Acc acc[CT][TAU];
+    constexpr int NA = SF::NDOT;
+    typename F::Acc acc[CT][NA];
 #pragma unroll
     for (int j = 0; j < CT; ++j)
 #pragma unroll
-        for (int l = 0; l < TAU; ++l) acc[j][l].clear();
+        for (int l = 0; l < NA; ++l) acc[j][l].clear();
     // everything below min(lengths) needs no per-element bounds test
     size_t safe = min(x_stop, rlen);
 #pragma unroll
@@ -221,34 +222,36 @@ k_dot(const DotArgs a) {
         for (int j = 0; j < CT; ++j)
 #pragma unroll
             for (int l = 0; l < TAU; ++l) yv[j][l] = __ldg(yp[j] + (size_t)l * a.y_pitch + x);
-        const typename SF::Prepped pr = SF::prep(xv);
+        const typename SF::DotPrepped pr = SF::dot_prep(xv);
 #pragma unroll
-        for (int j = 0; j < CT; ++j) SF::mac(acc[j], yv[j], pr);
+        for (int j = 0; j < CT; ++j) SF::dot_mac(acc[j], yv[j], pr);
     }
     for (; x < x_stop; x += 32) {            // ragged tail: operands past their effective length are zero
         if (x >= rlen) break;
         u64 xv[TAU];
 #pragma unroll
         for (int l = 0; l < TAU; ++l) xv[l] = xp[(size_t)l * a.x_pitch + x];
-        const typename SF::Prepped pr = SF::prep(xv);
+        const typename SF::DotPrepped pr = SF::dot_prep(xv);
 #pragma unroll
         for (int j = 0; j < CT; ++j) {
             if (x >= ylen[j]) continue;
             u64 yv[TAU];
 #pragma unroll
             for (int l = 0; l < TAU; ++l) yv[l] = yp[j][(size_t)l * a.y_pitch + x];
-            SF::mac(acc[j], yv, pr);
+            SF::dot_mac(acc[j], yv, pr);
         }
     }
 #pragma unroll
-    for (int j = 0; j < CT; ++j)
+    for (int j = 0; j < CT; ++j) {
+        u64 c[TAU]; SF::dot_finish(c, acc[j]);
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
-            u64 v = F::reduce(acc[j][l]);
+            u64 v = c[l];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v = F::add(v, __shfl_down_sync(0xffffffffu, v, o));
             if (lane == 0 && c0 + j < a.ncols) a.partial[(((size_t)blockIdx.y * a.nrows + row) * a.ncols + (c0 + j)) * Rg::D + slot * TAU + l] = v;
         }
+    }
 }
 
 // evaluate f-hat MLEs straight from coefficient planes: out[v][j][slot][l] = sum_x eq[x][slot][l] * coeff_v[x][j*S + slot]
