@@ -216,6 +216,27 @@ lf_status lf_prover_last_timings(const lf_prover* p, double* out5);
 /* diagnostic: with LF_TIMING_DETAIL=1 in the environment the step synchronises at phase marks; one line "mark ms" each */
 lf_status lf_prover_timing_detail(const lf_prover* p, char* buf, size_t buf_len);
 
+/* ---- K12: batched negacyclic NTT over Z_p[X]/(X^N + 1), N = 2^8 .. 2^16 (BASELINE.json configs[4]).
+ * The reference has no transform of this shape -- its "NTT form" is the CRT of the degree-24/72/16 rings (lf_crt / lf_icrt,
+ * a2/a3 above, stark-rings CRT::elementwise_crt) -- so the definition is the textbook one:
+ *     forward  A[k] = sum_j a[j] psi^(j(2k+1)),   inverse  a[j] = N^-1 sum_k A[k] psi^(-j(2k+1)),   natural order both sides,
+ * psi = the primitive 2N-th root of unity returned by lf_ntt_root (rule: latticefold_b200/csrc/ntt.cuh).  Elements are canonical
+ * little-endian words: uint64_t for LF_FIELD_GOLDILOCKS, uint32_t for LF_FIELD_BABYBEAR; a batch is `batch` polynomials of N
+ * words back to back.  The *_device entry points take plain device pointers (16-byte aligned) and run on the context's stream,
+ * in place if d_in == d_out; the *_host ones copy in, transform and copy out.  The ring of `ctx` is irrelevant here.            */
+enum { LF_FIELD_GOLDILOCKS = 0, LF_FIELD_BABYBEAR = 1 };
+typedef struct lf_ntt_plan lf_ntt_plan;
+lf_status lf_ntt_root(int32_t field, int32_t log_n, uint64_t* psi_out);
+lf_status lf_ntt_plan_create(lf_ctx* ctx, int32_t field, int32_t log_n, lf_ntt_plan** out);
+void lf_ntt_plan_free(lf_ctx* ctx, lf_ntt_plan* plan);
+lf_status lf_ntt_forward_device(lf_ctx* ctx, const lf_ntt_plan* plan, const void* d_in, void* d_out, size_t batch);
+lf_status lf_ntt_inverse_device(lf_ctx* ctx, const lf_ntt_plan* plan, const void* d_in, void* d_out, size_t batch);
+lf_status lf_ntt_forward_host(lf_ctx* ctx, const lf_ntt_plan* plan, const void* h_in, void* h_out, size_t batch);
+lf_status lf_ntt_inverse_host(lf_ctx* ctx, const lf_ntt_plan* plan, const void* h_in, void* h_out, size_t batch);
+/* slot-wise product of two transformed batches, and the full negacyclic ring product INTT(NTT(a) . NTT(b))                     */
+lf_status lf_ntt_pointwise_mul_device(lf_ctx* ctx, const lf_ntt_plan* plan, const void* d_a, const void* d_b, void* d_out, size_t batch);
+lf_status lf_ntt_negacyclic_mul_host(lf_ctx* ctx, const lf_ntt_plan* plan, const void* h_a, const void* h_b, void* h_out, size_t batch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,5 +4,5 @@ Importing the package does not load CUDA; `latticefold_b200.lib()` loads the C-A
 (latticefold_b200/_lib/liblf_b200.so) and raises if it is missing -- there is no CPU fallback.
 """
 from . import synth  # noqa: F401
-from .api import (AjtaiCommitmentScheme, Context, DeviceVec, LfError, MLSumcheck, NIFSProver, SparseMatrix,  # noqa: E402,F401
-                  Transcript, lib)
+from .api import (AjtaiCommitmentScheme, Context, DeviceVec, LfError, MLSumcheck, NIFSProver, NttPlan, SparseMatrix,  # noqa: E402,F401
+                  Transcript, lib, ntt_root)

@@ -31,7 +31,9 @@ lf_sumcheck_finish lf_sumcheck_free lf_transcript_create lf_transcript_clone lf_
 lf_transcript_absorb_base lf_transcript_absorb_tag lf_transcript_get_challenge lf_transcript_get_short_challenge
 lf_transcript_permutations lf_rot_lin_combination lf_prover_create lf_prover_free lf_proof_words lf_lcccs_words
 lf_witness_f_from_w_ccs lf_linearize lf_nifs_prove lf_prover_upload_witness lf_witness_free lf_witness_download_f
-lf_nifs_prove_resident lf_prover_last_timings lf_prover_timing_detail""".split()
+lf_nifs_prove_resident lf_prover_last_timings lf_prover_timing_detail
+lf_ntt_root lf_ntt_plan_create lf_ntt_plan_free lf_ntt_forward_device lf_ntt_inverse_device lf_ntt_forward_host lf_ntt_inverse_host
+lf_ntt_pointwise_mul_device lf_ntt_negacyclic_mul_host""".split()
 
 
 class LfError(RuntimeError):
@@ -170,6 +172,12 @@ def lib():
     L.lf_nifs_prove_resident.argtypes = [vp, C.POINTER(Problem), vp, vp, vp, u64p, u64p, C.POINTER(vp)]
     L.lf_prover_last_timings.argtypes = [vp, C.POINTER(C.c_double)]
     L.lf_prover_timing_detail.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.lf_ntt_root.argtypes = [C.c_int32, C.c_int32, u64p]
+    L.lf_ntt_plan_create.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.lf_ntt_plan_free.argtypes = [vp, vp]
+    for f in ("lf_ntt_forward_device", "lf_ntt_inverse_device", "lf_ntt_forward_host", "lf_ntt_inverse_host"):
+        getattr(L, f).argtypes = [vp, vp, vp, vp, C.c_size_t]
+    L.lf_ntt_pointwise_mul_device.argtypes = L.lf_ntt_negacyclic_mul_host.argtypes = [vp, vp, vp, vp, vp, C.c_size_t]
     _lib = L
     return L
 
@@ -368,6 +376,66 @@ class Context:
     def linearize(self, prob):                            # ops interface: accumulator = linearization of the instance
         pr = NIFSProver(self, prob); lc, _ = pr.linearize(prob, Transcript(self.ring)); pr.close()
         return synth.split_lcccs(self.ring, prob, lc)
+
+
+FIELD_GOLDILOCKS, FIELD_BABYBEAR = 0, 1
+NTT_DTYPE = {FIELD_GOLDILOCKS: np.uint64, FIELD_BABYBEAR: np.uint32}
+
+
+def ntt_root(field, log_n):
+    """psi_N, the primitive 2N-th root of unity the transform uses (rule in csrc/ntt.cuh)."""
+    o = C.c_uint64()
+    rc = lib().lf_ntt_root(field, log_n, C.byref(o))
+    if rc:
+        raise LfError(rc, lib().lf_last_error(None).decode())
+    return int(o.value)
+
+
+class NttPlan:
+    """Batched negacyclic NTT over Z_p[X]/(X^N + 1) (K12, include/lf_b200.h).  Arrays are (batch, N) of uint64 (Goldilocks)
+    or uint32 (BabyBear), canonical values, natural order on both sides."""
+
+    def __init__(self, ctx, field, log_n):
+        self.ctx, self.field, self.log_n, self.n, self.dtype = ctx, field, log_n, 1 << log_n, NTT_DTYPE.get(field, np.uint64)
+        h = vp(); ctx.check(ctx.L.lf_ntt_plan_create(ctx.h, field, log_n, C.byref(h))); self.h = h
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.L.lf_ntt_plan_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _host(self, fn, a):
+        a = np.ascontiguousarray(a, dtype=self.dtype); assert a.size % self.n == 0
+        o = np.empty_like(a)
+        self.ctx.check(fn(self.ctx.h, self.h, a.ctypes.data_as(vp), o.ctypes.data_as(vp), a.size // self.n)); return o
+
+    def forward(self, a):
+        return self._host(self.ctx.L.lf_ntt_forward_host, a)
+
+    def inverse(self, a):
+        return self._host(self.ctx.L.lf_ntt_inverse_host, a)
+
+    def negacyclic_mul(self, a, b):
+        a = np.ascontiguousarray(a, dtype=self.dtype); b = np.ascontiguousarray(b, dtype=self.dtype); assert a.shape == b.shape
+        o = np.empty_like(a)
+        self.ctx.check(self.ctx.L.lf_ntt_negacyclic_mul_host(self.ctx.h, self.h, a.ctypes.data_as(vp), b.ctypes.data_as(vp), o.ctypes.data_as(vp), a.size // self.n))
+        return o
+
+    # device-pointer entry points (torch tensors' data_ptr(), any allocation 16-byte aligned); asynchronous on ctx.stream()
+    def forward_device(self, d_in, d_out, batch):
+        self.ctx.check(self.ctx.L.lf_ntt_forward_device(self.ctx.h, self.h, vp(d_in), vp(d_out), batch))
+
+    def inverse_device(self, d_in, d_out, batch):
+        self.ctx.check(self.ctx.L.lf_ntt_inverse_device(self.ctx.h, self.h, vp(d_in), vp(d_out), batch))
+
+    def pointwise_mul_device(self, d_a, d_b, d_out, batch):
+        self.ctx.check(self.ctx.L.lf_ntt_pointwise_mul_device(self.ctx.h, self.h, vp(d_a), vp(d_b), vp(d_out), batch))
 
 
 class AjtaiCommitmentScheme:

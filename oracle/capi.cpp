@@ -4,6 +4,7 @@
 // All ring elements cross this boundary as d canonical u64 limbs (NTT form: slot-major; coefficient form:
 // power of X), vectors as contiguous arrays of such elements -- the same host format the product C-ABI uses.
 #include "protocol.hpp"
+#include "ntt.hpp"
 #include <map>
 #include <memory>
 #include <chrono>
@@ -225,4 +226,18 @@ int lfo_nifs_verify(const lfo_problem* P, void* tr, const u64* proof, u64* out_l
     });
 }
 
+
+// ---- negacyclic NTT (ntt.hpp): field 0 = Goldilocks, 1 = BabyBear; elements are u64 on this side for both fields
+u64 lfo_ntt_root(int field, int log_n) { u64 r = 0; guard([&] { r = nttx::root(nttx::field(field), log_n); }); return r; }
+int lfo_ntt_naive(int field, int log_n, const u64* in, u64* out, int inverse) {
+    return guard([&] { nttx::naive(nttx::field(field), log_n, in, out, inverse != 0); });
+}
+int lfo_ntt_fast(int field, int log_n, const u64* in, u64* out, size_t batch, int inverse) {
+    return guard([&] { auto F = nttx::field(field); auto pw = nttx::powers(F, log_n); const size_t n = (size_t)1 << log_n;
+        #pragma omp parallel for schedule(static)
+        for (long long b = 0; b < (long long)batch; ++b) nttx::fast(F, log_n, in + b * n, out + b * n, inverse != 0, pw); });
+}
+int lfo_ntt_schoolbook(int field, int log_n, const u64* a, const u64* b, u64* out) {
+    return guard([&] { nttx::schoolbook(nttx::field(field), log_n, a, b, out); });
+}
 }  // extern "C"

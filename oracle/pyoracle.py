@@ -16,7 +16,7 @@ i32p = C.POINTER(C.c_int)
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, f) for f in ("capi.cpp", "ring.hpp", "transcript.hpp", "sumcheck.hpp", "protocol.hpp")]
+    srcs = [os.path.join(HERE, f) for f in ("capi.cpp", "ntt.hpp", "ring.hpp", "transcript.hpp", "sumcheck.hpp", "protocol.hpp")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "-s"], stdout=subprocess.DEVNULL)
     return LIB_PATH
@@ -107,6 +107,11 @@ class Oracle:
         L.lfo_eq_eval.argtypes = [C.c_int, u64p, u64p, C.c_int, u64p]
         L.lfo_evaluate_mles.argtypes = [C.c_int, u64p, C.c_int, C.c_size_t, C.c_int, u64p, C.c_int, u64p]
         L.lfo_rot_lin_combination.argtypes = [C.c_int, u64p, u64p, C.c_int, u64p]
+        L.lfo_ntt_root.restype = C.c_uint64
+        L.lfo_ntt_root.argtypes = [C.c_int, C.c_int]
+        L.lfo_ntt_naive.argtypes = [C.c_int, C.c_int, u64p, u64p, C.c_int]
+        L.lfo_ntt_fast.argtypes = [C.c_int, C.c_int, u64p, u64p, C.c_size_t, C.c_int]
+        L.lfo_ntt_schoolbook.argtypes = [C.c_int, C.c_int, u64p, u64p, u64p]
         L.lfo_short_challenge_from_bytes.argtypes = [C.c_int, C.POINTER(C.c_uint8), u64p]
         L.lfo_sumcheck_prove.argtypes = [C.c_int, C.c_void_p, u64p, C.c_int, C.c_size_t, u64p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, u64p, i32p, i32p, C.c_int, C.c_int, u64p, u64p, u64p, u64p]
@@ -132,6 +137,25 @@ class Oracle:
             self.check(self.lib.lfo_ring_info(ring, ptr(o)))
             self._info[ring] = dict(p=int(o[0]), d=int(o[1]), S=int(o[2]), tau=int(o[3]), g=int(o[4]), nu=int(o[5]), trinomial=bool(o[6]), cs_bytes=int(o[7]))
         return self._info[ring]
+
+    # ---- negacyclic NTT over Z_p[X]/(X^N + 1) (oracle/ntt.hpp); field 0 = Goldilocks, 1 = BabyBear; values as uint64
+    NTT_P = {0: 0xFFFFFFFF00000001, 1: 2013265921}
+
+    def ntt_root(self, field, log_n):
+        return int(self.lib.lfo_ntt_root(field, log_n))
+
+    def ntt_naive(self, field, log_n, a, inverse=False):
+        a = np.ascontiguousarray(a, dtype=np.uint64); o = np.empty_like(a)
+        self.check(self.lib.lfo_ntt_naive(field, log_n, ptr(a), ptr(o), int(inverse))); return o
+
+    def ntt(self, field, log_n, a, inverse=False):
+        """a: (batch, N) uint64 -> fast CPU transform of every row (textbook radix-2, OpenMP over the batch)"""
+        a = np.ascontiguousarray(a, dtype=np.uint64); o = np.empty_like(a)
+        self.check(self.lib.lfo_ntt_fast(field, log_n, ptr(a), ptr(o), a.size >> log_n, int(inverse))); return o
+
+    def ntt_schoolbook(self, field, log_n, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint64); b = np.ascontiguousarray(b, dtype=np.uint64); o = np.empty_like(a)
+        self.check(self.lib.lfo_ntt_schoolbook(field, log_n, ptr(a), ptr(b), ptr(o))); return o
 
     def threads(self):
         return self.lib.lfo_num_threads()
