@@ -101,41 +101,84 @@ struct Goldilocks {
     static constexpr u64 NU = (u64)1 << NU_SHIFT;
     typedef Acc192 Acc;
 
-    // host builds use mask arithmetic: the comparisons are data dependent coin flips and a mispredicted branch costs more
-    // than the whole reduction (the Poseidon transcript runs ~10^7 of these per prover step)
-    static LF_HD u64 add(u64 a, u64 b) {
-        u64 s = a + b;
-#if defined(__CUDA_ARCH__)
-        if (s < a || s >= P) s -= P;
-#else
-        s -= (0 - (u64)((s < a) | (s >= P))) & P;
-#endif
-        return s;
-    }
+    // Device: straight-line carry-flag code, no compares or selects (ncu showed the 64-bit compare/select form the compiler
+    // emits for `if (s < a || s >= P) s -= P` saturating the ALU pipe): a borrow becomes the mask 0xFFFFFFFF = 2^64 - p,
+    // so "+= p on borrow" is one more masked subtract.  sub = 5 instructions, add(a, b) = a - (p - b) = 7.
+    // Host: mask arithmetic -- the comparisons are data dependent coin flips and a mispredicted branch costs more than the
+    // whole reduction (the Poseidon transcript runs ~10^7 of these per prover step).
     static LF_HD u64 sub(u64 a, u64 b) {
-        u64 d = a - b;
 #if defined(__CUDA_ARCH__)
-        if (a < b) d += P;
+        u32 d0, d1, m;
+        asm("sub.cc.u32 %0, %3, %5;\n\t"
+            "subc.cc.u32 %1, %4, %6;\n\t"
+            "subc.u32 %2, 0, 0;\n\t"
+            "sub.cc.u32 %0, %0, %2;\n\t"
+            "subc.u32 %1, %1, 0;"
+            : "=&r"(d0), "=&r"(d1), "=&r"(m) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+        return ((u64)d1 << 32) | d0;
 #else
-        d += (0 - (u64)(a < b)) & P;
+        u64 d = a - b; d += (0 - (u64)(a < b)) & P; return d;
 #endif
-        return d;
     }
-    static LF_HD u64 neg(u64 a) { return a ? P - a : 0; }
+    static LF_HD u64 add(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+        u32 n0, n1, d0, d1, m;
+        asm("sub.cc.u32 %0, 1, %7;\n\t"             // n = p - b  (b < p: no borrow out)
+            "subc.u32 %1, 0xffffffff, %8;\n\t"
+            "sub.cc.u32 %2, %5, %0;\n\t"            // d = a - n
+            "subc.cc.u32 %3, %6, %1;\n\t"
+            "subc.u32 %4, 0, 0;\n\t"
+            "sub.cc.u32 %2, %2, %4;\n\t"
+            "subc.u32 %3, %3, 0;"
+            : "=&r"(n0), "=&r"(n1), "=&r"(d0), "=&r"(d1), "=&r"(m) : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+        return ((u64)d1 << 32) | d0;
+#else
+        u64 s = a + b; s -= (0 - (u64)((s < a) | (s >= P))) & P; return s;
+#endif
+    }
+    static LF_HD u64 neg(u64 a) {
+#if defined(__CUDA_ARCH__)
+        return sub(0, a);
+#else
+        return a ? P - a : 0;
+#endif
+    }
     // (hi:lo) mod p, canonical.  2^64 = EPS, 2^96 = -1.
     static LF_HD u64 reduce128(u64 lo, u64 hi) {
+#if defined(__CUDA_ARCH__)
+        // hi = hh*2^32 + hl:  r = (lo - hh) - (p - hl*(2^32 - 1)), every borrow repaired by the mask trick, then one
+        // canonicalising subtract of p.  Subtract chains only: ptxas keeps the hardware carry sense when a subc follows an
+        // add.cc, so mixed chains do not compute what the PTX text says.  18 instructions, no compares.
+        u32 t0, t1, n0, n1, m, v0, v1;
+        asm("sub.cc.u32 %0, %7, %10;\n\t"           // t = lo - hh
+            "subc.cc.u32 %1, %8, 0;\n\t"
+            "subc.u32 %4, 0, 0;\n\t"
+            "sub.cc.u32 %0, %0, %4;\n\t"            // wrapped by 2^64 = eps too much
+            "subc.u32 %1, %1, 0;\n\t"
+            "not.b32 %3, %9;\n\t"                   // n = p - hl * eps = (~hl) * 2^32 + hl + 1
+            "add.cc.u32 %2, %9, 1;\n\t"
+            "addc.u32 %3, %3, 0;\n\t"
+            "sub.cc.u32 %0, %0, %2;\n\t"            // t -= n
+            "subc.cc.u32 %1, %1, %3;\n\t"
+            "subc.u32 %4, 0, 0;\n\t"
+            "sub.cc.u32 %0, %0, %4;\n\t"            // borrowed: += p
+            "subc.u32 %1, %1, 0;\n\t"
+            "sub.cc.u32 %5, %0, 1;\n\t"             // canonicalise: v = t - p, keep t if that borrows
+            "subc.cc.u32 %6, %1, 0xffffffff;\n\t"
+            "subc.u32 %4, 0, 0;\n\t"
+            "sub.cc.u32 %0, %5, %4;\n\t"
+            "subc.u32 %1, %6, 0;"
+            : "=&r"(t0), "=&r"(t1), "=&r"(n0), "=&r"(n1), "=&r"(m), "=&r"(v0), "=&r"(v1)
+            : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"((u32)hi), "r"((u32)(hi >> 32)));
+        return ((u64)t1 << 32) | t0;
+#else
         u64 hh = hi >> 32, hl = hi & EPS;
         u64 t1 = (hl << 32) - hl;                      // hl * EPS < 2^64
-#if defined(__CUDA_ARCH__)
-        u64 t0 = lo - hh; if (lo < hh) t0 -= EPS;      // wrapped by 2^64 = EPS too much
-        u64 r = t0 + t1; if (r < t1) r += EPS;         // wrapped: add 2^64 mod p
-        if (r >= P) r -= P;
-#else
         u64 t0 = lo - hh; t0 -= (0 - (u64)(lo < hh)) & EPS;
         u64 r = t0 + t1; r += (0 - (u64)(r < t1)) & EPS;
         r -= (0 - (u64)(r >= P)) & P;
-#endif
         return r;
+#endif
     }
     static LF_HD u64 mul(u64 a, u64 b) { u64 lo, hi; mul_wide(a, b, lo, hi); return reduce128(lo, hi); }
     static LF_HD u64 sqr(u64 a) { return mul(a, a); }

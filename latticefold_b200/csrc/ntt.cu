@@ -13,7 +13,9 @@ __device__ __forceinline__ u32 lf::ntt::BbF::mul_w16(u32 a, int e) { e &= 15; re
 namespace {
 
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ int pad(int a) { return a + (a >> 4); }
+// shared-memory index of logical word a: one pad word in 16, so that the radix-16 scatter of pass 1 (16 consecutive words per
+// thread) hits distinct banks.  (An XOR swizzle inside groups of 32 words was measured for the 4-byte field and lost 8 %.)
+template <class T> __device__ __forceinline__ int sidx(int a) { return a + (a >> 4); }
 
 // radix-R DFT (decimation in frequency) of the R registers x[g + j*G], j < R; natural order in and out.
 // root = omega_16^(16/R) forward, its inverse for INV.  Everything is unrolled: exponents and register indices are constants.
@@ -55,7 +57,7 @@ __device__ __forceinline__ void pass(typename F::T* x, int t, typename F::T* s, 
     constexpr int G = 16 / R, TP = N / 16, L = LPREV * R;
     if (LPREV > 1) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) x[q] = s[pad(q * TP + t)];
+        for (int q = 0; q < 16; ++q) x[q] = s[sidx<T>(q * TP + t)];
     }
     if (!(INV && LPREV == 1)) {
 #pragma unroll
@@ -72,7 +74,7 @@ __device__ __forceinline__ void pass(typename F::T* x, int t, typename F::T* s, 
     } else {
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) { int k = q / G, g = q % G, b = t + g * TP, J = b / LPREV, K = b & (LPREV - 1); s[pad(J * L + k * LPREV + K)] = x[q]; }
+        for (int q = 0; q < 16; ++q) { int k = q / G, g = q % G, b = t + g * TP, J = b / LPREV, K = b & (LPREV - 1); s[sidx<T>(J * L + k * LPREV + K)] = x[q]; }
         __syncthreads();
     }
 }
@@ -83,35 +85,41 @@ __device__ __forceinline__ void pass(typename F::T* x, int t, typename F::T* s, 
 //   inverse: row input  = in[r*N + k]                          (always contiguous: TMA)
 //            row output = out[poly*N*stride + lo + stride*j]
 // tw: per-pass twiddle tables back to back; post: inverse only, scale * psi^-k.
-template <class F, int LOGN, bool INV, bool TMA_IN>
-__global__ void __launch_bounds__(Geo<LOGN>::THREADS, Geo<LOGN>::MINB)
+// STRIDED (four-step rows, stride > 1): four adjacent rows per CTA with the row index in the low two bits of the thread id, so
+// that a warp's strided accesses fall on whole 32-byte sectors (4 x 8 B) instead of one word per sector.
+template <class F, int LOGN, bool INV, bool STRIDED>
+__global__ void __launch_bounds__(Geo<LOGN, STRIDED>::THREADS, Geo<LOGN, STRIDED>::MINB)
 k_ntt_cta(const typename F::T* __restrict__ in, typename F::T* __restrict__ out, const typename F::T* __restrict__ tw,
           const typename F::T* __restrict__ post, size_t rows, int stride) {
-    typedef typename F::T T; typedef Geo<LOGN> Gm;
+    typedef typename F::T T; typedef Geo<LOGN, STRIDED> Gm;
     constexpr int N = Gm::N, TP = Gm::TP, PP = Gm::PP, P = Gm::P, R1 = Gm::R1;
+    constexpr bool TMA_IN = !STRIDED || INV;
+    constexpr int RS = Gm::PADN + (STRIDED ? 32 / (int)sizeof(T) : 0);     // words between the rows of a CTA; the stagger spreads
+                                                                           // the 4 interleaved rows of a warp over distinct banks
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
     __shared__ __align__(8) unsigned long long mbar;
-    const int tid = threadIdx.x, pl = tid / TP, t = tid % TP;
+    const int tid = threadIdx.x, pl = STRIDED ? tid % PP : tid / TP, t = STRIDED ? tid / PP : tid % TP;
     const size_t row0 = (size_t)blockIdx.x * PP, row = row0 + pl;
     const bool valid = row < rows;
     T x[16];
     if (TMA_IN) {
-        const size_t nrows = rows - row0 < (size_t)PP ? rows - row0 : (size_t)PP;
-        const u32 bytes = (u32)(nrows * N * sizeof(T)), bar = smem_u32(&mbar);
+        const int nrows = (int)(rows - row0 < (size_t)PP ? rows - row0 : (size_t)PP);
+        const u32 bar = smem_u32(&mbar);
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(smem)), "l"(in + row0 * N), "r"(bytes), "r"(bar) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((u32)(nrows * N * sizeof(T))) : "memory");
+            for (int r = 0; r < nrows; ++r)      // one bulk copy per row: rows land RS words apart (bank stagger, see Geo::RS)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(smem + r * RS)), "l"(in + (row0 + r) * N), "r"((u32)(N * sizeof(T))), "r"(bar) : "memory");
         }
         __syncthreads();                       // the barrier is initialised before anyone polls it
         u32 done = 0;
         while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
         if (valid) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) x[q] = smem[pl * N + q * TP + t];
+            for (int q = 0; q < 16; ++q) x[q] = smem[pl * RS + q * TP + t];
         }
         __syncthreads();                       // raw (unpadded) image fully consumed before the padded layout overwrites it
     } else {
@@ -125,7 +133,7 @@ k_ntt_cta(const typename F::T* __restrict__ in, typename F::T* __restrict__ out,
 #pragma unroll
         for (int q = 0; q < 16; ++q) x[q] = 0;
     }
-    T* s = smem + pl * Gm::PADN;
+    T* s = smem + pl * RS;
     T* dst; size_t ostride;
     if (INV) { dst = out + (row / stride) * (size_t)N * stride + (row % stride); ostride = stride; }
     else { dst = out + row * N; ostride = 1; }
@@ -231,9 +239,7 @@ template <class F> void build_plan(lf_ctx* c, lf_ntt_plan* pl) {
             for (u64 cidx = 0; cidx < n; ++cidx) { if (j) cf[(j - 1) * n + cidx] = vf; ci[j * n + cidx] = vi; vf = hmul<F>(vf, sf); vi = hmul<F>(vi, si); }
         }
         pl->ctw_f = upload_table<F>(c, cf); pl->ctw_i = upload_table<F>(c, ci);
-        // scratch for the sub-transform rows of one chunk of polynomials; 48 MB keeps it (and the chunk it came from) inside the L2
-        size_t poly_bytes = N * sizeof(typename F::T); pl->scratch_polys = std::max<size_t>(1, ((size_t)48 << 20) / poly_bytes);
-        LF_CUDA(cudaMalloc(&pl->scratch, pl->scratch_polys * poly_bytes));
+        (void)N;      // the row scratch is allocated by the first transform, sized to its batch (capped at 4 GiB per launch pair)
     }
     if (F::ID == 1) {
         u64 w16 = hpow<F>(psi_of<F>(4), 2); u32 tab[16]; u64 v = 1;
@@ -251,10 +257,10 @@ template <class Fn> void launch(lf_ctx* c, const char* name, Fn&& fn) {
     ++c->launches; LF_CUDA(cudaGetLastError());
 }
 
-template <class F, int LOGN, bool INV, bool TMA_IN> void launch_cta(lf_ctx* c, const lf_ntt_plan* pl, const void* in, void* out, size_t rows, int stride) {
-    typedef typename F::T T; typedef Geo<LOGN> Gm;
-    auto kern = k_ntt_cta<F, LOGN, INV, TMA_IN>;
-    const size_t smem = (size_t)Gm::PP * Gm::PADN * sizeof(T);
+template <class F, int LOGN, bool INV, bool STRIDED> void launch_cta(lf_ctx* c, const lf_ntt_plan* pl, const void* in, void* out, size_t rows, int stride) {
+    typedef typename F::T T; typedef Geo<LOGN, STRIDED> Gm;
+    auto kern = k_ntt_cta<F, LOGN, INV, STRIDED>;
+    const size_t smem = (size_t)Gm::PP * (Gm::PADN + (STRIDED ? 32 / sizeof(T) : 0)) * sizeof(T);
     static bool attr_set[8] = {false};      // per device
     if (!attr_set[c->device & 7]) { LF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set[c->device & 7] = true; }
     const unsigned grid = (unsigned)((rows + Gm::PP - 1) / Gm::PP);
@@ -263,9 +269,9 @@ template <class F, int LOGN, bool INV, bool TMA_IN> void launch_cta(lf_ctx* c, c
     });
 }
 
-template <class F, bool INV, bool TMA_IN> void dispatch_cta(lf_ctx* c, const lf_ntt_plan* pl, const void* in, void* out, size_t rows, int stride) {
+template <class F, bool INV> void dispatch_cta(lf_ctx* c, const lf_ntt_plan* pl, const void* in, void* out, size_t rows, int stride) {
     switch (pl->sub_log) {
-#define LF_NTT_CASE(L) case L: launch_cta<F, L, INV, TMA_IN>(c, pl, in, out, rows, stride); break;
+#define LF_NTT_CASE(L) case L: launch_cta<F, L, INV, false>(c, pl, in, out, rows, stride); break;
         LF_NTT_CASE(8) LF_NTT_CASE(9) LF_NTT_CASE(10) LF_NTT_CASE(11) LF_NTT_CASE(12) LF_NTT_CASE(13) LF_NTT_CASE(14)
 #undef LF_NTT_CASE
         default: throw LfException(LF_ERR_UNSUPPORTED, "NTT size outside 2^8 .. 2^16");
@@ -273,7 +279,7 @@ template <class F, bool INV, bool TMA_IN> void dispatch_cta(lf_ctx* c, const lf_
 }
 // strided sub-transforms exist for the 4096-point rows of the four-step path only
 template <class F, bool INV> void dispatch_sub(lf_ctx* c, const lf_ntt_plan* pl, const void* in, void* out, size_t rows, int stride) {
-    if (INV) launch_cta<F, 12, true, true>(c, pl, in, out, rows, stride); else launch_cta<F, 12, false, false>(c, pl, in, out, rows, stride);
+    launch_cta<F, 12, INV, true>(c, pl, in, out, rows, stride);
 }
 
 template <class F, int R, bool INV> void launch_cross(lf_ctx* c, const lf_ntt_plan* pl, const void* in, void* out, size_t polys) {
@@ -290,11 +296,19 @@ template <class F, bool INV> void dispatch_cross(lf_ctx* c, const lf_ntt_plan* p
     }
 }
 
-template <class F, bool INV> void exec(lf_ctx* c, const lf_ntt_plan* pl, const void* in, void* out, size_t batch) {
+template <class F, bool INV> void exec(lf_ctx* c, lf_ntt_plan* pl, const void* in, void* out, size_t batch) {
     typedef typename F::T T;
     if (!batch) return;
-    if (pl->n1 == 1) { dispatch_cta<F, INV, true>(c, pl, in, out, batch, 1); return; }
+    if (pl->n1 == 1) { dispatch_cta<F, INV>(c, pl, in, out, batch, 1); return; }
     const size_t N = (size_t)1 << pl->log_n;
+    // The sub-transform rows go through a scratch of the batch's size.  These kernels are bound by the integer pipes, not by HBM
+    // (ncu: ALU pipe ~90 % busy at 25 % of the HBM peak), so a second trip through memory costs less than the launch tails of
+    // L2-sized chunks did (measured: 86 launches per transform at 2 GiB, 11 % of peak).
+    const size_t want = std::min(batch, std::max<size_t>(1, ((size_t)4 << 30) / (N * sizeof(T))));
+    if (pl->scratch_polys < want) {
+        LF_CUDA(cudaStreamSynchronize(c->stream)); if (pl->scratch) cudaFree(pl->scratch); pl->scratch = nullptr; pl->scratch_polys = 0;
+        LF_CUDA(cudaMalloc(&pl->scratch, want * N * sizeof(T))); pl->scratch_polys = want;
+    }
     for (size_t p0 = 0; p0 < batch; p0 += pl->scratch_polys) {
         size_t np = std::min(pl->scratch_polys, batch - p0);
         const T* ci = (const T*)in + p0 * N; T* co = (T*)out + p0 * N;
@@ -312,8 +326,9 @@ template <class Fn> lf_status guard(lf_ctx* ctx, Fn&& fn) {
 size_t esize(int field) { return field == LF_FIELD_GOLDILOCKS ? 8 : 4; }
 void check_plan(const lf_ctx* c, const lf_ntt_plan* pl) { if (!c || !pl) throw LfException(LF_ERR_INVALID_ARG, "null context or plan"); }
 
-void run(lf_ctx* c, const lf_ntt_plan* pl, bool inv, const void* in, void* out, size_t batch) {
+void run(lf_ctx* c, const lf_ntt_plan* cpl, bool inv, const void* in, void* out, size_t batch) {
     LF_CUDA(cudaSetDevice(c->device));
+    lf_ntt_plan* pl = const_cast<lf_ntt_plan*>(cpl);      // the scratch grows on demand; a plan is used from one context at a time
     if (pl->field == LF_FIELD_GOLDILOCKS) { if (inv) exec<GlF, true>(c, pl, in, out, batch); else exec<GlF, false>(c, pl, in, out, batch); }
     else { if (inv) exec<BbF, true>(c, pl, in, out, batch); else exec<BbF, false>(c, pl, in, out, batch); }
 }

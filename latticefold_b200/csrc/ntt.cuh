@@ -18,7 +18,8 @@
 // (shared-memory index padded by 1/16 so the radix-16 scatter is bank-conflict free) -- and the last pass stores straight to
 // global memory, coalesced, in natural order.  HBM traffic = the algorithmic 2 * N * sizeof(T) per polynomial.
 // N = 2^15, 2^16 run as a four-step transform (N = N1 * 4096): strided 4096-point sub-transforms into a scratch that is
-// sized to stay L2 resident (126 MB L2), then a radix-N1 cross pass; the batch is processed in L2-sized chunks.
+// the size of the batch, then a radix-N1 cross pass (the kernels are integer-pipe bound: the second trip through HBM is cheaper
+// than the launch tails of L2-sized chunks were).
 #pragma once
 #include "field.cuh"
 
@@ -67,10 +68,10 @@ struct BbF {
 
 // ------------------------------------------------------------------------------------------------ plan geometry
 // N = 2^LOGN = R1 * 16^(P-1): P passes, the first of radix R1 in {2,4,8,16}
-template <int LOGN> struct Geo {
+template <int LOGN, bool STRIDED = false> struct Geo {
     static constexpr int N = 1 << LOGN, P = (LOGN + 3) / 4, R1 = 1 << (LOGN - 4 * (P - 1));
     static constexpr int TP = N / 16;                               // threads per polynomial
-    static constexpr int PP = TP >= 256 ? 1 : 256 / TP;             // polynomials per CTA
+    static constexpr int PP = STRIDED ? 4 : (TP >= 256 ? 1 : 256 / TP);   // polynomials per CTA
     static constexpr int THREADS = TP * PP;
     static constexpr int PADN = N + N / 16;                         // padded shared-memory words per polynomial
     static constexpr int MINB = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : 4);
