@@ -82,6 +82,12 @@ lf_status lf_ctx_set_shard(lf_ctx* ctx, int32_t rank, int32_t world, lf_collecti
 lf_status lf_nccl_unique_id(uint8_t* out128);
 lf_status lf_ctx_set_shard_nccl(lf_ctx* ctx, int32_t rank, int32_t world, const uint8_t* id128);
 uint64_t lf_ctx_collectives(const lf_ctx* ctx);
+/* NVLink peer memory for the small all-reduces (one per commit batch / sumcheck round / evaluation batch): every rank exports a
+ * mailbox region as a 64-byte CUDA IPC handle, the host side all-gathers the handles, and after the import the final reduction
+ * of those ops and their all-reduce run as ONE kernel that stores its sums into every peer's mailbox (k_reduce_allreduce_p2p)
+ * instead of split-limbs + ncclAllReduce + combine.  Call after lf_ctx_set_shard_nccl, on every rank, in the same order.     */
+lf_status lf_ctx_p2p_export(lf_ctx* ctx, uint8_t* out_handle64);
+lf_status lf_ctx_p2p_import(lf_ctx* ctx, int32_t rank, int32_t world, const uint8_t* handles /* world x 64 bytes; NULL = switch the peer path off again */);
 
 /* ---- vectors: Vec<R> <-> device ------------------------------------------------------------------------------- */
 lf_status lf_vec_upload(lf_ctx* ctx, const uint64_t* host, size_t n, int32_t form, lf_vec** out);

@@ -23,7 +23,7 @@ LF_COMB_PRODUCTS, LF_COMB_LIN, LF_COMB_FOLD = 0, 1, 2
 FORM_NTT, FORM_COEFF = 0, 1
 
 # every symbol include/lf_b200.h declares (tests check that the built library exports all of them)
-SYMBOLS = """lf_ring_describe lf_ctx_create lf_ctx_destroy lf_last_error lf_ctx_sync lf_ctx_stream lf_ctx_launches lf_ctx_profile lf_ctx_profile_report lf_ctx_set_shard lf_ctx_collectives lf_nccl_unique_id lf_ctx_set_shard_nccl
+SYMBOLS = """lf_ring_describe lf_ctx_create lf_ctx_destroy lf_last_error lf_ctx_sync lf_ctx_stream lf_ctx_launches lf_ctx_profile lf_ctx_profile_report lf_ctx_set_shard lf_ctx_collectives lf_nccl_unique_id lf_ctx_set_shard_nccl lf_ctx_p2p_export lf_ctx_p2p_import
 lf_vec_upload lf_vec_download lf_vec_len lf_vec_form lf_vec_free lf_crt lf_icrt lf_gadget_decompose lf_gadget_recompose
 lf_decompose_to_vec lf_fhat lf_ajtai_create lf_ajtai_free lf_ajtai_kappa lf_ajtai_width lf_commit lf_commit_batch
 lf_sparse_create lf_sparse_free lf_spmv lf_eq_table lf_mle_eval_batch lf_lincomb lf_sumcheck_begin lf_sumcheck_round
@@ -120,6 +120,8 @@ def lib():
     L.lf_ctx_set_shard.argtypes = [vp, C.c_int32, C.c_int32, COLLECTIVE_FN, vp]
     L.lf_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.lf_ctx_set_shard_nccl.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
+    L.lf_ctx_p2p_export.argtypes = [vp, C.POINTER(C.c_uint8)]
+    L.lf_ctx_p2p_import.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
     L.lf_ctx_collectives.restype = C.c_uint64
     L.lf_ctx_collectives.argtypes = [vp]
     L.lf_ctx_profile.argtypes = [vp, C.c_int32]
@@ -305,10 +307,33 @@ class Context:
             dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             ident = (C.c_uint8 * 128)(*t.cpu().tolist())
             self.check(self.L.lf_ctx_set_shard_nccl(self.h, rank, world, ident))
+            self.rank, self.world = rank, world
+            if os.environ.get("LF_P2P", "1") != "0":
+                self._enable_p2p(rank, world, group, torch, dist)
         else:
             self._coll = parallel.make_collective(self, group)      # keep the ctypes callback alive
             self.check(self.L.lf_ctx_set_shard(self.h, rank, world, self._coll, None))
         self.rank, self.world = rank, world
+
+    def _enable_p2p(self, rank, world, group, torch, dist):
+        """Map every rank's mailbox region (CUDA IPC) so that the small all-reduces run as one kernel with NVLink peer stores.
+        All ranks must agree: if any rank cannot export or import, everyone stays on the NCCL path."""
+        hbuf = (C.c_uint8 * 64)()
+        ok = self.L.lf_ctx_p2p_export(self.h, hbuf) == 0
+        mine = torch.tensor(list(hbuf) + [1 if ok else 0], dtype=torch.uint8, device=f"cuda:{self.device}")
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        allh = torch.stack(allh).cpu()
+        self.p2p = False
+        if bool(allh[:, 64].all()):
+            flat = (C.c_uint8 * (64 * world))(*allh[:, :64].reshape(-1).tolist())
+            ok = self.L.lf_ctx_p2p_import(self.h, rank, world, flat) == 0
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{self.device}")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 1:
+                self.p2p = True
+            else:
+                self.L.lf_ctx_p2p_import(self.h, rank, world, None)
 
     def collectives(self):
         return int(self.L.lf_ctx_collectives(self.h))

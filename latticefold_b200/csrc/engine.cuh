@@ -69,6 +69,9 @@ struct lf_ctx {
     // (buffer = world x words, this rank's part at rank * words).  The pointer is device memory on this context's device.
     int rank = 0, world = 1; lf_collective_fn coll = nullptr; void* coll_user = nullptr; uint64_t collectives = 0;
     void* nccl = nullptr;          // ncclComm_t when the collectives run on this context's stream (no host round trip)
+    // peer-memory mailboxes (k_reduce_allreduce_p2p): this rank's region and the IPC mappings of every peer's
+    struct XGpu { bool on = false; void* region = nullptr; void* peer_region[8] = {nullptr}; lf::u64* inbox[8] = {nullptr}; unsigned long long* flags[8] = {nullptr};
+                  size_t cap = 0; unsigned long long calls = 0, blocks = 0; } xg;
     bool profiling = false;
     struct ProfRec { const char* name; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
@@ -177,6 +180,21 @@ template <class Rg> struct Engine {
         sync(); ++c->collectives;
         if (c->coll(c->coll_user, op, dev, words) != 0) throw LfException(LF_ERR_CUDA, "collective callback failed");
     }
+    static constexpr size_t XG_CAP = 16384, XG_FLAG_BYTES = 256;      // mailbox words per (parity, source); flag area in front
+    // out[j] = sum over ranks of (sum_b partial[b * nout + j]): one kernel with peer stores when the mailboxes are mapped,
+    // otherwise the local reduction followed by the NCCL all-reduce
+    void reduce_partials_allreduce(const u64* partial, int nblk, size_t nout, u64* d_out) {
+        if (sharded() && c->xg.on && nout <= c->xg.cap) {
+            const unsigned grid = blocks_for(nout, 128);
+            XgArgs x; for (int r = 0; r < 8; ++r) { x.inbox[r] = c->xg.inbox[r]; x.flags[r] = c->xg.flags[r]; }
+            x.rank = c->rank; x.world = c->world; x.parity = (unsigned)(c->xg.calls & 1); x.cap = c->xg.cap;
+            c->xg.blocks += grid; c->xg.calls += 1; x.expected = c->xg.blocks; ++c->collectives;
+            launch("k_reduce_allreduce_p2p", [&] { k_reduce_allreduce_p2p<F><<<grid, 128, 0, st()>>>(partial, nblk, (int)nout, d_out, x); });
+            return;
+        }
+        launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(partial, nblk, (int)nout, d_out); });
+        allreduce_field(d_out, nout);
+    }
     // sum mod p across ranks of `words` field elements at dev (in place)
     void allreduce_field(u64* dev, size_t words) {
         if (!sharded() || !words) return;
@@ -260,8 +278,7 @@ template <class Rg> struct Engine {
                 if (ct == 4) k_dot<Rg, 4, 512><<<g, wpb * 32, 0, st()>>>(a); else if (ct == 2) k_dot<Rg, 2, 512><<<g, wpb * 32, 0, st()>>>(a); else k_dot<Rg, 1, 512><<<g, wpb * 32, 0, st()>>>(a);
             }
         });
-        launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(a.partial, (int)xt, (int)nout, d_out); });
-        allreduce_field(d_out, nout);      // x axis sharded across ranks: one small all-reduce per batched dot
+        reduce_partials_allreduce(a.partial, (int)xt, nout, d_out);      // x axis sharded across ranks: one small all-reduce per batched dot
     }
     // f-hat evaluation from coefficient planes; result nvec x TAU x D limbs on the device
     template <class TIn> void coeff_eval(const TIn* coeff, size_t c_pitch, size_t c_vec_stride, int nvec, const u64* eq, size_t eq_pitch, size_t n, u64* d_out) {
@@ -270,8 +287,7 @@ template <class Rg> struct Engine {
         const size_t nout = (size_t)nvec * TAU * D;
         u64* partial = partial_dev((size_t)xt * nout);
         launch("k_coeff_eval", [&] { k_coeff_eval<Rg, TIn><<<dim3(xt, S, nvec), 128, 0, st()>>>(coeff, c_pitch, c_vec_stride, eq, eq_pitch, n, xpb, nvec, partial); });
-        launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(partial, (int)xt, (int)nout, d_out); });
-        allreduce_field(d_out, nout);
+        reduce_partials_allreduce(partial, (int)xt, nout, d_out);
     }
     void spmv(const lf_sparse* M, const u64* head, size_t head_len, size_t head_pitch, const u64* tail, size_t tail_pitch, u64* out, size_t out_pitch, size_t nrows,
               size_t tail_chunk = ~(size_t)0, size_t tail_chunk_stride = 0, int batch = 1, size_t head_batch_stride = 0, size_t tail_batch_stride = 0, size_t out_batch_stride = 0) {

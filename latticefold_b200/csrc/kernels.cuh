@@ -66,6 +66,41 @@ template <class F> __global__ void k_combine_limbs(const u64* __restrict__ in, u
     if (i < words) { const u64 lo = in[2 * i], hi = in[2 * i + 1];        // each < world * 2^32
         out[i] = F::from_split(lo, hi); }
 }
+// Fused block-partial reduction + all-reduce over NVLink peer memory (every collective of the sharded step is a few
+// KB, so latency is everything).  Every rank owns a "mailbox" region that all peers map through CUDA IPC:
+//   flags[src]                        monotonically increasing count of blocks that have delivered, per source rank
+//   inbox[parity][src][cap]           the source's reduced values for the call of that parity
+// One launch per call on every rank, in the same order (the prover's call sequence is replicated):  thread j sums its column
+// of block partials, STORES the sum straight into every rank's inbox over NVLink, the block publishes with a system-scope
+// atomic on every rank's flag, waits until all blocks of all sources have delivered to it, and adds the world values mod p in
+// rank order (exact arithmetic: any order gives the same canonical element).  Two parities: a rank can only be one call ahead of
+// a peer (call k+1 cannot complete before every peer has finished call k), so slot k+2 never overwrites data still being read.
+struct XgArgs { u64* inbox[8]; unsigned long long* flags[8]; int rank, world; unsigned parity; size_t cap; unsigned long long expected; };
+template <class F> __global__ void __launch_bounds__(128)
+k_reduce_allreduce_p2p(const u64* __restrict__ partial, int nblk, int nout, u64* __restrict__ out, const XgArgs x) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nout) {
+        u64 acc = 0;
+        if (partial) { for (int b = 0; b < nblk; ++b) acc = F::add(acc, partial[(size_t)b * nout + j]); } else acc = out[j];
+        const size_t slot = ((size_t)x.parity * x.world + x.rank) * x.cap + j;
+        for (int r = 0; r < x.world; ++r) x.inbox[r][slot] = acc;              // peer stores (NVLink) for r != rank
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < x.world) {
+        atomicAdd_system(x.flags[threadIdx.x] + x.rank, 1ULL);                  // publish to rank threadIdx.x
+        const volatile unsigned long long* f = x.flags[x.rank] + threadIdx.x;   // and wait for source threadIdx.x
+        while (*f < x.expected) { }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (j < nout) {
+        u64 acc = 0;
+        for (int src = 0; src < x.world; ++src) acc = F::add(acc, __ldcv(x.inbox[x.rank] + ((size_t)x.parity * x.world + src) * x.cap + j));
+        out[j] = acc;
+    }
+}
+
 // entry 0 of every (table, plane) -> column `rank` of a zeroed [rows][pitch_out] buffer (all-gather by summation)
 template <int = 0> __global__ void k_scatter_entry(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t rows, int rank) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -46,6 +46,8 @@ lf_status lf_ctx_create(int32_t ring_id, int32_t device, lf_ctx** out) {
 void lf_ctx_destroy(lf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
+    for (int r = 0; r < 8; ++r) if (c->xg.peer_region[r]) cudaIpcCloseMemHandle(c->xg.peer_region[r]);
+    if (c->xg.region) cudaFree(c->xg.region);
     if (c->nccl) NcclApi::get().CommDestroy(c->nccl);
     for (auto& kv : c->block_size) cudaFree(kv.first);
     if (!c->shared_tables) { for (int i = 0; i < 2; ++i) { cudaFree(c->d_tab_idx[i]); cudaFree(c->d_tab_val[i]); } try { ops(c->ring)->ctx_tables_destroy(c); } catch (...) {} }
@@ -72,6 +74,38 @@ lf_status lf_ctx_set_shard_nccl(lf_ctx* c, int32_t rank, int32_t world, const ui
                           int rc = n.CommInitRank(&c->nccl, world, id, rank);
                           if (rc != 0) throw LfException(LF_ERR_CUDA, std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"));
                           c->rank = rank; c->world = world; });
+}
+
+// ---- peer-memory mailboxes for the fused reduce + all-reduce kernel (k_reduce_allreduce_p2p)
+lf_status lf_ctx_p2p_export(lf_ctx* c, uint8_t* out_handle64) {
+    return guard(c, [&] {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        LF_CUDA(cudaSetDevice(c->device));
+        if (!c->xg.region) {
+            const size_t cap = Engine<GoldilocksRing>::XG_CAP, bytes = Engine<GoldilocksRing>::XG_FLAG_BYTES + 2 * 8 * cap * sizeof(u64);
+            LF_CUDA(cudaMalloc(&c->xg.region, bytes)); LF_CUDA(cudaMemset(c->xg.region, 0, bytes)); LF_CUDA(cudaDeviceSynchronize());
+            c->xg.cap = cap;
+        }
+        cudaIpcMemHandle_t h; LF_CUDA(cudaIpcGetMemHandle(&h, c->xg.region)); std::memcpy(out_handle64, &h, 64);
+    });
+}
+lf_status lf_ctx_p2p_import(lf_ctx* c, int32_t rank, int32_t world, const uint8_t* handles) {
+    return guard(c, [&] {
+        if (!handles) { c->xg.on = false; return; }      // some rank could not map its peers: everyone stays on NCCL
+        if (world < 2 || world > 8 || rank != c->rank || world != c->world) throw LfException(LF_ERR_INVALID_ARG, "p2p import: rank / world must match the shard setup (2..8 ranks)");
+        if (!c->xg.region) throw LfException(LF_ERR_INVALID_ARG, "p2p import before export");
+        LF_CUDA(cudaSetDevice(c->device));
+        for (int r = 0; r < world; ++r) {
+            void* base = c->xg.region;
+            if (r != rank) {
+                cudaIpcMemHandle_t h; std::memcpy(&h, handles + 64 * r, 64);
+                LF_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess)); c->xg.peer_region[r] = base;
+            }
+            c->xg.flags[r] = (unsigned long long*)base;
+            c->xg.inbox[r] = (u64*)((unsigned char*)base + Engine<GoldilocksRing>::XG_FLAG_BYTES);
+        }
+        c->xg.on = true; c->xg.calls = 0; c->xg.blocks = 0;
+    });
 }
 
 lf_status lf_ctx_profile(lf_ctx* c, int32_t enable) {

@@ -45,7 +45,7 @@ def main():
         assert np.array_equal(lc, elc), "folded LCCCS differs"
         assert np.array_equal(f, ef[rank * n_loc:(rank + 1) * n_loc]), "folded witness slice differs"
         pr.close()
-        print(f"rank {rank}/{world} [{backend}] W={W} {kind}: sharded step bit-exact, {ctx.collectives()} collectives so far", flush=True)
+        print(f"rank {rank}/{world} [{backend}] W={W} {kind}: sharded step bit-exact, {ctx.collectives()} collectives so far, p2p={getattr(ctx, "p2p", False)}", flush=True)
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
