@@ -395,6 +395,12 @@ class Context:
         w = np.ascontiguousarray(w_ccs, dtype=np.uint64); W = w.size // self.d; o = np.empty((W * L, self.d), dtype=np.uint64)
         self.check(self.L.lf_witness_f_from_w_ccs(self.h, ptr(w), W, B, L, ptr(o))); return o
 
+    def ntt_mul(self, ring, a, b):                        # ops interface: slot-wise product (test-sized; host integers, nu from the library)
+        class Info(C.Structure):
+            _fields_ = [("p", C.c_uint64), ("d", C.c_int32), ("n_slots", C.c_int32), ("tau", C.c_int32), ("nu", C.c_uint64)]
+        info = Info(); self.check_global(self.L.lf_ring_describe(ring, C.byref(info)))
+        return synth.sf_mul(ring, np.asarray(a, dtype=np.uint64), np.asarray(b, dtype=np.uint64), int(info.nu))
+
     def commit(self, ring, A, f):                         # ops interface: one-shot commit from host arrays
         sch = AjtaiCommitmentScheme(self, A); return sch.commit(self.upload(f))
 

@@ -221,8 +221,47 @@ template <u64 P_, u64 NU_, bool SMALL> struct ModField {
     static inline u64 inv(u64 a) { return pow(a, P - 2); }
 };
 // nu = the primitive g-th root of unity h^((p-1)/g) for the smallest h of exact order g (same rule as the oracle's
-// find_nu; this convention is "unpinned"): 1398021245 for BabyBear (g = 24), 2755067726615789629 for Frog (g = 8)
-typedef ModField<2013265921ULL, 1398021245ULL, true> BabyBear;
+// find_nu; this convention is "unpinned"): 1398021245 for BabyBear (g = 24, struct below), 2755067726615789629 for Frog (g = 8)
+// BabyBear p = 15 * 2^27 + 1 (31 bits).  Same canonical-u64 interface as ModField, but sums of products stay lazily reduced:
+// a product of two canonical values is < 2^62, one multiply-accumulate is one IMAD.WIDE.U32 with carry-out plus one carry
+// add into a 96-bit accumulator (capacity 2^34 products), and the accumulator is folded mod p once
+// (2^32 = 2^28 - 2 and 2^64 = (2^28 - 2)^2 mod p, then a single 64-bit remainder).  The eager ModField accumulator spent a
+// full `%` per product: the commit's dot products and the FOLD sumcheck are ~81 MACs per slot-field product on this ring.
+struct BabyBear {
+    static constexpr u64 P = 2013265921ULL, NU = 1398021245ULL;
+    static constexpr u64 C32 = ((u64)1 << 32) % P, C64 = (C32 * C32) % P;
+    static LF_HD u64 add(u64 a, u64 b) { u64 s = a + b; if (s >= P) s -= P; return s; }
+    static LF_HD u64 sub(u64 a, u64 b) { return a >= b ? a - b : a + (P - b); }
+    static LF_HD u64 neg(u64 a) { return a ? P - a : 0; }
+    static LF_HD u64 mul(u64 a, u64 b) { return (a * b) % P; }
+    static LF_HD u64 sqr(u64 a) { return mul(a, a); }
+    static LF_HD u64 mul_nu(u64 a) { return mul(a, NU); }
+    struct Acc {
+#if defined(__CUDA_ARCH__)
+        u32 e0, e1, e2;
+        LF_HD void clear() { e0 = e1 = e2 = 0; }
+        LF_HD void mac(u64 a, u64 b) {
+            asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;" : "+r"(e0), "+r"(e1), "+r"(e2) : "r"((u32)a), "r"((u32)b));
+        }
+        LF_HD void add(u64 a) { asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+r"(e0), "+r"(e1), "+r"(e2) : "r"((u32)a), "r"((u32)(a >> 32))); }
+        LF_HD u64 fold() const { return ((u64)e2 * C64 + (u64)e1 * C32 + e0) % P; }      // < 2^61 + 2^60 + 2^32
+#else
+        u128 v;
+        LF_HD void clear() { v = 0; }
+        LF_HD void mac(u64 a, u64 b) { v += (u128)a * b; }
+        LF_HD void add(u64 a) { v += a; }
+        LF_HD u64 fold() const { return (u64)(v % P); }
+#endif
+    };
+    static LF_HD u64 reduce(const Acc& a) { return a.fold(); }
+    static LF_HD u64 reduce128(u64 lo, u64 hi) { return (u64)((((u128)hi << 64) | lo) % P); }
+    static LF_HD u64 from_split(u64 lo, u64 hi) { return (u64)((((u128)hi << 32) + lo) % P); }
+    static inline u64 reduce_wide(u128 lo, u128 hi) { u128 t = ((hi % P) * (((u128)1 << 64) % P)) % P; return (u64)((t + lo % P) % P); }
+    static LF_HD u64 from_i64(int64_t v) { return v >= 0 ? (u64)v % P : (P - ((u64)(-v) % P)) % P; }
+    static LF_HD int64_t to_signed(u64 a) { return a <= (P - 1) / 2 ? (int64_t)a : -(int64_t)(P - a); }
+    static inline u64 pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = mul(r, a); a = mul(a, a); e >>= 1; } return r; }
+    static inline u64 inv(u64 a) { return pow(a, P - 2); }
+};
 typedef ModField<15912092521325583641ULL, 2755067726615789629ULL, false> FrogField;
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -78,8 +78,24 @@ def make_witness(ring, W, kind, seed):
     raise ValueError(kind)
 
 
-def make_ccs(ring, W, L, kind, w_ccs, x_len=1):
-    """The reference's dummy R1CS as a padded CCS.  z = x || 1 || w with x = ones."""
+def sf_mul(ring, a, b, nu):
+    """slot-wise product of NTT-form ring elements (count x d) in Fq[Y]/(Y^tau - nu), with Python integers (test-sized inputs only)"""
+    R = RINGS[ring]; p, S, tau = R["p"], R["S"], R["tau"]
+    x = a.reshape(-1, S, tau).astype(object); y = b.reshape(-1, S, tau).astype(object)
+    out = np.zeros_like(x)
+    for i in range(tau):
+        for j in range(tau):
+            t = x[:, :, i] * y[:, :, j]
+            if i + j < tau:
+                out[:, :, i + j] = (out[:, :, i + j] + t) % p
+            else:
+                out[:, :, i + j - tau] = (out[:, :, i + j - tau] + nu * t) % p
+    return np.ascontiguousarray(out.astype(np.uint64).reshape(-1, R["d"]))
+
+
+def make_ccs(ring, W, L, kind, w_ccs, x_len=1, degree=2, ops=None):
+    """The reference's dummy R1CS as a padded CCS (degree 2), or its dummy degree-three CCS (arith/ccs.rs:14-43: A = B = C =
+    identity-like, D = diag(z^2), (Az)(Bz)(Cz) - Dz = 0).  z = x || 1 || w with x = ones."""
     R = RINGS[ring]
     ncols = x_len + W + 1
     rows = x_len + W + 1
@@ -88,6 +104,12 @@ def make_ccs(ring, W, L, kind, w_ccs, x_len=1):
     while m < max((ncols - 1 - 1) * L, n):
         m <<= 1
     z = np.concatenate([one(ring, x_len), one(ring, 1), w_ccs])
+    if degree == 3:
+        neg_one = np.zeros((1, R["d"]), dtype=np.uint64)
+        neg_one[:, ::R["tau"]] = R["p"] - 1
+        Ms = [dummy_csr(ring, rows, ncols, m) for _ in range(3)] + [dummy_csr(ring, rows, ncols, m, diag=ops.ntt_mul(ring, z, z))]
+        return dict(m=m, n_ccs=ncols, l=1, t=4, q=2, d=3, s=m.bit_length() - 1, M=Ms, S=[[0, 1, 2], [3]],
+                    c=np.ascontiguousarray(np.concatenate([one(ring, 1), neg_one])))
     A = dummy_csr(ring, rows, ncols, m)
     Bm = dummy_csr(ring, rows, ncols, m)
     Cm = dummy_csr(ring, rows, ncols, m, diag=None if kind == "scalar" else z)
@@ -98,14 +120,14 @@ def make_ccs(ring, W, L, kind, w_ccs, x_len=1):
                 c=np.ascontiguousarray(np.concatenate([one(ring, 1), neg_one])))
 
 
-def make_instance(ring, W, B, L, b, K, kappa, kind="non_scalar", config_id=0, ops=None, with_acc=True, x_len=1):
+def make_instance(ring, W, B, L, b, K, kappa, kind="non_scalar", config_id=0, ops=None, with_acc=True, x_len=1, degree=2):
     """One prover-step input set.  `ops` must offer witness_f_from_w_ccs(ring, w_ccs, B, L) -> f (n x d, NTT form),
     commit(ring, A, f) -> (kappa x d) and linearize(problem) -> dict(r, v, cm, u, x_w, h)."""
     R = RINGS[ring]
     seed = (SEED_BASE + config_id) & MASK
     n = W * L
     w_ccs = make_witness(ring, W, kind, seed)
-    ccs = make_ccs(ring, W, L, kind, w_ccs, x_len)
+    ccs = make_ccs(ring, W, L, kind, w_ccs, x_len, degree, ops)
     A = uniform_field(R["p"], kappa * n * R["d"], seed).reshape(kappa, n, R["d"])
     prob = dict(ring=ring, B=B, L=L, b=b, K=K, kappa=kappa, n=n, W=W, A=A, ccs=ccs, w_ccs=w_ccs,
                 cm_i_x_ccs=one(ring, x_len), constraints=x_len + W + 1, kind=kind)

@@ -16,6 +16,9 @@ class OracleOps:
     def commit(self, ring, A, f):
         return self.o.commit(ring, A, f)
 
+    def ntt_mul(self, ring, a, b):
+        return self.o.ntt_mul(ring, a, b)
+
     def linearize(self, prob):
         lc, _ = self.o.linearize(prob, self.o.transcript(prob["ring"]))
         return synth.split_lcccs(prob["ring"], prob, lc)

@@ -74,3 +74,19 @@ def test_roundtrips_and_linearity_fullsize(setup, gpu):
     assert np.array_equal(((c1.astype(object) + c2.astype(object)) % P).astype(np.uint64), c3)
     both = sch.commit_batch([dv, ctx.upload(g)])
     assert np.array_equal(both[0], c1) and np.array_equal(both[1], c2)
+
+
+def test_babybear_degree_three_ccs_c3_shape(oracle, gpu):
+    """BASELINE configs[2] (C3) at a size one GPU holds with 8-byte limbs: BabyBear ring, BabyBearDP (256, 4, 2, 8), kappa = 8,
+    degree-three CCS, W = 2^12 (the full 2^20 needs the packed 4-byte limb layout: the folding tables alone are 174 GB at 8 bytes
+    per limb).  The oracle's verifier accepts the GPU proof and the folded commitment opens to the folded witness."""
+    BBR = synth.RING_BABYBEAR
+    ctx = gpu.Context(BBR, 0)
+    prob = synth.make_instance(BBR, 1 << 12, 256, 4, 2, 8, 8, kind="non_scalar", config_id=12, ops=ctx, degree=3)
+    pr = gpu.NIFSProver(ctx, prob)
+    proof, lc, f0 = pr.prove(prob, gpu.Transcript(BBR))
+    light = {k: v for k, v in prob.items() if k not in ("A", "w_i_f", "w_acc_f")}
+    assert np.array_equal(oracle.nifs_verify(light, oracle.transcript(BBR), proof), lc)
+    sch = gpu.AjtaiCommitmentScheme(ctx, prob["A"])
+    assert np.array_equal(sch.commit(ctx.upload(f0)), synth.split_lcccs(BBR, prob, lc)["cm"])
+    pr.close(); ctx.close()

@@ -252,3 +252,24 @@ def test_nifs_prove_matches_oracle(ctx, oracle, oracle_ops, gpu, W, B, L, b, K, 
     for h in (wa, wi, w):
         pr.free_witness(h)
     pr.close()
+
+
+@pytest.mark.parametrize("W,B,L,b,K,kappa,kind", [(8, 1 << 8, 4, 2, 8, 4, "non_scalar"), (4, 1 << 15, 5, 2, 15, 3, "scalar"), (16, 1 << 8, 4, 2, 8, 8, "uniform")])
+def test_nifs_degree_three_ccs_matches_oracle(ctx, oracle, oracle_ops, gpu, W, B, L, b, K, kappa, kind):
+    """BASELINE configs[2] shape: the reference's degree-three CCS (arith/ccs.rs:14-43; t = 4 matrices, LIN sumcheck of degree 4)
+    through the full step, byte-identical to the oracle, on every ring (BabyBearDP = (256, 4, 2, 8), kappa = 8 for the last case)."""
+    if kind != "scalar" and B ** L < P:
+        pytest.skip("witness coefficients do not fit L digits of base B in this field")
+    prob = synth.make_instance(G, W, B, L, b, K, kappa, kind=kind, config_id=5, ops=oracle_ops, degree=3)
+    assert prob["ccs"]["t"] == 4 and prob["ccs"]["d"] == 3
+    pr = gpu.NIFSProver(ctx, prob)
+    eproof, elc, ef, _ = oracle.nifs_prove(prob, oracle.transcript(G))
+    proof, lc, f = pr.prove(prob, gpu.Transcript(G))
+    assert np.array_equal(proof, eproof) and np.array_equal(lc, elc) and np.array_equal(f, ef)
+    oracle.nifs_verify(prob, oracle.transcript(G), proof)
+    pr.close()
+
+
+def test_ops_ntt_mul_matches_oracle(ctx, oracle):
+    a, b = rand_elems(G, 9, 41), rand_elems(G, 9, 42)
+    assert np.array_equal(ctx.ntt_mul(G, a, b), oracle.ntt_mul(G, a, b))

@@ -67,3 +67,15 @@ def test_witness_forms_agree(oracle):
     assert np.array_equal(oracle.icrt(G, f), fc)
     assert np.array_equal(oracle.gadget_recompose(G, f, B, L), w)
     assert np.array_equal(oracle.crt(G, oracle.gadget_recompose(G, fc, B, L)), w)
+
+
+@pytest.mark.parametrize("ring,W,B,L,b,K,kappa,kind", [(BB, 4, 1 << 8, 4, 2, 8, 4, "non_scalar"), (G, 4, 1 << 15, 5, 2, 15, 3, "uniform"), (FROG, 4, 1 << 8, 8, 2, 10, 3, "scalar")])
+def test_nifs_prove_verify_degree_three_ccs(oracle, oracle_ops, ring, W, B, L, b, K, kappa, kind):
+    """the reference's dummy degree-three CCS (arith/ccs.rs:14-43) through prove -> verify (BASELINE configs[2] shape)"""
+    prob = synth.make_instance(ring, W, B, L, b, K, kappa, kind=kind, config_id=6, ops=oracle_ops, degree=3)
+    assert prob["ccs"]["t"] == 4 and prob["ccs"]["q"] == 2 and prob["ccs"]["d"] == 3
+    proof, lc, f, _ = oracle.nifs_prove(prob, oracle.transcript(ring))
+    assert np.array_equal(lc, oracle.nifs_verify(prob, oracle.transcript(ring), proof))
+    bad = proof.copy(); bad[3] = (int(bad[3]) + 1) % synth.RINGS[ring]["p"]
+    with pytest.raises(OracleError):
+        oracle.nifs_verify(prob, oracle.transcript(ring), bad)
