@@ -38,6 +38,8 @@ enum {
     LF_ERR_SUMCHECK_MISUSE = -6,   /* the panics of sumcheck/prover.rs:41,63,74,80 reported as a status       */
     LF_ERR_UNSUPPORTED = -8,       /* ring / parameter outside what this build implements                     */
     LF_ERR_DOES_NOT_FIT = -9,      /* a coefficient needs more digits than requested                          */
+    LF_ERR_SUMCHECK_FAILED = -10,  /* SumCheckError::SumCheckFailed / evaluation-claim mismatch (verifier)    nifs/error.rs:13-66 */
+    LF_ERR_RECOMPOSED = -11,       /* DecompositionError::RecomposedError (verifier)                          nifs/error.rs:35-48 */
     LF_ERR_CUDA = -20,
     LF_ERR_INVALID_ARG = -21
 };
@@ -208,6 +210,11 @@ lf_status lf_linearize(lf_prover* p, const lf_problem* in, lf_transcript* t, uin
 /* one full step from HOST inputs: uploads w_acc_f / w_i_f, proves, downloads proof, folded LCCCS and (if out_f is
  * not NULL) the folded witness f_0.  Proof layout: lin{msgs,v,u} | dec_acc{x,y,u,v per piece} | dec_new | fold{msgs,theta,eta} */
 lf_status lf_nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, uint64_t* out_f);
+/* NIFSVerifier::verify (nifs.rs:117-162): host code like the reference's (no witness-sized data, no GPU needed).  `in` carries
+ * the CCS shape (M may be NULL), the accumulator and cm_i; A and the witnesses are not read.  LF_OK = accepted, out_lcccs (may be
+ * NULL) receives the folded instance; a rejected proof returns LF_ERR_SUMCHECK_FAILED / LF_ERR_RECOMPOSED / LF_ERR_INCORRECT_LENGTH
+ * with the reason in lf_last_error(NULL).                                                                                       */
+lf_status lf_nifs_verify(const lf_problem* in, lf_transcript* t, const uint64_t* proof, uint64_t* out_lcccs);
 /* the same step with both witnesses already resident in HBM (bench.py's `value`): witnesses are handles made by
  * lf_prover_upload_witness; the folded witness stays on the device and is returned as a new handle                 */
 typedef struct lf_witness lf_witness;

@@ -30,7 +30,7 @@ lf_sparse_create lf_sparse_free lf_spmv lf_eq_table lf_mle_eval_batch lf_lincomb
 lf_sumcheck_finish lf_sumcheck_free lf_transcript_create lf_transcript_clone lf_transcript_free lf_transcript_absorb
 lf_transcript_absorb_base lf_transcript_absorb_tag lf_transcript_get_challenge lf_transcript_get_short_challenge
 lf_transcript_permutations lf_rot_lin_combination lf_prover_create lf_prover_free lf_proof_words lf_lcccs_words
-lf_witness_f_from_w_ccs lf_linearize lf_nifs_prove lf_prover_upload_witness lf_witness_free lf_witness_download_f
+lf_witness_f_from_w_ccs lf_linearize lf_nifs_prove lf_nifs_verify lf_prover_upload_witness lf_witness_free lf_witness_download_f
 lf_nifs_prove_resident lf_prover_last_timings lf_prover_timing_detail
 lf_ntt_root lf_ntt_plan_create lf_ntt_plan_free lf_ntt_forward_device lf_ntt_inverse_device lf_ntt_forward_host lf_ntt_inverse_host
 lf_ntt_pointwise_mul_device lf_ntt_negacyclic_mul_host""".split()
@@ -168,6 +168,7 @@ def lib():
     L.lf_witness_f_from_w_ccs.argtypes = [vp, u64p, C.c_size_t, C.c_uint64, C.c_int32, u64p]
     L.lf_linearize.argtypes = [vp, C.POINTER(Problem), vp, u64p, u64p]
     L.lf_nifs_prove.argtypes = [vp, C.POINTER(Problem), vp, u64p, u64p, u64p]
+    L.lf_nifs_verify.argtypes = [C.POINTER(Problem), vp, u64p, u64p]
     L.lf_prover_upload_witness.argtypes = [vp, u64p, C.POINTER(vp)]
     L.lf_witness_free.argtypes = [vp, vp]
     L.lf_witness_download_f.argtypes = [vp, vp, u64p]
@@ -556,6 +557,20 @@ class MLSumcheck:
         finally:
             ctx.L.lf_sumcheck_free(sc)
         return (msgs, point, final) if want_final else (msgs, point)
+
+
+def nifs_verify(prob, transcript, proof):
+    """NIFSVerifier::verify (nifs.rs:117-162) through the product library's host verifier: returns the folded LCCCS words, raises
+    LfError on rejection.  Needs no GPU and none of the witness-sized inputs (A, w_i_f, w_acc_f may be absent from prob)."""
+    L = lib()
+    light = {k: v for k, v in prob.items() if k not in ("A", "w_i_f", "w_acc_f")}
+    P, keep = make_problem(light)
+    lc = np.empty(int(L.lf_lcccs_words(C.byref(P))), dtype=np.uint64)
+    proof = np.ascontiguousarray(proof, dtype=np.uint64)
+    rc = L.lf_nifs_verify(C.byref(P), transcript.h, ptr(proof), ptr(lc))
+    if rc:
+        raise LfError(rc, L.lf_last_error(None).decode())
+    return lc
 
 
 class NIFSProver:

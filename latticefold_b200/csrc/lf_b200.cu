@@ -188,6 +188,9 @@ lf_status lf_nifs_prove_resident(lf_prover* p, const lf_problem* in, const lf_wi
                                  uint64_t* out_proof, uint64_t* out_lcccs, lf_witness** out_w) {
     return guard(p->ctx, [&] { ops(p->ring)->nifs_prove_resident(p, in, w_acc, w_i, t, out_proof, out_lcccs, out_w); });
 }
+lf_status lf_nifs_verify(const lf_problem* in, lf_transcript* t, const uint64_t* proof, uint64_t* out_lcccs) {
+    return guard(nullptr, [&] { if (!in || !t || !proof) throw LfException(LF_ERR_INVALID_ARG, "null argument"); ops(in->ring)->nifs_verify(in, t, proof, out_lcccs); });
+}
 lf_status lf_nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, uint64_t* out_f) {
     return guard(p->ctx, [&] { ops(p->ring)->nifs_prove(p, in, t, out_proof, out_lcccs, out_f); });
 }

@@ -3,6 +3,7 @@
 // on the context's ring id.  Methods throw LfException; the extern "C" wrappers turn that into status codes.
 #pragma once
 #include "prover.cuh"
+#include "verifier_host.hpp"
 
 struct lf_transcript { int ring; void* impl; };      // impl = lf::Transcript<Rg>*
 
@@ -53,6 +54,7 @@ struct RingOps {
     virtual void linearize(lf_prover* p, const lf_problem* in, lf_transcript* t, uint64_t* out_lcccs, uint64_t* out_proof) = 0;
     virtual void nifs_prove_resident(lf_prover* p, const lf_problem* in, const lf_witness* w_acc, const lf_witness* w_i, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, lf_witness** out_w) = 0;
     virtual void nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, uint64_t* out_f) = 0;
+    virtual void nifs_verify(const lf_problem* in, lf_transcript* t, const uint64_t* proof, uint64_t* out_lcccs) = 0;
 };
 RingOps* ring_ops_goldilocks();
 RingOps* ring_ops_babybear();
@@ -278,6 +280,9 @@ template <class Rg> struct RingOpsImpl final : RingOps {
     }
     void nifs_prove_resident(lf_prover* p, const lf_problem* in, const lf_witness* w_acc, const lf_witness* w_i, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, lf_witness** out_w) override {
         Prover<Rg> pr(p); lf_witness* w = pr.prove(*in, w_acc, w_i, tr(t), out_proof, out_lcccs); if (out_w) *out_w = w; else pr.free_witness(w);
+    }
+    void nifs_verify(const lf_problem* in, lf_transcript* t, const uint64_t* proof, uint64_t* out_lcccs) override {
+        Verifier<Rg> v(*in); LCCCS lc = v.verify(proof, tr(t)); if (out_lcccs) Prover<Rg>::put_lcccs(out_lcccs, lc);
     }
     void nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, uint64_t* out_f) override {
         Prover<Rg> pr(p);

@@ -85,3 +85,33 @@ def test_product_host_side_matches_oracle_all_rings(oracle, ring):
     out = np.empty((tau, d), dtype=np.uint64)
     assert lf.lib().lf_rot_lin_combination(ring, api.ptr(rho), api.ptr(theta), 2, api.ptr(out)) == 0
     assert np.array_equal(out, oracle.rot_lin_combination(ring, rho, theta))
+
+
+VERIFY_CASES = [  # ring, W, B, L, b, K, kappa, kind, CCS degree
+    (synth.RING_GOLDILOCKS, 4, 1 << 15, 5, 2, 15, 4, "non_scalar", 2),
+    (synth.RING_GOLDILOCKS, 8, 1 << 16, 4, 2, 16, 3, "uniform", 3),
+    (synth.RING_BABYBEAR, 4, 1 << 8, 4, 2, 8, 4, "non_scalar", 3),
+    (synth.RING_FROG, 4, 1 << 8, 8, 2, 10, 4, "uniform", 2),
+]
+
+
+@pytest.mark.parametrize("ring,W,B,L,b,K,kappa,kind,degree", VERIFY_CASES)
+def test_product_verifier_accepts_oracle_proofs_and_rejects_tampering(oracle, oracle_ops, ring, W, B, L, b, K, kappa, kind, degree):
+    """NIFSVerifier::verify of the product library (host code, csrc/verifier_host.hpp; nifs.rs:117-162) against the oracle's
+    prover: same folded instance, and each sub-proof region is protected (nifs/tests.rs:58-117 and the per-protocol tamper tests)."""
+    prob = synth.make_instance(ring, W, B, L, b, K, kappa, kind=kind, config_id=21, ops=oracle_ops, degree=degree)
+    proof, lc, _, _ = oracle.nifs_prove(prob, oracle.transcript(ring))
+    assert np.array_equal(lf.nifs_verify(prob, lf.Transcript(ring), proof), lc)
+    assert np.array_equal(lc, oracle.nifs_verify(prob, oracle.transcript(ring), proof))
+    p = synth.RINGS[ring]["p"]
+    codes = set()
+    for pos in (0, proof.size // 5, proof.size // 3, proof.size // 2, (2 * proof.size) // 3, proof.size - 1):
+        bad = proof.copy(); bad[pos] = (int(bad[pos]) + 1) % p
+        with pytest.raises(lf.LfError) as e:
+            lf.nifs_verify(prob, lf.Transcript(ring), bad)
+        codes.add(e.value.code)
+    assert codes <= {-10, -11} and -10 in codes      # LF_ERR_SUMCHECK_FAILED / LF_ERR_RECOMPOSED
+    # a wrong accumulator is rejected as well
+    prob2 = dict(prob); acc = dict(prob["acc"]); acc["v"] = acc["v"].copy(); acc["v"][0, 0] = (int(acc["v"][0, 0]) + 1) % p; prob2["acc"] = acc
+    with pytest.raises(lf.LfError):
+        lf.nifs_verify(prob2, lf.Transcript(ring), proof)

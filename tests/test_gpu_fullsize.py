@@ -29,6 +29,7 @@ def test_full_step_verifies_and_opens(setup, oracle, gpu):
     light = {k: v for k, v in prob.items() if k not in ("A", "w_i_f", "w_acc_f")}      # the verifier needs no witness-sized input
     lc_v = oracle.nifs_verify(light, oracle.transcript(G), proof)
     assert np.array_equal(lc_v, lc)
+    assert np.array_equal(gpu.nifs_verify(prob, gpu.Transcript(G), proof), lc)      # the product's own (host) verifier agrees
     out = synth.split_lcccs(G, prob, lc)
     sch = gpu.AjtaiCommitmentScheme(ctx, prob["A"])
     assert np.array_equal(sch.commit(ctx.upload(f0)), out["cm"])
