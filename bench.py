@@ -248,7 +248,7 @@ def main():
     S_slots, tau = 8, 3
     pairs_r2 = max(((1 << s) // world) // 2 - 1, 0) + max(world - 1, 0)                # sum over rounds >= 2 of the pair count
     macs = {"k_dot_commit": 2 * kappa * (K - 1) * n * S_slots * 9,
-            "k_fold_sc_round": pairs_r2 * S_slots * (2 * K * tau) * 93}
+            "k_fold_sc_round": pairs_r2 * S_slots * (2 * K * tau) * 66}       # two lanes x (mu*t 9 + t^2 6 + two MACs 18)
     top_name, (top_cnt, top_ms) = top
     a_bytes = alg.get(top_name)
     # DRAM bytes of this kernel from the committed `ncu --set full` capture (profiles/): largest launch (round 2 at C2) moved

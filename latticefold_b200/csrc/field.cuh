@@ -188,6 +188,23 @@ struct Goldilocks {
         return sub(reduce128(w0, w1), (u64)w2 << 32);
     }
     static LF_HD u64 reduce(const Acc192& a) { return reduce192(a); }
+    // slim accumulator for plain sums of field elements (no products): 96 bits in three registers, 2^32 terms
+    struct Sum {
+#if defined(__CUDA_ARCH__)
+        u32 a0, a1, a2;
+        LF_HD void clear() { a0 = a1 = a2 = 0; }
+        LF_HD void add(u64 v) { asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+r"(a0), "+r"(a1), "+r"(a2) : "r"((u32)v), "r"((u32)(v >> 32))); }
+        LF_HD u64 lo() const { return ((u64)a1 << 32) | a0; }
+        LF_HD u64 hi() const { return a2; }
+#else
+        u128 v;
+        LF_HD void clear() { v = 0; }
+        LF_HD void add(u64 x) { v += x; }
+        LF_HD u64 lo() const { return (u64)v; }
+        LF_HD u64 hi() const { return (u64)(v >> 64); }
+#endif
+    };
+    static LF_HD u64 reduce(const Sum& a) { return reduce128(a.lo(), a.hi()); }
     static LF_HD u64 mul_nu(u64 a) { return reduce128(a << NU_SHIFT, a >> (64 - NU_SHIFT)); }
     // (lo + hi * 2^32) mod p for lo, hi < 2^40: recombination of the split-limb all-reduce
     static LF_HD u64 from_split(u64 lo, u64 hi) { return add(reduce128(lo, 0), reduce128(hi << 32, hi >> 32)); }
@@ -211,6 +228,7 @@ template <u64 P_, u64 NU_, bool SMALL> struct ModField {
     static LF_HD u64 sqr(u64 a) { return mul(a, a); }
     static LF_HD u64 mul_nu(u64 a) { return mul(a, NU); }
     struct Acc { u64 v; LF_HD void clear() { v = 0; } LF_HD void mac(u64 a, u64 b) { v = ModField::add(v, ModField::mul(a, b)); } LF_HD void add(u64 a) { v = ModField::add(v, a % P); } };
+    typedef Acc Sum;
     static LF_HD u64 reduce(const Acc& a) { return a.v; }
     static LF_HD_CALL u64 reduce128(u64 lo, u64 hi) { return (u64)((((u128)hi << 64) | lo) % P); }
     static LF_HD_CALL u64 from_split(u64 lo, u64 hi) { return (u64)((((u128)hi << 32) + lo) % P); }
@@ -253,6 +271,7 @@ struct BabyBear {
         LF_HD u64 fold() const { return (u64)(v % P); }
 #endif
     };
+    typedef Acc Sum;
     static LF_HD u64 reduce(const Acc& a) { return a.fold(); }
     static LF_HD u64 reduce128(u64 lo, u64 hi) { return (u64)((((u128)hi << 64) | lo) % P); }
     static LF_HD u64 from_split(u64 lo, u64 hi) { return (u64)((((u128)hi << 32) + lo) % P); }
@@ -308,6 +327,14 @@ template <class Rg> struct SlotField {
 #pragma unroll
         for (int k = 0; k < TAU; ++k) c[k] = F::reduce(acc[k]);
     }
+    static LF_HD_CALL void mul_prepped(u64* c, const u64* a, const Prepped& p) {
+        typename F::Acc acc[Rg::TAU];
+#pragma unroll
+        for (int k = 0; k < TAU; ++k) acc[k].clear();
+        mac(acc, a, p);
+#pragma unroll
+        for (int k = 0; k < TAU; ++k) c[k] = F::reduce(acc[k]);
+    }
     static LF_HD_CALL void sqr(u64* c, const u64* a) { u64 t[Rg::TAU];
 #pragma unroll
         for (int k = 0; k < TAU; ++k) t[k] = a[k]; mul(c, a, t); }
@@ -350,6 +377,14 @@ template <> struct SlotField<GoldilocksRing> {
     // lazy multiply-accumulate: acc[l] += (a*b)[l] with bn = (b0, nu*b1, nu*b2 precomputed by prep())
     struct Prepped { u64 b0, b1, b2, b1n, b2n; };
     static LF_HD Prepped prep(const u64* b) { Prepped p; p.b0 = b[0]; p.b1 = b[1]; p.b2 = b[2]; p.b1n = F::mul_nu(b[1]); p.b2n = F::mul_nu(b[2]); return p; }
+    // c = a * b with b prepared: one accumulator live at a time
+    static LF_HD void mul_prepped(u64* c, const u64* a, const Prepped& p) {
+        Acc192 x; u64 c0, c1, c2;
+        x.clear(); x.mac(a[0], p.b0); x.mac(a[1], p.b2n); x.mac(a[2], p.b1n); c0 = F::reduce192(x);
+        x.clear(); x.mac(a[0], p.b1); x.mac(a[1], p.b0);  x.mac(a[2], p.b2n); c1 = F::reduce192(x);
+        x.clear(); x.mac(a[0], p.b2); x.mac(a[1], p.b1);  x.mac(a[2], p.b0);  c2 = F::reduce192(x);
+        c[0] = c0; c[1] = c1; c[2] = c2;
+    }
     static LF_HD void mac(Acc192* acc, const u64* a, const Prepped& p) {
         acc[0].mac(a[0], p.b0); acc[0].mac(a[1], p.b2n); acc[0].mac(a[2], p.b1n);
         acc[1].mac(a[0], p.b1); acc[1].mac(a[1], p.b0);  acc[1].mac(a[2], p.b2n);

@@ -4,6 +4,7 @@
 // whole slot-field element in registers.  Tensor cores are not used (nothing here is a dense FP contraction).
 // Each kernel cites the reference loop it replaces; byte counts per unit are in DESIGN.md.
 #pragma once
+#include <type_traits>
 #include "field.cuh"
 #include "ring_host.hpp"
 #include <cuda_runtime.h>
@@ -564,7 +565,7 @@ struct FoldScArgs {
     // rounds >= 2: slot-field tables, f-hat (k,d) at fh + (k*tau+d) * fh_stride
     const u64* fh; size_t fh_pitch, fh_stride;
 };
-template <class Rg, bool WITH_PRODUCTS = true> __device__ __forceinline__ void fold_sc_tail(const FoldScArgs& a, size_t b, bool active, int slot, const u64 (*h)[Rg::TAU] /* h(0..4) */, u64* red, size_t partial_block = ~(size_t)0) {
+template <class Rg, bool WITH_PRODUCTS = true> __device__ __forceinline__ void fold_sc_tail(const FoldScArgs& a, size_t b, bool active, int slot, const u64 (*h)[Rg::TAU] /* h(0..4) */, u64* red, size_t partial_block = ~(size_t)0, bool rt_products = true) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     u64 ev[5][TAU];
 #pragma unroll
@@ -586,7 +587,7 @@ template <class Rg, bool WITH_PRODUCTS = true> __device__ __forceinline__ void f
         for (int e = 0; e < 5; ++e) {
             u64 t0[TAU], t1[TAU];
             SF::mul(t1, val[4], h[e]);
-            if (WITH_PRODUCTS) { SF::mul(t0, val[0], val[1]); SF::add(t1, t1, t0); SF::mul(t0, val[2], val[3]); SF::add(t1, t1, t0); }
+            if (WITH_PRODUCTS && rt_products) { SF::mul(t0, val[0], val[1]); SF::add(t1, t1, t0); SF::mul(t0, val[2], val[3]); SF::add(t1, t1, t0); }
 #pragma unroll
             for (int l = 0; l < TAU; ++l) ev[e][l] = t1[l];
 #pragma unroll
@@ -663,75 +664,72 @@ template <class Rg> __global__ void k_fold_digits(const int8_t* __restrict__ dig
 }
 // rounds >= 2.  Along the pair's line f(X) = u + X s:
 //   f^3 - f = (u^3 - u) + 3X u^2 s + 3X^2 u s^2 + X^3 (s^3 - s) + (X^3 - X) s,
-// so h(X) = A + 3X B + 3X^2 C + X^3 Dd + (X^3 - X) Es with five mu-weighted sums that stay lazily reduced over all 2K*tau
-// tables.  The sums are split over two thread sets (blockIdx.z): PART 0 carries {A, B, Es} and the v0 v1 + v2 v3 term,
-// PART 1 carries {C, Dd}; the round message is linear in them, so the two sets simply contribute separate partial sums.
-// Halving the live accumulators per thread (15 -> 9 / 6 accumulators) is what lets enough warps be resident to cover the
-// IMAD / carry-chain latencies (ncu before the split: 211 registers, 12 % occupancy, issue slot busy 43 %).
-template <class Rg, int PART> __device__ __forceinline__ void fold_sc_round_part(const FoldScArgs& a, u64* red, const u64* s_mu /* n_f x TAU */) {
+// so h(X) = A + 3X B + 3X^2 C + X^3 D + (X^3 - X) Es with five mu-weighted sums over all 2K*tau tables that stay lazily reduced.
+// (History: one thread per pair with all five sums needed 211 registers; two thread sets over {A,B,Es} / {C,D} -- 95 MACs per
+// (pair, slot, table), 10.0 ms per step -- were the round-1 form before the two-lane kernel below: 7.8 ms.)
+// Rounds >= 2, two lanes per pair.  With w = mu u and z = mu s (one slot-field product each) the five sums become
+//   A = sum (w u^2 - w),  B = sum z u^2,  C = sum w s^2,  D = sum (z s^2 - z),  Es = sum z
+// -- 68 instead of 95 multiply-accumulates and 12 instead of 15 reductions per (pair, slot, table).  Holding all of it in one
+// thread needs 12 lazily reduced accumulators (168 registers with spills, 12 warps per SM: measured 9.5 ms, latency bound), so
+// the work is split over two ADJACENT LANES that run the same code on different operands: lane 0 owns t = u, lane 1 owns t = s;
+// each forms mine = mu t and q = t^2, swaps `mine` with its neighbour by one shuffle per limb, and accumulates mine*q, other*q
+// and the plain sum of mine.  Lane 0 thus holds {A, B}, lane 1 {D, C, Es}; the round message is linear in them.
+// 128 registers (4 blocks of 128 threads per SM) with the table loop not unrolled measured best: 152 registers / 3 blocks 8.3 ms,
+// 96 registers / 5 blocks 7.9 ms, this 7.8 ms.
+template <class Rg> __global__ void __launch_bounds__(128, 4)
+k_fold_sc_round(const FoldScArgs a) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
-    const int slot = blockIdx.y;
-    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const bool active = b < a.n_pairs;
+    __shared__ u64 red[5 * TAU * 32];
+    // mu and its nu-multiples, prepared once per block where that fits the static shared-memory budget (5 words per table on the
+    // Goldilocks ring); the wide-slot rings keep mu itself and prepare it per table
+    constexpr bool PREP_SMEM = sizeof(typename SF::Prepped) * MAX_MU <= 16384;
+    typedef typename std::conditional<PREP_SMEM, typename SF::Prepped, u64>::type MuT;
+    __shared__ MuT s_mu[PREP_SMEM ? MAX_MU : MAX_MU * TAU];
+    if constexpr (PREP_SMEM) { for (int i = threadIdx.x; i < a.n_f; i += blockDim.x) s_mu[i] = SF::prep(a.mu_pow + (size_t)i * TAU); }
+    else { for (int i = threadIdx.x; i < a.n_f * TAU; i += blockDim.x) s_mu[i] = a.mu_pow[i]; }
+    __syncthreads();
+    const int slot = blockIdx.y, role = threadIdx.x & 1;
+    const size_t b = (size_t)blockIdx.x * (blockDim.x / 2) + (threadIdx.x >> 1); const bool active = b < a.n_pairs;
+    const unsigned lanes = __ballot_sync(0xffffffffu, active);      // both lanes of a pair are active together
     u64 h[5][TAU];
 #pragma unroll
     for (int e = 0; e < 5; ++e)
 #pragma unroll
         for (int l = 0; l < TAU; ++l) h[e][l] = 0;
     if (active) {
-        typename F::Acc s0[TAU], s1[TAU], s2[TAU];      // PART 0: A, B, Es    PART 1: C, Dd, (unused)
+        typename F::Acc s_mine[TAU], s_other[TAU]; typename F::Sum sum_mine[TAU];
 #pragma unroll
-        for (int l = 0; l < TAU; ++l) { s0[l].clear(); s1[l].clear(); s2[l].clear(); }
-#pragma unroll 2
+        for (int l = 0; l < TAU; ++l) { s_mine[l].clear(); s_other[l].clear(); sum_mine[l].clear(); }
+#pragma unroll 1
         for (int kd = 0; kd < a.n_f; ++kd) {
-            u64 u[TAU], s[TAU];
+            u64 t[TAU], mine[TAU], other[TAU], q[TAU];
 #pragma unroll
             for (int l = 0; l < TAU; ++l) {
                 const ulonglong2 p = __ldg(reinterpret_cast<const ulonglong2*>(a.fh + (size_t)kd * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b));
-                u[l] = p.x; s[l] = F::sub(p.y, p.x);
+                const u64 sl = F::sub(p.y, p.x); t[l] = role ? sl : p.x;
             }
-            u64 q[TAU], t[TAU];
-            const typename SF::Prepped mu = SF::prep(s_mu + kd * TAU);
-            if (PART == 0) {
-                SF::sqr(q, u);
-                SF::mul(t, q, u); SF::sub(t, t, u); SF::mac(s0, t, mu);      // u^3 - u
-                SF::mul(t, q, s); SF::mac(s1, t, mu);                        // u^2 s
-                SF::mac(s2, s, mu);                                          // s
-            } else {
-                SF::sqr(q, s);
-                SF::mul(t, q, u); SF::mac(s0, t, mu);                        // u s^2
-                SF::mul(t, q, s); SF::sub(t, t, s); SF::mac(s1, t, mu);      // s^3 - s
-            }
+            if constexpr (PREP_SMEM) SF::mul_prepped(mine, t, s_mu[kd]); else SF::mul_prepped(mine, t, SF::prep(&s_mu[kd * TAU]));
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) { other[l] = __shfl_xor_sync(lanes, mine[l], 1); sum_mine[l].add(mine[l]); }
+            SF::sqr(q, t); const typename SF::Prepped qp = SF::prep(q);
+            SF::mac(s_mine, mine, qp); SF::mac(s_other, other, qp);
         }
         auto mulc = [](u64 v, u64 c) { return F::mul(v, c); };
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
-            const u64 x0 = F::reduce(s0[l]), x1 = F::reduce(s1[l]);
-            if (PART == 0) {
-                const u64 Es = F::reduce(s2[l]);
-                h[0][l] = x0;
-                h[1][l] = F::add(x0, mulc(x1, 3));
-                h[2][l] = F::add(F::add(x0, mulc(x1, 6)), mulc(Es, 6));
-                h[3][l] = F::add(F::add(x0, mulc(x1, 9)), mulc(Es, 24));
-                h[4][l] = F::add(F::add(x0, mulc(x1, 12)), mulc(Es, 60));
-            } else {
+            const u64 sm = F::reduce(sum_mine[l]), x0 = F::sub(F::reduce(s_mine[l]), sm), x1 = F::reduce(s_other[l]);
+            if (role == 0) {            // x0 = A, x1 = B:  A + 3X B
+                h[0][l] = x0; h[1][l] = F::add(x0, mulc(x1, 3)); h[2][l] = F::add(x0, mulc(x1, 6)); h[3][l] = F::add(x0, mulc(x1, 9)); h[4][l] = F::add(x0, mulc(x1, 12));
+            } else {                    // x0 = D, x1 = C, sm = Es:  3X^2 C + X^3 D + (X^3 - X) Es
                 h[0][l] = 0;
-                h[1][l] = F::add(mulc(x0, 3), x1);
-                h[2][l] = F::add(mulc(x0, 12), mulc(x1, 8));
-                h[3][l] = F::add(mulc(x0, 27), mulc(x1, 27));
-                h[4][l] = F::add(mulc(x0, 48), mulc(x1, 64));
+                h[1][l] = F::add(mulc(x1, 3), x0);
+                h[2][l] = F::add(F::add(mulc(x1, 12), mulc(x0, 8)), mulc(sm, 6));
+                h[3][l] = F::add(F::add(mulc(x1, 27), mulc(x0, 27)), mulc(sm, 24));
+                h[4][l] = F::add(F::add(mulc(x1, 48), mulc(x0, 64)), mulc(sm, 60));
             }
         }
     }
-    fold_sc_tail<Rg, PART == 0>(a, b, active, slot, h, red, (size_t)blockIdx.z * gridDim.x + blockIdx.x);
-}
-template <class Rg> __global__ void __launch_bounds__(128, 3)
-k_fold_sc_round(const FoldScArgs a) {
-    typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
-    __shared__ u64 red[5 * TAU * 32];
-    __shared__ u64 s_mu[MAX_MU * TAU];
-    for (int i = threadIdx.x; i < a.n_f * TAU; i += blockDim.x) s_mu[i] = a.mu_pow[i];
-    __syncthreads();
-    if (blockIdx.z == 0) fold_sc_round_part<Rg, 0>(a, red, s_mu); else fold_sc_round_part<Rg, 1>(a, red, s_mu);
+    fold_sc_tail<Rg, true>(a, b, active, slot, h, red, blockIdx.x, role == 0);
 }
 
 }  // namespace lf

@@ -60,13 +60,14 @@ template <class Rg> struct SumcheckDriver {
         unsigned nblk; u64* partial;
         if (sc->kind == LF_COMB_FOLD) {
             const bool round1 = sc->dig && sc->applied == 0;
-            const unsigned gx = (unsigned)((n_pairs + 127) / 128); nblk = round1 ? gx : 2 * gx;     // rounds >= 2 run two thread sets (blockIdx.z)
+            const unsigned gx1 = (unsigned)((n_pairs + 127) / 128), gx2 = (unsigned)((n_pairs + 63) / 64);      // rounds >= 2: two lanes per pair
+            nblk = round1 ? gx1 : gx2;
             partial = E.partial_dev((size_t)nblk * 5 * D);
             FoldScArgs a; a.dense = sc->dense.cur; a.dense_pitch = sc->dense.pitch; a.dense_stride = sc->dense.stride; a.mu_pow = sc->d_mu_pow; a.n_f = sc->n_f;
             a.n_pairs = n_pairs; a.partial = partial; a.dig = sc->dig; a.dig_pitch = sc->dig_pitch; a.dig_stride = sc->dig_stride;
             a.fh = sc->fh.cur; a.fh_pitch = sc->fh.pitch; a.fh_stride = sc->fh.stride;
-            if (round1) E.launch("k_fold_sc_round1", [&] { k_fold_sc_round1<Rg><<<dim3(gx, S), 128, 0, E.st()>>>(a); });
-            else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(gx, S, 2), 128, 0, E.st()>>>(a); });
+            if (round1) E.launch("k_fold_sc_round1", [&] { k_fold_sc_round1<Rg><<<dim3(gx1, S), 128, 0, E.st()>>>(a); });
+            else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(gx2, S), 128, 0, E.st()>>>(a); });
         } else {
             nblk = (unsigned)std::min<size_t>((n_pairs + 127) / 128, 148 * 8); partial = E.partial_dev((size_t)nblk * ne * D);
             ScGenericArgs a = sc->gen; a.pitch = sc->dense.pitch; a.n_pairs = n_pairs; a.partial = partial; a.coef = sc->d_coef;
