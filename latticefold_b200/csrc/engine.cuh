@@ -192,8 +192,12 @@ template <class Rg> struct Engine {
             launch("k_reduce_allreduce_p2p", [&] { k_reduce_allreduce_p2p<F><<<grid, 128, 0, st()>>>(partial, nblk, (int)nout, d_out, x); });
             return;
         }
-        launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(partial, nblk, (int)nout, d_out); });
+        reduce_partials(partial, nblk, nout, d_out);
         allreduce_field(d_out, nout);
+    }
+    void reduce_partials(const u64* partial, int nblk, size_t nout, u64* d_out) {
+        if (nblk >= 64 && nout <= 4096) launch("k_reduce_partials", [&] { k_reduce_partials_wide<F><<<blocks_for(nout, 32), 256, 0, st()>>>(partial, nblk, (int)nout, d_out); });
+        else launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(partial, nblk, (int)nout, d_out); });
     }
     // sum mod p across ranks of `words` field elements at dev (in place)
     void allreduce_field(u64* dev, size_t words) {

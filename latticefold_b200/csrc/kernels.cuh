@@ -54,6 +54,16 @@ template <class F> __global__ void k_reduce_partials(const u64* __restrict__ par
     for (int b = 0; b < nblk; ++b) acc = F::add(acc, partial[(size_t)b * nout + j]);
     out[j] = acc;
 }
+// the same sum for few outputs and many blocks (a sumcheck round: 120 outputs, up to ~1200 block partials): 8 lanes per output
+// walk the blocks and combine by shuffles, so a warp still reads 4 x 8 consecutive words per request
+template <class F> __global__ void __launch_bounds__(256) k_reduce_partials_wide(const u64* __restrict__ partial, int nblk, int nout, u64* __restrict__ out) {
+    const int g = blockIdx.x * (blockDim.x / 8) + threadIdx.x / 8, sub = threadIdx.x & 7;      // output g, lane group member sub
+    u64 acc = 0;
+    if (g < nout) for (int b = sub; b < nblk; b += 8) acc = F::add(acc, partial[(size_t)b * nout + g]);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) acc = F::add(acc, __shfl_down_sync(0xffffffffu, acc, o, 8));
+    if (g < nout && sub == 0) out[g] = acc;
+}
 
 // ------------------------------------------------------------------------------------------------ multi-GPU helpers
 // NCCL has no "sum mod p": a field element is sent as two 32-bit halves in u64 lanes, summed with ncclSum (world * 2^32

@@ -82,7 +82,7 @@ template <class Rg> struct SumcheckDriver {
         }
         u64* d_out = E.small_dev((size_t)ne * D);
         if (sc->sharded) E.reduce_partials_allreduce(partial, (int)nblk, (size_t)ne * D, d_out);      // one all-reduce of (deg+1) ring elements per round, fused with the reduction
-        else E.launch("k_reduce_partials", [&] { k_reduce_partials<F><<<Engine<Rg>::blocks_for((size_t)ne * D, 128), 128, 0, E.st()>>>(partial, (int)nblk, ne * D, d_out); });
+        else E.reduce_partials(partial, (int)nblk, (size_t)ne * D, d_out);
         E.download_words(d_out, (size_t)ne * D, out_host);
         sc->round += 1;
     }
