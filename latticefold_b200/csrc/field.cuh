@@ -71,6 +71,20 @@ struct Acc192 {
             : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(o1), "+r"(o2), "+r"(o3)
             : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     }
+    // a < 2^32: two wide multiplies instead of four
+    LF_HD void mac_small(u32 a, u64 b) {
+        u32 b0 = (u32)b, b1 = (u32)(b >> 32);
+        asm("mad.lo.cc.u32 %0, %8, %9, %0;\n\t"
+            "madc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+            "addc.cc.u32 %2, %2, 0;\n\t"
+            "addc.cc.u32 %3, %3, 0;\n\t"
+            "addc.u32 %4, %4, 0;\n\t"
+            "mad.lo.cc.u32 %5, %8, %10, %5;\n\t"
+            "madc.hi.cc.u32 %6, %8, %10, %6;\n\t"
+            "addc.u32 %7, %7, 0;"
+            : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(o1), "+r"(o2), "+r"(o3)
+            : "r"(a), "r"(b0), "r"(b1));
+    }
     LF_HD void add(u64 a) {
         u32 a0 = (u32)a, a1 = (u32)(a >> 32);
         asm("add.cc.u32 %0, %0, %5;\n\taddc.cc.u32 %1, %1, %6;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.cc.u32 %3, %3, 0;\n\taddc.u32 %4, %4, 0;"
@@ -89,6 +103,7 @@ struct Acc192 {
         u128 x = (u128)a * b; u128 s = (u128)h0 + (u64)x; h0 = (u64)s;
         s = (u128)h1 + (u64)(x >> 64) + (u64)(s >> 64); h1 = (u64)s; h2 += (u64)(s >> 64);
     }
+    LF_HD void mac_small(u32 a, u64 b) { mac((u64)a, b); }
     LF_HD void add(u64 a) { u128 s = (u128)h0 + a; h0 = (u64)s; s = (u128)h1 + (u64)(s >> 64); h1 = (u64)s; h2 += (u64)(s >> 64); }
     LF_HD void words(u64& w0, u64& w1, u32& w2) const { w0 = h0; w1 = h1; w2 = (u32)h2; }
 #endif
@@ -227,7 +242,7 @@ template <u64 P_, u64 NU_, bool SMALL> struct ModField {
     static LF_HD_CALL u64 mul(u64 a, u64 b) { if (SMALL) return (a * b) % P; return (u64)(((u128)a * b) % P); }
     static LF_HD u64 sqr(u64 a) { return mul(a, a); }
     static LF_HD u64 mul_nu(u64 a) { return mul(a, NU); }
-    struct Acc { u64 v; LF_HD void clear() { v = 0; } LF_HD void mac(u64 a, u64 b) { v = ModField::add(v, ModField::mul(a, b)); } LF_HD void add(u64 a) { v = ModField::add(v, a % P); } };
+    struct Acc { u64 v; LF_HD void clear() { v = 0; } LF_HD void mac(u64 a, u64 b) { v = ModField::add(v, ModField::mul(a, b)); } LF_HD void mac_small(u32 a, u64 b) { mac((u64)a, b); } LF_HD void add(u64 a) { v = ModField::add(v, a % P); } };
     typedef Acc Sum;
     static LF_HD u64 reduce(const Acc& a) { return a.v; }
     static LF_HD_CALL u64 reduce128(u64 lo, u64 hi) { return (u64)((((u128)hi << 64) | lo) % P); }
@@ -261,12 +276,14 @@ struct BabyBear {
         LF_HD void mac(u64 a, u64 b) {
             asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;" : "+r"(e0), "+r"(e1), "+r"(e2) : "r"((u32)a), "r"((u32)b));
         }
+        LF_HD void mac_small(u32 a, u64 b) { mac((u64)a, b); }
         LF_HD void add(u64 a) { asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+r"(e0), "+r"(e1), "+r"(e2) : "r"((u32)a), "r"((u32)(a >> 32))); }
         LF_HD u64 fold() const { return ((u64)e2 * C64 + (u64)e1 * C32 + e0) % P; }      // < 2^61 + 2^60 + 2^32
 #else
         u128 v;
         LF_HD void clear() { v = 0; }
         LF_HD void mac(u64 a, u64 b) { v += (u128)a * b; }
+        LF_HD void mac_small(u32 a, u64 b) { mac((u64)a, b); }
         LF_HD void add(u64 a) { v += a; }
         LF_HD u64 fold() const { return (u64)(v % P); }
 #endif

@@ -634,23 +634,27 @@ k_fold_sc_round1(const FoldScArgs a) {
 #pragma unroll
         for (int l = 0; l < TAU; ++l) h[e][l] = 0;
     if (active) {
-        typename F::Acc p2[TAU], n2[TAU], p3[TAU], n3[TAU];   // positive / negative parts of h(2), h(3)
+        // g(X) = f(X)^3 - f(X) is one of 0, +-6, +-24 at X = 2 and 0, +-6, ..., +-120 at X = 3.  The signed weights are shifted to
+        // non-negative ones (g + 24, g + 120) so that every table feeds the same branch-free small-multiplier MACs -- no lane
+        // divergence on the digits, and the loads of several tables can be in flight together -- and the shift is taken out
+        // again as 24 / 120 times the sum of all mu.
+        typename F::Acc a2[TAU], a3[TAU], am[TAU];
 #pragma unroll
-        for (int l = 0; l < TAU; ++l) { p2[l].clear(); n2[l].clear(); p3[l].clear(); n3[l].clear(); }
-        const int K2 = a.n_f / TAU;
-        for (int k = 0; k < K2; ++k)
+        for (int l = 0; l < TAU; ++l) { a2[l].clear(); a3[l].clear(); am[l].clear(); }
+#pragma unroll 4
+        for (int kd = 0; kd < a.n_f; ++kd) {
+            const int k = kd / TAU, d = kd - k * TAU;
+            const char2 dd = *reinterpret_cast<const char2*>(a.dig + (size_t)k * a.dig_stride + (size_t)(d * S + slot) * a.dig_pitch + 2 * b);
+            const int f2 = 2 * dd.y - dd.x, f3 = 3 * dd.y - 2 * dd.x;
+            const u32 g2 = (u32)(f2 * f2 * f2 - f2 + 24), g3 = (u32)(f3 * f3 * f3 - f3 + 120);
+            const u64* mu = &s_mu[kd * TAU];
 #pragma unroll
-            for (int d = 0; d < TAU; ++d) {
-                const char2 dd = *reinterpret_cast<const char2*>(a.dig + (size_t)k * a.dig_stride + (size_t)(d * S + slot) * a.dig_pitch + 2 * b);
-                const int f2 = 2 * dd.y - dd.x, f3 = 3 * dd.y - 2 * dd.x;
-                const int g2 = f2 * f2 * f2 - f2, g3 = f3 * f3 * f3 - f3;
-                const u64* mu = &s_mu[(k * TAU + d) * TAU];
-                if (g2 > 0) { for (int l = 0; l < TAU; ++l) p2[l].mac((u64)g2, mu[l]); } else if (g2 < 0) { for (int l = 0; l < TAU; ++l) n2[l].mac((u64)(-g2), mu[l]); }
-                if (g3 > 0) { for (int l = 0; l < TAU; ++l) p3[l].mac((u64)g3, mu[l]); } else if (g3 < 0) { for (int l = 0; l < TAU; ++l) n3[l].mac((u64)(-g3), mu[l]); }
-            }
+            for (int l = 0; l < TAU; ++l) { a2[l].mac_small(g2, mu[l]); a3[l].mac_small(g3, mu[l]); am[l].add(mu[l]); }
+        }
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
-            const u64 h2 = F::sub(F::reduce(p2[l]), F::reduce(n2[l])), h3 = F::sub(F::reduce(p3[l]), F::reduce(n3[l]));
+            const u64 ms = F::reduce(am[l]);
+            const u64 h2 = F::sub(F::reduce(a2[l]), F::mul(ms, 24)), h3 = F::sub(F::reduce(a3[l]), F::mul(ms, 120));
             h[2][l] = h2; h[3][l] = h3;
             // h(0) = h(1) = 0 and third differences constant: h(4) = 4 h(3) - 6 h(2)
             const u64 h3x2 = F::add(h3, h3), h3x4 = F::add(h3x2, h3x2), h2x2 = F::add(h2, h2), h2x6 = F::add(F::add(h2x2, h2x2), h2x2);
