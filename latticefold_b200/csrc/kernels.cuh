@@ -361,13 +361,14 @@ template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, cons
     for (int l = 0; l < TAU; ++l) acc[l].clear();
     for (u32 e = row_ptr[row]; e < row_ptr[row + 1]; ++e) {
         u64 v[TAU], z[TAU]; const size_t c = col[e];
+        // the tail may be the all-gathered concatenation of per-rank slabs: chunk r lives at z_tail + r * tail_chunk_stride
+        // (one 64-bit division per non-zero, skipped on the unsharded path where the tail is one chunk)
+        const size_t tc = c - head_len;
+        const size_t toff = tail_chunk == ~(size_t)0 ? tc : (tc / tail_chunk) * tail_chunk_stride + (tc % tail_chunk);
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
             v[l] = val[(size_t)(slot * TAU + l) * val_pitch + e];
-            // the tail may be the all-gathered concatenation of per-rank slabs: chunk r lives at z_tail + r * tail_chunk_stride
-            const size_t tc = c - head_len;
-            z[l] = c < head_len ? z_head[(size_t)(slot * TAU + l) * head_pitch + c]
-                                : z_tail[(tc / tail_chunk) * tail_chunk_stride + (size_t)(slot * TAU + l) * tail_pitch + (tc % tail_chunk)];
+            z[l] = c < head_len ? z_head[(size_t)(slot * TAU + l) * head_pitch + c] : z_tail[toff + (size_t)(slot * TAU + l) * tail_pitch];
         }
         SF::mac(acc, v, SF::prep(z));
     }

@@ -140,7 +140,7 @@ template <class Rg> struct Prover {
         HV beta = sf_to_ring(squeeze(T, "beta_s", s));                                                       // linearization/utils.rs:113-124
         MzSet mz = alloc_mz(1);
         { const size_t words = w->w_pitch * D; u64* tail = gather_wccs(w->w_ccs, words);
-          compute_mz(mz, 0, head, tail, w->w_pitch, w->W * world(), w->W, words);
+          compute_mz(mz, 0, head, tail, w->w_pitch, w->W * world(), world() == 1 ? ~(size_t)0 : w->W, words);
           if (tail != w->w_ccs) E.dfree(tail); }
         // sumcheck list: for each term with c_i != 0, the Mz named by S_i; eq(beta,.) last (linearization/utils.rs:63-88)
         std::vector<int> list; for (size_t i = 0; i < P->q; ++i) { bool z = true; for (int l = 0; l < D; ++l) z = z && P->c[i * D + l] == 0; if (z) continue; for (int j : P->S[i]) list.push_back(j); }
@@ -254,7 +254,7 @@ template <class Rg> struct Prover {
         mark("dec.v_s");
         // compute_mz_mles / compute_u_s (decomposition.rs:214-256): z_k = x_s[k] || w_ccs_k
         { const size_t words = (size_t)K * sb.wc_stride; u64* all = gather_wccs(wccs, words);     // one all-gather per decomposition
-          compute_mz_batch(sb.mz, half * K, K, o.x_s, all, sb.wc_pitch, sb.wc_stride, w->W * world(), w->W, words);
+          compute_mz_batch(sb.mz, half * K, K, o.x_s, all, sb.wc_pitch, sb.wc_stride, w->W * world(), world() == 1 ? ~(size_t)0 : w->W, words);
           if (all != wccs) E.dfree(all); }
         o.u_pin = eval_mz_async(sb.mz, half * K * (int)P->t, K * (int)P->t, eq_r);
         mark("dec.mz_u_s");
