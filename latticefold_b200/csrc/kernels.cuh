@@ -147,12 +147,19 @@ k_matrix_apply(const TIn* __restrict__ in, size_t in_pitch, u64* __restrict__ ou
     in += (size_t)blockIdx.y * in_batch_stride; out += (size_t)blockIdx.y * out_batch_stride;      // blockIdx.y = vector of a batch
     __shared__ u64 s_in[D][matrix_apply_tpb<Rg>()];
     __shared__ int s_idx[D * NNZ]; __shared__ u64 s_val[D * NNZ];
+    __shared__ u64 s_corr[D];      // digits only: 128 * (sum of the row's table values), see below
     for (int i = threadIdx.x; i < D * NNZ; i += blockDim.x) { s_idx[i] = tab_idx[i]; s_val[i] = tab_val[i]; }
+    constexpr bool DIGITS = sizeof(TIn) == 1;
+    if (DIGITS) {
+        // balanced digits are small signed integers: shifted to d + 128 >= 0 they feed the two-multiply small MAC, and the
+        // shift leaves as 128 * rowsum (a full 64 x 64 MAC with the field image of -1 = p - 1 would cost twice as much)
+        for (int r = threadIdx.x; r < D; r += blockDim.x) { u64 sum = 0; for (int c = 0; c < NNZ; ++c) sum = F::add(sum, tab_val[r * NNZ + c]); s_corr[r] = F::mul(sum, 128); }
+    }
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) {
 #pragma unroll
         for (int l = 0; l < D; ++l) {
-            if (sizeof(TIn) == 1) s_in[l][threadIdx.x] = F::from_i64((int64_t)(int8_t)in[(size_t)l * in_pitch + e]);
+            if (DIGITS) s_in[l][threadIdx.x] = (u64)((int)(int8_t)in[(size_t)l * in_pitch + e] + 128);
             else s_in[l][threadIdx.x] = (u64)in[(size_t)l * in_pitch + e];
         }
     }
@@ -162,8 +169,11 @@ k_matrix_apply(const TIn* __restrict__ in, size_t in_pitch, u64* __restrict__ ou
     for (int r = 0; r < D; ++r) {
         typename F::Acc a; a.clear();
 #pragma unroll
-        for (int c = 0; c < NNZ; ++c) a.mac(s_val[r * NNZ + c], s_in[s_idx[r * NNZ + c]][threadIdx.x]);
-        out[(size_t)r * out_pitch + e] = F::reduce(a);
+        for (int c = 0; c < NNZ; ++c) {
+            if (DIGITS) a.mac_small((u32)s_in[s_idx[r * NNZ + c]][threadIdx.x], s_val[r * NNZ + c]);
+            else a.mac(s_val[r * NNZ + c], s_in[s_idx[r * NNZ + c]][threadIdx.x]);
+        }
+        out[(size_t)r * out_pitch + e] = DIGITS ? F::sub(F::reduce(a), s_corr[r]) : F::reduce(a);
     }
 }
 

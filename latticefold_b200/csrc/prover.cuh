@@ -17,6 +17,8 @@ struct lf_witness { lf::u64 *f = nullptr, *f_coeff = nullptr, *w_ccs = nullptr; 
 struct lf_prover {
     lf_ctx* ctx = nullptr;
     lf_ctx* aux = nullptr;         // second stream + scratch: the accumulator's decomposition runs beside the linearization
+    cudaEvent_t acc_ready = nullptr;   // host-buffer entry point: recorded when the accumulator witness is on the device, so that its
+                                       // decomposition starts while the incoming witness is still being copied
     int ring = 0, L = 0, K = 0; uint64_t B = 0, b = 0;
     size_t kappa = 0, n = 0;
     size_t m = 0, n_ccs = 0, l = 0, t = 0, q = 0, d = 0, s = 0;
@@ -403,10 +405,10 @@ template <class Rg> struct Prover {
         LCCCS a; auto ld = [&](const u64* p, size_t n) { if (!p && n) throw LfException(LF_ERR_INVALID_ARG, "accumulator field is NULL"); return HV(p, p + n * D); };
         a.r = ld(in.acc_r, P->s); a.v = ld(in.acc_v, TAU); a.cm = ld(in.acc_cm, P->kappa); a.u = ld(in.acc_u, P->t); a.x_w = ld(in.acc_x_w, P->l); a.h = ld(in.acc_h, 1); return a;
     }
-    lf_witness* prove(const lf_problem& in, const lf_witness* w_acc, const lf_witness* w_i, Transcript<Rg>& T, u64* out_proof, u64* out_lcccs) {
+    lf_witness* prove(const lf_problem& in, const lf_witness* w_acc, const lf_witness* w_i, Transcript<Rg>& T, u64* out_proof, u64* out_lcccs, bool presynced = false) {
         using clk = std::chrono::steady_clock; auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         for (double& x : P->timings) x = 0;
-        E.sync(); E.arena_reset();
+        if (!presynced) { E.sync(); E.arena_reset(); }      // presynced: the caller did both before queueing the witness uploads
         P->detail = std::getenv("LF_TIMING_DETAIL") != nullptr; P->marks.clear(); P->last_mark = clk::now();
         auto t_begin = clk::now();
         sanity_check();
@@ -434,8 +436,9 @@ template <class Rg> struct Prover {
             lf_ctx* main_ctx = E.c;
             if (overlap) {
                 lf_ctx* aux = aux_ctx();
-                cudaEvent_t ready; LF_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)); LF_CUDA(cudaEventRecord(ready, main_ctx->stream));
-                LF_CUDA(cudaStreamWaitEvent(aux->stream, ready, 0)); cudaEventDestroy(ready);
+                if (P->acc_ready) { LF_CUDA(cudaStreamWaitEvent(aux->stream, P->acc_ready, 0)); }
+                else { cudaEvent_t ready; LF_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)); LF_CUDA(cudaEventRecord(ready, main_ctx->stream));
+                       LF_CUDA(cudaStreamWaitEvent(aux->stream, ready, 0)); cudaEventDestroy(ready); }
                 aux->arena_off = 0; aux->profiling = main_ctx->profiling;
                 E.c = aux;
             }

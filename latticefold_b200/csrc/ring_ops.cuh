@@ -286,8 +286,15 @@ template <class Rg> struct RingOpsImpl final : RingOps {
     }
     void nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, uint64_t* out_f) override {
         Prover<Rg> pr(p);
-        lf_witness* wa = pr.upload_witness(in->w_acc_f); lf_witness* wi = pr.upload_witness(in->w_i_f);
-        lf_witness* w = pr.prove(*in, wa, wi, tr(t), out_proof, out_lcccs);
+        pr.E.sync(); pr.E.arena_reset();
+        lf_witness* wa = pr.upload_witness(in->w_acc_f);
+        if (!p->acc_ready) LF_CUDA(cudaEventCreateWithFlags(&p->acc_ready, cudaEventDisableTiming));
+        LF_CUDA(cudaEventRecord(p->acc_ready, pr.E.st()));
+        lf_witness* wi = pr.upload_witness(in->w_i_f);
+        lf_witness* w = nullptr;
+        cudaEvent_t ev = p->acc_ready;
+        try { w = pr.prove(*in, wa, wi, tr(t), out_proof, out_lcccs, true); } catch (...) { p->acc_ready = nullptr; cudaEventDestroy(ev); pr.free_witness(wa); pr.free_witness(wi); throw; }
+        p->acc_ready = nullptr; cudaEventDestroy(ev);
         if (out_f) pr.E.download_planes(w->f, w->pitch, w->n, out_f);
         pr.free_witness(w); pr.free_witness(wa); pr.free_witness(wi); pr.E.sync();
     }
