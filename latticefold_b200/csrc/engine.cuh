@@ -70,8 +70,14 @@ struct lf_ctx {
     int rank = 0, world = 1; lf_collective_fn coll = nullptr; void* coll_user = nullptr; uint64_t collectives = 0;
     void* nccl = nullptr;          // ncclComm_t when the collectives run on this context's stream (no host round trip)
     // peer-memory mailboxes (k_reduce_allreduce_p2p): this rank's region and the IPC mappings of every peer's
-    struct XGpu { bool on = false; void* region = nullptr; void* peer_region[8] = {nullptr}; lf::u64* inbox[8] = {nullptr}; unsigned long long* flags[8] = {nullptr};
-                  size_t cap = 0; unsigned long long calls = 0, blocks = 0; } xg;
+    // Two channels per region: channel 0 serves this context's stream, channel 1 the prover's auxiliary stream (the accumulator's
+    // decomposition runs beside the linearization), each with its own call sequence.
+    struct XGpu { bool on = false; void* region = nullptr; void* peer_region[8] = {nullptr}; unsigned char* base[8] = {nullptr};
+                  lf::u64* inbox[8] = {nullptr}; unsigned long long* flags[8] = {nullptr};
+                  size_t cap = 0; unsigned long long calls = 0, blocks = 0;
+                  // channel 1 outlives any one prover's auxiliary context (the flags are monotone counters that are never reset), so
+                  // its call sequence is kept here, in the owning context; an auxiliary context points at its parent
+                  unsigned long long aux_calls = 0, aux_blocks = 0; XGpu* parent = nullptr; } xg;
     bool profiling = false;
     struct ProfRec { const char* name; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
@@ -152,7 +158,9 @@ template <class Rg> struct Engine {
     }
     void check_err_flag(int code, const char* msg) {
         int h = 0; LF_CUDA(cudaMemcpyAsync(&h, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, st())); sync();
-        if (h) { LF_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), st())); throw LfException(code, msg); }
+        if (h) { LF_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), st()));
+                 if (h == 2) throw LfException(LF_ERR_CUDA, "peer-memory all-reduce timed out waiting for another rank");
+                 throw LfException(code, msg); }
     }
     // host elements -> small SoA device vector, staged through the pinned arena (asynchronous)
     void upload_small(const u64* host, size_t n, u64* dev, size_t pitch) {
@@ -181,14 +189,17 @@ template <class Rg> struct Engine {
         if (c->coll(c->coll_user, op, dev, words) != 0) throw LfException(LF_ERR_CUDA, "collective callback failed");
     }
     static constexpr size_t XG_CAP = 16384, XG_FLAG_BYTES = 256;      // mailbox words per (parity, source); flag area in front
+    static constexpr size_t XG_CHANNEL_BYTES = XG_FLAG_BYTES + 2 * 8 * XG_CAP * sizeof(u64), XG_CHANNELS = 2;
     // out[j] = sum over ranks of (sum_b partial[b * nout + j]): one kernel with peer stores when the mailboxes are mapped,
     // otherwise the local reduction followed by the NCCL all-reduce
     void reduce_partials_allreduce(const u64* partial, int nblk, size_t nout, u64* d_out) {
         if (sharded() && c->xg.on && nout <= c->xg.cap) {
             const unsigned grid = blocks_for(nout, 128);
             XgArgs x; for (int r = 0; r < 8; ++r) { x.inbox[r] = c->xg.inbox[r]; x.flags[r] = c->xg.flags[r]; }
-            x.rank = c->rank; x.world = c->world; x.parity = (unsigned)(c->xg.calls & 1); x.cap = c->xg.cap;
-            c->xg.blocks += grid; c->xg.calls += 1; x.expected = c->xg.blocks; ++c->collectives;
+            unsigned long long& calls = c->xg.parent ? c->xg.parent->aux_calls : c->xg.calls;
+            unsigned long long& blocks = c->xg.parent ? c->xg.parent->aux_blocks : c->xg.blocks;
+            x.rank = c->rank; x.world = c->world; x.parity = (unsigned)(calls & 1); x.cap = c->xg.cap; x.err = c->d_err;
+            blocks += grid; calls += 1; x.expected = blocks; ++c->collectives;
             launch("k_reduce_allreduce_p2p", [&] { k_reduce_allreduce_p2p<F><<<grid, 128, 0, st()>>>(partial, nblk, (int)nout, d_out, x); });
             return;
         }

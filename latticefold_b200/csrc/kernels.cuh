@@ -86,7 +86,7 @@ template <class F> __global__ void k_combine_limbs(const u64* __restrict__ in, u
 // atomic on every rank's flag, waits until all blocks of all sources have delivered to it, and adds the world values mod p in
 // rank order (exact arithmetic: any order gives the same canonical element).  Two parities: a rank can only be one call ahead of
 // a peer (call k+1 cannot complete before every peer has finished call k), so slot k+2 never overwrites data still being read.
-struct XgArgs { u64* inbox[8]; unsigned long long* flags[8]; int rank, world; unsigned parity; size_t cap; unsigned long long expected; };
+struct XgArgs { u64* inbox[8]; unsigned long long* flags[8]; int rank, world; unsigned parity; size_t cap; unsigned long long expected; int* err; };
 template <class F> __global__ void __launch_bounds__(128)
 k_reduce_allreduce_p2p(const u64* __restrict__ partial, int nblk, int nout, u64* __restrict__ out, const XgArgs x) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,7 +101,10 @@ k_reduce_allreduce_p2p(const u64* __restrict__ partial, int nblk, int nout, u64*
     if (threadIdx.x < x.world) {
         atomicAdd_system(x.flags[threadIdx.x] + x.rank, 1ULL);                  // publish to rank threadIdx.x
         const volatile unsigned long long* f = x.flags[x.rank] + threadIdx.x;   // and wait for source threadIdx.x
-        while (*f < x.expected) { }
+        // bounded spin (a rank that died must not hang the others' GPUs): ~2 s, then the error flag (2) is raised and the
+        // host reports LF_ERR_CUDA at its next flag check
+        unsigned long long spins = 0;
+        while (*f < x.expected) { if (++spins > (1ULL << 28)) { atomicExch(x.err, 2); break; } }
         __threadfence_system();
     }
     __syncthreads();

@@ -48,7 +48,7 @@ void lf_ctx_destroy(lf_ctx* c) {
     cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
     for (int r = 0; r < 8; ++r) if (c->xg.peer_region[r]) cudaIpcCloseMemHandle(c->xg.peer_region[r]);
     if (c->xg.region) cudaFree(c->xg.region);
-    if (c->nccl) NcclApi::get().CommDestroy(c->nccl);
+    if (c->nccl && !c->shared_tables) NcclApi::get().CommDestroy(c->nccl);      // an auxiliary context borrows its parent's communicator
     for (auto& kv : c->block_size) cudaFree(kv.first);
     if (!c->shared_tables) { for (int i = 0; i < 2; ++i) { cudaFree(c->d_tab_idx[i]); cudaFree(c->d_tab_val[i]); } try { ops(c->ring)->ctx_tables_destroy(c); } catch (...) {} }
     cudaFree(c->d_err); cudaFree(c->d_small); cudaFree(c->d_partial); if (c->h_pinned) cudaFreeHost(c->h_pinned); if (c->h_arena) cudaFreeHost(c->h_arena);
@@ -82,7 +82,7 @@ lf_status lf_ctx_p2p_export(lf_ctx* c, uint8_t* out_handle64) {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
         LF_CUDA(cudaSetDevice(c->device));
         if (!c->xg.region) {
-            const size_t cap = Engine<GoldilocksRing>::XG_CAP, bytes = Engine<GoldilocksRing>::XG_FLAG_BYTES + 2 * 8 * cap * sizeof(u64);
+            const size_t cap = Engine<GoldilocksRing>::XG_CAP, bytes = Engine<GoldilocksRing>::XG_CHANNELS * Engine<GoldilocksRing>::XG_CHANNEL_BYTES;
             LF_CUDA(cudaMalloc(&c->xg.region, bytes)); LF_CUDA(cudaMemset(c->xg.region, 0, bytes)); LF_CUDA(cudaDeviceSynchronize());
             c->xg.cap = cap;
         }
@@ -101,6 +101,7 @@ lf_status lf_ctx_p2p_import(lf_ctx* c, int32_t rank, int32_t world, const uint8_
                 cudaIpcMemHandle_t h; std::memcpy(&h, handles + 64 * r, 64);
                 LF_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess)); c->xg.peer_region[r] = base;
             }
+            c->xg.base[r] = (unsigned char*)base;
             c->xg.flags[r] = (unsigned long long*)base;
             c->xg.inbox[r] = (u64*)((unsigned char*)base + Engine<GoldilocksRing>::XG_FLAG_BYTES);
         }

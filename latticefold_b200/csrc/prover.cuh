@@ -136,12 +136,14 @@ template <class Rg> struct Prover {
 
     // ------------------------------------------------------------------ linearization (linearization.rs:145-189)
     struct LinOut { LCCCS lc; HV msgs; DevVec eq_r; };
-    LinOut linearize(const HV& cm_i_cm, const HV& x_ccs, const lf_witness* w, Transcript<Rg>& T) {
+    // pre_tail: the all-gathered w_ccs slabs when the caller has already queued that collective (the sharded step issues it before
+    // the accumulator's decomposition so that NCCL's cross-stream ordering does not park the linearization behind the auxiliary stream)
+    LinOut linearize(const HV& cm_i_cm, const HV& x_ccs, const lf_witness* w, Transcript<Rg>& T, u64* pre_tail = nullptr) {
         LinOut o; const int s = (int)P->s; const size_t m = ml();    // tables hold this rank's slab
         HV head = x_ccs; { El one = HR::from_u64(1); head.insert(head.end(), one.begin(), one.end()); }      // z = x || 1 || w  (arith.rs:399-409)
         HV beta = sf_to_ring(squeeze(T, "beta_s", s));                                                       // linearization/utils.rs:113-124
         MzSet mz = alloc_mz(1);
-        { const size_t words = w->w_pitch * D; u64* tail = gather_wccs(w->w_ccs, words);
+        { const size_t words = w->w_pitch * D; u64* tail = pre_tail ? pre_tail : gather_wccs(w->w_ccs, words);
           compute_mz(mz, 0, head, tail, w->w_pitch, w->W * world(), world() == 1 ? ~(size_t)0 : w->W, words);
           if (tail != w->w_ccs) E.dfree(tail); }
         // sumcheck list: for each term with c_i != 0, the Mz named by S_i; eq(beta,.) last (linearization/utils.rs:63-88)
@@ -396,6 +398,11 @@ template <class Rg> struct Prover {
         for (int i = 0; i < 2; ++i) { a->d_tab_idx[i] = m->d_tab_idx[i]; a->d_tab_val[i] = m->d_tab_val[i]; }
         LF_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking));
         LF_CUDA(cudaMalloc(&a->d_err, sizeof(int))); LF_CUDA(cudaMemset(a->d_err, 0, sizeof(int)));
+        if (m->world > 1 && m->nccl && m->xg.on) {      // sharded: same rank / communicator, channel 1 of the peer-memory mailboxes
+            a->rank = m->rank; a->world = m->world; a->nccl = m->nccl; a->xg.on = true; a->xg.cap = m->xg.cap; a->xg.parent = &m->xg;
+            for (int r = 0; r < m->world; ++r) { unsigned char* b = m->xg.base[r] + Engine<Rg>::XG_CHANNEL_BYTES;
+                a->xg.flags[r] = (unsigned long long*)b; a->xg.inbox[r] = (u64*)(b + Engine<Rg>::XG_FLAG_BYTES); }
+        }
         P->aux = a.release(); return P->aux;
     }
     // ------------------------------------------------------------------ NIFSProver::prove (nifs.rs:48-103)
@@ -430,7 +437,9 @@ template <class Rg> struct Prover {
         sb.wc_pitch = pitch_of(w_i->W); sb.wc_stride = sb.wc_pitch * D; sb.wccs = E.template dalloc<u64>((size_t)2 * K * sb.wc_stride);
         sb.mz = alloc_mz(2 * K);
         DevVec eq_acc; eq_acc.n = ((size_t)1 << cnt(acc.r)) / world(); eq_acc.pitch = pitch_of(eq_acc.n); eq_acc.p = E.template dalloc<u64>(eq_acc.pitch * D);
-        const bool overlap = world() == 1 && !P->detail && !std::getenv("LF_NO_OVERLAP");
+        // sharded steps overlap too when the collectives are stream-ordered on both streams (own NCCL communicator + mailbox channels)
+        const bool overlap = (world() == 1 || (E.c->nccl && E.c->xg.on)) && !P->detail && !std::getenv("LF_NO_OVERLAP");
+        u64* lin_tail = (overlap && world() > 1) ? gather_wccs(w_i->w_ccs, w_i->w_pitch * D) : nullptr;
         DecPending pl;
         {
             lf_ctx* main_ctx = E.c;
@@ -450,7 +459,7 @@ template <class Rg> struct Prover {
         }
         mark("alloc+dec_acc_enqueue");
         auto t0 = clk::now();
-        LinOut lin = linearize(cm_i_cm, x_ccs, w_i, T);
+        LinOut lin = linearize(cm_i_cm, x_ccs, w_i, T, lin_tail);
         mark("linearize");
         E.sync(); auto t1 = clk::now(); P->timings[0] = ms(t0, t1);
         DecPending prr = decompose_enqueue(lin.lc, w_i, lin.eq_r, sb, 1);
@@ -460,7 +469,7 @@ template <class Rg> struct Prover {
         mark("decompose_new");
         if (P->aux) {      // fold the auxiliary context's bookkeeping (launch count, event pairs, digit-overflow flag) into the main one
             lf_ctx* m = E.c; lf_ctx* a = P->aux;
-            m->launches += a->launches; a->launches = 0;
+            m->launches += a->launches; a->launches = 0; m->collectives += a->collectives; a->collectives = 0;
             for (auto& r : a->prof) m->prof.push_back(r); a->prof.clear();
             E.c = a; try { E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_witness: a coefficient does not fit K digits of base b"); } catch (...) { E.c = m; throw; } E.c = m;
         }
