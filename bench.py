@@ -253,7 +253,7 @@ def main():
     a_bytes = alg.get(top_name)
     # DRAM bytes of this kernel from the committed `ncu --set full` capture (profiles/): largest launch (round 2 at C2) moved
     # 2.545 GB read + 5 MB written for 2.54 GB algorithmic; the batched commit 2.10 GB for 2.06 GB algorithmic
-    ncu_traffic = {"k_fold_sc_round": 2.551e9, "k_dot_commit": 2.145e9}
+    ncu_traffic = {"k_fold_sc_round": 2.578e9, "k_dot_commit": 2.086e9}      # profiles/r01d_*: 2.544 GB + 34 MB; 2.073 GB + 13.5 MB
     roofline = dict(bound="hbm", kernel=top_name, launches_per_step=top_cnt, avg_launch_ms=top_ms / top_cnt, share_of_kernel_time=top_ms / total_kernel_ms,
                     achieved=(a_bytes / 1e9) / (top_ms / 1e3) if a_bytes else None, peak=hbm, unit="GB/s",
                     frac=((a_bytes / 1e9) / (top_ms / 1e3) / hbm) if a_bytes else None,
