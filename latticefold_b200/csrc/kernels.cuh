@@ -101,10 +101,13 @@ k_reduce_allreduce_p2p(const u64* __restrict__ partial, int nblk, int nout, u64*
     if (threadIdx.x < x.world) {
         atomicAdd_system(x.flags[threadIdx.x] + x.rank, 1ULL);                  // publish to rank threadIdx.x
         const volatile unsigned long long* f = x.flags[x.rank] + threadIdx.x;   // and wait for source threadIdx.x
-        // bounded spin (a rank that died must not hang the others' GPUs): ~2 s, then the error flag (2) is raised and the
-        // host reports LF_ERR_CUDA at its next flag check
-        unsigned long long spins = 0;
-        while (*f < x.expected) { if (++spins > (1ULL << 28)) { atomicExch(x.err, 2); break; } }
+        // bounded spin (a rank that died must not hang the others' GPUs): 20 s on the global timer, then the error flag (2) is
+        // raised and the host reports LF_ERR_CUDA at its next flag check
+        unsigned long long t0 = 0, now = 0; unsigned spins = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*f < x.expected) {
+            if ((++spins & 1023u) == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); if (now - t0 > 20000000000ULL) { atomicExch(x.err, 2); break; } }
+        }
         __threadfence_system();
     }
     __syncthreads();
