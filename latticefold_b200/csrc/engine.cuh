@@ -194,6 +194,9 @@ template <class Rg> struct Engine {
     // otherwise the local reduction followed by the NCCL all-reduce
     void reduce_partials_allreduce(const u64* partial, int nblk, size_t nout, u64* d_out) {
         if (sharded() && c->xg.on && nout <= c->xg.cap) {
+            // many block partials (large shards): sum them with the wide reduction first and let the exchange kernel work in place --
+            // its own column sum walks the blocks serially, one thread per output
+            if (nblk >= 64) { reduce_partials(partial, nblk, nout, d_out); partial = nullptr; }
             const unsigned grid = blocks_for(nout, 128);
             XgArgs x; for (int r = 0; r < 8; ++r) { x.inbox[r] = c->xg.inbox[r]; x.flags[r] = c->xg.flags[r]; }
             unsigned long long& calls = c->xg.parent ? c->xg.parent->aux_calls : c->xg.calls;
@@ -207,7 +210,13 @@ template <class Rg> struct Engine {
         allreduce_field(d_out, nout);
     }
     void reduce_partials(const u64* partial, int nblk, size_t nout, u64* d_out) {
-        if (nblk >= 64 && nout <= 4096) launch("k_reduce_partials", [&] { k_reduce_partials_wide<F><<<blocks_for(nout, 32), 256, 0, st()>>>(partial, nblk, (int)nout, d_out); });
+        if (nblk > 512) {      // two levels: chunks of 32 blocks first
+            const int chunk = 32, nch = (nblk + chunk - 1) / chunk;
+            u64* tmp = dalloc<u64>((size_t)nch * nout);
+            launch("k_reduce_partials", [&] { k_reduce_chunks<F><<<dim3(blocks_for(nout, 128), nch), 128, 0, st()>>>(partial, nblk, (int)nout, chunk, tmp); });
+            reduce_partials(tmp, nch, nout, d_out); dfree(tmp); return;
+        }
+        if (nblk >= 64 && nout <= 16384) launch("k_reduce_partials", [&] { k_reduce_partials_wide<F><<<blocks_for(nout, 32), 256, 0, st()>>>(partial, nblk, (int)nout, d_out); });
         else launch("k_reduce_partials", [&] { k_reduce_partials<F><<<blocks_for(nout, 128), 128, 0, st()>>>(partial, nblk, (int)nout, d_out); });
     }
     // sum mod p across ranks of `words` field elements at dev (in place)

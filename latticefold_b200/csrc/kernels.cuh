@@ -54,6 +54,16 @@ template <class F> __global__ void k_reduce_partials(const u64* __restrict__ par
     for (int b = 0; b < nblk; ++b) acc = F::add(acc, partial[(size_t)b * nout + j]);
     out[j] = acc;
 }
+// first level for very many block partials (large shards: a FOLD round at 2^20 pairs leaves 16384 of them): the blocks are cut
+// into chunks of `chunk`, thread (output j, chunk c) sums its chunk with loads that are coalesced across j
+template <class F> __global__ void k_reduce_chunks(const u64* __restrict__ partial, int nblk, int nout, int chunk, u64* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (j >= nout) return;
+    const int b0 = c * chunk, b1 = min(nblk, b0 + chunk);
+    u64 acc = 0;
+    for (int b = b0; b < b1; ++b) acc = F::add(acc, partial[(size_t)b * nout + j]);
+    out[(size_t)c * nout + j] = acc;
+}
 // the same sum for few outputs and many blocks (a sumcheck round: 120 outputs, up to ~1200 block partials): 8 lanes per output
 // walk the blocks and combine by shuffles, so a warp still reads 4 x 8 consecutive words per request
 template <class F> __global__ void __launch_bounds__(256) k_reduce_partials_wide(const u64* __restrict__ partial, int nblk, int nout, u64* __restrict__ out) {
