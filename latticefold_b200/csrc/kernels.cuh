@@ -342,24 +342,65 @@ k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride,
 #pragma unroll
         for (int l = 0; l < TAU; ++l) acc[j][l].clear();
     const size_t x_begin = (size_t)blockIdx.x * x_per_block, x_end = min(n, x_begin + x_per_block);
-    for (size_t x = x_begin + threadIdx.x; x < x_end; x += blockDim.x) {
-        u64 e[TAU];
-#pragma unroll
-        for (int l = 0; l < TAU; ++l) e[l] = eq[(size_t)(slot * TAU + l) * eq_pitch + x];
-#pragma unroll
-        for (int j = 0; j < TAU; ++j) {
-            u64 c;
-            if (sizeof(TIn) == 1) c = F::from_i64((int64_t)(int8_t)cv[(size_t)(j * S + slot) * c_pitch + x]);
-            else c = (u64)cv[(size_t)(j * S + slot) * c_pitch + x];
-#pragma unroll
-            for (int l = 0; l < TAU; ++l) acc[j][l].mac(c, e[l]);
-        }
-    }
     u64 v[TAU * TAU];
+    if constexpr (sizeof(TIn) == 1) {
+        // digit planes: four consecutive x per thread (one 4-byte digit load per plane, two 16-byte eq loads per limb); the signed
+        // digits are shifted to d + 128 >= 0 for the two-multiply small MAC and the shift leaves as 128 * sum_x eq[x]
+        typename F::Sum se[TAU];
 #pragma unroll
-    for (int j = 0; j < TAU; ++j)
+        for (int l = 0; l < TAU; ++l) se[l].clear();
+        const size_t x_vec_end = x_begin + ((x_end - x_begin) & ~(size_t)3);       // x_begin is a multiple of x_per_block (a multiple of 4)
+        for (size_t x = x_begin + 4 * (size_t)threadIdx.x; x < x_vec_end; x += 4 * (size_t)blockDim.x) {
+            u64 e[TAU][4];
 #pragma unroll
-        for (int l = 0; l < TAU; ++l) v[j * TAU + l] = F::reduce(acc[j][l]);
+            for (int l = 0; l < TAU; ++l) {
+                const ulonglong2* ep = reinterpret_cast<const ulonglong2*>(eq + (size_t)(slot * TAU + l) * eq_pitch + x);
+                const ulonglong2 p0 = __ldg(ep), p1 = __ldg(ep + 1);
+                e[l][0] = p0.x; e[l][1] = p0.y; e[l][2] = p1.x; e[l][3] = p1.y;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) se[l].add(e[l][q]);
+            }
+#pragma unroll
+            for (int j = 0; j < TAU; ++j) {
+                const char4 d = *reinterpret_cast<const char4*>(cv + (size_t)(j * S + slot) * c_pitch + x);
+                const u32 g[4] = {(u32)((int)d.x + 128), (u32)((int)d.y + 128), (u32)((int)d.z + 128), (u32)((int)d.w + 128)};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int l = 0; l < TAU; ++l) acc[j][l].mac_small(g[q], e[l][q]);
+            }
+        }
+        for (size_t x = x_vec_end + threadIdx.x; x < x_end; x += blockDim.x) {      // ragged tail
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) {
+                const u64 el = eq[(size_t)(slot * TAU + l) * eq_pitch + x]; se[l].add(el);
+#pragma unroll
+                for (int j = 0; j < TAU; ++j) acc[j][l].mac_small((u32)((int)(int8_t)cv[(size_t)(j * S + slot) * c_pitch + x] + 128), el);
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) {
+            const u64 corr = F::mul(F::reduce(se[l]), 128);
+#pragma unroll
+            for (int j = 0; j < TAU; ++j) v[j * TAU + l] = F::sub(F::reduce(acc[j][l]), corr);
+        }
+    } else {
+        for (size_t x = x_begin + threadIdx.x; x < x_end; x += blockDim.x) {
+            u64 e[TAU];
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) e[l] = eq[(size_t)(slot * TAU + l) * eq_pitch + x];
+#pragma unroll
+            for (int j = 0; j < TAU; ++j) {
+                const u64 c = (u64)cv[(size_t)(j * S + slot) * c_pitch + x];
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) acc[j][l].mac(c, e[l]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < TAU; ++j)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) v[j * TAU + l] = F::reduce(acc[j][l]);
+    }
     block_reduce_add<F, TAU * TAU>(v, red);
     if (threadIdx.x == 0) {
 #pragma unroll
