@@ -268,7 +268,9 @@ template <class Rg> struct Engine {
     void digit_split(const u64* in, size_t in_pitch, int8_t* out, size_t out_pitch, size_t n, u64 b, int K) {
         if (b < 2 || b > 254 || K < 1 || K > 64) throw LfException(LF_ERR_UNSUPPORTED, "decompose_to_vec: need 2 <= b <= 254 (int8 digits), 1 <= K <= 64");
         if (!n) return;
-        launch("k_digit_split", [&] { k_digit_split<Rg><<<blocks_for(n * D), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n, (int64_t)b, K, c->d_err); });
+        if (b == 2 && out_pitch % 4 == 0 && out_pitch >= (n + 3) / 4 * 4)      // the 4-byte stores of the last group stay inside the plane's padding
+            launch("k_digit_split", [&] { k_digit_split_b2<Rg><<<dim3(blocks_for((n + 3) / 4), D), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n, K, c->d_err); });
+        else launch("k_digit_split", [&] { k_digit_split<Rg><<<blocks_for(n * D), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n, (int64_t)b, K, c->d_err); });
     }
 
     // ---------------------------------------------------------------- batched dot products (commit, MLE evaluation)

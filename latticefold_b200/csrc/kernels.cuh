@@ -216,6 +216,28 @@ template <class Rg> __global__ void k_digit_split(const u64* __restrict__ in, si
     if (!balanced_digits(F::to_signed(in[(size_t)c * in_pitch + i]), b, K, dg)) atomicExch(err, 1);
     for (int k = 0; k < K; ++k) out[((size_t)k * Rg::D + c) * out_pitch + i] = (int8_t)dg[k];
 }
+// b = 2 (every reference parameter set of the 64/31-bit rings): the balanced digits of v are sign(v) times the bits of |v| -- no
+// divisions, no digit array.  Four consecutive elements per thread, one 4-byte store per digit plane; grid.y = coefficient plane.
+template <class Rg> __global__ void __launch_bounds__(256) k_digit_split_b2(const u64* __restrict__ in, size_t in_pitch, int8_t* __restrict__ out, size_t out_pitch,
+                                                                           size_t n, int K, int* __restrict__ err) {
+    typedef typename Rg::F F;
+    const size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); const int c = blockIdx.y;
+    if (i >= n) return;
+    u64 mag[4]; int sgn[4]; bool bad = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t v = i + q < n ? F::to_signed(in[(size_t)c * in_pitch + i + q]) : 0;
+        sgn[q] = v < 0 ? -1 : 1; mag[q] = (u64)(v < 0 ? -v : v);
+        bad = bad || (K < 64 && (mag[q] >> K) != 0);
+    }
+    if (bad) atomicExch(err, 1);
+    for (int k = 0; k < K; ++k) {
+        char4 d;
+        d.x = (signed char)(sgn[0] * (int)((mag[0] >> k) & 1)); d.y = (signed char)(sgn[1] * (int)((mag[1] >> k) & 1));
+        d.z = (signed char)(sgn[2] * (int)((mag[2] >> k) & 1)); d.w = (signed char)(sgn[3] * (int)((mag[3] >> k) & 1));
+        *reinterpret_cast<char4*>(out + ((size_t)k * Rg::D + c) * out_pitch + i) = d;
+    }
+}
 template <class Rg> __global__ void k_digits_to_field(const int8_t* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t n) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * Rg::D) return;
