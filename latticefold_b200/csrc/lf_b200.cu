@@ -37,7 +37,10 @@ lf_status lf_ctx_create(int32_t ring_id, int32_t device, lf_ctx** out) {
         if (device < 0 || device >= ndev) throw LfException(LF_ERR_INVALID_ARG, "device index out of range");
         LF_CUDA(cudaSetDevice(device));
         std::unique_ptr<lf_ctx> c(new lf_ctx); c->ring = ring_id; c->device = device;
-        LF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        // the context's own stream outranks the prover's auxiliary stream (created at default = lowest priority): the host-paced
+        // sumcheck rounds on this stream are chains of small kernels that must not queue behind the decompositions' long ones
+        { int least = 0, greatest = 0; LF_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+          LF_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatest)); }
         o->ctx_tables_create(c.get());
         LF_CUDA(cudaMalloc(&c->d_err, sizeof(int))); LF_CUDA(cudaMemset(c->d_err, 0, sizeof(int)));
         *out = c.release();

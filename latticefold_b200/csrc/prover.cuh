@@ -462,7 +462,13 @@ template <class Rg> struct Prover {
         LinOut lin = linearize(cm_i_cm, x_ccs, w_i, T, lin_tail);
         mark("linearize");
         E.sync(); auto t1 = clk::now(); P->timings[0] = ms(t0, t1);
-        DecPending prr = decompose_enqueue(lin.lc, w_i, lin.eq_r, sb, 1);
+        // The second decomposition queues behind the first on the auxiliary stream (the linearization's device work is complete:
+        // synchronised above), so the accumulator's results -- the ones the transcript absorbs first -- are never delayed by it.
+        DecPending prr;
+        { lf_ctx* main_ctx = E.c;
+          if (overlap) { E.c = aux_ctx(); E.c->profiling = main_ctx->profiling; }
+          try { prr = decompose_enqueue(lin.lc, w_i, lin.eq_r, sb, 1); } catch (...) { E.c = main_ctx; throw; }
+          E.c = main_ctx; }
         DecOut dl = decompose_finish(pl, T);
         mark("decompose_acc");
         DecOut dr = decompose_finish(prr, T);
