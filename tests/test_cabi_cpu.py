@@ -115,3 +115,16 @@ def test_product_verifier_accepts_oracle_proofs_and_rejects_tampering(oracle, or
     prob2 = dict(prob); acc = dict(prob["acc"]); acc["v"] = acc["v"].copy(); acc["v"][0, 0] = (int(acc["v"][0, 0]) + 1) % p; prob2["acc"] = acc
     with pytest.raises(lf.LfError):
         lf.nifs_verify(prob2, lf.Transcript(ring), proof)
+
+
+@pytest.mark.parametrize("ring", [synth.RING_GOLDILOCKS, synth.RING_BABYBEAR, synth.RING_FROG])
+def test_ring_describe_and_slot_product_agree_with_oracle(oracle, ring):
+    """lf_ring_describe (host, no GPU) reports the ring shape the generator assumes, and the slot-field product built from its nu
+    (synth.sf_mul, used for the degree-three CCS's diag(z^2)) equals the oracle's NTT-form product"""
+    class Info(api.C.Structure):
+        _fields_ = [("p", api.C.c_uint64), ("d", api.C.c_int32), ("n_slots", api.C.c_int32), ("tau", api.C.c_int32), ("nu", api.C.c_uint64)]
+    info = Info(); assert lf.lib().lf_ring_describe(ring, api.C.byref(info)) == 0
+    R = synth.RINGS[ring]
+    assert (info.p, info.d, info.n_slots, info.tau) == (R["p"], R["d"], R["S"], R["tau"]) and info.nu == oracle.info(ring)["nu"]
+    a = synth.uniform_field(R["p"], 5 * R["d"], 31).reshape(5, R["d"]); b = synth.uniform_field(R["p"], 5 * R["d"], 32).reshape(5, R["d"])
+    assert np.array_equal(synth.sf_mul(ring, a, b, int(info.nu)), oracle.ntt_mul(ring, a, b))
