@@ -309,10 +309,8 @@ template <class Rg> struct Prover {
         if ((int)lcs.size() != 2 * K) throw LfException(LF_ERR_INCORRECT_LENGTH, "IncorrectLength");
         if (P->b != 2) throw LfException(LF_ERR_UNSUPPORTED, "folding sumcheck kernels are specialised for b = 2 (every reference parameter set but Stark)");
         // squeeze_alpha_beta_zeta_mu (folding/utils.rs:51-96)
-        std::vector<u64> alpha = squeeze(T, "alpha_s", 2 * K), zeta = squeeze(T, "zeta_s", 2 * K), mu = squeeze(T, "mu_s", 2 * K - 1);
-        { u64 one[TAU] = {0}; one[0] = 1; mu.insert(mu.end(), one, one + TAU); }
-        HV beta = sf_to_ring(squeeze(T, "beta_s", s));
-        mark("fold.challenges");
+        // alpha and zeta first: the G tables below need only these two, so their kernels run while the host squeezes mu and beta
+        std::vector<u64> alpha = squeeze(T, "alpha_s", 2 * K), zeta = squeeze(T, "zeta_s", 2 * K);
         // dense tables [eq(r_acc), G_acc, eq(r_new), G_new, eq(beta)]  (create_sumcheck_polynomial, folding/utils.rs:200-259)
         lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = 2 * (int)P->b; sc.kind = LF_COMB_FOLD; sc.len = m; sc.sharded = world() > 1;
         SumcheckDriver<Rg> drv(P->ctx, &sc);
@@ -320,7 +318,6 @@ template <class Rg> struct Prover {
         auto tbl = [&](int i) { return sc.dense.cur + (size_t)i * sc.dense.stride; };
         LF_CUDA(cudaMemcpy2DAsync(tbl(0), sc.dense.pitch * 8, eq_acc.p, eq_acc.pitch * 8, m * 8, D, cudaMemcpyDeviceToDevice, E.st()));
         LF_CUDA(cudaMemcpy2DAsync(tbl(2), sc.dense.pitch * 8, eq_new.p, eq_new.pitch * 8, m * 8, D, cudaMemcpyDeviceToDevice, E.st()));
-        E.eq_table(beta.data(), s, tbl(4), sc.dense.pitch, (size_t)rank() * m, m);
         for (int half = 0; half < 2; ++half) {
             u64* G = tbl(1 + 2 * half);
             LF_CUDA(cudaMemsetAsync(G, 0, sc.dense.stride * 8, E.st()));
@@ -344,6 +341,11 @@ template <class Rg> struct Prover {
                 E.lincomb(pl, sb.mz.pitch, chunk, &coef[done * D], G, sc.dense.pitch, sb.mz.pitch, true);
             }
         }
+        std::vector<u64> mu = squeeze(T, "mu_s", 2 * K - 1);
+        { u64 one[TAU] = {0}; one[0] = 1; mu.insert(mu.end(), one, one + TAU); }
+        HV beta = sf_to_ring(squeeze(T, "beta_s", s));
+        mark("fold.challenges");
+        E.eq_table(beta.data(), s, tbl(4), sc.dense.pitch, (size_t)rank() * m, m);
         mark("fold.tables");
         sc.dig = sb.dig; sc.dig_pitch = sb.dig_pitch; sc.dig_stride = sb.dig_stride;
         { HV mu_ring = sf_to_ring(mu); drv.set_mu(mu_ring.data(), 2 * K); }
@@ -355,11 +357,13 @@ template <class Rg> struct Prover {
         // theta_i = f-hat_i(r_0): the sumcheck's fully folded f-hat tables (get_thetas, folding.rs:236-246)
         for (int i = 0; i < 2 * K; ++i) o.theta.emplace_back(finals.begin() + (size_t)(5 + i * TAU) * D, finals.begin() + (size_t)(5 + (i + 1) * TAU) * D);
         // eta_i = Mz_i(r_0) (get_etas, folding.rs:248-256)
-        { DevVec eq0 = eq_table(r0); HV all = eval_mz(sb.mz, 0, 2 * K * (int)t, eq0); E.dfree(eq0.p);
-          for (int i = 0; i < 2 * K; ++i) o.eta.emplace_back(all.begin() + (size_t)i * t * D, all.begin() + (size_t)(i + 1) * t * D); }
-        mark("fold.eta");
+        // queued without waiting: the host absorbs the thetas while the device evaluates the etas
+        DevVec eq0 = eq_table(r0); const u64* eta_land = eval_mz_async(sb.mz, 0, 2 * K * (int)t, eq0); E.dfree(eq0.p);
         auto t0 = std::chrono::steady_clock::now();
         for (auto& th : o.theta) T.absorb_slice(th.data(), cnt(th));
+        E.sync();
+        for (int i = 0; i < 2 * K; ++i) o.eta.emplace_back(eta_land + (size_t)i * t * D, eta_land + (size_t)(i + 1) * t * D);
+        mark("fold.eta");
         for (auto& et : o.eta) T.absorb_slice(et.data(), cnt(et));
         // get_rhos (folding/utils.rs:116-131)
         T.absorb_tag("rho_s");
