@@ -83,14 +83,16 @@ template <class Rg> struct Prover {
     }
     // Mz tables for a list of z = head_k || tail_k; out: [count * t] rows of pitch mz_pitch, effective length eff[j]
     struct MzSet { u64* p = nullptr; size_t pitch = 0, stride = 0; int rows = 0; size_t* d_len = nullptr; std::vector<size_t> len; };
-    MzSet alloc_mz(int count) {
+    // upload = false: the caller copies the length table itself, on the stream that will read it (upload_mz_len)
+    MzSet alloc_mz(int count, bool upload = true) {
         MzSet z; z.rows = count * (int)P->t; size_t mx = 1; for (auto* M : P->M) mx = std::max(mx, M->eff_rows);
         z.pitch = pitch_of(mx); z.stride = z.pitch * D; z.p = E.template dalloc<u64>((size_t)z.rows * z.stride);
         z.len.resize(z.rows); for (int i = 0; i < z.rows; ++i) z.len[i] = P->M[i % P->t]->eff_rows;
         z.d_len = E.template dalloc<size_t>(z.rows);
-        E.h2d(z.d_len, z.len.data(), z.rows * sizeof(size_t));
+        if (upload) upload_mz_len(z);
         return z;
     }
+    void upload_mz_len(MzSet& z) { E.h2d(z.d_len, z.len.data(), z.rows * sizeof(size_t)); }
     void free_mz(MzSet& z) { E.dfree(z.p); E.dfree(z.d_len); z.p = nullptr; }
     // z = head || tail where the tail (w_ccs) is, when sharded, the all-gathered concatenation of the ranks' slabs:
     // chunk r (tail_chunk elements) at tail + r * tail_chunk_stride.  Rows of M are this rank's slab.
@@ -426,20 +428,14 @@ template <class Rg> struct Prover {
         const int K = P->K; const size_t n = nl();
         LCCCS acc = load_acc(in, P);
         HV cm_i_cm(in.cm_i_cm, in.cm_i_cm + P->kappa * D), x_ccs(in.cm_i_x_ccs, in.cm_i_x_ccs + P->l * D);
-        // absorb_public_input (nifs.rs:175-197)
-        T.absorb_tag("acc");
-        T.absorb_slice(acc.r.data(), cnt(acc.r)); T.absorb_slice(acc.v.data(), cnt(acc.v)); T.absorb_slice(acc.cm.data(), cnt(acc.cm));
-        T.absorb_slice(acc.u.data(), cnt(acc.u)); T.absorb_slice(acc.x_w.data(), cnt(acc.x_w)); T.absorb(acc.h.data());
-        T.absorb_tag("cm_i"); T.absorb_slice(cm_i_cm.data(), cnt(cm_i_cm)); T.absorb_slice(x_ccs.data(), cnt(x_ccs));
         // Schedule: the accumulator's decomposition depends on nothing the transcript produces, so its device half is
         // queued first on the auxiliary stream and runs beside the (latency-bound, host-paced) linearization sumcheck.
         StepBuffers sb;
         sb.dig_pitch = (std::max(n, ml()) + 255) / 256 * 256;   // the sumcheck walks all 2^s entries
         sb.dig_stride = sb.dig_pitch * D; sb.dig = E.template dalloc<int8_t>((size_t)2 * K * sb.dig_stride);
-        LF_CUDA(cudaMemsetAsync(sb.dig, 0, (size_t)2 * K * sb.dig_stride, E.st()));   // f-hat tables are zero on [n, 2^s)
         sb.pc_pitch = pitch_of(n); sb.pc_stride = sb.pc_pitch * D; sb.pieces = E.template dalloc<u64>((size_t)2 * K * sb.pc_stride);
         sb.wc_pitch = pitch_of(w_i->W); sb.wc_stride = sb.wc_pitch * D; sb.wccs = E.template dalloc<u64>((size_t)2 * K * sb.wc_stride);
-        sb.mz = alloc_mz(2 * K);
+        sb.mz = alloc_mz(2 * K, false);
         DevVec eq_acc; eq_acc.n = ((size_t)1 << cnt(acc.r)) / world(); eq_acc.pitch = pitch_of(eq_acc.n); eq_acc.p = E.template dalloc<u64>(eq_acc.pitch * D);
         // sharded steps overlap too when the collectives are stream-ordered on both streams (own NCCL communicator + mailbox channels)
         const bool overlap = (world() == 1 || (E.c->nccl && E.c->xg.on)) && !P->detail && !std::getenv("LF_NO_OVERLAP");
@@ -456,12 +452,21 @@ template <class Rg> struct Prover {
                 E.c = aux;
             }
             try {
+                // on the stream that runs the decompositions: when the accumulator's decomposition starts behind `acc_ready`
+                // (host-buffer entry point) it does NOT wait for what the main stream queues after that event
+                LF_CUDA(cudaMemsetAsync(sb.dig, 0, (size_t)2 * K * sb.dig_stride, E.st()));   // f-hat tables are zero on [n, 2^s)
+                upload_mz_len(sb.mz);
                 E.eq_table(acc.r.data(), (int)cnt(acc.r), eq_acc.p, eq_acc.pitch, (size_t)rank() * eq_acc.n, eq_acc.n);
                 pl = decompose_enqueue(acc, w_acc, eq_acc, sb, 0);
             } catch (...) { E.c = main_ctx; throw; }
             E.c = main_ctx;
         }
         mark("alloc+dec_acc_enqueue");
+        // absorb_public_input (nifs.rs:175-197): after the device has been given its first work
+        T.absorb_tag("acc");
+        T.absorb_slice(acc.r.data(), cnt(acc.r)); T.absorb_slice(acc.v.data(), cnt(acc.v)); T.absorb_slice(acc.cm.data(), cnt(acc.cm));
+        T.absorb_slice(acc.u.data(), cnt(acc.u)); T.absorb_slice(acc.x_w.data(), cnt(acc.x_w)); T.absorb(acc.h.data());
+        T.absorb_tag("cm_i"); T.absorb_slice(cm_i_cm.data(), cnt(cm_i_cm)); T.absorb_slice(x_ccs.data(), cnt(x_ccs));
         auto t0 = clk::now();
         LinOut lin = linearize(cm_i_cm, x_ccs, w_i, T, lin_tail);
         mark("linearize");

@@ -91,3 +91,20 @@ def test_babybear_degree_three_ccs_c3_shape(oracle, gpu):
     sch = gpu.AjtaiCommitmentScheme(ctx, prob["A"])
     assert np.array_equal(sch.commit(ctx.upload(f0)), synth.split_lcccs(BBR, prob, lc)["cm"])
     pr.close(); ctx.close()
+
+
+def test_host_buffer_step_with_pinned_memory(setup, gpu):
+    """Pinned inputs make the witness uploads truly asynchronous: the accumulator's decomposition starts (auxiliary stream) while
+    the incoming witness is still being copied on the main stream.  Same proof as with pageable (synchronously copied) inputs."""
+    import torch
+    ctx, prob = setup
+    keep, p2 = [], dict(prob)
+    for k in ("w_i_f", "w_acc_f"):
+        t = torch.from_numpy(np.ascontiguousarray(prob[k]).view(np.int64)).pin_memory(); keep.append(t)
+        p2[k] = t.numpy().view(np.uint64)
+    pr = gpu.NIFSProver(ctx, prob)
+    ref_proof, ref_lc, ref_f = pr.prove(prob, gpu.Transcript(G))
+    for _ in range(3):
+        proof, lc, f = pr.prove(p2, gpu.Transcript(G))
+        assert np.array_equal(proof, ref_proof) and np.array_equal(lc, ref_lc) and np.array_equal(f, ref_f)
+    pr.close()
