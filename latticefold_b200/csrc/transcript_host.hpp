@@ -4,9 +4,10 @@
 //   TAU limbs and absorbs them back; short challenges from squeeze_bytes)
 //   crates/latticefold/src/transcript.rs:13-51           (absorb_field_element = broadcast to a ring element)
 // Sponge algorithm: ark-crypto-primitives 0.4.0 PoseidonSponge (duplex with Absorbing/Squeezing cursor).
-// Runs on the CPU by design (sequential); the MDS product uses lazily reduced 192-bit sums.
+// Runs on the CPU by design (sequential); the MDS product uses lazily reduced 192-bit sums (x86-64 add/adc chains).
 #pragma once
 #include "ring_host.hpp"
+#include <type_traits>
 #include "poseidon_w24_tables.inc"
 
 namespace lf {
@@ -25,6 +26,7 @@ template <class Rg> class Transcript {
         u64 pre[W * W];               // replaces MDS in the last full round before the partial rounds
         u64 sp_row0[RP][W];           // Ms_r first row
         u64 sp_col0[RP][W];           // Ms_r first column (entry 0 unused)
+        u64 sp_c0[RP];                // partial rounds: the only constant that has to be added before the S-box (lane 0)
         static void matmul(u64* o, const u64* a, const u64* b) {   // o = a * b (W x W)
             for (int i = 0; i < W; ++i) for (int j = 0; j < W; ++j) { u64 acc = 0; for (int k = 0; k < W; ++k) acc = F::add(acc, F::mul(a[i * W + k], b[k * W + j])); o[i * W + j] = acc; }
         }
@@ -59,6 +61,18 @@ template <class Rg> class Transcript {
                 matmul(nxt.data(), md.data(), mds); cur = nxt;   // matrix the previous round has to apply
             }
             std::memcpy(pre, cur.data(), sizeof pre);
+            // Lanes 1..W-1 skip the S-box, so their constants commute with it: push them through Ms_r into the next round
+            // (new_0 = row0 . k, new_i = k_i) until they land in the constants of the first full round after the partial ones.
+            u64 carry[W] = {0};
+            for (int r = 0; r < RP; ++r) {
+                u64* c = ark + (RF / 2 + r) * W; u64 k[W];
+                for (int i = 0; i < W; ++i) k[i] = F::add(c[i], carry[i]);
+                sp_c0[r] = k[0];
+                u64 acc = 0; for (int j = 1; j < W; ++j) acc = F::add(acc, F::mul(sp_row0[r][j], k[j]));
+                carry[0] = acc; for (int i = 1; i < W; ++i) carry[i] = k[i];
+            }
+            u64* c = ark + (RF / 2 + RP) * W;
+            for (int i = 0; i < W; ++i) c[i] = F::add(c[i], carry[i]);
         }
     };
     static const Tables& tables() { static const Tables t; return t; }
@@ -67,24 +81,50 @@ template <class Rg> class Transcript {
     bool squeezing_;
     unsigned long long permutations_ = 0;
 
-    static u64 pow7(u64 x) { u64 x2 = F::mul(x, x), x3 = F::mul(x2, x), x6 = F::mul(x3, x3); return F::mul(x6, x); }
-    // dot product of two W-vectors mod p with two independent carry chains (low / high product halves)
-    static u64 dot(const u64* a, const u64* b) {
-        u128 lo = 0, hi = 0;
-        for (int j = 0; j < W; ++j) { u128 x = (u128)a[j] * b[j]; lo += (u64)x; hi += (u64)(x >> 64); }
-        return F::reduce_wide(lo, hi);                     // (lo + hi * 2^64) mod p
+    // Lazy ("weak") representatives inside a round: any u64 congruent to the value.  For Goldilocks that drops the canonicalising
+    // subtract from every reduction; the dense layers' reduce_wide returns canonical lanes again.  Other fields keep canonical ops.
+    static constexpr bool LAZY = std::is_same<F, Goldilocks>::value;
+    static inline u64 wred(u64 lo, u64 hi) {               // (hi:lo) mod p, weak
+        if constexpr (LAZY) {
+            u64 hh = hi >> 32, hl = hi & 0xFFFFFFFFull, t1 = (hl << 32) - hl;
+            u64 t0 = lo - hh; t0 -= (0 - (u64)(lo < hh)) & 0xFFFFFFFFull;
+            u64 r = t0 + t1; r += (0 - (u64)(r < t1)) & 0xFFFFFFFFull;
+            return r;
+        } else return F::reduce128(lo, hi);
     }
+    static inline u64 wmul(u64 a, u64 b) { u128 x = (u128)a * b; return wred((u64)x, (u64)(x >> 64)); }
+    static inline u64 wadd(u64 a, u64 c) {                 // a weak, c canonical
+        if constexpr (LAZY) { u64 s = a + c; s += (0 - (u64)(s < a)) & 0xFFFFFFFFull; return s; } else return F::add(a, c);
+    }
+    // 192-bit sum of products in three registers, one add/adc/adc chain per product
+    struct Acc3 {
+        u64 c0 = 0, c1 = 0, c2 = 0;
+        inline void mac(u64 a, u64 b) {
+            u128 x = (u128)a * b; u64 lo = (u64)x, hi = (u64)(x >> 64);
+            asm("add %3, %0\n\tadc %4, %1\n\tadc $0, %2" : "+r"(c0), "+r"(c1), "+r"(c2) : "r"(lo), "r"(hi) : "cc");
+        }
+        inline u64 reduce() const { return F::reduce_wide((u128)c0, ((u128)c2 << 64) | c1); }
+    };
     // x -> (x + c)^7 on all lanes, one multiplication level at a time: 24 independent products per level keep the multiplier
-    // busy, where lane-by-lane pow7 chains four dependent reductions (measured 27 % faster on the host)
+    // busy, where lane-by-lane x^7 chains four dependent reductions
     void sbox_layer(const u64* c) {
         u64 a[W], x2[W], x3[W];
-        for (int i = 0; i < W; ++i) a[i] = F::add(st_[i], c[i]);
-        for (int i = 0; i < W; ++i) x2[i] = F::mul(a[i], a[i]);
-        for (int i = 0; i < W; ++i) x3[i] = F::mul(x2[i], a[i]);
-        for (int i = 0; i < W; ++i) x2[i] = F::mul(x3[i], x3[i]);
-        for (int i = 0; i < W; ++i) st_[i] = F::mul(x2[i], a[i]);
+        for (int i = 0; i < W; ++i) a[i] = wadd(st_[i], c[i]);
+        for (int i = 0; i < W; ++i) x2[i] = wmul(a[i], a[i]);
+        for (int i = 0; i < W; ++i) x3[i] = wmul(x2[i], a[i]);
+        for (int i = 0; i < W; ++i) x2[i] = wmul(x3[i], x3[i]);
+        for (int i = 0; i < W; ++i) st_[i] = wmul(x2[i], a[i]);
     }
-    void dense_layer(const u64* m) { u64 nx[W]; for (int i = 0; i < W; ++i) nx[i] = dot(m + i * W, st_); std::memcpy(st_, nx, sizeof st_); }
+    void dense_layer(const u64* m) {
+        u64 nx[W];
+        for (int i = 0; i < W; ++i) {
+            Acc3 acc; const u64* row = m + i * W;
+#pragma GCC unroll 24
+            for (int j = 0; j < W; ++j) acc.mac(row[j], st_[j]);
+            nx[i] = acc.reduce();
+        }
+        std::memcpy(st_, nx, sizeof st_);
+    }
     void permute() {
         const Tables& t = tables(); ++permutations_;
         int r = 0;
@@ -93,11 +133,16 @@ template <class Rg> class Transcript {
             dense_layer(r == RF / 2 - 1 ? t.pre : t.mds);
         }
         for (int pr = 0; pr < RP; ++pr, ++r) {
-            for (int i = 0; i < W; ++i) st_[i] = F::add(st_[i], t.ark[r * W + i]);
-            st_[0] = pow7(st_[0]);
-            const u64 x0 = st_[0]; const u64 n0 = dot(t.sp_row0[pr], st_);
-            for (int i = 1; i < W; ++i) { u128 x = (u128)t.sp_col0[pr][i] * x0 + st_[i]; st_[i] = F::reduce128((u64)x, (u64)(x >> 64)); }
-            st_[0] = n0;
+            const u64 a = wadd(st_[0], t.sp_c0[pr]);
+            const u64 a2 = wmul(a, a), a3 = wmul(a2, a), a6 = wmul(a3, a3), x0 = wmul(a6, a);
+            const u64* row = t.sp_row0[pr]; const u64* col = t.sp_col0[pr];
+            Acc3 acc;                                      // lane 0 last: the other 23 products do not wait for the S-box
+#pragma GCC unroll 23
+            for (int j = 1; j < W; ++j) acc.mac(row[j], st_[j]);
+            acc.mac(row[0], x0);
+#pragma GCC unroll 23
+            for (int i = 1; i < W; ++i) { u128 x = (u128)col[i] * x0 + st_[i]; st_[i] = wred((u64)x, (u64)(x >> 64)); }
+            st_[0] = acc.reduce();
         }
         for (; r < RF + RP; ++r) {
             sbox_layer(&t.ark[r * W]);
