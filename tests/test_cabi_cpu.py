@@ -46,6 +46,22 @@ def test_product_transcript_matches_oracle_on_long_schedule(oracle):
         assert np.array_equal(a.get_short_challenge(), b.get_short_challenge())
 
 
+def test_product_transcript_extreme_lanes_match_oracle(oracle):
+    """lanes at the edges of the field (0, 1, 2^32 +- 1, p - 2^32, p - 1): the product's Poseidon keeps lazily reduced
+    representatives inside a round, the oracle reduces canonically after every operation"""
+    p = synth.RINGS[G]["p"]
+    edge = np.array([0, 1, 2, (1 << 32) - 1, 1 << 32, (1 << 32) + 1, p - (1 << 32), p - (1 << 32) - 1, p - 2, p - 1], dtype=np.uint64)
+    a, b = lf.Transcript(G), oracle.transcript(G)
+    for rep in range(4):
+        v = np.resize(np.roll(edge, rep), 20 * 3 + rep)
+        a.absorb_base(v); b.absorb_base(v)
+        assert np.array_equal(a.get_challenge(), b.get_challenge())
+    v = np.full(20 * 5, p - 1, dtype=np.uint64)
+    a.absorb_base(v); b.absorb_base(v)
+    assert np.array_equal(a.get_challenge(), b.get_challenge())
+    assert np.array_equal(a.get_short_challenge(), b.get_short_challenge())
+
+
 def test_product_rot_lin_combination_kat():
     # crates/cyclotomic-rings/src/rotation.rs:174-776
     g = json.load(open(os.path.join(GOLD, "rotsum_goldilocks.json")))
