@@ -6,6 +6,7 @@ import pytest
 
 from latticefold_b200 import synth
 from oracle.pyoracle import OracleError
+from tests import helpers
 from tests.helpers import rand_elems
 
 G, BB, FROG = synth.RING_GOLDILOCKS, synth.RING_BABYBEAR, synth.RING_FROG
@@ -79,3 +80,12 @@ def test_nifs_prove_verify_degree_three_ccs(oracle, oracle_ops, ring, W, B, L, b
     bad = proof.copy(); bad[3] = (int(bad[3]) + 1) % synth.RINGS[ring]["p"]
     with pytest.raises(OracleError):
         oracle.nifs_verify(prob, oracle.transcript(ring), bad)
+
+
+@pytest.mark.parametrize("case", helpers.STEP_GOLDEN_CASES, ids=lambda c: helpers.step_case_key(*c))
+def test_step_digests_match_committed_golden(oracle, oracle_ops, case):
+    """the oracle's whole prover step (proof, folded LCCCS, folded witness) on the deterministic synthetic instance still hashes to
+    tests/golden/step_digests.json: pins oracle + instance generator; the GPU path is held to the same file in test_gpu_parity.py"""
+    prob = helpers.step_instance(case, oracle_ops)
+    proof, lc, f, _ = oracle.nifs_prove(prob, oracle.transcript(case[0]))
+    assert helpers.step_digests(proof, lc, f) == helpers.step_golden()[helpers.step_case_key(*case)]
