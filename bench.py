@@ -271,6 +271,7 @@ def main():
                          d2h_bytes_per_step=int(out_proof.nbytes + out_lc.nbytes + out_f.nbytes)),
                 roofline=roofline, phases_ms=phases,
                 kernels_ms={k: dict(launches=v[0], total_ms=round(v[1], 4)) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])})
+    line["host"] = dict(poseidon=lf.Transcript(RING).backend(), cpus=os.cpu_count())   # dense-layer code path of the host transcript
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.pyoracle import Oracle
         from tests.helpers import OracleOps

@@ -178,6 +178,9 @@ void lf_transcript_absorb_tag(lf_transcript* t, const char* tag);
 void lf_transcript_get_challenge(lf_transcript* t, uint64_t* out_sf);               /* TAU limbs                  */
 void lf_transcript_get_short_challenge(lf_transcript* t, uint64_t* out_coeffs);     /* D coefficients             */
 uint64_t lf_transcript_permutations(const lf_transcript* t);
+/* which dense-layer implementation the host Poseidon of the Goldilocks ring runs on this machine: "avx512-ifma" or "scalar"
+ * (same results; LF_POSEIDON_SCALAR=1 in the environment forces the scalar one)                                           */
+const char* lf_host_poseidon_backend(void);
 
 /* ---- a13: rot_lin_combination (cyclotomic-rings/src/rotation.rs:45-104), host                                    */
 lf_status lf_rot_lin_combination(int32_t ring_id, const uint64_t* rho_coeff, const uint64_t* theta_ntt, int32_t count, uint64_t* out);

@@ -29,7 +29,7 @@ lf_decompose_to_vec lf_fhat lf_ajtai_create lf_ajtai_free lf_ajtai_kappa lf_ajta
 lf_sparse_create lf_sparse_free lf_spmv lf_eq_table lf_mle_eval_batch lf_lincomb lf_sumcheck_begin lf_sumcheck_round
 lf_sumcheck_finish lf_sumcheck_free lf_transcript_create lf_transcript_clone lf_transcript_free lf_transcript_absorb
 lf_transcript_absorb_base lf_transcript_absorb_tag lf_transcript_get_challenge lf_transcript_get_short_challenge
-lf_transcript_permutations lf_rot_lin_combination lf_prover_create lf_prover_free lf_proof_words lf_lcccs_words
+lf_transcript_permutations lf_host_poseidon_backend lf_rot_lin_combination lf_prover_create lf_prover_free lf_proof_words lf_lcccs_words
 lf_witness_f_from_w_ccs lf_linearize lf_nifs_prove lf_nifs_verify lf_prover_upload_witness lf_witness_free lf_witness_download_f
 lf_nifs_prove_resident lf_prover_last_timings lf_prover_timing_detail
 lf_ntt_root lf_ntt_plan_create lf_ntt_plan_free lf_ntt_forward_device lf_ntt_inverse_device lf_ntt_forward_host lf_ntt_inverse_host
@@ -160,6 +160,8 @@ def lib():
     L.lf_transcript_get_challenge.argtypes = L.lf_transcript_get_short_challenge.argtypes = [vp, u64p]
     L.lf_transcript_permutations.restype = C.c_uint64
     L.lf_transcript_permutations.argtypes = [vp]
+    L.lf_host_poseidon_backend.restype = C.c_char_p
+    L.lf_host_poseidon_backend.argtypes = []
     L.lf_rot_lin_combination.argtypes = [C.c_int32, u64p, u64p, C.c_int32, u64p]
     L.lf_prover_create.argtypes = [vp, C.POINTER(Problem), C.POINTER(vp)]
     L.lf_prover_free.argtypes = [vp]
@@ -226,6 +228,10 @@ class Transcript:
 
     def permutations(self):
         return int(self.L.lf_transcript_permutations(self.h))
+
+    def backend(self):
+        """dense-layer implementation of the host Poseidon on this machine ("avx512-ifma" / "scalar")"""
+        return self.L.lf_host_poseidon_backend().decode()
 
 
 class DeviceVec:

@@ -177,6 +177,7 @@ void lf_transcript_absorb_tag(lf_transcript* t, const char* tag) { guard(nullptr
 void lf_transcript_get_challenge(lf_transcript* t, uint64_t* out) { guard(nullptr, [&] { ops(t->ring)->tr_get_challenge(t->impl, out); }); }
 void lf_transcript_get_short_challenge(lf_transcript* t, uint64_t* out) { guard(nullptr, [&] { ops(t->ring)->tr_get_short_challenge(t->impl, out); }); }
 uint64_t lf_transcript_permutations(const lf_transcript* t) { uint64_t r = 0; guard(nullptr, [&] { r = ops(t->ring)->tr_permutations(t->impl); }); return r; }
+const char* lf_host_poseidon_backend(void) { return lf::poseidon_use_ifma() ? "avx512-ifma" : "scalar"; }
 lf_status lf_rot_lin_combination(int32_t ring, const uint64_t* rho, const uint64_t* theta, int32_t count, uint64_t* out) { return guard(nullptr, [&] { ops(ring)->rot_lin_combination(rho, theta, count, out); }); }
 // ---- prover
 uint64_t lf_proof_words(const lf_problem* P) { uint64_t r = 0; guard(nullptr, [&] { r = ops(P->ring)->proof_words(P); }); return r; }

@@ -8,9 +8,18 @@
 #pragma once
 #include "ring_host.hpp"
 #include <type_traits>
+#include <cstdlib>
 #include "poseidon_w24_tables.inc"
 
 namespace lf {
+
+// AVX-512 IFMA dense layer for the Goldilocks field (poseidon_ifma.cpp, compiled by g++; chosen at run time)
+struct PoseidonIfmaMatrix { alignas(64) u64 limb[POSEIDON_W24_WIDTH][3][3][8]; };
+bool poseidon_ifma_supported();
+void poseidon_ifma_prepare(const u64* m, PoseidonIfmaMatrix* out);
+void poseidon_ifma_dense(const PoseidonIfmaMatrix* M, u64* st);
+// LF_POSEIDON_SCALAR=1 in the environment keeps the scalar dense layer (tests compare the two)
+inline bool poseidon_use_ifma() { static const bool on = poseidon_ifma_supported() && !(std::getenv("LF_POSEIDON_SCALAR") && std::getenv("LF_POSEIDON_SCALAR")[0] == '1'); return on; }
 
 template <class Rg> class Transcript {
     typedef typename Rg::F F;
@@ -27,6 +36,8 @@ template <class Rg> class Transcript {
         u64 sp_row0[RP][W];           // Ms_r first row
         u64 sp_col0[RP][W];           // Ms_r first column (entry 0 unused)
         u64 sp_c0[RP];                // partial rounds: the only constant that has to be added before the S-box (lane 0)
+        PoseidonIfmaMatrix mds_ifma, pre_ifma;   // limb images of mds / pre (Goldilocks on IFMA hosts only)
+        bool ifma = false;
         static void matmul(u64* o, const u64* a, const u64* b) {   // o = a * b (W x W)
             for (int i = 0; i < W; ++i) for (int j = 0; j < W; ++j) { u64 acc = 0; for (int k = 0; k < W; ++k) acc = F::add(acc, F::mul(a[i * W + k], b[k * W + j])); o[i * W + j] = acc; }
         }
@@ -73,6 +84,7 @@ template <class Rg> class Transcript {
             }
             u64* c = ark + (RF / 2 + RP) * W;
             for (int i = 0; i < W; ++i) c[i] = F::add(c[i], carry[i]);
+            if (std::is_same<F, Goldilocks>::value && poseidon_use_ifma()) { poseidon_ifma_prepare(mds, &mds_ifma); poseidon_ifma_prepare(pre, &pre_ifma); ifma = true; }
         }
     };
     static const Tables& tables() { static const Tables t; return t; }
@@ -115,7 +127,8 @@ template <class Rg> class Transcript {
         for (int i = 0; i < W; ++i) x2[i] = wmul(x3[i], x3[i]);
         for (int i = 0; i < W; ++i) st_[i] = wmul(x2[i], a[i]);
     }
-    void dense_layer(const u64* m) {
+    void dense_layer(const u64* m, const PoseidonIfmaMatrix* mi, bool ifma) {
+        if (ifma) { poseidon_ifma_dense(mi, st_); return; }
         u64 nx[W];
         for (int i = 0; i < W; ++i) {
             Acc3 acc; const u64* row = m + i * W;
@@ -130,7 +143,7 @@ template <class Rg> class Transcript {
         int r = 0;
         for (; r < RF / 2; ++r) {
             sbox_layer(&t.ark[r * W]);
-            dense_layer(r == RF / 2 - 1 ? t.pre : t.mds);
+            if (r == RF / 2 - 1) dense_layer(t.pre, &t.pre_ifma, t.ifma); else dense_layer(t.mds, &t.mds_ifma, t.ifma);
         }
         for (int pr = 0; pr < RP; ++pr, ++r) {
             const u64 a = wadd(st_[0], t.sp_c0[pr]);
@@ -146,7 +159,7 @@ template <class Rg> class Transcript {
         }
         for (; r < RF + RP; ++r) {
             sbox_layer(&t.ark[r * W]);
-            dense_layer(t.mds);
+            dense_layer(t.mds, &t.mds_ifma, t.ifma);
         }
     }
 public:

@@ -62,6 +62,34 @@ def test_product_transcript_extreme_lanes_match_oracle(oracle):
     assert np.array_equal(a.get_short_challenge(), b.get_short_challenge())
 
 
+_DIGEST_SNIPPET = """
+import hashlib, numpy as np, latticefold_b200 as lf
+from latticefold_b200 import synth
+G = synth.RING_GOLDILOCKS; p = synth.RINGS[G]["p"]
+t = lf.Transcript(G); h = hashlib.sha256()
+edge = np.array([0, 1, (1 << 32) - 1, 1 << 32, p - (1 << 32), p - 2, p - 1], dtype=np.uint64)
+for step in range(12):
+    t.absorb_base(synth.uniform_field(p, 20 * 7 + step, 100 + step)); t.absorb_base(np.roll(edge, step)); t.absorb_tag("rho_s")
+    for _ in range(3):
+        h.update(t.get_challenge().tobytes())
+    h.update(t.get_short_challenge().tobytes())
+print(t.backend(), t.permutations(), h.hexdigest())
+"""
+
+
+def test_product_poseidon_backends_agree():
+    """the AVX-512 IFMA dense layer (csrc/poseidon_ifma.cpp, picked at run time) and the scalar one give the same transcript; on a
+    host without IFMA both runs are the scalar path and the test only checks that the override is harmless"""
+    import subprocess, sys
+    outs = {}
+    for force_scalar in ("0", "1"):
+        env = dict(os.environ, LF_POSEIDON_SCALAR=force_scalar, PYTHONPATH=ROOT)
+        outs[force_scalar] = subprocess.run([sys.executable, "-c", _DIGEST_SNIPPET], env=env, capture_output=True, text=True, check=True, cwd=ROOT).stdout.split()
+    assert outs["1"][0] == "scalar" and outs["0"][0] in ("scalar", "avx512-ifma")
+    assert outs["0"][1:] == outs["1"][1:]
+    assert lf.Transcript(G).backend() in ("scalar", "avx512-ifma")
+
+
 def test_product_rot_lin_combination_kat():
     # crates/cyclotomic-rings/src/rotation.rs:174-776
     g = json.load(open(os.path.join(GOLD, "rotsum_goldilocks.json")))

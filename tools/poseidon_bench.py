@@ -9,6 +9,8 @@ L.lf_transcript_create.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_void_
 L.lf_transcript_absorb_base.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
 L.lf_transcript_permutations.restype = ctypes.c_uint64
 L.lf_transcript_permutations.argtypes = [ctypes.c_void_p]
+L.lf_host_poseidon_backend.restype = ctypes.c_char_p
+print("goldilocks dense layers:", L.lf_host_poseidon_backend().decode())
 for ring, name in ((0, "goldilocks"), (1, "babybear"), (2, "frog")):
     t = ctypes.c_void_p()
     if L.lf_transcript_create(ring, ctypes.byref(t)):
