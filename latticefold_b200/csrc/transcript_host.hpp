@@ -37,6 +37,11 @@ template <class Rg> class Transcript {
         u64 sp_col0[RP][W];           // Ms_r first column (entry 0 unused)
         u64 sp_c0[RP];                // partial rounds: the only constant that has to be added before the S-box (lane 0)
         PoseidonIfmaMatrix mds_ifma, pre_ifma;   // limb images of mds / pre (Goldilocks on IFMA hosts only)
+        // IFMA hosts run the RP partial rounds in closed form (partial_rounds_closed): with s the state on entry and x_r the S-box
+        // output of round r, lane i >= 1 on exit is s_i + sum_r col0_r[i] x_r and lane 0 after round r is
+        // row0_r[0] x_r + sum_{j>=1} row0_r[j] s_j + sum_{r'<r} pr_t[r][r'] x_r',  pr_t[r][r'] = sum_{j>=1} row0_r[j] col0_r'[j].
+        PoseidonIfmaMatrix pr_v_ifma, pr_c_ifma; // rows r < RP: row0_r without lane 0;  rows i >= 1: (col0_r[i])_r
+        u64 pr_t[RP][RP];
         bool ifma = false;
         static void matmul(u64* o, const u64* a, const u64* b) {   // o = a * b (W x W)
             for (int i = 0; i < W; ++i) for (int j = 0; j < W; ++j) { u64 acc = 0; for (int k = 0; k < W; ++k) acc = F::add(acc, F::mul(a[i * W + k], b[k * W + j])); o[i * W + j] = acc; }
@@ -84,7 +89,18 @@ template <class Rg> class Transcript {
             }
             u64* c = ark + (RF / 2 + RP) * W;
             for (int i = 0; i < W; ++i) c[i] = F::add(c[i], carry[i]);
-            if (std::is_same<F, Goldilocks>::value && poseidon_use_ifma()) { poseidon_ifma_prepare(mds, &mds_ifma); poseidon_ifma_prepare(pre, &pre_ifma); ifma = true; }
+            if (std::is_same<F, Goldilocks>::value && poseidon_use_ifma()) {
+                static_assert(RP <= W, "closed-form partial rounds keep one S-box output per state lane");
+                poseidon_ifma_prepare(mds, &mds_ifma); poseidon_ifma_prepare(pre, &pre_ifma);
+                std::vector<u64> v(W * W, 0), cm(W * W, 0);
+                for (int r = 0; r < RP; ++r) for (int j = 1; j < W; ++j) { v[r * W + j] = sp_row0[r][j]; cm[j * W + r] = sp_col0[r][j]; }
+                poseidon_ifma_prepare(v.data(), &pr_v_ifma); poseidon_ifma_prepare(cm.data(), &pr_c_ifma);
+                for (int r = 0; r < RP; ++r) for (int q = 0; q < RP; ++q) {
+                    u64 acc = 0; if (q < r) for (int j = 1; j < W; ++j) acc = F::add(acc, F::mul(sp_row0[r][j], sp_col0[q][j]));
+                    pr_t[r][q] = acc;
+                }
+                ifma = true;
+            }
         }
     };
     static const Tables& tables() { static const Tables t; return t; }
@@ -138,6 +154,24 @@ template <class Rg> class Transcript {
         }
         std::memcpy(st_, nx, sizeof st_);
     }
+    // all RP partial rounds with two IFMA matrix products and a short scalar chain (see Tables::pr_t): the 23 x RP lane updates lose
+    // their per-round reductions, and only x -> x^7 plus two multiply-adds per round remain serial
+    void partial_rounds_closed(const Tables& t) {
+        u64 u[W], x[W] = {0};
+        std::memcpy(u, st_, sizeof u); poseidon_ifma_dense(&t.pr_v_ifma, u);        // u_r = sum_{j>=1} row0_r[j] s_j, canonical
+        u64 s0 = st_[0];
+        for (int r = 0; r < RP; ++r) {
+            const u64 a = wadd(s0, t.sp_c0[r]);
+            const u64 a2 = wmul(a, a), a3 = wmul(a2, a), a4 = wmul(a2, a2); x[r] = wmul(a4, a3);   // depth 3: a^4 and a^3 in parallel
+            Acc3 acc; acc.mac(u[r], 1);
+            for (int q = 0; q < r; ++q) acc.mac(t.pr_t[r][q], x[q]);
+            acc.mac(t.sp_row0[r][0], x[r]);
+            s0 = acc.reduce();
+        }
+        poseidon_ifma_dense(&t.pr_c_ifma, x);                                       // x_i <- sum_r col0_r[i] x_r, canonical
+        for (int i = 1; i < W; ++i) st_[i] = wadd(st_[i], x[i]);
+        st_[0] = s0;
+    }
     void permute() {
         const Tables& t = tables(); ++permutations_;
         int r = 0;
@@ -145,9 +179,10 @@ template <class Rg> class Transcript {
             sbox_layer(&t.ark[r * W]);
             if (r == RF / 2 - 1) dense_layer(t.pre, &t.pre_ifma, t.ifma); else dense_layer(t.mds, &t.mds_ifma, t.ifma);
         }
-        for (int pr = 0; pr < RP; ++pr, ++r) {
+        if (t.ifma) { partial_rounds_closed(t); r += RP; }
+        else for (int pr = 0; pr < RP; ++pr, ++r) {
             const u64 a = wadd(st_[0], t.sp_c0[pr]);
-            const u64 a2 = wmul(a, a), a3 = wmul(a2, a), a6 = wmul(a3, a3), x0 = wmul(a6, a);
+            const u64 a2 = wmul(a, a), a3 = wmul(a2, a), a4 = wmul(a2, a2), x0 = wmul(a4, a3);     // depth 3: a^4 and a^3 in parallel
             const u64* row = t.sp_row0[pr]; const u64* col = t.sp_col0[pr];
             Acc3 acc;                                      // lane 0 last: the other 23 products do not wait for the S-box
 #pragma GCC unroll 23
