@@ -90,6 +90,22 @@ def test_product_poseidon_backends_agree():
     assert lf.Transcript(G).backend() in ("scalar", "avx512-ifma")
 
 
+def test_poseidon_ifma_dense_layer_edges(tmp_path):
+    """csrc/poseidon_ifma.cpp against 128-bit `%` arithmetic on 2.8 million lanes, random and at the edges of every limb / carry
+    decision (tests/native/poseidon_ifma_edge.cpp); skipped where the host has no AVX-512 IFMA or no g++"""
+    import shutil, subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "ifma_edge")
+    subprocess.run([gxx, "-O2", "-march=x86-64-v3", "-std=c++17", os.path.join(ROOT, "tests", "native", "poseidon_ifma_edge.cpp"),
+                    os.path.join(ROOT, "latticefold_b200", "csrc", "poseidon_ifma.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    if out[:1] == ["no-ifma"]:
+        pytest.skip("host without AVX-512 IFMA")
+    assert out[-4] == "lanes" and int(out[-3]) > 2_000_000 and out[-2:] == ["bad", "0"], out
+
+
 def test_product_rot_lin_combination_kat():
     # crates/cyclotomic-rings/src/rotation.rs:174-776
     g = json.load(open(os.path.join(GOLD, "rotsum_goldilocks.json")))
