@@ -14,7 +14,7 @@
 namespace lf {
 
 // AVX-512 IFMA dense layer for the Goldilocks field (poseidon_ifma.cpp, compiled by g++; chosen at run time)
-struct PoseidonIfmaMatrix { alignas(64) u64 limb[POSEIDON_W24_WIDTH][3][3][8]; };
+struct PoseidonIfmaMatrix { alignas(64) u64 limb[POSEIDON_W24_WIDTH][2][3][8]; };
 bool poseidon_ifma_supported();
 void poseidon_ifma_prepare(const u64* m, PoseidonIfmaMatrix* out);
 void poseidon_ifma_dense(const PoseidonIfmaMatrix* M, u64* st);

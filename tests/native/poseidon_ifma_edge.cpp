@@ -10,7 +10,7 @@
 #include <random>
 #include <vector>
 typedef uint64_t u64; typedef unsigned __int128 u128;
-namespace lf { struct PoseidonIfmaMatrix { alignas(64) u64 limb[24][3][3][8]; }; bool poseidon_ifma_supported(); void poseidon_ifma_prepare(const u64*, PoseidonIfmaMatrix*); void poseidon_ifma_dense(const PoseidonIfmaMatrix*, u64*); }
+namespace lf { struct PoseidonIfmaMatrix { alignas(64) u64 limb[24][2][3][8]; }; bool poseidon_ifma_supported(); void poseidon_ifma_prepare(const u64*, PoseidonIfmaMatrix*); void poseidon_ifma_dense(const PoseidonIfmaMatrix*, u64*); }
 static const u64 P = 0xFFFFFFFF00000001ULL;
 static long bad = 0, total = 0;
 static void check(const u64* m, const u64* st) {
