@@ -292,7 +292,13 @@ struct BabyBear {
     static LF_HD u64 reduce(const Acc& a) { return a.fold(); }
     static LF_HD u64 reduce128(u64 lo, u64 hi) { return (u64)((((u128)hi << 64) | lo) % P); }
     static LF_HD u64 from_split(u64 lo, u64 hi) { return (u64)((((u128)hi << 32) + lo) % P); }
-    static inline u64 reduce_wide(u128 lo, u128 hi) { u128 t = ((hi % P) * (((u128)1 << 64) % P)) % P; return (u64)((t + lo % P) % P); }
+    // (lo + hi * 2^64) mod p word by word: 64-bit remainders by the constant p only (the host Poseidon calls this once per state lane
+    // and layer; the 128-bit `%` it replaces is a library call)
+    static inline u64 reduce_wide(u128 lo, u128 hi) {
+        constexpr u64 C128 = (C64 * C64) % P;
+        const u64 w0 = (u64)lo % P, w1 = ((u64)(lo >> 64) % P + (u64)hi % P) % P, w2 = (u64)(hi >> 64) % P;
+        return (w0 + (w1 * C64) % P + (w2 * C128) % P) % P;
+    }
     static LF_HD u64 from_i64(int64_t v) { return v >= 0 ? (u64)v % P : (P - ((u64)(-v) % P)) % P; }
     static LF_HD int64_t to_signed(u64 a) { return a <= (P - 1) / 2 ? (int64_t)a : -(int64_t)(P - a); }
     static inline u64 pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = mul(r, a); a = mul(a, a); e >>= 1; } return r; }
