@@ -122,6 +122,17 @@ size_t lf_ajtai_width(const lf_ajtai* a);
 lf_status lf_commit(lf_ctx* ctx, const lf_ajtai* a, const lf_vec* f_ntt, uint64_t* out_host);
 /* the K-1 commits of one decomposition in a single pass over the matrix (decomposition.rs:178-201)                */
 lf_status lf_commit_batch(lf_ctx* ctx, const lf_ajtai* a, const lf_vec* const* f_ntt, int32_t count, uint64_t* out_host);
+/* commit_coeff (commitment_scheme.rs:80-87): CRT of every element, then commit                                      */
+lf_status lf_commit_coeff(lf_ctx* ctx, const lf_ajtai* a, const lf_vec* f_coeff, uint64_t* out_host);
+/* decompose_and_commit_coeff / _ntt (commitment_scheme.rs:89-114): G_B^{-1} of a coefficient-form (or, after ICRT, an NTT-form)
+ * vector of n / L elements -- every element becomes L consecutive digit elements -- then commit_coeff.  A coefficient that does
+ * not fit L digits of base B -> LF_ERR_DOES_NOT_FIT; (n / L) mismatch -> LF_ERR_WRONG_WITNESS_LEN                               */
+lf_status lf_decompose_and_commit_coeff(lf_ctx* ctx, const lf_ajtai* a, const lf_vec* f_coeff, uint64_t B, int32_t L, uint64_t* out_host);
+lf_status lf_decompose_and_commit_ntt(lf_ctx* ctx, const lf_ajtai* a, const lf_vec* w_ntt, uint64_t B, int32_t L, uint64_t* out_host);
+/* the commitments of all K pieces of decompose_to_vec(b, K) of a coefficient-form witness (decompose_witness + commit_witnesses,
+ * decomposition.rs:162-201, without the y_0 shortcut): out_host = K x kappa ring elements.  On the Goldilocks ring the pieces are
+ * committed straight from their int8 digits as an integer GEMM on the tensor cores (csrc/commit_mma.cuh)                         */
+lf_status lf_commit_pieces(lf_ctx* ctx, const lf_ajtai* a, const lf_vec* f_coeff, uint64_t b, int32_t K, uint64_t* out_host);
 
 /* ---- a6: mat_vec_mul / calculate_Mz_mles (arith/utils.rs:52-65; mle_helpers.rs:137-146)                          */
 lf_status lf_sparse_create(lf_ctx* ctx, size_t nrows, size_t ncols, const uint64_t* row_ptr, const uint64_t* col,

@@ -25,7 +25,8 @@ FORM_NTT, FORM_COEFF = 0, 1
 # every symbol include/lf_b200.h declares (tests check that the built library exports all of them)
 SYMBOLS = """lf_ring_describe lf_ctx_create lf_ctx_destroy lf_last_error lf_ctx_sync lf_ctx_stream lf_ctx_launches lf_ctx_profile lf_ctx_profile_report lf_ctx_set_shard lf_ctx_collectives lf_nccl_unique_id lf_ctx_set_shard_nccl lf_ctx_p2p_export lf_ctx_p2p_import
 lf_vec_upload lf_vec_download lf_vec_len lf_vec_form lf_vec_free lf_crt lf_icrt lf_gadget_decompose lf_gadget_recompose
-lf_decompose_to_vec lf_fhat lf_ajtai_create lf_ajtai_free lf_ajtai_kappa lf_ajtai_width lf_commit lf_commit_batch
+lf_decompose_to_vec lf_fhat lf_ajtai_create lf_ajtai_free lf_ajtai_kappa lf_ajtai_width lf_commit lf_commit_batch lf_commit_coeff
+lf_decompose_and_commit_coeff lf_decompose_and_commit_ntt lf_commit_pieces
 lf_sparse_create lf_sparse_free lf_spmv lf_eq_table lf_mle_eval_batch lf_lincomb lf_sumcheck_begin lf_sumcheck_round
 lf_sumcheck_finish lf_sumcheck_free lf_transcript_create lf_transcript_clone lf_transcript_free lf_transcript_absorb
 lf_transcript_absorb_base lf_transcript_absorb_tag lf_transcript_get_challenge lf_transcript_get_short_challenge
@@ -142,6 +143,9 @@ def lib():
     L.lf_ajtai_kappa.argtypes = L.lf_ajtai_width.argtypes = [vp]
     L.lf_commit.argtypes = [vp, vp, vp, u64p]
     L.lf_commit_batch.argtypes = [vp, vp, C.POINTER(vp), C.c_int32, u64p]
+    L.lf_commit_coeff.argtypes = [vp, vp, vp, u64p]
+    L.lf_decompose_and_commit_coeff.argtypes = L.lf_decompose_and_commit_ntt.argtypes = [vp, vp, vp, C.c_uint64, C.c_int32, u64p]
+    L.lf_commit_pieces.argtypes = [vp, vp, vp, C.c_uint64, C.c_int32, u64p]
     L.lf_sparse_create.argtypes = [vp, C.c_size_t, C.c_size_t, u64p, u64p, u64p, C.POINTER(vp)]
     L.lf_sparse_free.argtypes = [vp, vp]
     L.lf_spmv.argtypes = [vp, vp, vp, C.POINTER(vp)]
@@ -498,7 +502,16 @@ class AjtaiCommitmentScheme:
         self.ctx.check(self.ctx.L.lf_commit_batch(self.ctx.h, self.h, arr, len(fs), ptr(o))); return o
 
     def commit_coeff(self, f_coeff):    # commitment_scheme.rs:80-87
-        return self.commit(self.ctx.crt(f_coeff))
+        o = np.empty((self.kappa(), self.ctx.d), dtype=np.uint64); self.ctx.check(self.ctx.L.lf_commit_coeff(self.ctx.h, self.h, f_coeff.h, ptr(o))); return o
+
+    def decompose_and_commit_coeff(self, f_coeff, B, L):    # commitment_scheme.rs:89-101
+        o = np.empty((self.kappa(), self.ctx.d), dtype=np.uint64); self.ctx.check(self.ctx.L.lf_decompose_and_commit_coeff(self.ctx.h, self.h, f_coeff.h, B, L, ptr(o))); return o
+
+    def decompose_and_commit_ntt(self, w, B, L):            # commitment_scheme.rs:103-113
+        o = np.empty((self.kappa(), self.ctx.d), dtype=np.uint64); self.ctx.check(self.ctx.L.lf_decompose_and_commit_ntt(self.ctx.h, self.h, w.h, B, L, ptr(o))); return o
+
+    def commit_pieces(self, f_coeff, b, K):                 # decompose_witness + commit_witnesses, decomposition.rs:162-201
+        o = np.empty((K, self.kappa(), self.ctx.d), dtype=np.uint64); self.ctx.check(self.ctx.L.lf_commit_pieces(self.ctx.h, self.h, f_coeff.h, b, K, ptr(o))); return o
 
     def __del__(self):
         try:

@@ -1,6 +1,7 @@
 // Host-side engine: device memory, launches and the per-op drivers behind the C ABI (include/lf_b200.h).
 #pragma once
 #include "kernels.cuh"
+#include "commit_mma.cuh"
 #include "transcript_host.hpp"
 #include "../../include/lf_b200.h"
 #include <vector>
@@ -83,7 +84,9 @@ struct lf_ctx {
     std::vector<ProfRec> prof;
 };
 struct lf_vec { lf::u64* p = nullptr; size_t n = 0, pitch = 0; int form = 0; };
-struct lf_ajtai { lf::u64* p = nullptr; size_t kappa = 0, n = 0, pitch = 0; };
+struct lf_ajtai { lf::u64* p = nullptr; size_t kappa = 0, n = 0, pitch = 0;
+                  // byte-limb tiles of the matrix for the tensor-core digit commit (commit_mma.cuh); absent on rings that do not use it
+                  uint8_t* a8 = nullptr; int a8_tiles = 0, a8_chunks = 0; void* epi = nullptr; };
 struct lf_sparse { lf::u32 *row_ptr = nullptr, *col = nullptr; lf::u64* val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0, val_pitch = 0, eff_rows = 0; };
 
 namespace lf {
@@ -305,6 +308,54 @@ template <class Rg> struct Engine {
             }
         });
         reduce_partials_allreduce(a.partial, (int)xt, nout, d_out);      // x axis sharded across ranks: one small all-reduce per batched dot
+    }
+    // ---------------------------------------------------------------- tensor-core commit of digit pieces (commit_mma.cuh)
+    static bool commit_mma_supported() { return Rg::ID == 0 && !(std::getenv("LF_COMMIT_MMA") && std::getenv("LF_COMMIT_MMA")[0] == '0'); }
+    // byte-limb tiles + epilogue tables of an uploaded matrix (once per matrix)
+    void ajtai_build_tiles(lf_ajtai* A) {
+        if constexpr (Rg::ID == 0) {
+            if (!commit_mma_supported() || !A->kappa || !A->n || A->n >= ((size_t)1 << 23)) return;
+            const int g_total = (int)(S * TAU * A->kappa), ntiles = (g_total + cmma::GROUPS - 1) / cmma::GROUPS, nchunks = (int)((A->n + cmma::J - 1) / cmma::J);
+            LF_CUDA(cudaMalloc(&A->a8, (size_t)ntiles * nchunks * cmma::A_STAGE_BYTES));
+            const size_t work = (size_t)ntiles * cmma::GROUPS * nchunks * (cmma::J / 16);
+            launch("k_a8_tile", [&] { cmma::k_a8_tile<Rg><<<blocks_for(work), 256, 0, st()>>>(A->p, A->pitch * D, A->pitch, A->n, (int)A->kappa, g_total, nchunks, (size_t)ntiles * cmma::GROUPS, A->a8); });
+            cmma::EpiTables<Rg> t; const RingTables<Rg>& rt = tab();
+            for (int s = 0; s < S; ++s) {
+                for (int r = 0; r < TAU; ++r) { t.perm[s][r] = (rt.k[s] * r) % TAU; t.corr[s][r] = 0; }
+                for (int c = 0; c < D; ++c) { t.val[s][c] = rt.crt[s * TAU + t.perm[s][c % TAU]][c]; t.corr[s][c % TAU] = F::add(t.corr[s][c % TAU], t.val[s][c]); }
+                for (int r = 0; r < TAU; ++r) t.corr[s][r] = F::mul(t.corr[s][r], (u64)1 << 31);
+            }
+            LF_CUDA(cudaMalloc(&A->epi, sizeof t)); LF_CUDA(cudaMemcpyAsync(A->epi, &t, sizeof t, cudaMemcpyHostToDevice, st())); sync();
+            A->a8_tiles = ntiles; A->a8_chunks = nchunks;
+            static bool attr_set = false;
+            if (!attr_set) { LF_CUDA(cudaFuncSetAttribute(cmma::k_commit_mma<Rg>, cudaFuncAttributeMaxDynamicSharedMemorySize, commit_mma_smem())); attr_set = true; }
+        }
+    }
+    static constexpr int commit_mma_smem() { return cmma::STAGES * (cmma::A_STAGE_BYTES + D * cmma::MAX_PIECES * cmma::J); }
+    bool can_commit_digits(const lf_ajtai* A, int ncols, size_t dig_pitch) const { return A->a8 && ncols >= 1 && ncols <= cmma::MAX_PIECES && dig_pitch >= (size_t)A->a8_chunks * cmma::J && dig_pitch % 16 == 0; }
+    // y[i][p] = sum_j A[i][j] * CRT(digit piece p)[j] for `ncols` consecutive digit pieces (planes zero beyond n); result kappa x ncols x D limbs
+    void commit_digits(const lf_ajtai* A, const int8_t* dig, size_t dig_pitch, size_t dig_stride, int ncols, u64* d_out) {
+        if constexpr (Rg::ID == 0) {
+            const int nchunks = A->a8_chunks, ntiles = A->a8_tiles;
+            const size_t d_stage = (size_t)D * ncols * cmma::J;
+            int8_t* d8 = dalloc<int8_t>(d_stage * nchunks);
+            launch("k_d8_tile", [&] { cmma::k_d8_tile<Rg><<<blocks_for((size_t)ncols * D * (cmma::J / 16) * nchunks), 256, 0, st()>>>(dig, dig_pitch, dig_stride, ncols, nchunks, d8); });
+            // split the witness axis so that the grid fills whole waves of 148 SMs (one CTA per SM: 512 TMEM columns each)
+            int best = 1; double best_eff = 0;
+            for (int sp = 1; sp <= 64 && sp <= nchunks; ++sp) { const int ctas = ntiles * sp, waves = (ctas + 147) / 148; const double eff = (double)ctas / (148.0 * waves);
+                if (nchunks / sp < 8 && sp > 1) break; if (eff > best_eff + 1e-9 || (eff > best_eff - 0.02 && sp > best && waves <= 8)) { best_eff = std::max(best_eff, eff); best = sp; } }
+            if (const char* e = std::getenv("LF_COMMIT_SPLITS")) { int v = atoi(e); if (v >= 1 && v <= nchunks) best = v; }
+            const int nsplits = best, cps = (nchunks + nsplits - 1) / nsplits, nsp = (nchunks + cps - 1) / cps;
+            const int npad = (ncols + 1) / 2 * 2, ntot = D * npad;
+            cmma::Args a; a.A8 = A->a8; a.D8 = d8; a.nchunks = nchunks; a.chunks_per_split = cps; a.ncols = ncols;
+            a.n_mma1 = std::min(ntot, 192); a.n_mma2 = ntot - a.n_mma1; a.kappa = (int)A->kappa; a.g_total = (int)(S * TAU * A->kappa);
+            a.d_stage_bytes = (u32)d_stage; a.tables = A->epi;
+            const size_t nout = A->kappa * (size_t)ncols * D;
+            a.partial = partial_dev((size_t)nsp * TAU * nout);
+            launch("k_commit_mma", [&] { cmma::k_commit_mma<Rg><<<dim3(ntiles, nsp), cmma::THREADS, commit_mma_smem(), st()>>>(a); });
+            dfree(d8);
+            reduce_partials_allreduce(a.partial, nsp * TAU, nout, d_out);
+        } else throw LfException(LF_ERR_UNSUPPORTED, "tensor-core commit is built for the Goldilocks ring");
     }
     // f-hat evaluation from coefficient planes; result nvec x TAU x D limbs on the device
     template <class TIn> void coeff_eval(const TIn* coeff, size_t c_pitch, size_t c_vec_stride, int nvec, const u64* eq, size_t eq_pitch, size_t n, u64* d_out) {

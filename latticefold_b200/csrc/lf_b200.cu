@@ -144,11 +144,15 @@ lf_status lf_decompose_to_vec(lf_ctx* c, const lf_vec* in, uint64_t b, int32_t K
 lf_status lf_fhat(lf_ctx* c, const lf_vec* in, lf_vec** out_tau) { return guard(c, [&] { ops(c->ring)->fhat(c, in, out_tau); }); }
 // ---- Ajtai
 lf_status lf_ajtai_create(lf_ctx* c, size_t kappa, size_t n, const uint64_t* host, lf_ajtai** out) { *out = nullptr; return guard(c, [&] { ops(c->ring)->ajtai_create(c, kappa, n, host, out); }); }
-void lf_ajtai_free(lf_ctx* c, lf_ajtai* a) { if (a) { cudaStreamSynchronize(c->stream); cudaFree(a->p); delete a; } }
+void lf_ajtai_free(lf_ctx* c, lf_ajtai* a) { if (a) { cudaStreamSynchronize(c->stream); cudaFree(a->p); cudaFree(a->a8); cudaFree(a->epi); delete a; } }
 size_t lf_ajtai_kappa(const lf_ajtai* a) { return a->kappa; }
 size_t lf_ajtai_width(const lf_ajtai* a) { return a->n; }
 lf_status lf_commit_batch(lf_ctx* c, const lf_ajtai* a, const lf_vec* const* f, int32_t count, uint64_t* out_host) { return guard(c, [&] { ops(c->ring)->commit_batch(c, a, f, count, out_host); }); }
 lf_status lf_commit(lf_ctx* c, const lf_ajtai* a, const lf_vec* f, uint64_t* out_host) { return lf_commit_batch(c, a, &f, 1, out_host); }
+lf_status lf_commit_coeff(lf_ctx* c, const lf_ajtai* a, const lf_vec* f, uint64_t* out_host) { return guard(c, [&] { ops(c->ring)->commit_coeff(c, a, f, out_host); }); }
+lf_status lf_decompose_and_commit_coeff(lf_ctx* c, const lf_ajtai* a, const lf_vec* f, uint64_t B, int32_t L, uint64_t* out_host) { return guard(c, [&] { ops(c->ring)->decompose_and_commit(c, a, f, false, B, L, out_host); }); }
+lf_status lf_decompose_and_commit_ntt(lf_ctx* c, const lf_ajtai* a, const lf_vec* w, uint64_t B, int32_t L, uint64_t* out_host) { return guard(c, [&] { ops(c->ring)->decompose_and_commit(c, a, w, true, B, L, out_host); }); }
+lf_status lf_commit_pieces(lf_ctx* c, const lf_ajtai* a, const lf_vec* f, uint64_t b, int32_t K, uint64_t* out_host) { return guard(c, [&] { ops(c->ring)->commit_pieces(c, a, f, b, K, out_host); }); }
 // ---- sparse
 lf_status lf_sparse_create(lf_ctx* c, size_t nrows, size_t ncols, const uint64_t* row_ptr, const uint64_t* col, const uint64_t* val, lf_sparse** out) {
     *out = nullptr; return guard(c, [&] { ops(c->ring)->sparse_create(c, nrows, ncols, row_ptr, col, val, out); });

@@ -249,7 +249,9 @@ template <class Rg> struct Prover {
         if (K > 1) {
             PtrList Y; for (int k = 1; k < K; ++k) { Y.p[k - 1] = pieces + (size_t)k * sb.pc_stride; Y.len[k - 1] = n; }
             u64* d_y = E.template dalloc<u64>(kappa * (K - 1) * D);
-            E.dot(P->A->p, P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y, "k_dot_commit");
+            // digit pieces: integer GEMM on the tensor cores straight from the int8 digits (commit_mma.cuh); otherwise lazily reduced dot products
+            if (E.can_commit_digits(P->A, K - 1, sb.dig_pitch)) E.commit_digits(P->A, dig + sb.dig_stride, sb.dig_pitch, sb.dig_stride, K - 1, d_y);
+            else E.dot(P->A->p, P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y, "k_dot_commit");
             o.y_pin = E.d2h_async(d_y, kappa * (K - 1) * D); E.dfree(d_y);
         }
         mark("dec.commit");

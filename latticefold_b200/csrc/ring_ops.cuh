@@ -38,6 +38,9 @@ struct RingOps {
     virtual void fhat(lf_ctx* c, const lf_vec* in, lf_vec** out_tau) = 0;
     virtual void ajtai_create(lf_ctx* c, size_t kappa, size_t n, const uint64_t* host, lf_ajtai** out) = 0;
     virtual void commit_batch(lf_ctx* c, const lf_ajtai* a, const lf_vec* const* f, int32_t count, uint64_t* out_host) = 0;
+    virtual void commit_coeff(lf_ctx* c, const lf_ajtai* a, const lf_vec* f_coeff, uint64_t* out_host) = 0;
+    virtual void decompose_and_commit(lf_ctx* c, const lf_ajtai* a, const lf_vec* v, bool ntt_form, uint64_t B, int32_t L, uint64_t* out_host) = 0;
+    virtual void commit_pieces(lf_ctx* c, const lf_ajtai* a, const lf_vec* f_coeff, uint64_t b, int32_t K, uint64_t* out_host) = 0;
     virtual void sparse_create(lf_ctx* c, size_t nrows, size_t ncols, const uint64_t* row_ptr, const uint64_t* col, const uint64_t* val, lf_sparse** out) = 0;
     virtual void spmv(lf_ctx* c, const lf_sparse* m, const lf_vec* z, lf_vec** out) = 0;
     virtual void eq_table(lf_ctx* c, const uint64_t* r, int32_t s, lf_vec** out) = 0;
@@ -134,7 +137,7 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         LF_CUDA(cudaMalloc(&a->p, std::max<size_t>(1, kappa * a->pitch * Rg::D) * 8));
         // row by row so the staging buffer stays small (the matrix is 1.3 GB at kappa=26, n=2^18)
         for (size_t i = 0; i < kappa; ++i) E.upload_planes(host + i * n * Rg::D, n, a->p + i * a->pitch * Rg::D, a->pitch);
-        E.sync(); *out = a.release();
+        E.sync(); E.ajtai_build_tiles(a.get()); *out = a.release();
     }
     void commit_batch(lf_ctx* c, const lf_ajtai* a, const lf_vec* const* f, int32_t count, uint64_t* out_host) override {
         Engine<Rg> E(c);
@@ -147,6 +150,46 @@ template <class Rg> struct RingOpsImpl final : RingOps {
             HV all(a->kappa * chunk * Rg::D); E.download_words(d_out, all.size(), all.data());
             for (int i = 0; i < chunk; ++i) for (size_t r = 0; r < a->kappa; ++r) std::memcpy(out_host + ((size_t)(done + i) * a->kappa + r) * Rg::D, &all[(r * chunk + i) * Rg::D], 8 * Rg::D);
         }
+    }
+    void commit_coeff(lf_ctx* c, const lf_ajtai* a, const lf_vec* f_coeff, uint64_t* out_host) override {
+        if (f_coeff->n != a->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongWitnessLength(" + std::to_string(f_coeff->n) + ", " + std::to_string(a->n) + ")");
+        Engine<Rg> E(c); lf_vec* f = E.vec_alloc(f_coeff->n, LF_FORM_NTT); E.crt(f_coeff->p, f_coeff->pitch, f->p, f->pitch, f->n, false);
+        try { const lf_vec* fp = f; commit_batch(c, a, &fp, 1, out_host); } catch (...) { E.vec_free(f); throw; }
+        E.vec_free(f);
+    }
+    void decompose_and_commit(lf_ctx* c, const lf_ajtai* a, const lf_vec* v, bool ntt_form, uint64_t B, int32_t L, uint64_t* out_host) override {
+        if (L < 1 || v->n * (size_t)L != a->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongWitnessLength(" + std::to_string(v->n * (size_t)std::max(L, 0)) + ", " + std::to_string(a->n) + ")");
+        Engine<Rg> E(c); lf_vec* co = nullptr; lf_vec* dg = E.vec_alloc(a->n, LF_FORM_COEFF);
+        try {
+            const lf_vec* src = v;
+            if (ntt_form) { co = E.vec_alloc(v->n, LF_FORM_COEFF); E.crt(v->p, v->pitch, co->p, co->pitch, v->n, true); src = co; }
+            E.gadget_decompose(src->p, src->pitch, dg->p, dg->pitch, src->n, B, L);
+            E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_and_commit: a coefficient does not fit L digits of base B");
+            commit_coeff(c, a, dg, out_host);
+        } catch (...) { E.vec_free(co); E.vec_free(dg); throw; }
+        E.vec_free(co); E.vec_free(dg);
+    }
+    void commit_pieces(lf_ctx* c, const lf_ajtai* a, const lf_vec* f_coeff, uint64_t b, int32_t K, uint64_t* out_host) override {
+        if (f_coeff->n != a->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongWitnessLength(" + std::to_string(f_coeff->n) + ", " + std::to_string(a->n) + ")");
+        Engine<Rg> E(c); const size_t n = a->n, dp = (n + 255) / 256 * 256, ds = dp * Rg::D, kappa = a->kappa;
+        int8_t* dig = E.template dalloc<int8_t>((size_t)K * ds); u64* pieces = nullptr;
+        try {
+            LF_CUDA(cudaMemsetAsync(dig, 0, (size_t)K * ds, E.st()));
+            E.digit_split(f_coeff->p, f_coeff->pitch, dig, dp, n, b, K);
+            E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_to_vec: a coefficient does not fit K digits of base b");
+            const bool mma = E.can_commit_digits(a, 1, dp);
+            if (!mma) { pieces = E.template dalloc<u64>((size_t)K * pitch_of(n) * Rg::D); E.crt_digits(dig, dp, pieces, pitch_of(n), n, K, ds, pitch_of(n) * Rg::D); }
+            for (int done = 0; done < K; done += 16) {
+                const int chunk = std::min(16, K - done);
+                u64* d_out = E.small_dev(kappa * chunk * Rg::D);
+                if (mma) E.commit_digits(a, dig + (size_t)done * ds, dp, ds, chunk, d_out);
+                else { PtrList Y; for (int i = 0; i < chunk; ++i) { Y.p[i] = pieces + (size_t)(done + i) * pitch_of(n) * Rg::D; Y.len[i] = n; }
+                       E.dot(a->p, a->pitch * Rg::D, a->pitch, (int)kappa, nullptr, Y, pitch_of(n), chunk, n, d_out); }
+                HV all(kappa * chunk * Rg::D); E.download_words(d_out, all.size(), all.data());
+                for (int i = 0; i < chunk; ++i) for (size_t r = 0; r < kappa; ++r) std::memcpy(out_host + ((size_t)(done + i) * kappa + r) * Rg::D, &all[(r * chunk + i) * Rg::D], 8 * Rg::D);
+            }
+        } catch (...) { E.dfree(dig); E.dfree(pieces); throw; }
+        E.dfree(dig); E.dfree(pieces);
     }
     void sparse_create(lf_ctx* c, size_t nrows, size_t ncols, const uint64_t* row_ptr, const uint64_t* col, const uint64_t* val, lf_sparse** out) override {
         Engine<Rg> E(c); std::unique_ptr<lf_sparse> m(new lf_sparse); m->nrows = nrows; m->ncols = ncols; m->nnz = row_ptr[nrows];

@@ -153,3 +153,31 @@ def split_lcccs(ring, prob, words):
         o += cnt * d
     assert o == words.size
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The workloads bench.py times (BASELINE.json configs) -- shared by bench.py, the golden-digest
+# generator (tools/make_bench_golden.py) and the full-size GPU tests, so that all three prove the same instance.
+def bench_workload(config, log_w):
+    """c2: configs[1] = Goldilocks, DP (B, L, b, K) = (65536, 4, 2, 16), kappa = 26 (benches/config.toml goldilocks row n=32768
+    extrapolated, as SURVEY.md 8 does), dummy R1CS, non-scalar witness; weak-scaled over G ranks it is configs[3] (C4) at log_w = 19.
+    c3: configs[2] = BabyBear ring, BabyBearDP (256, 4, 2, 8) (decomposition_parameters.rs:98-104), kappa = 8, the reference's
+    degree-three CCS (arith/ccs.rs:14-43)."""
+    if config == "c2":
+        return dict(config="c2", ring=RING_GOLDILOCKS, W=1 << log_w, B=1 << 16, L=4, b=2, K=16, kappa=26, kind="non_scalar", degree=2)
+    if config == "c3":
+        return dict(config="c3", ring=RING_BABYBEAR, W=1 << log_w, B=1 << 8, L=4, b=2, K=8, kappa=8, kind="non_scalar", degree=3)
+    raise ValueError(config)
+
+
+def bench_instance(wl, rank, world, ops=None):
+    """Synthetic inputs of one step, holding only this rank's column slice of the Ajtai matrix (kappa x n/world independent
+    uniform ring elements, SplitMix64 seeded per rank) -- the full 8-GPU matrix would be 10.5 GB per process."""
+    ring = wl["ring"]; R = RINGS[ring]
+    seed = (SEED_BASE + 100) & MASK
+    n = wl["W"] * wl["L"]
+    w_ccs = make_witness(ring, wl["W"], wl["kind"], seed)
+    ccs = make_ccs(ring, wl["W"], wl["L"], wl["kind"], w_ccs, 1, wl.get("degree", 2), ops)
+    A = uniform_field(R["p"], wl["kappa"] * (n // world) * R["d"], seed + 7919 * (rank + 1)).reshape(wl["kappa"], n // world, R["d"])
+    return dict(ring=ring, B=wl["B"], L=wl["L"], b=wl["b"], K=wl["K"], kappa=wl["kappa"], n=n, W=wl["W"], A=A, ccs=ccs, w_ccs=w_ccs,
+                cm_i_x_ccs=one(ring, 1), constraints=1 + wl["W"] + 1, kind=wl["kind"])

@@ -73,3 +73,15 @@ def step_golden():
 def step_instance(case, ops):
     ring, W, B, L, b, K, kappa, kind, degree, config_id = case
     return synth.make_instance(ring, W, B, L, b, K, kappa, kind=kind, config_id=config_id, ops=ops, degree=degree)
+
+
+# ---- committed digests of the steps bench.py times (tests/golden/bench_digests.json, written by tools/make_bench_golden.py)
+BENCH_GOLDEN_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench_digests.json")
+
+
+def bench_case_key(config, log_w):
+    return "%s_logw%d" % (config, log_w)
+
+
+def bench_golden():
+    return json.load(open(BENCH_GOLDEN_PATH))["cases"]
