@@ -5,6 +5,8 @@
   python bench.py --impl reference --gpus N --steps K ...  CPU arm: the C++ restatement of the reference algorithm
                                                            (oracle/, kind "port": the reference itself is Rust with an
                                                            un-vendored dependency and cannot be built in this image)
+  python bench.py --config c3 [--log-w 20]                 BASELINE configs[2]: BabyBear ring, degree-three CCS, one GPU
+  python bench.py --config ntt [--gpus N]                  BASELINE configs[4]: negacyclic NTT sweep (GB/s per size, JSON line)
 
 A step = one NIFSProver::prove (linearization + 2 decompositions + folding; crates/latticefold/benches/utils.rs:619-680)
 on the configuration BASELINE.json quotes the metric on (configs[1]: Goldilocks ring, 2^16-constraint R1CS, 1 GPU).
@@ -25,14 +27,13 @@ sys.path.insert(0, ROOT)
 
 from latticefold_b200 import synth  # noqa: E402
 
-RING = synth.RING_GOLDILOCKS
-E_BYTES = 24 * 8     # bytes per ring element (reference layout: 24 u64 limbs)
+METRIC = "prover constraints/sec (commit+decomp+sumcheck)"
+DTYPE = {"c2": "u64 (mod 2^64-2^32+1)", "c3": "u32 (mod 15*2^27+1)"}
 
 
-def workload(log_w):
-    """configs[1] of BASELINE.json = SURVEY 8 row C2: W = 2^16, DP (B, L, b, K) = (65536, 4, 2, 16), kappa = 26
-    (crates/latticefold/benches/config.toml goldilocks row n=32768 extrapolated, as SURVEY.md 8 does)."""
-    return dict(W=1 << log_w, B=1 << 16, L=4, b=2, K=16, kappa=26, kind="non_scalar")
+def workload(log_w, config="c2"):
+    """configs[1] of BASELINE.json = SURVEY 8 row C2 (see synth.bench_workload); c3 = configs[2]."""
+    return synth.bench_workload(config, log_w)
 
 
 def peaks():
@@ -93,43 +94,88 @@ class ClockSampler:
 
 def cpu_step(orc, prob, threads):
     orc.set_threads(threads)
-    _, _, _, ms = orc.nifs_prove(prob, orc.transcript(RING), want_f=True)
+    _, _, _, ms = orc.nifs_prove(prob, orc.transcript(prob["ring"]), want_f=True)
     return ms
 
 
 def run_reference(args, rank, world):
-    """CPU arm: C++ restatement of the reference algorithm on the host cores, on a bounded sample of the workload."""
+    """CPU arm: C++ restatement of the reference algorithm on the host cores, on the SAME configuration as the product arm
+    (same instance generator, same W).  A full-size step takes about a minute on 16 cores, so the number of timed steps is capped
+    by a wall-clock budget (--cpu-budget-s, default 240 s; at least one step) and no untimed warm-up step is spent: the line's
+    `steps` / `warmup` are the counts actually run, the requested ones are kept under `requested`."""
     if rank != 0:
         return
     from oracle.pyoracle import Oracle
     from tests.helpers import OracleOps
+    from tools.make_bench_golden import oracle_bench_problem
     orc = Oracle()
     cores = os.cpu_count() or 1
     orc.set_threads(cores)
     import math
-    wl = workload(args.log_w + int(math.log2(max(args.gpus, 1))))
-    sample_log_w = min(args.log_w, args.cpu_sample_log_w)
-    swl = dict(wl, W=1 << sample_log_w)
-    prob = synth.make_instance(RING, swl["W"], swl["B"], swl["L"], swl["b"], swl["K"], swl["kappa"], kind=swl["kind"], config_id=2, ops=OracleOps(orc))
-    for _ in range(args.warmup):
-        cpu_step(orc, prob, cores)
-    t = [cpu_step(orc, prob, cores) for _ in range(args.steps)]
+    log_w = args.log_w + int(math.log2(max(args.gpus, 1)))
+    if args.cpu_sample_log_w is not None:
+        log_w = min(log_w, args.cpu_sample_log_w)
+    t_setup = time.time()
+    wl, prob = oracle_bench_problem(orc, args.config, log_w)
+    t_setup = time.time() - t_setup
+    t, t0 = [], time.time()
+    while len(t) < max(args.steps, 1) and (not t or (time.time() - t0) + t[-1] / 1e3 < args.cpu_budget_s):
+        t.append(cpu_step(orc, prob, cores))
     ms = float(np.mean(t))
     value = prob["constraints"] / (ms / 1e3)
-    sample = f"W=2^{sample_log_w} slice of the W={wl['W']} workload (same ring, DP, kappa={wl['kappa']}); constraints/s = (W+2)/step time"
-    line = dict(metric="prover constraints/sec (commit+decomp+sumcheck)", value=value, unit="constraints/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64 (mod 2^64-2^32+1)", data="synthetic", impl="reference",
+    full = wl["W"] == synth.bench_workload(args.config, args.log_w + int(math.log2(max(args.gpus, 1))))["W"]
+    sample = (f"{len(t)} full-size step(s) at W=2^{log_w} ({'the same configuration as the product arm' if full else 'a slice of the product arm configuration'}; "
+              f"requested steps={args.steps}, warmup={args.warmup}; capped by a {args.cpu_budget_s:.0f} s budget; instance set-up {t_setup:.0f} s untimed)")
+    line = dict(metric=METRIC, value=value, unit="constraints/s", n_gpus=args.gpus, steps=len(t), warmup=0,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=DTYPE[args.config], data="synthetic", impl="reference",
+                requested=dict(steps=args.steps, warmup=args.warmup),
                 config=config_of(wl, args, "cpu"), cpu_baseline=dict(value=value, unit="constraints/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="constraints/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
 def config_of(wl, args, where):
-    return dict(workload=f"Goldilocks ring X^24-X^12+1, dummy R1CS ({wl['kind']} witness) with {wl['W']}+2 constraints, one NIFSProver::prove step "
-                         f"(BASELINE.json configs[1]; weak-scaled to W = gpus * 2^{args.log_w} when gpus > 1, as configs[3])", W=wl["W"], B=wl["B"], L=wl["L"], b=wl["b"], K=wl["K"], kappa=wl["kappa"], n=wl["W"] * wl["L"],
+    R = synth.RINGS[wl["ring"]]
+    circuit = "dummy R1CS" if wl["degree"] == 2 else "degree-three CCS (arith/ccs.rs:14-43)"
+    which = "configs[1]; weak-scaled to W = gpus * 2^%d when gpus > 1, as configs[3]" % args.log_w if wl["config"] == "c2" else "configs[2]"
+    return dict(workload=f"{R['name']} ring (d = {R['d']}), {circuit} ({wl['kind']} witness) with {wl['W']}+2 constraints, one NIFSProver::prove step "
+                         f"(BASELINE.json {which})", W=wl["W"], B=wl["B"], L=wl["L"], b=wl["b"], K=wl["K"], kappa=wl["kappa"], n=wl["W"] * wl["L"],
                 parallelism=("cpu threads" if where == "cpu" else ("1 GPU" if args.gpus == 1 else
                              f"{args.gpus} GPUs: witness columns / hypercube sharded, one all-reduce per commit batch, sumcheck round and evaluation")),
-                l2="inputs larger than L2: Ajtai matrix 1.3 GB + 2K witness pieces 1.6 GB per step vs 126 MB L2")
+                l2="inputs larger than L2: Ajtai matrix + 2K witness pieces per step are GBs vs 126 MB L2")
+
+
+def algorithmic_bytes(wl, ccs, world):
+    """SURVEY 8(d) per-unit figures in the REFERENCE layout (E bytes per ring element), summed over each kernel's launches in one
+    step, per rank.  These are the bytes the reference's data structures would move for the same work; kernels that read int8
+    digits or packed limbs move fewer real bytes, which is the point of those layouts."""
+    R = synth.RINGS[wl["ring"]]
+    E = R["d"] * 8
+    s, t, d_ccs = ccs["s"], ccs["t"], ccs["d"]
+    n, K, kappa, L = wl["W"] * wl["L"] // world, wl["K"], wl["kappa"], wl["L"]
+    m = (1 << s) // world
+    rows = wl["W"] + 2                                  # effective rows of every Mz table (the dummy circuits have W + 2 non-empty rows)
+    tau = R["tau"]
+    M_fold, M_lin = 5 + 2 * K * tau, t + 1
+    commit = 2 * (kappa * n + (K - 1) * n + (K - 1) * kappa) * E
+    return {
+        "k_commit_mma": commit, "k_dot_commit": commit,
+        # K9 with the fold fused into the next round's evaluation: round 1 reads M 2^s, round r >= 2 reads M 2^(s-r+2) and writes M 2^(s-r+1)
+        "k_fold_sc_round1": M_fold * m * E,
+        "k_fold_sc_round": M_fold * (3 * m // 2) * E,                       # sum over r >= 2 of (2^(s-r+2) + 2^(s-r+1)) ~ 3 * 2^(s-1)
+        "k_fold_sc_round2": M_fold * (m + m // 4) * E,
+        "k_sc_generic": M_lin * (m + 3 * m // 2) * E,
+        "k_fold": None, "k_fold_digits": M_fold * (m + m // 2) * E,
+        "k_matrix_apply": 2 * (2 * K + 1) * n * E,                           # CRT of the 2K pieces + ICRT of the folded witness
+        "k_gadget_recompose": (2 * K + 1) * (n + n // L) * E,
+        "k_digit_split": 2 * (n + K * n) * E,
+        "k_coeff_eval": (2 * K + 1 + 3) * n * E,                            # v_s of 2K pieces + v of the instance, each against one eq table
+        "k_dot_eval": (4 * K * t + t + 3) * rows * E,                       # u_s, eta (2K t rows each), u
+        "k_spmv": (2 * K + 1) * t * (rows * (E + 8) + 2 * rows * E),
+        "k_lincomb": (2 * K + 1) * n * E + 2 * (K * t + 1) * rows * E,       # f_0 over 2K pieces + the two zeta-Horner combinations
+        "k_digit_lincomb": 2 * (K * tau + 1) * n * E,
+        "k_eq_table": None, "k_eq_combine": 5 * m * E,
+    }
 
 
 def main():
@@ -138,15 +184,24 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--log-w", type=int, default=16, dest="log_w")
-    ap.add_argument("--cpu-sample-log-w", type=int, default=11, dest="cpu_sample_log_w")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "ntt"])
+    ap.add_argument("--log-w", type=int, default=None, dest="log_w")
+    ap.add_argument("--cpu-sample-log-w", type=int, default=None, dest="cpu_sample_log_w", help="reference arm: prove a smaller slice instead of the full W")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0, dest="cpu_budget_s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
+    if args.log_w is None:
+        args.log_w = {"c2": 16, "c3": 20, "ntt": 0}[args.config]
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.config == "ntt":
+        from tools import ntt_bench
+        return ntt_bench.main(args, rank, world, local)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
+    import hashlib
     import torch
     import torch.distributed as dist
     import latticefold_b200 as lf
@@ -164,13 +219,14 @@ def main():
     # Weak scaling: N GPUs prove ONE instance of N * 2^log_w constraints, witness columns / hypercube sharded over the
     # ranks with one small all-reduce per commit batch, sumcheck round and evaluation (BASELINE configs[3]).
     import math
-    wl = workload(args.log_w + int(math.log2(world)))
+    wl = workload(args.log_w + int(math.log2(world)), args.config)
+    RING = wl["ring"]
     assert world & (world - 1) == 0, "rank count must be a power of two"
     ctx = lf.Context(RING, local)
     if world > 1:
         ctx.set_shard(rank, world)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    prob = make_sharded_instance(wl, rank, world)
+    prob = synth.bench_instance(wl, rank, world, ops=ctx)
     pr = lf.NIFSProver(ctx, prob)                 # static inputs (Ajtai matrix slice, CCS) go to HBM once, outside the timed region
     W_loc = wl["W"] // world
     f = ctx.witness_f_from_w_ccs(RING, prob["w_ccs"][rank * W_loc:(rank + 1) * W_loc], wl["B"], wl["L"])     # elementwise: local slice
@@ -181,6 +237,7 @@ def main():
         return arr, t_
     keep = []
     f_pin, k_ = pinned_like(f); keep.append(k_)
+    del f
     prob["w_i_f"], prob["w_acc_f"] = f_pin, f_pin
     prob["cm_i_cm"] = np.ascontiguousarray(_commit_with_prover(ctx, pr, lf, prob, f_pin))
     lc, _ = pr.linearize(prob, lf.Transcript(RING))
@@ -188,10 +245,11 @@ def main():
     ccs = prob["ccs"]
     w_acc, w_i = pr.upload_witness(f_pin), pr.upload_witness(f_pin)
     out_proof, k1 = pinned_like(np.zeros(pr.proof_words, dtype=np.uint64)); out_lc, k2 = pinned_like(np.zeros(pr.lcccs_words, dtype=np.uint64))
-    out_f, k3 = pinned_like(np.zeros((pr.n, 24), dtype=np.uint64)); keep += [k1, k2, k3]
+    out_f, k3 = pinned_like(np.zeros((pr.n, synth.RINGS[RING]["d"]), dtype=np.uint64)); keep += [k1, k2, k3]
+    last = {}
 
     def step_resident():
-        return pr.prove_resident(prob, w_acc, w_i, lf.Transcript(RING))
+        last["resident"] = pr.prove_resident(prob, w_acc, w_i, lf.Transcript(RING))
 
     def step_e2e():
         return pr.prove(prob, lf.Transcript(RING), out=(out_proof, out_lc, out_f))
@@ -224,6 +282,46 @@ def main():
     value = constraints / (ms_res / 1e3)          # one sharded instance: its constraints are the whole job's
     e2e_value = constraints / (ms_e2e / 1e3)
 
+    # ---- checker, after the timed regions: the proof of the last timed step is (i) identical on every rank and
+    # to the proof the host-buffer entry point produced, (ii) accepted by the product's own NIFSVerifier and by the oracle's, and
+    # (iii) at sizes that have a committed golden digest (tests/golden/bench_digests.json: oracle outputs on the same instance),
+    # proof, folded LCCCS and folded witness hash to it.
+    verify = None
+    if not args.no_verify:
+        from tests import helpers
+        proof_res, lc_res = last["resident"]
+        dg = helpers.step_digests(out_proof, out_lc, out_f)
+        same_entry = bool(np.array_equal(proof_res, out_proof) and np.array_equal(lc_res, out_lc))
+        ranks_agree = True
+        if world > 1:
+            h8 = int.from_bytes(hashlib.sha256(np.ascontiguousarray(proof_res).tobytes() + np.ascontiguousarray(lc_res).tobytes()).digest()[:7], "little")
+            tmax = torch.tensor([h8], dtype=torch.int64, device="cuda"); tmin = tmax.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            ranks_agree = bool(tmax.item() == tmin.item())
+        verify = dict(proof_sha256=dg["proof"], lcccs_sha256=dg["lcccs"], entry_points_agree=same_entry, ranks_agree=ranks_agree)
+        if rank == 0:
+            try:
+                lc_v = lf.nifs_verify(prob, lf.Transcript(RING), proof_res)
+                verify["product_verifier"] = "accept" if np.array_equal(lc_v, lc_res) else "accept, but folded instance differs"
+            except lf.LfError as e:
+                verify["product_verifier"] = f"REJECT: {e}"
+            try:
+                from oracle.pyoracle import Oracle
+                orc_v = Oracle()
+                light = {k: v for k, v in prob.items() if k not in ("A", "w_i_f", "w_acc_f")}
+                lc_o = orc_v.nifs_verify(light, orc_v.transcript(RING), proof_res)
+                verify["oracle_verifier"] = "accept" if np.array_equal(lc_o, lc_res) else "accept, but folded instance differs"
+            except Exception as e:      # noqa: BLE001
+                verify["oracle_verifier"] = f"REJECT: {e}"
+            gold = helpers.bench_golden().get(helpers.bench_case_key(args.config, args.log_w)) if world == 1 and os.path.exists(helpers.BENCH_GOLDEN_PATH) else None
+            if gold is not None:
+                verify["golden"] = "match" if all(gold[k] == dg[k] for k in ("proof", "lcccs", "witness")) else "MISMATCH"
+                verify["witness_sha256"] = dg["witness"]
+            else:
+                verify["golden"] = "none committed for this size" if world == 1 else "n/a (sharded: verifier acceptance + rank agreement)"
+            verify["verified"] = bool(same_entry and ranks_agree and verify["product_verifier"] == "accept" and verify["oracle_verifier"] == "accept"
+                                      and verify["golden"] != "MISMATCH")
+
     # per-kernel device time of one extra step (events around every launch; not part of the timed region above)
     ctx.profile(True)
     step_resident()
@@ -232,55 +330,57 @@ def main():
     total_kernel_ms = sum(v[1] for v in prof.values())
     top = max(prof.items(), key=lambda kv: kv[1][1])
     hbm, peak_src = peaks()
-    s, t = ccs["s"], ccs["t"]
-    n, K, kappa = wl["W"] * wl["L"] // world, wl["K"], wl["kappa"]          # per rank
-    M_fold = 5 + 2 * K * 3
-    alg = {
-        # SURVEY 8(d) per-unit figures in the reference layout (E = 192 B), summed over that kernel's launches in one step
-        "k_dot_commit": 2 * (kappa * n + (K - 1) * n + (K - 1) * kappa) * E_BYTES,
-        "k_fold_sc_round": M_fold * (((1 << s) // world) - 2 + 2 * max(world - 1, 0)) * E_BYTES,              # rounds 2..s read M tables of length 2^(s-r+1)
-        "k_fold_sc_round1": M_fold * ((1 << s) // world) * E_BYTES,
-        "k_fold": None, "k_matrix_apply": 2 * (2 * K + 3) * n * E_BYTES,
-    }
-    # 64-bit multiply-accumulates per step of the two integer-bound kernels against the measured
+    alg = algorithmic_bytes(wl, ccs, world)
+    s, K, kappa = ccs["s"], wl["K"], wl["kappa"]
+    n = wl["W"] * wl["L"] // world
+    R = synth.RINGS[RING]
+    # 64-bit multiply-accumulates per step of the integer-bound sumcheck kernel against the measured
     # IMAD.WIDE-bound ceiling of tools/microbench/imad_peak.cu on B200: 1.785e12 lazily reduced MACs / s
     MAC_PEAK = 1.785e12
-    S_slots, tau = 8, 3
     pairs_r2 = max(((1 << s) // world) // 2 - 1, 0) + max(world - 1, 0)                # sum over rounds >= 2 of the pair count
-    macs = {"k_dot_commit": 2 * kappa * (K - 1) * n * S_slots * 9,
-            "k_fold_sc_round": pairs_r2 * S_slots * (2 * K * tau) * 66}       # two lanes x (mu*t 9 + t^2 6 + two MACs 18)
+    macs = {"k_fold_sc_round": pairs_r2 * R["S"] * (2 * K * R["tau"]) * 66} if RING == synth.RING_GOLDILOCKS else {}
     top_name, (top_cnt, top_ms) = top
     a_bytes = alg.get(top_name)
-    # DRAM bytes of this kernel from the committed `ncu --set full` capture (profiles/): largest launch (round 2 at C2) moved
-    # 2.545 GB read + 5 MB written for 2.54 GB algorithmic; the batched commit 2.10 GB for 2.06 GB algorithmic
-    ncu_traffic = {"k_fold_sc_round": 2.578e9, "k_dot_commit": 2.086e9}      # profiles/r01d_*: 2.544 GB + 34 MB; 2.073 GB + 13.5 MB
+    # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/): see profiles/README.md
+    ncu_traffic = NCU_TRAFFIC if (world == 1 and args.config == "c2" and args.log_w == 16) else {}
+    kernels = []
+    for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        if ms < 0.5 and name != top_name:
+            continue
+        b = alg.get(name)
+        kernels.append(dict(kernel=name, launches=cnt, total_ms=round(ms, 4), algorithmic_bytes=b,
+                            achieved_gbs=(b / 1e9) / (ms / 1e3) if b else None, frac=((b / 1e9) / (ms / 1e3) / hbm) if b else None,
+                            bound=KERNEL_BOUND.get(name, "hbm")))
     roofline = dict(bound="hbm", kernel=top_name, launches_per_step=top_cnt, avg_launch_ms=top_ms / top_cnt, share_of_kernel_time=top_ms / total_kernel_ms,
                     achieved=(a_bytes / 1e9) / (top_ms / 1e3) if a_bytes else None, peak=hbm, unit="GB/s",
                     frac=((a_bytes / 1e9) / (top_ms / 1e3) / hbm) if a_bytes else None,
-                    traffic=ncu_traffic.get(top_name) if (world == 1 and args.log_w == 16) else None,
-                    traffic_note="dram read+write of the largest launch of this kernel in profiles/ (ncu --set full); its algorithmic bytes are the same to 1%",
-                    peak_source=peak_src, algorithmic_bytes_per_step=a_bytes,
+                    traffic=ncu_traffic.get(top_name),
+                    traffic_note="dram read+write per launch of this kernel's largest launch in profiles/ (ncu --set full)",
+                    peak_source=peak_src, algorithmic_bytes_per_step=a_bytes, kernels=kernels,
                     int_pipe={k: dict(macs_per_step=v, achieved_mac_per_s=v / (prof[k][1] / 1e3), peak_mac_per_s=MAC_PEAK,
                                       frac=v / (prof[k][1] / 1e3) / MAC_PEAK) for k, v in macs.items() if k in prof and prof[k][1] > 0},
-                    note="this kernel is bound by the IMAD.WIDE issue rate (64-bit modular multiply-accumulates on 32-bit pipes), not by HBM: "
-                         "frac is the HBM fraction the contract asks for, int_pipe.frac the fraction of the measured multiply-accumulate ceiling")
-    line = dict(metric="prover constraints/sec (commit+decomp+sumcheck)", value=value, unit="constraints/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_res, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u64 (mod 2^64-2^32+1)", data="synthetic",
+                    note="achieved = algorithmic bytes in the reference layout (SURVEY 8d) / CUDA-event time of the kernel's launches in one step; "
+                         "kernels[] lists every kernel >= 0.5 ms per step with the same arithmetic and the resource that bounds it")
+    line = dict(metric=METRIC, value=value, unit="constraints/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_res, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=DTYPE[args.config], data="synthetic",
                 config=config_of(wl, args, "gpu"), clocks=clk.summary(), gpu_launches=int(launches), collectives_per_step=collectives,
                 e2e=dict(value=e2e_value, unit="constraints/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(2 * f_pin.nbytes),
                          d2h_bytes_per_step=int(out_proof.nbytes + out_lc.nbytes + out_f.nbytes)),
                 roofline=roofline, phases_ms=phases,
                 kernels_ms={k: dict(launches=v[0], total_ms=round(v[1], 4)) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])})
+    if verify is not None:
+        line["verified"] = verify.get("verified"); line["proof_sha256"] = verify["proof_sha256"]; line["verify"] = verify
     line["host"] = dict(poseidon=lf.Transcript(RING).backend(), cpus=os.cpu_count())   # dense-layer code path of the host transcript
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.pyoracle import Oracle
-        from tests.helpers import OracleOps
-        orc = Oracle(); cores = os.cpu_count() or 1
-        sl = min(args.log_w, args.cpu_sample_log_w)
-        sprob = synth.make_instance(RING, 1 << sl, wl["B"], wl["L"], wl["b"], wl["K"], wl["kappa"], kind=wl["kind"], config_id=2, ops=OracleOps(orc))
+        from tools.make_bench_golden import oracle_bench_problem
+        orc = Oracle(); cores = os.cpu_count() or 1; orc.set_threads(cores)
+        sl = min(args.log_w, {"c2": 12, "c3": 10}[args.config])
+        _, sprob = oracle_bench_problem(orc, args.config, sl)
         ms_cpu = cpu_step(orc, sprob, cores)
         line["cpu_baseline"] = dict(value=sprob["constraints"] / (ms_cpu / 1e3), unit="constraints/s", cores=cores, kind="port",
-                                    sample=f"one step at W=2^{sl} (same ring, DP, kappa) on {cores} host threads: {ms_cpu:.0f} ms")
+                                    sample=f"one step of the same workload at W=2^{sl} (same ring, DP, kappa, circuit) on {cores} host threads: {ms_cpu:.0f} ms; "
+                                           f"the full-size CPU run is `bench.py --impl reference`")
     if rank == 0:
         print(json.dumps(line), flush=True)
     pr.free_witness(w_acc); pr.free_witness(w_i); pr.close(); ctx.close()
@@ -288,17 +388,11 @@ def main():
         dist.destroy_process_group()
 
 
-def make_sharded_instance(wl, rank, world):
-    """Synthetic inputs of one step, holding only this rank's column slice of the Ajtai matrix (kappa x n/world independent
-    uniform ring elements, SplitMix64 seeded per rank) -- the full 8-GPU matrix would be 10.5 GB per process."""
-    R = synth.RINGS[RING]
-    seed = (synth.SEED_BASE + 100) & synth.MASK
-    n = wl["W"] * wl["L"]
-    w_ccs = synth.make_witness(RING, wl["W"], wl["kind"], seed)
-    ccs = synth.make_ccs(RING, wl["W"], wl["L"], wl["kind"], w_ccs, 1)
-    A = synth.uniform_field(R["p"], wl["kappa"] * (n // world) * R["d"], seed + 7919 * (rank + 1)).reshape(wl["kappa"], n // world, R["d"])
-    return dict(ring=RING, B=wl["B"], L=wl["L"], b=wl["b"], K=wl["K"], kappa=wl["kappa"], n=n, W=wl["W"], A=A, ccs=ccs, w_ccs=w_ccs,
-                cm_i_x_ccs=synth.one(RING, 1), constraints=1 + wl["W"] + 1, kind=wl["kind"])
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the round's `ncu --set full` captures (profiles/r02*_full.md)
+NCU_TRAFFIC = {"k_fold_sc_round": 2.578e9, "k_dot_commit": 2.086e9}
+# what bounds each kernel (ncu evidence in profiles/): "hbm" unless stated
+KERNEL_BOUND = {"k_fold_sc_round": "int-pipe (IMAD.WIDE / ALU)", "k_commit_mma": "hbm + L2 (tensor pipe idle-waiting on operand fill)", "k_dot_commit": "int-pipe (IMAD.WIDE)",
+                "k_sc_generic": "latency (host-paced rounds)", "k_fold_sc_round1": "int-pipe"}
 
 
 def _commit_with_prover(ctx, pr, lf, prob, f):

@@ -416,8 +416,17 @@ template <class Rg> struct Prover {
     // ------------------------------------------------------------------ NIFSProver::prove (nifs.rs:48-103)
     static void put(u64*& p, const HV& v) { std::memcpy(p, v.data(), 8 * v.size()); p += v.size(); }
     static void put_lcccs(u64* p, const LCCCS& L) { put(p, L.r); put(p, L.v); put(p, L.cm); put(p, L.u); put(p, L.x_w); put(p, L.h); }
+    static u64 proof_words_of(const lf_problem& P) {
+        const u64 d = D, tau = TAU;
+        return P.s * (P.d + 2) * d + tau * d + P.t * d + 2 * (u64)P.K * ((P.l + 1) + P.kappa + P.t + tau) * d + P.s * (2 * P.b + 1) * d + 2 * (u64)P.K * (tau + P.t) * d;
+    }
+    static HV load_canonical(const u64* p, size_t n, const char* what) {
+        if (!p && n) throw LfException(LF_ERR_INVALID_ARG, std::string(what) + " is NULL");
+        for (size_t i = 0; i < n * D; ++i) if (p[i] >= F::P) throw LfException(LF_ERR_INVALID_ARG, std::string("non-canonical field element in ") + what);
+        return HV(p, p + n * D);
+    }
     static LCCCS load_acc(const lf_problem& in, const lf_prover* P) {
-        LCCCS a; auto ld = [&](const u64* p, size_t n) { if (!p && n) throw LfException(LF_ERR_INVALID_ARG, "accumulator field is NULL"); return HV(p, p + n * D); };
+        LCCCS a; auto ld = [&](const u64* p, size_t n) { return load_canonical(p, n, "the accumulator"); };
         a.r = ld(in.acc_r, P->s); a.v = ld(in.acc_v, TAU); a.cm = ld(in.acc_cm, P->kappa); a.u = ld(in.acc_u, P->t); a.x_w = ld(in.acc_x_w, P->l); a.h = ld(in.acc_h, 1); return a;
     }
     lf_witness* prove(const lf_problem& in, const lf_witness* w_acc, const lf_witness* w_i, Transcript<Rg>& T, u64* out_proof, u64* out_lcccs, bool presynced = false) {
@@ -429,7 +438,7 @@ template <class Rg> struct Prover {
         sanity_check();
         const int K = P->K; const size_t n = nl();
         LCCCS acc = load_acc(in, P);
-        HV cm_i_cm(in.cm_i_cm, in.cm_i_cm + P->kappa * D), x_ccs(in.cm_i_x_ccs, in.cm_i_x_ccs + P->l * D);
+        HV cm_i_cm = load_canonical(in.cm_i_cm, P->kappa, "cm_i"), x_ccs = load_canonical(in.cm_i_x_ccs, P->l, "x_ccs");
         // Schedule: the accumulator's decomposition depends on nothing the transcript produces, so its device half is
         // queued first on the auxiliary stream and runs beside the (latency-bound, host-paced) linearization sumcheck.
         StepBuffers sb;

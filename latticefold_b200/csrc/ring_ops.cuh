@@ -79,10 +79,7 @@ template <class Rg> struct RingOpsImpl final : RingOps {
     void vec_free(lf_ctx* c, lf_vec* v) override { Engine<Rg> E(c); E.vec_free(v); }
     void sumcheck_free(lf_sumcheck* sc) override { SumcheckDriver<Rg> drv(sc->ctx, sc); drv.free_all(); delete sc; }
     void witness_free(lf_prover* p, lf_witness* w) override { Prover<Rg> pr(p); pr.free_witness(w); }
-    uint64_t proof_words(const lf_problem* P) override {
-        const u64 d = Rg::D, tau = Rg::TAU;
-        return P->s * (P->d + 2) * d + tau * d + P->t * d + 2 * (u64)P->K * ((P->l + 1) + P->kappa + P->t + tau) * d + P->s * (2 * P->b + 1) * d + 2 * (u64)P->K * (tau + P->t) * d;
-    }
+    uint64_t proof_words(const lf_problem* P) override { return Prover<Rg>::proof_words_of(*P); }
     uint64_t lcccs_words(const lf_problem* P) override { return (P->s + Rg::TAU + P->kappa + P->t + P->l + 1) * (u64)Rg::D; }
     void* tr_new() override { return new Transcript<Rg>(); }
     void* tr_clone(const void* t) override { return new Transcript<Rg>(*(const Transcript<Rg>*)t); }

@@ -153,7 +153,12 @@ template <class Rg> struct Verifier {
     LCCCS verify(const u64* proof, Transcript<Rg>& T) const {
         { size_t want = std::max((size_t)(in.n_ccs - in.l - 1) * (size_t)in.L, (size_t)in.m), p2 = 1; while (p2 < want) p2 <<= 1;      // nifs.rs:165-173
           if (in.m != p2 || ((u64)1 << in.s) != in.m) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "InvalidSizeBounds"); }
-        auto ld = [&](const u64* p, size_t n) { if (!p && n) throw LfException(LF_ERR_INVALID_ARG, "accumulator field is NULL"); return HV(p, p + n * D); };
+        // Every limb that crosses the boundary must be a canonical representative (< p): the reference's arkworks deserialisation
+        // rejects anything else, and a non-canonical limb would both make the proof malleable and overflow the lazily reduced host sums.
+        auto canonical = [](const u64* p, size_t limbs, const char* what) { for (size_t i = 0; i < limbs; ++i) if (p[i] >= F::P) throw LfException(LF_ERR_INVALID_ARG, std::string("non-canonical field element in ") + what); };
+        auto ld = [&](const u64* p, size_t n) { if (!p && n) throw LfException(LF_ERR_INVALID_ARG, "accumulator field is NULL"); canonical(p, n * D, "the public input"); return HV(p, p + n * D); };
+        canonical(proof, (size_t)Prover<Rg>::proof_words_of(in), "the proof");
+        for (size_t i = 0; i < in.q * (size_t)D; ++i) if (in.c[i] >= F::P) throw LfException(LF_ERR_INVALID_ARG, "non-canonical field element in the CCS constants");
         LCCCS acc; acc.r = ld(in.acc_r, in.s); acc.v = ld(in.acc_v, TAU); acc.cm = ld(in.acc_cm, in.kappa); acc.u = ld(in.acc_u, in.t); acc.x_w = ld(in.acc_x_w, in.l); acc.h = ld(in.acc_h, 1);
         HV cm_i = ld(in.cm_i_cm, in.kappa), x_ccs = ld(in.cm_i_x_ccs, in.l);
         T.absorb_tag("acc");                                                       // absorb_public_input, nifs.rs:175-197

@@ -175,6 +175,21 @@ def test_product_verifier_accepts_oracle_proofs_and_rejects_tampering(oracle, or
     prob2 = dict(prob); acc = dict(prob["acc"]); acc["v"] = acc["v"].copy(); acc["v"][0, 0] = (int(acc["v"][0, 0]) + 1) % p; prob2["acc"] = acc
     with pytest.raises(lf.LfError):
         lf.nifs_verify(prob2, lf.Transcript(ring), proof)
+    # non-canonical encodings (limb + k p, congruent to the honest value) are rejected like arkworks' deserialisation does:
+    # accepting them would make proofs malleable
+    for pos in (0, 7, proof.size // 4, proof.size // 2, proof.size - 1):
+        for k in (1, 2, 1024):
+            if int(proof[pos]) + k * p >= 1 << 64:
+                continue
+            bad = proof.copy(); bad[pos] = int(bad[pos]) + k * p
+            with pytest.raises(lf.LfError) as e:
+                lf.nifs_verify(prob, lf.Transcript(ring), bad)
+            assert e.value.code == -21, (pos, k)        # LF_ERR_INVALID_ARG
+    if int(prob["acc"]["u"][0, 0]) + p < 1 << 64:
+        prob3 = dict(prob); acc = dict(prob["acc"]); acc["u"] = acc["u"].copy(); acc["u"][0, 0] = int(acc["u"][0, 0]) + p; prob3["acc"] = acc
+        with pytest.raises(lf.LfError) as e:
+            lf.nifs_verify(prob3, lf.Transcript(ring), proof)
+        assert e.value.code == -21
 
 
 @pytest.mark.parametrize("ring", [synth.RING_GOLDILOCKS, synth.RING_BABYBEAR, synth.RING_FROG])

@@ -89,3 +89,15 @@ def test_step_digests_match_committed_golden(oracle, oracle_ops, case):
     prob = helpers.step_instance(case, oracle_ops)
     proof, lc, f, _ = oracle.nifs_prove(prob, oracle.transcript(case[0]))
     assert helpers.step_digests(proof, lc, f) == helpers.step_golden()[helpers.step_case_key(*case)]
+
+
+@pytest.mark.parametrize("config,log_w", [("c2", 10), ("c3", 8)])
+def test_bench_digests_match_committed_golden(oracle, config, log_w):
+    """the oracle on the instance bench.py proves (synth.bench_instance; small sizes here, the full sizes are regenerated by
+    tools/make_bench_golden.py) still hashes to tests/golden/bench_digests.json"""
+    from tools.make_bench_golden import oracle_bench_problem
+    wl, prob = oracle_bench_problem(oracle, config, log_w)
+    proof, lc, f, _ = oracle.nifs_prove(prob, oracle.transcript(wl["ring"]))
+    gold = helpers.bench_golden()[helpers.bench_case_key(config, log_w)]
+    got = helpers.step_digests(proof, lc, f)
+    assert all(got[k] == gold[k] for k in ("proof", "lcccs", "witness", "proof_words"))
