@@ -83,17 +83,25 @@ struct lf_ctx {
     struct ProfRec { const char* name; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
 };
-struct lf_vec { lf::u64* p = nullptr; size_t n = 0, pitch = 0; int form = 0; };
-struct lf_ajtai { lf::u64* p = nullptr; size_t kappa = 0, n = 0, pitch = 0;
+// Limb planes are arrays of the ring's word type (Rg::W: u64, or packed u32 for the 31-bit BabyBear prime).  The ring-independent
+// handle structs hold them behind an incomplete type, so that any pointer arithmetic outside the typed accessors (Engine::wp) is a
+// compile error rather than a wrong stride.
+struct lf_words;
+struct lf_vec { lf_words* p = nullptr; size_t n = 0, pitch = 0; int form = 0; };
+struct lf_ajtai { lf_words* p = nullptr; size_t kappa = 0, n = 0, pitch = 0;
                   // byte-limb tiles of the matrix for the tensor-core digit commit (commit_mma.cuh); absent on rings that do not use it
                   uint8_t* a8 = nullptr; int a8_tiles = 0, a8_chunks = 0; void* epi = nullptr; };
-struct lf_sparse { lf::u32 *row_ptr = nullptr, *col = nullptr; lf::u64* val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0, val_pitch = 0, eff_rows = 0; };
+struct lf_sparse { lf::u32 *row_ptr = nullptr, *col = nullptr; lf_words* val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0, val_pitch = 0, eff_rows = 0; };
 
 namespace lf {
 
 template <class Rg> struct Engine {
-    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef HostRing<Rg> HR; typedef typename HR::El El;
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef HostRing<Rg> HR; typedef typename HR::El El; typedef typename Rg::W W;
+    typedef PtrListT<W> PL;
     static constexpr int D = Rg::D, S = Rg::S, TAU = Rg::TAU, TPB_MA = matrix_apply_tpb<Rg>();
+    static W* wp(lf_words* p) { return reinterpret_cast<W*>(p); }
+    static const W* wp(const lf_words* p) { return reinterpret_cast<const W*>(p); }
+    static lf_words* ow(W* p) { return reinterpret_cast<lf_words*>(p); }
     lf_ctx* c;
     explicit Engine(lf_ctx* ctx) : c(ctx) {}
     const RingTables<Rg>& tab() const { return *(const RingTables<Rg>*)c->tables; }
@@ -112,7 +120,7 @@ template <class Rg> struct Engine {
         c->block_size[p] = bytes; return (T*)p;
     }
     void dfree(void* p) { if (!p) return; auto it = c->block_size.find(p); if (it == c->block_size.end()) return; c->block_cache.emplace(it->second, p); c->cached_bytes += it->second; }
-    lf_vec* vec_alloc(size_t n, int form) { lf_vec* v = new lf_vec; v->n = n; v->pitch = pitch_of(n); v->form = form; v->p = dalloc<u64>(v->pitch * D); return v; }
+    lf_vec* vec_alloc(size_t n, int form) { lf_vec* v = new lf_vec; v->n = n; v->pitch = pitch_of(n); v->form = form; v->p = ow(dalloc<W>(v->pitch * D)); return v; }
     void vec_free(lf_vec* v) { if (v) { dfree(v->p); delete v; } }
     u64* pinned(size_t words) {
         if (c->h_pinned_words < words) { if (c->h_pinned) { LF_CUDA(cudaStreamSynchronize(st())); cudaFreeHost(c->h_pinned); } size_t w = std::max(words, (size_t)1 << 16); LF_CUDA(cudaMallocHost(&c->h_pinned, w * 8)); c->h_pinned_words = w; }
@@ -166,10 +174,10 @@ template <class Rg> struct Engine {
                  throw LfException(code, msg); }
     }
     // host elements -> small SoA device vector, staged through the pinned arena (asynchronous)
-    void upload_small(const u64* host, size_t n, u64* dev, size_t pitch) {
-        u64* soa = (u64*)arena_alloc(pitch * D * 8); std::memset(soa, 0, pitch * D * 8);
-        for (size_t i = 0; i < n; ++i) for (int l = 0; l < D; ++l) soa[(size_t)l * pitch + i] = host[i * D + l];
-        LF_CUDA(cudaMemcpyAsync(dev, soa, pitch * D * 8, cudaMemcpyHostToDevice, st()));
+    void upload_small(const u64* host, size_t n, W* dev, size_t pitch) {
+        W* soa = (W*)arena_alloc(pitch * D * sizeof(W)); std::memset(soa, 0, pitch * D * sizeof(W));
+        for (size_t i = 0; i < n; ++i) for (int l = 0; l < D; ++l) soa[(size_t)l * pitch + i] = (W)host[i * D + l];
+        LF_CUDA(cudaMemcpyAsync(dev, soa, pitch * D * sizeof(W), cudaMemcpyHostToDevice, st()));
     }
     // download `words` u64 from the device into a host vector (through the pinned landing zone)
     void download_words(const u64* dev, size_t words, u64* host) {
@@ -233,42 +241,42 @@ template <class Rg> struct Engine {
     }
 
     // ---------------------------------------------------------------- layout
-    void upload_planes(const u64* host, size_t n, u64* dev, size_t pitch) {   // host AoS -> device planes
+    void upload_planes(const u64* host, size_t n, W* dev, size_t pitch) {   // host AoS (u64 limbs) -> device planes
         if (!n) return;
         u64* stage = dalloc<u64>(n * D);
         LF_CUDA(cudaMemcpyAsync(stage, host, n * D * 8, cudaMemcpyHostToDevice, st()));
-        launch("k_aos_to_soa", [&] { k_aos_to_soa<D><<<(unsigned)((n + 63) / 64), 256, 0, st()>>>(stage, dev, n, pitch); });
+        launch("k_aos_to_soa", [&] { k_aos_to_soa<D, W><<<(unsigned)((n + 63) / 64), 256, 0, st()>>>(stage, dev, n, pitch); });
         dfree(stage);
     }
-    void download_planes(const u64* dev, size_t pitch, size_t n, u64* host) {
+    void download_planes(const W* dev, size_t pitch, size_t n, u64* host) {
         if (!n) return;
         u64* stage = dalloc<u64>(n * D);
-        launch("k_soa_to_aos", [&] { k_soa_to_aos<D><<<(unsigned)((n + 63) / 64), 256, 0, st()>>>(dev, stage, n, pitch); });
+        launch("k_soa_to_aos", [&] { k_soa_to_aos<D, W><<<(unsigned)((n + 63) / 64), 256, 0, st()>>>(dev, stage, n, pitch); });
         LF_CUDA(cudaMemcpyAsync(host, stage, n * D * 8, cudaMemcpyDeviceToHost, st())); sync();
         dfree(stage);
     }
 
     // ---------------------------------------------------------------- elementwise ops
-    void crt(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, bool inverse) {
+    void crt(const W* in, size_t in_pitch, W* out, size_t out_pitch, size_t n, bool inverse) {
         if (!n) return;
-        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, u64><<<(unsigned)((n + TPB_MA - 1) / TPB_MA), TPB_MA, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[inverse], c->d_tab_val[inverse], 0, 0); });
+        launch("k_matrix_apply", [&] { k_matrix_apply<Rg, W><<<(unsigned)((n + TPB_MA - 1) / TPB_MA), TPB_MA, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[inverse], c->d_tab_val[inverse], 0, 0); });
     }
     // CRT of `batch` digit vectors (in/out strides between consecutive vectors) in one launch
-    void crt_digits(const int8_t* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, int batch = 1, size_t in_stride = 0, size_t out_stride = 0) {
+    void crt_digits(const int8_t* in, size_t in_pitch, W* out, size_t out_pitch, size_t n, int batch = 1, size_t in_stride = 0, size_t out_stride = 0) {
         if (!n || !batch) return;
         launch("k_matrix_apply", [&] { k_matrix_apply<Rg, int8_t><<<dim3((unsigned)((n + TPB_MA - 1) / TPB_MA), batch), TPB_MA, 0, st()>>>(in, in_pitch, out, out_pitch, n, c->d_tab_idx[0], c->d_tab_val[0], in_stride, out_stride); });
     }
     static unsigned blocks_for(size_t work, int bs = 256) { return (unsigned)((work + bs - 1) / bs); }
-    void gadget_decompose(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n, u64 B, int L) {
+    void gadget_decompose(const W* in, size_t in_pitch, W* out, size_t out_pitch, size_t n, u64 B, int L) {
         if (B < 2 || B >= ((u64)1 << 62) || L < 1 || L > 64) throw LfException(LF_ERR_UNSUPPORTED, "gadget_decompose: need 2 <= B < 2^62, 1 <= L <= 64");
         if (!n) return;
         launch("k_gadget_decompose", [&] { k_gadget_decompose<Rg><<<blocks_for(n * D), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n, (int64_t)B, L, c->d_err); });
     }
-    void gadget_recompose(const u64* in, size_t in_pitch, u64* out, size_t out_pitch, size_t n_out, u64 B, int L, int batch = 1, size_t in_stride = 0, size_t out_stride = 0) {
+    void gadget_recompose(const W* in, size_t in_pitch, W* out, size_t out_pitch, size_t n_out, u64 B, int L, int batch = 1, size_t in_stride = 0, size_t out_stride = 0) {
         if (!n_out || !batch) return;
         launch("k_gadget_recompose", [&] { k_gadget_recompose<Rg><<<dim3(blocks_for(n_out * D), batch), 256, 0, st()>>>(in, in_pitch, out, out_pitch, n_out, B % F::P, L, in_stride, out_stride); });
     }
-    void digit_split(const u64* in, size_t in_pitch, int8_t* out, size_t out_pitch, size_t n, u64 b, int K) {
+    void digit_split(const W* in, size_t in_pitch, int8_t* out, size_t out_pitch, size_t n, u64 b, int K) {
         if (b < 2 || b > 254 || K < 1 || K > 64) throw LfException(LF_ERR_UNSUPPORTED, "decompose_to_vec: need 2 <= b <= 254 (int8 digits), 1 <= K <= 64");
         if (!n) return;
         if (b == 2 && out_pitch % 4 == 0 && out_pitch >= (n + 3) / 4 * 4)      // the 4-byte stores of the last group stay inside the plane's padding
@@ -278,11 +286,11 @@ template <class Rg> struct Engine {
 
     // ---------------------------------------------------------------- batched dot products (commit, MLE evaluation)
     // result: nrows x ncols x D limbs on the device (d_out)
-    void dot(const u64* X, size_t x_row_stride, size_t x_pitch, int nrows, const size_t* x_len_dev,
-             const PtrList& Y, size_t y_pitch, int ncols, size_t n, u64* d_out, const char* name = "k_dot") {
+    void dot(const W* X, size_t x_row_stride, size_t x_pitch, int nrows, const size_t* x_len_dev,
+             const PL& Y, size_t y_pitch, int ncols, size_t n, u64* d_out, const char* name = "k_dot") {
         if (nrows == 0 || ncols == 0) return;
         if (ncols > MAX_LIST) throw LfException(LF_ERR_INVALID_ARG, "dot: too many columns in one launch");
-        DotArgs a; a.X = X; a.x_row_stride = x_row_stride; a.x_pitch = x_pitch; a.nrows = nrows; a.Y = Y; a.y_pitch = y_pitch; a.ncols = ncols;
+        DotArgsT<W> a; a.X = X; a.x_row_stride = x_row_stride; a.x_pitch = x_pitch; a.nrows = nrows; a.Y = Y; a.y_pitch = y_pitch; a.ncols = ncols;
         a.x_len = x_len_dev; a.n = n;
         // x tile: long enough to amortise the per-warp reduction, short enough to fill 148 SMs
         // measured on B200 (tools/dot_ab.py, kappa=26, n=2^18, 15 pieces): CT=2 with 4-8 warps per block runs at 87% of the
@@ -318,7 +326,7 @@ template <class Rg> struct Engine {
             const int g_total = (int)(S * TAU * A->kappa), ntiles = (g_total + cmma::GROUPS - 1) / cmma::GROUPS, nchunks = (int)((A->n + cmma::J - 1) / cmma::J);
             LF_CUDA(cudaMalloc(&A->a8, (size_t)ntiles * nchunks * cmma::A_STAGE_BYTES));
             const size_t work = (size_t)ntiles * cmma::GROUPS * nchunks * (cmma::J / 16);
-            launch("k_a8_tile", [&] { cmma::k_a8_tile<Rg><<<blocks_for(work), 256, 0, st()>>>(A->p, A->pitch * D, A->pitch, A->n, (int)A->kappa, g_total, nchunks, (size_t)ntiles * cmma::GROUPS, A->a8); });
+            launch("k_a8_tile", [&] { cmma::k_a8_tile<Rg><<<blocks_for(work), 256, 0, st()>>>(wp(A->p), A->pitch * D, A->pitch, A->n, (int)A->kappa, g_total, nchunks, (size_t)ntiles * cmma::GROUPS, A->a8); });
             cmma::EpiTables<Rg> t; const RingTables<Rg>& rt = tab();
             for (int s = 0; s < S; ++s) {
                 for (int r = 0; r < TAU; ++r) { t.perm[s][r] = (rt.k[s] * r) % TAU; t.corr[s][r] = 0; }
@@ -341,9 +349,11 @@ template <class Rg> struct Engine {
             int8_t* d8 = dalloc<int8_t>(d_stage * nchunks);
             launch("k_d8_tile", [&] { cmma::k_d8_tile<Rg><<<blocks_for((size_t)ncols * D * (cmma::J / 16) * nchunks), 256, 0, st()>>>(dig, dig_pitch, dig_stride, ncols, nchunks, d8); });
             // split the witness axis so that the grid fills whole waves of 148 SMs (one CTA per SM: 512 TMEM columns each)
-            int best = 1; double best_eff = 0;
-            for (int sp = 1; sp <= 64 && sp <= nchunks; ++sp) { const int ctas = ntiles * sp, waves = (ctas + 147) / 148; const double eff = (double)ctas / (148.0 * waves);
-                if (nchunks / sp < 8 && sp > 1) break; if (eff > best_eff + 1e-9 || (eff > best_eff - 0.02 && sp > best && waves <= 8)) { best_eff = std::max(best_eff, eff); best = sp; } }
+            // (every CTA pays a fixed prologue + epilogue, so among the well-filled grids the one with the fewest splits wins: score = wave
+            // efficiency minus 1 % per split; measured at C2: 11 splits 0.50 ms, 15 0.54 ms, 27 0.60 ms, 53 0.71 ms per batch)
+            int best = 1; double best_score = -1;
+            for (int sp = 1; sp <= 64 && sp <= nchunks; ++sp) { const int ctas = ntiles * sp, waves = (ctas + 147) / 148; const double score = (double)ctas / (148.0 * waves) - 0.01 * sp;
+                if (score > best_score) { best_score = score; best = sp; } }
             if (const char* e = std::getenv("LF_COMMIT_SPLITS")) { int v = atoi(e); if (v >= 1 && v <= nchunks) best = v; }
             const int nsplits = best, cps = (nchunks + nsplits - 1) / nsplits, nsp = (nchunks + cps - 1) / cps;
             const int npad = (ncols + 1) / 2 * 2, ntot = D * npad;
@@ -358,7 +368,7 @@ template <class Rg> struct Engine {
         } else throw LfException(LF_ERR_UNSUPPORTED, "tensor-core commit is built for the Goldilocks ring");
     }
     // f-hat evaluation from coefficient planes; result nvec x TAU x D limbs on the device
-    template <class TIn> void coeff_eval(const TIn* coeff, size_t c_pitch, size_t c_vec_stride, int nvec, const u64* eq, size_t eq_pitch, size_t n, u64* d_out) {
+    template <class TIn> void coeff_eval(const TIn* coeff, size_t c_pitch, size_t c_vec_stride, int nvec, const W* eq, size_t eq_pitch, size_t n, u64* d_out) {
         if (!nvec) return;
         const int xpb = 128 * 8; const unsigned xt = (unsigned)std::max<size_t>(1, (n + xpb - 1) / xpb);
         const size_t nout = (size_t)nvec * TAU * D;
@@ -366,14 +376,14 @@ template <class Rg> struct Engine {
         launch("k_coeff_eval", [&] { k_coeff_eval<Rg, TIn><<<dim3(xt, S, nvec), 128, 0, st()>>>(coeff, c_pitch, c_vec_stride, eq, eq_pitch, n, xpb, nvec, partial); });
         reduce_partials_allreduce(partial, (int)xt, nout, d_out);
     }
-    void spmv(const lf_sparse* M, const u64* head, size_t head_len, size_t head_pitch, const u64* tail, size_t tail_pitch, u64* out, size_t out_pitch, size_t nrows,
+    void spmv(const lf_sparse* M, const W* head, size_t head_len, size_t head_pitch, const W* tail, size_t tail_pitch, W* out, size_t out_pitch, size_t nrows,
               size_t tail_chunk = ~(size_t)0, size_t tail_chunk_stride = 0, int batch = 1, size_t head_batch_stride = 0, size_t tail_batch_stride = 0, size_t out_batch_stride = 0) {
         if (!nrows || !batch) return;
-        launch("k_spmv", [&] { k_spmv<Rg><<<dim3(blocks_for(nrows, 128), S, batch), 128, 0, st()>>>(M->row_ptr, M->col, M->val, M->val_pitch, head, head_len, head_pitch, tail, tail_pitch, tail_chunk, tail_chunk_stride, out, out_pitch, nrows, head_batch_stride, tail_batch_stride, out_batch_stride); });
+        launch("k_spmv", [&] { k_spmv<Rg><<<dim3(blocks_for(nrows, 128), S, batch), 128, 0, st()>>>(M->row_ptr, M->col, wp(M->val), M->val_pitch, head, head_len, head_pitch, tail, tail_pitch, tail_chunk, tail_chunk_stride, out, out_pitch, nrows, head_batch_stride, tail_batch_stride, out_batch_stride); });
     }
     // eq(., r) for r given as s ring elements on the host
     // x_offset / n_local: the slab [x_offset, x_offset + n_local) of the table (hypercube sharding); default = whole table
-    void eq_table(const u64* r_host, int s, u64* out, size_t out_pitch, size_t x_offset = 0, size_t n_local = 0) {
+    void eq_table(const u64* r_host, int s, W* out, size_t out_pitch, size_t x_offset = 0, size_t n_local = 0) {
         if (s < 1 || s > 40) throw LfException(LF_ERR_INVALID_ARG, "eq_table: r length is 0 or too large");
         std::vector<u64> pair((size_t)s * 2 * D);
         El one = HR::from_u64(1);
@@ -385,7 +395,7 @@ template <class Rg> struct Engine {
             launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(n, 128), S), 128, (size_t)s * 2 * TAU * 8, st()>>>(d_pair, s, out, out_pitch, n, x_offset); });
         } else {      // two half tables, then one multiply per entry
             const int h = s / 2; const size_t nlo = (size_t)1 << h, nhi = (size_t)1 << (s - h), plo = pitch_of(nlo), phi = pitch_of(nhi);
-            u64 *lo = dalloc<u64>(plo * D), *hi = dalloc<u64>(phi * D);
+            W *lo = dalloc<W>(plo * D), *hi = dalloc<W>(phi * D);
             launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(nlo, 128), S), 128, (size_t)h * 2 * TAU * 8, st()>>>(d_pair, h, lo, plo, nlo, 0); });
             launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(nhi, 128), S), 128, (size_t)(s - h) * 2 * TAU * 8, st()>>>(d_pair + (size_t)h * 2 * D, s - h, hi, phi, nhi, 0); });
             launch("k_eq_combine", [&] { k_eq_combine<Rg><<<dim3(blocks_for(n, 128), S), 128, 0, st()>>>(lo, plo, hi, phi, h, out, out_pitch, n, x_offset); });
@@ -394,11 +404,11 @@ template <class Rg> struct Engine {
         dfree(d_pair);
     }
     // out (+)= sum_i coef_i (.) vecs_i ; coef on the host (count x D)
-    void lincomb(const PtrList& vecs, size_t v_pitch, int count, const u64* coef_host, u64* out, size_t out_pitch, size_t n, bool accumulate) {
+    void lincomb(const PL& vecs, size_t v_pitch, int count, const u64* coef_host, W* out, size_t out_pitch, size_t n, bool accumulate) {
         int done = 0;
         while (done < count || (count == 0 && !accumulate && done == 0)) {
             const int chunk = std::min(MAX_LIST, count - done);
-            PtrList pl; for (int i = 0; i < chunk; ++i) { pl.p[i] = vecs.p[done + i]; pl.len[i] = vecs.len[done + i]; }
+            PL pl; for (int i = 0; i < chunk; ++i) { pl.p[i] = vecs.p[done + i]; pl.len[i] = vecs.len[done + i]; }
             u64* d_coef = dalloc<u64>((size_t)std::max(chunk, 1) * D);
             if (chunk) h2d(d_coef, coef_host + (size_t)done * D, (size_t)chunk * D * 8);
             launch("k_lincomb", [&] { k_lincomb<Rg><<<dim3(blocks_for(n, 128), S), 128, 0, st()>>>(pl, v_pitch, chunk, d_coef, out, out_pitch, n, (accumulate || done > 0) ? 1 : 0); });

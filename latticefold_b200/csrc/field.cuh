@@ -309,20 +309,20 @@ typedef ModField<15912092521325583641ULL, 2755067726615789629ULL, false> FrogFie
 // ---------------------------------------------------------------------------------------------------------------
 // Ring descriptor: slot field Fq[Y]/(Y^TAU - nu).  Rg::F is the base field.
 struct GoldilocksRing {
-    typedef Goldilocks F;
+    typedef Goldilocks F; typedef u64 W;      // W: word type of one limb in device planes
     static constexpr int ID = 0, D = 24, S = 8, TAU = 3, G = 24;
     static constexpr bool TRINOMIAL = true;   // X^24 = X^12 - 1
     static constexpr int CS_BYTES = 18;
 };
 
 struct BabyBearRing {      // Z_p[X]/(X^72 - X^36 + 1), 8 slots of Fq9   (crates/cyclotomic-rings/src/rings/babybear.rs:9-20)
-    typedef BabyBear F;
+    typedef BabyBear F; typedef u32 W;        // 31-bit prime: limb planes are packed 4-byte words (288 B per ring element)
     static constexpr int ID = 1, D = 72, S = 8, TAU = 9, G = 24;
     static constexpr bool TRINOMIAL = true;
     static constexpr int CS_BYTES = 18;
 };
 struct FrogRing {          // Z_p[X]/(X^16 + 1), 4 slots of Fq4           (crates/cyclotomic-rings/src/rings/frog.rs:9-20)
-    typedef FrogField F;
+    typedef FrogField F; typedef u64 W;
     static constexpr int ID = 2, D = 16, S = 4, TAU = 4, G = 8;
     static constexpr bool TRINOMIAL = false;
     static constexpr int CS_BYTES = 16;

@@ -15,8 +15,18 @@ constexpr int MAX_LIST = 32;          // pointer-list capacity of one launch (pi
 constexpr int MAX_MU = 320;           // 2K * tau (K = 16 on the BabyBear ring: 288)
 constexpr int SC_MAX_MLES = 8, SC_MAX_TERMS = 4, SC_MAX_FACTORS = 4, SC_MAX_DEG = 7;
 
-struct PtrList { const u64* p[MAX_LIST]; size_t len[MAX_LIST]; };
+template <class W> struct PtrListT { const W* p[MAX_LIST]; size_t len[MAX_LIST]; };
+typedef PtrListT<u64> PtrList;
 struct PtrList8 { const int8_t* p[MAX_LIST]; };
+
+// Limb planes hold words of type Rg::W (u64, or packed u32 for the 31-bit ring); arithmetic is on u64 values.
+// Two / four consecutive words with one vector load (index even / multiple of four: planes are 128-byte aligned).
+__device__ __forceinline__ void ld_pair(const u64* p, u64& a, u64& b) { const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p); a = v.x; b = v.y; }
+__device__ __forceinline__ void ld_pair(const u32* p, u64& a, u64& b) { const uint2 v = *reinterpret_cast<const uint2*>(p); a = v.x; b = v.y; }
+__device__ __forceinline__ void ldg_pair(const u64* p, u64& a, u64& b) { const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p)); a = v.x; b = v.y; }
+__device__ __forceinline__ void ldg_pair(const u32* p, u64& a, u64& b) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(p)); a = v.x; b = v.y; }
+__device__ __forceinline__ void ldg_quad(const u64* p, u64* o) { const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(p)), b = __ldg(reinterpret_cast<const ulonglong2*>(p) + 1); o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; }
+__device__ __forceinline__ void ldg_quad(const u32* p, u64* o) { const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)); o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; }
 
 // ------------------------------------------------------------------------------------------------ reductions
 // sum over the block of NV field elements per thread; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
@@ -129,21 +139,21 @@ k_reduce_allreduce_p2p(const u64* __restrict__ partial, int nblk, int nout, u64*
 }
 
 // entry 0 of every (table, plane) -> column `rank` of a zeroed [rows][pitch_out] buffer (all-gather by summation)
-template <int = 0> __global__ void k_scatter_entry(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t rows, int rank) {
+template <class W> __global__ void k_scatter_entry(const W* __restrict__ in, size_t in_pitch, W* __restrict__ out, size_t out_pitch, size_t rows, int rank) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows) out[i * out_pitch + rank] = in[i * in_pitch];
 }
 
 // ------------------------------------------------------------------------------------------------ layout changes
 // host "Vec<R>" image (element-major) <-> limb planes.  64 elements per block through shared memory so both sides coalesce.
-template <int D> __global__ void k_aos_to_soa(const u64* __restrict__ aos, u64* __restrict__ soa, size_t n, size_t pitch) {
+template <int D, class W> __global__ void k_aos_to_soa(const u64* __restrict__ aos, W* __restrict__ soa, size_t n, size_t pitch) {
     __shared__ u64 tile[64][D + 1];
     size_t base = (size_t)blockIdx.x * 64; int cnt = (int)min((size_t)64, n - base);
     for (int i = threadIdx.x; i < cnt * D; i += blockDim.x) tile[i / D][i % D] = aos[base * D + i];
     __syncthreads();
-    for (int i = threadIdx.x; i < 64 * D; i += blockDim.x) { int l = i / 64, e = i % 64; if (e < cnt) soa[(size_t)l * pitch + base + e] = tile[e][l]; }
+    for (int i = threadIdx.x; i < 64 * D; i += blockDim.x) { int l = i / 64, e = i % 64; if (e < cnt) soa[(size_t)l * pitch + base + e] = (W)tile[e][l]; }
 }
-template <int D> __global__ void k_soa_to_aos(const u64* __restrict__ soa, u64* __restrict__ aos, size_t n, size_t pitch) {
+template <int D, class W> __global__ void k_soa_to_aos(const W* __restrict__ soa, u64* __restrict__ aos, size_t n, size_t pitch) {
     __shared__ u64 tile[64][D + 1];
     size_t base = (size_t)blockIdx.x * 64; int cnt = (int)min((size_t)64, n - base);
     for (int i = threadIdx.x; i < 64 * D; i += blockDim.x) { int l = i / 64, e = i % 64; if (e < cnt) tile[e][l] = soa[(size_t)l * pitch + base + e]; }
@@ -157,7 +167,7 @@ template <int D> __global__ void k_soa_to_aos(const u64* __restrict__ soa, u64* 
 // dynamically.  tab_idx/tab_val: D rows x NNZ entries.  TIn = u64 (field elements) or int8_t (balanced digits).
 template <class Rg> constexpr int matrix_apply_tpb() { return Rg::D > 32 ? 64 : 128; }      // [D][tpb] u64 staging must fit 48 KB
 template <class Rg, class TIn> __global__ void __launch_bounds__(128)
-k_matrix_apply(const TIn* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t n,
+k_matrix_apply(const TIn* __restrict__ in, size_t in_pitch, typename Rg::W* __restrict__ out, size_t out_pitch, size_t n,
                const int* __restrict__ tab_idx, const u64* __restrict__ tab_val, size_t in_batch_stride, size_t out_batch_stride) {
     typedef typename Rg::F F; constexpr int D = Rg::D, NNZ = Rg::S;
     in += (size_t)blockIdx.y * in_batch_stride; out += (size_t)blockIdx.y * out_batch_stride;      // blockIdx.y = vector of a batch
@@ -189,13 +199,13 @@ k_matrix_apply(const TIn* __restrict__ in, size_t in_pitch, u64* __restrict__ ou
             if (DIGITS) a.mac_small((u32)s_in[s_idx[r * NNZ + c]][threadIdx.x], s_val[r * NNZ + c]);
             else a.mac(s_val[r * NNZ + c], s_in[s_idx[r * NNZ + c]][threadIdx.x]);
         }
-        out[(size_t)r * out_pitch + e] = DIGITS ? F::sub(F::reduce(a), s_corr[r]) : F::reduce(a);
+        out[(size_t)r * out_pitch + e] = (typename Rg::W)(DIGITS ? F::sub(F::reduce(a), s_corr[r]) : F::reduce(a));
     }
 }
 
 // ------------------------------------------------------------------------------------------------ K4/K5 digits
 // gadget_decompose(B, L) (arith.rs:235): coefficient c of element i -> digits l = 0..L-1 at element i*L + l.
-template <class Rg> __global__ void k_gadget_decompose(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch,
+template <class Rg> __global__ void k_gadget_decompose(const typename Rg::W* __restrict__ in, size_t in_pitch, typename Rg::W* __restrict__ out, size_t out_pitch,
                                                        size_t n, int64_t B, int L, int* __restrict__ err) {
     typedef typename Rg::F F;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,10 +213,10 @@ template <class Rg> __global__ void k_gadget_decompose(const u64* __restrict__ i
     size_t i = t % n; int c = (int)(t / n);
     int64_t dg[64];
     if (!balanced_digits(F::to_signed(in[(size_t)c * in_pitch + i]), B, L, dg)) atomicExch(err, 1);
-    for (int l = 0; l < L; ++l) out[(size_t)c * out_pitch + i * L + l] = F::from_i64(dg[l]);
+    for (int l = 0; l < L; ++l) out[(size_t)c * out_pitch + i * L + l] = (typename Rg::W)F::from_i64(dg[l]);
 }
 // decompose_to_vec(b, K).transpose() (decomposition/utils.rs:45-49) into K int8 digit planes sets: out[k][c][i]
-template <class Rg> __global__ void k_digit_split(const u64* __restrict__ in, size_t in_pitch, int8_t* __restrict__ out, size_t out_pitch,
+template <class Rg> __global__ void k_digit_split(const typename Rg::W* __restrict__ in, size_t in_pitch, int8_t* __restrict__ out, size_t out_pitch,
                                                   size_t n, int64_t b, int K, int* __restrict__ err) {
     typedef typename Rg::F F;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,7 +228,7 @@ template <class Rg> __global__ void k_digit_split(const u64* __restrict__ in, si
 }
 // b = 2 (every reference parameter set of the 64/31-bit rings): the balanced digits of v are sign(v) times the bits of |v| -- no
 // divisions, no digit array.  Four consecutive elements per thread, one 4-byte store per digit plane; grid.y = coefficient plane.
-template <class Rg> __global__ void __launch_bounds__(256) k_digit_split_b2(const u64* __restrict__ in, size_t in_pitch, int8_t* __restrict__ out, size_t out_pitch,
+template <class Rg> __global__ void __launch_bounds__(256) k_digit_split_b2(const typename Rg::W* __restrict__ in, size_t in_pitch, int8_t* __restrict__ out, size_t out_pitch,
                                                                            size_t n, int K, int* __restrict__ err) {
     typedef typename Rg::F F;
     const size_t i = 4 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); const int c = blockIdx.y;
@@ -238,14 +248,14 @@ template <class Rg> __global__ void __launch_bounds__(256) k_digit_split_b2(cons
         *reinterpret_cast<char4*>(out + ((size_t)k * Rg::D + c) * out_pitch + i) = d;
     }
 }
-template <class Rg> __global__ void k_digits_to_field(const int8_t* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t n) {
+template <class Rg> __global__ void k_digits_to_field(const int8_t* __restrict__ in, size_t in_pitch, typename Rg::W* __restrict__ out, size_t out_pitch, size_t n) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * Rg::D) return;
     size_t i = t % n; int c = (int)(t / n);
-    out[(size_t)c * out_pitch + i] = Rg::F::from_i64((int64_t)in[(size_t)c * in_pitch + i]);
+    out[(size_t)c * out_pitch + i] = (typename Rg::W)Rg::F::from_i64((int64_t)in[(size_t)c * in_pitch + i]);
 }
 // gadget_recompose(B, L): out[i] = sum_l in[i*L + l] * B^l, limb-wise (B is an integer scalar; arith.rs:305,330)
-template <class Rg> __global__ void k_gadget_recompose(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch,
+template <class Rg> __global__ void k_gadget_recompose(const typename Rg::W* __restrict__ in, size_t in_pitch, typename Rg::W* __restrict__ out, size_t out_pitch,
                                                        size_t n_out, u64 Bmod, int L, size_t in_batch_stride, size_t out_batch_stride) {
     typedef typename Rg::F F;
     in += (size_t)blockIdx.y * in_batch_stride; out += (size_t)blockIdx.y * out_batch_stride;
@@ -254,10 +264,10 @@ template <class Rg> __global__ void k_gadget_recompose(const u64* __restrict__ i
     size_t i = t % n_out; int c = (int)(t / n_out);
     u64 acc = 0, pw = 1;
     for (int l = 0; l < L; ++l) { acc = F::add(acc, F::mul(in[(size_t)c * in_pitch + i * L + l], pw)); pw = F::mul(pw, Bmod); }
-    out[(size_t)c * out_pitch + i] = acc;
+    out[(size_t)c * out_pitch + i] = (typename Rg::W)acc;
 }
 // get_fhat (arith.rs:273-297): MLE j, slot k, limb 0 = coefficient j*S + k; other limbs 0.  `in` points at plane j*S.
-template <class Rg> __global__ void k_fhat(const u64* __restrict__ in, size_t in_pitch, u64* __restrict__ out, size_t out_pitch, size_t n) {
+template <class Rg> __global__ void k_fhat(const typename Rg::W* __restrict__ in, size_t in_pitch, typename Rg::W* __restrict__ out, size_t out_pitch, size_t n) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * Rg::S) return;
     size_t i = t % n; int k = (int)(t / n);
@@ -275,16 +285,16 @@ template <class Rg> __global__ void k_fhat(const u64* __restrict__ in, size_t in
 // x tile are adjacent in launch order, which keeps HBM traffic at one pass over X and Y (ncu: 2.1 GB for the 2.06 GB
 // algorithmic at kappa=26, n=2^18, 15 pieces).  Accumulators are lazily reduced (F::Acc): the inner loop is
 // 9 * CT 64-bit multiply-accumulates per x with no modular reduction and no branch.
-struct DotArgs {
-    const u64* X; size_t x_row_stride, x_pitch; int nrows;    // rows: X + r * x_row_stride
-    PtrList Y; size_t y_pitch; int ncols;                     // columns: separate vectors, len[] = effective length
+template <class W> struct DotArgsT {
+    const W* X; size_t x_row_stride, x_pitch; int nrows;      // rows: X + r * x_row_stride
+    PtrListT<W> Y; size_t y_pitch; int ncols;                 // columns: separate vectors, len[] = effective length
     const size_t* x_len;                                      // optional per-row effective length (device), else n
     size_t n; int x_per_block;
     u64* partial;                                             // [x tile][row][col][D]
 };
 template <class Rg, int CT, int MAXT> __global__ void __launch_bounds__(MAXT)
-k_dot(const DotArgs a) {
-    typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+k_dot(const DotArgsT<typename Rg::W> a) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef typename Rg::W W; constexpr int TAU = Rg::TAU;
     const int col_tiles = (a.ncols + CT - 1) / CT, n_units = a.nrows * col_tiles;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const int unit = blockIdx.x * wpb + warp, slot = blockIdx.z;
@@ -292,8 +302,8 @@ k_dot(const DotArgs a) {
     const int row = unit / col_tiles, c0 = (unit % col_tiles) * CT;
     const size_t x_begin = (size_t)blockIdx.y * a.x_per_block, x_stop = min(a.n, x_begin + a.x_per_block);
     const size_t rlen = a.x_len ? a.x_len[row] : a.n;
-    const u64* xp = a.X + (size_t)row * a.x_row_stride + (size_t)(slot * TAU) * a.x_pitch;
-    const u64* yp[CT]; size_t ylen[CT];
+    const W* xp = a.X + (size_t)row * a.x_row_stride + (size_t)(slot * TAU) * a.x_pitch;
+    const W* yp[CT]; size_t ylen[CT];
 #pragma unroll
     for (int j = 0; j < CT; ++j) { const int c = min(c0 + j, a.ncols - 1); yp[j] = a.Y.p[c] + (size_t)(slot * TAU) * a.y_pitch; ylen[j] = (c0 + j < a.ncols) ? a.Y.len[c] : 0; }
     constexpr int NA = SF::NDOT;
@@ -352,7 +362,7 @@ k_dot(const DotArgs a) {
 // (compute_v_s, decomposition.rs:204-211; linearization.rs:126-131).  TIn = int8_t (digit pieces) or u64 (field coefficients).
 // grid = (x tiles, slots, vectors); partial: [x tile][vector][tau_j][D]
 template <class Rg, class TIn> __global__ void __launch_bounds__(128)
-k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride, const u64* __restrict__ eq, size_t eq_pitch,
+k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride, const typename Rg::W* __restrict__ eq, size_t eq_pitch,
              size_t n, int x_per_block, int nvec, u64* __restrict__ partial) {
     typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
     __shared__ u64 red[TAU * TAU * 32];
@@ -376,9 +386,7 @@ k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride,
             u64 e[TAU][4];
 #pragma unroll
             for (int l = 0; l < TAU; ++l) {
-                const ulonglong2* ep = reinterpret_cast<const ulonglong2*>(eq + (size_t)(slot * TAU + l) * eq_pitch + x);
-                const ulonglong2 p0 = __ldg(ep), p1 = __ldg(ep + 1);
-                e[l][0] = p0.x; e[l][1] = p0.y; e[l][2] = p1.x; e[l][3] = p1.y;
+                ldg_quad(eq + (size_t)(slot * TAU + l) * eq_pitch + x, e[l]);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) se[l].add(e[l][q]);
             }
@@ -435,10 +443,10 @@ k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride,
 // ------------------------------------------------------------------------------------------------ K7 sparse mat-vec
 // mat_vec_mul (arith/utils.rs:52-65): out[row] = sum (val, col) val (.) z[col].  thread = (row, slot).  z may be the
 // concatenation z = head || tail (x_s[k] || w_ccs_k, decomposition.rs:238-246) without materialising it.
-template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, const u32* __restrict__ col, const u64* __restrict__ val, size_t val_pitch,
-                                           const u64* __restrict__ z_head, size_t head_len, size_t head_pitch,
-                                           const u64* __restrict__ z_tail, size_t tail_pitch, size_t tail_chunk, size_t tail_chunk_stride,
-                                           u64* __restrict__ out, size_t out_pitch, size_t nrows,
+template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, const u32* __restrict__ col, const typename Rg::W* __restrict__ val, size_t val_pitch,
+                                           const typename Rg::W* __restrict__ z_head, size_t head_len, size_t head_pitch,
+                                           const typename Rg::W* __restrict__ z_tail, size_t tail_pitch, size_t tail_chunk, size_t tail_chunk_stride,
+                                           typename Rg::W* __restrict__ out, size_t out_pitch, size_t nrows,
                                            size_t head_batch_stride, size_t tail_batch_stride, size_t out_batch_stride) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
@@ -462,7 +470,7 @@ template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, cons
         SF::mac(acc, v, SF::prep(z));
     }
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + row] = F::reduce(acc[l]);
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + row] = (typename Rg::W)F::reduce(acc[l]);
 }
 
 // ------------------------------------------------------------------------------------------------ K8 eq table
@@ -470,7 +478,7 @@ template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, cons
 // r_pair: s x 2 x D limbs on the device = (1 - r_i, r_i) per variable.  thread = (x, slot).
 // The table is built as lo(x mod 2^h) * hi(x div 2^h) from two half tables held in shared memory would save multiplies;
 // at s <= 24 the direct product is s-1 slot-field multiplies per entry and is not on the critical path.
-template <class Rg> __global__ void k_eq_table(const u64* __restrict__ r_pair, int s, u64* __restrict__ out, size_t out_pitch, size_t n, size_t x_offset) {
+template <class Rg> __global__ void k_eq_table(const u64* __restrict__ r_pair, int s, typename Rg::W* __restrict__ out, size_t out_pitch, size_t n, size_t x_offset) {
     typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU, D = Rg::D;
     extern __shared__ u64 s_r[];   // s * 2 * TAU for this slot
     const int slot = blockIdx.y;
@@ -484,12 +492,12 @@ template <class Rg> __global__ void k_eq_table(const u64* __restrict__ r_pair, i
     for (int l = 0; l < TAU; ++l) acc[l] = s_r[((x & 1) ? TAU : 0) + l];
     for (int v = 1; v < s; ++v) SF::mul(acc, acc, &s_r[(v * 2 + ((x >> v) & 1)) * TAU]);
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + xl] = acc[l];
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + xl] = (typename Rg::W)acc[l];
 }
 
 // eq[x] = lo[x mod 2^h] * hi[x div 2^h]: the table over s variables from two half tables (one multiply per entry instead of s-1)
-template <class Rg> __global__ void k_eq_combine(const u64* __restrict__ lo, size_t lo_pitch, const u64* __restrict__ hi, size_t hi_pitch, int h,
-                                                 u64* __restrict__ out, size_t out_pitch, size_t n, size_t x_offset) {
+template <class Rg> __global__ void k_eq_combine(const typename Rg::W* __restrict__ lo, size_t lo_pitch, const typename Rg::W* __restrict__ hi, size_t hi_pitch, int h,
+                                                 typename Rg::W* __restrict__ out, size_t out_pitch, size_t n, size_t x_offset) {
     typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     const size_t xl = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
     if (xl >= n) return;
@@ -499,14 +507,14 @@ template <class Rg> __global__ void k_eq_combine(const u64* __restrict__ lo, siz
     for (int l = 0; l < TAU; ++l) { a[l] = __ldg(lo + (size_t)(slot * TAU + l) * lo_pitch + xlo); b[l] = __ldg(hi + (size_t)(slot * TAU + l) * hi_pitch + xhi); }
     SF::mul(a, a, b);
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + xl] = a[l];
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + xl] = (typename Rg::W)a[l];
 }
 
 // ------------------------------------------------------------------------------------------------ K11 linear combinations
 // out[x] (+)= sum_i c_i (.) v_i[x]   (compute_f_0 folding.rs:258-268; zeta-Horner combination of Mz MLEs folding.rs:208-226)
 // coef: count x D limbs on the device.  thread = (x, slot).
-template <class Rg> __global__ void k_lincomb(const PtrList vecs, size_t v_pitch, int count, const u64* __restrict__ coef,
-                                              u64* __restrict__ out, size_t out_pitch, size_t n, int accumulate) {
+template <class Rg> __global__ void k_lincomb(const PtrListT<typename Rg::W> vecs, size_t v_pitch, int count, const u64* __restrict__ coef,
+                                              typename Rg::W* __restrict__ out, size_t out_pitch, size_t n, int accumulate) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU, D = Rg::D;
     __shared__ typename SF::Prepped s_c[MAX_LIST];
     const int slot = blockIdx.y;
@@ -525,12 +533,12 @@ template <class Rg> __global__ void k_lincomb(const PtrList vecs, size_t v_pitch
         SF::mac(acc, v, s_c[i]);
     }
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = F::reduce(acc[l]);
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = (typename Rg::W)F::reduce(acc[l]);
 }
 // out[x][slot] (+)= sum_k sum_j w[k][j] * digit_k[x][j*S + slot]     (prepare_g1_and_3_k_mles_list, folding/utils.rs:524-546:
 // the alpha-Horner combination of the f-hat MLEs, computed from the int8 digits).  w: K x TAU slot-field elements.
 template <class Rg> __global__ void k_digit_lincomb(const int8_t* __restrict__ dig, size_t d_pitch, size_t d_vec_stride, int K,
-                                                    const u64* __restrict__ w, u64* __restrict__ out, size_t out_pitch, size_t n, int accumulate) {
+                                                    const u64* __restrict__ w, typename Rg::W* __restrict__ out, size_t out_pitch, size_t n, int accumulate) {
     typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
     __shared__ u64 s_w[MAX_MU * TAU];
     for (int i = threadIdx.x; i < K * TAU * TAU; i += blockDim.x) s_w[i] = w[i];
@@ -548,37 +556,37 @@ template <class Rg> __global__ void k_digit_lincomb(const int8_t* __restrict__ d
             for (int l = 0; l < TAU; ++l) acc[l].mac(c, s_w[(k * TAU + j) * TAU + l]);
         }
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = F::reduce(acc[l]);
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + x] = (typename Rg::W)F::reduce(acc[l]);
 }
 
 // ------------------------------------------------------------------------------------------------ K9 sumcheck
 // fix_variables on a list of tables (sumcheck/prover.rs:61-72): new[b] = old[2b] + r (old[2b+1] - old[2b]).
 // in/out may alias only through separate buffers (ping-pong).  r_sf: TAU limbs (slot-constant challenge).
 // grid = (b tiles, slots, tables)
-struct FoldArgs { const u64* in; u64* out; size_t in_pitch, out_pitch, in_stride, out_stride; size_t n_out; u64 r[16]; };      // r: TAU limbs of the challenge (TAU <= 9)
-template <class Rg> __global__ void k_fold(const FoldArgs a) {
-    typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+template <class W> struct FoldArgsT { const W* in; W* out; size_t in_pitch, out_pitch, in_stride, out_stride; size_t n_out; u64 r[16]; };      // r: TAU limbs of the challenge (TAU <= 9)
+template <class Rg> __global__ void k_fold(const FoldArgsT<typename Rg::W> a) {
+    typedef SlotField<Rg> SF; typedef typename Rg::W W; constexpr int TAU = Rg::TAU;
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
     if (b >= a.n_out) return;
-    const u64* in = a.in + (size_t)blockIdx.z * a.in_stride; u64* out = a.out + (size_t)blockIdx.z * a.out_stride;
+    const W* in = a.in + (size_t)blockIdx.z * a.in_stride; W* out = a.out + (size_t)blockIdx.z * a.out_stride;
     u64 f0[TAU], f1[TAU], t[TAU];
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) { const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(in + (size_t)(slot * TAU + l) * a.in_pitch + 2 * b); f0[l] = p.x; f1[l] = p.y; }
+    for (int l = 0; l < TAU; ++l) ld_pair(in + (size_t)(slot * TAU + l) * a.in_pitch + 2 * b, f0[l], f1[l]);
     SF::sub(t, f1, f0); SF::mul(t, t, a.r); SF::add(t, t, f0);
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * a.out_pitch + b] = t[l];
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * a.out_pitch + b] = (W)t[l];
 }
 
 // generic round evaluation for PRODUCTS / LIN combination functions (prove_round, sumcheck/prover.rs:111-143):
 // evals[e] = sum_b comb(v_k(2b) + e (v_k(2b+1) - v_k(2b))), e = 0..deg.   thread = (b, slot); partial: [b tile][deg+1][D]
-struct ScGenericArgs {
-    const u64* mle[SC_MAX_MLES]; size_t pitch; int n_mles, deg, n_terms, lin;
+template <class W> struct ScGenericArgsT {
+    const W* mle[SC_MAX_MLES]; size_t pitch; int n_mles, deg, n_terms, lin;
     int term_len[SC_MAX_TERMS]; int term_idx[SC_MAX_TERMS][SC_MAX_FACTORS];
     const u64* coef;           // n_terms x D on the device
     size_t n_pairs; u64* partial;
 };
 template <class Rg, int NM> __global__ void __launch_bounds__(128)
-k_sc_generic(const ScGenericArgs a) {
+k_sc_generic(const ScGenericArgsT<typename Rg::W> a) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     __shared__ u64 red[(SC_MAX_DEG + 1) * TAU * 32];
     const int slot = blockIdx.y;
@@ -598,8 +606,8 @@ k_sc_generic(const ScGenericArgs a) {
         for (int k = 0; k < NM; ++k)
 #pragma unroll
             for (int l = 0; l < TAU; ++l) {
-                const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(a.mle[k] + (size_t)(slot * TAU + l) * a.pitch + 2 * b);
-                val[k][l] = p.x; step[k][l] = F::sub(p.y, p.x);
+                u64 p1; ld_pair(a.mle[k] + (size_t)(slot * TAU + l) * a.pitch + 2 * b, val[k][l], p1);
+                step[k][l] = F::sub(p1, val[k][l]);
             }
 #pragma unroll
         for (int e = 0; e <= SC_MAX_DEG; ++e) {
@@ -655,17 +663,17 @@ k_sc_generic(const ScGenericArgs a) {
 //   g(x) = v0 v1 + v2 v3 + v4 * h(x),   h = sum_{k<2K} sum_{d<tau} mu_k^{d+1} (f_{k,d}^3 - f_{k,d})
 // h is a cubic along the line through a pair, so 4 points determine it; the degree-4 message needs 5 points of g.
 // "dense" = the five tables [eq(r_acc), G_acc, eq(r_new), G_new, eq(beta)].
-struct FoldScArgs {
-    const u64* dense; size_t dense_pitch, dense_stride;     // 5 tables
+template <class W> struct FoldScArgsT {
+    const W* dense; size_t dense_pitch, dense_stride;       // 5 tables
     const u64* mu_pow;                                      // n_f x TAU limbs: mu_k^{d+1} (slot-constant)
     int n_f;                                                // 2K * tau
     size_t n_pairs; u64* partial;                           // [b tile][5][D]
     // round 1: int8 digits, piece k at dig + k * dig_stride, coefficient plane c at c * dig_pitch
     const int8_t* dig; size_t dig_pitch, dig_stride;
     // rounds >= 2: slot-field tables, f-hat (k,d) at fh + (k*tau+d) * fh_stride
-    const u64* fh; size_t fh_pitch, fh_stride;
+    const W* fh; size_t fh_pitch, fh_stride;
 };
-template <class Rg, bool WITH_PRODUCTS = true> __device__ __forceinline__ void fold_sc_tail(const FoldScArgs& a, size_t b, bool active, int slot, const u64 (*h)[Rg::TAU] /* h(0..4) */, u64* red, size_t partial_block = ~(size_t)0, bool rt_products = true) {
+template <class Rg, bool WITH_PRODUCTS = true> __device__ __forceinline__ void fold_sc_tail(const FoldScArgsT<typename Rg::W>& a, size_t b, bool active, int slot, const u64 (*h)[Rg::TAU] /* h(0..4) */, u64* red, size_t partial_block = ~(size_t)0, bool rt_products = true) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     u64 ev[5][TAU];
 #pragma unroll
@@ -679,8 +687,8 @@ template <class Rg, bool WITH_PRODUCTS = true> __device__ __forceinline__ void f
             if (!WITH_PRODUCTS && k < 4) continue;
 #pragma unroll
             for (int l = 0; l < TAU; ++l) {
-                const ulonglong2 p = *reinterpret_cast<const ulonglong2*>(a.dense + (size_t)k * a.dense_stride + (size_t)(slot * TAU + l) * a.dense_pitch + 2 * b);
-                val[k][l] = p.x; step[k][l] = F::sub(p.y, p.x);
+                u64 p1; ld_pair(a.dense + (size_t)k * a.dense_stride + (size_t)(slot * TAU + l) * a.dense_pitch + 2 * b, val[k][l], p1);
+                step[k][l] = F::sub(p1, val[k][l]);
             }
         }
 #pragma unroll
@@ -710,7 +718,7 @@ template <class Rg, bool WITH_PRODUCTS = true> __device__ __forceinline__ void f
 // round 1: every f-hat entry is a balanced digit in {-1,0,1} embedded in the base field (arith.rs:283-289), so
 // f^3 - f vanishes at X = 0, 1 and is a small integer at X = 2, 3; h(4) follows from the cubic's finite differences.
 template <class Rg> __global__ void __launch_bounds__(128)
-k_fold_sc_round1(const FoldScArgs a) {
+k_fold_sc_round1(const FoldScArgsT<typename Rg::W> a) {
     typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
     __shared__ u64 red[5 * TAU * 32];
     __shared__ u64 s_mu[MAX_MU * TAU];
@@ -755,16 +763,16 @@ k_fold_sc_round1(const FoldScArgs a) {
 }
 // after the first challenge r: f-hat tables become slot-field valued: new[b] = d0 + r (d1 - d0)
 template <class Rg> __global__ void k_fold_digits(const int8_t* __restrict__ dig, size_t dig_pitch, size_t dig_stride, int n_f,
-                                                  u64* __restrict__ out, size_t out_pitch, size_t out_stride, size_t n_out, const FoldArgs r) {
+                                                  typename Rg::W* __restrict__ out, size_t out_pitch, size_t out_stride, size_t n_out, const FoldArgsT<typename Rg::W> r) {
     typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
     const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y, kd = blockIdx.z;
     if (b >= n_out) return;
     const int k = kd / TAU, d = kd % TAU;
     const char2 dd = *reinterpret_cast<const char2*>(dig + (size_t)k * dig_stride + (size_t)(d * S + slot) * dig_pitch + 2 * b);
     const u64 st = F::from_i64((int64_t)dd.y - dd.x), d0 = F::from_i64((int64_t)dd.x);
-    u64* o = out + (size_t)kd * out_stride;
+    typename Rg::W* o = out + (size_t)kd * out_stride;
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) { u64 v = F::mul(st, r.r[l]); if (l == 0) v = F::add(v, d0); o[(size_t)(slot * TAU + l) * out_pitch + b] = v; }
+    for (int l = 0; l < TAU; ++l) { u64 v = F::mul(st, r.r[l]); if (l == 0) v = F::add(v, d0); o[(size_t)(slot * TAU + l) * out_pitch + b] = (typename Rg::W)v; }
 }
 // rounds >= 2.  Along the pair's line f(X) = u + X s:
 //   f^3 - f = (u^3 - u) + 3X u^2 s + 3X^2 u s^2 + X^3 (s^3 - s) + (X^3 - X) s,
@@ -781,7 +789,7 @@ template <class Rg> __global__ void k_fold_digits(const int8_t* __restrict__ dig
 // 128 registers (4 blocks of 128 threads per SM) with the table loop not unrolled measured best: 152 registers / 3 blocks 8.3 ms,
 // 96 registers / 5 blocks 7.9 ms, this 7.8 ms.
 template <class Rg> __global__ void __launch_bounds__(128, 4)
-k_fold_sc_round(const FoldScArgs a) {
+k_fold_sc_round(const FoldScArgsT<typename Rg::W> a) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     __shared__ u64 red[5 * TAU * 32];
     // mu and its nu-multiples, prepared once per block where that fits the static shared-memory budget (5 words per table on the
@@ -809,8 +817,8 @@ k_fold_sc_round(const FoldScArgs a) {
             u64 t[TAU], mine[TAU], other[TAU], q[TAU];
 #pragma unroll
             for (int l = 0; l < TAU; ++l) {
-                const ulonglong2 p = __ldg(reinterpret_cast<const ulonglong2*>(a.fh + (size_t)kd * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b));
-                const u64 sl = F::sub(p.y, p.x); t[l] = role ? sl : p.x;
+                u64 p0, p1; ldg_pair(a.fh + (size_t)kd * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b, p0, p1);
+                const u64 sl = F::sub(p1, p0); t[l] = role ? sl : p0;
             }
             if constexpr (PREP_SMEM) SF::mul_prepped(mine, t, s_mu[kd]); else SF::mul_prepped(mine, t, SF::prep(&s_mu[kd * TAU]));
 #pragma unroll

@@ -12,7 +12,7 @@
 #pragma once
 #include "sumcheck.cuh"
 
-struct lf_witness { lf::u64 *f = nullptr, *f_coeff = nullptr, *w_ccs = nullptr; size_t n = 0, pitch = 0, W = 0, w_pitch = 0; };
+struct lf_witness { lf_words *f = nullptr, *f_coeff = nullptr, *w_ccs = nullptr; size_t n = 0, pitch = 0, W = 0, w_pitch = 0; };
 
 struct lf_prover {
     lf_ctx* ctx = nullptr;
@@ -34,8 +34,12 @@ namespace lf {
 struct LCCCS { HV r, v, cm, u, x_w, h; };
 
 template <class Rg> struct Prover {
-    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef HostRing<Rg> HR; typedef typename HR::El El;
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef HostRing<Rg> HR; typedef typename HR::El El; typedef typename Rg::W W;
+    typedef PtrListT<W> PL;
     static constexpr int D = Rg::D, S = Rg::S, TAU = Rg::TAU;
+    static W* wp(lf_words* p) { return reinterpret_cast<W*>(p); }
+    static const W* wp(const lf_words* p) { return reinterpret_cast<const W*>(p); }
+    static lf_words* ow(W* p) { return reinterpret_cast<lf_words*>(p); }
     lf_prover* P; Engine<Rg> E; HR H;
     explicit Prover(lf_prover* p) : P(p), E(p->ctx), H(E.tab()) {}
     // diagnostic phase marks (LF_TIMING_DETAIL=1): synchronise and record the time since the previous mark
@@ -61,32 +65,32 @@ template <class Rg> struct Prover {
     }
 
     // ------------------------------------------------------------------ witnesses (arith.rs:299-313, Witness::from_f)
-    lf_witness* witness_from_f_device(u64* f_dev /* takes ownership, pitch = pitch_of(n) */) {
-        lf_witness* w = new lf_witness; w->n = nl(); w->pitch = pitch_of(nl()); w->f = f_dev;
+    lf_witness* witness_from_f_device(W* f_dev /* takes ownership, pitch = pitch_of(n) */) {
+        lf_witness* w = new lf_witness; w->n = nl(); w->pitch = pitch_of(nl()); w->f = ow(f_dev);
         if (P->n % (P->L * (size_t)world())) throw LfException(LF_ERR_INCORRECT_LENGTH, "witness length is not a multiple of L (times the rank count)");
         w->W = Wl(); w->w_pitch = pitch_of(w->W);
-        w->f_coeff = E.template dalloc<u64>(w->pitch * D); E.crt(w->f, w->pitch, w->f_coeff, w->pitch, w->n, true);
-        w->w_ccs = E.template dalloc<u64>(w->w_pitch * D); E.gadget_recompose(w->f, w->pitch, w->w_ccs, w->w_pitch, w->W, P->B, P->L);
+        w->f_coeff = ow(E.template dalloc<W>(w->pitch * D)); E.crt(wp(w->f), w->pitch, wp(w->f_coeff), w->pitch, w->n, true);
+        w->w_ccs = ow(E.template dalloc<W>(w->w_pitch * D)); E.gadget_recompose(wp(w->f), w->pitch, wp(w->w_ccs), w->w_pitch, w->W, P->B, P->L);
         return w;
     }
     lf_witness* upload_witness(const u64* f_host) {
-        u64* f = E.template dalloc<u64>(pitch_of(nl()) * D); E.upload_planes(f_host, nl(), f, pitch_of(nl()));   // this rank's slice
+        W* f = E.template dalloc<W>(pitch_of(nl()) * D); E.upload_planes(f_host, nl(), f, pitch_of(nl()));   // this rank's slice
         return witness_from_f_device(f);
     }
     void free_witness(lf_witness* w) { if (!w) return; E.dfree(w->f); E.dfree(w->f_coeff); E.dfree(w->w_ccs); delete w; }
 
     // ------------------------------------------------------------------ shared device helpers
-    struct DevVec { u64* p = nullptr; size_t n = 0, pitch = 0; };
+    struct DevVec { W* p = nullptr; size_t n = 0, pitch = 0; };
     DevVec eq_table(const HV& r) {      // this rank's slab of eq(., r)
-        DevVec v; v.n = ((size_t)1 << cnt(r)) / world(); v.pitch = pitch_of(v.n); v.p = E.template dalloc<u64>(v.pitch * D);
+        DevVec v; v.n = ((size_t)1 << cnt(r)) / world(); v.pitch = pitch_of(v.n); v.p = E.template dalloc<W>(v.pitch * D);
         E.eq_table(r.data(), (int)cnt(r), v.p, v.pitch, (size_t)rank() * v.n, v.n); return v;
     }
     // Mz tables for a list of z = head_k || tail_k; out: [count * t] rows of pitch mz_pitch, effective length eff[j]
-    struct MzSet { u64* p = nullptr; size_t pitch = 0, stride = 0; int rows = 0; size_t* d_len = nullptr; std::vector<size_t> len; };
+    struct MzSet { W* p = nullptr; size_t pitch = 0, stride = 0; int rows = 0; size_t* d_len = nullptr; std::vector<size_t> len; };
     // upload = false: the caller copies the length table itself, on the stream that will read it (upload_mz_len)
     MzSet alloc_mz(int count, bool upload = true) {
         MzSet z; z.rows = count * (int)P->t; size_t mx = 1; for (auto* M : P->M) mx = std::max(mx, M->eff_rows);
-        z.pitch = pitch_of(mx); z.stride = z.pitch * D; z.p = E.template dalloc<u64>((size_t)z.rows * z.stride);
+        z.pitch = pitch_of(mx); z.stride = z.pitch * D; z.p = E.template dalloc<W>((size_t)z.rows * z.stride);
         z.len.resize(z.rows); for (int i = 0; i < z.rows; ++i) z.len[i] = P->M[i % P->t]->eff_rows;
         z.d_len = E.template dalloc<size_t>(z.rows);
         if (upload) upload_mz_len(z);
@@ -96,9 +100,9 @@ template <class Rg> struct Prover {
     void free_mz(MzSet& z) { E.dfree(z.p); E.dfree(z.d_len); z.p = nullptr; }
     // z = head || tail where the tail (w_ccs) is, when sharded, the all-gathered concatenation of the ranks' slabs:
     // chunk r (tail_chunk elements) at tail + r * tail_chunk_stride.  Rows of M are this rank's slab.
-    void compute_mz(MzSet& z, int k, const HV& head, const u64* tail, size_t tail_pitch, size_t tail_len, size_t tail_chunk = ~(size_t)0, size_t tail_chunk_stride = 0) {   // mat_vec_mul x t (arith/utils.rs:52-65)
+    void compute_mz(MzSet& z, int k, const HV& head, const W* tail, size_t tail_pitch, size_t tail_len, size_t tail_chunk = ~(size_t)0, size_t tail_chunk_stride = 0) {   // mat_vec_mul x t (arith/utils.rs:52-65)
         const size_t hl = cnt(head), hp = pitch_of(hl);
-        u64* d_head = E.template dalloc<u64>(hp * D); E.upload_small(head.data(), hl, d_head, hp);
+        W* d_head = E.template dalloc<W>(hp * D); E.upload_small(head.data(), hl, d_head, hp);
         for (size_t j = 0; j < P->t; ++j) {
             if (P->M[j]->ncols != hl + tail_len) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "LengthsNotEqual(M, z)");
             E.spmv(P->M[j], d_head, hl, hp, tail, tail_pitch, z.p + ((size_t)k * P->t + j) * z.stride, z.pitch, P->M[j]->eff_rows, tail_chunk, tail_chunk_stride);
@@ -106,9 +110,9 @@ template <class Rg> struct Prover {
         E.dfree(d_head);
     }
     // the K pieces of one decomposition against every CCS matrix: t launches (blockIdx.z = piece) instead of K * t
-    void compute_mz_batch(MzSet& z, int k0, int K, const std::vector<HV>& heads, const u64* tail, size_t tail_pitch, size_t tail_piece_stride, size_t tail_len, size_t tail_chunk, size_t tail_chunk_stride) {
+    void compute_mz_batch(MzSet& z, int k0, int K, const std::vector<HV>& heads, const W* tail, size_t tail_pitch, size_t tail_piece_stride, size_t tail_len, size_t tail_chunk, size_t tail_chunk_stride) {
         const size_t hl = cnt(heads[0]), hp = pitch_of(hl);
-        u64* d_heads = E.template dalloc<u64>((size_t)K * hp * D);
+        W* d_heads = E.template dalloc<W>((size_t)K * hp * D);
         for (int k = 0; k < K; ++k) { if (cnt(heads[k]) != hl) throw LfException(LF_ERR_INCORRECT_LENGTH, "IncorrectLength"); E.upload_small(heads[k].data(), hl, d_heads + (size_t)k * hp * D, hp); }
         for (size_t j = 0; j < P->t; ++j) {
             if (P->M[j]->ncols != hl + tail_len) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "LengthsNotEqual(M, z)");
@@ -118,16 +122,16 @@ template <class Rg> struct Prover {
         E.dfree(d_heads);
     }
     // all-gather `count` consecutive per-piece w_ccs slabs (each wc_stride words) of every rank: returns [world][count][D][pitch]
-    u64* gather_wccs(const u64* local, size_t words) {
-        if (world() == 1) return const_cast<u64*>(local);
-        u64* all = E.template dalloc<u64>(words * world());
-        LF_CUDA(cudaMemcpyAsync(all + (size_t)rank() * words, local, words * 8, cudaMemcpyDeviceToDevice, E.st()));
-        E.collective(1, all, words);
+    W* gather_wccs(const W* local, size_t words) {      // words of type W; the collective moves them as u64 lanes (pitches are multiples of 32 words)
+        if (world() == 1) return const_cast<W*>(local);
+        W* all = E.template dalloc<W>(words * world());
+        LF_CUDA(cudaMemcpyAsync(all + (size_t)rank() * words, local, words * sizeof(W), cudaMemcpyDeviceToDevice, E.st()));
+        E.collective(1, reinterpret_cast<u64*>(all), words * sizeof(W) / 8);
         return all;
     }
     // evaluate every Mz row at the point whose eq table is given -> rows x D limbs (host)
     const u64* eval_mz_async(const MzSet& z, int row0, int rows, const DevVec& eq) {      // pinned result, valid after the next sync / event
-        PtrList Y; Y.p[0] = eq.p; Y.len[0] = eq.n;
+        PL Y; Y.p[0] = eq.p; Y.len[0] = eq.n;
         u64* d_out = E.template dalloc<u64>((size_t)rows * D);
         E.dot(z.p + (size_t)row0 * z.stride, z.stride, z.pitch, rows, z.d_len + row0, Y, eq.pitch, 1, z.pitch, d_out, "k_dot_eval");
         const u64* land = E.d2h_async(d_out, (size_t)rows * D); E.dfree(d_out); return land;
@@ -140,14 +144,14 @@ template <class Rg> struct Prover {
     struct LinOut { LCCCS lc; HV msgs; DevVec eq_r; };
     // pre_tail: the all-gathered w_ccs slabs when the caller has already queued that collective (the sharded step issues it before
     // the accumulator's decomposition so that NCCL's cross-stream ordering does not park the linearization behind the auxiliary stream)
-    LinOut linearize(const HV& cm_i_cm, const HV& x_ccs, const lf_witness* w, Transcript<Rg>& T, u64* pre_tail = nullptr) {
+    LinOut linearize(const HV& cm_i_cm, const HV& x_ccs, const lf_witness* w, Transcript<Rg>& T, W* pre_tail = nullptr) {
         LinOut o; const int s = (int)P->s; const size_t m = ml();    // tables hold this rank's slab
         HV head = x_ccs; { El one = HR::from_u64(1); head.insert(head.end(), one.begin(), one.end()); }      // z = x || 1 || w  (arith.rs:399-409)
         HV beta = sf_to_ring(squeeze(T, "beta_s", s));                                                       // linearization/utils.rs:113-124
         MzSet mz = alloc_mz(1);
-        { const size_t words = w->w_pitch * D; u64* tail = pre_tail ? pre_tail : gather_wccs(w->w_ccs, words);
+        { const size_t words = w->w_pitch * D; W* tail = pre_tail ? pre_tail : gather_wccs(wp(w->w_ccs), words);
           compute_mz(mz, 0, head, tail, w->w_pitch, w->W * world(), world() == 1 ? ~(size_t)0 : w->W, words);
-          if (tail != w->w_ccs) E.dfree(tail); }
+          if (tail != wp(w->w_ccs)) E.dfree(tail); }
         // sumcheck list: for each term with c_i != 0, the Mz named by S_i; eq(beta,.) last (linearization/utils.rs:63-88)
         std::vector<int> list; for (size_t i = 0; i < P->q; ++i) { bool z = true; for (int l = 0; l < D; ++l) z = z && P->c[i * D + l] == 0; if (z) continue; for (int j : P->S[i]) list.push_back(j); }
         const int Mn = (int)list.size() + 1;
@@ -155,10 +159,11 @@ template <class Rg> struct Prover {
         lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = (int)P->d + 1; sc.kind = LF_COMB_LIN; sc.len = m; sc.sharded = world() > 1;
         SumcheckDriver<Rg> drv(P->ctx, &sc);
         SumcheckDriver<Rg>::alloc_group(E, sc.dense, Mn, m);
-        LF_CUDA(cudaMemsetAsync(sc.dense.cur, 0, (size_t)Mn * sc.dense.stride * 8, E.st()));
+        W* dense = wp(sc.dense.cur); constexpr size_t WB = sizeof(W);
+        LF_CUDA(cudaMemsetAsync(dense, 0, (size_t)Mn * sc.dense.stride * WB, E.st()));
         for (int k = 0; k + 1 < Mn; ++k) { const int j = list[k];
-            LF_CUDA(cudaMemcpy2DAsync(sc.dense.cur + (size_t)k * sc.dense.stride, sc.dense.pitch * 8, mz.p + (size_t)j * mz.stride, mz.pitch * 8, mz.len[j] * 8, D, cudaMemcpyDeviceToDevice, E.st())); }
-        E.eq_table(beta.data(), s, sc.dense.cur + (size_t)(Mn - 1) * sc.dense.stride, sc.dense.pitch, (size_t)rank() * m, m);
+            LF_CUDA(cudaMemcpy2DAsync(dense + (size_t)k * sc.dense.stride, sc.dense.pitch * WB, mz.p + (size_t)j * mz.stride, mz.pitch * WB, mz.len[j] * WB, D, cudaMemcpyDeviceToDevice, E.st())); }
+        E.eq_table(beta.data(), s, dense + (size_t)(Mn - 1) * sc.dense.stride, sc.dense.pitch, (size_t)rank() * m, m);
         // LIN comb (linearization/utils.rs:90-107): vals[] is indexed by the CCS matrix index j.  The list position of
         // matrix j coincides with j for R1CS and the degree-3 CCS; reproduce the reference literally and refuse anything else.
         sc.gen.n_mles = Mn; sc.gen.deg = sc.deg; sc.gen.lin = 1; sc.gen.n_terms = (int)P->q;
@@ -172,7 +177,7 @@ template <class Rg> struct Prover {
         o.eq_r = eq_table(o.lc.r);
         // v = f-hat(r) (linearization.rs:126-131), u = Mz(r) (:133-139)
         u64* d_v = E.small_dev((size_t)TAU * D);
-        E.template coeff_eval<u64>(w->f_coeff, w->pitch, 0, 1, o.eq_r.p, o.eq_r.pitch, w->n, d_v);
+        E.template coeff_eval<W>(wp(w->f_coeff), w->pitch, 0, 1, o.eq_r.p, o.eq_r.pitch, w->n, d_v);
         o.lc.v.resize((size_t)TAU * D); E.download_words(d_v, o.lc.v.size(), o.lc.v.data());
         o.lc.u = eval_mz(mz, 0, (int)P->t, o.eq_r);
         free_mz(mz);
@@ -201,8 +206,8 @@ template <class Rg> struct Prover {
     // ------------------------------------------------------------------ decomposition (decomposition.rs:33-88)
     struct StepBuffers {    // witness-sized state shared by the two decompositions and the folding
         int8_t* dig = nullptr; size_t dig_pitch = 0, dig_stride = 0;     // [2K][D][pitch]
-        u64* pieces = nullptr; size_t pc_pitch = 0, pc_stride = 0;       // NTT form of every piece, [2K][D][pitch]
-        u64* wccs = nullptr; size_t wc_pitch = 0, wc_stride = 0;         // gadget_recompose of every piece, [2K][D][pitch]
+        W* pieces = nullptr; size_t pc_pitch = 0, pc_stride = 0;         // NTT form of every piece, [2K][D][pitch]
+        W* wccs = nullptr; size_t wc_pitch = 0, wc_stride = 0;         // gadget_recompose of every piece, [2K][D][pitch]
         MzSet mz;                                                        // [2K * t]
     };
     struct DecOut { std::vector<HV> x_s, y_s, u_s, v_s; std::vector<LCCCS> lc; };
@@ -235,11 +240,11 @@ template <class Rg> struct Prover {
     DecPending decompose_enqueue(const LCCCS& cm, const lf_witness* w, const DevVec& eq_r, StepBuffers& sb, int half) {
         DecPending o; o.cm = cm; const int K = P->K; const size_t n = nl(), kappa = P->kappa;
         int8_t* dig = sb.dig + (size_t)half * K * sb.dig_stride;
-        u64* pieces = sb.pieces + (size_t)half * K * sb.pc_stride;
-        u64* wccs = sb.wccs + (size_t)half * K * sb.wc_stride;
+        W* pieces = sb.pieces + (size_t)half * K * sb.pc_stride;
+        W* wccs = sb.wccs + (size_t)half * K * sb.wc_stride;
         if (cnt(cm.cm) != kappa) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongCommitmentLength");
         // decompose_witness: f_coeff.decompose_to_vec(b, K).transpose() (decomposition.rs:162-167), then CRT and recompose per piece (arith.rs:324-338)
-        E.digit_split(w->f_coeff, w->pitch, dig, sb.dig_pitch, n, P->b, K);
+        E.digit_split(wp(w->f_coeff), w->pitch, dig, sb.dig_pitch, n, P->b, K);
         E.crt_digits(dig, sb.dig_pitch, pieces, sb.pc_pitch, n, K, sb.dig_stride, sb.pc_stride);                       // all K pieces, one launch each
         E.gadget_recompose(pieces, sb.pc_pitch, wccs, sb.wc_pitch, w->W, P->B, P->L, K, sb.pc_stride, sb.wc_stride);
         mark("dec.split_crt");
@@ -247,11 +252,11 @@ template <class Rg> struct Prover {
         mark("dec.x_s");
         // commit_witnesses (decomposition.rs:178-201): K-1 commits in one pass over A
         if (K > 1) {
-            PtrList Y; for (int k = 1; k < K; ++k) { Y.p[k - 1] = pieces + (size_t)k * sb.pc_stride; Y.len[k - 1] = n; }
+            PL Y; for (int k = 1; k < K; ++k) { Y.p[k - 1] = pieces + (size_t)k * sb.pc_stride; Y.len[k - 1] = n; }
             u64* d_y = E.template dalloc<u64>(kappa * (K - 1) * D);
             // digit pieces: integer GEMM on the tensor cores straight from the int8 digits (commit_mma.cuh); otherwise lazily reduced dot products
             if (E.can_commit_digits(P->A, K - 1, sb.dig_pitch)) E.commit_digits(P->A, dig + sb.dig_stride, sb.dig_pitch, sb.dig_stride, K - 1, d_y);
-            else E.dot(P->A->p, P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y, "k_dot_commit");
+            else E.dot(wp(P->A->p), P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y, "k_dot_commit");
             o.y_pin = E.d2h_async(d_y, kappa * (K - 1) * D); E.dfree(d_y);
         }
         mark("dec.commit");
@@ -261,7 +266,7 @@ template <class Rg> struct Prover {
           o.v_pin = E.d2h_async(d_v, (size_t)K * TAU * D); E.dfree(d_v); }
         mark("dec.v_s");
         // compute_mz_mles / compute_u_s (decomposition.rs:214-256): z_k = x_s[k] || w_ccs_k
-        { const size_t words = (size_t)K * sb.wc_stride; u64* all = gather_wccs(wccs, words);     // one all-gather per decomposition
+        { const size_t words = (size_t)K * sb.wc_stride; W* all = gather_wccs(wccs, words);     // one all-gather per decomposition
           compute_mz_batch(sb.mz, half * K, K, o.x_s, all, sb.wc_pitch, sb.wc_stride, w->W * world(), world() == 1 ? ~(size_t)0 : w->W, words);
           if (all != wccs) E.dfree(all); }
         o.u_pin = eval_mz_async(sb.mz, half * K * (int)P->t, K * (int)P->t, eq_r);
@@ -293,7 +298,7 @@ template <class Rg> struct Prover {
     }
 
     // ------------------------------------------------------------------ folding (folding.rs:42-130)
-    struct FoldOut { HV msgs; std::vector<HV> theta, eta; LCCCS lc; u64* f0 = nullptr; };
+    struct FoldOut { HV msgs; std::vector<HV> theta, eta; LCCCS lc; W* f0 = nullptr; };
     // rot_lin_combination (cyclotomic-rings/src/rotation.rs:45-104), host: d^2 base-by-slot-field products per term
     static HV rot_lin_combination(const std::vector<El>& rho_coeff, const std::vector<HV>& theta) {
         HV acc((size_t)D * TAU, 0);
@@ -319,12 +324,13 @@ template <class Rg> struct Prover {
         lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = 2 * (int)P->b; sc.kind = LF_COMB_FOLD; sc.len = m; sc.sharded = world() > 1;
         SumcheckDriver<Rg> drv(P->ctx, &sc);
         SumcheckDriver<Rg>::alloc_group(E, sc.dense, 5, m);
-        auto tbl = [&](int i) { return sc.dense.cur + (size_t)i * sc.dense.stride; };
-        LF_CUDA(cudaMemcpy2DAsync(tbl(0), sc.dense.pitch * 8, eq_acc.p, eq_acc.pitch * 8, m * 8, D, cudaMemcpyDeviceToDevice, E.st()));
-        LF_CUDA(cudaMemcpy2DAsync(tbl(2), sc.dense.pitch * 8, eq_new.p, eq_new.pitch * 8, m * 8, D, cudaMemcpyDeviceToDevice, E.st()));
+        constexpr size_t WB = sizeof(W);
+        auto tbl = [&](int i) { return wp(sc.dense.cur) + (size_t)i * sc.dense.stride; };
+        LF_CUDA(cudaMemcpy2DAsync(tbl(0), sc.dense.pitch * WB, eq_acc.p, eq_acc.pitch * WB, m * WB, D, cudaMemcpyDeviceToDevice, E.st()));
+        LF_CUDA(cudaMemcpy2DAsync(tbl(2), sc.dense.pitch * WB, eq_new.p, eq_new.pitch * WB, m * WB, D, cudaMemcpyDeviceToDevice, E.st()));
         for (int half = 0; half < 2; ++half) {
-            u64* G = tbl(1 + 2 * half);
-            LF_CUDA(cudaMemsetAsync(G, 0, sc.dense.stride * 8, E.st()));
+            W* G = tbl(1 + 2 * half);
+            LF_CUDA(cudaMemsetAsync(G, 0, sc.dense.stride * WB, E.st()));
             // sum_i Horner_{alpha_i}(f-hat_i[tau-1..0]) = sum_i sum_d alpha_i^{d+1} f-hat_{i,d}   (folding/utils.rs:524-546)
             std::vector<u64> wts((size_t)K * TAU * TAU);
             for (int i = 0; i < K; ++i) { const u64* a = &alpha[(size_t)(half * K + i) * TAU]; u64 pw[TAU]; std::memcpy(pw, a, 8 * TAU);
@@ -334,7 +340,7 @@ template <class Rg> struct Prover {
             E.launch("k_digit_lincomb", [&] { k_digit_lincomb<Rg><<<dim3(Engine<Rg>::blocks_for(n, 128), S), 128, 0, E.st()>>>(sb.dig + (size_t)half * K * sb.dig_stride, sb.dig_pitch, sb.dig_stride, K, d_w, G, sc.dense.pitch, n, 0); });
             E.dfree(d_w);
             // + sum_i Horner_{zeta_i}(Mz_i[t-1..0])   (calculate_challenged_mz_mle, folding.rs:208-226)
-            HV coef((size_t)K * t * D); PtrList pl; std::vector<const u64*> ptrs; std::vector<size_t> lens;
+            HV coef((size_t)K * t * D); PL pl; std::vector<const W*> ptrs; std::vector<size_t> lens;
             for (int i = 0; i < K; ++i) { const u64* z = &zeta[(size_t)(half * K + i) * TAU]; u64 pw[TAU]; std::memcpy(pw, z, 8 * TAU);
                 for (size_t j = 0; j < t; ++j) { El e = HR::from_sf(pw); std::memcpy(&coef[((size_t)i * t + j) * D], e.data(), 8 * D); SF::mul(pw, pw, z);
                     ptrs.push_back(sb.mz.p + ((size_t)(half * K + i) * t + j) * sb.mz.stride); lens.push_back(sb.mz.len[(size_t)(half * K + i) * t + j]); } }
@@ -378,8 +384,8 @@ template <class Rg> struct Prover {
         P->timings[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         mark("fold.absorb_rho");
         // compute_f_0 = sum_i rho_i f_i (folding.rs:258-268)
-        o.f0 = E.template dalloc<u64>(pitch_of(n) * D);
-        { PtrList pl; for (int i = 0; i < 2 * K; ++i) { pl.p[i] = sb.pieces + (size_t)i * sb.pc_stride; pl.len[i] = n; }
+        o.f0 = E.template dalloc<W>(pitch_of(n) * D);
+        { PL pl; for (int i = 0; i < 2 * K; ++i) { pl.p[i] = sb.pieces + (size_t)i * sb.pc_stride; pl.len[i] = n; }
           if (2 * K > MAX_LIST) throw LfException(LF_ERR_UNSUPPORTED, "2K exceeds MAX_LIST");
           E.lincomb(pl, sb.pc_pitch, 2 * K, rho.data(), o.f0, pitch_of(n), n, false); }
         mark("fold.f0");
@@ -444,13 +450,13 @@ template <class Rg> struct Prover {
         StepBuffers sb;
         sb.dig_pitch = (std::max(n, ml()) + 255) / 256 * 256;   // the sumcheck walks all 2^s entries
         sb.dig_stride = sb.dig_pitch * D; sb.dig = E.template dalloc<int8_t>((size_t)2 * K * sb.dig_stride);
-        sb.pc_pitch = pitch_of(n); sb.pc_stride = sb.pc_pitch * D; sb.pieces = E.template dalloc<u64>((size_t)2 * K * sb.pc_stride);
-        sb.wc_pitch = pitch_of(w_i->W); sb.wc_stride = sb.wc_pitch * D; sb.wccs = E.template dalloc<u64>((size_t)2 * K * sb.wc_stride);
+        sb.pc_pitch = pitch_of(n); sb.pc_stride = sb.pc_pitch * D; sb.pieces = E.template dalloc<W>((size_t)2 * K * sb.pc_stride);
+        sb.wc_pitch = pitch_of(w_i->W); sb.wc_stride = sb.wc_pitch * D; sb.wccs = E.template dalloc<W>((size_t)2 * K * sb.wc_stride);
         sb.mz = alloc_mz(2 * K, false);
-        DevVec eq_acc; eq_acc.n = ((size_t)1 << cnt(acc.r)) / world(); eq_acc.pitch = pitch_of(eq_acc.n); eq_acc.p = E.template dalloc<u64>(eq_acc.pitch * D);
+        DevVec eq_acc; eq_acc.n = ((size_t)1 << cnt(acc.r)) / world(); eq_acc.pitch = pitch_of(eq_acc.n); eq_acc.p = E.template dalloc<W>(eq_acc.pitch * D);
         // sharded steps overlap too when the collectives are stream-ordered on both streams (own NCCL communicator + mailbox channels)
         const bool overlap = (world() == 1 || (E.c->nccl && E.c->xg.on)) && !P->detail && !std::getenv("LF_NO_OVERLAP");
-        u64* lin_tail = (overlap && world() > 1) ? gather_wccs(w_i->w_ccs, w_i->w_pitch * D) : nullptr;
+        W* lin_tail = (overlap && world() > 1) ? gather_wccs(wp(w_i->w_ccs), w_i->w_pitch * D) : nullptr;
         DecPending pl;
         {
             lf_ctx* main_ctx = E.c;

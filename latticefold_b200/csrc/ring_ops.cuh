@@ -64,6 +64,10 @@ RingOps* ring_ops_babybear();
 RingOps* ring_ops_frog();
 
 template <class Rg> struct RingOpsImpl final : RingOps {
+    typedef typename Rg::W W; typedef PtrListT<W> PL;
+    static W* wp(lf_words* p) { return reinterpret_cast<W*>(p); }
+    static const W* wp(const lf_words* p) { return reinterpret_cast<const W*>(p); }
+    static lf_words* ow(W* p) { return reinterpret_cast<lf_words*>(p); }
     static Transcript<Rg>& tr(lf_transcript* t) { if (t->ring != Rg::ID) throw LfException(LF_ERR_INVALID_ARG, "transcript ring differs from the context's ring"); return *(Transcript<Rg>*)t->impl; }
     void describe(lf_ring_info* out) override { out->p = Rg::F::P; out->d = Rg::D; out->n_slots = Rg::S; out->tau = Rg::TAU; out->nu = Rg::F::NU; }
     void ctx_tables_create(lf_ctx* c) override {
@@ -92,48 +96,48 @@ template <class Rg> struct RingOpsImpl final : RingOps {
     uint64_t tr_permutations(const void* t) override { return ((const Transcript<Rg>*)t)->permutations(); }
 
     void vec_upload(lf_ctx* c, const uint64_t* host, size_t n, int32_t form, lf_vec** out) override {
-        Engine<Rg> E(c); lf_vec* v = E.vec_alloc(n, form); E.upload_planes(host, n, v->p, v->pitch); E.sync(); *out = v;
+        Engine<Rg> E(c); lf_vec* v = E.vec_alloc(n, form); E.upload_planes(host, n, wp(v->p), v->pitch); E.sync(); *out = v;
     }
     void vec_download(lf_ctx* c, const lf_vec* v, uint64_t* host) override {
-        Engine<Rg> E(c); E.download_planes(v->p, v->pitch, v->n, host);
+        Engine<Rg> E(c); E.download_planes(wp(v->p), v->pitch, v->n, host);
     }
     void crt(lf_ctx* c, const lf_vec* in, lf_vec** out) override {
-        Engine<Rg> E(c); lf_vec* o = E.vec_alloc(in->n, LF_FORM_NTT); E.crt(in->p, in->pitch, o->p, o->pitch, in->n, false); *out = o;
+        Engine<Rg> E(c); lf_vec* o = E.vec_alloc(in->n, LF_FORM_NTT); E.crt(wp(in->p), in->pitch, wp(o->p), o->pitch, in->n, false); *out = o;
     }
     void icrt(lf_ctx* c, const lf_vec* in, lf_vec** out) override {
-        Engine<Rg> E(c); lf_vec* o = E.vec_alloc(in->n, LF_FORM_COEFF); E.crt(in->p, in->pitch, o->p, o->pitch, in->n, true); *out = o;
+        Engine<Rg> E(c); lf_vec* o = E.vec_alloc(in->n, LF_FORM_COEFF); E.crt(wp(in->p), in->pitch, wp(o->p), o->pitch, in->n, true); *out = o;
     }
     void gadget_decompose(lf_ctx* c, const lf_vec* in, uint64_t B, int32_t L, lf_vec** out) override {
         Engine<Rg> E(c); lf_vec* o = E.vec_alloc(in->n * (size_t)L, LF_FORM_COEFF);
-                          try { E.gadget_decompose(in->p, in->pitch, o->p, o->pitch, in->n, B, L); E.check_err_flag(LF_ERR_DOES_NOT_FIT, "gadget_decompose: a coefficient does not fit L digits of base B"); }
+                          try { E.gadget_decompose(wp(in->p), in->pitch, wp(o->p), o->pitch, in->n, B, L); E.check_err_flag(LF_ERR_DOES_NOT_FIT, "gadget_decompose: a coefficient does not fit L digits of base B"); }
                           catch (...) { E.vec_free(o); throw; }
                           *out = o;
     }
     void gadget_recompose(lf_ctx* c, const lf_vec* in, uint64_t B, int32_t L, lf_vec** out) override {
         if (L < 1 || in->n % (size_t)L) throw LfException(LF_ERR_INCORRECT_LENGTH, "gadget_recompose: length is not a multiple of L");
-                          Engine<Rg> E(c); lf_vec* o = E.vec_alloc(in->n / L, in->form); E.gadget_recompose(in->p, in->pitch, o->p, o->pitch, o->n, B, L); *out = o;
+                          Engine<Rg> E(c); lf_vec* o = E.vec_alloc(in->n / L, in->form); E.gadget_recompose(wp(in->p), in->pitch, wp(o->p), o->pitch, o->n, B, L); *out = o;
     }
     void decompose_to_vec(lf_ctx* c, const lf_vec* in, uint64_t b, int32_t K, lf_vec** out_k) override {
         Engine<Rg> E(c); const size_t n = in->n, dp = (n + 255) / 256 * 256;
         int8_t* dig = E.template dalloc<int8_t>((size_t)K * Rg::D * dp);
-        try { E.digit_split(in->p, in->pitch, dig, dp, n, b, K); E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_to_vec: a coefficient does not fit K digits of base b"); }
+        try { E.digit_split(wp(in->p), in->pitch, dig, dp, n, b, K); E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_to_vec: a coefficient does not fit K digits of base b"); }
         catch (...) { E.dfree(dig); throw; }
         for (int k = 0; k < K; ++k) { lf_vec* o = E.vec_alloc(n, LF_FORM_COEFF);
-            if (n) { E.launch("k_digits_to_field", [&] { k_digits_to_field<Rg><<<Engine<Rg>::blocks_for(n * Rg::D), 256, 0, E.st()>>>(dig + (size_t)k * Rg::D * dp, dp, o->p, o->pitch, n); }); }
+            if (n) { E.launch("k_digits_to_field", [&] { k_digits_to_field<Rg><<<Engine<Rg>::blocks_for(n * Rg::D), 256, 0, E.st()>>>(dig + (size_t)k * Rg::D * dp, dp, wp(o->p), o->pitch, n); }); }
             out_k[k] = o; }
         E.dfree(dig);
     }
     void fhat(lf_ctx* c, const lf_vec* in, lf_vec** out_tau) override {
         Engine<Rg> E(c); const size_t n = in->n;
         for (int j = 0; j < Rg::TAU; ++j) { lf_vec* o = E.vec_alloc(n, LF_FORM_NTT);
-            if (n) { E.launch("k_fhat", [&] { k_fhat<Rg><<<Engine<Rg>::blocks_for(n * Rg::S), 256, 0, E.st()>>>(in->p + (size_t)j * Rg::S * in->pitch, in->pitch, o->p, o->pitch, n); }); }
+            if (n) { E.launch("k_fhat", [&] { k_fhat<Rg><<<Engine<Rg>::blocks_for(n * Rg::S), 256, 0, E.st()>>>(wp(in->p) + (size_t)j * Rg::S * in->pitch, in->pitch, wp(o->p), o->pitch, n); }); }
             out_tau[j] = o; }
     }
     void ajtai_create(lf_ctx* c, size_t kappa, size_t n, const uint64_t* host, lf_ajtai** out) override {
         Engine<Rg> E(c); std::unique_ptr<lf_ajtai> a(new lf_ajtai); a->kappa = kappa; a->n = n; a->pitch = pitch_of(n);
-        LF_CUDA(cudaMalloc(&a->p, std::max<size_t>(1, kappa * a->pitch * Rg::D) * 8));
+        LF_CUDA(cudaMalloc(&a->p, std::max<size_t>(1, kappa * a->pitch * Rg::D) * sizeof(W)));
         // row by row so the staging buffer stays small (the matrix is 1.3 GB at kappa=26, n=2^18)
-        for (size_t i = 0; i < kappa; ++i) E.upload_planes(host + i * n * Rg::D, n, a->p + i * a->pitch * Rg::D, a->pitch);
+        for (size_t i = 0; i < kappa; ++i) E.upload_planes(host + i * n * Rg::D, n, wp(a->p) + i * a->pitch * Rg::D, a->pitch);
         E.sync(); E.ajtai_build_tiles(a.get()); *out = a.release();
     }
     void commit_batch(lf_ctx* c, const lf_ajtai* a, const lf_vec* const* f, int32_t count, uint64_t* out_host) override {
@@ -141,16 +145,16 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         for (int i = 0; i < count; ++i) if (f[i]->n != a->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongWitnessLength(" + std::to_string(f[i]->n) + ", " + std::to_string(a->n) + ")");
         for (int done = 0; done < count; done += MAX_LIST) {
             const int chunk = std::min(MAX_LIST, count - done);
-            PtrList Y; for (int i = 0; i < chunk; ++i) { Y.p[i] = f[done + i]->p; Y.len[i] = a->n; }
+            PL Y; for (int i = 0; i < chunk; ++i) { Y.p[i] = wp(f[done + i]->p); Y.len[i] = a->n; }
             u64* d_out = E.small_dev(a->kappa * chunk * Rg::D);
-            E.dot(a->p, a->pitch * Rg::D, a->pitch, (int)a->kappa, nullptr, Y, pitch_of(a->n), chunk, a->n, d_out);
+            E.dot(wp(a->p), a->pitch * Rg::D, a->pitch, (int)a->kappa, nullptr, Y, pitch_of(a->n), chunk, a->n, d_out);
             HV all(a->kappa * chunk * Rg::D); E.download_words(d_out, all.size(), all.data());
             for (int i = 0; i < chunk; ++i) for (size_t r = 0; r < a->kappa; ++r) std::memcpy(out_host + ((size_t)(done + i) * a->kappa + r) * Rg::D, &all[(r * chunk + i) * Rg::D], 8 * Rg::D);
         }
     }
     void commit_coeff(lf_ctx* c, const lf_ajtai* a, const lf_vec* f_coeff, uint64_t* out_host) override {
         if (f_coeff->n != a->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongWitnessLength(" + std::to_string(f_coeff->n) + ", " + std::to_string(a->n) + ")");
-        Engine<Rg> E(c); lf_vec* f = E.vec_alloc(f_coeff->n, LF_FORM_NTT); E.crt(f_coeff->p, f_coeff->pitch, f->p, f->pitch, f->n, false);
+        Engine<Rg> E(c); lf_vec* f = E.vec_alloc(f_coeff->n, LF_FORM_NTT); E.crt(wp(f_coeff->p), f_coeff->pitch, wp(f->p), f->pitch, f->n, false);
         try { const lf_vec* fp = f; commit_batch(c, a, &fp, 1, out_host); } catch (...) { E.vec_free(f); throw; }
         E.vec_free(f);
     }
@@ -159,8 +163,8 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         Engine<Rg> E(c); lf_vec* co = nullptr; lf_vec* dg = E.vec_alloc(a->n, LF_FORM_COEFF);
         try {
             const lf_vec* src = v;
-            if (ntt_form) { co = E.vec_alloc(v->n, LF_FORM_COEFF); E.crt(v->p, v->pitch, co->p, co->pitch, v->n, true); src = co; }
-            E.gadget_decompose(src->p, src->pitch, dg->p, dg->pitch, src->n, B, L);
+            if (ntt_form) { co = E.vec_alloc(v->n, LF_FORM_COEFF); E.crt(wp(v->p), v->pitch, wp(co->p), co->pitch, v->n, true); src = co; }
+            E.gadget_decompose(wp(src->p), src->pitch, wp(dg->p), dg->pitch, src->n, B, L);
             E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_and_commit: a coefficient does not fit L digits of base B");
             commit_coeff(c, a, dg, out_host);
         } catch (...) { E.vec_free(co); E.vec_free(dg); throw; }
@@ -169,19 +173,19 @@ template <class Rg> struct RingOpsImpl final : RingOps {
     void commit_pieces(lf_ctx* c, const lf_ajtai* a, const lf_vec* f_coeff, uint64_t b, int32_t K, uint64_t* out_host) override {
         if (f_coeff->n != a->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongWitnessLength(" + std::to_string(f_coeff->n) + ", " + std::to_string(a->n) + ")");
         Engine<Rg> E(c); const size_t n = a->n, dp = (n + 255) / 256 * 256, ds = dp * Rg::D, kappa = a->kappa;
-        int8_t* dig = E.template dalloc<int8_t>((size_t)K * ds); u64* pieces = nullptr;
+        int8_t* dig = E.template dalloc<int8_t>((size_t)K * ds); W* pieces = nullptr;
         try {
             LF_CUDA(cudaMemsetAsync(dig, 0, (size_t)K * ds, E.st()));
-            E.digit_split(f_coeff->p, f_coeff->pitch, dig, dp, n, b, K);
+            E.digit_split(wp(f_coeff->p), f_coeff->pitch, dig, dp, n, b, K);
             E.check_err_flag(LF_ERR_DOES_NOT_FIT, "decompose_to_vec: a coefficient does not fit K digits of base b");
             const bool mma = E.can_commit_digits(a, 1, dp);
-            if (!mma) { pieces = E.template dalloc<u64>((size_t)K * pitch_of(n) * Rg::D); E.crt_digits(dig, dp, pieces, pitch_of(n), n, K, ds, pitch_of(n) * Rg::D); }
+            if (!mma) { pieces = E.template dalloc<W>((size_t)K * pitch_of(n) * Rg::D); E.crt_digits(dig, dp, pieces, pitch_of(n), n, K, ds, pitch_of(n) * Rg::D); }
             for (int done = 0; done < K; done += 16) {
                 const int chunk = std::min(16, K - done);
                 u64* d_out = E.small_dev(kappa * chunk * Rg::D);
                 if (mma) E.commit_digits(a, dig + (size_t)done * ds, dp, ds, chunk, d_out);
-                else { PtrList Y; for (int i = 0; i < chunk; ++i) { Y.p[i] = pieces + (size_t)(done + i) * pitch_of(n) * Rg::D; Y.len[i] = n; }
-                       E.dot(a->p, a->pitch * Rg::D, a->pitch, (int)kappa, nullptr, Y, pitch_of(n), chunk, n, d_out); }
+                else { PL Y; for (int i = 0; i < chunk; ++i) { Y.p[i] = pieces + (size_t)(done + i) * pitch_of(n) * Rg::D; Y.len[i] = n; }
+                       E.dot(wp(a->p), a->pitch * Rg::D, a->pitch, (int)kappa, nullptr, Y, pitch_of(n), chunk, n, d_out); }
                 HV all(kappa * chunk * Rg::D); E.download_words(d_out, all.size(), all.data());
                 for (int i = 0; i < chunk; ++i) for (size_t r = 0; r < kappa; ++r) std::memcpy(out_host + ((size_t)(done + i) * kappa + r) * Rg::D, &all[(r * chunk + i) * Rg::D], 8 * Rg::D);
             }
@@ -197,27 +201,27 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         for (size_t i = 0; i < m->nnz; ++i) { if (col[i] >= ncols) throw LfException(LF_ERR_INVALID_ARG, "column index out of range"); cl[i] = (u32)col[i]; }
         LF_CUDA(cudaMalloc(&m->row_ptr, (nrows + 1) * 4)); LF_CUDA(cudaMalloc(&m->col, std::max<size_t>(1, m->nnz) * 4));
         LF_CUDA(cudaMemcpy(m->row_ptr, rp.data(), (nrows + 1) * 4, cudaMemcpyHostToDevice)); if (m->nnz) LF_CUDA(cudaMemcpy(m->col, cl.data(), m->nnz * 4, cudaMemcpyHostToDevice));
-        m->val_pitch = pitch_of(m->nnz); LF_CUDA(cudaMalloc(&m->val, m->val_pitch * Rg::D * 8));
-        E.upload_planes(val, m->nnz, m->val, m->val_pitch); E.sync(); *out = m.release();
+        m->val_pitch = pitch_of(m->nnz); LF_CUDA(cudaMalloc(&m->val, m->val_pitch * Rg::D * sizeof(W)));
+        E.upload_planes(val, m->nnz, wp(m->val), m->val_pitch); E.sync(); *out = m.release();
     }
     void spmv(lf_ctx* c, const lf_sparse* m, const lf_vec* z, lf_vec** out) override {
         if (z->n != m->ncols) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "LengthsNotEqual(M, z)");
-        Engine<Rg> E(c); lf_vec* o = E.vec_alloc(m->nrows, LF_FORM_NTT); E.spmv(m, z->p, z->n, z->pitch, z->p, z->pitch, o->p, o->pitch, m->nrows); *out = o;
+        Engine<Rg> E(c); lf_vec* o = E.vec_alloc(m->nrows, LF_FORM_NTT); E.spmv(m, wp(z->p), z->n, z->pitch, wp(z->p), z->pitch, wp(o->p), o->pitch, m->nrows); *out = o;
     }
     void eq_table(lf_ctx* c, const uint64_t* r, int32_t s, lf_vec** out) override {
         if (s < 1 || s > 34) throw LfException(LF_ERR_INVALID_ARG, "r length is 0 (or too large)"); Engine<Rg> E(c); lf_vec* o = E.vec_alloc((size_t)1 << s, LF_FORM_NTT);
-                          try { E.eq_table(r, s, o->p, o->pitch); } catch (...) { E.vec_free(o); throw; } *out = o;
+                          try { E.eq_table(r, s, wp(o->p), o->pitch); } catch (...) { E.vec_free(o); throw; } *out = o;
     }
     void mle_eval_batch(lf_ctx* c, const lf_vec* const* mles, int32_t count, int32_t nv, const uint64_t* point, int32_t point_len, uint64_t* out_host) override {
         if (point_len != nv) throw LfException(LF_ERR_MLE_LEN, "IncorrectLength: point length != num_vars");
         for (int i = 0; i < count; ++i) if (mles[i]->n > ((size_t)1 << nv)) throw LfException(LF_ERR_MLE_LEN, "IncorrectLength: MLE longer than 2^num_vars");
         Engine<Rg> E(c); const size_t n = (size_t)1 << nv, ep = pitch_of(n);
-        u64* eq = E.template dalloc<u64>(ep * Rg::D); E.eq_table(point, nv, eq, ep);
+        W* eq = E.template dalloc<W>(ep * Rg::D); E.eq_table(point, nv, eq, ep);
         // the dot kernel treats the MLEs as columns against the eq table as the single row
         for (int done = 0; done < count; done += MAX_LIST) {
             const int chunk = std::min(MAX_LIST, count - done);
-            PtrList Y; size_t pitch = 0;
-            for (int i = 0; i < chunk; ++i) { Y.p[i] = mles[done + i]->p; Y.len[i] = mles[done + i]->n; if (i && mles[done + i]->pitch != pitch) throw LfException(LF_ERR_INVALID_ARG, "MLEs of one batch must have equal length"); pitch = mles[done + i]->pitch; }
+            PL Y; size_t pitch = 0;
+            for (int i = 0; i < chunk; ++i) { Y.p[i] = wp(mles[done + i]->p); Y.len[i] = mles[done + i]->n; if (i && mles[done + i]->pitch != pitch) throw LfException(LF_ERR_INVALID_ARG, "MLEs of one batch must have equal length"); pitch = mles[done + i]->pitch; }
             u64* d_out = E.small_dev((size_t)chunk * Rg::D);
             E.dot(eq, 0, ep, 1, nullptr, Y, pitch, chunk, n, d_out);
             E.download_words(d_out, (size_t)chunk * Rg::D, out_host + (size_t)done * Rg::D);
@@ -228,8 +232,8 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         if (count < 1) throw LfException(LF_ERR_INVALID_ARG, "lincomb of nothing");
         for (int i = 1; i < count; ++i) if (vecs[i]->n != vecs[0]->n) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "LengthsNotEqual");
         Engine<Rg> E(c); lf_vec* o = E.vec_alloc(vecs[0]->n, vecs[0]->form);
-        for (int done = 0; done < count; done += MAX_LIST) { const int chunk = std::min(MAX_LIST, count - done); PtrList pl; for (int i = 0; i < chunk; ++i) { pl.p[i] = vecs[done + i]->p; pl.len[i] = o->n; }
-            E.lincomb(pl, o->pitch, chunk, coeffs + (size_t)done * Rg::D, o->p, o->pitch, o->n, done > 0); }
+        for (int done = 0; done < count; done += MAX_LIST) { const int chunk = std::min(MAX_LIST, count - done); PL pl; for (int i = 0; i < chunk; ++i) { pl.p[i] = wp(vecs[done + i]->p); pl.len[i] = o->n; }
+            E.lincomb(pl, o->pitch, chunk, coeffs + (size_t)done * Rg::D, wp(o->p), o->pitch, o->n, done > 0); }
         *out = o;
     }
     void sumcheck_begin(lf_ctx* c, lf_vec** mles, int32_t M, int32_t nv, int32_t degree, const lf_comb* comb, lf_sumcheck** out) override {
@@ -249,8 +253,9 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         }
         auto fill = [&](lf_sumcheck::Group& g, int first, int count) {
             SumcheckDriver<Rg>::alloc_group(E, g, count, n);
-            LF_CUDA(cudaMemsetAsync(g.cur, 0, (size_t)count * g.stride * 8, E.st()));
-            for (int k = 0; k < count; ++k) { const lf_vec* v = mles[first + k]; if (v->n) LF_CUDA(cudaMemcpy2DAsync(g.cur + (size_t)k * g.stride, g.pitch * 8, v->p, v->pitch * 8, v->n * 8, Rg::D, cudaMemcpyDeviceToDevice, E.st())); }
+            constexpr size_t WB = sizeof(W);
+            LF_CUDA(cudaMemsetAsync(g.cur, 0, (size_t)count * g.stride * WB, E.st()));
+            for (int k = 0; k < count; ++k) { const lf_vec* v = mles[first + k]; if (v->n) LF_CUDA(cudaMemcpy2DAsync(wp(g.cur) + (size_t)k * g.stride, g.pitch * WB, v->p, v->pitch * WB, v->n * WB, Rg::D, cudaMemcpyDeviceToDevice, E.st())); }
         };
         fill(sc->dense, 0, n_dense);
         if (comb->kind == LF_COMB_FOLD) { fill(sc->fh, 5, M - 5); drv.set_mu(comb->mu_host, comb->n_mu); }
@@ -302,12 +307,12 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         Prover<Rg> pr(p); *out = pr.upload_witness(f_host);
     }
     void witness_download_f(lf_prover* p, const lf_witness* w, uint64_t* f_host) override {
-        Engine<Rg> E(p->ctx); E.download_planes(w->f, w->pitch, w->n, f_host);
+        Engine<Rg> E(p->ctx); E.download_planes(wp(w->f), w->pitch, w->n, f_host);
     }
     void witness_f_from_w_ccs(lf_ctx* c, const uint64_t* w_ccs, size_t W, uint64_t B, int32_t L, uint64_t* f_host) override {
-        Engine<Rg> E(c); const size_t wp = pitch_of(W), n = W * (size_t)L, np = pitch_of(n);
-        u64 *w = E.template dalloc<u64>(wp * Rg::D), *wc = E.template dalloc<u64>(wp * Rg::D), *fc = E.template dalloc<u64>(np * Rg::D), *f = E.template dalloc<u64>(np * Rg::D);
-        E.upload_planes(w_ccs, W, w, wp); E.crt(w, wp, wc, wp, W, true); E.gadget_decompose(wc, wp, fc, np, W, B, L); E.crt(fc, np, f, np, n, false);
+        Engine<Rg> E(c); const size_t wpt = pitch_of(W), n = W * (size_t)L, np = pitch_of(n);
+        typename Rg::W *w = E.template dalloc<typename Rg::W>(wpt * Rg::D), *wc = E.template dalloc<typename Rg::W>(wpt * Rg::D), *fc = E.template dalloc<typename Rg::W>(np * Rg::D), *f = E.template dalloc<typename Rg::W>(np * Rg::D);
+        E.upload_planes(w_ccs, W, w, wpt); E.crt(w, wpt, wc, wpt, W, true); E.gadget_decompose(wc, wpt, fc, np, W, B, L); E.crt(fc, np, f, np, n, false);
         E.check_err_flag(LF_ERR_DOES_NOT_FIT, "from_w_ccs: a coefficient does not fit L digits of base B");
         E.download_planes(f, np, n, f_host); E.dfree(w); E.dfree(wc); E.dfree(fc); E.dfree(f);
     }
@@ -335,7 +340,7 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         cudaEvent_t ev = p->acc_ready;
         try { w = pr.prove(*in, wa, wi, tr(t), out_proof, out_lcccs, true); } catch (...) { p->acc_ready = nullptr; cudaEventDestroy(ev); pr.free_witness(wa); pr.free_witness(wi); throw; }
         p->acc_ready = nullptr; cudaEventDestroy(ev);
-        if (out_f) pr.E.download_planes(w->f, w->pitch, w->n, out_f);
+        if (out_f) pr.E.download_planes(wp(w->f), w->pitch, w->n, out_f);
         pr.free_witness(w); pr.free_witness(wa); pr.free_witness(wi); pr.E.sync();
     }
 };

@@ -9,14 +9,14 @@ struct lf_sumcheck {
     lf_ctx* ctx = nullptr;
     int nv = 0, deg = 0, round = 0, kind = 0;
     // table groups, each [count][D planes][pitch]; ping-pong buffers (cur -> nxt on every applied challenge)
-    struct Group { lf::u64 *cur = nullptr, *nxt = nullptr, *alt = nullptr; size_t pitch = 0, stride = 0, nxt_cap = 0, alt_cap = 0; int count = 0; bool cur_owned = true; };
+    struct Group { lf_words *cur = nullptr, *nxt = nullptr, *alt = nullptr; size_t pitch = 0, stride = 0, nxt_cap = 0, alt_cap = 0; int count = 0; bool cur_owned = true; };
     Group dense;          // PRODUCTS/LIN: all MLEs.  FOLD: the first five
     Group fh;             // FOLD: the 2K*tau f-hat tables (slot-field valued); empty while still in digit form
     const int8_t* dig = nullptr; size_t dig_pitch = 0, dig_stride = 0;   // FOLD round 1 in the prover: borrowed int8 digits
     int n_f = 0;
     lf::u64* d_mu_pow = nullptr;      // n_f x TAU
     lf::u64* d_coef = nullptr;        // PRODUCTS/LIN term coefficients, n_terms x D
-    lf::ScGenericArgs gen;            // term structure
+    lf::ScGenericArgsT<lf::u64> gen;  // term structure (the table pointers are filled per launch, in the ring's word type)
     size_t len = 0;                   // current LOCAL table length (2^(nv - applied challenges) / ranks while sharded)
     int applied = 0;
     bool sharded = false;             // tables hold this rank's slab of the hypercube (high bits = rank)
@@ -25,13 +25,15 @@ struct lf_sumcheck {
 namespace lf {
 
 template <class Rg> struct SumcheckDriver {
-    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef HostRing<Rg> HR;
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef HostRing<Rg> HR; typedef typename Rg::W W;
     static constexpr int D = Rg::D, S = Rg::S, TAU = Rg::TAU;
+    static W* wp(lf_words* p) { return reinterpret_cast<W*>(p); }
+    static lf_words* ow(W* p) { return reinterpret_cast<lf_words*>(p); }
     Engine<Rg> E; lf_sumcheck* sc;
     SumcheckDriver(lf_ctx* c, lf_sumcheck* s) : E(c), sc(s) {}
 
     static void alloc_group(Engine<Rg>& E, lf_sumcheck::Group& g, int count, size_t len) {
-        g.count = count; g.pitch = pitch_of(len); g.stride = g.pitch * D; g.cur = E.template dalloc<u64>((size_t)count * g.stride); g.cur_owned = true;
+        g.count = count; g.pitch = pitch_of(len); g.stride = g.pitch * D; g.cur = ow(E.template dalloc<W>((size_t)count * g.stride)); g.cur_owned = true;
     }
     void free_all() {
         for (lf_sumcheck::Group* g : {&sc->dense, &sc->fh}) { if (g->cur_owned && g->cur != g->nxt && g->cur != g->alt) E.dfree(g->cur); E.dfree(g->nxt); E.dfree(g->alt); g->cur = g->nxt = g->alt = nullptr; g->nxt_cap = g->alt_cap = 0; }
@@ -63,15 +65,18 @@ template <class Rg> struct SumcheckDriver {
             const unsigned gx1 = (unsigned)((n_pairs + 127) / 128), gx2 = (unsigned)((n_pairs + 63) / 64);      // rounds >= 2: two lanes per pair
             nblk = round1 ? gx1 : gx2;
             partial = E.partial_dev((size_t)nblk * 5 * D);
-            FoldScArgs a; a.dense = sc->dense.cur; a.dense_pitch = sc->dense.pitch; a.dense_stride = sc->dense.stride; a.mu_pow = sc->d_mu_pow; a.n_f = sc->n_f;
+            FoldScArgsT<W> a; a.dense = wp(sc->dense.cur); a.dense_pitch = sc->dense.pitch; a.dense_stride = sc->dense.stride; a.mu_pow = sc->d_mu_pow; a.n_f = sc->n_f;
             a.n_pairs = n_pairs; a.partial = partial; a.dig = sc->dig; a.dig_pitch = sc->dig_pitch; a.dig_stride = sc->dig_stride;
-            a.fh = sc->fh.cur; a.fh_pitch = sc->fh.pitch; a.fh_stride = sc->fh.stride;
+            a.fh = wp(sc->fh.cur); a.fh_pitch = sc->fh.pitch; a.fh_stride = sc->fh.stride;
             if (round1) E.launch("k_fold_sc_round1", [&] { k_fold_sc_round1<Rg><<<dim3(gx1, S), 128, 0, E.st()>>>(a); });
             else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(gx2, S), 128, 0, E.st()>>>(a); });
         } else {
             nblk = (unsigned)std::min<size_t>((n_pairs + 127) / 128, 148 * 8); partial = E.partial_dev((size_t)nblk * ne * D);
-            ScGenericArgs a = sc->gen; a.pitch = sc->dense.pitch; a.n_pairs = n_pairs; a.partial = partial; a.coef = sc->d_coef;
-            for (int k = 0; k < a.n_mles; ++k) a.mle[k] = sc->dense.cur + (size_t)k * sc->dense.stride;
+            ScGenericArgsT<W> a; const auto& gen = sc->gen;
+            a.n_mles = gen.n_mles; a.deg = gen.deg; a.n_terms = gen.n_terms; a.lin = gen.lin;
+            for (int t = 0; t < SC_MAX_TERMS; ++t) { a.term_len[t] = gen.term_len[t]; for (int f = 0; f < SC_MAX_FACTORS; ++f) a.term_idx[t][f] = gen.term_idx[t][f]; }
+            a.pitch = sc->dense.pitch; a.n_pairs = n_pairs; a.partial = partial; a.coef = sc->d_coef;
+            for (int k = 0; k < a.n_mles; ++k) a.mle[k] = wp(sc->dense.cur) + (size_t)k * sc->dense.stride;
             dim3 g(nblk, S);
             for (int k = a.n_mles; k < SC_MAX_MLES; ++k) a.mle[k] = a.mle[0];   // padding tables are loaded but never referenced by a term
             E.launch("k_sc_generic", [&] {
@@ -87,34 +92,35 @@ template <class Rg> struct SumcheckDriver {
         sc->round += 1;
     }
     // ping-pong targets are allocated once (sizes len/2 and len/4 of the first fold) and reused by all later rounds
-    u64* pingpong_target(lf_sumcheck::Group& g, size_t n_out) {
+    W* pingpong_target(lf_sumcheck::Group& g, size_t n_out) {
         const size_t need = (size_t)g.count * pitch_of(n_out) * D;
-        u64*& slot = (g.cur == g.nxt) ? g.alt : g.nxt;
+        lf_words*& slot = (g.cur == g.nxt) ? g.alt : g.nxt;
         size_t& cap = (g.cur == g.nxt) ? g.alt_cap : g.nxt_cap;
-        if (cap < need) { E.dfree(slot); slot = E.template dalloc<u64>(need); cap = need; }
-        return slot;
+        if (cap < need) { E.dfree(slot); slot = ow(E.template dalloc<W>(need)); cap = need; }
+        return wp(slot);
     }
     void fold_group(lf_sumcheck::Group& g, const u64* r_sf, size_t n_out) {
         if (!g.count || !g.cur) return;
         const size_t np = pitch_of(n_out);
-        u64* out = pingpong_target(g, n_out);
-        FoldArgs a; a.in = g.cur; a.out = out; a.in_pitch = g.pitch; a.out_pitch = np; a.in_stride = g.stride; a.out_stride = np * D; a.n_out = n_out;
+        W* out = pingpong_target(g, n_out);
+        FoldArgsT<W> a; a.in = wp(g.cur); a.out = out; a.in_pitch = g.pitch; a.out_pitch = np; a.in_stride = g.stride; a.out_stride = np * D; a.n_out = n_out;
         for (int l = 0; l < TAU; ++l) a.r[l] = r_sf[l];
         E.launch("k_fold", [&] { k_fold<Rg><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, g.count), 128, 0, E.st()>>>(a); });
         if (g.cur_owned && g.cur != g.nxt && g.cur != g.alt) E.dfree(g.cur);     // the caller-provided / initial table set
-        g.cur = out; g.cur_owned = false; g.pitch = np; g.stride = np * D;
+        g.cur = ow(out); g.cur_owned = false; g.pitch = np; g.stride = np * D;
     }
     // every rank holds one entry per table: all-gather them (summing into a zeroed buffer) so the remaining variables,
     // which index the ranks, can be bound on every rank redundantly
     void gather_group(lf_sumcheck::Group& g) {
         if (!g.count || !g.cur) return;
         const int G = E.c->world; const size_t np = pitch_of(G), rows = (size_t)g.count * D;
-        u64* out = E.template dalloc<u64>(rows * np);
-        LF_CUDA(cudaMemsetAsync(out, 0, rows * np * 8, E.st()));
-        E.launch("k_scatter_entry", [&] { k_scatter_entry<0><<<Engine<Rg>::blocks_for(rows), 256, 0, E.st()>>>(g.cur, g.pitch, out, np, rows, E.c->rank); });
-        E.collective(0, out, rows * np);
+        // (summed as u64 lanes: every word is non-zero on exactly one rank, so packed 4-byte words cannot carry into each other)
+        W* out = E.template dalloc<W>(rows * np);
+        LF_CUDA(cudaMemsetAsync(out, 0, rows * np * sizeof(W), E.st()));
+        E.launch("k_scatter_entry", [&] { k_scatter_entry<W><<<Engine<Rg>::blocks_for(rows), 256, 0, E.st()>>>(wp(g.cur), g.pitch, out, np, rows, E.c->rank); });
+        E.collective(0, reinterpret_cast<u64*>(out), rows * np * sizeof(W) / 8);
         if (g.cur_owned && g.cur != g.nxt && g.cur != g.alt) E.dfree(g.cur);
-        g.cur = out; g.cur_owned = true; g.pitch = np; g.stride = np * D;
+        g.cur = ow(out); g.cur_owned = true; g.pitch = np; g.stride = np * D;
     }
     void gather_tables() {
         if (sc->kind == LF_COMB_FOLD && sc->dig && sc->applied == 0) throw LfException(LF_ERR_UNSUPPORTED, "sharded FOLD sumcheck needs at least 2 local entries");
@@ -129,9 +135,9 @@ template <class Rg> struct SumcheckDriver {
         if (sc->kind == LF_COMB_FOLD) {
             if (sc->dig && sc->applied == 0) {
                 sc->fh.count = sc->n_f; sc->fh.pitch = pitch_of(n_out); sc->fh.stride = sc->fh.pitch * D; sc->fh.cur = nullptr;
-                sc->fh.cur = pingpong_target(sc->fh, n_out); sc->fh.cur_owned = false;
-                FoldArgs a; for (int l = 0; l < TAU; ++l) a.r[l] = r_sf[l];
-                E.launch("k_fold_digits", [&] { k_fold_digits<Rg><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, sc->n_f), 128, 0, E.st()>>>(sc->dig, sc->dig_pitch, sc->dig_stride, sc->n_f, sc->fh.cur, sc->fh.pitch, sc->fh.stride, n_out, a); });
+                sc->fh.cur = ow(pingpong_target(sc->fh, n_out)); sc->fh.cur_owned = false;
+                FoldArgsT<W> a; for (int l = 0; l < TAU; ++l) a.r[l] = r_sf[l];
+                E.launch("k_fold_digits", [&] { k_fold_digits<Rg><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, sc->n_f), 128, 0, E.st()>>>(sc->dig, sc->dig_pitch, sc->dig_stride, sc->n_f, wp(sc->fh.cur), sc->fh.pitch, sc->fh.stride, n_out, a); });
             } else fold_group(sc->fh, r_sf, n_out);
         }
         sc->len = n_out; sc->applied += 1;
@@ -140,12 +146,12 @@ template <class Rg> struct SumcheckDriver {
     void final_values(u64* out_host) {
         if (sc->len != 1 || sc->sharded) throw LfException(LF_ERR_SUMCHECK_MISUSE, "sumcheck not finished");
         const int total = sc->dense.count + (sc->kind == LF_COMB_FOLD ? sc->n_f : 0);
-        std::vector<u64> tmp;
+        std::vector<W> tmp;
         auto grab = [&](const lf_sumcheck::Group& g, u64* dst) {
             if (!g.count) return;
-            tmp.resize((size_t)g.count * g.stride);
-            E.download_words(g.cur, tmp.size(), tmp.data());
-            for (int k = 0; k < g.count; ++k) for (int l = 0; l < D; ++l) dst[(size_t)k * D + l] = tmp[(size_t)k * g.stride + (size_t)l * g.pitch];
+            tmp.resize((size_t)g.count * g.stride + 8 / sizeof(W));
+            E.download_words(reinterpret_cast<const u64*>(g.cur), ((size_t)g.count * g.stride * sizeof(W) + 7) / 8, reinterpret_cast<u64*>(tmp.data()));
+            for (int k = 0; k < g.count; ++k) for (int l = 0; l < D; ++l) dst[(size_t)k * D + l] = (u64)tmp[(size_t)k * g.stride + (size_t)l * g.pitch];
         };
         grab(sc->dense, out_host);
         if (sc->kind == LF_COMB_FOLD) grab(sc->fh, out_host + (size_t)sc->dense.count * D);
