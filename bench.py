@@ -197,6 +197,8 @@ def main():
     if args.config == "ntt":
         from tools import ntt_bench
         return ntt_bench.main(args, rank, world, local)
+    if args.config == "c3":
+        return run_c3(args, rank, world, local)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -386,6 +388,141 @@ def main():
     pr.free_witness(w_acc); pr.free_witness(w_i); pr.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_c3(args, rank, world, local):
+    """BASELINE configs[2] = SURVEY 8 row C3 as BASELINE.md states it: BabyBear ring (d = 72, packed 4-byte limbs on the device), W = 2^20
+    constraints of the reference's degree-three CCS, BabyBearDP (256, 4, 2, 8), kappa = 8, ONE GPU; a step = Witness::commit (A f, the
+    witness-sized Ajtai commitment, arith.rs:357-362) + LFLinearizationProver::prove (linearization.rs:145-189: 4 sparse mat-vecs,
+    eq table, the degree-4 sumcheck over 5 MLEs of 2^22 entries, evaluations).  `--impl reference`: the CPU restatement on the same
+    configuration (bounded step count)."""
+    if rank != 0:
+        return
+    wl = workload(args.log_w, "c3")
+    RING = wl["ring"]; R = synth.RINGS[RING]
+    if args.impl == "reference":
+        from oracle.pyoracle import Oracle
+        from tools.make_bench_golden import oracle_c3lin
+        orc = Oracle(); cores = os.cpu_count() or 1; orc.set_threads(cores)
+        log_w = args.log_w if args.cpu_sample_log_w is None else min(args.log_w, args.cpu_sample_log_w)
+        t, t0 = [], time.time()
+        while len(t) < max(args.steps, 1) and (not t or (time.time() - t0) * (len(t) + 1) / len(t) < args.cpu_budget_s):
+            wl_s, prob, _, _, ms = oracle_c3lin(orc, log_w); t.append(ms)
+        ms = float(np.mean(t)); value = prob["constraints"] / (ms / 1e3)
+        sample = (f"{len(t)} step(s) of commit + linearization at W=2^{log_w} ({'the same configuration as the product arm' if log_w == args.log_w else 'a slice of the product arm configuration'}; "
+                  f"requested steps={args.steps}, warmup={args.warmup}; {args.cpu_budget_s:.0f} s budget)")
+        print(json.dumps(dict(metric=METRIC, value=value, unit="constraints/s", n_gpus=1, steps=len(t), warmup=0, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                              vs_baseline=None, dtype=DTYPE["c3"], data="synthetic", impl="reference", requested=dict(steps=args.steps, warmup=args.warmup),
+                              config=config_of(wl_s, args, "cpu"), cpu_baseline=dict(value=value, unit="constraints/s", cores=cores, kind="port", sample=sample),
+                              e2e=dict(value=value, unit="constraints/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))), flush=True)
+        return
+    import torch
+    import latticefold_b200 as lf
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    ctx = lf.Context(RING, local)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    t_setup = time.time()
+    prob = synth.bench_instance(wl, 0, 1, ops=ctx)
+    pr = lf.NIFSProver(ctx, prob)
+    prob.pop("A")                                   # 19 GB of host limbs at 2^20: the device copy is all the step needs
+    f = ctx.witness_f_from_w_ccs(RING, prob["w_ccs"], wl["B"], wl["L"])
+    f_pin_t = torch.empty(f.shape, dtype=torch.int64, pin_memory=True); f_pin = f_pin_t.numpy().view(np.uint64); f_pin[...] = f; del f
+    prob["w_i_f"] = f_pin
+    w_i = pr.upload_witness(f_pin)
+    cm = pr.witness_commit(w_i); prob["cm_i_cm"] = np.ascontiguousarray(cm)
+    out_lc, out_pf, out_cm = np.empty(pr.lcccs_words, dtype=np.uint64), np.empty(pr.lin_proof_words(prob), dtype=np.uint64), np.empty_like(cm)
+    t_setup = time.time() - t_setup
+
+    def step_resident():
+        pr.witness_commit(w_i, out=out_cm)
+        prob["cm_i_cm"] = out_cm
+        return pr.linearize_resident(prob, w_i, lf.Transcript(RING), out=(out_lc, out_pf))
+
+    def step_e2e():
+        w = pr.upload_witness(f_pin)
+        pr.witness_commit(w, out=out_cm); prob["cm_i_cm"] = out_cm
+        r = pr.linearize_resident(prob, w, lf.Transcript(RING), out=(out_lc, out_pf))
+        pr.free_witness(w)
+        return r
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream); torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / steps
+
+    for _ in range(args.warmup):
+        step_resident()
+    l0 = ctx.launches()
+    with ClockSampler(local) as clk:
+        ms_res = timed(step_resident, args.steps)
+    launches = (ctx.launches() - l0) // max(args.steps, 1)
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    constraints = prob["constraints"]
+    # checker: the product's LFLinearizationVerifier accepts and reproduces the LCCCS; committed golden digest where one exists;
+    # the commitment is linear (A (f + f) = 2 A f on the device: a size-independent property at the full 2^20)
+    from tests import helpers
+    verify = dict()
+    try:
+        lc_v = lf.linearization_verify(prob, lf.Transcript(RING), out_pf)
+        verify["product_verifier"] = "accept" if np.array_equal(lc_v, out_lc) else "accept, but LCCCS differs"
+    except lf.LfError as e:
+        verify["product_verifier"] = f"REJECT: {e}"
+    try:
+        from oracle.pyoracle import Oracle
+        orc = Oracle()
+        lc_o = orc.linearization_verify({k: v for k, v in prob.items() if k != "w_i_f"}, orc.transcript(RING), out_pf)
+        verify["oracle_verifier"] = "accept" if np.array_equal(lc_o, out_lc) else "accept, but LCCCS differs"
+    except Exception as e:      # noqa: BLE001
+        verify["oracle_verifier"] = f"REJECT: {e}"
+    dg = {"cm": helpers.limb_digest(out_cm), "lcccs": helpers.limb_digest(out_lc), "lin_proof": helpers.limb_digest(out_pf)}
+    gold = helpers.bench_golden().get(helpers.bench_case_key("c3lin", args.log_w)) if os.path.exists(helpers.BENCH_GOLDEN_PATH) else None
+    verify["golden"] = "none committed for this size" if gold is None else ("match" if all(gold[k] == dg[k] for k in dg) else "MISMATCH")
+    verify.update(cm_sha256=dg["cm"], proof_sha256=dg["lin_proof"], lcccs_sha256=dg["lcccs"])
+    verify["verified"] = bool(verify["product_verifier"] == "accept" and verify["oracle_verifier"] == "accept" and verify["golden"] != "MISMATCH")
+    ctx.profile(True); step_resident(); prof = ctx.profile_report(); ctx.profile(False)
+    total_kernel_ms = sum(v[1] for v in prof.values())
+    hbm, peak_src = peaks()
+    ccs = prob["ccs"]; E = R["d"] * 8; n, m, kappa, t = wl["W"] * wl["L"], 1 << ccs["s"], wl["kappa"], ccs["t"]
+    rows = wl["W"] + 2
+    alg = {"k_dot": (kappa * n + n + kappa) * E, "k_sc_generic": (t + 1) * (m + 3 * m // 2) * E, "k_fold": None,
+           "k_spmv": t * (rows * (E + 8) + 2 * rows * E), "k_eq_combine": 2 * m * E, "k_coeff_eval": 4 * n * E, "k_dot_eval": (t + 1) * rows * E}
+    kernels = []
+    for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        b = alg.get(name)
+        if ms >= 0.5 or not kernels:
+            kernels.append(dict(kernel=name, launches=cnt, total_ms=round(ms, 4), algorithmic_bytes=b, achieved_gbs=(b / 1e9) / (ms / 1e3) if b else None,
+                                frac=((b / 1e9) / (ms / 1e3) / hbm) if b else None))
+    top = kernels[0]
+    line = dict(metric=METRIC, value=constraints / (ms_res / 1e3), unit="constraints/s", n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms_res,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype=DTYPE["c3"], data="synthetic",
+                config=dict(config_of(wl, args, "gpu"), step="Witness::commit (A f) + LFLinearizationProver::prove (BASELINE.md C3: commit + linearization sumcheck)",
+                            limbs="packed u32 planes: 288 B per ring element on the device (576 B in reference memory)", setup_s=round(t_setup, 1)),
+                clocks=clk.summary(), gpu_launches=int(launches),
+                e2e=dict(value=constraints / (ms_e2e / 1e3), unit="constraints/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(f_pin.nbytes),
+                         d2h_bytes_per_step=int(out_lc.nbytes + out_pf.nbytes + out_cm.nbytes)),
+                roofline=dict(bound="hbm", kernel=top["kernel"], launches_per_step=top["launches"], avg_launch_ms=top["total_ms"] / top["launches"],
+                              share_of_kernel_time=top["total_ms"] / total_kernel_ms, achieved=top["achieved_gbs"], peak=hbm, unit="GB/s", frac=top["frac"], traffic=None,
+                              peak_source=peak_src, algorithmic_bytes_per_step=top["algorithmic_bytes"], kernels=kernels,
+                              note="algorithmic bytes in the REFERENCE layout (576 B per element); the packed planes move half of that"),
+                kernels_ms={k: dict(launches=v[0], total_ms=round(v[1], 4)) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+                verified=verify["verified"], proof_sha256=verify["proof_sha256"], verify=verify,
+                host=dict(poseidon=lf.Transcript(RING).backend(), cpus=os.cpu_count()))
+    if not args.no_cpu_baseline:
+        from tools.make_bench_golden import oracle_c3lin
+        orc = Oracle(); cores = os.cpu_count() or 1; orc.set_threads(cores)
+        sl = min(args.log_w, 14)
+        _, sprob, _, _, ms_cpu = oracle_c3lin(orc, sl)
+        line["cpu_baseline"] = dict(value=sprob["constraints"] / (ms_cpu / 1e3), unit="constraints/s", cores=cores, kind="port",
+                                    sample=f"commit + linearization of the same workload at W=2^{sl} on {cores} host threads: {ms_cpu:.0f} ms")
+    print(json.dumps(line), flush=True)
+    pr.free_witness(w_i); pr.close(); ctx.close()
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the round's `ncu --set full` captures (profiles/r02*_full.md)

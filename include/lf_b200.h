@@ -229,11 +229,17 @@ lf_status lf_nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, ui
  * NULL) receives the folded instance; a rejected proof returns LF_ERR_SUMCHECK_FAILED / LF_ERR_RECOMPOSED / LF_ERR_INCORRECT_LENGTH
  * with the reason in lf_last_error(NULL).                                                                                       */
 lf_status lf_nifs_verify(const lf_problem* in, lf_transcript* t, const uint64_t* proof, uint64_t* out_lcccs);
+/* LFLinearizationVerifier::verify (nifs/linearization.rs:192-285) on the linearization part of a proof (msgs, v, u), host code.   */
+lf_status lf_linearization_verify(const lf_problem* in, lf_transcript* t, const uint64_t* lin_proof, uint64_t* out_lcccs);
 /* the same step with both witnesses already resident in HBM (bench.py's `value`): witnesses are handles made by
  * lf_prover_upload_witness; the folded witness stays on the device and is returned as a new handle                 */
 typedef struct lf_witness lf_witness;
 lf_status lf_prover_upload_witness(lf_prover* p, const uint64_t* f_host_ntt, lf_witness** out);
 void lf_witness_free(lf_prover* p, lf_witness* w);
+/* LFLinearizationProver::prove on a resident witness, and Witness::commit (arith.rs:357-362) = A f of a resident witness
+ * (BASELINE configs[2]: commit + linearization sumcheck)                                                                     */
+lf_status lf_linearize_resident(lf_prover* p, const lf_problem* in, const lf_witness* w_i, lf_transcript* t, uint64_t* out_lcccs, uint64_t* out_lin_proof);
+lf_status lf_witness_commit(lf_prover* p, const lf_witness* w, uint64_t* out_host);
 lf_status lf_witness_download_f(lf_prover* p, const lf_witness* w, uint64_t* f_host);
 lf_status lf_nifs_prove_resident(lf_prover* p, const lf_problem* in, const lf_witness* w_acc, const lf_witness* w_i,
                                  lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, lf_witness** out_w);

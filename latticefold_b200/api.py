@@ -32,7 +32,7 @@ lf_sumcheck_finish lf_sumcheck_free lf_transcript_create lf_transcript_clone lf_
 lf_transcript_absorb_base lf_transcript_absorb_tag lf_transcript_get_challenge lf_transcript_get_short_challenge
 lf_transcript_permutations lf_host_poseidon_backend lf_rot_lin_combination lf_prover_create lf_prover_free lf_proof_words lf_lcccs_words
 lf_witness_f_from_w_ccs lf_linearize lf_nifs_prove lf_nifs_verify lf_prover_upload_witness lf_witness_free lf_witness_download_f
-lf_nifs_prove_resident lf_prover_last_timings lf_prover_timing_detail
+lf_nifs_prove_resident lf_linearization_verify lf_linearize_resident lf_witness_commit lf_prover_last_timings lf_prover_timing_detail
 lf_ntt_root lf_ntt_plan_create lf_ntt_plan_free lf_ntt_forward_device lf_ntt_inverse_device lf_ntt_forward_host lf_ntt_inverse_host
 lf_ntt_pointwise_mul_device lf_ntt_negacyclic_mul_host""".split()
 
@@ -175,6 +175,9 @@ def lib():
     L.lf_linearize.argtypes = [vp, C.POINTER(Problem), vp, u64p, u64p]
     L.lf_nifs_prove.argtypes = [vp, C.POINTER(Problem), vp, u64p, u64p, u64p]
     L.lf_nifs_verify.argtypes = [C.POINTER(Problem), vp, u64p, u64p]
+    L.lf_linearization_verify.argtypes = [C.POINTER(Problem), vp, u64p, u64p]
+    L.lf_linearize_resident.argtypes = [vp, C.POINTER(Problem), vp, vp, u64p, u64p]
+    L.lf_witness_commit.argtypes = [vp, vp, u64p]
     L.lf_prover_upload_witness.argtypes = [vp, u64p, C.POINTER(vp)]
     L.lf_witness_free.argtypes = [vp, vp]
     L.lf_witness_download_f.argtypes = [vp, vp, u64p]
@@ -592,6 +595,19 @@ def nifs_verify(prob, transcript, proof):
     return lc
 
 
+def linearization_verify(prob, transcript, lin_proof):
+    """LFLinearizationVerifier::verify (nifs/linearization.rs:192-285), host code: returns the LCCCS words, raises LfError on rejection."""
+    L = lib()
+    light = {k: v for k, v in prob.items() if k not in ("A", "w_i_f", "w_acc_f", "acc")}
+    P, keep = make_problem(light)
+    lc = np.empty(int(L.lf_lcccs_words(C.byref(P))), dtype=np.uint64)
+    lin_proof = np.ascontiguousarray(lin_proof, dtype=np.uint64)
+    rc = L.lf_linearization_verify(C.byref(P), transcript.h, ptr(lin_proof), ptr(lc))
+    if rc:
+        raise LfError(rc, L.lf_last_error(None).decode())
+    return lc
+
+
 class NIFSProver:
     """NIFSProver::prove (crates/latticefold/src/nifs.rs:48-103).  The Ajtai matrix and the CCS are uploaded once."""
 
@@ -601,6 +617,7 @@ class NIFSProver:
         h = vp(); ctx.check(ctx.L.lf_prover_create(ctx.h, C.byref(P), C.byref(h))); self.h = h
         self.proof_words = int(ctx.L.lf_proof_words(C.byref(P))); self.lcccs_words = int(ctx.L.lf_lcccs_words(C.byref(P)))
         self.n = prob["n"] // ctx.world      # witness elements held by this rank
+        self.kappa = prob["kappa"]
 
     def close(self):
         if self.h:
@@ -611,6 +628,20 @@ class NIFSProver:
         lc = np.empty(self.lcccs_words, dtype=np.uint64)
         pf = np.empty((ccs["s"] * (ccs["d"] + 2) + self.ctx.tau + ccs["t"]) * self.ctx.d, dtype=np.uint64)
         self.ctx.check(self.ctx.L.lf_linearize(self.h, C.byref(P), transcript.h, ptr(lc), ptr(pf))); return lc, pf
+
+    def lin_proof_words(self, prob):
+        ccs = prob["ccs"]; return (ccs["s"] * (ccs["d"] + 2) + self.ctx.tau + ccs["t"]) * self.ctx.d
+
+    def linearize_resident(self, prob, w_i, transcript, out=None):
+        """LFLinearizationProver::prove on a resident witness (BASELINE configs[2])"""
+        P, keep = make_problem({k: v for k, v in prob.items() if k not in ("w_i_f", "w_acc_f")})
+        lc, pf = out if out is not None else (np.empty(self.lcccs_words, dtype=np.uint64), np.empty(self.lin_proof_words(prob), dtype=np.uint64))
+        self.ctx.check(self.ctx.L.lf_linearize_resident(self.h, C.byref(P), w_i, transcript.h, ptr(lc), ptr(pf))); return lc, pf
+
+    def witness_commit(self, w, out=None):
+        """Witness::commit (arith.rs:357-362): A f of a resident witness"""
+        o = out if out is not None else np.empty((self.kappa, self.ctx.d), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.lf_witness_commit(self.h, w, ptr(o))); return o
 
     def prove(self, prob, transcript, want_f=True, out=None):
         """host inputs -> (proof, folded LCCCS, folded witness f); H2D of both witnesses and D2H of the results inside."""

@@ -200,6 +200,13 @@ lf_status lf_nifs_prove_resident(lf_prover* p, const lf_problem* in, const lf_wi
 lf_status lf_nifs_verify(const lf_problem* in, lf_transcript* t, const uint64_t* proof, uint64_t* out_lcccs) {
     return guard(nullptr, [&] { if (!in || !t || !proof) throw LfException(LF_ERR_INVALID_ARG, "null argument"); ops(in->ring)->nifs_verify(in, t, proof, out_lcccs); });
 }
+lf_status lf_linearization_verify(const lf_problem* in, lf_transcript* t, const uint64_t* lin_proof, uint64_t* out_lcccs) {
+    return guard(nullptr, [&] { if (!in || !t || !lin_proof) throw LfException(LF_ERR_INVALID_ARG, "null argument"); ops(in->ring)->linearization_verify(in, t, lin_proof, out_lcccs); });
+}
+lf_status lf_linearize_resident(lf_prover* p, const lf_problem* in, const lf_witness* w, lf_transcript* t, uint64_t* out_lcccs, uint64_t* out_proof) {
+    return guard(p->ctx, [&] { ops(p->ring)->linearize_resident(p, in, w, t, out_lcccs, out_proof); });
+}
+lf_status lf_witness_commit(lf_prover* p, const lf_witness* w, uint64_t* out_host) { return guard(p->ctx, [&] { ops(p->ring)->witness_commit(p, w, out_host); }); }
 lf_status lf_nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, uint64_t* out_f) {
     return guard(p->ctx, [&] { ops(p->ring)->nifs_prove(p, in, t, out_proof, out_lcccs, out_f); });
 }

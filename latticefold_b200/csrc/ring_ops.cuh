@@ -58,6 +58,9 @@ struct RingOps {
     virtual void nifs_prove_resident(lf_prover* p, const lf_problem* in, const lf_witness* w_acc, const lf_witness* w_i, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, lf_witness** out_w) = 0;
     virtual void nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, uint64_t* out_f) = 0;
     virtual void nifs_verify(const lf_problem* in, lf_transcript* t, const uint64_t* proof, uint64_t* out_lcccs) = 0;
+    virtual void linearization_verify(const lf_problem* in, lf_transcript* t, const uint64_t* lin_proof, uint64_t* out_lcccs) = 0;
+    virtual void linearize_resident(lf_prover* p, const lf_problem* in, const lf_witness* w, lf_transcript* t, uint64_t* out_lcccs, uint64_t* out_proof) = 0;
+    virtual void witness_commit(lf_prover* p, const lf_witness* w, uint64_t* out_host) = 0;
 };
 RingOps* ring_ops_goldilocks();
 RingOps* ring_ops_babybear();
@@ -322,6 +325,24 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         auto lo = pr.linearize(cm, x, w, tr(t)); pr.E.dfree(lo.eq_r.p); pr.free_witness(w);
         Prover<Rg>::put_lcccs(out_lcccs, lo.lc);
         if (out_proof) { u64* q = out_proof; Prover<Rg>::put(q, lo.msgs); Prover<Rg>::put(q, lo.lc.v); Prover<Rg>::put(q, lo.lc.u); }
+    }
+    void linearize_resident(lf_prover* p, const lf_problem* in, const lf_witness* w, lf_transcript* t, uint64_t* out_lcccs, uint64_t* out_proof) override {
+        Prover<Rg> pr(p); pr.E.sync(); pr.E.arena_reset();
+        HV cm = Prover<Rg>::load_canonical(in->cm_i_cm, p->kappa, "cm_i"), x = Prover<Rg>::load_canonical(in->cm_i_x_ccs, p->l, "x_ccs");
+        auto lo = pr.linearize(cm, x, w, tr(t)); pr.E.dfree(lo.eq_r.p);
+        Prover<Rg>::put_lcccs(out_lcccs, lo.lc);
+        if (out_proof) { u64* q = out_proof; Prover<Rg>::put(q, lo.msgs); Prover<Rg>::put(q, lo.lc.v); Prover<Rg>::put(q, lo.lc.u); }
+    }
+    void witness_commit(lf_prover* p, const lf_witness* w, uint64_t* out_host) override {
+        Engine<Rg> E(p->ctx); const lf_ajtai* a = p->A;
+        if (w->n != a->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongWitnessLength(" + std::to_string(w->n) + ", " + std::to_string(a->n) + ")");
+        PL Y; Y.p[0] = wp(w->f); Y.len[0] = a->n;
+        u64* d_out = E.small_dev(a->kappa * Rg::D);
+        E.dot(wp(a->p), a->pitch * Rg::D, a->pitch, (int)a->kappa, nullptr, Y, w->pitch, 1, a->n, d_out);
+        E.download_words(d_out, a->kappa * Rg::D, out_host);
+    }
+    void linearization_verify(const lf_problem* in, lf_transcript* t, const uint64_t* lin_proof, uint64_t* out_lcccs) override {
+        Verifier<Rg> v(*in); LCCCS lc = v.verify_linearization_only(lin_proof, tr(t)); if (out_lcccs) Prover<Rg>::put_lcccs(out_lcccs, lc);
     }
     void nifs_prove_resident(lf_prover* p, const lf_problem* in, const lf_witness* w_acc, const lf_witness* w_i, lf_transcript* t, uint64_t* out_proof, uint64_t* out_lcccs, lf_witness** out_w) override {
         Prover<Rg> pr(p); lf_witness* w = pr.prove(*in, w_acc, w_i, tr(t), out_proof, out_lcccs); if (out_w) *out_w = w; else pr.free_witness(w);

@@ -149,6 +149,15 @@ template <class Rg> struct Verifier {
         return o;
     }
 
+    // LFLinearizationVerifier::verify alone (linearization.rs:192-285): lin_proof = msgs | v | u
+    LCCCS verify_linearization_only(const u64* lin_proof, Transcript<Rg>& T) const {
+        const size_t words = ((size_t)in.s * (in.d + 2) + TAU + in.t) * D;
+        for (size_t i = 0; i < words; ++i) if (lin_proof[i] >= F::P) throw LfException(LF_ERR_INVALID_ARG, "non-canonical field element in the proof");
+        HV cm_i = Prover<Rg>::load_canonical(in.cm_i_cm, in.kappa, "cm_i"), x_ccs = Prover<Rg>::load_canonical(in.cm_i_x_ccs, in.l, "x_ccs");
+        const u64* p = lin_proof; const u64* msgs = p; p += (size_t)in.s * (in.d + 2) * D;
+        HV v = take(p, TAU), u = take(p, in.t);
+        return verify_linearization(cm_i, x_ccs, msgs, v, u, T);
+    }
     // the whole step; throws LfException(LF_ERR_SUMCHECK_FAILED / LF_ERR_RECOMPOSED / LF_ERR_INCORRECT_LENGTH / ...) on rejection
     LCCCS verify(const u64* proof, Transcript<Rg>& T) const {
         { size_t want = std::max((size_t)(in.n_ccs - in.l - 1) * (size_t)in.L, (size_t)in.m), p2 = 1; while (p2 < want) p2 <<= 1;      // nifs.rs:165-173

@@ -178,6 +178,12 @@ def bench_instance(wl, rank, world, ops=None):
     n = wl["W"] * wl["L"]
     w_ccs = make_witness(ring, wl["W"], wl["kind"], seed)
     ccs = make_ccs(ring, wl["W"], wl["L"], wl["kind"], w_ccs, 1, wl.get("degree", 2), ops)
-    A = uniform_field(R["p"], wl["kappa"] * (n // world) * R["d"], seed + 7919 * (rank + 1)).reshape(wl["kappa"], n // world, R["d"])
+    row = (n // world) * R["d"]
+    if wl["kappa"] * row <= 1 << 28:
+        A = uniform_field(R["p"], wl["kappa"] * row, seed + 7919 * (rank + 1)).reshape(wl["kappa"], n // world, R["d"])
+    else:       # large matrices row by row (bounded temporaries: configs[2] at 2^20 is 19 GB of host limbs): row i seeded on its own
+        A = np.empty((wl["kappa"], n // world, R["d"]), dtype=np.uint64)
+        for i in range(wl["kappa"]):
+            A[i] = uniform_field(R["p"], row, seed + 7919 * (rank + 1) + 104729 * (i + 1)).reshape(n // world, R["d"])
     return dict(ring=ring, B=wl["B"], L=wl["L"], b=wl["b"], K=wl["K"], kappa=wl["kappa"], n=n, W=wl["W"], A=A, ccs=ccs, w_ccs=w_ccs,
                 cm_i_x_ccs=one(ring, 1), constraints=1 + wl["W"] + 1, kind=wl["kind"])

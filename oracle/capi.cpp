@@ -200,6 +200,16 @@ int lfo_linearize(const lfo_problem* P, void* tr, u64* out_lcccs, u64* out_proof
         if (out_proof) { p = out_proof; put(p, pf.sumcheck.msgs); put(p, pf.v); put(p, pf.u); }
     });
 }
+// LFLinearizationVerifier::verify (nifs/linearization.rs:192-285) on the linearization part of a proof (msgs, v, u): returns 0 when accepted
+int lfo_linearization_verify(const lfo_problem* P, void* tr, const u64* lin_proof, u64* out_lcccs) {
+    return guard([&] {
+        const RingParams& R = ring(P->ring); DecompParams dp; CCS ccs; Ajtai sch; LCCCS acc; CCCS cmi; load_problem(*P, R, dp, ccs, sch, acc, cmi);
+        LinearizationProof pf; const u64* p = lin_proof; const size_t d = R.d;
+        pf.sumcheck.nvars = (int)P->s; pf.sumcheck.degree = (int)P->d + 1; get(p, pf.sumcheck.msgs, P->s * (P->d + 2) * d); get(p, pf.v, R.tau * d); get(p, pf.u, P->t * d);
+        LCCCS out; linearization_verify(R, cmi, pf, *(Transcript*)tr, ccs, out);
+        if (out_lcccs) { u64* q = out_lcccs; put_lcccs(q, out); }
+    });
+}
 // NIFSProver::prove (nifs.rs:48-103).  out_proof: lfo_proof_words; out_lcccs: lfo_lcccs_words; out_f: n x d (folded witness, NTT form)
 // timing_ms (optional, 4 doubles): linearization, decomposition x2, folding, total
 int lfo_nifs_prove(const lfo_problem* P, void* tr, u64* out_proof, u64* out_lcccs, u64* out_f, double* timing_ms) {

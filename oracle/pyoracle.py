@@ -117,6 +117,7 @@ class Oracle:
                                          C.c_int, u64p, i32p, i32p, C.c_int, C.c_int, u64p, u64p, u64p, u64p]
         L.lfo_sumcheck_verify.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, u64p, u64p, u64p, u64p]
         L.lfo_linearize.argtypes = [C.POINTER(Problem), C.c_void_p, u64p, u64p]
+        L.lfo_linearization_verify.argtypes = [C.POINTER(Problem), C.c_void_p, u64p, u64p]
         L.lfo_nifs_prove.argtypes = [C.POINTER(Problem), C.c_void_p, u64p, u64p, u64p, C.POINTER(C.c_double)]
         L.lfo_nifs_verify.argtypes = [C.POINTER(Problem), C.c_void_p, u64p, u64p]
         L.lfo_proof_words.argtypes = [C.POINTER(Problem)]
@@ -258,6 +259,12 @@ class Oracle:
         pf = np.empty((ccs["s"] * (ccs["d"] + 2) + tau + ccs["t"]) * d, dtype=np.uint64)
         self.check(self.lib.lfo_linearize(C.byref(P), tr.h, ptr(lc), ptr(pf)))
         return lc, pf
+
+    def linearization_verify(self, prob, tr, lin_proof):
+        P, keep = make_problem(prob)
+        lc = np.empty(self.lib.lfo_lcccs_words(C.byref(P)), dtype=np.uint64)
+        self.check(self.lib.lfo_linearization_verify(C.byref(P), tr.h, ptr(np.ascontiguousarray(lin_proof)), ptr(lc)))
+        return lc
 
     def nifs_prove(self, prob, tr, want_f=True):
         P, keep = make_problem(prob)

@@ -66,3 +66,32 @@ def test_bench_step_matches_committed_golden(gpu, config, log_w):
         pr.close()
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("log_w", [10, 12, 16, 18])
+def test_c3_commit_and_linearization_match_committed_golden(gpu, log_w):
+    """BASELINE configs[2] as bench.py --config c3 runs it (BabyBear ring, packed 4-byte limb planes, degree-three CCS): the witness
+    commitment A f and LFLinearizationProver::prove against the digests of the CPU oracle on the same instance, through the
+    resident-witness entry points, plus the product's LFLinearizationVerifier"""
+    key = helpers.bench_case_key("c3lin", log_w)
+    gold = helpers.bench_golden()
+    if key not in gold:
+        pytest.skip("no committed digest for " + key)
+    wl = synth.bench_workload("c3", log_w); ring = wl["ring"]
+    c = gpu.Context(ring, 0)
+    try:
+        prob = synth.bench_instance(wl, 0, 1, ops=c)
+        pr = gpu.NIFSProver(c, prob)
+        f = c.witness_f_from_w_ccs(ring, prob["w_ccs"], wl["B"], wl["L"])
+        w = pr.upload_witness(f)
+        cm = pr.witness_commit(w); prob["cm_i_cm"] = np.ascontiguousarray(cm)
+        lc, pf = pr.linearize_resident(prob, w, gpu.Transcript(ring))
+        got = {"cm": helpers.limb_digest(cm), "lcccs": helpers.limb_digest(lc), "lin_proof": helpers.limb_digest(pf), "lin_proof_words": int(pf.size)}
+        assert got == {k: gold[key][k] for k in got}
+        assert np.array_equal(gpu.linearization_verify(prob, gpu.Transcript(ring), pf), lc)
+        bad = pf.copy(); bad[5] = (int(bad[5]) + 1) % synth.RINGS[ring]["p"]
+        with pytest.raises(gpu.LfError):
+            gpu.linearization_verify(prob, gpu.Transcript(ring), bad)
+        pr.free_witness(w); pr.close()
+    finally:
+        c.close()

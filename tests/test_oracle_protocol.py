@@ -101,3 +101,21 @@ def test_bench_digests_match_committed_golden(oracle, config, log_w):
     gold = helpers.bench_golden()[helpers.bench_case_key(config, log_w)]
     got = helpers.step_digests(proof, lc, f)
     assert all(got[k] == gold[k] for k in ("proof", "lcccs", "witness", "proof_words"))
+
+
+def test_c3lin_digest_matches_committed_golden(oracle):
+    """commit + linearization of the BASELINE configs[2] workload (small size) still hashes to tests/golden/bench_digests.json, and
+    the oracle's and the product's LFLinearizationVerifier accept it"""
+    import latticefold_b200 as lf
+    from tools.make_bench_golden import oracle_c3lin, c3lin_digests
+    wl, prob, lc, pf, _ = oracle_c3lin(oracle, 10)
+    gold = helpers.bench_golden()[helpers.bench_case_key("c3lin", 10)]
+    got = c3lin_digests(prob["cm_i_cm"], lc, pf)
+    assert all(got[k] == gold[k] for k in got)
+    assert np.array_equal(oracle.linearization_verify(prob, oracle.transcript(wl["ring"]), pf), lc)
+    assert np.array_equal(lf.linearization_verify(prob, lf.Transcript(wl["ring"]), pf), lc)
+    bad = pf.copy(); bad[3] = (int(bad[3]) + 1) % synth.RINGS[wl["ring"]]["p"]
+    with pytest.raises(OracleError):
+        oracle.linearization_verify(prob, oracle.transcript(wl["ring"]), bad)
+    with pytest.raises(lf.LfError):
+        lf.linearization_verify(prob, lf.Transcript(wl["ring"]), bad)
