@@ -361,6 +361,7 @@ template <class Rg> struct SlotField {
     static LF_HD_CALL void sqr(u64* c, const u64* a) { u64 t[Rg::TAU];
 #pragma unroll
         for (int k = 0; k < TAU; ++k) t[k] = a[k]; mul(c, a, t); }
+    static LF_HD void mul_inl(u64* c, const u64* a, const u64* b) { mul(c, a, b); }
     static LF_HD void add(u64* c, const u64* a, const u64* b) {
 #pragma unroll
         for (int i = 0; i < TAU; ++i) c[i] = F::add(a[i], b[i]); }
@@ -388,6 +389,7 @@ template <> struct SlotField<GoldilocksRing> {
         x.clear(); x.mac(a[0], b[2]); x.mac(a[1], b[1]); x.mac(a[2], b[0]); c2 = F::reduce192(x);
         c[0] = c0; c[1] = c1; c[2] = c2;
     }
+    static LF_HD void mul_inl(u64* c, const u64* a, const u64* b) { mul(c, a, b); }
     static LF_HD void sqr(u64* c, const u64* a) {
         u64 a1n = F::mul_nu(a[1]), a2n = F::mul_nu(a[2]);
         u64 d1 = F::add(a[1], a[1]), d2 = F::add(a[2], a[2]);
@@ -424,6 +426,65 @@ template <> struct SlotField<GoldilocksRing> {
     static LF_HD DotPrepped dot_prep(const u64* x) { return prep(x); }
     static LF_HD void dot_mac(Acc192* acc, const u64* y, const DotPrepped& x) { mac(acc, y, x); }
     static LF_HD void dot_finish(u64* c, const Acc192* acc) { for (int i = 0; i < 3; ++i) c[i] = F::reduce192(acc[i]); }
+};
+
+// BabyBear ring: slot field Fq9 = Fq[Y]/(Y^9 - nu).  Same interface as the generic SlotField, but the 81 partial products of a
+// multiplication are straight-line lazily reduced MACs (one IMAD.WIDE + one carry add each, 9 per output limb, one 96-bit accumulator
+// live at a time) with the fixed operand's nu-multiples prepared once, and the accumulating dot products (k_dot) keep the 17
+// coefficients of the unreduced product so that their inner loop has no multiplication by nu at all.  The functions stay real calls
+// (LF_HD_CALL): the generic sumcheck kernel instantiates them at many call sites.
+template <> struct SlotField<BabyBearRing> {
+    typedef BabyBear F;
+    static constexpr int TAU = 9;
+    // element arrays may be u64 or packed u32 words (template parameters below): values are < 2^31 either way
+    struct Prepped { u32 b[9], bn[9]; };      // b and nu * b (bn[0] unused)
+    template <class TB> static LF_HD Prepped prep(const TB* b) { Prepped p;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { p.b[i] = (u32)b[i]; p.bn[i] = (u32)F::mul_nu((u64)b[i]); } return p; }
+    template <class TA> static LF_HD void mac(F::Acc* acc, const TA* a, const Prepped& p) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+            for (int i = 0; i < 9; ++i) acc[k].mac((u64)a[i], i <= k ? (u64)p.b[k - i] : (u64)p.bn[k + 9 - i]);
+    }
+    template <class TC, class TA> static LF_HD void mul_prepped_inl(TC* c, const TA* a, const Prepped& p) {
+        u32 r[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { F::Acc x; x.clear();
+#pragma unroll
+            for (int i = 0; i < 9; ++i) x.mac((u64)a[i], i <= k ? (u64)p.b[k - i] : (u64)p.bn[k + 9 - i]);
+            r[k] = (u32)F::reduce(x); }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) c[k] = (TC)r[k];
+    }
+    template <class TC, class TA, class TB> static LF_HD void mul_inl(TC* c, const TA* a, const TB* b) { const Prepped p = prep(b); mul_prepped_inl(c, a, p); }
+    static LF_HD_CALL void mul_prepped(u64* c, const u64* a, const Prepped& p) { mul_prepped_inl(c, a, p); }
+    static LF_HD_CALL void mul(u64* c, const u64* a, const u64* b) { const Prepped p = prep(b); mul_prepped_inl(c, a, p); }
+    static LF_HD_CALL void sqr(u64* c, const u64* a) { const Prepped p = prep(a); mul_prepped_inl(c, a, p); }
+    template <class TC, class TA, class TB> static LF_HD void add(TC* c, const TA* a, const TB* b) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) c[i] = (TC)F::add((u64)a[i], (u64)b[i]); }
+    template <class TC, class TA, class TB> static LF_HD void sub(TC* c, const TA* a, const TB* b) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) c[i] = (TC)F::sub((u64)a[i], (u64)b[i]); }
+    // accumulating dot products: the 17 coefficients of the unreduced product, folded with nu once at the end
+    static constexpr int NDOT = 17;
+    struct DotPrepped { u32 x[9]; };
+    static LF_HD DotPrepped dot_prep(const u64* x) { DotPrepped p;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) p.x[i] = (u32)x[i]; return p; }
+    static LF_HD void dot_mac(F::Acc* acc, const u64* y, const DotPrepped& x) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = 0; j < 9; ++j) acc[i + j].mac(y[i], (u64)x.x[j]);
+    }
+    static LF_HD void dot_finish(u64* c, F::Acc* acc) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const u64 hi = F::reduce(acc[k + 9]); acc[k].mac(hi, F::NU); }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) c[k] = F::reduce(acc[k]);
+    }
 };
 
 }  // namespace lf

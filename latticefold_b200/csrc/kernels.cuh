@@ -659,6 +659,82 @@ k_sc_generic(const ScGenericArgsT<typename Rg::W> a) {
             for (int l = 0; l < TAU; ++l) a.partial[((size_t)blockIdx.x * (a.deg + 1) + e) * Rg::D + slot * TAU + l] = v[e * TAU + l];
 }
 
+// The same round evaluation with one thread per (pair, evaluation point): (deg+1) times the parallelism and a (deg+1)-th of the
+// live state per thread -- the wide slot field of the BabyBear ring (9 limbs: 45 table words per point) spilled and ran at two warps
+// per scheduler in the one-thread-per-pair form above, and the late, small rounds of every ring are latency bound.  Thread
+// (pair b, point e) forms v_k(e) = v_k(2b) + e (v_k(2b+1) - v_k(2b)) for every table and evaluates the combination once.
+template <class Rg, int NM> __global__ void __launch_bounds__(128)
+k_sc_points(const ScGenericArgsT<typename Rg::W> a) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef typename Rg::W E; constexpr int TAU = Rg::TAU;
+    __shared__ u64 red[TAU * 128];
+    const int slot = blockIdx.y, npts = a.deg + 1, ppb = blockDim.x / npts;
+    const int e = threadIdx.x % npts, pl = threadIdx.x / npts;
+    E cf[SC_MAX_TERMS][TAU];
+#pragma unroll
+    for (int t = 0; t < SC_MAX_TERMS; ++t)
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) cf[t][l] = t < a.n_terms ? (E)a.coef[(size_t)t * Rg::D + slot * TAU + l] : (E)0;
+    E ev[TAU];
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) ev[l] = 0;
+    if (pl < ppb)
+    for (size_t b = (size_t)blockIdx.x * ppb + pl; b < a.n_pairs; b += (size_t)gridDim.x * ppb) {
+        E val[NM][TAU];
+#pragma unroll
+        for (int k = 0; k < NM; ++k) {
+            if (k >= a.n_mles) break;
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) {
+                u64 v0, v1; ld_pair(a.mle[k] + (size_t)(slot * TAU + l) * a.pitch + 2 * b, v0, v1);
+                const u64 st = F::sub(v1, v0); u64 x = v0;
+#pragma unroll
+                for (int i = 0; i < SC_MAX_DEG; ++i) if (i < e) x = F::add(x, st);
+                val[k][l] = (E)x;
+            }
+        }
+        E res[TAU];
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) res[l] = 0;
+#pragma unroll 1
+        for (int t = 0; t < a.n_terms; ++t) {
+            E term[TAU];
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) term[l] = cf[t][l];
+#pragma unroll 1
+            for (int f = 0; f < a.term_len[t]; ++f) {
+                const int idx = a.term_idx[t][f];
+                E fac[TAU];
+#pragma unroll
+                for (int k = 0; k < NM; ++k) if (k == idx) {
+#pragma unroll
+                    for (int l = 0; l < TAU; ++l) fac[l] = val[k][l];
+                }
+                SF::mul_inl(term, term, fac);
+            }
+            SF::add(res, res, term);
+        }
+        if (a.lin) {
+            E last[TAU];
+#pragma unroll
+            for (int k = 0; k < NM; ++k) if (k == a.n_mles - 1) {
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) last[l] = val[k][l];
+            }
+            SF::mul_inl(res, res, last);
+        }
+        SF::add(ev, ev, res);
+    }
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) red[l * 128 + threadIdx.x] = (u64)ev[l];
+    __syncthreads();
+    if (threadIdx.x < npts * TAU) {
+        const int pe = threadIdx.x / TAU, l = threadIdx.x % TAU;
+        u64 acc = 0;
+        for (int q = 0; q < ppb; ++q) acc = F::add(acc, red[l * 128 + q * npts + pe]);
+        a.partial[((size_t)blockIdx.x * npts + pe) * Rg::D + slot * TAU + l] = acc;
+    }
+}
+
 // ---- FOLD combination function, b = 2 (folding/utils.rs:273-325):
 //   g(x) = v0 v1 + v2 v3 + v4 * h(x),   h = sum_{k<2K} sum_{d<tau} mu_k^{d+1} (f_{k,d}^3 - f_{k,d})
 // h is a cubic along the line through a pair, so 4 points determine it; the degree-4 message needs 5 points of g.

@@ -71,18 +71,23 @@ template <class Rg> struct SumcheckDriver {
             if (round1) E.launch("k_fold_sc_round1", [&] { k_fold_sc_round1<Rg><<<dim3(gx1, S), 128, 0, E.st()>>>(a); });
             else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(gx2, S), 128, 0, E.st()>>>(a); });
         } else {
-            nblk = (unsigned)std::min<size_t>((n_pairs + 127) / 128, 148 * 8); partial = E.partial_dev((size_t)nblk * ne * D);
+            // one thread per (pair, evaluation point): see k_sc_points
+            const int ppb = 128 / ne;
+            nblk = (unsigned)std::min<size_t>((n_pairs + ppb - 1) / ppb, 148 * 16); partial = E.partial_dev((size_t)nblk * ne * D);
             ScGenericArgsT<W> a; const auto& gen = sc->gen;
             a.n_mles = gen.n_mles; a.deg = gen.deg; a.n_terms = gen.n_terms; a.lin = gen.lin;
             for (int t = 0; t < SC_MAX_TERMS; ++t) { a.term_len[t] = gen.term_len[t]; for (int f = 0; f < SC_MAX_FACTORS; ++f) a.term_idx[t][f] = gen.term_idx[t][f]; }
             a.pitch = sc->dense.pitch; a.n_pairs = n_pairs; a.partial = partial; a.coef = sc->d_coef;
             for (int k = 0; k < a.n_mles; ++k) a.mle[k] = wp(sc->dense.cur) + (size_t)k * sc->dense.stride;
             dim3 g(nblk, S);
-            for (int k = a.n_mles; k < SC_MAX_MLES; ++k) a.mle[k] = a.mle[0];   // padding tables are loaded but never referenced by a term
+            for (int k = a.n_mles; k < SC_MAX_MLES; ++k) a.mle[k] = a.mle[0];
+            const bool legacy = std::getenv("LF_SC_LEGACY") != nullptr;       // the one-thread-per-pair kernel, kept for A/B measurements
             E.launch("k_sc_generic", [&] {
-                if (a.n_mles <= 2) k_sc_generic<Rg, 2><<<g, 128, 0, E.st()>>>(a);
-                else if (a.n_mles <= 4) k_sc_generic<Rg, 4><<<g, 128, 0, E.st()>>>(a);
-                else k_sc_generic<Rg, 8><<<g, 128, 0, E.st()>>>(a);
+                if (legacy) { if (a.n_mles <= 2) k_sc_generic<Rg, 2><<<g, 128, 0, E.st()>>>(a); else if (a.n_mles <= 4) k_sc_generic<Rg, 4><<<g, 128, 0, E.st()>>>(a); else k_sc_generic<Rg, 8><<<g, 128, 0, E.st()>>>(a); }
+                else if (a.n_mles <= 2) k_sc_points<Rg, 2><<<g, 128, 0, E.st()>>>(a);
+                else if (a.n_mles <= 4) k_sc_points<Rg, 4><<<g, 128, 0, E.st()>>>(a);
+                else if (a.n_mles <= 5) k_sc_points<Rg, 5><<<g, 128, 0, E.st()>>>(a);      // the degree-three CCS: four matrices + eq
+                else k_sc_points<Rg, 8><<<g, 128, 0, E.st()>>>(a);
             });
         }
         u64* d_out = E.small_dev((size_t)ne * D);
