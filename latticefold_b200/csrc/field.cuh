@@ -220,6 +220,28 @@ struct Goldilocks {
 #endif
     };
     static LF_HD u64 reduce(const Sum& a) { return reduce128(a.lo(), a.hi()); }
+    // slim accumulator for sums of (small multiplier) x (field element): 96 bits in three registers; holds 2^20 terms with
+    // multipliers below 2^12 (the digit-weighted sums of the FOLD sumcheck's first two rounds)
+    struct AccS {
+#if defined(__CUDA_ARCH__)
+        u32 e0, e1, e2;
+        LF_HD void clear() { e0 = e1 = e2 = 0; }
+        LF_HD void mac_small(u32 a, u64 b) {
+            asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;\n\t"
+                "mad.lo.cc.u32 %1, %3, %5, %1;\n\tmadc.hi.u32 %2, %3, %5, %2;"
+                : "+r"(e0), "+r"(e1), "+r"(e2) : "r"(a), "r"((u32)b), "r"((u32)(b >> 32)));
+        }
+        LF_HD u64 lo() const { return ((u64)e1 << 32) | e0; }
+        LF_HD u64 hi() const { return e2; }
+#else
+        u128 v;
+        LF_HD void clear() { v = 0; }
+        LF_HD void mac_small(u32 a, u64 b) { v += (u128)a * b; }
+        LF_HD u64 lo() const { return (u64)v; }
+        LF_HD u64 hi() const { return (u64)(v >> 64); }
+#endif
+    };
+    static LF_HD u64 reduce(const AccS& a) { return reduce128(a.lo(), a.hi()); }
     static LF_HD u64 mul_nu(u64 a) { return reduce128(a << NU_SHIFT, a >> (64 - NU_SHIFT)); }
     // (lo + hi * 2^32) mod p for lo, hi < 2^40: recombination of the split-limb all-reduce
     static LF_HD u64 from_split(u64 lo, u64 hi) { return add(reduce128(lo, 0), reduce128(hi << 32, hi >> 32)); }
@@ -243,7 +265,7 @@ template <u64 P_, u64 NU_, bool SMALL> struct ModField {
     static LF_HD u64 sqr(u64 a) { return mul(a, a); }
     static LF_HD u64 mul_nu(u64 a) { return mul(a, NU); }
     struct Acc { u64 v; LF_HD void clear() { v = 0; } LF_HD void mac(u64 a, u64 b) { v = ModField::add(v, ModField::mul(a, b)); } LF_HD void mac_small(u32 a, u64 b) { mac((u64)a, b); } LF_HD void add(u64 a) { v = ModField::add(v, a % P); } };
-    typedef Acc Sum;
+    typedef Acc Sum; typedef Acc AccS;
     static LF_HD u64 reduce(const Acc& a) { return a.v; }
     static LF_HD_CALL u64 reduce128(u64 lo, u64 hi) { return (u64)((((u128)hi << 64) | lo) % P); }
     static LF_HD_CALL u64 from_split(u64 lo, u64 hi) { return (u64)((((u128)hi << 32) + lo) % P); }
@@ -266,7 +288,28 @@ struct BabyBear {
     static LF_HD u64 add(u64 a, u64 b) { u64 s = a + b; if (s >= P) s -= P; return s; }
     static LF_HD u64 sub(u64 a, u64 b) { return a >= b ? a - b : a + (P - b); }
     static LF_HD u64 neg(u64 a) { return a ? P - a : 0; }
-    static LF_HD u64 mul(u64 a, u64 b) { return (a * b) % P; }
+    // x mod p for any 64-bit x without a 64-bit division or multiply-high (the compiler's `x % P` is a 64 x 64 multiply-high on
+    // 32-bit pipes): the upper word is brought below p, folded with 2^32 = 2^28 - 2 (mod p) into y < 2^60, and a Barrett quotient
+    // estimate floor((y >> 28) * floor(2^62 / p) / 2^34) -- one 32-bit multiply-high, off by at most one -- leaves a 32-bit remainder.
+    static constexpr u32 M62 = (u32)(((u128)1 << 62) / P);
+    static LF_HD u64 red60(u64 y) {
+        const u32 t = (u32)(y >> 28);
+#if defined(__CUDA_ARCH__)
+        const u32 q = __umulhi(t, M62) >> 2;
+#else
+        const u32 q = (u32)(((u64)t * M62) >> 34);
+#endif
+        u32 r = (u32)y - q * (u32)P;
+        if (r >= (u32)P) r -= (u32)P;
+        return r;
+    }
+    static LF_HD u64 red64(u64 x) {
+        u32 xh = (u32)(x >> 32);
+        if (xh >= 2 * (u32)P) xh -= 2 * (u32)P;
+        if (xh >= (u32)P) xh -= (u32)P;
+        return red60((u64)xh * (u32)C32 + (u32)x);
+    }
+    static LF_HD u64 mul(u64 a, u64 b) { const u64 x = a * b; return red60((x >> 32) * (u32)C32 + (u32)x); }      // a, b < p: upper word < 2^30
     static LF_HD u64 sqr(u64 a) { return mul(a, a); }
     static LF_HD u64 mul_nu(u64 a) { return mul(a, NU); }
     struct Acc {
@@ -278,7 +321,7 @@ struct BabyBear {
         }
         LF_HD void mac_small(u32 a, u64 b) { mac((u64)a, b); }
         LF_HD void add(u64 a) { asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+r"(e0), "+r"(e1), "+r"(e2) : "r"((u32)a), "r"((u32)(a >> 32))); }
-        LF_HD u64 fold() const { return ((u64)e2 * C64 + (u64)e1 * C32 + e0) % P; }      // < 2^61 + 2^60 + 2^32
+        LF_HD u64 fold() const { return BabyBear::red64((u64)e2 * C64 + (u64)e1 * C32 + e0); }      // < 2^63 + 2^60 + 2^32
 #else
         u128 v;
         LF_HD void clear() { v = 0; }
@@ -288,7 +331,7 @@ struct BabyBear {
         LF_HD u64 fold() const { return (u64)(v % P); }
 #endif
     };
-    typedef Acc Sum;
+    typedef Acc Sum; typedef Acc AccS;
     static LF_HD u64 reduce(const Acc& a) { return a.fold(); }
     static LF_HD u64 reduce128(u64 lo, u64 hi) { return (u64)((((u128)hi << 64) | lo) % P); }
     static LF_HD u64 from_split(u64 lo, u64 hi) { return (u64)((((u128)hi << 32) + lo) % P); }

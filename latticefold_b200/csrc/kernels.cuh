@@ -748,6 +748,7 @@ template <class W> struct FoldScArgsT {
     const int8_t* dig; size_t dig_pitch, dig_stride;
     // rounds >= 2: slot-field tables, f-hat (k,d) at fh + (k*tau+d) * fh_stride
     const W* fh; size_t fh_pitch, fh_stride;
+    u64 r1[16];                                             // round 2 from digits: the first challenge (TAU limbs)
 };
 template <class Rg, bool WITH_PRODUCTS = true> __device__ __forceinline__ void fold_sc_tail(const FoldScArgsT<typename Rg::W>& a, size_t b, bool active, int slot, const u64 (*h)[Rg::TAU] /* h(0..4) */, u64* red, size_t partial_block = ~(size_t)0, bool rt_products = true) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
@@ -849,6 +850,88 @@ template <class Rg> __global__ void k_fold_digits(const int8_t* __restrict__ dig
     typename Rg::W* o = out + (size_t)kd * out_stride;
 #pragma unroll
     for (int l = 0; l < TAU; ++l) { u64 v = F::mul(st, r.r[l]); if (l == 0) v = F::add(v, d0); o[(size_t)(slot * TAU + l) * out_pitch + b] = (typename Rg::W)v; }
+}
+// Round 2 straight from the digits.  After the first challenge r an f-hat entry is T1[i] = d[2i] + r (d[2i+1] - d[2i]), so along the
+// line through the pair (T1[2b], T1[2b+1]) the value at an integer point X is f = P(X) + r Q(X) with small INTEGERS
+//   P = a0 + X (a1 - a0),  Q = e0 + X (e1 - e0),    a0 = d[4b], e0 = d[4b+1] - d[4b], a1 = d[4b+2], e1 = d[4b+3] - d[4b+2],
+// and  f^3 - f = (P^3 - P) + r Q (3 P^2 - 1) + r^2 3 P Q^2 + r^3 Q^3.   Summed over the tables with the weights mu this is
+//   h(X) = S0 + r S1 + r^2 S2 + r^3 S3,   S_j = sum_kd mu_kd c_j(kd, X)   with |c_j| < 2048,
+// i.e. four sums of mu with small integer weights per point -- two-multiply MACs on 96-bit accumulators, no slot-field product per
+// table -- instead of the 66 full multiply-accumulates per table of the general round kernel, and the 2.4 GB of T1 tables are never
+// written or read.  Four lanes per pair take the points X = 0..3 (h is a cubic: h(4) follows from its finite differences).
+template <class Rg> __global__ void __launch_bounds__(128)
+k_fold_sc_round2(const FoldScArgsT<typename Rg::W> a) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU, S = Rg::S;
+    __shared__ u64 red[5 * TAU * 32];
+    __shared__ u64 s_mu[MAX_MU * TAU];
+    __shared__ u64 s_corr[TAU];                              // 2048 * sum of all mu
+    for (int i = threadIdx.x; i < a.n_f * TAU; i += blockDim.x) s_mu[i] = a.mu_pow[i];
+    __syncthreads();
+    if (threadIdx.x < TAU) { typename F::Sum sm; sm.clear(); for (int kd = 0; kd < a.n_f; ++kd) sm.add(s_mu[kd * TAU + threadIdx.x]); s_corr[threadIdx.x] = F::mul(F::reduce(sm), 2048); }
+    __syncthreads();
+    const int slot = blockIdx.y, X = threadIdx.x & 3;
+    const size_t b = (size_t)blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2); const bool active = b < a.n_pairs;
+    u64 hx[TAU];
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) hx[l] = 0;
+    if (active) {
+        typename F::AccS acc[4][TAU];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) acc[j][l].clear();
+#pragma unroll 2
+        for (int kd = 0; kd < a.n_f; ++kd) {
+            const int k = kd / TAU, d = kd - k * TAU;
+            const char4 dd = *reinterpret_cast<const char4*>(a.dig + (size_t)k * a.dig_stride + (size_t)(d * S + slot) * a.dig_pitch + 4 * b);
+            const int a0 = dd.x, e0 = dd.y - dd.x, a1 = dd.z, e1 = dd.w - dd.z;
+            const int P = a0 + X * (a1 - a0), Q = e0 + X * (e1 - e0);
+            const u32 c0 = (u32)(P * P * P - P + 2048), c1 = (u32)(Q * (3 * P * P - 1) + 2048), c2 = (u32)(3 * P * Q * Q + 2048), c3 = (u32)(Q * Q * Q + 2048);
+            const u64* mu = &s_mu[kd * TAU];
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) { const u64 m = mu[l]; acc[0][l].mac_small(c0, m); acc[1][l].mac_small(c1, m); acc[2][l].mac_small(c2, m); acc[3][l].mac_small(c3, m); }
+        }
+        u64 sj[4][TAU];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) sj[j][l] = F::sub(F::reduce(acc[j][l]), s_corr[l]);
+        // Horner in r
+        SF::mul(hx, sj[3], a.r1); SF::add(hx, hx, sj[2]); SF::mul(hx, hx, a.r1); SF::add(hx, hx, sj[1]); SF::mul(hx, hx, a.r1); SF::add(hx, hx, sj[0]);
+    }
+    // lane X = 0 of every quad gathers h(1), h(2), h(3) and extrapolates h(4) = 4 h(3) - 6 h(2) + 4 h(1) - h(0)
+    u64 h[5][TAU];
+    const int base = (threadIdx.x & 31) & ~3;
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) {
+        const u64 h0 = hx[l], h1 = __shfl_sync(0xffffffffu, hx[l], base + 1), h2 = __shfl_sync(0xffffffffu, hx[l], base + 2), h3 = __shfl_sync(0xffffffffu, hx[l], base + 3);
+        h[0][l] = h0; h[1][l] = h1; h[2][l] = h2; h[3][l] = h3;
+        const u64 t31 = F::add(h3, h1), t31x2 = F::add(t31, t31), t31x4 = F::add(t31x2, t31x2), h2x2 = F::add(h2, h2), h2x6 = F::add(F::add(h2x2, h2x2), h2x2);
+        h[4][l] = F::sub(F::sub(t31x4, h2x6), h0);
+    }
+    fold_sc_tail<Rg>(a, b, active && X == 0, slot, h, red);
+}
+// after the second challenge the f-hat tables are materialised for the first time, again from the digits:
+//   T2[b] = T1[2b] + r2 (T1[2b+1] - T1[2b]) = a0 + r1 e0 + r2 (a1 - a0) + r1 r2 (e1 - e0)
+// cs (device): TAU x 3 limbs (r1, r2, r1 r2) followed by TAU limbs of the correction 2 r1 + 2 r2 + 4 r1 r2 (the signed weights are shifted
+// to non-negative ones for the two-multiply MACs).  grid = (b tiles, slots, tables)
+template <class Rg> __global__ void k_fold_digits2(const int8_t* __restrict__ dig, size_t dig_pitch, size_t dig_stride, int n_f,
+                                                   typename Rg::W* __restrict__ out, size_t out_pitch, size_t out_stride, size_t n_out, const u64* __restrict__ cs) {
+    typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y, kd = blockIdx.z;
+    if (b >= n_out) return;
+    const int k = kd / TAU, d = kd % TAU;
+    const char4 dd = *reinterpret_cast<const char4*>(dig + (size_t)k * dig_stride + (size_t)(d * S + slot) * dig_pitch + 4 * b);
+    const int a0 = dd.x, e0 = dd.y - dd.x, al = dd.z - dd.x, be = (dd.w - dd.z) - e0;      // |e0| <= 2, |al| <= 2, |be| <= 4
+    typename Rg::W* o = out + (size_t)kd * out_stride;
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) {
+        typename F::AccS x; x.clear();
+        x.mac_small((u32)(e0 + 2), cs[l]); x.mac_small((u32)(al + 2), cs[TAU + l]); x.mac_small((u32)(be + 4), cs[2 * TAU + l]);
+        u64 v = F::sub(F::reduce(x), cs[3 * TAU + l]);
+        if (l == 0) v = F::add(v, F::from_i64((int64_t)a0));
+        o[(size_t)(slot * TAU + l) * out_pitch + b] = (typename Rg::W)v;
+    }
 }
 // rounds >= 2.  Along the pair's line f(X) = u + X s:
 //   f^3 - f = (u^3 - u) + 3X u^2 s + 3X^2 u s^2 + X^3 (s^3 - s) + (X^3 - X) s,

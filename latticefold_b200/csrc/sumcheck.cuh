@@ -20,6 +20,9 @@ struct lf_sumcheck {
     size_t len = 0;                   // current LOCAL table length (2^(nv - applied challenges) / ranks while sharded)
     int applied = 0;
     bool sharded = false;             // tables hold this rank's slab of the hypercube (high bits = rank)
+    // FOLD from digits: after the first challenge the f-hat tables stay in digit form (round 2 is evaluated straight from the digits,
+    // k_fold_sc_round2) and are materialised only after the second challenge (k_fold_digits2)
+    bool fh_deferred = false; lf::u64 r1[16] = {0};
 };
 
 namespace lf {
@@ -61,14 +64,16 @@ template <class Rg> struct SumcheckDriver {
         const size_t n_pairs = sc->len / 2; const int ne = sc->deg + 1;
         unsigned nblk; u64* partial;
         if (sc->kind == LF_COMB_FOLD) {
-            const bool round1 = sc->dig && sc->applied == 0;
+            const bool round1 = sc->dig && sc->applied == 0, round2d = sc->dig && sc->applied == 1 && sc->fh_deferred;
             const unsigned gx1 = (unsigned)((n_pairs + 127) / 128), gx2 = (unsigned)((n_pairs + 63) / 64);      // rounds >= 2: two lanes per pair
-            nblk = round1 ? gx1 : gx2;
+            nblk = round1 ? gx1 : round2d ? (unsigned)((n_pairs + 31) / 32) : gx2;                                 // round 2 from digits: four lanes per pair
             partial = E.partial_dev((size_t)nblk * 5 * D);
             FoldScArgsT<W> a; a.dense = wp(sc->dense.cur); a.dense_pitch = sc->dense.pitch; a.dense_stride = sc->dense.stride; a.mu_pow = sc->d_mu_pow; a.n_f = sc->n_f;
             a.n_pairs = n_pairs; a.partial = partial; a.dig = sc->dig; a.dig_pitch = sc->dig_pitch; a.dig_stride = sc->dig_stride;
             a.fh = wp(sc->fh.cur); a.fh_pitch = sc->fh.pitch; a.fh_stride = sc->fh.stride;
+            for (int l = 0; l < TAU; ++l) a.r1[l] = sc->r1[l];
             if (round1) E.launch("k_fold_sc_round1", [&] { k_fold_sc_round1<Rg><<<dim3(gx1, S), 128, 0, E.st()>>>(a); });
+            else if (round2d) E.launch("k_fold_sc_round2", [&] { k_fold_sc_round2<Rg><<<dim3(nblk, S), 128, 0, E.st()>>>(a); });
             else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(gx2, S), 128, 0, E.st()>>>(a); });
         } else {
             // one thread per (pair, evaluation point): see k_sc_points
@@ -138,7 +143,20 @@ template <class Rg> struct SumcheckDriver {
         const size_t n_out = sc->len / 2;
         fold_group(sc->dense, r_sf, n_out);
         if (sc->kind == LF_COMB_FOLD) {
-            if (sc->dig && sc->applied == 0) {
+            if (sc->dig && sc->applied == 0 && sc->nv >= 2 && n_out >= 2 && !std::getenv("LF_FOLD_R2_LEGACY")) {
+                sc->fh_deferred = true; sc->fh.count = sc->n_f; sc->fh.cur = nullptr;
+                for (int l = 0; l < TAU; ++l) sc->r1[l] = r_sf[l];
+            } else if (sc->dig && sc->applied == 1 && sc->fh_deferred) {
+                // T2 = a0 + r1 e0 + r2 (a1 - a0) + r1 r2 (e1 - e0) from four digits per entry
+                sc->fh.pitch = pitch_of(n_out); sc->fh.stride = sc->fh.pitch * D;
+                sc->fh.cur = ow(pingpong_target(sc->fh, n_out)); sc->fh.cur_owned = false; sc->fh_deferred = false;
+                u64 cs[4 * TAU], r12[TAU]; SF::mul(r12, sc->r1, r_sf);
+                for (int l = 0; l < TAU; ++l) { cs[l] = sc->r1[l]; cs[TAU + l] = r_sf[l]; cs[2 * TAU + l] = r12[l];
+                    const u64 two = F::add(F::add(sc->r1[l], sc->r1[l]), F::add(r_sf[l], r_sf[l])), r12x2 = F::add(r12[l], r12[l]); cs[3 * TAU + l] = F::add(two, F::add(r12x2, r12x2)); }
+                u64* d_cs = E.template dalloc<u64>(4 * TAU); E.h2d(d_cs, cs, sizeof cs);
+                E.launch("k_fold_digits", [&] { k_fold_digits2<Rg><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, sc->n_f), 128, 0, E.st()>>>(sc->dig, sc->dig_pitch, sc->dig_stride, sc->n_f, wp(sc->fh.cur), sc->fh.pitch, sc->fh.stride, n_out, d_cs); });
+                E.dfree(d_cs);
+            } else if (sc->dig && sc->applied == 0) {
                 sc->fh.count = sc->n_f; sc->fh.pitch = pitch_of(n_out); sc->fh.stride = sc->fh.pitch * D; sc->fh.cur = nullptr;
                 sc->fh.cur = ow(pingpong_target(sc->fh, n_out)); sc->fh.cur_owned = false;
                 FoldArgsT<W> a; for (int l = 0; l < TAU; ++l) a.r[l] = r_sf[l];
