@@ -91,7 +91,9 @@ struct lf_vec { lf_words* p = nullptr; size_t n = 0, pitch = 0; int form = 0; };
 struct lf_ajtai { lf_words* p = nullptr; size_t kappa = 0, n = 0, pitch = 0;
                   // byte-limb tiles of the matrix for the tensor-core digit commit (commit_mma.cuh); absent on rings that do not use it
                   uint8_t* a8 = nullptr; int a8_tiles = 0, a8_chunks = 0; void* epi = nullptr; };
-struct lf_sparse { lf::u32 *row_ptr = nullptr, *col = nullptr; lf_words* val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0, val_pitch = 0, eff_rows = 0; };
+struct lf_sparse { lf::u32 *row_ptr = nullptr, *col = nullptr; lf_words* val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0, val_pitch = 0, eff_rows = 0;
+                   // transposed image of the rank's columns (k_csc_eq): all rows of the whole matrix, local column indices
+                   lf::u32 *t_col_ptr = nullptr, *t_row = nullptr; lf_words* t_val = nullptr; size_t t_ncols = 0, t_nnz = 0, t_val_pitch = 0; };
 
 namespace lf {
 
@@ -377,9 +379,31 @@ template <class Rg> struct Engine {
         reduce_partials_allreduce(partial, (int)xt, nout, d_out);
     }
     void spmv(const lf_sparse* M, const W* head, size_t head_len, size_t head_pitch, const W* tail, size_t tail_pitch, W* out, size_t out_pitch, size_t nrows,
-              size_t tail_chunk = ~(size_t)0, size_t tail_chunk_stride = 0, int batch = 1, size_t head_batch_stride = 0, size_t tail_batch_stride = 0, size_t out_batch_stride = 0) {
+              size_t tail_chunk = ~(size_t)0, size_t tail_chunk_stride = 0, int batch = 1, size_t head_batch_stride = 0, size_t tail_batch_stride = 0, size_t out_batch_stride = 0, bool accumulate = false) {
         if (!nrows || !batch) return;
-        launch("k_spmv", [&] { k_spmv<Rg><<<dim3(blocks_for(nrows, 128), S, batch), 128, 0, st()>>>(M->row_ptr, M->col, wp(M->val), M->val_pitch, head, head_len, head_pitch, tail, tail_pitch, tail_chunk, tail_chunk_stride, out, out_pitch, nrows, head_batch_stride, tail_batch_stride, out_batch_stride); });
+        launch("k_spmv", [&] { k_spmv<Rg><<<dim3(blocks_for(nrows, 128), S, batch), 128, 0, st()>>>(M->row_ptr, M->col, wp(M->val), M->val_pitch, head, head_len, head_pitch, tail, tail_pitch, tail_chunk, tail_chunk_stride, out, out_pitch, nrows, head_batch_stride, tail_batch_stride, out_batch_stride, accumulate ? 1 : 0); });
+    }
+    // the two half tables of eq(., r): lo over variables [0, h), hi over [h, s); every rank builds them whole (2^(s/2) entries each)
+    struct EqHalves { W *lo = nullptr, *hi = nullptr; size_t plo = 0, phi = 0; int h = 0; };
+    EqHalves eq_halves(const u64* r_host, int s) {
+        if (s < 1 || s > 40) throw LfException(LF_ERR_INVALID_ARG, "eq_table: r length is 0 or too large");
+        std::vector<u64> pair((size_t)s * 2 * D);
+        El one = HR::from_u64(1);
+        for (int i = 0; i < s; ++i) { El r = HR::load(r_host + (size_t)i * D), m = HR::sub(one, r); std::memcpy(&pair[((size_t)i * 2) * D], m.data(), 8 * D); std::memcpy(&pair[((size_t)i * 2 + 1) * D], r.data(), 8 * D); }
+        u64* d_pair = dalloc<u64>(pair.size()); h2d(d_pair, pair.data(), pair.size() * 8);
+        EqHalves q; q.h = std::max(1, s / 2); const int sh = s - q.h;      // s = 1: lo over the single variable, hi = the empty product
+        const size_t nlo = (size_t)1 << q.h, nhi = (size_t)1 << sh; q.plo = pitch_of(nlo); q.phi = pitch_of(nhi);
+        q.lo = dalloc<W>(q.plo * D); q.hi = dalloc<W>(q.phi * D);
+        launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(nlo, 128), S), 128, (size_t)q.h * 2 * TAU * 8, st()>>>(d_pair, q.h, q.lo, q.plo, nlo, 0); });
+        if (sh > 0) launch("k_eq_table", [&] { k_eq_table<Rg><<<dim3(blocks_for(nhi, 128), S), 128, (size_t)sh * 2 * TAU * 8, st()>>>(d_pair + (size_t)q.h * 2 * D, sh, q.hi, q.phi, nhi, 0); });
+        else upload_small(one.data(), 1, q.hi, q.phi);
+        dfree(d_pair); return q;
+    }
+    void free_halves(EqHalves& q) { dfree(q.lo); dfree(q.hi); q.lo = q.hi = nullptr; }
+    // v = M^T eq(., r) on the rank's columns
+    void csc_eq(const lf_sparse* M, const EqHalves& q, W* out, size_t out_pitch) {
+        if (!M->t_ncols) return;
+        launch("k_csc_eq", [&] { k_csc_eq<Rg><<<dim3(blocks_for(M->t_ncols, 128), S), 128, 0, st()>>>(M->t_col_ptr, M->t_row, wp(M->t_val), M->t_val_pitch, q.lo, q.plo, q.hi, q.phi, q.h, out, out_pitch, M->t_ncols); });
     }
     // eq(., r) for r given as s ring elements on the host
     // x_offset / n_local: the slab [x_offset, x_offset + n_local) of the table (hypercube sharding); default = whole table

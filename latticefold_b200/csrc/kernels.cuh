@@ -447,7 +447,7 @@ template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, cons
                                            const typename Rg::W* __restrict__ z_head, size_t head_len, size_t head_pitch,
                                            const typename Rg::W* __restrict__ z_tail, size_t tail_pitch, size_t tail_chunk, size_t tail_chunk_stride,
                                            typename Rg::W* __restrict__ out, size_t out_pitch, size_t nrows,
-                                           size_t head_batch_stride, size_t tail_batch_stride, size_t out_batch_stride) {
+                                           size_t head_batch_stride, size_t tail_batch_stride, size_t out_batch_stride, int accumulate) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
     if (row >= nrows) return;
@@ -455,7 +455,7 @@ template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, cons
     z_head += (size_t)blockIdx.z * head_batch_stride; z_tail += (size_t)blockIdx.z * tail_batch_stride; out += (size_t)blockIdx.z * out_batch_stride;
     typename F::Acc acc[TAU];
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) acc[l].clear();
+    for (int l = 0; l < TAU; ++l) { acc[l].clear(); if (accumulate) acc[l].add((u64)out[(size_t)(slot * TAU + l) * out_pitch + row]); }
     for (u32 e = row_ptr[row]; e < row_ptr[row + 1]; ++e) {
         u64 v[TAU], z[TAU]; const size_t c = col[e];
         // the tail may be the all-gathered concatenation of per-rank slabs: chunk r lives at z_tail + r * tail_chunk_stride
@@ -471,6 +471,33 @@ template <class Rg> __global__ void k_spmv(const u32* __restrict__ row_ptr, cons
     }
 #pragma unroll
     for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + row] = (typename Rg::W)F::reduce(acc[l]);
+}
+
+// Transposed evaluation.  An Mz MLE evaluated at a point r is  (M z)(r) = sum_row eq(row, r) (M z)[row] = sum_col (M^T eq(., r))[col] (.) z[col]
+// (arith/utils.rs:52-65 followed by evaluate_mles, mle_helpers.rs:65-88, regrouped: exact arithmetic).  v = M^T eq depends only on the
+// matrix and the point, so the 2K t evaluations u_s / eta of a step become t sparse products with the transposed matrix plus dot
+// products over the COLUMN axis -- the axis the witness is sharded along: every rank works on its own columns, nothing is gathered
+// and the per-piece Mz tables are never materialised.  eq at an arbitrary row comes from two half tables (lo over the low h
+// variables, hi over the rest), which every rank holds whole.  CSC of the rank's columns: col_ptr / row (global row index) / val planes.
+// thread = (local column, slot)
+template <class Rg> __global__ void k_csc_eq(const u32* __restrict__ col_ptr, const u32* __restrict__ row, const typename Rg::W* __restrict__ val, size_t val_pitch,
+                                             const typename Rg::W* __restrict__ lo, size_t lo_pitch, const typename Rg::W* __restrict__ hi, size_t hi_pitch, int h,
+                                             typename Rg::W* __restrict__ out, size_t out_pitch, size_t ncols) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU;
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int slot = blockIdx.y;
+    if (c >= ncols) return;
+    u64 acc[TAU];
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) acc[l] = 0;
+    for (u32 e = col_ptr[c]; e < col_ptr[c + 1]; ++e) {
+        const size_t r = row[e], rlo = r & (((size_t)1 << h) - 1), rhi = r >> h;
+        u64 v[TAU], a[TAU], b[TAU];
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) { v[l] = val[(size_t)(slot * TAU + l) * val_pitch + e]; a[l] = lo[(size_t)(slot * TAU + l) * lo_pitch + rlo]; b[l] = hi[(size_t)(slot * TAU + l) * hi_pitch + rhi]; }
+        SF::mul(a, a, b); SF::mul(a, a, v); SF::add(acc, acc, a);
+    }
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) out[(size_t)(slot * TAU + l) * out_pitch + c] = (typename Rg::W)acc[l];
 }
 
 // ------------------------------------------------------------------------------------------------ K8 eq table

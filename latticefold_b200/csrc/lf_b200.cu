@@ -157,7 +157,7 @@ lf_status lf_commit_pieces(lf_ctx* c, const lf_ajtai* a, const lf_vec* f, uint64
 lf_status lf_sparse_create(lf_ctx* c, size_t nrows, size_t ncols, const uint64_t* row_ptr, const uint64_t* col, const uint64_t* val, lf_sparse** out) {
     *out = nullptr; return guard(c, [&] { ops(c->ring)->sparse_create(c, nrows, ncols, row_ptr, col, val, out); });
 }
-void lf_sparse_free(lf_ctx* c, lf_sparse* m) { if (m) { cudaStreamSynchronize(c->stream); cudaFree(m->row_ptr); cudaFree(m->col); cudaFree(m->val); delete m; } }
+void lf_sparse_free(lf_ctx* c, lf_sparse* m) { if (m) { cudaStreamSynchronize(c->stream); cudaFree(m->row_ptr); cudaFree(m->col); cudaFree(m->val); cudaFree(m->t_col_ptr); cudaFree(m->t_row); cudaFree(m->t_val); delete m; } }
 lf_status lf_spmv(lf_ctx* c, const lf_sparse* m, const lf_vec* z, lf_vec** out) { *out = nullptr; return guard(c, [&] { ops(c->ring)->spmv(c, m, z, out); }); }
 lf_status lf_eq_table(lf_ctx* c, const uint64_t* r, int32_t s, lf_vec** out) { *out = nullptr; return guard(c, [&] { ops(c->ring)->eq_table(c, r, s, out); }); }
 lf_status lf_mle_eval_batch(lf_ctx* c, const lf_vec* const* mles, int32_t count, int32_t nv, const uint64_t* point, int32_t point_len, uint64_t* out_host) {

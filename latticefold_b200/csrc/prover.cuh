@@ -140,6 +140,35 @@ template <class Rg> struct Prover {
         const u64* land = eval_mz_async(z, row0, rows, eq); E.sync(); return HV(land, land + (size_t)rows * D);
     }
 
+    // local z vectors: z = head || tail with the l+1 head elements (x || 1, or x_s[k]) in front of this rank's slice of w_ccs; the head
+    // entries are real on rank 0 and zero elsewhere, so that sums over ranks count them once
+    size_t hc() const { return P->l + 1; }
+    size_t zcols() const { return hc() + Wl(); }
+    // (M_j z_k)(r) for every matrix j and `count` local z vectors, transposed (k_csc_eq): pinned result [t][count][D], valid after the next sync / event
+    const u64* eval_z_async(const W* z, size_t z_pitch, size_t z_stride, int count, const HV& point) {
+        const size_t t = P->t; const int s = (int)cnt(point);
+        for (auto* M : P->M) if (M->t_ncols != zcols()) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "LengthsNotEqual(M, z)");
+        typename Engine<Rg>::EqHalves q = E.eq_halves(point.data(), s);
+        const size_t vp = pitch_of(zcols()), vs = vp * D;
+        W* v = E.template dalloc<W>(t * vs);
+        for (size_t j = 0; j < t; ++j) E.csc_eq(P->M[j], q, v + j * vs, vp);
+        E.free_halves(q);
+        if (count > MAX_LIST) throw LfException(LF_ERR_UNSUPPORTED, "more than MAX_LIST z vectors in one evaluation");
+        PL Y; for (int k = 0; k < count; ++k) { Y.p[k] = z + (size_t)k * z_stride; Y.len[k] = zcols(); }
+        u64* d_out = E.template dalloc<u64>(t * count * D);
+        E.dot(v, vs, vp, (int)t, nullptr, Y, z_pitch, count, zcols(), d_out, "k_dot_eval");
+        const u64* land = E.d2h_async(d_out, t * count * D); E.dfree(d_out); E.dfree(v); return land;
+    }
+    // head entries of `count` consecutive local z vectors (rank 0: the given elements; other ranks: zero), one strided copy
+    void write_heads(W* z, size_t z_pitch, int count, const std::vector<HV>& heads) {
+        const size_t h = hc();
+        if (rank() != 0) { LF_CUDA(cudaMemset2DAsync(z, z_pitch * sizeof(W), 0, h * sizeof(W), (size_t)count * D, E.st())); return; }
+        W* stage = (W*)E.arena_alloc((size_t)count * D * h * sizeof(W));
+        for (int k = 0; k < count; ++k) { if (cnt(heads[k]) != h) throw LfException(LF_ERR_INCORRECT_LENGTH, "IncorrectLength");
+            for (int l = 0; l < D; ++l) for (size_t e = 0; e < h; ++e) stage[((size_t)k * D + l) * h + e] = (W)heads[k][e * D + l]; }
+        LF_CUDA(cudaMemcpy2DAsync(z, z_pitch * sizeof(W), stage, h * sizeof(W), h * sizeof(W), (size_t)count * D, cudaMemcpyHostToDevice, E.st()));
+    }
+
     // ------------------------------------------------------------------ linearization (linearization.rs:145-189)
     struct LinOut { LCCCS lc; HV msgs; DevVec eq_r; };
     // pre_tail: the all-gathered w_ccs slabs when the caller has already queued that collective (the sharded step issues it before
@@ -207,8 +236,7 @@ template <class Rg> struct Prover {
     struct StepBuffers {    // witness-sized state shared by the two decompositions and the folding
         int8_t* dig = nullptr; size_t dig_pitch = 0, dig_stride = 0;     // [2K][D][pitch]
         W* pieces = nullptr; size_t pc_pitch = 0, pc_stride = 0;         // NTT form of every piece, [2K][D][pitch]
-        W* wccs = nullptr; size_t wc_pitch = 0, wc_stride = 0;         // gadget_recompose of every piece, [2K][D][pitch]
-        MzSet mz;                                                        // [2K * t]
+        W* zl = nullptr; size_t zl_pitch = 0, zl_stride = 0;           // local z of every piece (head || gadget_recompose of the piece), [2K][D][pitch]
     };
     struct DecOut { std::vector<HV> x_s, y_s, u_s, v_s; std::vector<LCCCS> lc; };
     // decompose_big_vec_into_k_vec_and_compose_back (decomposition/utils.rs:12-42) on l+1 elements: host
@@ -241,14 +269,15 @@ template <class Rg> struct Prover {
         DecPending o; o.cm = cm; const int K = P->K; const size_t n = nl(), kappa = P->kappa;
         int8_t* dig = sb.dig + (size_t)half * K * sb.dig_stride;
         W* pieces = sb.pieces + (size_t)half * K * sb.pc_stride;
-        W* wccs = sb.wccs + (size_t)half * K * sb.wc_stride;
+        W* zl = sb.zl + (size_t)half * K * sb.zl_stride;
         if (cnt(cm.cm) != kappa) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongCommitmentLength");
         // decompose_witness: f_coeff.decompose_to_vec(b, K).transpose() (decomposition.rs:162-167), then CRT and recompose per piece (arith.rs:324-338)
         E.digit_split(wp(w->f_coeff), w->pitch, dig, sb.dig_pitch, n, P->b, K);
         E.crt_digits(dig, sb.dig_pitch, pieces, sb.pc_pitch, n, K, sb.dig_stride, sb.pc_stride);                       // all K pieces, one launch each
-        E.gadget_recompose(pieces, sb.pc_pitch, wccs, sb.wc_pitch, w->W, P->B, P->L, K, sb.pc_stride, sb.wc_stride);
+        E.gadget_recompose(pieces, sb.pc_pitch, zl + hc(), sb.zl_pitch, w->W, P->B, P->L, K, sb.pc_stride, sb.zl_stride);
         mark("dec.split_crt");
         o.x_s = compute_x_s(cm);
+        write_heads(zl, sb.zl_pitch, K, o.x_s);
         mark("dec.x_s");
         // commit_witnesses (decomposition.rs:178-201): K-1 commits in one pass over A
         if (K > 1) {
@@ -265,11 +294,9 @@ template <class Rg> struct Prover {
           E.template coeff_eval<int8_t>(dig, sb.dig_pitch, sb.dig_stride, K, eq_r.p, eq_r.pitch, n, d_v);
           o.v_pin = E.d2h_async(d_v, (size_t)K * TAU * D); E.dfree(d_v); }
         mark("dec.v_s");
-        // compute_mz_mles / compute_u_s (decomposition.rs:214-256): z_k = x_s[k] || w_ccs_k
-        { const size_t words = (size_t)K * sb.wc_stride; W* all = gather_wccs(wccs, words);     // one all-gather per decomposition
-          compute_mz_batch(sb.mz, half * K, K, o.x_s, all, sb.wc_pitch, sb.wc_stride, w->W * world(), world() == 1 ? ~(size_t)0 : w->W, words);
-          if (all != wccs) E.dfree(all); }
-        o.u_pin = eval_mz_async(sb.mz, half * K * (int)P->t, K * (int)P->t, eq_r);
+        // compute_mz_mles / compute_u_s (decomposition.rs:214-256): u_s[k][j] = (M_j z_k)(r), z_k = x_s[k] || w_ccs_k, evaluated through
+        // the transposed matrices on this rank's columns -- no Mz table per piece, no gather
+        o.u_pin = eval_z_async(zl, sb.zl_pitch, sb.zl_stride, K, cm.r);
         mark("dec.mz_u_s");
         LF_CUDA(cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming)); LF_CUDA(cudaEventRecord(o.ev, E.st()));
         return o;
@@ -284,7 +311,7 @@ template <class Rg> struct Prover {
           for (int k = K - 1; k >= 1; --k) for (size_t i = 0; i < kappa * D; ++i) bsum[i] = F::mul(F::add(bsum[i], o.y_s[k][i]), bm);
           for (size_t i = 0; i < kappa * D; ++i) o.y_s[0][i] = F::sub(cm.cm[i], bsum[i]); }
         for (int k = 0; k < K; ++k) o.v_s.emplace_back(pd.v_pin + (size_t)k * TAU * D, pd.v_pin + (size_t)(k + 1) * TAU * D);
-        for (int k = 0; k < K; ++k) o.u_s.emplace_back(pd.u_pin + (size_t)k * t * D, pd.u_pin + (size_t)(k + 1) * t * D);
+        for (int k = 0; k < K; ++k) { HV u(t * D); for (size_t j = 0; j < t; ++j) std::memcpy(&u[j * D], pd.u_pin + (j * K + k) * D, 8 * D); o.u_s.push_back(std::move(u)); }      // [t][K] -> per piece
         auto t0 = std::chrono::steady_clock::now();
         for (int k = 0; k < K; ++k) {
             const HV& x = o.x_s[k];
@@ -339,17 +366,30 @@ template <class Rg> struct Prover {
             E.h2d(d_w, wts.data(), wts.size() * 8);
             E.launch("k_digit_lincomb", [&] { k_digit_lincomb<Rg><<<dim3(Engine<Rg>::blocks_for(n, 128), S), 128, 0, E.st()>>>(sb.dig + (size_t)half * K * sb.dig_stride, sb.dig_pitch, sb.dig_stride, K, d_w, G, sc.dense.pitch, n, 0); });
             E.dfree(d_w);
-            // + sum_i Horner_{zeta_i}(Mz_i[t-1..0])   (calculate_challenged_mz_mle, folding.rs:208-226)
-            HV coef((size_t)K * t * D); PL pl; std::vector<const W*> ptrs; std::vector<size_t> lens;
-            for (int i = 0; i < K; ++i) { const u64* z = &zeta[(size_t)(half * K + i) * TAU]; u64 pw[TAU]; std::memcpy(pw, z, 8 * TAU);
-                for (size_t j = 0; j < t; ++j) { El e = HR::from_sf(pw); std::memcpy(&coef[((size_t)i * t + j) * D], e.data(), 8 * D); SF::mul(pw, pw, z);
-                    ptrs.push_back(sb.mz.p + ((size_t)(half * K + i) * t + j) * sb.mz.stride); lens.push_back(sb.mz.len[(size_t)(half * K + i) * t + j]); } }
-            for (size_t done = 0; done < ptrs.size(); done += MAX_LIST) {
-                const int chunk = (int)std::min<size_t>(MAX_LIST, ptrs.size() - done);
-                for (int i = 0; i < chunk; ++i) { pl.p[i] = ptrs[done + i]; pl.len[i] = lens[done + i]; }
-                if (sb.mz.pitch > sc.dense.pitch) throw LfException(LF_ERR_MLE_LEN, "IncorrectLength");
-                E.lincomb(pl, sb.mz.pitch, chunk, &coef[done * D], G, sc.dense.pitch, sb.mz.pitch, true);
-            }
+            // + sum_i Horner_{zeta_i}(Mz_i[t-1..0]) = sum_j M_j (sum_i zeta_i^(j+1) z_i)   (calculate_challenged_mz_mle, folding.rs:208-226;
+            // slot-wise scalars commute with the sparse product): the z vectors are combined first, on every rank's own columns, and
+            // only the t combined vectors are gathered for the row owners' sparse products
+            { const size_t zs = sb.zl_stride, zp = sb.zl_pitch; W* Z = E.template dalloc<W>(t * zs);
+              std::vector<HV> zhead(t, HV(hc() * D, 0));
+              for (size_t j = 0; j < t; ++j) {
+                  HV coef((size_t)K * D); PL pl;
+                  for (int i = 0; i < K; ++i) { const u64* z = &zeta[(size_t)(half * K + i) * TAU]; u64 pw[TAU]; std::memcpy(pw, z, 8 * TAU);
+                      for (size_t e = 0; e < j; ++e) SF::mul(pw, pw, z);
+                      El ce = HR::from_sf(pw); std::memcpy(&coef[(size_t)i * D], ce.data(), 8 * D);
+                      pl.p[i] = sb.zl + (size_t)(half * K + i) * zs; pl.len[i] = zcols();
+                      const LCCCS& L = lcs[half * K + i]; HV xh = L.x_w; xh.insert(xh.end(), L.h.begin(), L.h.end());
+                      for (size_t e = 0; e < hc() && e < cnt(xh); ++e) { El pr = HR::mul(HR::load(&xh[e * D]), ce); for (int l = 0; l < D; ++l) zhead[j][e * D + l] = F::add(zhead[j][e * D + l], pr[l]); } }
+                  E.lincomb(pl, zp, K, coef.data(), Z + j * zs, zp, zcols(), false);
+              }
+              W* all = gather_wccs(Z, t * zs);
+              const size_t hp = pitch_of(hc()); W* d_head = E.template dalloc<W>(t * hp * D);
+              for (size_t j = 0; j < t; ++j) {
+                  if (P->M[j]->eff_rows > sc.dense.pitch) throw LfException(LF_ERR_MLE_LEN, "IncorrectLength");
+                  E.upload_small(zhead[j].data(), hc(), d_head + j * hp * D, hp);
+                  E.spmv(P->M[j], d_head + j * hp * D, hc(), hp, all + j * zs + hc(), zp, G, sc.dense.pitch, P->M[j]->eff_rows,
+                         world() == 1 ? ~(size_t)0 : Wl(), t * zs, 1, 0, 0, 0, true);
+              }
+              E.dfree(d_head); if (all != Z) E.dfree(all); E.dfree(Z); }
         }
         std::vector<u64> mu = squeeze(T, "mu_s", 2 * K - 1);
         { u64 one[TAU] = {0}; one[0] = 1; mu.insert(mu.end(), one, one + TAU); }
@@ -368,11 +408,11 @@ template <class Rg> struct Prover {
         for (int i = 0; i < 2 * K; ++i) o.theta.emplace_back(finals.begin() + (size_t)(5 + i * TAU) * D, finals.begin() + (size_t)(5 + (i + 1) * TAU) * D);
         // eta_i = Mz_i(r_0) (get_etas, folding.rs:248-256)
         // queued without waiting: the host absorbs the thetas while the device evaluates the etas
-        DevVec eq0 = eq_table(r0); const u64* eta_land = eval_mz_async(sb.mz, 0, 2 * K * (int)t, eq0); E.dfree(eq0.p);
+        const u64* eta_land = eval_z_async(sb.zl, sb.zl_pitch, sb.zl_stride, 2 * K, r0);
         auto t0 = std::chrono::steady_clock::now();
         for (auto& th : o.theta) T.absorb_slice(th.data(), cnt(th));
         E.sync();
-        for (int i = 0; i < 2 * K; ++i) o.eta.emplace_back(eta_land + (size_t)i * t * D, eta_land + (size_t)(i + 1) * t * D);
+        for (int i = 0; i < 2 * K; ++i) { HV et(t * D); for (size_t j = 0; j < t; ++j) std::memcpy(&et[j * D], eta_land + (j * 2 * K + i) * D, 8 * D); o.eta.push_back(std::move(et)); }
         mark("fold.eta");
         for (auto& et : o.eta) T.absorb_slice(et.data(), cnt(et));
         // get_rhos (folding/utils.rs:116-131)
@@ -451,8 +491,7 @@ template <class Rg> struct Prover {
         sb.dig_pitch = (std::max(n, ml()) + 255) / 256 * 256;   // the sumcheck walks all 2^s entries
         sb.dig_stride = sb.dig_pitch * D; sb.dig = E.template dalloc<int8_t>((size_t)2 * K * sb.dig_stride);
         sb.pc_pitch = pitch_of(n); sb.pc_stride = sb.pc_pitch * D; sb.pieces = E.template dalloc<W>((size_t)2 * K * sb.pc_stride);
-        sb.wc_pitch = pitch_of(w_i->W); sb.wc_stride = sb.wc_pitch * D; sb.wccs = E.template dalloc<W>((size_t)2 * K * sb.wc_stride);
-        sb.mz = alloc_mz(2 * K, false);
+        sb.zl_pitch = pitch_of(zcols()); sb.zl_stride = sb.zl_pitch * D; sb.zl = E.template dalloc<W>((size_t)2 * K * sb.zl_stride);
         DevVec eq_acc; eq_acc.n = ((size_t)1 << cnt(acc.r)) / world(); eq_acc.pitch = pitch_of(eq_acc.n); eq_acc.p = E.template dalloc<W>(eq_acc.pitch * D);
         // sharded steps overlap too when the collectives are stream-ordered on both streams (own NCCL communicator + mailbox channels)
         const bool overlap = (world() == 1 || (E.c->nccl && E.c->xg.on)) && !P->detail && !std::getenv("LF_NO_OVERLAP");
@@ -472,7 +511,6 @@ template <class Rg> struct Prover {
                 // on the stream that runs the decompositions: when the accumulator's decomposition starts behind `acc_ready`
                 // (host-buffer entry point) it does NOT wait for what the main stream queues after that event
                 LF_CUDA(cudaMemsetAsync(sb.dig, 0, (size_t)2 * K * sb.dig_stride, E.st()));   // f-hat tables are zero on [n, 2^s)
-                upload_mz_len(sb.mz);
                 E.eq_table(acc.r.data(), (int)cnt(acc.r), eq_acc.p, eq_acc.pitch, (size_t)rank() * eq_acc.n, eq_acc.n);
                 pl = decompose_enqueue(acc, w_acc, eq_acc, sb, 0);
             } catch (...) { E.c = main_ctx; throw; }
@@ -511,7 +549,7 @@ template <class Rg> struct Prover {
         FoldOut fo = fold(lcs, sb, eq_acc, lin.eq_r, T);
         mark("fold.host_tail");
         lf_witness* w_out = witness_from_f_device(fo.f0);
-        E.dfree(sb.dig); E.dfree(sb.pieces); E.dfree(sb.wccs); free_mz(sb.mz); E.dfree(eq_acc.p); E.dfree(lin.eq_r.p);
+        E.dfree(sb.dig); E.dfree(sb.pieces); E.dfree(sb.zl); E.dfree(eq_acc.p); E.dfree(lin.eq_r.p);
         E.sync(); auto t3 = clk::now(); P->timings[2] = ms(t2, t3);
         mark("witness_out_free");
         // serialise: lin{msgs,v,u} | dec_acc | dec_new | fold{msgs,theta,eta}

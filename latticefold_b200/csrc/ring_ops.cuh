@@ -303,7 +303,25 @@ template <class Rg> struct RingOpsImpl final : RingOps {
             const lf_csr& M = sh->M[j]; if (M.nrows != sh->m) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "CCS matrix rows != m");
             const size_t r0 = (size_t)c->rank * m_loc; const u64 e0 = M.row_ptr[r0];
             std::vector<u64> rp(m_loc + 1); for (size_t i = 0; i <= m_loc; ++i) rp[i] = M.row_ptr[r0 + i] - e0;
-            lf_sparse* m = nullptr; sparse_create(c, m_loc, M.ncols, rp.data(), M.col + e0, M.val + e0 * Rg::D, &m); p->M.push_back(m); }
+            lf_sparse* m = nullptr; sparse_create(c, m_loc, M.ncols, rp.data(), M.col + e0, M.val + e0 * Rg::D, &m); p->M.push_back(m);
+            // transposed image of the rank's columns (k_csc_eq): the l+1 head columns on every rank + the columns of its witness slice, all rows
+            const size_t hc = sh->l + 1, W_all = sh->L ? sh->n / sh->L : 0, W_loc = W_all / G;
+            if (M.ncols == hc + W_all && W_all % G == 0 && M.row_ptr[sh->m] < ((u64)1 << 32)) {
+                const size_t c0 = hc + (size_t)c->rank * W_loc, nloc = hc + W_loc;
+                auto local = [&](u64 col) -> long long { return col < hc ? (long long)col : (col >= c0 && col < c0 + W_loc ? (long long)(hc + (col - c0)) : -1); };
+                std::vector<u32> cp(nloc + 1, 0);
+                for (u64 r = 0; r < sh->m; ++r) for (u64 e = M.row_ptr[r]; e < M.row_ptr[r + 1]; ++e) { const long long lc = local(M.col[e]); if (lc >= 0) ++cp[lc + 1]; }
+                for (size_t i = 0; i < nloc; ++i) cp[i + 1] += cp[i];
+                const size_t tn = cp[nloc]; std::vector<u32> fill(cp.begin(), cp.end() - 1), tr(std::max<size_t>(tn, 1)); HV tv(std::max<size_t>(tn, 1) * Rg::D);
+                for (u64 r = 0; r < sh->m; ++r) for (u64 e = M.row_ptr[r]; e < M.row_ptr[r + 1]; ++e) { const long long lc = local(M.col[e]); if (lc < 0) continue;
+                    const u32 pos = fill[lc]++; tr[pos] = (u32)r; std::memcpy(&tv[(size_t)pos * Rg::D], M.val + e * Rg::D, 8 * Rg::D); }
+                Engine<Rg> E(c);
+                LF_CUDA(cudaMalloc(&m->t_col_ptr, (nloc + 1) * 4)); LF_CUDA(cudaMalloc(&m->t_row, std::max<size_t>(1, tn) * 4));
+                LF_CUDA(cudaMemcpy(m->t_col_ptr, cp.data(), (nloc + 1) * 4, cudaMemcpyHostToDevice)); if (tn) LF_CUDA(cudaMemcpy(m->t_row, tr.data(), tn * 4, cudaMemcpyHostToDevice));
+                m->t_val_pitch = pitch_of(tn); LF_CUDA(cudaMalloc(&m->t_val, m->t_val_pitch * Rg::D * sizeof(W)));
+                E.upload_planes(tv.data(), tn, wp(m->t_val), m->t_val_pitch); E.sync();
+                m->t_ncols = nloc; m->t_nnz = tn;
+            } }
         *out = p.release();
     }
     void prover_upload_witness(lf_prover* p, const uint64_t* f_host, lf_witness** out) override {
