@@ -211,6 +211,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        bind_to_gpu_numa_node(local)      # pinned staging buffers and the transcript thread next to the GPU's PCIe root
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -530,6 +531,28 @@ NCU_TRAFFIC = {"k_fold_sc_round": 2.578e9, "k_dot_commit": 2.086e9}
 # what bounds each kernel (ncu evidence in profiles/): "hbm" unless stated
 KERNEL_BOUND = {"k_fold_sc_round": "int-pipe (IMAD.WIDE / ALU)", "k_commit_mma": "hbm + L2 (tensor pipe idle-waiting on operand fill)", "k_dot_commit": "int-pipe (IMAD.WIDE)",
                 "k_sc_generic": "latency (host-paced rounds)", "k_fold_sc_round1": "int-pipe"}
+
+
+def bind_to_gpu_numa_node(local):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off (first-touch then places the pinned host buffers there too):
+    with 8 ranks on a two-socket host, half of the host<->device copies otherwise cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit(); bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else str(bus)).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-"); cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass
 
 
 def _commit_with_prover(ctx, pr, lf, prob, f):
