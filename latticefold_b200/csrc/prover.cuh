@@ -146,18 +146,7 @@ template <class Rg> struct Prover {
     size_t zcols() const { return hc() + Wl(); }
     // (M_j z_k)(r) for every matrix j and `count` local z vectors, transposed (k_csc_eq): pinned result [t][count][D], valid after the next sync / event
     const u64* eval_z_async(const W* z, size_t z_pitch, size_t z_stride, int count, const HV& point) {
-        const size_t t = P->t; const int s = (int)cnt(point);
-        for (auto* M : P->M) if (M->t_ncols != zcols()) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "LengthsNotEqual(M, z)");
-        typename Engine<Rg>::EqHalves q = E.eq_halves(point.data(), s);
-        const size_t vp = pitch_of(zcols()), vs = vp * D;
-        W* v = E.template dalloc<W>(t * vs);
-        for (size_t j = 0; j < t; ++j) E.csc_eq(P->M[j], q, v + j * vs, vp);
-        E.free_halves(q);
-        if (count > MAX_LIST) throw LfException(LF_ERR_UNSUPPORTED, "more than MAX_LIST z vectors in one evaluation");
-        PL Y; for (int k = 0; k < count; ++k) { Y.p[k] = z + (size_t)k * z_stride; Y.len[k] = zcols(); }
-        u64* d_out = E.template dalloc<u64>(t * count * D);
-        E.dot(v, vs, vp, (int)t, nullptr, Y, z_pitch, count, zcols(), d_out, "k_dot_eval");
-        const u64* land = E.d2h_async(d_out, t * count * D); E.dfree(d_out); E.dfree(v); return land;
+        EvalPrep e = eval_prepare(point); const u64* land = eval_with(e, z, z_pitch, z_stride, count); E.dfree(e.v); return land;
     }
     // head entries of `count` consecutive local z vectors (rank 0: the given elements; other ranks: zero), one strided copy
     void write_heads(W* z, size_t z_pitch, int count, const std::vector<HV>& heads) {
@@ -264,63 +253,103 @@ template <class Rg> struct Prover {
     }
     // The device half of a decomposition is enqueued without any host synchronisation (results land in the pinned arena
     // behind an event); the host half (y_0 Horner, transcript absorbs) runs later, overlapping whatever the GPU does next.
-    struct DecPending { LCCCS cm; std::vector<HV> x_s; const u64 *y_pin = nullptr, *v_pin = nullptr, *u_pin = nullptr; cudaEvent_t ev = nullptr; };
+    // Results arrive in groups of pieces, each behind its own event: the commitments of all pieces first (one pass over the matrix),
+    // then CRT / recompose / v_s / u_s group by group, so that the host hashes group g (Fiat-Shamir absorbs x_s, y_s, u_s, v_s piece by
+    // piece) while the device works on group g+1 -- only the last group's absorb is exposed.
+    static constexpr int DEC_GROUPS = 4;
+    struct DecPending { LCCCS cm; std::vector<HV> x_s; const u64* y_pin = nullptr; bool y_early = false; int ngroups = 0; int g0[DEC_GROUPS + 1] = {0};
+                        const u64 *v_pin[DEC_GROUPS] = {nullptr}, *u_pin[DEC_GROUPS] = {nullptr}; cudaEvent_t ev[DEC_GROUPS] = {nullptr}; };
+    struct EvalPrep { W* v = nullptr; size_t vp = 0, vs = 0; };
+    EvalPrep eval_prepare(const HV& point) {      // v_j = M_j^T eq(., point) on this rank's columns
+        const size_t t = P->t;
+        for (auto* M : P->M) if (M->t_ncols != zcols()) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "LengthsNotEqual(M, z)");
+        typename Engine<Rg>::EqHalves q = E.eq_halves(point.data(), (int)cnt(point));
+        EvalPrep e; e.vp = pitch_of(zcols()); e.vs = e.vp * D; e.v = E.template dalloc<W>(t * e.vs);
+        for (size_t j = 0; j < t; ++j) E.csc_eq(P->M[j], q, e.v + j * e.vs, e.vp);
+        E.free_halves(q); return e;
+    }
+    const u64* eval_with(const EvalPrep& e, const W* z, size_t z_pitch, size_t z_stride, int count) {      // pinned [t][count][D]
+        if (count > MAX_LIST) throw LfException(LF_ERR_UNSUPPORTED, "more than MAX_LIST z vectors in one evaluation");
+        const size_t t = P->t;
+        PL Y; for (int k = 0; k < count; ++k) { Y.p[k] = z + (size_t)k * z_stride; Y.len[k] = zcols(); }
+        u64* d_out = E.template dalloc<u64>(t * count * D);
+        E.dot(e.v, e.vs, e.vp, (int)t, nullptr, Y, z_pitch, count, zcols(), d_out, "k_dot_eval");
+        const u64* land = E.d2h_async(d_out, t * count * D); E.dfree(d_out); return land;
+    }
     DecPending decompose_enqueue(const LCCCS& cm, const lf_witness* w, const DevVec& eq_r, StepBuffers& sb, int half) {
         DecPending o; o.cm = cm; const int K = P->K; const size_t n = nl(), kappa = P->kappa;
         int8_t* dig = sb.dig + (size_t)half * K * sb.dig_stride;
         W* pieces = sb.pieces + (size_t)half * K * sb.pc_stride;
         W* zl = sb.zl + (size_t)half * K * sb.zl_stride;
         if (cnt(cm.cm) != kappa) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongCommitmentLength");
-        // decompose_witness: f_coeff.decompose_to_vec(b, K).transpose() (decomposition.rs:162-167), then CRT and recompose per piece (arith.rs:324-338)
+        // decompose_witness: f_coeff.decompose_to_vec(b, K).transpose() (decomposition.rs:162-167)
         E.digit_split(wp(w->f_coeff), w->pitch, dig, sb.dig_pitch, n, P->b, K);
-        E.crt_digits(dig, sb.dig_pitch, pieces, sb.pc_pitch, n, K, sb.dig_stride, sb.pc_stride);                       // all K pieces, one launch each
-        E.gadget_recompose(pieces, sb.pc_pitch, zl + hc(), sb.zl_pitch, w->W, P->B, P->L, K, sb.pc_stride, sb.zl_stride);
-        mark("dec.split_crt");
         o.x_s = compute_x_s(cm);
         write_heads(zl, sb.zl_pitch, K, o.x_s);
-        mark("dec.x_s");
-        // commit_witnesses (decomposition.rs:178-201): K-1 commits in one pass over A
-        if (K > 1) {
-            PL Y; for (int k = 1; k < K; ++k) { Y.p[k - 1] = pieces + (size_t)k * sb.pc_stride; Y.len[k - 1] = n; }
-            u64* d_y = E.template dalloc<u64>(kappa * (K - 1) * D);
-            // digit pieces: integer GEMM on the tensor cores straight from the int8 digits (commit_mma.cuh); otherwise lazily reduced dot products
-            if (E.can_commit_digits(P->A, K - 1, sb.dig_pitch)) E.commit_digits(P->A, dig + sb.dig_stride, sb.dig_pitch, sb.dig_stride, K - 1, d_y);
-            else E.dot(wp(P->A->p), P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y, "k_dot_commit");
-            o.y_pin = E.d2h_async(d_y, kappa * (K - 1) * D); E.dfree(d_y);
-        }
+        mark("dec.split_x_s");
+        // commit_witnesses (decomposition.rs:178-201): K-1 commits in one pass over A.  Digit pieces: integer GEMM on the tensor cores
+        // straight from the int8 digits (commit_mma.cuh); otherwise (other rings) lazily reduced dot products on the pieces' NTT forms
+        const bool mma = K > 1 && E.can_commit_digits(P->A, K - 1, sb.dig_pitch); o.y_early = mma;
+        if (mma) { u64* d_y = E.template dalloc<u64>(kappa * (K - 1) * D);
+            E.commit_digits(P->A, dig + sb.dig_stride, sb.dig_pitch, sb.dig_stride, K - 1, d_y);
+            o.y_pin = E.d2h_async(d_y, kappa * (K - 1) * D); E.dfree(d_y); }
         mark("dec.commit");
-        // compute_v_s (decomposition.rs:204-211): f-hat of piece k evaluated at r, straight from the digits
-        { u64* d_v = E.template dalloc<u64>((size_t)K * TAU * D);
-          E.template coeff_eval<int8_t>(dig, sb.dig_pitch, sb.dig_stride, K, eq_r.p, eq_r.pitch, n, d_v);
-          o.v_pin = E.d2h_async(d_v, (size_t)K * TAU * D); E.dfree(d_v); }
-        mark("dec.v_s");
-        // compute_mz_mles / compute_u_s (decomposition.rs:214-256): u_s[k][j] = (M_j z_k)(r), z_k = x_s[k] || w_ccs_k, evaluated through
-        // the transposed matrices on this rank's columns -- no Mz table per piece, no gather
-        o.u_pin = eval_z_async(zl, sb.zl_pitch, sb.zl_stride, K, cm.r);
-        mark("dec.mz_u_s");
-        LF_CUDA(cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming)); LF_CUDA(cudaEventRecord(o.ev, E.st()));
+        EvalPrep ep = eval_prepare(cm.r);
+        o.ngroups = std::min(DEC_GROUPS, K); if (std::getenv("LF_DEC_ONE_GROUP")) o.ngroups = 1;
+        for (int g = 0; g <= o.ngroups; ++g) o.g0[g] = (int)((size_t)K * g / o.ngroups);
+        for (int g = 0; g < o.ngroups; ++g) {
+            const int k0 = o.g0[g], c = o.g0[g + 1] - k0;
+            // CRT and recompose per piece (arith.rs:324-338)
+            E.crt_digits(dig + (size_t)k0 * sb.dig_stride, sb.dig_pitch, pieces + (size_t)k0 * sb.pc_stride, sb.pc_pitch, n, c, sb.dig_stride, sb.pc_stride);
+            E.gadget_recompose(pieces + (size_t)k0 * sb.pc_stride, sb.pc_pitch, zl + (size_t)k0 * sb.zl_stride + hc(), sb.zl_pitch, w->W, P->B, P->L, c, sb.pc_stride, sb.zl_stride);
+            if (!mma && K > 1 && g == o.ngroups - 1) {      // the dot-product commit needs every piece's NTT form
+                PL Y; for (int k = 1; k < K; ++k) { Y.p[k - 1] = pieces + (size_t)k * sb.pc_stride; Y.len[k - 1] = n; }
+                u64* d_y = E.template dalloc<u64>(kappa * (K - 1) * D);
+                E.dot(wp(P->A->p), P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y, "k_dot_commit");
+                o.y_pin = E.d2h_async(d_y, kappa * (K - 1) * D); E.dfree(d_y);
+            }
+            // compute_v_s (decomposition.rs:204-211): f-hat of piece k evaluated at r, straight from the digits
+            { u64* d_v = E.template dalloc<u64>((size_t)c * TAU * D);
+              E.template coeff_eval<int8_t>(dig + (size_t)k0 * sb.dig_stride, sb.dig_pitch, sb.dig_stride, c, eq_r.p, eq_r.pitch, n, d_v);
+              o.v_pin[g] = E.d2h_async(d_v, (size_t)c * TAU * D); E.dfree(d_v); }
+            // compute_mz_mles / compute_u_s (decomposition.rs:214-256): u_s[k][j] = (M_j z_k)(r), z_k = x_s[k] || w_ccs_k, evaluated through
+            // the transposed matrices on this rank's columns -- no Mz table per piece, no gather
+            o.u_pin[g] = eval_with(ep, zl + (size_t)k0 * sb.zl_stride, sb.zl_pitch, sb.zl_stride, c);
+            LF_CUDA(cudaEventCreateWithFlags(&o.ev[g], cudaEventDisableTiming)); LF_CUDA(cudaEventRecord(o.ev[g], E.st()));
+        }
+        E.dfree(ep.v);
+        mark("dec.groups");
         return o;
     }
     DecOut decompose_finish(DecPending& pd, Transcript<Rg>& T) {
         DecOut o; const int K = P->K; const size_t kappa = P->kappa, t = P->t; const LCCCS& cm = pd.cm;
-        LF_CUDA(cudaEventSynchronize(pd.ev)); cudaEventDestroy(pd.ev); pd.ev = nullptr;
         o.x_s = std::move(pd.x_s);
-        o.y_s.assign(K, HV(kappa * D, 0));
-        for (int k = 1; k < K; ++k) for (size_t i = 0; i < kappa; ++i) std::memcpy(&o.y_s[k][i * D], pd.y_pin + (i * (K - 1) + (k - 1)) * D, 8 * D);
-        { HV bsum(kappa * D, 0); const u64 bm = P->b % F::P;      // y_0 = cm - b (y_1 + b (y_2 + ...))
-          for (int k = K - 1; k >= 1; --k) for (size_t i = 0; i < kappa * D; ++i) bsum[i] = F::mul(F::add(bsum[i], o.y_s[k][i]), bm);
-          for (size_t i = 0; i < kappa * D; ++i) o.y_s[0][i] = F::sub(cm.cm[i], bsum[i]); }
-        for (int k = 0; k < K; ++k) o.v_s.emplace_back(pd.v_pin + (size_t)k * TAU * D, pd.v_pin + (size_t)(k + 1) * TAU * D);
-        for (int k = 0; k < K; ++k) { HV u(t * D); for (size_t j = 0; j < t; ++j) std::memcpy(&u[j * D], pd.u_pin + (j * K + k) * D, 8 * D); o.u_s.push_back(std::move(u)); }      // [t][K] -> per piece
-        auto t0 = std::chrono::steady_clock::now();
-        for (int k = 0; k < K; ++k) {
-            const HV& x = o.x_s[k];
-            T.absorb_slice(x.data(), cnt(x)); T.absorb_slice(o.y_s[k].data(), kappa); T.absorb_slice(o.u_s[k].data(), cnt(o.u_s[k])); T.absorb_slice(o.v_s[k].data(), cnt(o.v_s[k]));
-            if (x.empty()) throw LfException(LF_ERR_INCORRECT_LENGTH, "IncorrectLength");
-            LCCCS L; L.r = cm.r; L.v = o.v_s[k]; L.cm = o.y_s[k]; L.u = o.u_s[k]; L.x_w.assign(x.begin(), x.end() - D); L.h.assign(x.end() - D, x.end());
-            o.lc.push_back(std::move(L));
+        o.y_s.assign(K, HV(kappa * D, 0)); o.v_s.resize(K); o.u_s.resize(K);
+        // the dot-product commit (rings without the tensor path) lands with the last group; the tensor-core commit before the first
+        const bool y_early = pd.y_early || K == 1;
+        auto take_y = [&] {
+            for (int k = 1; k < K; ++k) for (size_t i = 0; i < kappa; ++i) std::memcpy(&o.y_s[k][i * D], pd.y_pin + (i * (K - 1) + (k - 1)) * D, 8 * D);
+            HV bsum(kappa * D, 0); const u64 bm = P->b % F::P;      // y_0 = cm - b (y_1 + b (y_2 + ...))
+            for (int k = K - 1; k >= 1; --k) for (size_t i = 0; i < kappa * D; ++i) bsum[i] = F::mul(F::add(bsum[i], o.y_s[k][i]), bm);
+            for (size_t i = 0; i < kappa * D; ++i) o.y_s[0][i] = F::sub(cm.cm[i], bsum[i]);
+        };
+        if (!y_early) { LF_CUDA(cudaEventSynchronize(pd.ev[pd.ngroups - 1])); take_y(); }
+        for (int g = 0; g < pd.ngroups; ++g) {
+            LF_CUDA(cudaEventSynchronize(pd.ev[g])); cudaEventDestroy(pd.ev[g]); pd.ev[g] = nullptr;
+            if (g == 0 && y_early) take_y();
+            const int k0 = pd.g0[g], c = pd.g0[g + 1] - k0;
+            auto t0 = std::chrono::steady_clock::now();
+            for (int k = k0; k < k0 + c; ++k) {
+                o.v_s[k].assign(pd.v_pin[g] + (size_t)(k - k0) * TAU * D, pd.v_pin[g] + (size_t)(k - k0 + 1) * TAU * D);
+                o.u_s[k].resize(t * D); for (size_t j = 0; j < t; ++j) std::memcpy(&o.u_s[k][j * D], pd.u_pin[g] + (j * c + (k - k0)) * D, 8 * D);      // [t][c] -> per piece
+                const HV& x = o.x_s[k];
+                T.absorb_slice(x.data(), cnt(x)); T.absorb_slice(o.y_s[k].data(), kappa); T.absorb_slice(o.u_s[k].data(), cnt(o.u_s[k])); T.absorb_slice(o.v_s[k].data(), cnt(o.v_s[k]));
+                if (x.empty()) throw LfException(LF_ERR_INCORRECT_LENGTH, "IncorrectLength");
+                LCCCS L; L.r = cm.r; L.v = o.v_s[k]; L.cm = o.y_s[k]; L.u = o.u_s[k]; L.x_w.assign(x.begin(), x.end() - D); L.h.assign(x.end() - D, x.end());
+                o.lc.push_back(std::move(L));
+            }
+            P->timings[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         }
-        P->timings[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return o;
     }
 
