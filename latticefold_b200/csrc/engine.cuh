@@ -337,8 +337,7 @@ template <class Rg> struct Engine {
             }
             LF_CUDA(cudaMalloc(&A->epi, sizeof t)); LF_CUDA(cudaMemcpyAsync(A->epi, &t, sizeof t, cudaMemcpyHostToDevice, st())); sync();
             A->a8_tiles = ntiles; A->a8_chunks = nchunks;
-            static bool attr_set = false;
-            if (!attr_set) { LF_CUDA(cudaFuncSetAttribute(cmma::k_commit_mma<Rg>, cudaFuncAttributeMaxDynamicSharedMemorySize, commit_mma_smem())); attr_set = true; }
+            LF_CUDA(cudaFuncSetAttribute(cmma::k_commit_mma<Rg>, cudaFuncAttributeMaxDynamicSharedMemorySize, commit_mma_smem()));      // per device
         }
     }
     static constexpr int commit_mma_smem() { return cmma::STAGES * (cmma::A_STAGE_BYTES + D * cmma::MAX_PIECES * cmma::J); }

@@ -890,14 +890,24 @@ template <class Rg> __global__ void __launch_bounds__(128)
 k_fold_sc_round2(const FoldScArgsT<typename Rg::W> a) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU, S = Rg::S;
     __shared__ u64 red[5 * TAU * 32];
-    __shared__ u64 s_mu[MAX_MU * TAU];
     __shared__ u64 s_corr[TAU];                              // 2048 * sum of all mu
+    extern __shared__ __align__(16) unsigned char dyn_smem[];   // n_f * TAU mu limbs, then the block's digits [table][32 pairs]
+    u64* s_mu = reinterpret_cast<u64*>(dyn_smem);
+    char4 (*s_dig)[32] = reinterpret_cast<char4 (*)[32]>(dyn_smem + (size_t)a.n_f * TAU * 8);
+    const int slot = blockIdx.y, X = threadIdx.x & 3, pl = threadIdx.x >> 2;
+    const size_t b0 = (size_t)blockIdx.x * 32, b = b0 + pl; const bool active = b < a.n_pairs;
+    // all digit loads of the block are issued up front (n_f / 4 independent 4-byte loads per thread, one 128-byte row per warp and
+    // table) instead of one dependent load per table inside the accumulation loop
+    for (int kd = threadIdx.x >> 5; kd < a.n_f; kd += 4) {
+        const int k = kd / TAU, d = kd - k * TAU; const int lane = threadIdx.x & 31;
+        char4 v = make_char4(0, 0, 0, 0);
+        if (b0 + lane < a.n_pairs) v = *reinterpret_cast<const char4*>(a.dig + (size_t)k * a.dig_stride + (size_t)(d * S + slot) * a.dig_pitch + 4 * (b0 + lane));
+        s_dig[kd][lane] = v;
+    }
     for (int i = threadIdx.x; i < a.n_f * TAU; i += blockDim.x) s_mu[i] = a.mu_pow[i];
     __syncthreads();
     if (threadIdx.x < TAU) { typename F::Sum sm; sm.clear(); for (int kd = 0; kd < a.n_f; ++kd) sm.add(s_mu[kd * TAU + threadIdx.x]); s_corr[threadIdx.x] = F::mul(F::reduce(sm), 2048); }
     __syncthreads();
-    const int slot = blockIdx.y, X = threadIdx.x & 3;
-    const size_t b = (size_t)blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2); const bool active = b < a.n_pairs;
     u64 hx[TAU];
 #pragma unroll
     for (int l = 0; l < TAU; ++l) hx[l] = 0;
@@ -909,8 +919,7 @@ k_fold_sc_round2(const FoldScArgsT<typename Rg::W> a) {
             for (int l = 0; l < TAU; ++l) acc[j][l].clear();
 #pragma unroll 2
         for (int kd = 0; kd < a.n_f; ++kd) {
-            const int k = kd / TAU, d = kd - k * TAU;
-            const char4 dd = *reinterpret_cast<const char4*>(a.dig + (size_t)k * a.dig_stride + (size_t)(d * S + slot) * a.dig_pitch + 4 * b);
+            const char4 dd = s_dig[kd][pl];
             const int a0 = dd.x, e0 = dd.y - dd.x, a1 = dd.z, e1 = dd.w - dd.z;
             const int P = a0 + X * (a1 - a0), Q = e0 + X * (e1 - e0);
             const u32 c0 = (u32)(P * P * P - P + 2048), c1 = (u32)(Q * (3 * P * P - 1) + 2048), c2 = (u32)(3 * P * Q * Q + 2048), c3 = (u32)(Q * Q * Q + 2048);
@@ -998,13 +1007,18 @@ k_fold_sc_round(const FoldScArgsT<typename Rg::W> a) {
         typename F::Acc s_mine[TAU], s_other[TAU]; typename F::Sum sum_mine[TAU];
 #pragma unroll
         for (int l = 0; l < TAU; ++l) { s_mine[l].clear(); s_other[l].clear(); sum_mine[l].clear(); }
+        // the next table's pair is requested before the current one is consumed (the loop is not unrolled: register budget)
+        u64 nx0[TAU], nx1[TAU];
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) ldg_pair(a.fh + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b, nx0[l], nx1[l]);
 #pragma unroll 1
         for (int kd = 0; kd < a.n_f; ++kd) {
             u64 t[TAU], mine[TAU], other[TAU], q[TAU];
 #pragma unroll
-            for (int l = 0; l < TAU; ++l) {
-                u64 p0, p1; ldg_pair(a.fh + (size_t)kd * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b, p0, p1);
-                const u64 sl = F::sub(p1, p0); t[l] = role ? sl : p0;
+            for (int l = 0; l < TAU; ++l) { const u64 sl = F::sub(nx1[l], nx0[l]); t[l] = role ? sl : nx0[l]; }
+            if (kd + 1 < a.n_f) {
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) ldg_pair(a.fh + (size_t)(kd + 1) * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b, nx0[l], nx1[l]);
             }
             if constexpr (PREP_SMEM) SF::mul_prepped(mine, t, s_mu[kd]); else SF::mul_prepped(mine, t, SF::prep(&s_mu[kd * TAU]));
 #pragma unroll

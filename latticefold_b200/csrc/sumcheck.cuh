@@ -73,7 +73,10 @@ template <class Rg> struct SumcheckDriver {
             a.fh = wp(sc->fh.cur); a.fh_pitch = sc->fh.pitch; a.fh_stride = sc->fh.stride;
             for (int l = 0; l < TAU; ++l) a.r1[l] = sc->r1[l];
             if (round1) E.launch("k_fold_sc_round1", [&] { k_fold_sc_round1<Rg><<<dim3(gx1, S), 128, 0, E.st()>>>(a); });
-            else if (round2d) E.launch("k_fold_sc_round2", [&] { k_fold_sc_round2<Rg><<<dim3(nblk, S), 128, 0, E.st()>>>(a); });
+            else if (round2d) {
+                // up to MAX_MU tables: 64 KB of dynamic shared memory (above the 48 KB default; per device, so set on every use)
+                LF_CUDA(cudaFuncSetAttribute(k_fold_sc_round2<Rg>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_MU * (TAU * 8 + 128)));
+                E.launch("k_fold_sc_round2", [&] { k_fold_sc_round2<Rg><<<dim3(nblk, S), 128, (size_t)sc->n_f * (TAU * 8 + 128), E.st()>>>(a); }); }
             else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(gx2, S), 128, 0, E.st()>>>(a); });
         } else {
             // one thread per (pair, evaluation point): see k_sc_points
