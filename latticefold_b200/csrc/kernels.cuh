@@ -762,6 +762,63 @@ k_sc_points(const ScGenericArgsT<typename Rg::W> a) {
     }
 }
 
+// The same per-point evaluation for ARBITRARY sums of products: any number of tables (one contiguous group: table k at base + k *
+// stride), any number of terms and factors -- the reference's `comb_fn` is an arbitrary closure; every one it ships is a sum of products
+// with ring coefficients (CCS of any shape, linearization/utils.rs:90-107; LatticeFold+ v0 (v1 v2 - v3), latticefold-plus/src/r1cs.rs:92;
+// the set-check and commitment-transformation batches, setchk.rs:155-186, cm.rs:285-307).  The term list lives in device memory
+// (term_off[n_terms + 1], idx[]); factors are re-read per term (L1 resident) instead of being held in registers.
+template <class W> struct ScTermsArgsT {
+    const W* base; size_t stride, pitch; int n_mles, deg, n_terms, lin;
+    const int* term_off; const int* idx; const u64* coef;      // coef: n_terms x D
+    size_t n_pairs; u64* partial;
+};
+template <class Rg> __global__ void __launch_bounds__(128)
+k_sc_terms(const ScTermsArgsT<typename Rg::W> a) {
+    typedef typename Rg::F F; typedef SlotField<Rg> SF; typedef typename Rg::W E; constexpr int TAU = Rg::TAU;
+    __shared__ u64 red[TAU * 128];
+    const int slot = blockIdx.y, npts = a.deg + 1, ppb = blockDim.x / npts;
+    const int e = threadIdx.x % npts, pl = threadIdx.x / npts;
+    E ev[TAU];
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) ev[l] = 0;
+    auto at_point = [&](int k, size_t b, E* out) {
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) {
+            u64 v0, v1; ldg_pair(a.base + (size_t)k * a.stride + (size_t)(slot * TAU + l) * a.pitch + 2 * b, v0, v1);
+            const u64 st = F::sub(v1, v0); u64 x = v0;
+#pragma unroll
+            for (int i = 0; i < SC_MAX_DEG; ++i) if (i < e) x = F::add(x, st);
+            out[l] = (E)x;
+        }
+    };
+    if (pl < ppb)
+    for (size_t b = (size_t)blockIdx.x * ppb + pl; b < a.n_pairs; b += (size_t)gridDim.x * ppb) {
+        E res[TAU];
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) res[l] = 0;
+#pragma unroll 1
+        for (int t = 0; t < a.n_terms; ++t) {
+            E term[TAU];
+#pragma unroll
+            for (int l = 0; l < TAU; ++l) term[l] = (E)a.coef[(size_t)t * Rg::D + slot * TAU + l];
+#pragma unroll 1
+            for (int f = a.term_off[t]; f < a.term_off[t + 1]; ++f) { E fac[TAU]; at_point(a.idx[f], b, fac); SF::mul_inl(term, term, fac); }
+            SF::add(res, res, term);
+        }
+        if (a.lin) { E last[TAU]; at_point(a.n_mles - 1, b, last); SF::mul_inl(res, res, last); }
+        SF::add(ev, ev, res);
+    }
+#pragma unroll
+    for (int l = 0; l < TAU; ++l) red[l * 128 + threadIdx.x] = (u64)ev[l];
+    __syncthreads();
+    if (threadIdx.x < npts * TAU) {
+        const int pe = threadIdx.x / TAU, l = threadIdx.x % TAU;
+        u64 acc = 0;
+        for (int q = 0; q < ppb; ++q) acc = F::add(acc, red[l * 128 + q * npts + pe]);
+        a.partial[((size_t)blockIdx.x * npts + pe) * Rg::D + slot * TAU + l] = acc;
+    }
+}
+
 // ---- FOLD combination function, b = 2 (folding/utils.rs:273-325):
 //   g(x) = v0 v1 + v2 v3 + v4 * h(x),   h = sum_{k<2K} sum_{d<tau} mu_k^{d+1} (f_{k,d}^3 - f_{k,d})
 // h is a cubic along the line through a pair, so 4 points determine it; the degree-4 message needs 5 points of g.

@@ -173,7 +173,6 @@ template <class Rg> struct Prover {
         // sumcheck list: for each term with c_i != 0, the Mz named by S_i; eq(beta,.) last (linearization/utils.rs:63-88)
         std::vector<int> list; for (size_t i = 0; i < P->q; ++i) { bool z = true; for (int l = 0; l < D; ++l) z = z && P->c[i * D + l] == 0; if (z) continue; for (int j : P->S[i]) list.push_back(j); }
         const int Mn = (int)list.size() + 1;
-        if (Mn > SC_MAX_MLES || (int)P->q > SC_MAX_TERMS) throw LfException(LF_ERR_UNSUPPORTED, "CCS shape exceeds SC_MAX_MLES / SC_MAX_TERMS");
         lf_sumcheck sc; sc.ctx = P->ctx; sc.nv = s; sc.deg = (int)P->d + 1; sc.kind = LF_COMB_LIN; sc.len = m; sc.sharded = world() > 1;
         SumcheckDriver<Rg> drv(P->ctx, &sc);
         SumcheckDriver<Rg>::alloc_group(E, sc.dense, Mn, m);
@@ -184,9 +183,7 @@ template <class Rg> struct Prover {
         E.eq_table(beta.data(), s, dense + (size_t)(Mn - 1) * sc.dense.stride, sc.dense.pitch, (size_t)rank() * m, m);
         // LIN comb (linearization/utils.rs:90-107): vals[] is indexed by the CCS matrix index j.  The list position of
         // matrix j coincides with j for R1CS and the degree-3 CCS; reproduce the reference literally and refuse anything else.
-        sc.gen.n_mles = Mn; sc.gen.deg = sc.deg; sc.gen.lin = 1; sc.gen.n_terms = (int)P->q;
-        for (size_t i = 0; i < P->q; ++i) { if (P->S[i].size() > SC_MAX_FACTORS) throw LfException(LF_ERR_UNSUPPORTED, "CCS multiset too large"); sc.gen.term_len[i] = (int)P->S[i].size();
-            for (size_t f = 0; f < P->S[i].size(); ++f) { int j = P->S[i][f]; if (j < 0 || j >= Mn) throw LfException(LF_ERR_INCORRECT_LENGTH, "comb index outside MLE list"); sc.gen.term_idx[i][f] = j; } }
+        drv.set_terms(Mn, sc.deg, true, P->S);
         sc.d_coef = E.template dalloc<u64>(P->q * D);
         E.h2d(sc.d_coef, P->c.data(), P->q * D * 8);
         std::vector<u64> point; o.msgs = run_sumcheck(drv, T, point);

@@ -252,7 +252,7 @@ template <class Rg> struct RingOpsImpl final : RingOps {
             if (degree != 4 || M != 5 + comb->n_mu * Rg::TAU) throw LfException(LF_ERR_INVALID_ARG, "FOLD: need degree 2b and 5 + n_mu*tau MLEs");
             n_dense = 5;
         } else {
-            if (M > SC_MAX_MLES || degree > SC_MAX_DEG || comb->n_terms > SC_MAX_TERMS || comb->n_terms < 1) throw LfException(LF_ERR_UNSUPPORTED, "PRODUCTS/LIN: at most 8 MLEs, degree 7, 4 terms");
+            if (degree > SC_MAX_DEG || comb->n_terms < 1) throw LfException(LF_ERR_UNSUPPORTED, "PRODUCTS/LIN: degree at most 7, at least one term");
         }
         auto fill = [&](lf_sumcheck::Group& g, int first, int count) {
             SumcheckDriver<Rg>::alloc_group(E, g, count, n);
@@ -263,10 +263,9 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         fill(sc->dense, 0, n_dense);
         if (comb->kind == LF_COMB_FOLD) { fill(sc->fh, 5, M - 5); drv.set_mu(comb->mu_host, comb->n_mu); }
         else {
-            sc->gen.n_mles = M; sc->gen.deg = degree; sc->gen.lin = comb->kind == LF_COMB_LIN; sc->gen.n_terms = comb->n_terms;
-            int o = 0;
-            for (int t = 0; t < comb->n_terms; ++t) { if (comb->idx_len[t] > SC_MAX_FACTORS) throw LfException(LF_ERR_UNSUPPORTED, "more than 4 factors in one term"); sc->gen.term_len[t] = comb->idx_len[t];
-                for (int f = 0; f < comb->idx_len[t]; ++f) { int j = comb->idx[o++]; if (j < 0 || j >= M) throw LfException(LF_ERR_INVALID_ARG, "comb index outside MLE list"); sc->gen.term_idx[t][f] = j; } }
+            std::vector<std::vector<int>> terms; int o = 0;
+            for (int t = 0; t < comb->n_terms; ++t) { if (comb->idx_len[t] < 0) throw LfException(LF_ERR_INVALID_ARG, "negative term length"); terms.emplace_back(comb->idx + o, comb->idx + o + comb->idx_len[t]); o += comb->idx_len[t]; }
+            drv.set_terms(M, degree, comb->kind == LF_COMB_LIN, terms);
             sc->d_coef = E.template dalloc<u64>((size_t)comb->n_terms * Rg::D);
             LF_CUDA(cudaMemcpyAsync(sc->d_coef, comb->coef_host, (size_t)comb->n_terms * Rg::D * 8, cudaMemcpyHostToDevice, E.st())); E.sync();
         }

@@ -16,6 +16,8 @@ struct lf_sumcheck {
     int n_f = 0;
     lf::u64* d_mu_pow = nullptr;      // n_f x TAU
     lf::u64* d_coef = nullptr;        // PRODUCTS/LIN term coefficients, n_terms x D
+    // general term list (any number of tables / terms / factors: k_sc_terms); empty when the shape fits the register-resident kernel
+    int* d_term_off = nullptr; int* d_term_idx = nullptr; int n_terms_general = 0;
     lf::ScGenericArgsT<lf::u64> gen;  // term structure (the table pointers are filled per launch, in the ring's word type)
     size_t len = 0;                   // current LOCAL table length (2^(nv - applied challenges) / ranks while sharded)
     int applied = 0;
@@ -41,6 +43,7 @@ template <class Rg> struct SumcheckDriver {
     void free_all() {
         for (lf_sumcheck::Group* g : {&sc->dense, &sc->fh}) { if (g->cur_owned && g->cur != g->nxt && g->cur != g->alt) E.dfree(g->cur); E.dfree(g->nxt); E.dfree(g->alt); g->cur = g->nxt = g->alt = nullptr; g->nxt_cap = g->alt_cap = 0; }
         E.dfree(sc->d_mu_pow); E.dfree(sc->d_coef); sc->d_mu_pow = sc->d_coef = nullptr;
+        E.dfree(sc->d_term_off); E.dfree(sc->d_term_idx); sc->d_term_off = sc->d_term_idx = nullptr;
     }
     // mu (n_mu ring elements, slot-constant) -> mu_k^{d+1} for d < tau as slot-field elements (folding/utils.rs:293-322)
     void set_mu(const u64* mu_host, int n_mu) {
@@ -54,6 +57,20 @@ template <class Rg> struct SumcheckDriver {
         }
         sc->d_mu_pow = E.template dalloc<u64>(pw.size());
         E.h2d(sc->d_mu_pow, pw.data(), pw.size() * 8);
+    }
+
+    // PRODUCTS / LIN term structure: term t multiplies the tables idx[off[t] .. off[t+1]) (and its coefficient).  Shapes within
+    // SC_MAX_MLES / SC_MAX_TERMS / SC_MAX_FACTORS run on the register-resident kernel, anything else on the general one.
+    void set_terms(int n_mles, int deg, bool lin, const std::vector<std::vector<int>>& terms) {
+        if (deg < 1 || deg > SC_MAX_DEG) throw LfException(LF_ERR_UNSUPPORTED, "sumcheck degree above SC_MAX_DEG (7)");
+        sc->gen.n_mles = n_mles; sc->gen.deg = deg; sc->gen.lin = lin ? 1 : 0; sc->gen.n_terms = (int)terms.size();
+        bool small = n_mles <= SC_MAX_MLES && (int)terms.size() <= SC_MAX_TERMS;
+        for (auto& t : terms) { small = small && (int)t.size() <= SC_MAX_FACTORS; for (int j : t) if (j < 0 || j >= n_mles) throw LfException(LF_ERR_INVALID_ARG, "comb index outside MLE list"); }
+        if (small) { for (size_t t = 0; t < terms.size(); ++t) { sc->gen.term_len[t] = (int)terms[t].size(); for (size_t f = 0; f < terms[t].size(); ++f) sc->gen.term_idx[t][f] = terms[t][f]; } return; }
+        std::vector<int> off(1, 0), idx; for (auto& t : terms) { idx.insert(idx.end(), t.begin(), t.end()); off.push_back((int)idx.size()); }
+        sc->n_terms_general = (int)terms.size();
+        sc->d_term_off = E.template dalloc<int>(off.size()); sc->d_term_idx = E.template dalloc<int>(std::max<size_t>(idx.size(), 1));
+        E.h2d(sc->d_term_off, off.data(), off.size() * sizeof(int)); if (!idx.empty()) E.h2d(sc->d_term_idx, idx.data(), idx.size() * sizeof(int));
     }
 
     // prove_round's evaluation half: out_host = (deg+1) x D limbs
@@ -82,6 +99,11 @@ template <class Rg> struct SumcheckDriver {
             // one thread per (pair, evaluation point): see k_sc_points
             const int ppb = 128 / ne;
             nblk = (unsigned)std::min<size_t>((n_pairs + ppb - 1) / ppb, 148 * 16); partial = E.partial_dev((size_t)nblk * ne * D);
+            if (sc->n_terms_general) {
+                ScTermsArgsT<W> g; g.base = wp(sc->dense.cur); g.stride = sc->dense.stride; g.pitch = sc->dense.pitch; g.n_mles = sc->gen.n_mles; g.deg = sc->gen.deg;
+                g.n_terms = sc->n_terms_general; g.lin = sc->gen.lin; g.term_off = sc->d_term_off; g.idx = sc->d_term_idx; g.coef = sc->d_coef; g.n_pairs = n_pairs; g.partial = partial;
+                E.launch("k_sc_generic", [&] { k_sc_terms<Rg><<<dim3(nblk, S), 128, 0, E.st()>>>(g); });
+            } else {
             ScGenericArgsT<W> a; const auto& gen = sc->gen;
             a.n_mles = gen.n_mles; a.deg = gen.deg; a.n_terms = gen.n_terms; a.lin = gen.lin;
             for (int t = 0; t < SC_MAX_TERMS; ++t) { a.term_len[t] = gen.term_len[t]; for (int f = 0; f < SC_MAX_FACTORS; ++f) a.term_idx[t][f] = gen.term_idx[t][f]; }
@@ -97,6 +119,7 @@ template <class Rg> struct SumcheckDriver {
                 else if (a.n_mles <= 5) k_sc_points<Rg, 5><<<g, 128, 0, E.st()>>>(a);      // the degree-three CCS: four matrices + eq
                 else k_sc_points<Rg, 8><<<g, 128, 0, E.st()>>>(a);
             });
+            }
         }
         u64* d_out = E.small_dev((size_t)ne * D);
         if (sc->sharded) E.reduce_partials_allreduce(partial, (int)nblk, (size_t)ne * D, d_out);      // one all-reduce of (deg+1) ring elements per round, fused with the reduction

@@ -273,3 +273,47 @@ def test_nifs_degree_three_ccs_matches_oracle(ctx, oracle, oracle_ops, gpu, W, B
 def test_ops_ntt_mul_matches_oracle(ctx, oracle):
     a, b = rand_elems(G, 9, 41), rand_elems(G, 9, 42)
     assert np.array_equal(ctx.ntt_mul(G, a, b), oracle.ntt_mul(G, a, b))
+
+
+def _lfplus_setchk_terms(n_M, ncols, n_m):
+    """term list of the LatticeFold+ set-check batch (latticefold-plus/src/setchk.rs:155-186):
+    sum_i rc^i eq_i sum_j alpha_i^j (m_ij^2 - m'_ij)  +  sum_i rc^(n_M+i) alpha eq (m^2 - m'); tables laid out as the reference pushes them"""
+    terms = []
+    for i in range(n_M):
+        s = i * (2 * ncols + 1)
+        for j in range(ncols):
+            terms += [[s + 2 * ncols, s + 2 * j, s + 2 * j], [s + 2 * ncols, s + 2 * j + 1]]
+    base = n_M * (2 * ncols + 1)
+    for i in range(n_m):
+        s = base + 3 * i
+        terms += [[s + 2, s, s], [s + 2, s + 1]]
+    return terms, base + 3 * n_m
+
+
+@pytest.mark.parametrize("nv,shape", [(5, "r1cs"), (4, "setchk"), (6, "cm"), (3, "wide")])
+def test_sumcheck_general_terms_lfplus_shapes(ctx, oracle, gpu, nv, shape):
+    """sums of products beyond the register-resident kernel's 8 tables / 4 terms (k_sc_terms): the comb functions of LatticeFold+
+    -- v0 (v1 v2 - v3) (r1cs.rs:92), the set-check batch (setchk.rs:155-186), the commitment-transformation batch (cm.rs:285-307) --
+    and a wide random sum of products, against the oracle's sumcheck"""
+    if shape == "r1cs":
+        M, deg, idx = 4, 3, [[0, 1, 2], [0, 3]]
+        coef = np.stack([const_el(1), const_el(P - 1)])
+    elif shape == "setchk":
+        idx, M = _lfplus_setchk_terms(2, 3, 2); deg = 3
+        coef = rand_sf_broadcast(G, len(idx), 71)
+    elif shape == "cm":
+        L_, Mlen = 2, 2; M = 1 + L_ * (4 + 4 * Mlen) + 2; deg = 2; idx = []
+        for l in range(L_):
+            li = 1 + l * (4 + 4 * Mlen)
+            idx += [[0, li + q] for q in range(4 + 4 * Mlen)] + [[li, M - 2], [li, M - 1]]
+        coef = rand_sf_broadcast(G, len(idx), 72)
+    else:
+        M, deg = 19, 4
+        rng = np.random.default_rng(9)
+        idx = [list(rng.integers(0, M, int(rng.integers(1, 5)))) for _ in range(23)]
+        coef = rand_elems(G, len(idx), 73)
+    mles = rand_elems(G, M * (1 << nv), 70).reshape(M, 1 << nv, D)
+    comb = dict(kind="products", coef=coef, idx=idx)
+    emsgs, epoint, efinal = oracle.sumcheck_prove(G, oracle.transcript(G), mles, nv, deg, comb, want_final=True)
+    msgs, point, final = gpu.MLSumcheck.prove_as_subprotocol(ctx, gpu.Transcript(G), [ctx.upload(m) for m in mles], nv, deg, comb, want_final=True)
+    assert np.array_equal(msgs, emsgs) and np.array_equal(point, epoint) and np.array_equal(final, efinal)
