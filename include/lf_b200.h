@@ -231,6 +231,13 @@ lf_status lf_nifs_prove(lf_prover* p, const lf_problem* in, lf_transcript* t, ui
 lf_status lf_nifs_verify(const lf_problem* in, lf_transcript* t, const uint64_t* proof, uint64_t* out_lcccs);
 /* LFLinearizationVerifier::verify (nifs/linearization.rs:192-285) on the linearization part of a proof (msgs, v, u), host code.   */
 lf_status lf_linearization_verify(const lf_problem* in, lf_transcript* t, const uint64_t* lin_proof, uint64_t* out_lcccs);
+/* Proof wire format: the bytes of `LFProof::serialize_with_mode(.., Compress::Yes)` (nifs.rs:28-34,
+ * examples/e2e.rs:126-146; ark-serialize 0.4: u64-LE length prefixes, canonical little-endian field elements) <-> the flat u64 proof
+ * of lf_nifs_prove.  Host code.  Deserialisation validates every length prefix against the problem's shape and rejects non-canonical
+ * field elements (LF_ERR_INCORRECT_LENGTH / LF_ERR_INVALID_ARG), as arkworks does.                                                 */
+uint64_t lf_proof_wire_bytes(const lf_problem* shape);
+lf_status lf_proof_serialize(const lf_problem* shape, const uint64_t* proof_words, uint8_t* out_bytes);
+lf_status lf_proof_deserialize(const lf_problem* shape, const uint8_t* bytes, uint64_t n_bytes, uint64_t* out_proof_words);
 /* the same step with both witnesses already resident in HBM (bench.py's `value`): witnesses are handles made by
  * lf_prover_upload_witness; the folded witness stays on the device and is returned as a new handle                 */
 typedef struct lf_witness lf_witness;

@@ -5,4 +5,4 @@ Importing the package does not load CUDA; `latticefold_b200.lib()` loads the C-A
 """
 from . import synth  # noqa: F401
 from .api import (AjtaiCommitmentScheme, Context, DeviceVec, LfError, MLSumcheck, NIFSProver, NttPlan, SparseMatrix,  # noqa: E402,F401
-                  Transcript, lib, linearization_verify, nifs_verify, ntt_root)
+                  Transcript, lib, linearization_verify, nifs_verify, ntt_root, proof_from_bytes, proof_to_bytes)

@@ -32,7 +32,7 @@ lf_sumcheck_finish lf_sumcheck_free lf_transcript_create lf_transcript_clone lf_
 lf_transcript_absorb_base lf_transcript_absorb_tag lf_transcript_get_challenge lf_transcript_get_short_challenge
 lf_transcript_permutations lf_host_poseidon_backend lf_rot_lin_combination lf_prover_create lf_prover_free lf_proof_words lf_lcccs_words
 lf_witness_f_from_w_ccs lf_linearize lf_nifs_prove lf_nifs_verify lf_prover_upload_witness lf_witness_free lf_witness_download_f
-lf_nifs_prove_resident lf_linearization_verify lf_linearize_resident lf_witness_commit lf_prover_last_timings lf_prover_timing_detail
+lf_proof_wire_bytes lf_proof_serialize lf_proof_deserialize lf_nifs_prove_resident lf_linearization_verify lf_linearize_resident lf_witness_commit lf_prover_last_timings lf_prover_timing_detail
 lf_ntt_root lf_ntt_plan_create lf_ntt_plan_free lf_ntt_forward_device lf_ntt_inverse_device lf_ntt_forward_host lf_ntt_inverse_host
 lf_ntt_pointwise_mul_device lf_ntt_negacyclic_mul_host""".split()
 
@@ -175,6 +175,10 @@ def lib():
     L.lf_linearize.argtypes = [vp, C.POINTER(Problem), vp, u64p, u64p]
     L.lf_nifs_prove.argtypes = [vp, C.POINTER(Problem), vp, u64p, u64p, u64p]
     L.lf_nifs_verify.argtypes = [C.POINTER(Problem), vp, u64p, u64p]
+    L.lf_proof_wire_bytes.restype = C.c_uint64
+    L.lf_proof_wire_bytes.argtypes = [C.POINTER(Problem)]
+    L.lf_proof_serialize.argtypes = [C.POINTER(Problem), u64p, C.POINTER(C.c_uint8)]
+    L.lf_proof_deserialize.argtypes = [C.POINTER(Problem), C.POINTER(C.c_uint8), C.c_uint64, u64p]
     L.lf_linearization_verify.argtypes = [C.POINTER(Problem), vp, u64p, u64p]
     L.lf_linearize_resident.argtypes = [vp, C.POINTER(Problem), vp, vp, u64p, u64p]
     L.lf_witness_commit.argtypes = [vp, vp, u64p]
@@ -593,6 +597,26 @@ def nifs_verify(prob, transcript, proof):
     if rc:
         raise LfError(rc, L.lf_last_error(None).decode())
     return lc
+
+
+def proof_to_bytes(prob, proof):
+    """LFProof::serialize_with_mode(Compress::Yes) of a flat u64 proof (nifs.rs:28-34; examples/e2e.rs:126-146)"""
+    L = lib(); P, keep = make_problem({k: v for k, v in prob.items() if k not in ("A", "w_i_f", "w_acc_f")})
+    proof = np.ascontiguousarray(proof, dtype=np.uint64); out = np.empty(int(L.lf_proof_wire_bytes(C.byref(P))), dtype=np.uint8)
+    rc = L.lf_proof_serialize(C.byref(P), ptr(proof), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    if rc:
+        raise LfError(rc, L.lf_last_error(None).decode())
+    return out.tobytes()
+
+
+def proof_from_bytes(prob, data):
+    """the inverse, validating length prefixes and canonical field elements like ark-serialize's deserializer"""
+    L = lib(); P, keep = make_problem({k: v for k, v in prob.items() if k not in ("A", "w_i_f", "w_acc_f")})
+    buf = np.frombuffer(bytes(data), dtype=np.uint8); out = np.empty(int(L.lf_proof_words(C.byref(P))), dtype=np.uint64)
+    rc = L.lf_proof_deserialize(C.byref(P), buf.ctypes.data_as(C.POINTER(C.c_uint8)), buf.size, ptr(out))
+    if rc:
+        raise LfError(rc, L.lf_last_error(None).decode())
+    return out
 
 
 def linearization_verify(prob, transcript, lin_proof):

@@ -186,6 +186,9 @@ lf_status lf_rot_lin_combination(int32_t ring, const uint64_t* rho, const uint64
 // ---- prover
 uint64_t lf_proof_words(const lf_problem* P) { uint64_t r = 0; guard(nullptr, [&] { r = ops(P->ring)->proof_words(P); }); return r; }
 uint64_t lf_lcccs_words(const lf_problem* P) { uint64_t r = 0; guard(nullptr, [&] { r = ops(P->ring)->lcccs_words(P); }); return r; }
+uint64_t lf_proof_wire_bytes(const lf_problem* P) { uint64_t r = 0; guard(nullptr, [&] { r = ops(P->ring)->wire_bytes(P); }); return r; }
+lf_status lf_proof_serialize(const lf_problem* P, const uint64_t* w, uint8_t* out) { return guard(nullptr, [&] { if (!P || !w || !out) throw LfException(LF_ERR_INVALID_ARG, "null argument"); ops(P->ring)->wire_serialize(P, w, out); }); }
+lf_status lf_proof_deserialize(const lf_problem* P, const uint8_t* in, uint64_t n, uint64_t* w) { return guard(nullptr, [&] { if (!P || !in || !w) throw LfException(LF_ERR_INVALID_ARG, "null argument"); ops(P->ring)->wire_deserialize(P, in, n, w); }); }
 lf_status lf_prover_create(lf_ctx* c, const lf_problem* sh, lf_prover** out) { *out = nullptr; return guard(c, [&] { ops(c->ring)->prover_create(c, sh, out); }); }
 void lf_prover_free(lf_prover* p) { if (!p) return; if (p->aux) lf_ctx_destroy(p->aux); for (auto* m : p->M) lf_sparse_free(p->ctx, m); lf_ajtai_free(p->ctx, p->A); delete p; }
 lf_status lf_prover_upload_witness(lf_prover* p, const uint64_t* f_host, lf_witness** out) { *out = nullptr; return guard(p->ctx, [&] { ops(p->ring)->prover_upload_witness(p, f_host, out); }); }

@@ -4,6 +4,7 @@
 #pragma once
 #include "prover.cuh"
 #include "verifier_host.hpp"
+#include "wire_host.hpp"
 
 struct lf_transcript { int ring; void* impl; };      // impl = lf::Transcript<Rg>*
 
@@ -19,6 +20,9 @@ struct RingOps {
     virtual void witness_free(lf_prover* p, lf_witness* w) = 0;
     virtual uint64_t proof_words(const lf_problem* P) = 0;
     virtual uint64_t lcccs_words(const lf_problem* P) = 0;
+    virtual uint64_t wire_bytes(const lf_problem* P) = 0;
+    virtual void wire_serialize(const lf_problem* P, const uint64_t* w, uint8_t* out) = 0;
+    virtual void wire_deserialize(const lf_problem* P, const uint8_t* in, uint64_t n, uint64_t* w) = 0;
     virtual void* tr_new() = 0;
     virtual void* tr_clone(const void* t) = 0;
     virtual void tr_free(void* t) = 0;
@@ -87,6 +91,9 @@ template <class Rg> struct RingOpsImpl final : RingOps {
     void sumcheck_free(lf_sumcheck* sc) override { SumcheckDriver<Rg> drv(sc->ctx, sc); drv.free_all(); delete sc; }
     void witness_free(lf_prover* p, lf_witness* w) override { Prover<Rg> pr(p); pr.free_witness(w); }
     uint64_t proof_words(const lf_problem* P) override { return Prover<Rg>::proof_words_of(*P); }
+    uint64_t wire_bytes(const lf_problem* P) override { return Wire<Rg>::bytes(*P); }
+    void wire_serialize(const lf_problem* P, const uint64_t* w, uint8_t* out) override { Wire<Rg>::serialize(*P, w, out); }
+    void wire_deserialize(const lf_problem* P, const uint8_t* in, uint64_t n, uint64_t* w) override { Wire<Rg>::deserialize(*P, in, n, w); }
     uint64_t lcccs_words(const lf_problem* P) override { return (P->s + Rg::TAU + P->kappa + P->t + P->l + 1) * (u64)Rg::D; }
     void* tr_new() override { return new Transcript<Rg>(); }
     void* tr_clone(const void* t) override { return new Transcript<Rg>(*(const Transcript<Rg>*)t); }

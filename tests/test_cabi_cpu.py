@@ -203,3 +203,37 @@ def test_ring_describe_and_slot_product_agree_with_oracle(oracle, ring):
     assert (info.p, info.d, info.n_slots, info.tau) == (R["p"], R["d"], R["S"], R["tau"]) and info.nu == oracle.info(ring)["nu"]
     a = synth.uniform_field(R["p"], 5 * R["d"], 31).reshape(5, R["d"]); b = synth.uniform_field(R["p"], 5 * R["d"], 32).reshape(5, R["d"])
     assert np.array_equal(synth.sf_mul(ring, a, b, int(info.nu)), oracle.ntt_mul(ring, a, b))
+
+
+@pytest.mark.parametrize("ring,W,B,L,b,K,kappa,kind,degree", VERIFY_CASES[:3])
+def test_proof_wire_format_roundtrip_and_validation(oracle, oracle_ops, ring, W, B, L, b, K, kappa, kind, degree):
+    """LFProof::serialize_with_mode(Compress::Yes) restated (nifs.rs:28-34, examples/e2e.rs:126-146; csrc/wire_host.hpp): size formula,
+    round trip, field order (the v of the linearization proof sits right behind its sumcheck), and the deserialiser's validation"""
+    prob = synth.make_instance(ring, W, B, L, b, K, kappa, kind=kind, config_id=23, ops=oracle_ops, degree=degree)
+    proof, lc, _, _ = oracle.nifs_prove(prob, oracle.transcript(ring))
+    R = synth.RINGS[ring]; d, tau, fb = R["d"], R["tau"], (8 if R["p"] >> 32 else 4)
+    ccs = prob["ccs"]; s, t, l = ccs["s"], ccs["t"], ccs["l"]; rb = d * fb
+    vec = lambda n: 8 + n * rb
+    want = (8 + s * vec(ccs["d"] + 2) + vec(tau) + vec(t)) + 2 * (4 * 8 + K * (vec(t) + vec(tau) + vec(l + 1) + vec(kappa))) + (8 + s * vec(2 * b + 1) + 2 * 8 + 2 * K * (vec(tau) + vec(t)))
+    data = lf.proof_to_bytes(prob, proof)
+    assert len(data) == want
+    assert np.array_equal(lf.proof_from_bytes(prob, data), proof)
+    assert int.from_bytes(data[:8], "little") == s and int.from_bytes(data[8:16], "little") == ccs["d"] + 2
+    first = np.frombuffer(data[16:16 + rb], dtype="<u8" if fb == 8 else "<u4").astype(np.uint64)
+    assert np.array_equal(first, proof[:d])                                       # first evaluation of the first round message
+    off_v = 8 + s * vec(ccs["d"] + 2)
+    assert int.from_bytes(data[off_v:off_v + 8], "little") == tau
+    # the verifier accepts what comes back from the wire
+    assert np.array_equal(lf.nifs_verify(prob, lf.Transcript(ring), lf.proof_from_bytes(prob, data)), lc)
+    bad = bytearray(data); bad[0] ^= 1                                            # wrong length prefix
+    with pytest.raises(lf.LfError) as e:
+        lf.proof_from_bytes(prob, bytes(bad))
+    assert e.value.code == -5
+    bad = bytearray(data); bad[16:16 + fb] = (R["p"]).to_bytes(fb, "little")      # non-canonical field element (= p)
+    with pytest.raises(lf.LfError) as e:
+        lf.proof_from_bytes(prob, bytes(bad))
+    assert e.value.code == -21
+    with pytest.raises(lf.LfError):
+        lf.proof_from_bytes(prob, data[:-1])
+    with pytest.raises(lf.LfError):
+        lf.proof_from_bytes(prob, data + b"\\0")
