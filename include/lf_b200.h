@@ -67,6 +67,14 @@ void* lf_ctx_stream(lf_ctx* ctx);                        /* the cudaStream_t eve
 uint64_t lf_ctx_launches(const lf_ctx* ctx);
 /* measurement aid: with profiling on, every kernel launch is bracketed by CUDA events on the context's stream;
  * the report is one line "kernel_name launches total_ms" per kernel.  Off by default (it adds two event records per launch). */
+/* Representation of the WITNESS-SIZED host vectors (lf_vec_upload / lf_vec_download, lf_ajtai_create, lf_sparse_create values,
+ * lf_prover_upload_witness / lf_witness_download_f, the witness arguments of lf_nifs_prove / lf_linearize):
+ *   LF_REPR_CANONICAL  (default) canonical little-endian limbs, the image of a Vec<R> after into_bigint()
+ *   LF_REPR_MONTGOMERY           ark-ff 0.4 Montgomery limbs (a * 2^64 mod p per base-field limb): the memory of a Vec<R> as it is
+ * The conversion rides on the layout kernels of the copy.  Everything small (commitments, proofs, challenges, LCCCS fields,
+ * transcript data) is canonical in either mode.                                                                              */
+enum { LF_REPR_CANONICAL = 0, LF_REPR_MONTGOMERY = 1 };
+lf_status lf_ctx_set_bulk_repr(lf_ctx* ctx, int32_t repr);
 lf_status lf_ctx_profile(lf_ctx* ctx, int32_t enable);
 lf_status lf_ctx_profile_report(lf_ctx* ctx, char* buf, size_t buf_len);
 

@@ -23,7 +23,7 @@ LF_COMB_PRODUCTS, LF_COMB_LIN, LF_COMB_FOLD = 0, 1, 2
 FORM_NTT, FORM_COEFF = 0, 1
 
 # every symbol include/lf_b200.h declares (tests check that the built library exports all of them)
-SYMBOLS = """lf_ring_describe lf_ctx_create lf_ctx_destroy lf_last_error lf_ctx_sync lf_ctx_stream lf_ctx_launches lf_ctx_profile lf_ctx_profile_report lf_ctx_set_shard lf_ctx_collectives lf_nccl_unique_id lf_ctx_set_shard_nccl lf_ctx_p2p_export lf_ctx_p2p_import
+SYMBOLS = """lf_ring_describe lf_ctx_create lf_ctx_destroy lf_last_error lf_ctx_sync lf_ctx_stream lf_ctx_launches lf_ctx_set_bulk_repr lf_ctx_profile lf_ctx_profile_report lf_ctx_set_shard lf_ctx_collectives lf_nccl_unique_id lf_ctx_set_shard_nccl lf_ctx_p2p_export lf_ctx_p2p_import
 lf_vec_upload lf_vec_download lf_vec_len lf_vec_form lf_vec_free lf_crt lf_icrt lf_gadget_decompose lf_gadget_recompose
 lf_decompose_to_vec lf_fhat lf_ajtai_create lf_ajtai_free lf_ajtai_kappa lf_ajtai_width lf_commit lf_commit_batch lf_commit_coeff
 lf_decompose_and_commit_coeff lf_decompose_and_commit_ntt lf_commit_pieces
@@ -125,6 +125,7 @@ def lib():
     L.lf_ctx_p2p_import.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
     L.lf_ctx_collectives.restype = C.c_uint64
     L.lf_ctx_collectives.argtypes = [vp]
+    L.lf_ctx_set_bulk_repr.argtypes = [vp, C.c_int32]
     L.lf_ctx_profile.argtypes = [vp, C.c_int32]
     L.lf_ctx_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.lf_vec_upload.argtypes = [vp, u64p, C.c_size_t, C.c_int32, C.POINTER(vp)]
@@ -352,6 +353,10 @@ class Context:
                 self.p2p = True
             else:
                 self.L.lf_ctx_p2p_import(self.h, rank, world, None)
+
+    def set_bulk_repr(self, montgomery):
+        """witness-sized host vectors are arkworks Montgomery limbs (a * 2^64 mod p) instead of canonical ones"""
+        self.check(self.L.lf_ctx_set_bulk_repr(self.h, 1 if montgomery else 0))
 
     def collectives(self):
         return int(self.L.lf_ctx_collectives(self.h))

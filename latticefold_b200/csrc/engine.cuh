@@ -63,6 +63,9 @@ struct lf_ctx {
     // size-keyed cache of device blocks.  Every use is on this context's single stream, so a block handed back by dfree can be
     // re-issued at once (stream order serialises the old and the new user); steady-state prover steps allocate nothing.
     std::unordered_multimap<size_t, void*> block_cache; std::unordered_map<void*, size_t> block_size; size_t cached_bytes = 0;
+    // blocks whose last use may still be pending on this stream when ANOTHER stream (the prover's auxiliary one) could be handed them:
+    // they return to the cache only at the next synchronisation of this stream (upload staging buffers, see Engine::dfree_later)
+    std::vector<void*> deferred_free;
     // pinned bump arena: staging for small async H2D copies and landing zone for async D2H results; reset per prover step
     unsigned char* h_arena = nullptr; size_t arena_size = 0, arena_off = 0;
     // column / hypercube sharding across the GPUs of one box: rank, world and the collective the host side
@@ -79,6 +82,7 @@ struct lf_ctx {
                   // channel 1 outlives any one prover's auxiliary context (the flags are monotone counters that are never reset), so
                   // its call sequence is kept here, in the owning context; an auxiliary context points at its parent
                   unsigned long long aux_calls = 0, aux_blocks = 0; XGpu* parent = nullptr; } xg;
+    int bulk_repr = 0;             // LF_REPR_CANONICAL / LF_REPR_MONTGOMERY for witness-sized host vectors (lf_ctx_set_bulk_repr)
     bool profiling = false;
     struct ProfRec { const char* name; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
@@ -136,7 +140,8 @@ template <class Rg> struct Engine {
         if (c->d_partial_words < words) { if (c->d_partial) { LF_CUDA(cudaStreamSynchronize(st())); cudaFree(c->d_partial); } size_t w = std::max(words, (size_t)1 << 20); LF_CUDA(cudaMalloc(&c->d_partial, w * 8)); c->d_partial_words = w; }
         return c->d_partial;
     }
-    void sync() { LF_CUDA(cudaStreamSynchronize(st())); }
+    void sync() { LF_CUDA(cudaStreamSynchronize(st())); for (void* p : c->deferred_free) dfree(p); c->deferred_free.clear(); }
+    void dfree_later(void* p) { if (p) c->deferred_free.push_back(p); }
     // ---- pinned arena (no synchronisation: the staged bytes stay untouched until arena_reset at the next step)
     void* arena_alloc(size_t bytes, bool may_wrap = true) {
         if (!c->h_arena) { c->arena_size = (size_t)64 << 20; LF_CUDA(cudaMallocHost(&c->h_arena, c->arena_size)); c->arena_off = 0; }
@@ -243,17 +248,21 @@ template <class Rg> struct Engine {
     }
 
     // ---------------------------------------------------------------- layout
+    // 2^64 mod p (to Montgomery form) or its inverse (from Montgomery form): ark-ff's R for one-limb fields
+    static u64 mont_factor(bool to_mont) { const u64 r = (u64)((((u128)1) << 64) % F::P); return to_mont ? r : F::inv(r); }
     void upload_planes(const u64* host, size_t n, W* dev, size_t pitch) {   // host AoS (u64 limbs) -> device planes
         if (!n) return;
         u64* stage = dalloc<u64>(n * D);
         LF_CUDA(cudaMemcpyAsync(stage, host, n * D * 8, cudaMemcpyHostToDevice, st()));
-        launch("k_aos_to_soa", [&] { k_aos_to_soa<D, W><<<(unsigned)((n + 63) / 64), 256, 0, st()>>>(stage, dev, n, pitch); });
-        dfree(stage);
+        launch("k_aos_to_soa", [&] { k_aos_to_soa<F, D, W><<<(unsigned)((n + 63) / 64), 256, 0, st()>>>(stage, dev, n, pitch, c->bulk_repr ? mont_factor(false) : 0); });
+        // not back into the cache yet: the prover allocates buffers that its auxiliary stream writes first, and that stream does not
+        // wait for this copy (the accumulator's decomposition starts while the incoming witness is still uploading)
+        dfree_later(stage);
     }
     void download_planes(const W* dev, size_t pitch, size_t n, u64* host) {
         if (!n) return;
         u64* stage = dalloc<u64>(n * D);
-        launch("k_soa_to_aos", [&] { k_soa_to_aos<D, W><<<(unsigned)((n + 63) / 64), 256, 0, st()>>>(dev, stage, n, pitch); });
+        launch("k_soa_to_aos", [&] { k_soa_to_aos<F, D, W><<<(unsigned)((n + 63) / 64), 256, 0, st()>>>(dev, stage, n, pitch, c->bulk_repr ? mont_factor(true) : 0); });
         LF_CUDA(cudaMemcpyAsync(host, stage, n * D * 8, cudaMemcpyDeviceToHost, st())); sync();
         dfree(stage);
     }

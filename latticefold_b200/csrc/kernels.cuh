@@ -146,19 +146,22 @@ template <class W> __global__ void k_scatter_entry(const W* __restrict__ in, siz
 
 // ------------------------------------------------------------------------------------------------ layout changes
 // host "Vec<R>" image (element-major) <-> limb planes.  64 elements per block through shared memory so both sides coalesce.
-template <int D, class W> __global__ void k_aos_to_soa(const u64* __restrict__ aos, W* __restrict__ soa, size_t n, size_t pitch) {
+// mont != 0: the host limbs are arkworks Montgomery representatives a * 2^64 mod p (ark-ff 0.4 Fp64<MontBackend>, one u64 limb): the
+// factor is taken out on the way in (mont = 2^-64 mod p) and put back on the way out (mont = 2^64 mod p), so a Rust caller can pass
+// the memory of a Vec<R> as it is (LF_REPR_MONTGOMERY) instead of converting 50 MB per witness with into_bigint().
+template <class F, int D, class W> __global__ void k_aos_to_soa(const u64* __restrict__ aos, W* __restrict__ soa, size_t n, size_t pitch, u64 mont) {
     __shared__ u64 tile[64][D + 1];
     size_t base = (size_t)blockIdx.x * 64; int cnt = (int)min((size_t)64, n - base);
-    for (int i = threadIdx.x; i < cnt * D; i += blockDim.x) tile[i / D][i % D] = aos[base * D + i];
+    for (int i = threadIdx.x; i < cnt * D; i += blockDim.x) { u64 v = aos[base * D + i]; if (mont) v = F::mul(v % F::P, mont); tile[i / D][i % D] = v; }
     __syncthreads();
     for (int i = threadIdx.x; i < 64 * D; i += blockDim.x) { int l = i / 64, e = i % 64; if (e < cnt) soa[(size_t)l * pitch + base + e] = (W)tile[e][l]; }
 }
-template <int D, class W> __global__ void k_soa_to_aos(const W* __restrict__ soa, u64* __restrict__ aos, size_t n, size_t pitch) {
+template <class F, int D, class W> __global__ void k_soa_to_aos(const W* __restrict__ soa, u64* __restrict__ aos, size_t n, size_t pitch, u64 mont) {
     __shared__ u64 tile[64][D + 1];
     size_t base = (size_t)blockIdx.x * 64; int cnt = (int)min((size_t)64, n - base);
     for (int i = threadIdx.x; i < 64 * D; i += blockDim.x) { int l = i / 64, e = i % 64; if (e < cnt) tile[e][l] = soa[(size_t)l * pitch + base + e]; }
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt * D; i += blockDim.x) aos[base * D + i] = tile[i / D][i % D];
+    for (int i = threadIdx.x; i < cnt * D; i += blockDim.x) { u64 v = tile[i / D][i % D]; if (mont) v = F::mul(v, mont); aos[base * D + i] = v; }
 }
 
 // ------------------------------------------------------------------------------------------------ K2/K3 CRT / ICRT

@@ -52,6 +52,7 @@ void lf_ctx_destroy(lf_ctx* c) {
     for (int r = 0; r < 8; ++r) if (c->xg.peer_region[r]) cudaIpcCloseMemHandle(c->xg.peer_region[r]);
     if (c->xg.region) cudaFree(c->xg.region);
     if (c->nccl && !c->shared_tables) NcclApi::get().CommDestroy(c->nccl);      // an auxiliary context borrows its parent's communicator
+    c->deferred_free.clear();      // (they are entries of block_size and are released with it)
     for (auto& kv : c->block_size) cudaFree(kv.first);
     if (!c->shared_tables) { for (int i = 0; i < 2; ++i) { cudaFree(c->d_tab_idx[i]); cudaFree(c->d_tab_val[i]); } try { ops(c->ring)->ctx_tables_destroy(c); } catch (...) {} }
     cudaFree(c->d_err); cudaFree(c->d_small); cudaFree(c->d_partial); if (c->h_pinned) cudaFreeHost(c->h_pinned); if (c->h_arena) cudaFreeHost(c->h_arena);
@@ -112,6 +113,9 @@ lf_status lf_ctx_p2p_import(lf_ctx* c, int32_t rank, int32_t world, const uint8_
     });
 }
 
+lf_status lf_ctx_set_bulk_repr(lf_ctx* c, int32_t repr) {
+    return guard(c, [&] { if (repr != LF_REPR_CANONICAL && repr != LF_REPR_MONTGOMERY) throw LfException(LF_ERR_INVALID_ARG, "unknown representation"); c->bulk_repr = repr; });
+}
 lf_status lf_ctx_profile(lf_ctx* c, int32_t enable) {
     return guard(c, [&] { LF_CUDA(cudaStreamSynchronize(c->stream)); for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } c->prof.clear(); c->profiling = enable != 0; });
 }

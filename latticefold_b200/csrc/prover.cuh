@@ -369,7 +369,6 @@ template <class Rg> struct Prover {
     FoldOut fold(const std::vector<LCCCS>& lcs, StepBuffers& sb, const DevVec& eq_acc, const DevVec& eq_new, Transcript<Rg>& T) {
         FoldOut o; const int K = P->K, s = (int)P->s; const size_t n = nl(), m = ml(), t = P->t;
         if ((int)lcs.size() != 2 * K) throw LfException(LF_ERR_INCORRECT_LENGTH, "IncorrectLength");
-        if (P->b != 2) throw LfException(LF_ERR_UNSUPPORTED, "folding sumcheck kernels are specialised for b = 2 (every reference parameter set but Stark)");
         // squeeze_alpha_beta_zeta_mu (folding/utils.rs:51-96)
         // alpha and zeta first: the G tables below need only these two, so their kernels run while the host squeezes mu and beta
         std::vector<u64> alpha = squeeze(T, "alpha_s", 2 * K), zeta = squeeze(T, "zeta_s", 2 * K);
@@ -514,15 +513,20 @@ template <class Rg> struct Prover {
         // Schedule: the accumulator's decomposition depends on nothing the transcript produces, so its device half is
         // queued first on the auxiliary stream and runs beside the (latency-bound, host-paced) linearization sumcheck.
         StepBuffers sb;
+        DevVec eq_acc; LinOut lin; DecPending pl, prr;
+        // whatever a throw leaves behind (step buffers, eq tables, pending events) is released here
+        struct Cleanup { Prover* self; StepBuffers* sb; DevVec* eq_acc; LinOut* lin; DecPending *a, *b; bool armed = true;
+            ~Cleanup() { if (!armed) return; try { self->E.sync(); } catch (...) {}
+                for (DecPending* d : {a, b}) for (cudaEvent_t& e : d->ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+                self->E.dfree(sb->dig); self->E.dfree(sb->pieces); self->E.dfree(sb->zl); self->E.dfree(eq_acc->p); self->E.dfree(lin->eq_r.p); } } cleanup{this, &sb, &eq_acc, &lin, &pl, &prr};
         sb.dig_pitch = (std::max(n, ml()) + 255) / 256 * 256;   // the sumcheck walks all 2^s entries
         sb.dig_stride = sb.dig_pitch * D; sb.dig = E.template dalloc<int8_t>((size_t)2 * K * sb.dig_stride);
         sb.pc_pitch = pitch_of(n); sb.pc_stride = sb.pc_pitch * D; sb.pieces = E.template dalloc<W>((size_t)2 * K * sb.pc_stride);
         sb.zl_pitch = pitch_of(zcols()); sb.zl_stride = sb.zl_pitch * D; sb.zl = E.template dalloc<W>((size_t)2 * K * sb.zl_stride);
-        DevVec eq_acc; eq_acc.n = ((size_t)1 << cnt(acc.r)) / world(); eq_acc.pitch = pitch_of(eq_acc.n); eq_acc.p = E.template dalloc<W>(eq_acc.pitch * D);
+        eq_acc.n = ((size_t)1 << cnt(acc.r)) / world(); eq_acc.pitch = pitch_of(eq_acc.n); eq_acc.p = E.template dalloc<W>(eq_acc.pitch * D);
         // sharded steps overlap too when the collectives are stream-ordered on both streams (own NCCL communicator + mailbox channels)
         const bool overlap = (world() == 1 || (E.c->nccl && E.c->xg.on)) && !P->detail && !std::getenv("LF_NO_OVERLAP");
         W* lin_tail = (overlap && world() > 1) ? gather_wccs(wp(w_i->w_ccs), w_i->w_pitch * D) : nullptr;
-        DecPending pl;
         {
             lf_ctx* main_ctx = E.c;
             if (overlap) {
@@ -549,12 +553,11 @@ template <class Rg> struct Prover {
         T.absorb_slice(acc.u.data(), cnt(acc.u)); T.absorb_slice(acc.x_w.data(), cnt(acc.x_w)); T.absorb(acc.h.data());
         T.absorb_tag("cm_i"); T.absorb_slice(cm_i_cm.data(), cnt(cm_i_cm)); T.absorb_slice(x_ccs.data(), cnt(x_ccs));
         auto t0 = clk::now();
-        LinOut lin = linearize(cm_i_cm, x_ccs, w_i, T, lin_tail);
+        lin = linearize(cm_i_cm, x_ccs, w_i, T, lin_tail);
         mark("linearize");
         E.sync(); auto t1 = clk::now(); P->timings[0] = ms(t0, t1);
         // The second decomposition queues behind the first on the auxiliary stream (the linearization's device work is complete:
         // synchronised above), so the accumulator's results -- the ones the transcript absorbs first -- are never delayed by it.
-        DecPending prr;
         { lf_ctx* main_ctx = E.c;
           if (overlap) { E.c = aux_ctx(); E.c->profiling = main_ctx->profiling; }
           try { prr = decompose_enqueue(lin.lc, w_i, lin.eq_r, sb, 1); } catch (...) { E.c = main_ctx; throw; }
@@ -575,6 +578,7 @@ template <class Rg> struct Prover {
         FoldOut fo = fold(lcs, sb, eq_acc, lin.eq_r, T);
         mark("fold.host_tail");
         lf_witness* w_out = witness_from_f_device(fo.f0);
+        cleanup.armed = false;
         E.dfree(sb.dig); E.dfree(sb.pieces); E.dfree(sb.zl); E.dfree(eq_acc.p); E.dfree(lin.eq_r.p);
         E.sync(); auto t3 = clk::now(); P->timings[2] = ms(t2, t3);
         mark("witness_out_free");

@@ -299,6 +299,12 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         p->kappa = sh->kappa; p->n = sh->n; p->m = sh->m; p->n_ccs = sh->n_ccs; p->l = sh->l; p->t = sh->t; p->q = sh->q; p->d = sh->d; p->s = sh->s;
         int o = 0; for (u64 i = 0; i < sh->q; ++i) { p->S.emplace_back(sh->S_flat + o, sh->S_flat + o + sh->S_len[i]); o += sh->S_len[i]; }
         p->c.assign(sh->c, sh->c + sh->q * Rg::D);
+        // limits of the step's kernels, checked here rather than deep inside a step (a throw on one rank of a sharded run would
+        // desynchronise the peer-memory mailboxes)
+        if (sh->b != 2) throw LfException(LF_ERR_UNSUPPORTED, "folding sumcheck kernels are specialised for b = 2 (every reference parameter set but Stark)");
+        if (sh->K < 1 || 2 * sh->K > MAX_LIST) throw LfException(LF_ERR_UNSUPPORTED, "need 1 <= K <= " + std::to_string(MAX_LIST / 2));
+        if (2 * sh->K * Rg::TAU > MAX_MU) throw LfException(LF_ERR_UNSUPPORTED, "2 K tau exceeds MAX_MU");
+        if (sh->L < 1 || sh->L > 64) throw LfException(LF_ERR_UNSUPPORTED, "need 1 <= L <= 64");
         if (!sh->A) throw LfException(LF_ERR_INVALID_ARG, "Ajtai matrix is NULL");
         // sharded context: the caller passes this rank's column slice of A (kappa x n/world); CCS matrices are given whole
         // and cut to this rank's row slab here

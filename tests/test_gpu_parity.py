@@ -317,3 +317,29 @@ def test_sumcheck_general_terms_lfplus_shapes(ctx, oracle, gpu, nv, shape):
     emsgs, epoint, efinal = oracle.sumcheck_prove(G, oracle.transcript(G), mles, nv, deg, comb, want_final=True)
     msgs, point, final = gpu.MLSumcheck.prove_as_subprotocol(ctx, gpu.Transcript(G), [ctx.upload(m) for m in mles], nv, deg, comb, want_final=True)
     assert np.array_equal(msgs, emsgs) and np.array_equal(point, epoint) and np.array_equal(final, efinal)
+
+
+@pytest.mark.parametrize("ring", [synth.RING_GOLDILOCKS, synth.RING_BABYBEAR])
+def test_montgomery_representation_at_the_boundary(gpu, oracle, ring):
+    """LF_REPR_MONTGOMERY: witness-sized host vectors given as ark-ff Montgomery limbs (a * 2^64 mod p) are the same device vectors as
+    their canonical images, in both directions, and a commitment of Montgomery-form inputs equals the canonical one"""
+    R = synth.RINGS[ring]; p, d = R["p"], R["d"]
+    c = gpu.Context(ring, 0)
+    try:
+        a = rand_elems(ring, 100, 91)
+        mont = ((a.astype(object) << 64) % p).astype(np.uint64)
+        c.set_bulk_repr(True); v = c.upload(mont); c.set_bulk_repr(False)
+        assert np.array_equal(v.download(), a)
+        c.set_bulk_repr(True); got = v.download(); c.set_bulk_repr(False)
+        assert np.array_equal(got, mont)
+        kappa, n = 3, 100
+        A = rand_elems(ring, kappa * n, 92).reshape(kappa, n, d)
+        want = oracle.commit(ring, A, a)
+        c.set_bulk_repr(True)
+        sch = gpu.AjtaiCommitmentScheme(c, ((A.astype(object) << 64) % p).astype(np.uint64))
+        cm = sch.commit(c.upload(mont))                    # the kappa result elements are small data: canonical in either mode
+        c.set_bulk_repr(False)
+        assert np.array_equal(cm, want)
+        del sch
+    finally:
+        c.close()
