@@ -471,6 +471,65 @@ template <> struct SlotField<GoldilocksRing> {
     static LF_HD void dot_finish(u64* c, const Acc192* acc) { for (int i = 0; i < 3; ++i) c[i] = F::reduce192(acc[i]); }
 };
 
+// BabyBear slot field on BALANCED representatives (|a| <= (p-1)/2, signed 32-bit words).  (p/2)^2 < 2^59.82, so a sum of NINE
+// products fits a signed 64-bit accumulator (9 (p-1)^2 / 4 = 0.9888 * 2^63): one multiply-accumulate is ONE IMAD.WIDE with no carry
+// word, where the unsigned 96-bit accumulator of BabyBear::Acc needs a second instruction per product.  A product in Fq[Y]/(Y^9 - nu)
+// is then 81 + 8 multiply-accumulates and 17 reductions: the 8 wrapped coefficient sums H_k = sum_{i>k} a_i b_{k+9-i} are reduced
+// once and enter c_k = L_k + nu H_k as one more product; a fixed right operand (fix_variables: the round's challenge) carries its
+// nu-multiples with it and needs only the 9 final reductions.  Exact integer arithmetic: any representative of the right residue
+// class gives the same canonical limb, so results are bit-identical to BabyBear::mul chains.
+// Reduction of |x| < 2^63: fold the upper word with 2^32 = 2^28 - 2 (mod p) -> |y| < 2^59 + 2^32; quotient estimate
+// q = round((y >> 29) * round(2^61 / p) / 2^32), off from y / p by (-0.892, +0.625]; remainder in 32-bit wrap-around arithmetic,
+// then one conditional +-p on either side.
+struct BbBal {
+    static constexpr int P = 2013265921, HALF = (P - 1) / 2;
+    static constexpr int NUB = (int)(1398021245LL - 2013265921LL);                              // nu as a balanced representative
+    static constexpr long long C32 = (1LL << 32) % P;
+    static constexpr int M29 = (int)(((1LL << 61) + P / 2) / P);
+    static LF_HD int bal(u32 a) { return (int)a - ((int)a > HALF ? P : 0); }                     // canonical [0, p) -> balanced
+    static LF_HD u32 canon(int r) { return (u32)(r + (r < 0 ? P : 0)); }                         // (-p, p) -> canonical
+    static LF_HD int fix(int r) { if (r > HALF) r -= P; if (r < -HALF) r += P; return r; }       // (-3p/2, 3p/2) -> balanced
+    static LF_HD int red_small(long long y) {                                                     // |y| < 2^59 + 2^33
+        const int t = (int)(y >> 29);
+        const int q = (int)(((long long)t * M29 + (1LL << 31)) >> 32);
+        return fix((int)((u32)y - (u32)q * (u32)P));
+    }
+    static LF_HD int red(long long x) { return red_small((long long)(int)(x >> 32) * C32 + (long long)(u32)x); }
+    // c = a * b (all balanced, 9 limbs).  c may alias a or b.
+    static LF_HD void mul(int* c, const int* a, const int* b) {
+        int h[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { long long x = 0;
+#pragma unroll
+            for (int i = k + 1; i < 9; ++i) x += (long long)a[i] * b[k + 9 - i];
+            h[k] = red(x); }
+        int r[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { long long x = k < 8 ? (long long)h[k < 8 ? k : 0] * NUB : 0;
+#pragma unroll
+            for (int i = 0; i <= k; ++i) x += (long long)a[i] * b[k - i];
+            r[k] = red(x); }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) c[k] = r[k];
+    }
+    // fixed right operand: b and nu * b (balanced)
+    struct Fixed { int b[9], bn[9]; };
+    static LF_HD Fixed fixed(const u64* b_canonical) { Fixed f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { f.b[i] = bal((u32)b_canonical[i]); f.bn[i] = red((long long)f.b[i] * NUB); } return f; }
+    // c = add + a * b: 81 multiply-accumulates, 9 reductions (add, a balanced)
+    static LF_HD void mul_fixed_add(int* c, const int* a, const Fixed& f, const int* add) {
+        int r[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { long long x = add[k];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) x += (long long)a[i] * (i <= k ? f.b[k - i] : f.bn[k + 9 - i]);
+            r[k] = red(x); }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) c[k] = r[k];
+    }
+};
+
 // BabyBear ring: slot field Fq9 = Fq[Y]/(Y^9 - nu).  Same interface as the generic SlotField, but the 81 partial products of a
 // multiplication are straight-line lazily reduced MACs (one IMAD.WIDE + one carry add each, 9 per output limb, one 96-bit accumulator
 // live at a time) with the fixed operand's nu-multiples prepared once, and the accumulating dot products (k_dot) keep the 17

@@ -4,6 +4,7 @@
 // back and is applied (fix_variables) before the next evaluation.
 #pragma once
 #include "engine.cuh"
+#include "sumcheck_wide.cuh"
 
 struct lf_sumcheck {
     lf_ctx* ctx = nullptr;
@@ -98,8 +99,23 @@ template <class Rg> struct SumcheckDriver {
         } else {
             // one thread per (pair, evaluation point): see k_sc_points
             const int ppb = 128 / ne;
-            nblk = (unsigned)std::min<size_t>((n_pairs + ppb - 1) / ppb, 148 * 16); partial = E.partial_dev((size_t)nblk * ne * D);
-            if (sc->n_terms_general) {
+            nblk = (unsigned)std::min<size_t>((n_pairs + ppb - 1) / ppb, 148 * 16);
+            bool wide = false;
+            if constexpr (std::is_same<Rg, BabyBearRing>::value)
+                wide = !sc->n_terms_general && n_pairs >= (size_t)SCW_TILE && n_pairs % SCW_TILE == 0 && ne <= 8 && !std::getenv("LF_SC_NARROW");      // (the narrow kernels are kept for A/B measurements and short tables)
+            if (wide) nblk = (unsigned)std::min<size_t>(n_pairs / SCW_TILE, 148 * 2);
+            partial = E.partial_dev((size_t)nblk * ne * D);
+            if (wide) {
+                if constexpr (std::is_same<Rg, BabyBearRing>::value) {
+                    ScGenericArgsT<W> a; const auto& gen = sc->gen;
+                    a.n_mles = gen.n_mles; a.deg = gen.deg; a.n_terms = gen.n_terms; a.lin = gen.lin;
+                    for (int t = 0; t < SC_MAX_TERMS; ++t) { a.term_len[t] = gen.term_len[t]; for (int f = 0; f < SC_MAX_FACTORS; ++f) a.term_idx[t][f] = gen.term_idx[t][f]; }
+                    a.pitch = sc->dense.pitch; a.n_pairs = n_pairs; a.partial = partial; a.coef = sc->d_coef;
+                    for (int k = 0; k < SC_MAX_MLES; ++k) a.mle[k] = wp(sc->dense.cur) + (size_t)std::min(k, a.n_mles - 1) * sc->dense.stride;
+                    const size_t smem = (size_t)2 * a.n_mles * TAU * 2 * SCW_TILE * sizeof(W);
+                    E.launch("k_sc_wide", [&] { k_sc_wide_bb<><<<dim3(nblk, S), 32 * ne, smem, E.st()>>>(a); });
+                }
+            } else if (sc->n_terms_general) {
                 ScTermsArgsT<W> g; g.base = wp(sc->dense.cur); g.stride = sc->dense.stride; g.pitch = sc->dense.pitch; g.n_mles = sc->gen.n_mles; g.deg = sc->gen.deg;
                 g.n_terms = sc->n_terms_general; g.lin = sc->gen.lin; g.term_off = sc->d_term_off; g.idx = sc->d_term_idx; g.coef = sc->d_coef; g.n_pairs = n_pairs; g.partial = partial;
                 E.launch("k_sc_generic", [&] { k_sc_terms<Rg><<<dim3(nblk, S), 128, 0, E.st()>>>(g); });
@@ -139,9 +155,19 @@ template <class Rg> struct SumcheckDriver {
         if (!g.count || !g.cur) return;
         const size_t np = pitch_of(n_out);
         W* out = pingpong_target(g, n_out);
+        bool wide = false;
+        if constexpr (std::is_same<Rg, BabyBearRing>::value) {
+            if (!std::getenv("LF_SC_NARROW")) {
+                wide = true;
+                FoldWideArgs a; a.in = wp(g.cur); a.out = out; a.in_pitch = g.pitch; a.out_pitch = np; a.in_stride = g.stride; a.out_stride = np * D; a.n_out = n_out; a.r = BbBal::fixed(r_sf);
+                E.launch("k_fold", [&] { k_fold_wide_bb<><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, g.count), 128, 0, E.st()>>>(a); });
+            }
+        }
+        if (!wide) {
         FoldArgsT<W> a; a.in = wp(g.cur); a.out = out; a.in_pitch = g.pitch; a.out_pitch = np; a.in_stride = g.stride; a.out_stride = np * D; a.n_out = n_out;
         for (int l = 0; l < TAU; ++l) a.r[l] = r_sf[l];
         E.launch("k_fold", [&] { k_fold<Rg><<<dim3(Engine<Rg>::blocks_for(n_out, 128), S, g.count), 128, 0, E.st()>>>(a); });
+        }
         if (g.cur_owned && g.cur != g.nxt && g.cur != g.alt) E.dfree(g.cur);     // the caller-provided / initial table set
         g.cur = ow(out); g.cur_owned = false; g.pitch = np; g.stride = np * D;
     }
