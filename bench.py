@@ -164,7 +164,7 @@ def algorithmic_bytes(wl, ccs, world):
         "k_fold_sc_round1": M_fold * m * E,
         "k_fold_sc_round": M_fold * (3 * m // 2) * E,                       # sum over r >= 2 of (2^(s-r+2) + 2^(s-r+1)) ~ 3 * 2^(s-1)
         "k_fold_sc_round2": M_fold * (m + m // 4) * E,
-        "k_sc_generic": M_lin * (m + 3 * m // 2) * E,
+        "k_sc_generic": M_lin * (m + 3 * m // 2) * E, "k_sc_wide": M_lin * 2 * m * E,
         "k_fold": None, "k_fold_digits": M_fold * (m + m // 2) * E,
         "k_matrix_apply": 2 * (2 * K + 1) * n * E,                           # CRT of the 2K pieces + ICRT of the folded witness
         "k_gadget_recompose": (2 * K + 1) * (n + n // L) * E,
@@ -499,7 +499,7 @@ def run_c3(args, rank, world, local):
     hbm, peak_src = peaks()
     ccs = prob["ccs"]; E = R["d"] * 8; n, m, kappa, t = wl["W"] * wl["L"], 1 << ccs["s"], wl["kappa"], ccs["t"]
     rows = wl["W"] + 2
-    alg = {"k_dot": (kappa * n + n + kappa) * E, "k_sc_generic": (t + 1) * (m + 3 * m // 2) * E, "k_fold": None,
+    alg = {"k_dot": (kappa * n + n + kappa) * E, "k_sc_generic": (t + 1) * (m + 3 * m // 2) * E, "k_sc_wide": (t + 1) * 2 * m * E, "k_fold": (t + 1) * 3 * m * E,
            "k_spmv": t * (rows * (E + 8) + 2 * rows * E), "k_eq_combine": 2 * m * E, "k_coeff_eval": 4 * n * E, "k_dot_eval": (t + 1) * rows * E}
     kernels = []
     for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):

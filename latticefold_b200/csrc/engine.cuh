@@ -48,7 +48,7 @@ struct NcclApi {
 }  // namespace lf
 
 struct lf_ctx {
-    int ring = 0, device = 0;
+    int ring = 0, device = 0, sm_count = 0;      // sm_count: filled on first use (persistent-grid kernels)
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;

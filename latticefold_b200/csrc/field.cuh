@@ -479,8 +479,8 @@ template <> struct SlotField<GoldilocksRing> {
 // nu-multiples with it and needs only the 9 final reductions.  Exact integer arithmetic: any representative of the right residue
 // class gives the same canonical limb, so results are bit-identical to BabyBear::mul chains.
 // Reduction of |x| < 2^63: fold the upper word with 2^32 = 2^28 - 2 (mod p) -> |y| < 2^59 + 2^32; quotient estimate
-// q = round((y >> 29) * round(2^61 / p) / 2^32), off from y / p by (-0.892, +0.625]; remainder in 32-bit wrap-around arithmetic,
-// then one conditional +-p on either side.
+// q = floor(((y >> 29) + 2) * round(2^61 / p) / 2^32), off from y / p by (-0.859, +0.659]; remainder in 32-bit wrap-around
+// arithmetic, then one conditional +-p on either side.
 struct BbBal {
     static constexpr int P = 2013265921, HALF = (P - 1) / 2;
     static constexpr int NUB = (int)(1398021245LL - 2013265921LL);                              // nu as a balanced representative
@@ -489,25 +489,46 @@ struct BbBal {
     static LF_HD int bal(u32 a) { return (int)a - ((int)a > HALF ? P : 0); }                     // canonical [0, p) -> balanced
     static LF_HD u32 canon(int r) { return (u32)(r + (r < 0 ? P : 0)); }                         // (-p, p) -> canonical
     static LF_HD int fix(int r) { if (r > HALF) r -= P; if (r < -HALF) r += P; return r; }       // (-3p/2, 3p/2) -> balanced
+    // signed 32 x 32 + 64 multiply-add: one IMAD.WIDE accumulating in place.  Written as a mad.lo.cc / madc.hi pair, which ptxas
+    // fuses into one chained IMAD.WIDE; `mad.wide.s32` and the C expression are both re-associated by ptxas into independent wide
+    // multiplies plus a tree of 64-bit three-input adds (two more instructions per product; measured on sm_100a, CUDA 12.9).
+    static LF_HD long long madw(int a, int b, long long c) {
+#if defined(__CUDA_ARCH__)
+        int lo = (int)c, hi = (int)(c >> 32);
+        asm("mad.lo.cc.s32 %0, %2, %3, %0;\n\tmadc.hi.s32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+        return (long long)(((u64)(u32)hi << 32) | (u32)lo);
+#else
+        return (long long)a * b + c;
+#endif
+    }
+    static LF_HD int mulhi(int a, int b) {
+#if defined(__CUDA_ARCH__)
+        return __mulhi(a, b);
+#else
+        return (int)(((long long)a * b) >> 32);
+#endif
+    }
+    // q = floor(((y >> 29) + 2) * M29 / 2^32): 2 * M29 / 2^32 = 0.533 is the rounding offset, so q - y / p lies in (-0.859, +0.659]
+    // and the 32-bit remainder in [-0.659 p, 0.859 p)
     static LF_HD int red_small(long long y) {                                                     // |y| < 2^59 + 2^33
-        const int t = (int)(y >> 29);
-        const int q = (int)(((long long)t * M29 + (1LL << 31)) >> 32);
+        const int q = mulhi((int)(y >> 29) + 2, M29);
         return fix((int)((u32)y - (u32)q * (u32)P));
     }
-    static LF_HD int red(long long x) { return red_small((long long)(int)(x >> 32) * C32 + (long long)(u32)x); }
+    static LF_HD int red(long long x) { return red_small(madw((int)(x >> 32), (int)C32, (long long)(u64)(u32)x)); }
     // c = a * b (all balanced, 9 limbs).  c may alias a or b.
     static LF_HD void mul(int* c, const int* a, const int* b) {
         int h[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { long long x = 0;
 #pragma unroll
-            for (int i = k + 1; i < 9; ++i) x += (long long)a[i] * b[k + 9 - i];
+            for (int i = k + 1; i < 9; ++i) x = madw(a[i], b[k + 9 - i], x);
             h[k] = red(x); }
         int r[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) { long long x = k < 8 ? (long long)h[k < 8 ? k : 0] * NUB : 0;
+        for (int k = 0; k < 9; ++k) { long long x = 0;
+            if (k < 8) x = madw(h[k < 8 ? k : 0], NUB, x);
 #pragma unroll
-            for (int i = 0; i <= k; ++i) x += (long long)a[i] * b[k - i];
+            for (int i = 0; i <= k; ++i) x = madw(a[i], b[k - i], x);
             r[k] = red(x); }
 #pragma unroll
         for (int k = 0; k < 9; ++k) c[k] = r[k];
@@ -523,7 +544,7 @@ struct BbBal {
 #pragma unroll
         for (int k = 0; k < 9; ++k) { long long x = add[k];
 #pragma unroll
-            for (int i = 0; i < 9; ++i) x += (long long)a[i] * (i <= k ? f.b[k - i] : f.bn[k + 9 - i]);
+            for (int i = 0; i < 9; ++i) x = madw(a[i], i <= k ? f.b[k - i] : f.bn[k + 9 - i], x);
             r[k] = red(x); }
 #pragma unroll
         for (int k = 0; k < 9; ++k) c[k] = r[k];

@@ -103,7 +103,16 @@ template <class Rg> struct SumcheckDriver {
             bool wide = false;
             if constexpr (std::is_same<Rg, BabyBearRing>::value)
                 wide = !sc->n_terms_general && n_pairs >= (size_t)SCW_TILE && n_pairs % SCW_TILE == 0 && ne <= 8 && !std::getenv("LF_SC_NARROW");      // (the narrow kernels are kept for A/B measurements and short tables)
-            if (wide) nblk = (unsigned)std::min<size_t>(n_pairs / SCW_TILE, 148 * 2);
+            size_t wide_smem = 0;
+            if constexpr (std::is_same<Rg, BabyBearRing>::value) if (wide) {
+                // persistent CTAs: as many as are resident on the chip at once, spread over the S slots
+                wide_smem = (size_t)sc->gen.n_mles * TAU * (SCW_STAGES * 2 * SCW_TILE + std::max(ne - 2, 0) * SCW_TILE) * sizeof(W);      // tile stages + values at the points >= 2
+                auto kern = ne <= 5 ? k_sc_wide_bb<160, 5> : k_sc_wide_bb<256, 3>;      // up to degree 4 (the degree-three CCS): five CTAs of five warps per SM
+                if (wide_smem > 48 * 1024) LF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem));
+                if (!E.c->sm_count) LF_CUDA(cudaDeviceGetAttribute(&E.c->sm_count, cudaDevAttrMultiProcessorCount, E.c->device));
+                int per_sm = 1; LF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * ne, wide_smem));
+                nblk = (unsigned)std::min<size_t>(n_pairs / SCW_TILE, (size_t)std::max(1, per_sm * E.c->sm_count / S));
+            }
             partial = E.partial_dev((size_t)nblk * ne * D);
             if (wide) {
                 if constexpr (std::is_same<Rg, BabyBearRing>::value) {
@@ -112,8 +121,7 @@ template <class Rg> struct SumcheckDriver {
                     for (int t = 0; t < SC_MAX_TERMS; ++t) { a.term_len[t] = gen.term_len[t]; for (int f = 0; f < SC_MAX_FACTORS; ++f) a.term_idx[t][f] = gen.term_idx[t][f]; }
                     a.pitch = sc->dense.pitch; a.n_pairs = n_pairs; a.partial = partial; a.coef = sc->d_coef;
                     for (int k = 0; k < SC_MAX_MLES; ++k) a.mle[k] = wp(sc->dense.cur) + (size_t)std::min(k, a.n_mles - 1) * sc->dense.stride;
-                    const size_t smem = (size_t)2 * a.n_mles * TAU * 2 * SCW_TILE * sizeof(W);
-                    E.launch("k_sc_wide", [&] { k_sc_wide_bb<><<<dim3(nblk, S), 32 * ne, smem, E.st()>>>(a); });
+                    E.launch("k_sc_wide", [&] { if (ne <= 5) k_sc_wide_bb<160, 5><<<dim3(nblk, S), 32 * ne, wide_smem, E.st()>>>(a); else k_sc_wide_bb<256, 3><<<dim3(nblk, S), 32 * ne, wide_smem, E.st()>>>(a); });
                 }
             } else if (sc->n_terms_general) {
                 ScTermsArgsT<W> g; g.base = wp(sc->dense.cur); g.stride = sc->dense.stride; g.pitch = sc->dense.pitch; g.n_mles = sc->gen.n_mles; g.deg = sc->gen.deg;

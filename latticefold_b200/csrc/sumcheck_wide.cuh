@@ -5,11 +5,15 @@
 // Why a second implementation next to k_sc_points / k_fold: one Fq9 product is 81 base-field multiply-accumulates, a table entry
 // is 36 B per slot, and the degree-three CCS needs five tables at every evaluation point.  Held per thread that state goes to
 // local memory (ncu r02f: long-scoreboard stalls, 25 % of the warps resident, 43 % ALU / 13 % FMA pipe).  Here
-//  * a CTA walks 32-pair tiles of the hypercube; the tile of every table (n_mles x 9 limb rows x 256 B) is brought into shared
-//    memory by bulk asynchronous copies (cp.async.bulk -> mbarrier, UBLKCP in SASS), double buffered: the next tile streams in
-//    while this one is evaluated, and no thread holds table words in registers;
-//  * warp e of the CTA evaluates point e for the 32 pairs of the tile (lanes = consecutive pairs: conflict-free 8-byte shared
-//    loads; the point is warp-uniform, so v(e) = v0 + e (v1 - v0) is straight-line code);
+//  * a persistent CTA walks 32-pair tiles of the hypercube; the tile of every table (n_mles x 9 limb rows x 256 B) is brought into
+//    shared memory by bulk asynchronous copies (cp.async.bulk -> mbarrier, UBLKCP in SASS), three stages deep: tiles stream in while
+//    earlier ones are evaluated and no thread holds table words in registers.  (A dedicated producer warp with full / empty
+//    barriers was measured and lost 30 %: the idle warp costs a fifth of the resident compute warps and its polling steals issue slots.)
+//  * warp e of the CTA evaluates point e for the 32 pairs of the tile (lanes = consecutive pairs: conflict-free shared loads).
+//    The table values at the points e >= 2, v(e) = v(e-1) + (v1 - v0), are formed ONCE per tile by all warps together (row r of
+//    the tile by warp r mod warps, one add and one conditional correction per point) and parked in shared memory: evaluated
+//    inside the point's own warp they cost a wide multiply and a reduction each and leave the warps of points 0 and 1 idle at
+//    the tile barrier (ncu r02r: 20 % barrier stalls);
 //  * arithmetic is on balanced representatives with signed 64-bit accumulators (field.cuh: BbBal) -- one IMAD.WIDE per
 //    multiply-accumulate, 17 reductions per product, 9 when the right operand is the round's challenge;
 //  * coefficients +-1 (every CCS the reference ships: c = [1, -1]) cost a sign, not a product.
@@ -21,25 +25,35 @@
 namespace lf {
 
 constexpr int SCW_TILE = 32;            // pairs per tile (one per lane)
+constexpr int SCW_STAGES = 2;           // tiles in flight per CTA
 
-template <int = 0> __global__ void __launch_bounds__(256)
+// block = (deg + 1) warps, warp e evaluates point e; grid = (CTAs resident on the chip / S, S), every CTA walks tiles blockIdx.x,
+// blockIdx.x + gridDim.x, ...  The lanes of warp 0 issue the row copies of the tile two iterations ahead.
+template <int MAXT, int MINB> __global__ void __launch_bounds__(MAXT, MINB)
 k_sc_wide_bb(const ScGenericArgsT<u32> a) {
     typedef BbBal B; constexpr int TAU = 9; constexpr int ROW = 2 * SCW_TILE;      // words per (table, limb) row of a tile
-    extern __shared__ __align__(128) u32 scw_smem[];                                // [2 stages][n_mles * 9][ROW]
-    __shared__ __align__(8) unsigned long long bars[2];
-    const int slot = blockIdx.y, e = threadIdx.x >> 5, lane = threadIdx.x & 31, rows = a.n_mles * TAU;
+    extern __shared__ __align__(128) u32 scw_smem[];                                // [stages][n_mles * 9][ROW] tiles, then [n_mles * 9][deg - 1][32] point values
+    __shared__ __align__(8) unsigned long long bars[SCW_STAGES];
+    const int slot = blockIdx.y, e = threadIdx.x >> 5, lane = threadIdx.x & 31, npts = a.deg + 1, rows = a.n_mles * TAU;
     const size_t n_tiles = a.n_pairs / SCW_TILE;
     const u32 bar0 = cmma::smem_addr(&bars[0]), stage_bytes = (u32)rows * ROW * 4;
-    if (threadIdx.x == 0) { cmma::mbar_init(bar0, 1); cmma::mbar_init(bar0 + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SCW_STAGES; ++s) cmma::mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    auto issue = [&](size_t tile, int stage) {          // one thread: n_mles * 9 row copies of 256 B
+    auto issue = [&](size_t tile, int stage) {          // warp 0: lane r copies rows r, r + 32, ... (256 B each)
         const u32 bar = bar0 + 8 * stage, dst = cmma::smem_addr(scw_smem) + stage * stage_bytes;
-        cmma::mbar_expect_tx(bar, stage_bytes);
-        for (int k = 0; k < a.n_mles; ++k)
-            for (int l = 0; l < TAU; ++l) cmma::bulk_g2s(dst + (u32)(k * TAU + l) * ROW * 4, a.mle[k] + (size_t)(slot * TAU + l) * a.pitch + tile * ROW, ROW * 4, bar);
+        if (lane == 0) cmma::mbar_expect_tx(bar, stage_bytes);
+        __syncwarp();
+        for (int r = lane; r < rows; r += 32) {
+            const int k = r / TAU, l = r - k * TAU;
+            cmma::bulk_g2s(dst + (u32)r * ROW * 4, a.mle[k] + (size_t)(slot * TAU + l) * a.pitch + tile * ROW, ROW * 4, bar);
+        }
     };
-    if (threadIdx.x == 0 && blockIdx.x < n_tiles) issue(blockIdx.x, 0);
-    // term coefficients of this slot: +-1 is a sign
+    if (e == 0)
+        for (int s = 0; s < SCW_STAGES - 1; ++s) if (blockIdx.x + (size_t)s * gridDim.x < n_tiles) issue(blockIdx.x + (size_t)s * gridDim.x, s);
+    // term coefficients of this slot: +-1 is a sign, not a product
     unsigned unit_pos = 0, unit_neg = 0;      // bit t
     for (int t = 0; t < a.n_terms; ++t) {
         if (a.term_len[t] <= 0) continue;
@@ -47,49 +61,64 @@ k_sc_wide_bb(const ScGenericArgsT<u32> a) {
         for (int l = 1; l < TAU; ++l) rest0 = rest0 && c[l] == 0;
         if (rest0 && c[0] == 1) unit_pos |= 1u << t; else if (rest0 && c[0] == (u64)B::P - 1) unit_neg |= 1u << t;
     }
+    const int n_pass = a.n_terms + (a.lin ? 1 : 0);      // the LIN factor is one more pass: (sum of the terms) * last table
     long long ev[TAU];
 #pragma unroll
     for (int l = 0; l < TAU; ++l) ev[l] = 0;
     int it = 0;
     for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int stage = it & 1;
-        if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) issue(tile + gridDim.x, stage ^ 1);      // stage^1 was released by the barrier that ended the previous iteration
-        cmma::mbar_wait(bar0 + 8 * stage, (it >> 1) & 1);
+        const int stage = it % SCW_STAGES;
+        // the stage refilled here was released by the barrier that ended the previous iteration
+        if (e == 0 && tile + (size_t)(SCW_STAGES - 1) * gridDim.x < n_tiles) issue(tile + (size_t)(SCW_STAGES - 1) * gridDim.x, (it + SCW_STAGES - 1) % SCW_STAGES);
+        cmma::mbar_wait(bar0 + 8 * stage, (it / SCW_STAGES) & 1);
         const u32* sm = scw_smem + (size_t)stage * rows * ROW + 2 * lane;
-        auto at_point = [&](int k, int* out) {
-#pragma unroll
-            for (int l = 0; l < TAU; ++l) {
-                const uint2 v = *reinterpret_cast<const uint2*>(sm + (k * TAU + l) * ROW);
-                if (e == 0) out[l] = B::bal(v.x);
-                else if (e == 1) out[l] = B::bal(v.y);
-                else out[l] = B::red_small((long long)e * ((int)v.y - (int)v.x) + (long long)v.x);
-            }
-        };
-        int res[TAU];
+        // table values at the points 2 .. deg (balanced), row r by warp r mod npts
+        int* pts = reinterpret_cast<int*>(scw_smem + (size_t)SCW_STAGES * rows * ROW);
+        for (int r = e; r < rows; r += npts) {
+            const uint2 v = *reinterpret_cast<const uint2*>(sm + r * ROW);
+            const int a0 = B::bal(v.x); int x = B::bal(v.y); const int d = B::fix(x - a0);
+            for (int q = 0; q < npts - 2; ++q) { x = B::fix(x + d); pts[(r * (npts - 2) + q) * SCW_TILE + lane] = x; }
+        }
+        __syncthreads();
+        int res[TAU], term[TAU];
 #pragma unroll
         for (int l = 0; l < TAU; ++l) res[l] = 0;
 #pragma unroll 1
-        for (int t = 0; t < a.n_terms; ++t) {
-            int term[TAU], fac[TAU];
-            const int len = a.term_len[t]; int f = 0;
-            if ((unit_pos | unit_neg) >> t & 1) {
-                at_point(a.term_idx[t][0], term); f = 1;
-                if (unit_neg >> t & 1) {
+        for (int t = 0; t < n_pass; ++t) {
+            const bool last = t == a.n_terms;
+            const int len = last ? 1 : a.term_len[t];
+            const bool unit = !last && ((unit_pos | unit_neg) >> t & 1), neg = !last && (unit_neg >> t & 1);
+            if (last) {
 #pragma unroll
-                    for (int l = 0; l < TAU; ++l) term[l] = -term[l]; }
-            } else {
+                for (int l = 0; l < TAU; ++l) term[l] = res[l];
+            } else if (!unit) {
                 const u64* c = a.coef + (size_t)t * BabyBearRing::D + slot * TAU;
 #pragma unroll
                 for (int l = 0; l < TAU; ++l) term[l] = B::bal((u32)c[l]);
             }
 #pragma unroll 1
-            for (; f < len; ++f) { at_point(a.term_idx[t][f], fac); B::mul(term, term, fac); }
+            for (int f = 0; f < len; ++f) {
+                const int k = last ? a.n_mles - 1 : a.term_idx[t][f];
+                int fac[TAU];
+                if (e >= 2) {
 #pragma unroll
-            for (int l = 0; l < TAU; ++l) res[l] = B::fix(res[l] + term[l]);
+                    for (int l = 0; l < TAU; ++l) fac[l] = pts[((k * TAU + l) * (npts - 2) + (e - 2)) * SCW_TILE + lane];
+                } else {
+#pragma unroll
+                    for (int l = 0; l < TAU; ++l) { const uint2 v = *reinterpret_cast<const uint2*>(sm + (k * TAU + l) * ROW); fac[l] = B::bal(e == 0 ? v.x : v.y); }
+                }
+                if (unit && f == 0) {
+#pragma unroll
+                    for (int l = 0; l < TAU; ++l) term[l] = neg ? -fac[l] : fac[l];
+                } else B::mul(term, term, fac);
+            }
+            if (!last) {
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) res[l] = B::fix(res[l] + term[l]);
+            }
         }
-        if (a.lin) { int last[TAU]; at_point(a.n_mles - 1, last); B::mul(res, res, last); }
 #pragma unroll
-        for (int l = 0; l < TAU; ++l) ev[l] += res[l];
+        for (int l = 0; l < TAU; ++l) ev[l] += a.lin ? term[l] : res[l];
         __syncthreads();                                  // every warp is done with this stage before it is refilled
     }
     // 32 lanes -> one canonical sum per (point, limb)
@@ -98,7 +127,7 @@ k_sc_wide_bb(const ScGenericArgsT<u32> a) {
         u32 v = B::canon(B::red(ev[l]));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); if (v >= (u32)B::P) v -= (u32)B::P; }
-        if (lane == 0) a.partial[((size_t)blockIdx.x * (a.deg + 1) + e) * BabyBearRing::D + slot * TAU + l] = v;
+        if (lane == 0) a.partial[((size_t)blockIdx.x * npts + e) * BabyBearRing::D + slot * TAU + l] = v;
     }
 }
 
