@@ -383,7 +383,7 @@ template <class Rg> struct Engine {
         const int xpb = 128 * 8; const unsigned xt = (unsigned)std::max<size_t>(1, (n + xpb - 1) / xpb);
         const size_t nout = (size_t)nvec * TAU * D;
         u64* partial = partial_dev((size_t)xt * nout);
-        launch("k_coeff_eval", [&] { k_coeff_eval<Rg, TIn><<<dim3(xt, S, nvec), 128, 0, st()>>>(coeff, c_pitch, c_vec_stride, eq, eq_pitch, n, xpb, nvec, partial); });
+        launch("k_coeff_eval", [&] { k_coeff_eval<Rg, TIn><<<dim3(xt, S, nvec * (TAU / coeff_eval_jb<Rg>())), 128, 0, st()>>>(coeff, c_pitch, c_vec_stride, eq, eq_pitch, n, xpb, nvec, partial); });
         reduce_partials_allreduce(partial, (int)xt, nout, d_out);
     }
     void spmv(const lf_sparse* M, const W* head, size_t head_len, size_t head_pitch, const W* tail, size_t tail_pitch, W* out, size_t out_pitch, size_t nrows,

@@ -580,10 +580,23 @@ template <> struct SlotField<BabyBearRing> {
 #pragma unroll
         for (int k = 0; k < 9; ++k) c[k] = (TC)r[k];
     }
-    template <class TC, class TA, class TB> static LF_HD void mul_inl(TC* c, const TA* a, const TB* b) { const Prepped p = prep(b); mul_prepped_inl(c, a, p); }
+    // general products: on the device through the balanced-representative form (BbBal: one IMAD.WIDE per multiply-accumulate,
+    // 54 instructions of conversion around ~330 of product, against ~600 for the unsigned 96-bit accumulators below)
+    template <class TC, class TA, class TB> static LF_HD void mul_inl(TC* c, const TA* a, const TB* b) {
+#if defined(__CUDA_ARCH__)
+        int x[9], y[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { x[i] = BbBal::bal((u32)a[i]); y[i] = BbBal::bal((u32)b[i]); }
+        BbBal::mul(x, x, y);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) c[i] = (TC)BbBal::canon(x[i]);
+#else
+        const Prepped p = prep(b); mul_prepped_inl(c, a, p);
+#endif
+    }
     static LF_HD_CALL void mul_prepped(u64* c, const u64* a, const Prepped& p) { mul_prepped_inl(c, a, p); }
-    static LF_HD_CALL void mul(u64* c, const u64* a, const u64* b) { const Prepped p = prep(b); mul_prepped_inl(c, a, p); }
-    static LF_HD_CALL void sqr(u64* c, const u64* a) { const Prepped p = prep(a); mul_prepped_inl(c, a, p); }
+    static LF_HD_CALL void mul(u64* c, const u64* a, const u64* b) { mul_inl(c, a, b); }
+    static LF_HD_CALL void sqr(u64* c, const u64* a) { mul_inl(c, a, a); }
     template <class TC, class TA, class TB> static LF_HD void add(TC* c, const TA* a, const TB* b) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) c[i] = (TC)F::add((u64)a[i], (u64)b[i]); }

@@ -363,21 +363,25 @@ k_dot(const DotArgsT<typename Rg::W> a) {
 
 // evaluate f-hat MLEs straight from coefficient planes: out[v][j][slot][l] = sum_x eq[x][slot][l] * coeff_v[x][j*S + slot]
 // (compute_v_s, decomposition.rs:204-211; linearization.rs:126-131).  TIn = int8_t (digit pieces) or u64 (field coefficients).
-// grid = (x tiles, slots, vectors); partial: [x tile][vector][tau_j][D]
+// grid = (x tiles, slots, vectors * (TAU / JB)); partial: [x tile][vector][tau_j][D].  A block covers JB of the TAU coefficient planes of
+// its slot: all of them on the narrow slot fields; THREE on the wide BabyBear field, whose 9 x 9 lazily reduced accumulators (243
+// registers) spilled -- 27 per thread stay in registers and the eq limbs are re-read by the three blocks of a tile through L2
+// (one plane per block, nine re-reads, measured L2-bound: 4.2 ms at configs[2] against 5.4 ms spilling).
+template <class Rg> constexpr int coeff_eval_jb() { return Rg::TAU > 4 ? 3 : Rg::TAU; }
 template <class Rg, class TIn> __global__ void __launch_bounds__(128)
 k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride, const typename Rg::W* __restrict__ eq, size_t eq_pitch,
              size_t n, int x_per_block, int nvec, u64* __restrict__ partial) {
-    typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
-    __shared__ u64 red[TAU * TAU * 32];
-    const int slot = blockIdx.y, vec = blockIdx.z;
-    const TIn* cv = coeff + (size_t)vec * c_vec_stride;
-    typename F::Acc acc[TAU][TAU];
+    typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S, JB = coeff_eval_jb<Rg>(), JG = TAU / JB;
+    __shared__ u64 red[JB * TAU * 32];
+    const int slot = blockIdx.y, vec = blockIdx.z / JG, j0 = (blockIdx.z % JG) * JB;
+    const TIn* cv = coeff + (size_t)vec * c_vec_stride + (size_t)j0 * S * c_pitch;
+    typename F::Acc acc[JB][TAU];
 #pragma unroll
-    for (int j = 0; j < TAU; ++j)
+    for (int j = 0; j < JB; ++j)
 #pragma unroll
         for (int l = 0; l < TAU; ++l) acc[j][l].clear();
     const size_t x_begin = (size_t)blockIdx.x * x_per_block, x_end = min(n, x_begin + x_per_block);
-    u64 v[TAU * TAU];
+    u64 v[JB * TAU];
     if constexpr (sizeof(TIn) == 1) {
         // digit planes: four consecutive x per thread (one 4-byte digit load per plane, two 16-byte eq loads per limb); the signed
         // digits are shifted to d + 128 >= 0 for the two-multiply small MAC and the shift leaves as 128 * sum_x eq[x]
@@ -394,7 +398,7 @@ k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride,
                 for (int q = 0; q < 4; ++q) se[l].add(e[l][q]);
             }
 #pragma unroll
-            for (int j = 0; j < TAU; ++j) {
+            for (int j = 0; j < JB; ++j) {
                 const char4 d = *reinterpret_cast<const char4*>(cv + (size_t)(j * S + slot) * c_pitch + x);
                 const u32 g[4] = {(u32)((int)d.x + 128), (u32)((int)d.y + 128), (u32)((int)d.z + 128), (u32)((int)d.w + 128)};
 #pragma unroll
@@ -408,14 +412,14 @@ k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride,
             for (int l = 0; l < TAU; ++l) {
                 const u64 el = eq[(size_t)(slot * TAU + l) * eq_pitch + x]; se[l].add(el);
 #pragma unroll
-                for (int j = 0; j < TAU; ++j) acc[j][l].mac_small((u32)((int)(int8_t)cv[(size_t)(j * S + slot) * c_pitch + x] + 128), el);
+                for (int j = 0; j < JB; ++j) acc[j][l].mac_small((u32)((int)(int8_t)cv[(size_t)(j * S + slot) * c_pitch + x] + 128), el);
             }
         }
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
             const u64 corr = F::mul(F::reduce(se[l]), 128);
 #pragma unroll
-            for (int j = 0; j < TAU; ++j) v[j * TAU + l] = F::sub(F::reduce(acc[j][l]), corr);
+            for (int j = 0; j < JB; ++j) v[j * TAU + l] = F::sub(F::reduce(acc[j][l]), corr);
         }
     } else {
         for (size_t x = x_begin + threadIdx.x; x < x_end; x += blockDim.x) {
@@ -423,23 +427,23 @@ k_coeff_eval(const TIn* __restrict__ coeff, size_t c_pitch, size_t c_vec_stride,
 #pragma unroll
             for (int l = 0; l < TAU; ++l) e[l] = eq[(size_t)(slot * TAU + l) * eq_pitch + x];
 #pragma unroll
-            for (int j = 0; j < TAU; ++j) {
+            for (int j = 0; j < JB; ++j) {
                 const u64 c = (u64)cv[(size_t)(j * S + slot) * c_pitch + x];
 #pragma unroll
                 for (int l = 0; l < TAU; ++l) acc[j][l].mac(c, e[l]);
             }
         }
 #pragma unroll
-        for (int j = 0; j < TAU; ++j)
+        for (int j = 0; j < JB; ++j)
 #pragma unroll
             for (int l = 0; l < TAU; ++l) v[j * TAU + l] = F::reduce(acc[j][l]);
     }
-    block_reduce_add<F, TAU * TAU>(v, red);
+    block_reduce_add<F, JB * TAU>(v, red);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int j = 0; j < TAU; ++j)
+        for (int j = 0; j < JB; ++j)
 #pragma unroll
-            for (int l = 0; l < TAU; ++l) partial[(((size_t)blockIdx.x * nvec + vec) * TAU + j) * Rg::D + slot * TAU + l] = v[j * TAU + l];
+            for (int l = 0; l < TAU; ++l) partial[(((size_t)blockIdx.x * nvec + vec) * TAU + j0 + j) * Rg::D + slot * TAU + l] = v[j * TAU + l];
     }
 }
 

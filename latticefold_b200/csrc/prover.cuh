@@ -273,15 +273,17 @@ template <class Rg> struct Prover {
         E.dot(e.v, e.vs, e.vp, (int)t, nullptr, Y, z_pitch, count, zcols(), d_out, "k_dot_eval");
         const u64* land = E.d2h_async(d_out, t * count * D); E.dfree(d_out); return land;
     }
-    DecPending decompose_enqueue(const LCCCS& cm, const lf_witness* w, const DevVec& eq_r, StepBuffers& sb, int half) {
-        DecPending o; o.cm = cm; const int K = P->K; const size_t n = nl(), kappa = P->kappa;
+    // Part A needs only the witness and the instance's public part (x_w, h): digit split, x_s, the K-1 commitments, CRT and
+    // gadget recomposition of every piece.  Part B needs the evaluation point r: v_s and u_s, group by group.  The incoming witness's
+    // part A is therefore queued BEFORE the linearization sumcheck has produced its r and runs beside it on the auxiliary stream.
+    DecPending decompose_enqueue_a(const HV& x_w, const HV& h, const lf_witness* w, StepBuffers& sb, int half) {
+        DecPending o; o.cm.x_w = x_w; o.cm.h = h; const int K = P->K; const size_t n = nl(), kappa = P->kappa;
         int8_t* dig = sb.dig + (size_t)half * K * sb.dig_stride;
         W* pieces = sb.pieces + (size_t)half * K * sb.pc_stride;
         W* zl = sb.zl + (size_t)half * K * sb.zl_stride;
-        if (cnt(cm.cm) != kappa) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongCommitmentLength");
         // decompose_witness: f_coeff.decompose_to_vec(b, K).transpose() (decomposition.rs:162-167)
         E.digit_split(wp(w->f_coeff), w->pitch, dig, sb.dig_pitch, n, P->b, K);
-        o.x_s = compute_x_s(cm);
+        o.x_s = compute_x_s(o.cm);
         write_heads(zl, sb.zl_pitch, K, o.x_s);
         mark("dec.split_x_s");
         // commit_witnesses (decomposition.rs:178-201): K-1 commits in one pass over A.  Digit pieces: integer GEMM on the tensor cores
@@ -291,20 +293,32 @@ template <class Rg> struct Prover {
             E.commit_digits(P->A, dig + sb.dig_stride, sb.dig_pitch, sb.dig_stride, K - 1, d_y);
             o.y_pin = E.d2h_async(d_y, kappa * (K - 1) * D); E.dfree(d_y); }
         mark("dec.commit");
+        // CRT and recompose of every piece (arith.rs:324-338), a few pieces at a time: the NTT forms a CRT launch writes (50 MB per
+        // piece at C2) are still in L2 when the recomposition reads them
+        for (int k0 = 0; k0 < K; k0 += 4) { const int c = std::min(4, K - k0);
+            E.crt_digits(dig + (size_t)k0 * sb.dig_stride, sb.dig_pitch, pieces + (size_t)k0 * sb.pc_stride, sb.pc_pitch, n, c, sb.dig_stride, sb.pc_stride);
+            E.gadget_recompose(pieces + (size_t)k0 * sb.pc_stride, sb.pc_pitch, zl + (size_t)k0 * sb.zl_stride + hc(), sb.zl_pitch, w->W, P->B, P->L, c, sb.pc_stride, sb.zl_stride); }
+        if (!mma && K > 1) {      // the dot-product commit needs every piece's NTT form
+            PL Y; for (int k = 1; k < K; ++k) { Y.p[k - 1] = pieces + (size_t)k * sb.pc_stride; Y.len[k - 1] = n; }
+            u64* d_y = E.template dalloc<u64>(kappa * (K - 1) * D);
+            E.dot(wp(P->A->p), P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y, "k_dot_commit");
+            o.y_pin = E.d2h_async(d_y, kappa * (K - 1) * D); E.dfree(d_y);
+        }
+        mark("dec.crt_recompose");
+        return o;
+    }
+    // Results of part B arrive in groups of pieces, each behind its own event, so that the host hashes group g while the device works on g+1
+    void decompose_enqueue_b(DecPending& o, const LCCCS& cm, const DevVec& eq_r, StepBuffers& sb, int half) {
+        const int K = P->K; const size_t n = nl();
+        if (cnt(cm.cm) != P->kappa) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "WrongCommitmentLength");
+        o.cm = cm;
+        int8_t* dig = sb.dig + (size_t)half * K * sb.dig_stride;
+        W* zl = sb.zl + (size_t)half * K * sb.zl_stride;
         EvalPrep ep = eval_prepare(cm.r);
         o.ngroups = std::min(DEC_GROUPS, K); if (std::getenv("LF_DEC_ONE_GROUP")) o.ngroups = 1;
         for (int g = 0; g <= o.ngroups; ++g) o.g0[g] = (int)((size_t)K * g / o.ngroups);
         for (int g = 0; g < o.ngroups; ++g) {
             const int k0 = o.g0[g], c = o.g0[g + 1] - k0;
-            // CRT and recompose per piece (arith.rs:324-338)
-            E.crt_digits(dig + (size_t)k0 * sb.dig_stride, sb.dig_pitch, pieces + (size_t)k0 * sb.pc_stride, sb.pc_pitch, n, c, sb.dig_stride, sb.pc_stride);
-            E.gadget_recompose(pieces + (size_t)k0 * sb.pc_stride, sb.pc_pitch, zl + (size_t)k0 * sb.zl_stride + hc(), sb.zl_pitch, w->W, P->B, P->L, c, sb.pc_stride, sb.zl_stride);
-            if (!mma && K > 1 && g == o.ngroups - 1) {      // the dot-product commit needs every piece's NTT form
-                PL Y; for (int k = 1; k < K; ++k) { Y.p[k - 1] = pieces + (size_t)k * sb.pc_stride; Y.len[k - 1] = n; }
-                u64* d_y = E.template dalloc<u64>(kappa * (K - 1) * D);
-                E.dot(wp(P->A->p), P->A->pitch * D, P->A->pitch, (int)kappa, nullptr, Y, sb.pc_pitch, K - 1, n, d_y, "k_dot_commit");
-                o.y_pin = E.d2h_async(d_y, kappa * (K - 1) * D); E.dfree(d_y);
-            }
             // compute_v_s (decomposition.rs:204-211): f-hat of piece k evaluated at r, straight from the digits
             { u64* d_v = E.template dalloc<u64>((size_t)c * TAU * D);
               E.template coeff_eval<int8_t>(dig + (size_t)k0 * sb.dig_stride, sb.dig_pitch, sb.dig_stride, c, eq_r.p, eq_r.pitch, n, d_v);
@@ -316,14 +330,16 @@ template <class Rg> struct Prover {
         }
         E.dfree(ep.v);
         mark("dec.groups");
-        return o;
+    }
+    DecPending decompose_enqueue(const LCCCS& cm, const lf_witness* w, const DevVec& eq_r, StepBuffers& sb, int half) {
+        DecPending o = decompose_enqueue_a(cm.x_w, cm.h, w, sb, half); decompose_enqueue_b(o, cm, eq_r, sb, half); return o;
     }
     DecOut decompose_finish(DecPending& pd, Transcript<Rg>& T) {
         DecOut o; const int K = P->K; const size_t kappa = P->kappa, t = P->t; const LCCCS& cm = pd.cm;
         o.x_s = std::move(pd.x_s);
         o.y_s.assign(K, HV(kappa * D, 0)); o.v_s.resize(K); o.u_s.resize(K);
-        // the dot-product commit (rings without the tensor path) lands with the last group; the tensor-core commit before the first
-        const bool y_early = pd.y_early || K == 1;
+        // the commitments are queued in part A, before any group: they have landed when the first group's event has
+        const bool y_early = true;
         auto take_y = [&] {
             for (int k = 1; k < K; ++k) for (size_t i = 0; i < kappa; ++i) std::memcpy(&o.y_s[k][i * D], pd.y_pin + (i * (K - 1) + (k - 1)) * D, 8 * D);
             HV bsum(kappa * D, 0); const u64 bm = P->b % F::P;      // y_0 = cm - b (y_1 + b (y_2 + ...))
@@ -527,6 +543,7 @@ template <class Rg> struct Prover {
         // sharded steps overlap too when the collectives are stream-ordered on both streams (own NCCL communicator + mailbox channels)
         const bool overlap = (world() == 1 || (E.c->nccl && E.c->xg.on)) && !P->detail && !std::getenv("LF_NO_OVERLAP");
         W* lin_tail = (overlap && world() > 1) ? gather_wccs(wp(w_i->w_ccs), w_i->w_pitch * D) : nullptr;
+        const bool early_a = overlap && !std::getenv("LF_NO_EARLY_DEC");      // (A/B switch for measurements)
         {
             lf_ctx* main_ctx = E.c;
             if (overlap) {
@@ -543,6 +560,13 @@ template <class Rg> struct Prover {
                 LF_CUDA(cudaMemsetAsync(sb.dig, 0, (size_t)2 * K * sb.dig_stride, E.st()));   // f-hat tables are zero on [n, 2^s)
                 E.eq_table(acc.r.data(), (int)cnt(acc.r), eq_acc.p, eq_acc.pitch, (size_t)rank() * eq_acc.n, eq_acc.n);
                 pl = decompose_enqueue(acc, w_acc, eq_acc, sb, 0);
+                // the incoming witness's digits, commitments and recomposed pieces do not wait for the linearization either
+                if (early_a) {
+                    // (the incoming witness may still be uploading on the main stream: everything queued there so far comes first)
+                    cudaEvent_t up; LF_CUDA(cudaEventCreateWithFlags(&up, cudaEventDisableTiming)); LF_CUDA(cudaEventRecord(up, main_ctx->stream));
+                    LF_CUDA(cudaStreamWaitEvent(E.st(), up, 0)); cudaEventDestroy(up);
+                    HV h_one; { El one = HR::from_u64(1); h_one.assign(one.begin(), one.end()); } prr = decompose_enqueue_a(x_ccs, h_one, w_i, sb, 1);
+                }
             } catch (...) { E.c = main_ctx; throw; }
             E.c = main_ctx;
         }
@@ -560,7 +584,7 @@ template <class Rg> struct Prover {
         // synchronised above), so the accumulator's results -- the ones the transcript absorbs first -- are never delayed by it.
         { lf_ctx* main_ctx = E.c;
           if (overlap) { E.c = aux_ctx(); E.c->profiling = main_ctx->profiling; }
-          try { prr = decompose_enqueue(lin.lc, w_i, lin.eq_r, sb, 1); } catch (...) { E.c = main_ctx; throw; }
+          try { if (early_a) decompose_enqueue_b(prr, lin.lc, lin.eq_r, sb, 1); else prr = decompose_enqueue(lin.lc, w_i, lin.eq_r, sb, 1); } catch (...) { E.c = main_ctx; throw; }
           E.c = main_ctx; }
         DecOut dl = decompose_finish(pl, T);
         mark("decompose_acc");

@@ -106,6 +106,21 @@ def test_poseidon_ifma_dense_layer_edges(tmp_path):
     assert out[-4] == "lanes" and int(out[-3]) > 2_000_000 and out[-2:] == ["bad", "0"], out
 
 
+def test_babybear_balanced_slot_field_arithmetic(tmp_path):
+    """csrc/field.cuh BbBal -- the balanced-representative Fq9 arithmetic of the wide-slot-field sumcheck kernels -- against 128-bit
+    arithmetic in Fq[Y]/(Y^9 - nu): reductions over the whole signed 64-bit range, products with every operand at +-(p-1)/2 (the
+    accumulator bound), fixed-operand products with an addend, and agreement with the canonical SlotField multiplication
+    (tests/native/bb_balanced.cpp; the same code runs on the device, where tests/test_gpu_parity.py holds it to the oracle)"""
+    import shutil, subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "bb_balanced")
+    subprocess.run([gxx, "-O2", "-std=c++17", os.path.join(ROOT, "tests", "native", "bb_balanced.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout[-2000:]
+
+
 def test_product_rot_lin_combination_kat():
     # crates/cyclotomic-rings/src/rotation.rs:174-776
     g = json.load(open(os.path.join(GOLD, "rotsum_goldilocks.json")))
