@@ -150,7 +150,7 @@ def algorithmic_bytes(wl, ccs, world):
     step, per rank.  These are the bytes the reference's data structures would move for the same work; kernels that read int8
     digits or packed limbs move fewer real bytes, which is the point of those layouts."""
     R = synth.RINGS[wl["ring"]]
-    E = R["d"] * 8
+    E = R["d"] * (4 if R["p"] < (1 << 32) else 8)      # SURVEY 8(d) sizes the 31-bit BabyBear ring with 4-byte limbs (288 B per element)
     s, t, d_ccs = ccs["s"], ccs["t"], ccs["d"]
     n, K, kappa, L = wl["W"] * wl["L"] // world, wl["K"], wl["kappa"], wl["L"]
     m = (1 << s) // world
@@ -497,7 +497,7 @@ def run_c3(args, rank, world, local):
     ctx.profile(True); step_resident(); prof = ctx.profile_report(); ctx.profile(False)
     total_kernel_ms = sum(v[1] for v in prof.values())
     hbm, peak_src = peaks()
-    ccs = prob["ccs"]; E = R["d"] * 8; n, m, kappa, t = wl["W"] * wl["L"], 1 << ccs["s"], wl["kappa"], ccs["t"]
+    ccs = prob["ccs"]; E = R["d"] * 4; n, m, kappa, t = wl["W"] * wl["L"], 1 << ccs["s"], wl["kappa"], ccs["t"]
     rows = wl["W"] + 2
     alg = {"k_dot": (kappa * n + n + kappa) * E, "k_sc_generic": (t + 1) * (m + 3 * m // 2) * E, "k_sc_wide": (t + 1) * 2 * m * E, "k_fold": (t + 1) * 3 * m * E,
            "k_spmv": t * (rows * (E + 8) + 2 * rows * E), "k_eq_combine": 2 * m * E, "k_coeff_eval": 4 * n * E, "k_dot_eval": (t + 1) * rows * E}
@@ -508,6 +508,14 @@ def run_c3(args, rank, world, local):
             kernels.append(dict(kernel=name, launches=cnt, total_ms=round(ms, 4), algorithmic_bytes=b, achieved_gbs=(b / 1e9) / (ms / 1e3) if b else None,
                                 frac=((b / 1e9) / (ms / 1e3) / hbm) if b else None))
     top = kernels[0]
+    # the sumcheck kernel is bound by the FMA-heavy (integer multiplier) pipe, not by HBM (profiles/r02s_k_sc_wide_bb_full.md): report the
+    # wide multiply-accumulates it issues against the measured IMAD.WIDE rate (profiles/r01d_imad_peak.md)
+    int_pipe = None
+    if "k_sc_wide" in prof:
+        npts = ccs["d"] + 2; muls_per_point = sum(max(len(S_i) - 1, 0) for S_i in ccs["S"]) + 1      # +-1 coefficients are signs; + the eq factor
+        wide = 2 * (m // 2) * R["S"] * npts * muls_per_point * 106                                   # all rounds ~ 2 x round 1; 89 + 17 wide multiplies per Fq9 product
+        int_pipe = dict(kernel="k_sc_wide", wide_multiplies_per_step=int(wide), achieved_per_s=wide / (prof["k_sc_wide"][1] / 1e3), peak_per_s=6.97e12,
+                        frac=wide / (prof["k_sc_wide"][1] / 1e3) / 6.97e12, fmaheavy_pipe_busy_ncu=0.648)
     line = dict(metric=METRIC, value=constraints / (ms_res / 1e3), unit="constraints/s", n_gpus=1, steps=args.steps, warmup=args.warmup, ms_per_step=ms_res,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype=DTYPE["c3"], data="synthetic",
                 config=dict(config_of(wl, args, "gpu"), step="Witness::commit (A f) + LFLinearizationProver::prove (BASELINE.md C3: commit + linearization sumcheck)",
@@ -518,7 +526,8 @@ def run_c3(args, rank, world, local):
                 roofline=dict(bound="hbm", kernel=top["kernel"], launches_per_step=top["launches"], avg_launch_ms=top["total_ms"] / top["launches"],
                               share_of_kernel_time=top["total_ms"] / total_kernel_ms, achieved=top["achieved_gbs"], peak=hbm, unit="GB/s", frac=top["frac"], traffic=None,
                               peak_source=peak_src, algorithmic_bytes_per_step=top["algorithmic_bytes"], kernels=kernels,
-                              note="algorithmic bytes in the REFERENCE layout (576 B per element); the packed planes move half of that"),
+                              note="algorithmic bytes per SURVEY 8(d): 288 B per BabyBear ring element (packed 4-byte limbs, the layout the planes have on the device; "
+                                   "the reference's own memory image is 576 B per element)", int_pipe=int_pipe),
                 kernels_ms={k: dict(launches=v[0], total_ms=round(v[1], 4)) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
                 verified=verify["verified"], proof_sha256=verify["proof_sha256"], verify=verify,
                 host=dict(poseidon=lf.Transcript(RING).backend(), cpus=os.cpu_count()))

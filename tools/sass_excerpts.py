@@ -27,10 +27,13 @@ dump(r"k_commit_mmaINS_14GoldilocksRing", "tensor-core digit commit: tcgen05.mma
      "mbarriers (SYNCS), tcgen05.commit (UTCBAR)", r"UTCIMMA|UBLKCP|LDTM|UTCBAR|UTCATOMSWS|SYNCS|ELECT", 60)
 dump(r"k_ntt_ctaIN2lf3ntt3GlFELi12ELb0ELb0", "negacyclic NTT (N = 2^12, Goldilocks, forward): bulk load of the polynomials (UBLKCP) completing on an mbarrier", r"UBLKCP|SYNCS", 20)
 dump(r"k_ntt_ctaIN2lf3ntt3BbFELi12ELb0ELb0", "negacyclic NTT (N = 2^12, BabyBear, forward)", r"UBLKCP|SYNCS", 20)
+dump(r"k_sc_wide_bbILi160ELi5", "wide-slot-field sumcheck round (BabyBear Fq9, csrc/sumcheck_wide.cuh): table tiles by bulk copies (UBLKCP) through a two-stage mbarrier ring (SYNCS)",
+     r"UBLKCP|SYNCS|ELECT", 20)
 out.append("\n## instruction mix of the integer kernels (counts of SASS mnemonics in the kernel body)\n\n| kernel | IMAD.WIDE | other IMAD | IADD3 / IADD3.X | SHFL | LDG | LDS | total |\n|---|---:|---:|---:|---:|---:|---:|---:|\n")
 for pat, label in ((r"15k_fold_sc_roundINS_14GoldilocksRing", "k_fold_sc_round<Goldilocks>"), (r"k_fold_sc_round2INS_14GoldilocksRing", "k_fold_sc_round2<Goldilocks>"),
                    (r"k_fold_sc_round1INS_14GoldilocksRing", "k_fold_sc_round1<Goldilocks>"), (r"k_sc_pointsINS_14GoldilocksRingELi4", "k_sc_points<Goldilocks, 4>"),
-                   (r"k_sc_pointsINS_12BabyBearRingELi5", "k_sc_points<BabyBear, 5>"), (r"5k_dotINS_14GoldilocksRingELi2ELi256", "k_dot<Goldilocks, 2>"),
+                   (r"k_sc_pointsINS_12BabyBearRingELi5", "k_sc_points<BabyBear, 5>"),
+                   (r"k_sc_wide_bbILi160ELi5", "k_sc_wide_bb<160, 5> (BabyBear, balanced Fq9)"), (r"k_fold_wide_bb", "k_fold_wide_bb (BabyBear)"), (r"5k_dotINS_14GoldilocksRingELi2ELi256", "k_dot<Goldilocks, 2>"),
                    (r"5k_dotINS_12BabyBearRingELi1ELi256", "k_dot<BabyBear, 1>"), (r"k_commit_mmaINS_14GoldilocksRing", "k_commit_mma<Goldilocks>")):
     for b in blocks:
         if re.search(pat, b.split("\n", 1)[0]):
