@@ -220,19 +220,22 @@ struct Goldilocks {
 #endif
     };
     static LF_HD u64 reduce(const Sum& a) { return reduce128(a.lo(), a.hi()); }
-    // slim accumulator for sums of (small multiplier) x (field element): 96 bits in three registers; holds 2^20 terms with
-    // multipliers below 2^12 (the digit-weighted sums of the FOLD sumcheck's first two rounds)
+    // slim accumulator for sums of (small multiplier) x (field element); holds 2^20 terms with multipliers below 2^12 (the
+    // digit-weighted sums of the FOLD sumcheck's first two rounds).  Two independent 64-bit sums, one per 32-bit half of the field
+    // element: each multiply-accumulate is two chained IMAD.WIDE on their own even-aligned register pairs and nothing else.  (The
+    // 96-bit three-register form this replaces made the second wide multiply accumulate into the pair (e1, e2), which cannot be
+    // even-aligned together with (e0, e1): ptxas inserted ~3.6 register moves per multiply-accumulate, all on the FMA-heavy pipe
+    // the wide multiplies already saturate -- 87 of 190 instructions in the round-2 table loop, ncu r02w.)
     struct AccS {
 #if defined(__CUDA_ARCH__)
-        u32 e0, e1, e2;
-        LF_HD void clear() { e0 = e1 = e2 = 0; }
+        u64 L, H;      // (64-bit operands: the register allocator keeps each sum in one even-aligned pair)
+        LF_HD void clear() { L = H = 0; }
         LF_HD void mac_small(u32 a, u64 b) {
-            asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;\n\t"
-                "mad.lo.cc.u32 %1, %3, %5, %1;\n\tmadc.hi.u32 %2, %3, %5, %2;"
-                : "+r"(e0), "+r"(e1), "+r"(e2) : "r"(a), "r"((u32)b), "r"((u32)(b >> 32)));
+            asm("mad.wide.u32 %0, %2, %3, %0;\n\tmad.wide.u32 %1, %2, %4, %1;" : "+l"(L), "+l"(H) : "r"(a), "r"((u32)b), "r"((u32)(b >> 32)));
         }
-        LF_HD u64 lo() const { return ((u64)e1 << 32) | e0; }
-        LF_HD u64 hi() const { return e2; }
+        // value = L + H 2^32
+        LF_HD u64 lo() const { return L + (H << 32); }
+        LF_HD u64 hi() const { const u64 s = L + (H << 32); return (H >> 32) + (s < L ? 1 : 0); }
 #else
         u128 v;
         LF_HD void clear() { v = 0; }

@@ -890,7 +890,13 @@ k_fold_sc_round1(const FoldScArgsT<typename Rg::W> a) {
     typedef typename Rg::F F; constexpr int TAU = Rg::TAU, S = Rg::S;
     __shared__ u64 red[5 * TAU * 32];
     __shared__ u64 s_mu[MAX_MU * TAU];
+    __shared__ u64 s_msum[TAU];                              // sum of all mu (the same for every pair: formed once per block)
+    __shared__ u32 s_g[9];                                   // (g2 + 24) | (g3 + 120) << 16 by digit pair
     for (int i = threadIdx.x; i < a.n_f * TAU; i += blockDim.x) s_mu[i] = a.mu_pow[i];
+    if (threadIdx.x < 9) { const int x = (int)threadIdx.x % 3 - 1, y = (int)threadIdx.x / 3 - 1, f2 = 2 * y - x, f3 = 3 * y - 2 * x;
+        s_g[threadIdx.x] = (u32)(f2 * f2 * f2 - f2 + 24) | ((u32)(f3 * f3 * f3 - f3 + 120) << 16); }
+    __syncthreads();
+    if (threadIdx.x < TAU) { typename F::Sum sm; sm.clear(); for (int kd = 0; kd < a.n_f; ++kd) sm.add(s_mu[kd * TAU + threadIdx.x]); s_msum[threadIdx.x] = F::reduce(sm); }
     __syncthreads();
     const int slot = blockIdx.y;
     const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const bool active = b < a.n_pairs;
@@ -903,23 +909,23 @@ k_fold_sc_round1(const FoldScArgsT<typename Rg::W> a) {
         // g(X) = f(X)^3 - f(X) is one of 0, +-6, +-24 at X = 2 and 0, +-6, ..., +-120 at X = 3.  The signed weights are shifted to
         // non-negative ones (g + 24, g + 120) so that every table feeds the same branch-free small-multiplier MACs -- no lane
         // divergence on the digits, and the loads of several tables can be in flight together -- and the shift is taken out
-        // again as 24 / 120 times the sum of all mu.
-        typename F::Acc a2[TAU], a3[TAU], am[TAU];
+        // again as 24 / 120 times the sum of all mu.  The weights come from a nine-entry table indexed by the digit pair (the
+        // integer multiplies of the closed form sit on the same FMA-heavy pipe as the wide multiplies that bound the kernel).
+        typename F::AccS a2[TAU], a3[TAU];
 #pragma unroll
-        for (int l = 0; l < TAU; ++l) { a2[l].clear(); a3[l].clear(); am[l].clear(); }
+        for (int l = 0; l < TAU; ++l) { a2[l].clear(); a3[l].clear(); }
 #pragma unroll 4
         for (int kd = 0; kd < a.n_f; ++kd) {
             const int k = kd / TAU, d = kd - k * TAU;
             const char2 dd = *reinterpret_cast<const char2*>(a.dig + (size_t)k * a.dig_stride + (size_t)(d * S + slot) * a.dig_pitch + 2 * b);
-            const int f2 = 2 * dd.y - dd.x, f3 = 3 * dd.y - 2 * dd.x;
-            const u32 g2 = (u32)(f2 * f2 * f2 - f2 + 24), g3 = (u32)(f3 * f3 * f3 - f3 + 120);
+            const u32 g = s_g[(dd.x + 1) + 3 * (dd.y + 1)], g2 = g & 0xffffu, g3 = g >> 16;
             const u64* mu = &s_mu[kd * TAU];
 #pragma unroll
-            for (int l = 0; l < TAU; ++l) { a2[l].mac_small(g2, mu[l]); a3[l].mac_small(g3, mu[l]); am[l].add(mu[l]); }
+            for (int l = 0; l < TAU; ++l) { a2[l].mac_small(g2, mu[l]); a3[l].mac_small(g3, mu[l]); }
         }
 #pragma unroll
         for (int l = 0; l < TAU; ++l) {
-            const u64 ms = F::reduce(am[l]);
+            const u64 ms = s_msum[l];
             const u64 h2 = F::sub(F::reduce(a2[l]), F::mul(ms, 24)), h3 = F::sub(F::reduce(a3[l]), F::mul(ms, 120));
             h[2][l] = h2; h[3][l] = h3;
             // h(0) = h(1) = 0 and third differences constant: h(4) = 4 h(3) - 6 h(2)
@@ -950,66 +956,131 @@ template <class Rg> __global__ void k_fold_digits(const int8_t* __restrict__ dig
 // i.e. four sums of mu with small integer weights per point -- two-multiply MACs on 96-bit accumulators, no slot-field product per
 // table -- instead of the 66 full multiply-accumulates per table of the general round kernel, and the 2.4 GB of T1 tables are never
 // written or read.  Four lanes per pair take the points X = 0..3 (h is a cubic: h(4) follows from its finite differences).
-template <class Rg> __global__ void __launch_bounds__(128)
+// A block walks R2_GROUPS groups of 32 pairs; the round message's five points are spread over the four lanes of a pair for the dense
+// part too -- lane X evaluates g at point X (its own h(X) times eq(beta) plus the two eq * G products, one lazily reduced sum of three
+// slot-field products), lane 0 also point 4 -- and the block's partial is reduced once.  (ncu r02y of the one-group form with the
+// whole dense part on lane 0: 6426 of a warp's 13 200 instructions were that tail and the 15-value block reduction.)
+constexpr int R2_GROUPS = 4;
+template <class Rg> __global__ void __launch_bounds__(128, Rg::TAU <= 3 ? 4 : 1)      // four blocks per SM on the narrow slot field (132 B of spills in the dense part)
 k_fold_sc_round2(const FoldScArgsT<typename Rg::W> a) {
     typedef typename Rg::F F; typedef SlotField<Rg> SF; constexpr int TAU = Rg::TAU, S = Rg::S;
-    __shared__ u64 red[5 * TAU * 32];
     __shared__ u64 s_corr[TAU];                              // 2048 * sum of all mu
-    extern __shared__ __align__(16) unsigned char dyn_smem[];   // n_f * TAU mu limbs, then the block's digits [table][32 pairs]
+    __shared__ ushort4 s_lut[81 * 4];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];   // n_f * TAU mu limbs, then the group's digits [table][32 pairs]
     u64* s_mu = reinterpret_cast<u64*>(dyn_smem);
     char4 (*s_dig)[32] = reinterpret_cast<char4 (*)[32]>(dyn_smem + (size_t)a.n_f * TAU * 8);
     const int slot = blockIdx.y, X = threadIdx.x & 3, pl = threadIdx.x >> 2;
-    const size_t b0 = (size_t)blockIdx.x * 32, b = b0 + pl; const bool active = b < a.n_pairs;
-    // all digit loads of the block are issued up front (n_f / 4 independent 4-byte loads per thread, one 128-byte row per warp and
-    // table) instead of one dependent load per table inside the accumulation loop
-    for (int kd = threadIdx.x >> 5; kd < a.n_f; kd += 4) {
-        const int k = kd / TAU, d = kd - k * TAU; const int lane = threadIdx.x & 31;
-        char4 v = make_char4(0, 0, 0, 0);
-        if (b0 + lane < a.n_pairs) v = *reinterpret_cast<const char4*>(a.dig + (size_t)k * a.dig_stride + (size_t)(d * S + slot) * a.dig_pitch + 4 * (b0 + lane));
-        s_dig[kd][lane] = v;
-    }
     for (int i = threadIdx.x; i < a.n_f * TAU; i += blockDim.x) s_mu[i] = a.mu_pow[i];
+    // the four weights (+ 2048) by digit quadruple and point: 81 x 4 entries (one dp4a and one load per table instead of the closed forms)
+    for (int i = threadIdx.x; i < 81 * 4; i += blockDim.x) {
+        const int q = i >> 2, Xi = i & 3, d0 = q % 3 - 1, d1 = (q / 3) % 3 - 1, d2 = (q / 9) % 3 - 1, d3 = q / 27 - 1;
+        const int a0 = d0, e0 = d1 - d0, a1 = d2, e1 = d3 - d2, P = a0 + Xi * (a1 - a0), Q = e0 + Xi * (e1 - e0);
+        s_lut[i] = make_ushort4((unsigned short)(P * P * P - P + 2048), (unsigned short)(Q * (3 * P * P - 1) + 2048), (unsigned short)(3 * P * Q * Q + 2048), (unsigned short)(Q * Q * Q + 2048));
+    }
     __syncthreads();
     if (threadIdx.x < TAU) { typename F::Sum sm; sm.clear(); for (int kd = 0; kd < a.n_f; ++kd) sm.add(s_mu[kd * TAU + threadIdx.x]); s_corr[threadIdx.x] = F::mul(F::reduce(sm), 2048); }
-    __syncthreads();
-    u64 hx[TAU];
+    u64 evx[TAU], ev4[TAU];                                  // running sums of g(X) (every lane) and g(4) (lane 0 of each quad)
 #pragma unroll
-    for (int l = 0; l < TAU; ++l) hx[l] = 0;
-    if (active) {
-        typename F::AccS acc[4][TAU];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int l = 0; l < TAU; ++l) acc[j][l].clear();
-#pragma unroll 2
-        for (int kd = 0; kd < a.n_f; ++kd) {
-            const char4 dd = s_dig[kd][pl];
-            const int a0 = dd.x, e0 = dd.y - dd.x, a1 = dd.z, e1 = dd.w - dd.z;
-            const int P = a0 + X * (a1 - a0), Q = e0 + X * (e1 - e0);
-            const u32 c0 = (u32)(P * P * P - P + 2048), c1 = (u32)(Q * (3 * P * P - 1) + 2048), c2 = (u32)(3 * P * Q * Q + 2048), c3 = (u32)(Q * Q * Q + 2048);
-            const u64* mu = &s_mu[kd * TAU];
-#pragma unroll
-            for (int l = 0; l < TAU; ++l) { const u64 m = mu[l]; acc[0][l].mac_small(c0, m); acc[1][l].mac_small(c1, m); acc[2][l].mac_small(c2, m); acc[3][l].mac_small(c3, m); }
+    for (int l = 0; l < TAU; ++l) evx[l] = ev4[l] = 0;
+    for (int grp = 0; grp < R2_GROUPS; ++grp) {
+        const size_t b0 = ((size_t)blockIdx.x * R2_GROUPS + grp) * 32, b = b0 + pl; const bool active = b < a.n_pairs;
+        if (b0 >= a.n_pairs) break;
+        __syncthreads();                                     // the previous group's digits have been consumed (first pass: s_corr is complete)
+        // all digit loads of the group are issued up front (n_f / 4 independent 4-byte loads per thread, one 128-byte row per warp and table)
+        for (int kd = threadIdx.x >> 5; kd < a.n_f; kd += 4) {
+            const int k = kd / TAU, d = kd - k * TAU; const int lane = threadIdx.x & 31;
+            char4 v = make_char4(0, 0, 0, 0);
+            if (b0 + lane < a.n_pairs) v = *reinterpret_cast<const char4*>(a.dig + (size_t)k * a.dig_stride + (size_t)(d * S + slot) * a.dig_pitch + 4 * (b0 + lane));
+            s_dig[kd][lane] = v;
         }
-        u64 sj[4][TAU];
+        __syncthreads();
+        u64 hx[TAU];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int l = 0; l < TAU; ++l) hx[l] = 0;
+        if (active) {
+            typename F::AccS acc[4][TAU];
 #pragma unroll
-            for (int l = 0; l < TAU; ++l) sj[j][l] = F::sub(F::reduce(acc[j][l]), s_corr[l]);
-        // Horner in r
-        SF::mul(hx, sj[3], a.r1); SF::add(hx, hx, sj[2]); SF::mul(hx, hx, a.r1); SF::add(hx, hx, sj[1]); SF::mul(hx, hx, a.r1); SF::add(hx, hx, sj[0]);
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) acc[j][l].clear();
+#pragma unroll 2
+            for (int kd = 0; kd < a.n_f; ++kd) {
+                const int q = __dp4a(reinterpret_cast<const int*>(&s_dig[kd][0])[pl], 0x1B090301, 40);      // (d0 + 1) + 3 (d1 + 1) + 9 (d2 + 1) + 27 (d3 + 1)
+                const ushort4 cw = s_lut[q * 4 + X];
+                const u32 c0 = cw.x, c1 = cw.y, c2 = cw.z, c3 = cw.w;
+                const u64* mu = &s_mu[kd * TAU];
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) { const u64 m = mu[l]; acc[0][l].mac_small(c0, m); acc[1][l].mac_small(c1, m); acc[2][l].mac_small(c2, m); acc[3][l].mac_small(c3, m); }
+            }
+            u64 sj[4][TAU];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) sj[j][l] = F::sub(F::reduce(acc[j][l]), s_corr[l]);
+            // Horner in r
+            SF::mul(hx, sj[3], a.r1); SF::add(hx, hx, sj[2]); SF::mul(hx, hx, a.r1); SF::add(hx, hx, sj[1]); SF::mul(hx, hx, a.r1); SF::add(hx, hx, sj[0]);
+        }
+        // h(4) = 4 h(3) - 6 h(2) + 4 h(1) - h(0) (h is a cubic), formed in every lane of the quad (lane 0 uses it)
+        u64 h4[TAU];
+        const int base = (threadIdx.x & 31) & ~3;
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) {
+            const u64 h0 = __shfl_sync(0xffffffffu, hx[l], base), h1 = __shfl_sync(0xffffffffu, hx[l], base + 1), h2 = __shfl_sync(0xffffffffu, hx[l], base + 2), h3 = __shfl_sync(0xffffffffu, hx[l], base + 3);
+            const u64 t31 = F::add(h3, h1), t31x2 = F::add(t31, t31), t31x4 = F::add(t31x2, t31x2), h2x2 = F::add(h2, h2), h2x6 = F::add(F::add(h2x2, h2x2), h2x2);
+            h4[l] = F::sub(F::sub(t31x4, h2x6), h0);
+        }
+        if (active) {
+            // g at this lane's point: v_k(X) = v_k(0) + X step_k, then eq(beta) h + eq(r_acc) G_acc + eq(r_new) G_new as ONE lazily reduced sum
+            auto g_at = [&](const u64 (*v)[TAU], const u64* hh, u64* out) {
+                typename F::Acc acc3[TAU];
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) acc3[l].clear();
+                SF::mac(acc3, v[4], SF::prep(hh)); SF::mac(acc3, v[0], SF::prep(v[1])); SF::mac(acc3, v[2], SF::prep(v[3]));
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) out[l] = F::reduce(acc3[l]);
+            };
+            // the pair's dense entries (the same addresses in the four lanes of a quad: one broadcast request)
+            u64 val[5][TAU], stp[5][TAU];
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) { u64 p1; ld_pair(a.dense + (size_t)k * a.dense_stride + (size_t)(slot * TAU + l) * a.dense_pitch + 2 * b, val[k][l], p1); stp[k][l] = F::sub(p1, val[k][l]); }
+            u64 v[5][TAU], g[TAU];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+#pragma unroll
+                for (int l = 0; l < TAU; ++l) v[k][l] = val[k][l];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) if (i < X) SF::add(v[k], v[k], stp[k]);
+            }
+            g_at(v, hx, g);
+            SF::add(evx, evx, g);
+            if (X == 0) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) { u64 s2[TAU]; SF::add(s2, stp[k], stp[k]); SF::add(s2, s2, s2); SF::add(v[k], val[k], s2); }
+                g_at(v, h4, g);
+                SF::add(ev4, ev4, g);
+            }
+        }
     }
-    // lane X = 0 of every quad gathers h(1), h(2), h(3) and extrapolates h(4) = 4 h(3) - 6 h(2) + 4 h(1) - h(0)
-    u64 h[5][TAU];
-    const int base = (threadIdx.x & 31) & ~3;
+    // quads of a warp -> lanes 0..3 hold the warp's sums of point X (lane X) and point 4 (lane 0); warps through shared memory
 #pragma unroll
     for (int l = 0; l < TAU; ++l) {
-        const u64 h0 = hx[l], h1 = __shfl_sync(0xffffffffu, hx[l], base + 1), h2 = __shfl_sync(0xffffffffu, hx[l], base + 2), h3 = __shfl_sync(0xffffffffu, hx[l], base + 3);
-        h[0][l] = h0; h[1][l] = h1; h[2][l] = h2; h[3][l] = h3;
-        const u64 t31 = F::add(h3, h1), t31x2 = F::add(t31, t31), t31x4 = F::add(t31x2, t31x2), h2x2 = F::add(h2, h2), h2x6 = F::add(F::add(h2x2, h2x2), h2x2);
-        h[4][l] = F::sub(F::sub(t31x4, h2x6), h0);
+#pragma unroll
+        for (int o = 16; o >= 4; o >>= 1) { evx[l] = F::add(evx[l], __shfl_xor_sync(0xffffffffu, evx[l], o)); ev4[l] = F::add(ev4[l], __shfl_xor_sync(0xffffffffu, ev4[l], o)); }
     }
-    fold_sc_tail<Rg>(a, b, active && X == 0, slot, h, red);
+    __shared__ u64 s_w[4][5][TAU];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < 4) {
+#pragma unroll
+        for (int l = 0; l < TAU; ++l) { s_w[warp][lane][l] = evx[l]; if (lane == 0) s_w[warp][4][l] = ev4[l]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 * TAU) {
+        const int e = threadIdx.x / TAU, l = threadIdx.x % TAU;
+        const u64 sum = F::add(F::add(s_w[0][e][l], s_w[1][e][l]), F::add(s_w[2][e][l], s_w[3][e][l]));
+        a.partial[((size_t)blockIdx.x * 5 + e) * Rg::D + slot * TAU + l] = sum;
+    }
 }
 // after the second challenge the f-hat tables are materialised for the first time, again from the digits:
 //   T2[b] = T1[2b] + r2 (T1[2b+1] - T1[2b]) = a0 + r1 e0 + r2 (a1 - a0) + r1 r2 (e1 - e0)

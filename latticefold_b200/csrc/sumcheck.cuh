@@ -84,7 +84,7 @@ template <class Rg> struct SumcheckDriver {
         if (sc->kind == LF_COMB_FOLD) {
             const bool round1 = sc->dig && sc->applied == 0, round2d = sc->dig && sc->applied == 1 && sc->fh_deferred;
             const unsigned gx1 = (unsigned)((n_pairs + 127) / 128), gx2 = (unsigned)((n_pairs + 63) / 64);      // rounds >= 2: two lanes per pair
-            nblk = round1 ? gx1 : round2d ? (unsigned)((n_pairs + 31) / 32) : gx2;                                 // round 2 from digits: four lanes per pair
+            nblk = round1 ? gx1 : round2d ? (unsigned)((n_pairs + 32 * R2_GROUPS - 1) / (32 * R2_GROUPS)) : gx2;      // round 2 from digits: four lanes per pair, R2_GROUPS groups of 32 pairs per block
             partial = E.partial_dev((size_t)nblk * 5 * D);
             FoldScArgsT<W> a; a.dense = wp(sc->dense.cur); a.dense_pitch = sc->dense.pitch; a.dense_stride = sc->dense.stride; a.mu_pow = sc->d_mu_pow; a.n_f = sc->n_f;
             a.n_pairs = n_pairs; a.partial = partial; a.dig = sc->dig; a.dig_pitch = sc->dig_pitch; a.dig_stride = sc->dig_stride;
