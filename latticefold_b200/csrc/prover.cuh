@@ -516,7 +516,8 @@ template <class Rg> struct Prover {
         LCCCS a; auto ld = [&](const u64* p, size_t n) { return load_canonical(p, n, "the accumulator"); };
         a.r = ld(in.acc_r, P->s); a.v = ld(in.acc_v, TAU); a.cm = ld(in.acc_cm, P->kappa); a.u = ld(in.acc_u, P->t); a.x_w = ld(in.acc_x_w, P->l); a.h = ld(in.acc_h, 1); return a;
     }
-    lf_witness* prove(const lf_problem& in, const lf_witness* w_acc, const lf_witness* w_i, Transcript<Rg>& T, u64* out_proof, u64* out_lcccs, bool presynced = false) {
+    // derive_out = false: the caller only downloads the folded f (host-buffer entry point) -- its coefficient form and w_ccs are not derived
+    lf_witness* prove(const lf_problem& in, const lf_witness* w_acc, const lf_witness* w_i, Transcript<Rg>& T, u64* out_proof, u64* out_lcccs, bool presynced = false, bool derive_out = true) {
         using clk = std::chrono::steady_clock; auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         for (double& x : P->timings) x = 0;
         if (!presynced) { E.sync(); E.arena_reset(); }      // presynced: the caller did both before queueing the witness uploads
@@ -601,7 +602,9 @@ template <class Rg> struct Prover {
         std::vector<LCCCS> lcs = dl.lc; lcs.insert(lcs.end(), dr.lc.begin(), dr.lc.end());
         FoldOut fo = fold(lcs, sb, eq_acc, lin.eq_r, T);
         mark("fold.host_tail");
-        lf_witness* w_out = witness_from_f_device(fo.f0);
+        lf_witness* w_out;
+        if (derive_out) w_out = witness_from_f_device(fo.f0);
+        else { w_out = new lf_witness; w_out->n = nl(); w_out->pitch = pitch_of(nl()); w_out->f = ow(fo.f0); w_out->W = Wl(); w_out->w_pitch = pitch_of(w_out->W); }
         cleanup.armed = false;
         E.dfree(sb.dig); E.dfree(sb.pieces); E.dfree(sb.zl); E.dfree(eq_acc.p); E.dfree(lin.eq_r.p);
         E.sync(); auto t3 = clk::now(); P->timings[2] = ms(t2, t3);

@@ -389,7 +389,7 @@ template <class Rg> struct RingOpsImpl final : RingOps {
         lf_witness* wi = pr.upload_witness(in->w_i_f);
         lf_witness* w = nullptr;
         cudaEvent_t ev = p->acc_ready;
-        try { w = pr.prove(*in, wa, wi, tr(t), out_proof, out_lcccs, true); } catch (...) { p->acc_ready = nullptr; cudaEventDestroy(ev); pr.free_witness(wa); pr.free_witness(wi); throw; }
+        try { w = pr.prove(*in, wa, wi, tr(t), out_proof, out_lcccs, true, false); } catch (...) { p->acc_ready = nullptr; cudaEventDestroy(ev); pr.free_witness(wa); pr.free_witness(wi); throw; }
         p->acc_ready = nullptr; cudaEventDestroy(ev);
         if (out_f) pr.E.download_planes(wp(w->f), w->pitch, w->n, out_f);
         pr.free_witness(w); pr.free_witness(wa); pr.free_witness(wi); pr.E.sync();
