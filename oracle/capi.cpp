@@ -5,6 +5,7 @@
 // power of X), vectors as contiguous arrays of such elements -- the same host format the product C-ABI uses.
 #include "protocol.hpp"
 #include "ntt.hpp"
+#include "lfplus.hpp"
 #include <map>
 #include <memory>
 #include <chrono>
@@ -250,4 +251,52 @@ int lfo_ntt_fast(int field, int log_n, const u64* in, u64* out, size_t batch, in
 int lfo_ntt_schoolbook(int field, int log_n, const u64* a, const u64* b, u64* out) {
     return guard([&] { nttx::schoolbook(nttx::field(field), log_n, a, b, out); });
 }
+
+// ---- LatticeFold+ set check / range check (lfplus.hpp).  Same struct layout as the product's lf_csr / lf_plus_set.
+struct lfo_plus_set { int32_t kind; int32_t pad; lfo_csr m; const u64* v; u64 n; };      // kind 0: matrix (m), 1: vector (v, n elements)
+namespace {
+plus::SparseR sparse_of(const RingParams& R, const lfo_csr& m) {
+    plus::SparseR S; S.nrows = m.nrows; S.ncols = m.ncols; S.row_ptr.assign(m.row_ptr, m.row_ptr + m.nrows + 1); const u64 nnz = S.row_ptr.back();
+    S.col.assign(m.col, m.col + nnz); S.val.assign(m.val, m.val + nnz * R.d); return S;
+}
+plus::PlusTranscript plus_transcript(const RingParams& R, const u64* seed, size_t n_seed) { plus::PlusTranscript T(R); if (n_seed) T.sp.absorb(seed, n_seed); return T; }
+}
+// returns the number of words written (or needed, when cap is too small: nothing is written), < 0 on error
+long lfo_plus_set_check(int id, int nvars, const lfo_plus_set* sets, int n_sets, const lfo_csr* M, int n_M, const u64* seed, size_t n_seed, u64* out, size_t cap) {
+    long n = -1; int rc = guard([&] { const RingParams& R = ring(id);
+        std::vector<plus::MonSet> S; for (int i = 0; i < n_sets; ++i) { plus::MonSet s; s.matrix = sets[i].kind == 0; if (s.matrix) s.M = sparse_of(R, sets[i].m); else s.v.assign(sets[i].v, sets[i].v + sets[i].n * R.d); S.push_back(std::move(s)); }
+        std::vector<plus::SparseR> Ms; for (int i = 0; i < n_M; ++i) Ms.push_back(sparse_of(R, M[i]));
+        auto T = plus_transcript(R, seed, n_seed);
+        auto w = plus::set_out_words(R, plus::set_check(R, nvars, S, Ms, T)); n = (long)w.size(); if (w.size() <= cap) memcpy(out, w.data(), 8 * w.size()); });
+    return rc ? rc : n;
+}
+int lfo_plus_set_check_verify(int id, const u64* words, size_t len, const u64* seed, size_t n_seed) {
+    int ok = 0; int rc = guard([&] { const RingParams& R = ring(id); plus::SetOut o; plus::set_out_parse(R, words, len, o); auto T = plus_transcript(R, seed, n_seed); ok = plus::set_check_verify(R, o, T) ? 1 : 0; });
+    return rc ? rc : ok;
+}
+// RgInstance::from_f: tau[n], fcoms[3 x kappa x d], comM[k x kappa x d x d] (any output pointer may be NULL)
+int lfo_plus_rg_from_f(int id, const u64* f, size_t n, const u64* A, size_t kappa, u64 b, int k, int l, u64* tau, u64* fcoms, u64* comM) {
+    return guard([&] { const RingParams& R = ring(id); const size_t d = R.d; plus::DecompParameters dp{b, k, l};
+        auto I = plus::rg_from_f(R, Vec(f, f + n * d), Vec(A, A + kappa * n * d), kappa, dp);
+        if (tau) memcpy(tau, I.tau.data(), 8 * n);
+        if (fcoms) { memcpy(fcoms, I.fcoms.cm_f.data(), 8 * kappa * d); memcpy(fcoms + kappa * d, I.fcoms.C_Mf.data(), 8 * kappa * d); memcpy(fcoms + 2 * kappa * d, I.fcoms.cm_mtau.data(), 8 * kappa * d); }
+        if (comM) for (int kk = 0; kk < k; ++kk) memcpy(comM + (size_t)kk * kappa * d * d, I.comM_f[kk].data(), 8 * kappa * d * d); });
+}
+// Rg{nvars, L instances from_f(f_l, A)}.range_check(M, transcript): f = L x n x d
+long lfo_plus_range_check(int id, int nvars, int L, const u64* f, size_t n, const u64* A, size_t kappa, u64 b, int k, int l, const lfo_csr* M, int n_M,
+                          const u64* seed, size_t n_seed, u64* out, size_t cap) {
+    long nw = -1; int rc = guard([&] { const RingParams& R = ring(id); const size_t d = R.d; plus::DecompParameters dp{b, k, l};
+        std::vector<plus::RgInstance> inst; for (int i = 0; i < L; ++i) inst.push_back(plus::rg_from_f(R, Vec(f + (size_t)i * n * d, f + (size_t)(i + 1) * n * d), Vec(A, A + kappa * n * d), kappa, dp));
+        std::vector<plus::SparseR> Ms; for (int i = 0; i < n_M; ++i) Ms.push_back(sparse_of(R, M[i]));
+        auto T = plus_transcript(R, seed, n_seed);
+        auto w = plus::dcom_words(R, plus::range_check(R, nvars, inst, dp, Ms, T), kappa); nw = (long)w.size(); if (w.size() <= cap) memcpy(out, w.data(), 8 * w.size()); });
+    return rc ? rc : nw;
+}
+int lfo_plus_range_check_verify(int id, const u64* words, size_t len, const u64* seed, size_t n_seed) {
+    int ok = 0; int rc = guard([&] { const RingParams& R = ring(id); plus::Dcom D; size_t kappa = 0; plus::dcom_parse(R, words, len, D, kappa); auto T = plus_transcript(R, seed, n_seed); ok = plus::range_check_verify(R, D, T) ? 1 : 0; });
+    return rc ? rc : ok;
+}
+int lfo_plus_tensor(int id, const u64* r, int n, u64* out) { return guard([&] { auto t = plus::tensor(ring(id), r, n); memcpy(out, t.data(), 8 * t.size()); }); }
+int lfo_plus_ring_mul(int id, const u64* a, const u64* b, u64* out) { return guard([&] { plus::r_mul(ring(id), out, a, b); }); }
+
 }  // extern "C"

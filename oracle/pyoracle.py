@@ -16,7 +16,7 @@ i32p = C.POINTER(C.c_int)
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, f) for f in ("capi.cpp", "ntt.hpp", "ring.hpp", "transcript.hpp", "sumcheck.hpp", "protocol.hpp")]
+    srcs = [os.path.join(HERE, f) for f in ("capi.cpp", "ntt.hpp", "ring.hpp", "transcript.hpp", "sumcheck.hpp", "protocol.hpp", "lfplus.hpp")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "-s"], stdout=subprocess.DEVNULL)
     return LIB_PATH
@@ -24,6 +24,34 @@ def build(force=False):
 
 class Csr(C.Structure):
     _fields_ = [("nrows", C.c_uint64), ("ncols", C.c_uint64), ("row_ptr", u64p), ("col", u64p), ("val", u64p)]
+
+
+class PlusSet(C.Structure):
+    """One monomial set of the LatticeFold+ set check (kind 0: sparse matrix, 1: vector); layout of `lfo_plus_set` / `lf_plus_set`."""
+    _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("m", Csr), ("v", u64p), ("n", C.c_uint64)]
+
+
+def make_csr_array(mats, csr_cls=Csr):
+    arr = (csr_cls * max(len(mats), 1))()
+    for j, M in enumerate(mats):
+        arr[j].nrows, arr[j].ncols = M["nrows"], M["ncols"]
+        arr[j].row_ptr, arr[j].col, arr[j].val = ptr(M["row_ptr"]), ptr(M["col"]), ptr(M["val"])
+    return arr
+
+
+def make_plus_sets(sets, set_cls=None, csr_cls=Csr):
+    """sets: list of ("matrix", csr dict) / ("vector", n x d uint64 array)."""
+    set_cls = set_cls or PlusSet
+    arr = (set_cls * max(len(sets), 1))()
+    for i, (kind, x) in enumerate(sets):
+        if kind == "matrix":
+            arr[i].kind = 0
+            arr[i].m.nrows, arr[i].m.ncols = x["nrows"], x["ncols"]
+            arr[i].m.row_ptr, arr[i].m.col, arr[i].m.val = ptr(x["row_ptr"]), ptr(x["col"]), ptr(x["val"])
+        else:
+            arr[i].kind = 1
+            arr[i].v, arr[i].n = ptr(x), x.shape[0]
+    return arr
 
 
 class Problem(C.Structure):
@@ -281,6 +309,92 @@ class Oracle:
         lc = np.empty(self.lib.lfo_lcccs_words(C.byref(P)), dtype=np.uint64)
         self.check(self.lib.lfo_nifs_verify(C.byref(P), tr.h, ptr(np.ascontiguousarray(proof)), ptr(lc)))
         return lc
+
+    # ---- LatticeFold+ (oracle/lfplus.hpp): set check and range check on the coefficient-form ring; results are flat uint64 images
+    def _plus_setup(self):
+        L = self.lib
+        if getattr(self, "_plus_ready", False):
+            return
+        L.lfo_plus_set_check.restype = C.c_long
+        L.lfo_plus_set_check.argtypes = [C.c_int, C.c_int, C.POINTER(PlusSet), C.c_int, C.POINTER(Csr), C.c_int, u64p, C.c_size_t, u64p, C.c_size_t]
+        L.lfo_plus_set_check_verify.argtypes = [C.c_int, u64p, C.c_size_t, u64p, C.c_size_t]
+        L.lfo_plus_rg_from_f.argtypes = [C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, C.c_int, C.c_int, u64p, u64p, u64p]
+        L.lfo_plus_range_check.restype = C.c_long
+        L.lfo_plus_range_check.argtypes = [C.c_int, C.c_int, C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, C.c_int, C.c_int, C.POINTER(Csr), C.c_int, u64p, C.c_size_t, u64p, C.c_size_t]
+        L.lfo_plus_range_check_verify.argtypes = [C.c_int, u64p, C.c_size_t, u64p, C.c_size_t]
+        L.lfo_plus_tensor.argtypes = [C.c_int, u64p, C.c_int, u64p]
+        L.lfo_plus_ring_mul.argtypes = [C.c_int, u64p, u64p, u64p]
+        self._plus_ready = True
+
+    @staticmethod
+    def _seed(seed):
+        seed = np.ascontiguousarray(np.asarray(seed if seed is not None else [], dtype=np.uint64))
+        return seed, (ptr(seed) if seed.size else None), seed.size
+
+    def _plus_call(self, fn):
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, dtype=np.uint64)
+            n = fn(out, cap)
+            if n < 0:
+                raise OracleError(int(n), self.err())
+            if n <= cap:
+                return out[:n].copy()
+            cap = int(n)
+
+    def plus_set_check(self, ring, nvars, sets, M=(), seed=None):
+        self._plus_setup()
+        sa, ma = make_plus_sets(sets), make_csr_array(list(M))
+        sd, sp, sn = self._seed(seed)
+        return self._plus_call(lambda out, cap: self.lib.lfo_plus_set_check(ring, nvars, sa, len(sets), ma, len(M), sp, sn, ptr(out), cap))
+
+    def plus_set_check_verify(self, ring, words, seed=None):
+        self._plus_setup()
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        sd, sp, sn = self._seed(seed)
+        rc = self.lib.lfo_plus_set_check_verify(ring, ptr(words), words.size, sp, sn)
+        if rc < 0:
+            raise OracleError(rc, self.err())
+        return bool(rc)
+
+    def plus_rg_from_f(self, ring, f, A, b, k, l):
+        """RgInstance::from_f: returns (tau[n], fcoms[3, kappa, d], comM_f[k, kappa, d, d])."""
+        self._plus_setup()
+        d = self.info(ring)["d"]
+        n, kappa = f.shape[0], A.shape[0]
+        tau, fc, cm = np.zeros(n, dtype=np.uint64), np.zeros((3, kappa, d), dtype=np.uint64), np.zeros((k, kappa, d, d), dtype=np.uint64)
+        self.check(self.lib.lfo_plus_rg_from_f(ring, ptr(np.ascontiguousarray(f)), n, ptr(np.ascontiguousarray(A)), kappa, b, k, l, ptr(tau), ptr(fc), ptr(cm)))
+        return tau, fc, cm
+
+    def plus_range_check(self, ring, nvars, fs, A, b, k, l, M=(), seed=None):
+        """fs: L x n x d witnesses; A: kappa x n x d.  Returns the Dcom image (from_f of every instance + range_check)."""
+        self._plus_setup()
+        fs, A = np.ascontiguousarray(fs), np.ascontiguousarray(A)
+        ma = make_csr_array(list(M))
+        sd, sp, sn = self._seed(seed)
+        return self._plus_call(lambda out, cap: self.lib.lfo_plus_range_check(ring, nvars, fs.shape[0], ptr(fs), fs.shape[1], ptr(A), A.shape[0], b, k, l, ma, len(M), sp, sn, ptr(out), cap))
+
+    def plus_range_check_verify(self, ring, words, seed=None):
+        self._plus_setup()
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        sd, sp, sn = self._seed(seed)
+        rc = self.lib.lfo_plus_range_check_verify(ring, ptr(words), words.size, sp, sn)
+        if rc < 0:
+            raise OracleError(rc, self.err())
+        return bool(rc)
+
+    def plus_tensor(self, ring, r):
+        self._plus_setup()
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        out = np.zeros(1 << r.size, dtype=np.uint64)
+        self.check(self.lib.lfo_plus_tensor(ring, ptr(r), r.size, ptr(out)))
+        return out
+
+    def plus_ring_mul(self, ring, a, b):
+        self._plus_setup()
+        out = np.zeros_like(a)
+        self.check(self.lib.lfo_plus_ring_mul(ring, ptr(np.ascontiguousarray(a)), ptr(np.ascontiguousarray(b)), ptr(out)))
+        return out
 
 
 class OracleError(RuntimeError):
