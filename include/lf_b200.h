@@ -285,6 +285,43 @@ lf_status lf_ntt_inverse_host(lf_ctx* ctx, const lf_ntt_plan* plan, const void* 
 lf_status lf_ntt_pointwise_mul_device(lf_ctx* ctx, const lf_ntt_plan* plan, const void* d_a, const void* d_b, void* d_out, size_t batch);
 lf_status lf_ntt_negacyclic_mul_host(lf_ctx* ctx, const lf_ntt_plan* plan, const void* h_a, const void* h_b, void* h_out, size_t batch);
 
+/* ---- LatticeFold+ consumers of the same kernels (crates/latticefold-plus) on the coefficient-form ring
+ * R = Z_q[X]/(X^16 + 1) (LF_RING_FROG, `frog_ring::RqPoly`, BaseRing = Fq).  Ring elements cross as 16 canonical coefficients.
+ * The transcript is the same Poseidon sponge (latticefold-plus/src/transcript.rs:16-56: absorb = the coefficients, a challenge is
+ * ONE field element squeezed and absorbed back): pass an lf_transcript created for LF_RING_FROG.
+ *
+ * Results are flat u64 images:
+ *   set check   (setchk.rs:28-36 `Out`):  [nvars, n_mat, ncols, n_vec, n_M]  r[nvars]  sumcheck messages [nvars][4][16]
+ *                                         e[(1 + n_M)][n_mat][ncols][16]  b[n_vec][16]
+ *   range check (rgchk.rs:50-64 `Dcom`):  [L, k, l, kappa, b]  the set-check image, then per instance
+ *                                         v[16] a[1 + n_M] b[1 + n_M][16] c[1 + n_M][16] cm_f[kappa][16] C_Mf[kappa][16] cm_mtau[kappa][16]
+ * Conventions of the un-vendored stark-rings pieces (exp(0) = 1, element order of `split`): DESIGN.md "Conventions".           */
+typedef struct { int32_t kind; int32_t pad; lf_csr m; const uint64_t* v; uint64_t n; } lf_plus_set; /* MonomialSet  setchk.rs:17-21: kind 0 = Matrix(m), 1 = Vector(v, n elements) */
+typedef struct lf_plus_mat lf_plus_mat;   /* Matrix<R> kappa x n, coefficient form, device resident (the matrix A of from_f)  */
+typedef struct lf_plus_rg lf_plus_rg;     /* RgInstance<R>                            rgchk.rs:41-48                          */
+/* Transcript::get_challenge of latticefold-plus/src/transcript.rs:46-55 (extension degree 1)                                  */
+void lf_transcript_get_challenge_base(lf_transcript* t, uint64_t* out1);
+/* In::set_check                              setchk.rs:59-262.  LF_ERR_INVALID_ARG when out_cap is too small (*out_len = needed) */
+lf_status lf_plus_set_check(lf_ctx* ctx, lf_transcript* t, int32_t nvars, const lf_plus_set* sets, int32_t n_sets,
+                            const lf_csr* M, int32_t n_M, uint64_t* out, uint64_t out_cap, uint64_t* out_len);
+/* Out::verify                                setchk.rs:264-344 (host).  LF_OK = accepted, LF_ERR_SUMCHECK_FAILED = rejected   */
+lf_status lf_plus_set_check_verify(lf_transcript* t, const uint64_t* words, uint64_t len);
+lf_status lf_plus_mat_create(lf_ctx* ctx, uint64_t kappa, uint64_t n, const uint64_t* host_coeff, lf_plus_mat** out);
+void lf_plus_mat_free(lf_ctx* ctx, lf_plus_mat* a);
+/* RgInstance::from_f                         rgchk.rs:259-336: digits of cf(f), M_f = exp(D_f), A * M_f, split, cm_f, C_Mf, cm_mtau.
+ * LF_ERR_DOES_NOT_FIT when a coefficient of f needs more than k digits in base b                                              */
+lf_status lf_plus_rg_from_f(lf_ctx* ctx, const lf_plus_mat* A, const uint64_t* f_coeff, uint64_t n, uint64_t b, int32_t k, int32_t l, lf_plus_rg** out);
+/* tau[n], fcoms[3][kappa][16] = cm_f, C_Mf, cm_mtau, comM[k][kappa][16][16] = A * M_f[kk]; any pointer may be NULL             */
+lf_status lf_plus_rg_read(const lf_plus_rg* inst, uint64_t* tau, uint64_t* fcoms, uint64_t* comM);
+void lf_plus_rg_free(lf_ctx* ctx, lf_plus_rg* inst);
+/* Rg::range_check                            rgchk.rs:75-187                                                                   */
+lf_status lf_plus_range_check(lf_ctx* ctx, lf_transcript* t, int32_t nvars, lf_plus_rg* const* inst, int32_t L,
+                              const lf_csr* M, int32_t n_M, uint64_t* out, uint64_t out_cap, uint64_t* out_len);
+/* Dcom::verify                               rgchk.rs:190-246 (host).  LF_OK / LF_ERR_SUMCHECK_FAILED / LF_ERR_RECOMPOSED (a psi check) */
+lf_status lf_plus_range_check_verify(lf_transcript* t, const uint64_t* words, uint64_t len);
+/* utils.rs:74-86 tensor(r) (host): out has 2^n entries                                                                         */
+lf_status lf_plus_tensor(const uint64_t* r, int32_t n, uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,407 @@
+// Host drivers, host verifiers and extern "C" surface of the LatticeFold+ consumers (kernels: lfplus.cuh; declarations and image
+// layouts: include/lf_b200.h).  The Fiat-Shamir transcript stays on the host as in the reference; every witness-sized loop is a kernel.
+#include "ring_ops.cuh"
+#include "lfplus.cuh"
+#include <algorithm>
+#include <numeric>
+
+using namespace lf;
+using namespace lf::plus;
+
+struct lf_plus_mat { u64* d = nullptr; size_t kappa = 0, n = 0; };
+struct lf_plus_rg {
+    size_t n = 0, kappa = 0, code_pitch = 0; int k = 0, l = 0; u64 b = 0;
+    unsigned char* codes = nullptr;        // [k * 16 columns][code_pitch]: exponents of M_f[kk][.][c]
+    unsigned char* mtau_codes = nullptr;   // [code_pitch]: exponents of m_tau
+    signed char* tau = nullptr;            // [n]: the digits of split (small signed integers)
+    u64* f = nullptr;                      // [n][16] canonical
+    std::vector<u64> tau_host, fcoms, comM;
+};
+
+namespace {
+typedef Engine<FrogRing> Eng;
+typedef Transcript<FrogRing> Tr;
+thread_local std::string g_plus_err;
+template <class Fn> lf_status pguard(lf_ctx* ctx, Fn&& fn) {
+    try { fn(); return LF_OK; }
+    catch (const LfException& e) { if (ctx) ctx->err = e.what(); g_plus_err = e.what(); return e.code; }
+    catch (const std::exception& e) { if (ctx) ctx->err = e.what(); g_plus_err = e.what(); return LF_ERR_INVALID_ARG; }
+}
+Tr& tr_of(lf_transcript* t) { if (!t || t->ring != LF_RING_FROG) throw LfException(LF_ERR_INVALID_ARG, "LatticeFold+ entry points need a transcript of LF_RING_FROG"); return *(Tr*)t->impl; }
+void need_frog(lf_ctx* c) { if (!c || c->ring != LF_RING_FROG) throw LfException(LF_ERR_UNSUPPORTED, "LatticeFold+ entry points run on the Frog ring (X^16 + 1) only"); }
+
+// transcript surface of latticefold-plus/src/transcript.rs
+u64 challenge(Tr& T) { u64 c; T.squeeze_base(&c, 1); T.absorb_base(&c, 1); return c; }
+void absorb_field(Tr& T, u64 c) { u64 el[PD] = {0}; el[0] = c; T.absorb_base(el, PD); }
+
+// a sparse matrix / dense vector of ring elements grouped by columns on the device
+struct DevSparse {
+    u64* col_ptr = nullptr; u32 *erow = nullptr, *ecol = nullptr; u64* val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0;
+    void free(Eng& E) { E.dfree(col_ptr); E.dfree(erow); E.dfree(ecol); E.dfree(val); col_ptr = nullptr; erow = ecol = nullptr; val = nullptr; }
+};
+void check_canonical(const u64* v, size_t n, const char* what) { for (size_t i = 0; i < n; ++i) if (v[i] >= Fm::P) throw LfException(LF_ERR_INVALID_ARG, std::string(what) + ": non-canonical field element"); }
+DevSparse upload_by_columns(Eng& E, const lf_csr& m) {
+    if (!m.row_ptr || (m.row_ptr[m.nrows] && (!m.col || !m.val))) throw LfException(LF_ERR_INVALID_ARG, "sparse matrix: null arrays");
+    const size_t nnz = m.row_ptr[m.nrows];
+    if (m.nrows >> 32 || m.ncols >> 32) throw LfException(LF_ERR_UNSUPPORTED, "sparse matrix: more than 2^32 rows / columns");
+    check_canonical(m.val, nnz * PD, "sparse matrix");
+    std::vector<u64> cp(m.ncols + 1, 0); std::vector<u32> rows(nnz);
+    for (size_t r = 0; r < m.nrows; ++r) { if (m.row_ptr[r + 1] < m.row_ptr[r] || m.row_ptr[r + 1] > nnz) throw LfException(LF_ERR_INVALID_ARG, "sparse matrix: row_ptr not monotone");
+        for (u64 e = m.row_ptr[r]; e < m.row_ptr[r + 1]; ++e) { if (m.col[e] >= m.ncols) throw LfException(LF_ERR_INVALID_ARG, "sparse matrix: column index out of range"); cp[m.col[e] + 1]++; rows[e] = (u32)r; } }
+    for (size_t c = 0; c < m.ncols; ++c) cp[c + 1] += cp[c];
+    std::vector<u64> pos(cp.begin(), cp.end() - 1), val(std::max<size_t>(nnz, 1) * PD); std::vector<u32> er(std::max<size_t>(nnz, 1)), ec(std::max<size_t>(nnz, 1));
+    for (size_t e = 0; e < nnz; ++e) { const u64 p = pos[m.col[e]]++; er[p] = rows[e]; ec[p] = (u32)m.col[e]; std::memcpy(&val[p * PD], m.val + e * PD, 8 * PD); }
+    DevSparse S; S.nrows = m.nrows; S.ncols = m.ncols; S.nnz = nnz;
+    S.col_ptr = E.dalloc<u64>(cp.size()); S.erow = E.dalloc<u32>(er.size()); S.ecol = E.dalloc<u32>(ec.size()); S.val = E.dalloc<u64>(val.size());
+    LF_CUDA(cudaMemcpyAsync(S.col_ptr, cp.data(), cp.size() * 8, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemcpyAsync(S.erow, er.data(), er.size() * 4, cudaMemcpyHostToDevice, E.st()));
+    LF_CUDA(cudaMemcpyAsync(S.ecol, ec.data(), ec.size() * 4, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemcpyAsync(S.val, val.data(), val.size() * 8, cudaMemcpyHostToDevice, E.st()));
+    E.sync();      // the staging vectors die here
+    return S;
+}
+DevSparse upload_dense_vector(Eng& E, const u64* v, size_t n) {
+    if (!v || n >> 32) throw LfException(LF_ERR_INVALID_ARG, "vector set: null / too long");
+    check_canonical(v, n * PD, "vector set");
+    std::vector<u32> er(std::max<size_t>(n, 1)), ec(std::max<size_t>(n, 1), 0); std::iota(er.begin(), er.end(), 0u); const u64 cp[2] = {0, n};
+    DevSparse S; S.nrows = n; S.ncols = 1; S.nnz = n;
+    S.col_ptr = E.dalloc<u64>(2); S.erow = E.dalloc<u32>(er.size()); S.ecol = E.dalloc<u32>(ec.size()); S.val = E.dalloc<u64>(std::max<size_t>(n, 1) * PD);
+    LF_CUDA(cudaMemcpyAsync(S.col_ptr, cp, 16, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemcpyAsync(S.erow, er.data(), er.size() * 4, cudaMemcpyHostToDevice, E.st()));
+    LF_CUDA(cudaMemcpyAsync(S.ecol, ec.data(), ec.size() * 4, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemcpyAsync(S.val, v, n * PD * 8, cudaMemcpyHostToDevice, E.st()));
+    E.sync();
+    return S;
+}
+
+// one monomial set as the device sees it: exponent codes (the range check's own M_f / m_tau) or general entries (anything the caller passes)
+struct DevSet { const unsigned char* codes = nullptr; size_t code_pitch = 0; const DevSparse* gen = nullptr; size_t nrows = 0, ncols = 0; };
+
+unsigned chunks_for(size_t n, int tpb) { return (unsigned)std::min<size_t>(std::max<size_t>((n + tpb - 1) / tpb, 1), 148 * 4); }
+
+// out = sum over block partials -> host, `cols` ring elements; scale: 0 as is, 1 from Montgomery, 2 times 2^64 (canonical x canonical products)
+void finish_wsum(Eng& E, u64* partial, unsigned chunks, size_t cols, int scale, u64* out_host) {
+    u64* d_out = E.small_dev(cols * PD);
+    E.reduce_partials(partial, (int)chunks, cols * PD, d_out);
+    E.download_words(d_out, cols * PD, out_host);
+    if (scale == 1) for (size_t i = 0; i < cols * PD; ++i) out_host[i] = Fm::from_mont(out_host[i]);
+    if (scale == 2) for (size_t i = 0; i < cols * PD; ++i) out_host[i] = Fm::to_mont(out_host[i]);
+}
+// sum_x W[x] entry(x, col) for every column of a set; W scalar (Montgomery eq table) or ring-valued (canonical, 16 words per x)
+void wsum_set(Eng& E, const DevSet& S, const u64* W, bool ring_w, u64* out_host) {
+    if (S.codes) {
+        const unsigned ch = chunks_for(S.nrows, 256); u64* partial = E.partial_dev((size_t)ch * S.ncols * PD);
+        if (ring_w) E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, (unsigned)S.ncols), 256, 0, E.st()>>>(W, S.codes, S.code_pitch, S.nrows, partial); });
+        else E.launch("k_plus_wsum_scalar_mono", [&] { k_plus_wsum_scalar_mono<<<dim3(ch, (unsigned)S.ncols), 256, 0, E.st()>>>(W, S.codes, S.code_pitch, S.nrows, partial); });
+        finish_wsum(E, partial, ch, S.ncols, ring_w ? 0 : 1, out_host);
+    } else {
+        const DevSparse& G = *S.gen; const int tpb = ring_w ? 128 : 256;
+        const unsigned ch = chunks_for(std::max<size_t>(G.nnz / std::max<size_t>(G.ncols, 1), 1), tpb); u64* partial = E.partial_dev((size_t)ch * G.ncols * PD);
+        if (ring_w) E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, (unsigned)G.ncols), 128, 0, E.st()>>>(W, G.col_ptr, G.erow, G.val, partial); });
+        else E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, (unsigned)G.ncols), 256, 0, E.st()>>>(W, G.col_ptr, G.erow, G.val, partial); });
+        finish_wsum(E, partial, ch, G.ncols, ring_w ? 2 : 0, out_host);
+    }
+}
+SmallArgs small_consts() { SmallArgs s; for (int t = -8; t < 8; ++t) s.v[t & 15] = Fm::to_mont(t < 0 ? Fm::P - (u64)(-t) : (u64)t); return s; }
+void eq_table(Eng& E, const std::vector<u64>& c, u64* d_out, size_t N) {
+    if (c.size() > 40) throw LfException(LF_ERR_UNSUPPORTED, "more than 40 variables");
+    EqArgs a; a.nv = (int)c.size(); for (size_t i = 0; i < c.size(); ++i) { a.c[i] = Fm::to_mont(c[i]); a.omc[i] = Fm::to_mont(Fm::sub(1, c[i])); }
+    E.launch("k_plus_eq", [&] { k_plus_eq<<<Eng::blocks_for(N, 256), 256, 0, E.st()>>>(d_out, N, a, Fm::r1()); });
+}
+
+struct SetCheckResult {
+    int nvars = 0, n_mat = 0, ncols = 0, n_vec = 0, n_M = 0;
+    std::vector<u64> r, msgs, e, b;
+    u64* d_eq_r = nullptr; std::vector<u64*> d_w;      // eq(r, .) (Montgomery) and w_i = M_i^T eq(r, .) stay on the device for the range check
+    void free(Eng& E) { E.dfree(d_eq_r); for (u64* p : d_w) E.dfree(p); d_eq_r = nullptr; d_w.clear(); }
+    std::vector<u64> words() const {
+        std::vector<u64> w = {(u64)nvars, (u64)n_mat, (u64)ncols, (u64)n_vec, (u64)n_M};
+        for (auto* v : {&r, &msgs, &e, &b}) w.insert(w.end(), v->begin(), v->end());
+        return w;
+    }
+};
+
+// In::set_check (setchk.rs:59-262) with the tables of the sumcheck held as base-field words
+SetCheckResult set_check_core(Eng& E, Tr& T, int nvars, const std::vector<DevSet>& mats, const std::vector<DevSet>& vecs, const std::vector<DevSparse>& M) {
+    if (mats.empty()) throw LfException(LF_ERR_UNSUPPORTED, "set check needs at least one matrix set (setchk.rs:85)");
+    if (nvars < 1 || nvars > 30) throw LfException(LF_ERR_INVALID_ARG, "set check: nvars out of range");
+    const size_t N = (size_t)1 << nvars, ncols = mats[0].ncols, nrows = mats[0].nrows, nM = mats.size(), nV = vecs.size();
+    if (nrows > N || !ncols) throw LfException(LF_ERR_INVALID_ARG, "set check: more rows than 2^nvars / no columns");
+    for (auto& s : mats) if (s.ncols != ncols || s.nrows != nrows) throw LfException(LF_ERR_INVALID_ARG, "set check: matrix sets of different shapes");
+    for (auto& s : vecs) if (s.ncols != 1 || s.nrows != nrows) throw LfException(LF_ERR_INVALID_ARG, "set check: vector set of a different length");
+    for (auto& m : M) if (m.ncols != nrows || m.nrows > N) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "set check: M_i does not match the sets");
+    const size_t n_tables = nM * (2 * ncols + 1) + nV * 3;
+    u64* Tb = E.dalloc<u64>(n_tables * N); LF_CUDA(cudaMemsetAsync(Tb, 0, n_tables * N * 8, E.st()));
+    std::vector<Group> groups; std::vector<u64> alphas; size_t base = 0, wofs = 0;
+    auto one_set = [&](const DevSet& S) {      // Steps 1-2 for one set: c, beta, the tables, alpha
+        std::vector<u64> c(nvars); for (auto& x : c) x = challenge(T);
+        const u64 beta = challenge(T);
+        PowArgs pw; u64 bp = 1;
+        for (int e = 0; e < PD; ++e) { pw.v[e] = S.codes ? Fm::to_mont(bp) : Fm::to_mont(Fm::to_mont(bp)); bp = Fm::hmul(bp, beta); }
+        u64* Ts = Tb + base * N;
+        if (S.codes) E.launch("k_plus_tables", [&] { k_plus_tables_mono<<<dim3(Eng::blocks_for(S.nrows, 256), (unsigned)S.ncols), 256, 0, E.st()>>>(S.codes, S.code_pitch, S.nrows, Ts, N, pw); });
+        else if (S.gen->nnz) E.launch("k_plus_tables", [&] { k_plus_tables_general<<<Eng::blocks_for(S.gen->nnz, 256), 256, 0, E.st()>>>(S.gen->ecol, S.gen->erow, S.gen->val, S.gen->nnz, Ts, N, pw); });
+        eq_table(E, c, Ts + 2 * S.ncols * N, N);
+        groups.push_back(Group{(int)base, (int)S.ncols, (int)wofs, 0}); base += 2 * S.ncols + 1; wofs += S.ncols;
+        alphas.push_back(challenge(T));
+    };
+    for (auto& s : mats) one_set(s);
+    for (auto& s : vecs) one_set(s);
+    const bool have_rc = nM > 1; const u64 rc = have_rc ? challenge(T) : 1;
+    // weights alpha_i^j rc^i (matrix sets), alpha rc^(n_mat + i) (vector sets).  Without rc the reference's closure returns after the
+    // first matrix set (setchk.rs:169-173): only that group takes part in the sumcheck.
+    std::vector<u64> w(wofs);
+    for (size_t g = 0; g < groups.size(); ++g) { const u64 rcp = Fm::hpow(rc, g);
+        for (int j = 0; j < groups[g].ncols; ++j) w[groups[g].wofs + j] = Fm::to_mont(Fm::hmul(g < nM ? Fm::hpow(alphas[g], j) : alphas[g], rcp)); }
+    const int n_active = have_rc ? (int)groups.size() : 1;
+    Group* d_groups = E.dalloc<Group>(groups.size()); u64* d_w = E.dalloc<u64>(w.size());
+    E.h2d(d_groups, groups.data(), groups.size() * sizeof(Group)); E.h2d(d_w, w.data(), w.size() * 8);
+
+    SetCheckResult R; R.nvars = nvars; R.n_mat = (int)nM; R.ncols = (int)ncols; R.n_vec = (int)nV; R.n_M = (int)M.size();
+    // MLSumcheck::prove_as_subprotocol (sumcheck.rs:53-80), degree 3
+    absorb_field(T, (u64)nvars); absorb_field(T, 3);
+    R.msgs.assign((size_t)nvars * 4 * PD, 0);
+    u64* Tn = E.dalloc<u64>(n_tables * (N / 2)); u64 *cur = Tb, *nxt = Tn; size_t len = N; u64 r_prev = 0;
+    for (int i = 0; i < nvars; ++i) {
+        if (i > 0) {      // fix_variables with the previous challenge (prover.rs:61-72)
+            const size_t n_out = len / 2; const u64 rm = Fm::to_mont(r_prev);
+            E.launch("k_plus_fold", [&] { k_plus_fold<<<dim3(Eng::blocks_for(n_out, 256), (unsigned)n_tables), 256, 0, E.st()>>>(cur, len, nxt, n_out, rm); });
+            std::swap(cur, nxt); len = n_out;
+        }
+        const size_t n_pairs = len / 2; const unsigned nblk = chunks_for(n_pairs, 256);
+        u64* partial = E.partial_dev((size_t)nblk * 4); u64* d_out = E.small_dev(4);
+        E.launch("k_plus_round", [&] { k_plus_round<<<nblk, 256, 0, E.st()>>>(cur, len, n_pairs, d_groups, n_active, d_w, partial); });
+        E.reduce_partials(partial, (int)nblk, 4, d_out);
+        u64 h[4]; E.download_words(d_out, 4, h);
+        u64* msg = R.msgs.data() + (size_t)i * 4 * PD;
+        for (int X = 0; X < 4; ++X) msg[X * PD] = Fm::from_mont(h[X]);      // constants of R
+        T.absorb_slice(msg, 4);
+        r_prev = challenge(T); absorb_field(T, r_prev); R.r.push_back(r_prev);
+    }
+    E.dfree(Tb); E.dfree(Tn); E.dfree(d_groups); E.dfree(d_w);
+    // Step 3 (setchk.rs:199-257): e[0] = MLE(column)(r), e[1 + i] = MLE(M_i column)(r) = sum_x (M_i^T eq(r, .))[x] column[x], b = MLE(vector)(r)
+    R.d_eq_r = E.dalloc<u64>(N); eq_table(E, R.r, R.d_eq_r, N);
+    for (auto& m : M) { u64* wv = E.dalloc<u64>(std::max<size_t>(m.ncols, 1) * PD);
+        E.launch("k_plus_mt_eq", [&] { k_plus_mt_eq<<<Eng::blocks_for(m.ncols, 128), 128, 0, E.st()>>>(R.d_eq_r, m.col_ptr, m.erow, m.val, m.ncols, wv); });
+        R.d_w.push_back(wv); }
+    R.e.assign((1 + M.size()) * nM * ncols * PD, 0);
+    for (size_t mi = 0; mi <= M.size(); ++mi) for (size_t i = 0; i < nM; ++i)
+        wsum_set(E, mats[i], mi == 0 ? R.d_eq_r : R.d_w[mi - 1], mi != 0, R.e.data() + (mi * nM + i) * ncols * PD);
+    R.b.assign(nV * PD, 0);
+    for (size_t i = 0; i < nV; ++i) wsum_set(E, vecs[i], R.d_eq_r, false, R.b.data() + i * PD);
+    T.absorb_slice(R.e.data(), R.e.size() / PD); T.absorb_slice(R.b.data(), R.b.size() / PD);      // absorb_evaluations, setchk.rs:346-356
+    return R;
+}
+
+// ---------------------------------------------------------------- host verifiers (the reference's verifiers are host code as well)
+u64 ev_host(const u64* r, u64 x) { u64 acc = 0, e = 1; for (int i = 0; i < PD; ++i) { acc = Fm::add(acc, Fm::hmul(r[i], e)); e = Fm::hmul(e, x); } return acc; }      // setchk.rs:46-57
+struct SetImage { int nvars, n_mat, ncols, n_vec, n_M; const u64 *r, *msgs, *e, *b; size_t words; };
+SetImage parse_set_image(const u64* w, size_t len) {
+    if (!w || len < 5) throw LfException(LF_ERR_INCORRECT_LENGTH, "set-check image too short");
+    if (w[0] < 1 || w[0] > 40 || w[1] < 1 || w[1] > 4096 || w[2] < 1 || w[2] > (1u << 20) || w[3] > 4096 || w[4] > 64) throw LfException(LF_ERR_INVALID_ARG, "set-check image: implausible header");
+    SetImage s; s.nvars = (int)w[0]; s.n_mat = (int)w[1]; s.ncols = (int)w[2]; s.n_vec = (int)w[3]; s.n_M = (int)w[4];
+    const size_t nr = s.nvars, nm = (size_t)s.nvars * 4 * PD, ne = (size_t)(1 + s.n_M) * s.n_mat * s.ncols * PD, nb = (size_t)s.n_vec * PD;
+    s.words = 5 + nr + nm + ne + nb; if (len < s.words) throw LfException(LF_ERR_INCORRECT_LENGTH, "set-check image truncated");
+    s.r = w + 5; s.msgs = s.r + nr; s.e = s.msgs + nm; s.b = s.e + ne;
+    check_canonical(w + 5, s.words - 5, "set-check image");
+    return s;
+}
+// Out::verify (setchk.rs:264-344); `point` receives the sumcheck's challenges
+void verify_set_image(Tr& T, const SetImage& s, std::vector<u64>* point_out = nullptr) {
+    const int nv = s.nvars, nclaims = s.n_mat + s.n_vec;
+    struct Cba { std::vector<u64> c; u64 beta, alpha; }; std::vector<Cba> cba(nclaims);
+    for (auto& x : cba) { x.c.resize(nv); for (auto& v : x.c) v = challenge(T); x.beta = challenge(T); x.alpha = challenge(T); }
+    const u64 rc = s.n_mat > 1 ? challenge(T) : 1;
+    // MLSumcheck::verify_as_subprotocol (sumcheck.rs:84-104) with claimed sum 0, degree 3
+    absorb_field(T, (u64)nv); absorb_field(T, 3);
+    std::vector<u64> point(nv);
+    for (int i = 0; i < nv; ++i) { T.absorb_slice(s.msgs + (size_t)i * 4 * PD, 4); point[i] = challenge(T); absorb_field(T, point[i]); }
+    u64 expected[PD] = {0};
+    for (int i = 0; i < nv; ++i) { const u64* msg = s.msgs + (size_t)i * 4 * PD;
+        for (int c = 0; c < PD; ++c) if (Fm::add(msg[c], msg[PD + c]) != expected[c]) throw LfException(LF_ERR_SUMCHECK_FAILED, "set check: sumcheck round sum mismatch");
+        // interpolate through X = 0..3 at the challenge (verifier.rs:139-254)
+        u64 lag[4];
+        for (int a = 0; a < 4; ++a) { u64 num = 1, den = 1;
+            for (int b = 0; b < 4; ++b) if (b != a) { num = Fm::hmul(num, Fm::sub(point[i], (u64)b)); den = Fm::hmul(den, a > b ? (u64)(a - b) : Fm::P - (u64)(b - a)); }
+            lag[a] = Fm::hmul(num, Fm::hpow(den, Fm::P - 2)); }
+        for (int c = 0; c < PD; ++c) { u64 v = 0; for (int a = 0; a < 4; ++a) v = Fm::add(v, Fm::hmul(msg[a * PD + c], lag[a])); expected[c] = v; }
+    }
+    T.absorb_slice(s.e, (size_t)(1 + s.n_M) * s.n_mat * s.ncols); T.absorb_slice(s.b, s.n_vec);
+    auto eq_eval = [&](const std::vector<u64>& c) { u64 res = 1; for (int i = 0; i < nv; ++i) { const u64 xy = Fm::hmul(c[i], point[i]); res = Fm::hmul(res, Fm::add(Fm::sub(Fm::sub(Fm::add(xy, xy), c[i]), point[i]), 1)); } return res; };
+    u64 ver = 0;
+    for (int i = 0; i < s.n_mat; ++i) { u64 esum = 0, ap = 1; const u64 b2 = Fm::hmul(cba[i].beta, cba[i].beta);
+        for (int j = 0; j < s.ncols; ++j) { const u64* ej = s.e + ((size_t)i * s.ncols + j) * PD; const u64 e1 = ev_host(ej, cba[i].beta), e2 = ev_host(ej, b2);
+            esum = Fm::add(esum, Fm::hmul(Fm::sub(Fm::hmul(e1, e1), e2), ap)); ap = Fm::hmul(ap, cba[i].alpha); }
+        ver = Fm::add(ver, Fm::hmul(Fm::hmul(eq_eval(cba[i].c), esum), Fm::hpow(rc, i))); }
+    for (int i = 0; i < s.n_vec; ++i) { const Cba& x = cba[s.n_mat + i]; const u64* bi = s.b + (size_t)i * PD;
+        const u64 e1 = ev_host(bi, x.beta), e2 = ev_host(bi, Fm::hmul(x.beta, x.beta));
+        ver = Fm::add(ver, Fm::hmul(Fm::hmul(Fm::hmul(eq_eval(x.c), x.alpha), Fm::sub(Fm::hmul(e1, e1), e2)), Fm::hpow(rc, s.n_mat + i))); }
+    if (expected[0] != ver) throw LfException(LF_ERR_SUMCHECK_FAILED, "set check: recomputed claim mismatch (SetCheckError::ExpectedEvaluation)");
+    for (int c = 1; c < PD; ++c) if (expected[c]) throw LfException(LF_ERR_SUMCHECK_FAILED, "set check: recomputed claim mismatch (SetCheckError::ExpectedEvaluation)");
+    if (point_out) *point_out = point;
+}
+// ct(psi * a) with psi = sum_{0<i<d/2} i (X^-i + X^i): the constant coefficient of the negacyclic product
+// (psi_i = i, psi_{16-i} = -i, X^16 = -1  =>  ct = sum_i i (a_i - a_{16-i}))
+u64 ct_psi(const u64* a) { u64 acc = 0; for (int i = 1; i < PD / 2; ++i) acc = Fm::add(acc, Fm::hmul((u64)i, Fm::sub(a[i], a[PD - i]))); return acc; }
+}  // namespace
+
+extern "C" {
+
+void lf_transcript_get_challenge_base(lf_transcript* t, uint64_t* out1) { pguard(nullptr, [&] { *out1 = challenge(tr_of(t)); }); }
+
+lf_status lf_plus_set_check(lf_ctx* c, lf_transcript* t, int32_t nvars, const lf_plus_set* sets, int32_t n_sets, const lf_csr* M, int32_t n_M, uint64_t* out, uint64_t out_cap, uint64_t* out_len) {
+    return pguard(c, [&] {
+        need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (n_sets < 1 || !sets || n_M < 0 || (n_M && !M) || !out_len) throw LfException(LF_ERR_INVALID_ARG, "set check: null / empty arguments");
+        std::vector<DevSparse> store; store.reserve((size_t)n_sets + n_M); std::vector<DevSet> mats, vecs; std::vector<DevSparse> Ms; SetCheckResult R;
+        struct Cleanup { Eng& E; std::vector<DevSparse>& a; std::vector<DevSparse>& b; SetCheckResult& r; ~Cleanup() { for (auto& s : a) s.free(E); for (auto& s : b) s.free(E); r.free(E); } } cl{E, store, Ms, R};
+        for (int i = 0; i < n_sets; ++i) {
+            store.push_back(sets[i].kind == 0 ? upload_by_columns(E, sets[i].m) : upload_dense_vector(E, sets[i].v, sets[i].n));
+            DevSet s; s.gen = &store.back(); s.nrows = store.back().nrows; s.ncols = store.back().ncols; (sets[i].kind == 0 ? mats : vecs).push_back(s);
+        }
+        for (int i = 0; i < n_M; ++i) Ms.push_back(upload_by_columns(E, M[i]));
+        R = set_check_core(E, T, nvars, mats, vecs, Ms);
+        const std::vector<u64> w = R.words(); *out_len = w.size();
+        if (!out || out_cap < w.size()) throw LfException(LF_ERR_INVALID_ARG, "set check: output buffer too small");
+        std::memcpy(out, w.data(), w.size() * 8);
+    });
+}
+lf_status lf_plus_set_check_verify(lf_transcript* t, const uint64_t* words, uint64_t len) {
+    return pguard(nullptr, [&] { Tr& T = tr_of(t); verify_set_image(T, parse_set_image(words, len)); });
+}
+
+lf_status lf_plus_mat_create(lf_ctx* c, uint64_t kappa, uint64_t n, const uint64_t* host, lf_plus_mat** out) {
+    *out = nullptr;
+    return pguard(c, [&] { need_frog(c); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (!host || !kappa || !n) throw LfException(LF_ERR_INVALID_ARG, "matrix: null / empty"); check_canonical(host, kappa * n * PD, "matrix");
+        std::unique_ptr<lf_plus_mat> A(new lf_plus_mat); A->kappa = kappa; A->n = n; LF_CUDA(cudaMalloc(&A->d, kappa * n * PD * 8));
+        LF_CUDA(cudaMemcpyAsync(A->d, host, kappa * n * PD * 8, cudaMemcpyHostToDevice, E.st())); E.sync(); *out = A.release(); });
+}
+void lf_plus_mat_free(lf_ctx* c, lf_plus_mat* a) { if (a) { if (c) cudaStreamSynchronize(c->stream); cudaFree(a->d); delete a; } }
+
+lf_status lf_plus_rg_from_f(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, uint64_t n, uint64_t b, int32_t k, int32_t l, lf_plus_rg** out) {
+    *out = nullptr;
+    return pguard(c, [&] {
+        need_frog(c); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (!A || !f || n != A->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "from_f: witness length differs from the matrix width");
+        if (k < 1 || k > 16 || l < 1 || l > 64 || b < 2 || b > (1u << 20)) throw LfException(LF_ERR_INVALID_ARG, "from_f: decomposition parameters out of range");
+        check_canonical(f, n * PD, "from_f witness");
+        const size_t kappa = A->kappa, n_tau = kappa * (size_t)k * PD * l * PD;
+        if (n_tau >= n) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "from_f: n must exceed kappa * k * d * l * d (utils.rs:34-40)");
+        std::unique_ptr<lf_plus_rg> I(new lf_plus_rg); I->n = n; I->kappa = kappa; I->k = k; I->l = l; I->b = b; I->code_pitch = (n + 15) / 16 * 16;
+        struct Guard { lf_plus_rg* p; ~Guard() { if (p) { cudaFree(p->codes); cudaFree(p->mtau_codes); cudaFree(p->tau); cudaFree(p->f); } } } g{I.get()};
+        LF_CUDA(cudaMalloc(&I->f, n * PD * 8)); LF_CUDA(cudaMalloc(&I->codes, (size_t)k * PD * I->code_pitch)); LF_CUDA(cudaMalloc(&I->mtau_codes, I->code_pitch)); LF_CUDA(cudaMalloc(&I->tau, n));
+        LF_CUDA(cudaMemcpyAsync(I->f, f, n * PD * 8, cudaMemcpyHostToDevice, E.st()));
+        // D_f = decompose_to_vec(cf(f), b, k), M_f = exp(D_f) as exponent codes
+        E.launch("k_plus_digit_codes", [&] { k_plus_digit_codes<<<Eng::blocks_for(n * PD, 256), 256, 0, E.st()>>>(I->f, n, (long long)b, k, I->codes, I->code_pitch, c->d_err); });
+        E.check_err_flag(LF_ERR_DOES_NOT_FIT, "from_f: a coefficient of f does not fit k digits in base b inside (-d/2, d/2)");
+        // comM_f[kk] = A * M_f[kk]: rotations only.  com = hconcat: row r, column kk * d + c
+        I->comM.assign((size_t)k * kappa * PD * PD, 0); std::vector<u64> com(kappa * (size_t)k * PD * PD);
+        for (size_t r = 0; r < kappa; ++r) {
+            const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * k * PD * PD);
+            E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, (unsigned)(k * PD)), 256, 0, E.st()>>>(A->d + r * n * PD, I->codes, I->code_pitch, n, partial); });
+            finish_wsum(E, partial, ch, (size_t)k * PD, 0, com.data() + r * k * PD * PD);
+            for (int kk = 0; kk < k; ++kk) std::memcpy(&I->comM[(((size_t)kk * kappa + r) * PD) * PD], &com[(r * k + kk) * PD * PD], 8 * PD * PD);
+        }
+        // tau = split(com, n, d/2, l) (utils.rs:12-43): l balanced base-(d/2) digits of every coefficient, digit-major per entry; host work on kappa * k * d elements
+        I->tau_host.assign(n, 0); std::vector<signed char> tau8(n, 0); std::vector<unsigned char> mt(I->code_pitch, 0);      // exp(0) = X^0
+        int64_t dg[64];
+        for (size_t e = 0; e < kappa * (size_t)k * PD; ++e) for (int cf = 0; cf < PD; ++cf) {
+            const u64 v = com[e * PD + cf]; const bool neg = v > (Fm::P - 1) / 2; const u64 mag = neg ? Fm::P - v : v;
+            if (!balanced_digits(neg ? -(int64_t)mag : (int64_t)mag, PD / 2, l, dg)) throw LfException(LF_ERR_DOES_NOT_FIT, "split: l digits in base d/2 do not hold a commitment coefficient");
+            for (int i = 0; i < l; ++i) { const size_t pos = (e * l + i) * PD + cf; tau8[pos] = (signed char)dg[i]; I->tau_host[pos] = dg[i] < 0 ? Fm::P - (u64)(-dg[i]) : (u64)dg[i]; mt[pos] = (unsigned char)((dg[i] + PD) & (PD - 1)); }
+        }
+        LF_CUDA(cudaMemcpyAsync(I->tau, tau8.data(), n, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemcpyAsync(I->mtau_codes, mt.data(), I->code_pitch, cudaMemcpyHostToDevice, E.st()));
+        // cm_f = A f, C_Mf = A tau, cm_mtau = A m_tau (rgchk.rs:322-327)
+        I->fcoms.assign(3 * kappa * PD, 0); const SmallArgs sm = small_consts();
+        u64* cp = E.dalloc<u64>(2); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
+        for (size_t r = 0; r < kappa; ++r) { const u64* Ar = A->d + r * n * PD;
+            { const unsigned ch = chunks_for(n, 128); u64* partial = E.partial_dev((size_t)ch * PD);
+              E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(Ar, cp, nullptr, I->f, partial); }); finish_wsum(E, partial, ch, 1, 2, &I->fcoms[r * PD]); }
+            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+              E.launch("k_plus_wsum_ring_small", [&] { k_plus_wsum_ring_small<<<dim3(ch, 1), 256, 0, E.st()>>>(Ar, I->tau, n, sm, partial); }); finish_wsum(E, partial, ch, 1, 0, &I->fcoms[(kappa + r) * PD]); }
+            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+              E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, 1), 256, 0, E.st()>>>(Ar, I->mtau_codes, I->code_pitch, n, partial); }); finish_wsum(E, partial, ch, 1, 0, &I->fcoms[(2 * kappa + r) * PD]); }
+        }
+        E.sync(); E.dfree(cp);
+        g.p = nullptr; *out = I.release();
+    });
+}
+lf_status lf_plus_rg_read(const lf_plus_rg* I, uint64_t* tau, uint64_t* fcoms, uint64_t* comM) {
+    return pguard(nullptr, [&] { if (!I) throw LfException(LF_ERR_INVALID_ARG, "null instance");
+        if (tau) std::memcpy(tau, I->tau_host.data(), I->n * 8); if (fcoms) std::memcpy(fcoms, I->fcoms.data(), I->fcoms.size() * 8); if (comM) std::memcpy(comM, I->comM.data(), I->comM.size() * 8); });
+}
+void lf_plus_rg_free(lf_ctx* c, lf_plus_rg* I) { if (I) { if (c) cudaStreamSynchronize(c->stream); cudaFree(I->codes); cudaFree(I->mtau_codes); cudaFree(I->tau); cudaFree(I->f); delete I; } }
+
+lf_status lf_plus_range_check(lf_ctx* c, lf_transcript* t, int32_t nvars, lf_plus_rg* const* inst, int32_t L, const lf_csr* M, int32_t n_M, uint64_t* out, uint64_t out_cap, uint64_t* out_len) {
+    return pguard(c, [&] {
+        need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (L < 1 || !inst || n_M < 0 || (n_M && !M) || !out_len) throw LfException(LF_ERR_INVALID_ARG, "range check: null / empty arguments");
+        const lf_plus_rg& I0 = *inst[0];
+        for (int i = 0; i < L; ++i) if (!inst[i] || inst[i]->n != I0.n || inst[i]->k != I0.k || inst[i]->kappa != I0.kappa || inst[i]->l != I0.l || inst[i]->b != I0.b) throw LfException(LF_ERR_INVALID_ARG, "range check: instances of different shapes");
+        std::vector<DevSparse> Ms; SetCheckResult R;
+        struct Cleanup { Eng& E; std::vector<DevSparse>& a; SetCheckResult& r; ~Cleanup() { for (auto& s : a) s.free(E); r.free(E); } } cl{E, Ms, R};
+        for (int i = 0; i < n_M; ++i) Ms.push_back(upload_by_columns(E, M[i]));
+        // sets: the k matrices M_f of every instance, then every instance's m_tau (rgchk.rs:80-89)
+        std::vector<DevSet> mats, vecs;
+        for (int i = 0; i < L; ++i) for (int kk = 0; kk < I0.k; ++kk) { DevSet s; s.codes = inst[i]->codes + (size_t)kk * PD * inst[i]->code_pitch; s.code_pitch = inst[i]->code_pitch; s.nrows = I0.n; s.ncols = PD; mats.push_back(s); }
+        for (int i = 0; i < L; ++i) { DevSet s; s.codes = inst[i]->mtau_codes; s.code_pitch = inst[i]->code_pitch; s.nrows = I0.n; s.ncols = 1; vecs.push_back(s); }
+        R = set_check_core(E, T, nvars, mats, vecs, Ms);
+        // evaluations at r (rgchk.rs:101-171): v = c[0] = MLE(f)(r) coefficient-wise, a[0] = MLE(tau)(r), and through w_i = M_i^T eq(r, .) the M_i-images
+        const size_t nE = 1 + Ms.size(), n = I0.n; const SmallArgs sm = small_consts();
+        std::vector<u64> img = {(u64)L, (u64)I0.k, (u64)I0.l, (u64)I0.kappa, I0.b}; { auto w = R.words(); img.insert(img.end(), w.begin(), w.end()); }
+        u64* cp = E.dalloc<u64>(2); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
+        std::vector<std::vector<u64>> av(L), cv(L);
+        for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
+            std::vector<u64> v(PD), a(nE), b(nE * PD), cc(nE * PD), tmp(PD);
+            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+              E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, 1), 256, 0, E.st()>>>(R.d_eq_r, cp, nullptr, I.f, partial); }); finish_wsum(E, partial, ch, 1, 0, v.data()); }
+            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+              E.launch("k_plus_wsum_scalar_small", [&] { k_plus_wsum_scalar_small<<<dim3(ch, 1), 256, 0, E.st()>>>(R.d_eq_r, I.tau, n, sm, partial); }); finish_wsum(E, partial, ch, 1, 1, tmp.data()); a[0] = tmp[0]; }
+            std::memcpy(b.data(), R.b.data() + (size_t)li * PD, 8 * PD); std::memcpy(cc.data(), v.data(), 8 * PD);
+            for (size_t mi = 0; mi < Ms.size(); ++mi) { const u64* W = R.d_w[mi];
+                { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+                  E.launch("k_plus_wsum_ring_small", [&] { k_plus_wsum_ring_small<<<dim3(ch, 1), 256, 0, E.st()>>>(W, I.tau, n, sm, partial); }); finish_wsum(E, partial, ch, 1, 0, tmp.data()); a[1 + mi] = tmp[0]; }
+                { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+                  E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, 1), 256, 0, E.st()>>>(W, I.mtau_codes, I.code_pitch, n, partial); }); finish_wsum(E, partial, ch, 1, 0, &b[(1 + mi) * PD]); }
+                { const unsigned ch = chunks_for(n, 128); u64* partial = E.partial_dev((size_t)ch * PD);
+                  E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(W, cp, nullptr, I.f, partial); }); finish_wsum(E, partial, ch, 1, 2, &cc[(1 + mi) * PD]); }
+            }
+            for (auto* x : {&v, &a, &b, &cc, }) img.insert(img.end(), x->begin(), x->end());
+            img.insert(img.end(), I.fcoms.begin(), I.fcoms.end());
+            av[li] = a; cv[li] = cc;
+        }
+        E.dfree(cp);
+        for (int li = 0; li < L; ++li) { for (u64 a : av[li]) absorb_field(T, a); T.absorb_slice(cv[li].data(), nE); }      // rgchk.rs:338-343
+        *out_len = img.size();
+        if (!out || out_cap < img.size()) throw LfException(LF_ERR_INVALID_ARG, "range check: output buffer too small");
+        std::memcpy(out, img.data(), img.size() * 8);
+    });
+}
+lf_status lf_plus_range_check_verify(lf_transcript* t, const uint64_t* w, uint64_t len) {
+    return pguard(nullptr, [&] {
+        Tr& T = tr_of(t);
+        if (!w || len < 10) throw LfException(LF_ERR_INCORRECT_LENGTH, "range-check image too short");
+        const size_t L = w[0], k = w[1], kappa = w[3];
+        if (L < 1 || L > 64 || k < 1 || k > 16 || kappa < 1 || kappa > 4096) throw LfException(LF_ERR_INVALID_ARG, "range-check image: implausible header");
+        const SetImage s = parse_set_image(w + 5, len - 5);
+        const size_t nE = 1 + s.n_M, per = PD + nE + 2 * nE * PD + 3 * kappa * PD, off = 5 + s.words;
+        if (len < off + L * per) throw LfException(LF_ERR_INCORRECT_LENGTH, "range-check image truncated");
+        if ((size_t)s.n_mat != L * k || (size_t)s.n_vec != L || s.ncols != PD) throw LfException(LF_ERR_INVALID_ARG, "range-check image: set-check shape does not match L, k");
+        check_canonical(w + off, L * per, "range-check image");
+        verify_set_image(T, s);
+        for (size_t l = 0; l < L; ++l) { const u64* p = w + off + l * per; const u64 *a = p + PD, *c = a + nE + nE * PD; for (size_t i = 0; i < nE; ++i) absorb_field(T, a[i]); T.absorb_slice(c, nE); }
+        for (size_t l = 0; l < L; ++l) { const u64* p = w + off + l * per; const u64 *v = p, *a = p + PD, *b = a + nE, *c = b + nE * PD;
+            for (size_t i = 0; i < nE; ++i) if (ct_psi(b + i * PD) != a[i]) throw LfException(LF_ERR_RECOMPOSED, "range check: ct(psi b) != a (RangeCheckError::PsiCheckAB)");
+            for (size_t ni = 0; ni < nE; ++ni) for (int j = 0; j < PD; ++j) {
+                u64 uc[PD] = {0}; u64 dpw = 1;
+                for (size_t i = 0; i < k; ++i) { const u64* u = s.e + ((ni * s.n_mat + k * l + i) * s.ncols + j) * PD; for (int cf = 0; cf < PD; ++cf) uc[cf] = Fm::add(uc[cf], Fm::hmul(u[cf], dpw)); dpw = Fm::hmul(dpw, PD / 2); }
+                if (ct_psi(uc) != (ni == 0 ? v[j] : c[ni * PD + j])) throw LfException(LF_ERR_RECOMPOSED, "range check: ct(psi sum d'^i u_i) != v (RangeCheckError::PsiCheckVU)");
+            }
+        }
+    });
+}
+lf_status lf_plus_tensor(const uint64_t* r, int32_t n, uint64_t* out) {
+    return pguard(nullptr, [&] { if (!r || !out || n < 0 || n > 30) throw LfException(LF_ERR_INVALID_ARG, "tensor: bad arguments"); check_canonical(r, n, "tensor");
+        std::vector<u64> res(1, 1);
+        for (int i = 0; i < n; ++i) { std::vector<u64> nx; nx.reserve(res.size() * 2); for (u64 a : res) { nx.push_back(Fm::hmul(a, Fm::sub(1, r[i]))); nx.push_back(Fm::hmul(a, r[i])); } res.swap(nx); }
+        std::memcpy(out, res.data(), res.size() * 8); });
+}
+
+}  // extern "C"

@@ -1,0 +1,269 @@
+// LatticeFold+ consumers of the commitment / sumcheck path on the coefficient-form ring
+// R = Z_q[X]/(X^16 + 1) (`stark_rings::cyclotomic_ring::models::frog_ring::RqPoly`, BaseRing = Fq):
+//   monomial set check      crates/latticefold-plus/src/setchk.rs:59-262   (In::set_check)
+//   double commitment       crates/latticefold-plus/src/rgchk.rs:259-336   (RgInstance::from_f: decompose, exp, A * M_f, split, the three commitments)
+//   range check             crates/latticefold-plus/src/rgchk.rs:75-187    (Rg::range_check)
+//   transcript              crates/latticefold-plus/src/transcript.rs:16-56
+// The reference runs all of this on dense ring-valued MLEs (16 coefficients per entry) with ring products.  What the data IS:
+//   * every table of the set check's sumcheck holds constants of R (ev(entry, beta), its square, eq(c, .)), so the sumcheck runs on
+//     ONE base-field word per entry -- 1/16 of the reference's bytes and one field product where the reference does a ring product;
+//   * the matrices M_f and the vector m_tau hold monomials exp(a) = X^(a mod 16): ONE byte per entry (the exponent) instead of 128;
+//     a ring product with such an entry is a negacyclic rotation, so the double commitment A * M_f and the evaluations
+//     MLE(M * column)(r) need no multiplications at all;
+//   * MLE(M_i * v)(r) = sum_x (M_i^T eq(r, .))[x] * v[x]: one pass over M_i per point instead of one sparse mat-vec per column.
+// Field arithmetic is exact, so these regroupings give the reference's values bit for bit (tests/test_gpu_plus.py against oracle/lfplus.hpp).
+// Representation: device-resident sumcheck tables, weights and eq tables are in Montgomery form (Fm, R = 2^64); ring data that
+// crosses the boundary (A, f, M_i, results) is canonical.  mont x canonical products are canonical, mont x mont products Montgomery.
+#pragma once
+#include "engine.cuh"
+#include "transcript_host.hpp"
+
+namespace lf { namespace plus {
+
+constexpr int PD = 16;                 // ring dimension
+constexpr unsigned char CODE_ZERO = 0xFF;      // a zero entry of a monomial set (codes 0..15 are X^code)
+
+// 64-bit Montgomery arithmetic for the Frog prime (p > 2^63: the REDC sum can carry out of 64 bits)
+constexpr u64 inv_mod_2_64(u64 p) { u64 x = 1; for (int i = 0; i < 6; ++i) x *= 2 - p * x; return x; }      // p^-1 mod 2^64 (Newton, p odd)
+struct Fm {
+    static constexpr u64 P = FrogField::P;
+    static constexpr u64 NINV = ~inv_mod_2_64(FrogField::P) + 1;
+    static LF_HD u64 add(u64 a, u64 b) { u64 s = a + b; if (s < a || s >= P) s -= P; return s; }
+    static LF_HD u64 sub(u64 a, u64 b) { return a >= b ? a - b : a + (P - b); }
+    static LF_HD u64 neg(u64 a) { return a ? P - a : 0; }
+    static LF_HD u64 mul(u64 a, u64 b) {      // a b 2^-64 mod p
+        u64 lo, hi, mlo, mhi; mul_wide(a, b, lo, hi);
+        const u64 m = lo * NINV; mul_wide(m, P, mlo, mhi);      // lo + mlo = 0 mod 2^64: the carry is (lo != 0)
+        u64 t = hi + mhi; const bool c1 = t < hi; const u64 t2 = t + (lo != 0 ? 1 : 0); const bool c2 = t2 < t;
+        return (c1 || c2 || t2 >= P) ? t2 - P : t2;
+    }
+    // host-side conversions
+    static u64 r1() { return (u64)((((u128)1) << 64) % P); }
+    static u64 r2() { const u128 r = r1(); return (u64)(r * r % P); }
+    static u64 to_mont(u64 a) { return (u64)((u128)(a % P) * r1() % P); }
+    static u64 from_mont(u64 a) { return mul(a, 1); }
+    static u64 hmul(u64 a, u64 b) { return (u64)((u128)a * b % P); }      // canonical product on the host
+    static u64 hpow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = hmul(r, a); a = hmul(a, a); e >>= 1; } return r; }
+};
+
+// ---------------------------------------------------------------- kernels
+struct PowArgs { u64 v[PD]; };
+// tables of one monomial set held as exponent codes: T[2j][x] = beta^code, T[2j+1][x] = its square   (setchk.rs:100-113)
+__global__ void k_plus_tables_mono(const unsigned char* __restrict__ codes, size_t code_pitch, size_t nrows, u64* __restrict__ T, size_t stride, PowArgs bpow /* beta^e R */) {
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const int j = blockIdx.y;
+    if (x >= nrows) return;
+    const unsigned char c = codes[(size_t)j * code_pitch + x];
+    u64 m = 0;
+#pragma unroll
+    for (int e = 0; e < PD; ++e) if (c == e) m = bpow.v[e];
+    T[(size_t)(2 * j) * stride + x] = m; T[(size_t)(2 * j + 1) * stride + x] = Fm::mul(m, m);
+}
+// the same for a set given as general sparse entries (possibly not monomials): m = sum_i coef_i beta^i
+__global__ void k_plus_tables_general(const u32* __restrict__ ecol, const u32* __restrict__ erow, const u64* __restrict__ val, size_t nnz, u64* __restrict__ T, size_t stride, PowArgs bpow2 /* beta^i R^2 */) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    u64 m = 0;
+#pragma unroll
+    for (int i = 0; i < PD; ++i) m = Fm::add(m, Fm::mul(val[e * PD + i], bpow2.v[i]));
+    const size_t j = ecol[e], x = erow[e];
+    T[(2 * j) * stride + x] = m; T[(2 * j + 1) * stride + x] = Fm::mul(m, m);
+}
+struct EqArgs { u64 c[40], omc[40]; int nv; };      // Montgomery c_i and 1 - c_i
+__global__ void k_plus_eq(u64* __restrict__ out, size_t n, EqArgs a, u64 one /* R */) {      // eq(x, c), c[0] on bit 0 (sumcheck/utils.rs:100-170)
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    u64 v = one;
+    for (int i = 0; i < a.nv; ++i) v = Fm::mul(v, ((x >> i) & 1) ? a.c[i] : a.omc[i]);
+    out[x] = v;
+}
+struct Group { int base, ncols, wofs, pad; };      // tables base .. base + 2 ncols (m_j, m'_j pairs, then eq); weights w[wofs + j] = alpha^j rc^i
+// one round of the set check's sumcheck (comb of setchk.rs:157-189, degree 3): h(X) = sum_g eq_g(X) sum_j w_gj (m_gj(X)^2 - m'_gj(X))
+__global__ void __launch_bounds__(256) k_plus_round(const u64* __restrict__ T, size_t stride, size_t n_pairs, const Group* __restrict__ groups, int n_groups,
+                                                     const u64* __restrict__ w, u64* __restrict__ partial) {
+    u64 acc[4] = {0, 0, 0, 0};
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_pairs; b += (size_t)gridDim.x * blockDim.x) {
+        for (int g = 0; g < n_groups; ++g) {
+            const Group G = groups[g];
+            u64 s[4] = {0, 0, 0, 0};
+            for (int j = 0; j < G.ncols; ++j) {
+                const ulonglong2 m = *reinterpret_cast<const ulonglong2*>(T + (size_t)(G.base + 2 * j) * stride + 2 * b);
+                const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(T + (size_t)(G.base + 2 * j + 1) * stride + 2 * b);
+                const u64 wj = w[G.wofs + j], dm = Fm::sub(m.y, m.x), dq = Fm::sub(q.y, q.x);
+                u64 mx = m.x, qx = q.x;
+#pragma unroll
+                for (int X = 0; X < 4; ++X) {
+                    s[X] = Fm::add(s[X], Fm::mul(wj, Fm::sub(Fm::mul(mx, mx), qx)));
+                    mx = Fm::add(mx, dm); qx = Fm::add(qx, dq);
+                }
+            }
+            const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(T + (size_t)(G.base + 2 * G.ncols) * stride + 2 * b);
+            const u64 de = Fm::sub(e.y, e.x); u64 ex = e.x;
+#pragma unroll
+            for (int X = 0; X < 4; ++X) { acc[X] = Fm::add(acc[X], Fm::mul(ex, s[X])); ex = Fm::add(ex, de); }
+        }
+    }
+    __shared__ u64 sh[8][4];
+#pragma unroll
+    for (int X = 0; X < 4; ++X) {
+        u64 v = acc[X];
+        for (int o = 16; o; o >>= 1) v = Fm::add(v, __shfl_down_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][X] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) { u64 v = 0; for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v = Fm::add(v, sh[wv][threadIdx.x]); partial[(size_t)blockIdx.x * 4 + threadIdx.x] = v; }
+}
+// fix_variables for every table at once: out[t][b] = in[t][2b] + r (in[t][2b+1] - in[t][2b])
+__global__ void k_plus_fold(const u64* __restrict__ in, size_t in_stride, u64* __restrict__ out, size_t n_out, u64 r) {
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const size_t t = blockIdx.y;
+    if (b >= n_out) return;
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(in + t * in_stride + 2 * b);
+    out[t * n_out + b] = Fm::add(v.x, Fm::mul(r, Fm::sub(v.y, v.x)));
+}
+
+// ---- weighted sums  out[col] = sum_x W[x] (*) entry(x, col)  with block partials  partial[chunk][col][16]
+template <class Body> __device__ __forceinline__ void wsum_finish(u64 (&acc)[PD], u64* __restrict__ partial, int ncols) {
+    __shared__ u64 sh[8][PD];
+#pragma unroll
+    for (int c = 0; c < PD; ++c) {
+        u64 v = acc[c];
+        for (int o = 16; o; o >>= 1) v = Fm::add(v, __shfl_down_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < PD) { u64 v = 0; for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v = Fm::add(v, sh[wv][threadIdx.x]); partial[((size_t)blockIdx.x * ncols + blockIdx.y) * PD + threadIdx.x] = v; }
+}
+// scalar weights (eq(r, .), Montgomery), monomial entries: coefficient `code` of the result collects the weights      setchk.rs:199-214, 251-257
+__global__ void __launch_bounds__(256) k_plus_wsum_scalar_mono(const u64* __restrict__ W, const unsigned char* __restrict__ codes, size_t code_pitch, size_t nrows, u64* __restrict__ partial) {
+    u64 acc[PD];
+#pragma unroll
+    for (int c = 0; c < PD; ++c) acc[c] = 0;
+    const unsigned char* col = codes + (size_t)blockIdx.y * code_pitch;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < nrows; x += (size_t)gridDim.x * blockDim.x) {
+        const unsigned char cd = col[x]; const u64 wv = W[x];
+#pragma unroll
+        for (int c = 0; c < PD; ++c) acc[c] = Fm::add(acc[c], cd == c ? wv : 0);
+    }
+    wsum_finish<void>(acc, partial, gridDim.y);
+}
+// scalar weights, general entries grouped by column (col_ptr / row / val); row == nullptr: a dense vector, entry e sits in row e
+__global__ void __launch_bounds__(256) k_plus_wsum_scalar_general(const u64* __restrict__ W, const u64* __restrict__ col_ptr, const u32* __restrict__ erow, const u64* __restrict__ val, u64* __restrict__ partial) {
+    u64 acc[PD];
+#pragma unroll
+    for (int c = 0; c < PD; ++c) acc[c] = 0;
+    const size_t e0 = col_ptr[blockIdx.y], e1 = col_ptr[blockIdx.y + 1];
+    for (size_t e = e0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += (size_t)gridDim.x * blockDim.x) {
+        const u64 wv = W[erow ? erow[e] : e - e0];
+#pragma unroll
+        for (int c = 0; c < PD; ++c) acc[c] = Fm::add(acc[c], Fm::mul(wv, val[e * PD + c]));
+    }
+    wsum_finish<void>(acc, partial, gridDim.y);
+}
+// ring-valued weights W[x] (16 words each), monomial entries: W[x] X^code is a negacyclic rotation                  rgchk.rs:297-304 (A * M_f), setchk.rs:217-240
+__global__ void __launch_bounds__(256) k_plus_wsum_ring_mono(const u64* __restrict__ W, const unsigned char* __restrict__ codes, size_t code_pitch, size_t nrows, u64* __restrict__ partial) {
+    u64 acc[PD];
+#pragma unroll
+    for (int c = 0; c < PD; ++c) acc[c] = 0;
+    const unsigned char* col = codes + (size_t)blockIdx.y * code_pitch;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < nrows; x += (size_t)gridDim.x * blockDim.x) {
+        const unsigned cd = col[x];
+        if (cd >= PD) continue;
+        const u64* wx = W + x * PD;
+#pragma unroll
+        for (int o = 0; o < PD; ++o) {      // coefficient o of W X^cd: +W[o - cd] for o >= cd, -W[o - cd + 16] below (X^16 = -1)
+            const u64 v = wx[(o - cd) & (PD - 1)];
+            acc[o] = (unsigned)o >= cd ? Fm::add(acc[o], v) : Fm::sub(acc[o], v);
+        }
+    }
+    wsum_finish<void>(acc, partial, gridDim.y);
+}
+// ring-valued weights, general entries: negacyclic products (both operands canonical: the sum comes out times 2^-64)   rgchk.rs:322 (A f), 167-172 (M f)
+__global__ void __launch_bounds__(128) k_plus_wsum_ring_general(const u64* __restrict__ W, const u64* __restrict__ col_ptr, const u32* __restrict__ erow, const u64* __restrict__ val, u64* __restrict__ partial) {
+    u64 acc[PD];
+#pragma unroll
+    for (int c = 0; c < PD; ++c) acc[c] = 0;
+    const size_t e0 = col_ptr[blockIdx.y], e1 = col_ptr[blockIdx.y + 1];
+    for (size_t e = e0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += (size_t)gridDim.x * blockDim.x) {
+        const u64* wx = W + (size_t)(erow ? erow[e] : e - e0) * PD;
+        u64 v[PD];
+#pragma unroll
+        for (int j = 0; j < PD; ++j) v[j] = val[e * PD + j];
+#pragma unroll 1
+        for (int i = 0; i < PD; ++i) {      // acc += W_i (X^i v); X^i v is kept in registers by rotating v one step per iteration (X^16 = -1)
+            const u64 wi = wx[i];
+            if (wi) {
+#pragma unroll
+                for (int j = 0; j < PD; ++j) acc[j] = Fm::add(acc[j], Fm::mul(wi, v[j]));
+            }
+            const u64 top = v[PD - 1];
+#pragma unroll
+            for (int j = PD - 1; j > 0; --j) v[j] = v[j - 1];
+            v[0] = Fm::neg(top);
+        }
+    }
+    wsum_finish<void>(acc, partial, gridDim.y);
+}
+// ring-valued weights, small signed scalar entries (tau, |tau| < 8) given as Montgomery constants by value: W[x] * tau[x]   rgchk.rs:323-325 (A tau), 146-156
+struct SmallArgs { u64 v[16]; };      // Montgomery form of -8 .. 7 at index (t & 15)
+__global__ void __launch_bounds__(256) k_plus_wsum_ring_small(const u64* __restrict__ W, const signed char* __restrict__ tau, size_t nrows, SmallArgs sm, u64* __restrict__ partial) {
+    u64 acc[PD];
+#pragma unroll
+    for (int c = 0; c < PD; ++c) acc[c] = 0;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < nrows; x += (size_t)gridDim.x * blockDim.x) {
+        const int t = tau[x];
+        if (!t) continue;
+        u64 s = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if ((t & 15) == k) s = sm.v[k];
+        const u64* wx = W + x * PD;
+#pragma unroll
+        for (int c = 0; c < PD; ++c) acc[c] = Fm::add(acc[c], Fm::mul(s, wx[c]));
+    }
+    wsum_finish<void>(acc, partial, gridDim.y);
+}
+// scalar weights, small scalar entries: sum_x W[x] tau[x] (coefficient 0 of the partial; Montgomery)                 rgchk.rs:131-135
+__global__ void __launch_bounds__(256) k_plus_wsum_scalar_small(const u64* __restrict__ W, const signed char* __restrict__ tau, size_t nrows, SmallArgs sm, u64* __restrict__ partial) {
+    u64 acc[PD];
+#pragma unroll
+    for (int c = 0; c < PD; ++c) acc[c] = 0;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < nrows; x += (size_t)gridDim.x * blockDim.x) {
+        const int t = tau[x];
+        if (!t) continue;
+        u64 s = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if ((t & 15) == k) s = sm.v[k];
+        acc[0] = Fm::add(acc[0], Fm::mul(s, W[x]));
+    }
+    wsum_finish<void>(acc, partial, gridDim.y);
+}
+// w = M^T eq(r, .) for a sparse matrix of ring elements held by columns: thread x sums its column                      setchk.rs:217-240 regrouped
+__global__ void k_plus_mt_eq(const u64* __restrict__ eq, const u64* __restrict__ col_ptr, const u32* __restrict__ erow, const u64* __restrict__ val, size_t ncols, u64* __restrict__ w) {
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= ncols) return;
+    u64 acc[PD];
+#pragma unroll
+    for (int c = 0; c < PD; ++c) acc[c] = 0;
+    for (size_t e = col_ptr[x]; e < col_ptr[x + 1]; ++e) {
+        const u64 q = eq[erow[e]];
+#pragma unroll
+        for (int c = 0; c < PD; ++c) acc[c] = Fm::add(acc[c], Fm::mul(q, val[e * PD + c]));
+    }
+#pragma unroll
+    for (int c = 0; c < PD; ++c) w[x * PD + c] = acc[c];
+}
+// cf(f) -> k balanced base-b digits per coefficient -> exponent codes of M_f = exp(D_f): codes[kk][coefficient][x]       rgchk.rs:262-295
+__global__ void k_plus_digit_codes(const u64* __restrict__ f, size_t n, long long b, int k, unsigned char* __restrict__ codes, size_t code_pitch, int* __restrict__ err) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * PD) return;
+    const size_t x = i / PD; const int c = (int)(i % PD);
+    const u64 v = f[i];
+    const bool negv = v > (Fm::P - 1) / 2; const u64 mag = negv ? Fm::P - v : v;
+    if (mag >> 62) { atomicExch(err, 1); return; }
+    int64_t dg[16];
+    if (!balanced_digits(negv ? -(int64_t)mag : (int64_t)mag, b, k, dg)) { atomicExch(err, 1); return; }
+    for (int kk = 0; kk < k; ++kk) {
+        if (dg[kk] <= -(PD / 2) || dg[kk] >= PD / 2) { atomicExch(err, 1); return; }      // exp is defined on (-d/2, d/2)
+        codes[((size_t)kk * PD + c) * code_pitch + x] = (unsigned char)((dg[kk] + PD) & (PD - 1));
+    }
+}
+
+} }  // namespace lf::plus

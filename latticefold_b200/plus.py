@@ -1,0 +1,177 @@
+"""Host-side mirror of the LatticeFold+ operators built on the same kernels (crates/latticefold-plus), over the C ABI.
+
+Names follow the reference: `In.set_check` / `Out.verify` (setchk.rs), `RgInstance.from_f`, `Rg.range_check`, `Dcom.verify`
+(rgchk.rs), `tensor` (utils.rs), `PoseidonTranscript` (transcript.rs).  The ring is the Frog ring in coefficient form
+(`frog_ring::RqPoly`): elements are arrays of 16 canonical uint64 coefficients.  Proof objects are the flat uint64 images
+documented in include/lf_b200.h.  No CPU fallback: the provers need the CUDA library and a device; the verifiers are host code."""
+import ctypes as C
+
+import numpy as np
+
+from . import synth
+from .api import Csr, LfError, Transcript, lib, ptr, u64p, vp
+
+RING = synth.RING_FROG
+D = 16
+SYMBOLS = """lf_transcript_get_challenge_base lf_plus_set_check lf_plus_set_check_verify lf_plus_mat_create lf_plus_mat_free
+lf_plus_rg_from_f lf_plus_rg_read lf_plus_rg_free lf_plus_range_check lf_plus_range_check_verify lf_plus_tensor""".split()
+
+
+class PlusSet(C.Structure):      # lf_plus_set
+    _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("m", Csr), ("v", u64p), ("n", C.c_uint64)]
+
+
+_ready = False
+
+
+def _L():
+    global _ready
+    L = lib()
+    if not _ready:
+        L.lf_transcript_get_challenge_base.argtypes = [vp, u64p]
+        L.lf_plus_set_check.argtypes = [vp, vp, C.c_int32, C.POINTER(PlusSet), C.c_int32, C.POINTER(Csr), C.c_int32, u64p, C.c_uint64, u64p]
+        L.lf_plus_set_check_verify.argtypes = [vp, u64p, C.c_uint64]
+        L.lf_plus_mat_create.argtypes = [vp, C.c_uint64, C.c_uint64, u64p, C.POINTER(vp)]
+        L.lf_plus_mat_free.argtypes = [vp, vp]
+        L.lf_plus_rg_from_f.argtypes = [vp, vp, u64p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(vp)]
+        L.lf_plus_rg_read.argtypes = [vp, u64p, u64p, u64p]
+        L.lf_plus_rg_free.argtypes = [vp, vp]
+        L.lf_plus_range_check.argtypes = [vp, vp, C.c_int32, C.POINTER(vp), C.c_int32, C.POINTER(Csr), C.c_int32, u64p, C.c_uint64, u64p]
+        L.lf_plus_range_check_verify.argtypes = [vp, u64p, C.c_uint64]
+        L.lf_plus_tensor.argtypes = [u64p, C.c_int32, u64p]
+        _ready = True
+    return L
+
+
+class PoseidonTranscript(Transcript):
+    """latticefold-plus/src/transcript.rs: the same sponge; a challenge is one base-field element."""
+
+    def __init__(self, handle=None):
+        super().__init__(RING, handle)
+        _L()
+
+    def get_challenge(self):
+        o = np.empty(1, dtype=np.uint64); self.L.lf_transcript_get_challenge_base(self.h, ptr(o)); return int(o[0])
+
+
+def _csr_array(mats):
+    arr = (Csr * max(len(mats), 1))()
+    for j, M in enumerate(mats):
+        arr[j].nrows, arr[j].ncols = M["nrows"], M["ncols"]
+        arr[j].row_ptr, arr[j].col, arr[j].val = ptr(M["row_ptr"]), ptr(M["col"]), ptr(M["val"])
+    return arr
+
+
+def _grow(ctx, call):
+    cap = 1 << 16
+    while True:
+        out, n = np.zeros(cap, dtype=np.uint64), C.c_uint64(0)
+        rc = call(ptr(out), cap, C.byref(n))
+        if rc == 0:
+            return out[: n.value].copy()
+        if n.value > cap:
+            cap = int(n.value); continue
+        ctx.check(rc)
+
+
+class In:
+    """setchk.rs:23-27: `sets` is a list of ("matrix", csr dict) / ("vector", n x 16 array)."""
+
+    def __init__(self, ctx, nvars, sets):
+        self.ctx, self.nvars, self.sets = ctx, nvars, sets
+
+    def set_check(self, M, transcript):      # setchk.rs:59-262 -> the `Out` image
+        L = _L()
+        arr = (PlusSet * max(len(self.sets), 1))()
+        keep = []
+        for i, (kind, x) in enumerate(self.sets):
+            if kind == "matrix":
+                arr[i].kind = 0
+                arr[i].m.nrows, arr[i].m.ncols = x["nrows"], x["ncols"]
+                arr[i].m.row_ptr, arr[i].m.col, arr[i].m.val = ptr(x["row_ptr"]), ptr(x["col"]), ptr(x["val"])
+            else:
+                x = np.ascontiguousarray(x, dtype=np.uint64); keep.append(x)
+                arr[i].kind, arr[i].v, arr[i].n = 1, ptr(x), x.shape[0]
+        ma = _csr_array(list(M))
+        return _grow(self.ctx, lambda o, cap, n: L.lf_plus_set_check(self.ctx.h, transcript.h, self.nvars, arr, len(self.sets), ma, len(M), o, cap, n))
+
+
+def set_check_verify(words, transcript):      # Out::verify, setchk.rs:264-344: True = Ok(())
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    rc = _L().lf_plus_set_check_verify(transcript.h, ptr(words), words.size)
+    if rc in (0, -10):
+        return rc == 0
+    raise LfError(rc, "set-check image rejected as malformed")
+
+
+class Matrix:
+    """Matrix<R> kappa x n in coefficient form, device resident (the `A` of RgInstance::from_f)."""
+
+    def __init__(self, ctx, A):
+        A = np.ascontiguousarray(A, dtype=np.uint64)
+        self.ctx, self.kappa, self.n, self.h = ctx, A.shape[0], A.shape[1], vp()
+        ctx.check(_L().lf_plus_mat_create(ctx.h, self.kappa, self.n, ptr(A), C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                _L().lf_plus_mat_free(self.ctx.h, self.h)
+        except Exception:
+            pass
+
+
+class RgInstance:
+    """rgchk.rs:41-48; `from_f` (rgchk.rs:259-336) runs the double commitment on the device."""
+
+    def __init__(self, ctx, handle, n, kappa, k):
+        self.ctx, self.h, self.n, self.kappa, self.k = ctx, handle, n, kappa, k
+
+    @classmethod
+    def from_f(cls, ctx, f, A, b, k, l):
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        h = vp()
+        ctx.check(_L().lf_plus_rg_from_f(ctx.h, A.h, ptr(f), f.shape[0], b, k, l, C.byref(h)))
+        return cls(ctx, h, f.shape[0], A.kappa, k)
+
+    def read(self):
+        """(tau[n], fcoms[3, kappa, 16] = cm_f / C_Mf / cm_mtau, comM_f[k, kappa, 16, 16])"""
+        tau, fc, cm = np.zeros(self.n, dtype=np.uint64), np.zeros((3, self.kappa, D), dtype=np.uint64), np.zeros((self.k, self.kappa, D, D), dtype=np.uint64)
+        self.ctx.check(_L().lf_plus_rg_read(self.h, ptr(tau), ptr(fc), ptr(cm)))
+        return tau, fc, cm
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                _L().lf_plus_rg_free(self.ctx.h, self.h)
+        except Exception:
+            pass
+
+
+class Rg:
+    """rgchk.rs:34-39"""
+
+    def __init__(self, ctx, nvars, instances):
+        self.ctx, self.nvars, self.instances = ctx, nvars, instances
+
+    def range_check(self, M, transcript):      # rgchk.rs:75-187 -> the `Dcom` image
+        L = _L()
+        hs = (vp * len(self.instances))(*[i.h for i in self.instances])
+        ma = _csr_array(list(M))
+        return _grow(self.ctx, lambda o, cap, n: L.lf_plus_range_check(self.ctx.h, transcript.h, self.nvars, hs, len(self.instances), ma, len(M), o, cap, n))
+
+
+def range_check_verify(words, transcript):      # Dcom::verify, rgchk.rs:190-246
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    rc = _L().lf_plus_range_check_verify(transcript.h, ptr(words), words.size)
+    if rc in (0, -10, -11):
+        return rc == 0
+    raise LfError(rc, "range-check image rejected as malformed")
+
+
+def tensor(r):      # utils.rs:74-86
+    r = np.ascontiguousarray(r, dtype=np.uint64)
+    out = np.zeros(1 << r.size, dtype=np.uint64)
+    rc = _L().lf_plus_tensor(ptr(r), r.size, ptr(out))
+    if rc:
+        raise LfError(rc, "tensor")
+    return out

@@ -1,0 +1,113 @@
+"""GPU parity tests of the LatticeFold+ consumers (latticefold_b200/csrc/lfplus.cu) against the CPU oracle (oracle/lfplus.hpp):
+bit-exact proof images on the reference's own test cases (setchk.rs:358-495, rgchk.rs:344-433) and on seeded ones, both verifiers on
+both provers' outputs, and size-independent properties at the reference's benchmark sizes (benches/utils/mod.rs)."""
+import numpy as np
+import pytest
+
+import latticefold_b200 as lf
+from latticefold_b200 import plus
+from tests import plus_cases as pc
+
+pytestmark = pytest.mark.gpu
+RING = pc.RING_FROG
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = lf.Context(RING)
+    yield c
+    c.close()
+
+
+def seeded(seed=None):
+    t = plus.PoseidonTranscript()
+    if seed is not None:
+        t.absorb_base(np.asarray(seed, dtype=np.uint64))
+    return t
+
+
+@pytest.mark.parametrize("name", sorted(pc.set_check_cases()))
+def test_set_check_bit_exact(ctx, oracle, name):
+    nvars, sets, M, accept = pc.set_check_cases()[name]
+    for seed in (None, [3, 1, 4]):
+        got = plus.In(ctx, nvars, sets).set_check(M, seeded(seed))
+        want = oracle.plus_set_check(RING, nvars, sets, M, seed=seed)
+        assert got.shape == want.shape and np.array_equal(got, want)
+        assert plus.set_check_verify(got, seeded(seed)) is accept
+        assert oracle.plus_set_check_verify(RING, got, seed=seed) is accept
+
+
+def test_set_check_prover_leaves_transcript_in_verifier_state(ctx):
+    nvars, sets, M, _ = pc.set_check_cases()["rect_with_M"]
+    tp, tv = seeded(), seeded()
+    out = plus.In(ctx, nvars, sets).set_check(M, tp)
+    assert plus.set_check_verify(out, tv)
+    assert tp.get_challenge() == tv.get_challenge()
+
+
+def test_set_check_rejects_bad_shapes(ctx):
+    nvars, sets, M, _ = pc.set_check_cases()["rect_2sets"]
+    with pytest.raises(lf.LfError):
+        plus.In(ctx, 5, sets).set_check(M, seeded())      # 64 rows do not fit 2^5
+    with pytest.raises(lf.LfError):
+        plus.In(ctx, nvars, [sets[2]]).set_check(M, seeded())      # no matrix set (setchk.rs:85 panics)
+    with pytest.raises(lf.LfError):
+        plus.In(ctx, nvars, sets).set_check([pc.identity(32)], seeded())      # M of another width
+
+
+@pytest.mark.parametrize("n,kappa,k,L,with_M", [(1 << 14, 1, 2, 1, False), (1 << 14, 1, 2, 1, True), (1 << 15, 2, 2, 2, True), (1 << 15, 1, 3, 1, False)])
+def test_from_f_and_range_check_bit_exact(ctx, oracle, n, kappa, k, L, with_M):
+    l, nvars = pc.frog_l(), n.bit_length() - 1
+    fs, A = pc.range_check_inputs(n, kappa, seed=n + kappa + k, L=L, k=k)
+    if L == 1 and k == 2 and not with_M:
+        fs = pc.reference_range_check_f(n)      # the reference's own witness
+    M = [pc.random_ring_sparse(n, n, 2, 77, constant=True)] if with_M else []
+    Ad = plus.Matrix(ctx, A)
+    inst = [plus.RgInstance.from_f(ctx, fs[i], Ad, 8, k, l) for i in range(L)]
+    for i in range(L):
+        tau, fc, cm = inst[i].read()
+        otau, ofc, ocm = oracle.plus_rg_from_f(RING, fs[i], A, 8, k, l)
+        assert np.array_equal(cm, ocm) and np.array_equal(tau, otau) and np.array_equal(fc, ofc)
+    got = plus.Rg(ctx, nvars, inst).range_check(M, seeded([2, 7]))
+    want = oracle.plus_range_check(RING, nvars, fs, A, 8, k, l, M, seed=[2, 7])
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert plus.range_check_verify(got, seeded([2, 7])) and oracle.plus_range_check_verify(RING, got, seed=[2, 7])
+    assert not plus.range_check_verify(got, seeded())
+
+
+def test_from_f_errors(ctx):
+    n, kappa = 1 << 14, 1
+    fs, A = pc.range_check_inputs(n, kappa, seed=1)
+    Ad = plus.Matrix(ctx, A)
+    big = fs[0].copy(); big[5, 3] = 1000      # needs more than two base-8 digits
+    with pytest.raises(lf.LfError) as e:
+        plus.RgInstance.from_f(ctx, big, Ad, 8, 2, pc.frog_l())
+    assert e.value.code == -9
+    with pytest.raises(lf.LfError):
+        plus.RgInstance.from_f(ctx, fs[0][: n // 2], Ad, 8, 2, pc.frog_l())      # wrong witness length
+    fs2, A2 = pc.range_check_inputs(1 << 12, 1, seed=2)
+    with pytest.raises(lf.LfError):
+        plus.RgInstance.from_f(ctx, fs2[0], plus.Matrix(ctx, A2), 8, 2, pc.frog_l())      # n below the length of tau (utils.rs:34-40)
+    nc = fs[0].copy(); nc[0, 0] = np.uint64(pc.P_FROG)
+    with pytest.raises(lf.LfError):
+        plus.RgInstance.from_f(ctx, nc, Ad, 8, 2, pc.frog_l())
+
+
+def test_range_check_at_benchmark_size(ctx):
+    """benches/utils/mod.rs range_check::WITNESS_SCALING (n, k, kappa) = (2^17, 2, 2): too slow for the oracle; checked by
+    acceptance, by linearity of the commitments and by the recomposition identity of tau."""
+    n, kappa, k, l = 1 << 17, 2, 2, pc.frog_l()
+    fs, A = pc.range_check_inputs(n, kappa, seed=99, L=1)
+    Ad = plus.Matrix(ctx, A)
+    inst = plus.RgInstance.from_f(ctx, fs[0], Ad, 8, k, l)
+    tau, fc, cm = inst.read()
+    st = np.array([int(t) - pc.P_FROG if int(t) > pc.P_FROG // 2 else int(t) for t in tau[: kappa * k * 16 * l * 16]], dtype=object).reshape(kappa * k * 16, l, 16)
+    rec = [sum(int(st[0, i, c]) * 8 ** i for i in range(l)) % pc.P_FROG for c in range(16)]
+    assert rec == [int(x) for x in cm[0, 0, 0]]
+    f2 = fs[0].copy(); f2[:, :] = 0
+    z = plus.RgInstance.from_f(ctx, f2, Ad, 8, k, l).read()[1]
+    assert not z[0].any()      # cm_f of the zero witness
+    dcom = plus.Rg(ctx, 17, [inst]).range_check([], seeded())
+    assert plus.range_check_verify(dcom, seeded())
+    t = dcom.copy(); t[40] = (int(t[40]) + 1) % pc.P_FROG
+    assert not plus.range_check_verify(t, seeded())

@@ -1,0 +1,73 @@
+"""CPU tests of the product's LatticeFold+ host code: the verifiers (host code, as in the reference) accept the oracle's proofs
+of the reference's own test cases and reject the non-monomial / tampered ones; transcript and tensor agree with the oracle;
+the provers fail loudly without a device."""
+import numpy as np
+import pytest
+
+from latticefold_b200 import plus
+from tests import plus_cases as pc
+
+RING = pc.RING_FROG
+
+
+def seeded(seed):
+    t = plus.PoseidonTranscript()
+    if seed is not None:
+        t.absorb_base(np.asarray(seed, dtype=np.uint64))
+    return t
+
+
+@pytest.mark.parametrize("name", sorted(pc.set_check_cases()))
+def test_product_verifier_on_oracle_set_checks(oracle, name):
+    nvars, sets, M, accept = pc.set_check_cases()[name]
+    out = oracle.plus_set_check(RING, nvars, sets, M)
+    assert plus.set_check_verify(out, seeded(None)) is accept
+    assert oracle.plus_set_check_verify(RING, out) is accept
+    if accept:
+        for pos in (5 + nvars + 3, 5 + nvars + nvars * 64 + 1):
+            t = out.copy(); t[pos] = (int(t[pos]) + 1) % pc.P_FROG
+            assert not plus.set_check_verify(t, seeded(None))
+        assert not plus.set_check_verify(out, seeded([1, 2, 3]))
+        t = out.copy(); t[7] = np.uint64(pc.P_FROG)      # non-canonical limb
+        with pytest.raises(plus.LfError):
+            plus.set_check_verify(t, seeded(None))
+        with pytest.raises(plus.LfError):
+            plus.set_check_verify(out[:-1], seeded(None))
+
+
+def test_product_verifier_on_oracle_range_check(oracle):
+    n, kappa, k, l = 1 << 14, 1, 2, pc.frog_l()
+    f = pc.reference_range_check_f(n)
+    _, A = pc.range_check_inputs(n, kappa, seed=5)
+    m = pc.identity(n); m["val"] = m["val"].copy(); m["val"][0, 0] = 2
+    for M in ([], [m]):
+        dcom = oracle.plus_range_check(RING, 14, f, A, 8, k, l, M, seed=[4, 5])
+        assert plus.range_check_verify(dcom, seeded([4, 5]))
+        assert not plus.range_check_verify(dcom, seeded(None))
+        h = [int(x) for x in dcom[5:10]]
+        v0 = 10 + h[0] + h[0] * 64 + (1 + h[4]) * h[1] * h[2] * 16 + h[3] * 16
+        t = dcom.copy(); t[v0] = (int(t[v0]) + 1) % pc.P_FROG
+        assert not plus.range_check_verify(t, seeded([4, 5]))
+        a0 = v0 + 16      # a[0]: breaks ct(psi b) = a
+        t = dcom.copy(); t[a0] = (int(t[a0]) + 1) % pc.P_FROG
+        assert not plus.range_check_verify(t, seeded([4, 5]))
+
+
+def test_transcript_and_tensor_match_oracle(oracle):
+    t = seeded([9, 8, 7])
+    els = np.arange(48, dtype=np.uint64).reshape(3, 16)
+    t.absorb(els)
+    c = [t.get_challenge() for _ in range(25)]      # crosses a rate boundary
+    # the oracle's set check draws its first challenges the same way: compare through a set check of a fixed case instead of a raw API
+    r = [3, 5, 11]
+    assert np.array_equal(plus.tensor(r), oracle.plus_tensor(RING, r))
+    assert len(set(c)) == 25 and all(0 <= x < pc.P_FROG for x in c)
+
+
+def test_provers_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    import latticefold_b200 as lf
+    with pytest.raises(lf.LfError):
+        lf.Context(RING)
