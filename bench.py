@@ -7,6 +7,7 @@
                                                            un-vendored dependency and cannot be built in this image)
   python bench.py --config c3 [--log-w 20]                 BASELINE configs[2]: BabyBear ring, degree-three CCS, one GPU
   python bench.py --config ntt [--gpus N]                  BASELINE configs[4]: negacyclic NTT sweep (GB/s per size, JSON line)
+  python bench.py --config plus [--log-w 17]               LatticeFold+ range check at the reference's benchmark rows
 
 A step = one NIFSProver::prove (linearization + 2 decompositions + folding; crates/latticefold/benches/utils.rs:619-680)
 on the configuration BASELINE.json quotes the metric on (configs[1]: Goldilocks ring, 2^16-constraint R1CS, 1 GPU).
@@ -184,7 +185,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "ntt"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "ntt", "plus"])
     ap.add_argument("--log-w", type=int, default=None, dest="log_w")
     ap.add_argument("--cpu-sample-log-w", type=int, default=None, dest="cpu_sample_log_w", help="reference arm: prove a smaller slice instead of the full W")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, dest="cpu_budget_s")
@@ -193,11 +194,14 @@ def main():
     ap.add_argument("--full-step", action="store_true", dest="full_step", help="--config c3: time a whole NIFSProver::prove step instead of commit + linearization")
     args = ap.parse_args()
     if args.log_w is None:
-        args.log_w = {"c2": 16, "c3": 20, "ntt": 0}[args.config]
+        args.log_w = {"c2": 16, "c3": 20, "ntt": 0, "plus": 17}[args.config]
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.config == "ntt":
         from tools import ntt_bench
         return ntt_bench.main(args, rank, world, local)
+    if args.config == "plus":
+        from tools import plus_bench
+        return plus_bench.main(args, rank, world, local)
     if args.config == "c3" and not args.full_step:
         return run_c3(args, rank, world, local)
     if args.impl == "reference":

@@ -4,6 +4,8 @@
 #include "lfplus.cuh"
 #include <algorithm>
 #include <numeric>
+#include <chrono>
+#include <cstdio>
 
 using namespace lf;
 using namespace lf::plus;
@@ -164,7 +166,7 @@ SetCheckResult set_check_core(Eng& E, Tr& T, int nvars, const std::vector<DevSet
             E.launch("k_plus_fold", [&] { k_plus_fold<<<dim3(Eng::blocks_for(n_out, 256), (unsigned)n_tables), 256, 0, E.st()>>>(cur, len, nxt, n_out, rm); });
             std::swap(cur, nxt); len = n_out;
         }
-        const size_t n_pairs = len / 2; const unsigned nblk = chunks_for(n_pairs, 256);
+        const size_t n_pairs = len / 2; const unsigned nblk = (unsigned)std::min<size_t>(std::max<size_t>((n_pairs + 255) / 256, 1), 148 * 16);      // one pair per thread up to 2^19 pairs: the per-pair chain is long, occupancy hides it
         u64* partial = E.partial_dev((size_t)nblk * 4); u64* d_out = E.small_dev(4);
         E.launch("k_plus_round", [&] { k_plus_round<<<nblk, 256, 0, E.st()>>>(cur, len, n_pairs, d_groups, n_active, d_w, partial); });
         E.reduce_partials(partial, (int)nblk, 4, d_out);
@@ -279,18 +281,26 @@ lf_status lf_plus_rg_from_f(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, 
     *out = nullptr;
     return pguard(c, [&] {
         need_frog(c); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        const bool tm = std::getenv("LF_PLUS_TIMING") != nullptr; auto t_last = std::chrono::steady_clock::now();      // diagnostic: phase times on stderr
+        auto mark = [&](const char* what) { if (!tm) return; E.sync(); auto now = std::chrono::steady_clock::now(); std::fprintf(stderr, "from_f %-16s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count()); t_last = now; };
         if (!A || !f || n != A->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "from_f: witness length differs from the matrix width");
         if (k < 1 || k > 16 || l < 1 || l > 64 || b < 2 || b > (1u << 20)) throw LfException(LF_ERR_INVALID_ARG, "from_f: decomposition parameters out of range");
-        check_canonical(f, n * PD, "from_f witness");
         const size_t kappa = A->kappa, n_tau = kappa * (size_t)k * PD * l * PD;
         if (n_tau >= n) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "from_f: n must exceed kappa * k * d * l * d (utils.rs:34-40)");
         std::unique_ptr<lf_plus_rg> I(new lf_plus_rg); I->n = n; I->kappa = kappa; I->k = k; I->l = l; I->b = b; I->code_pitch = (n + 15) / 16 * 16;
-        struct Guard { lf_plus_rg* p; ~Guard() { if (p) { cudaFree(p->codes); cudaFree(p->mtau_codes); cudaFree(p->tau); cudaFree(p->f); } } } g{I.get()};
-        LF_CUDA(cudaMalloc(&I->f, n * PD * 8)); LF_CUDA(cudaMalloc(&I->codes, (size_t)k * PD * I->code_pitch)); LF_CUDA(cudaMalloc(&I->mtau_codes, I->code_pitch)); LF_CUDA(cudaMalloc(&I->tau, n));
+        // instance buffers come from the context's block cache: a steady stream of from_f / free pairs performs no cudaMalloc
+        struct Guard { Eng& E; lf_plus_rg* p; ~Guard() { if (p) { E.dfree(p->codes); E.dfree(p->mtau_codes); E.dfree(p->tau); E.dfree(p->f); } } } g{E, I.get()};
+        I->f = E.dalloc<u64>(n * PD); I->codes = E.dalloc<unsigned char>((size_t)k * PD * I->code_pitch); I->mtau_codes = E.dalloc<unsigned char>(I->code_pitch); I->tau = E.dalloc<signed char>(n);
+        mark("validate+alloc");
         LF_CUDA(cudaMemcpyAsync(I->f, f, n * PD * 8, cudaMemcpyHostToDevice, E.st()));
+        mark("h2d");
         // D_f = decompose_to_vec(cf(f), b, k), M_f = exp(D_f) as exponent codes
         E.launch("k_plus_digit_codes", [&] { k_plus_digit_codes<<<Eng::blocks_for(n * PD, 256), 256, 0, E.st()>>>(I->f, n, (long long)b, k, I->codes, I->code_pitch, c->d_err); });
-        E.check_err_flag(LF_ERR_DOES_NOT_FIT, "from_f: a coefficient of f does not fit k digits in base b inside (-d/2, d/2)");
+        { int h = 0; LF_CUDA(cudaMemcpyAsync(&h, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, E.st())); E.sync();      // (the kernel also validates f: every word is read there anyway)
+          if (h) { LF_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), E.st()));
+                   if (h == 3) throw LfException(LF_ERR_INVALID_ARG, "from_f witness: non-canonical field element");
+                   throw LfException(LF_ERR_DOES_NOT_FIT, "from_f: a coefficient of f does not fit k digits in base b inside (-d/2, d/2)"); } }
+        mark("digits");
         // comM_f[kk] = A * M_f[kk]: rotations only.  com = hconcat: row r, column kk * d + c
         I->comM.assign((size_t)k * kappa * PD * PD, 0); std::vector<u64> com(kappa * (size_t)k * PD * PD);
         for (size_t r = 0; r < kappa; ++r) {
@@ -299,6 +309,7 @@ lf_status lf_plus_rg_from_f(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, 
             finish_wsum(E, partial, ch, (size_t)k * PD, 0, com.data() + r * k * PD * PD);
             for (int kk = 0; kk < k; ++kk) std::memcpy(&I->comM[(((size_t)kk * kappa + r) * PD) * PD], &com[(r * k + kk) * PD * PD], 8 * PD * PD);
         }
+        mark("A*M_f");
         // tau = split(com, n, d/2, l) (utils.rs:12-43): l balanced base-(d/2) digits of every coefficient, digit-major per entry; host work on kappa * k * d elements
         I->tau_host.assign(n, 0); std::vector<signed char> tau8(n, 0); std::vector<unsigned char> mt(I->code_pitch, 0);      // exp(0) = X^0
         int64_t dg[64];
@@ -308,6 +319,7 @@ lf_status lf_plus_rg_from_f(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, 
             for (int i = 0; i < l; ++i) { const size_t pos = (e * l + i) * PD + cf; tau8[pos] = (signed char)dg[i]; I->tau_host[pos] = dg[i] < 0 ? Fm::P - (u64)(-dg[i]) : (u64)dg[i]; mt[pos] = (unsigned char)((dg[i] + PD) & (PD - 1)); }
         }
         LF_CUDA(cudaMemcpyAsync(I->tau, tau8.data(), n, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemcpyAsync(I->mtau_codes, mt.data(), I->code_pitch, cudaMemcpyHostToDevice, E.st()));
+        mark("split");
         // cm_f = A f, C_Mf = A tau, cm_mtau = A m_tau (rgchk.rs:322-327)
         I->fcoms.assign(3 * kappa * PD, 0); const SmallArgs sm = small_consts();
         u64* cp = E.dalloc<u64>(2); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
@@ -320,6 +332,7 @@ lf_status lf_plus_rg_from_f(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, 
               E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, 1), 256, 0, E.st()>>>(Ar, I->mtau_codes, I->code_pitch, n, partial); }); finish_wsum(E, partial, ch, 1, 0, &I->fcoms[(2 * kappa + r) * PD]); }
         }
         E.sync(); E.dfree(cp);
+        mark("commitments");
         g.p = nullptr; *out = I.release();
     });
 }
@@ -327,7 +340,7 @@ lf_status lf_plus_rg_read(const lf_plus_rg* I, uint64_t* tau, uint64_t* fcoms, u
     return pguard(nullptr, [&] { if (!I) throw LfException(LF_ERR_INVALID_ARG, "null instance");
         if (tau) std::memcpy(tau, I->tau_host.data(), I->n * 8); if (fcoms) std::memcpy(fcoms, I->fcoms.data(), I->fcoms.size() * 8); if (comM) std::memcpy(comM, I->comM.data(), I->comM.size() * 8); });
 }
-void lf_plus_rg_free(lf_ctx* c, lf_plus_rg* I) { if (I) { if (c) cudaStreamSynchronize(c->stream); cudaFree(I->codes); cudaFree(I->mtau_codes); cudaFree(I->tau); cudaFree(I->f); delete I; } }
+void lf_plus_rg_free(lf_ctx* c, lf_plus_rg* I) { if (I && c) { Eng E(c); E.dfree(I->codes); E.dfree(I->mtau_codes); E.dfree(I->tau); E.dfree(I->f); delete I; } }      // stream order protects pending readers of the re-issued blocks
 
 lf_status lf_plus_range_check(lf_ctx* c, lf_transcript* t, int32_t nvars, lf_plus_rg* const* inst, int32_t L, const lf_csr* M, int32_t n_M, uint64_t* out, uint64_t out_cap, uint64_t* out_len) {
     return pguard(c, [&] {

@@ -256,6 +256,7 @@ __global__ void k_plus_digit_codes(const u64* __restrict__ f, size_t n, long lon
     if (i >= n * PD) return;
     const size_t x = i / PD; const int c = (int)(i % PD);
     const u64 v = f[i];
+    if (v >= Fm::P) { atomicExch(err, 3); return; }      // non-canonical input
     const bool negv = v > (Fm::P - 1) / 2; const u64 mag = negv ? Fm::P - v : v;
     if (mag >> 62) { atomicExch(err, 1); return; }
     int64_t dg[16];
