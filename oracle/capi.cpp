@@ -299,4 +299,33 @@ int lfo_plus_range_check_verify(int id, const u64* words, size_t len, const u64*
 int lfo_plus_tensor(int id, const u64* r, int n, u64* out) { return guard([&] { auto t = plus::tensor(ring(id), r, n); memcpy(out, t.data(), 8 * t.size()); }); }
 int lfo_plus_ring_mul(int id, const u64* a, const u64* b, u64* out) { return guard([&] { plus::r_mul(ring(id), out, a, b); }); }
 
+
+// Cm{rg}.prove(M, transcript) (cm.rs:57-203) on instances built by from_f: returns the CmProof image; comx (ComX image) and g (L x n x d) optional
+long lfo_plus_cm_prove(int id, int nvars, int L, const u64* f, size_t n, const u64* A, size_t kappa, u64 b, int k, int l, const lfo_csr* M, int n_M,
+                       const u64* seed, size_t n_seed, u64* out, size_t cap, u64* comx, size_t comx_cap, u64* g) {
+    long nw = -1; int rc = guard([&] { const RingParams& R = ring(id); const size_t d = R.d; plus::DecompParameters dp{b, k, l};
+        std::vector<plus::RgInstance> inst; for (int i = 0; i < L; ++i) inst.push_back(plus::rg_from_f(R, Vec(f + (size_t)i * n * d, f + (size_t)(i + 1) * n * d), Vec(A, A + kappa * n * d), kappa, dp));
+        std::vector<plus::SparseR> Ms; for (int i = 0; i < n_M; ++i) Ms.push_back(sparse_of(R, M[i]));
+        auto T = plus_transcript(R, seed, n_seed); plus::Com com; plus::CmProof P;
+        plus::cm_prove(R, nvars, inst, dp, Ms, T, com, P);
+        auto w = plus::cm_proof_words(R, P); nw = (long)w.size(); if (w.size() <= cap) memcpy(out, w.data(), 8 * w.size());
+        if (comx) { auto x = plus::comx_words(com.x); if (x.size() > comx_cap) throw std::runtime_error("ComX buffer too small"); memcpy(comx, x.data(), 8 * x.size()); }
+        if (g) memcpy(g, com.g.data(), 8 * com.g.size()); });
+    return rc ? rc : nw;
+}
+// CmProof::verify(M, transcript): 1 accept (comx filled when not NULL), 0 reject
+int lfo_plus_cm_verify(int id, const u64* words, size_t len, const lfo_csr* M, int n_M, const u64* seed, size_t n_seed, u64* comx, size_t comx_cap) {
+    int ok = 0; int rc = guard([&] { const RingParams& R = ring(id); plus::CmProof P; plus::cm_proof_parse(R, words, len, P);
+        std::vector<plus::SparseR> Ms; for (int i = 0; i < n_M; ++i) Ms.push_back(sparse_of(R, M[i]));
+        auto T = plus_transcript(R, seed, n_seed); plus::ComX X; ok = plus::cm_verify(R, P, Ms, T, X) ? 1 : 0;
+        if (ok && comx) { auto x = plus::comx_words(X); if (x.size() > comx_cap) throw std::runtime_error("ComX buffer too small"); memcpy(comx, x.data(), 8 * x.size()); } });
+    return rc ? rc : ok;
+}
+
+
+// Matrix::try_mul_vec on the coefficient ring: out[kappa x d] = A[kappa x n] * x[n]
+int lfo_plus_mat_vec(int id, const u64* A, size_t kappa, size_t n, const u64* x, u64* out) {
+    return guard([&] { const RingParams& R = ring(id); auto y = plus::mat_mul_vec(R, Vec(A, A + kappa * n * R.d), kappa, n, Vec(x, x + n * R.d)); memcpy(out, y.data(), 8 * y.size()); });
+}
+
 }  // extern "C"

@@ -424,4 +424,171 @@ inline void dcom_parse(const RingParams& R, const u64* w, size_t len, Dcom& D, s
         D.evals.push_back(std::move(E)); D.fcoms.push_back(std::move(C)); }
 }
 
+// ---------------------------------------------------------------- commitment transformation (cm.rs)
+// utils.rs:88-103 short_challenge(lambda = 128): u = 2^(lambda / d) = 256, coefficient = (byte mod u) - u/2 from squeeze_bytes(d)
+inline void short_challenge128(const RingParams& R, PlusTranscript& T, u64* out) {
+    const int d = R.d; const unsigned u = 1u << (128 / d); std::vector<uint8_t> bs(d); T.sp.squeeze_bytes(bs.data(), d);
+    for (int i = 0; i < d; ++i) out[i] = R.F.from_i128((i128)(bs[i] % u) - (i128)(u / 2));
+}
+inline int ceil_log2(size_t x) { int l = 0; while (((size_t)1 << l) < x) ++l; return l; }      // ark_std::log2
+// t(z) = tensor(c) (x) s' (x) (1, d', .., d'^(l-1)) (x) (1, X, .., X^(d-1))   (cm.rs:590-601), ring elements
+inline std::vector<u64> calculate_t_z(const RingParams& R, const std::vector<u64>& c, const std::vector<u64>& s_prime_flat /* kd x d */, int l) {
+    const int d = R.d; const size_t kd = s_prime_flat.size() / d; std::vector<u64> tc = tensor(R, c.data(), (int)c.size());
+    std::vector<u64> out; out.reserve(tc.size() * kd * l * d * d); u64 e[64], xb[64], t[64];
+    for (u64 tci : tc) for (size_t j = 0; j < kd; ++j) for (int a = 0; a < l; ++a) for (int b = 0; b < d; ++b) {
+        r_scale(R, e, s_prime_flat.data() + j * d, tci);                              // tensor(c)_i * s'_j
+        r_scale(R, e, e, R.F.pow((u64)(d / 2), a));                                   // * d'^a
+        memset(xb, 0, 8 * d); xb[b] = 1; r_mul(R, t, e, xb);                          // * X^b
+        out.insert(out.end(), t, t + d);
+    }
+    return out;
+}
+struct CmProof { Dcom dcom; std::vector<u64> comh /* L x kappa x d */; PProof pf[2]; std::vector<u64> evals[2] /* L x (1+n_M) x 4 x d */; size_t kappa = 0; };
+struct ComX { std::vector<u64> cm_g /* L x kappa x d */, ro /* nvars x 2 */, vo /* L x (1+n_M) x 2 x d */; };
+struct Com { std::vector<u64> g /* L x n x d */; ComX x; };
+
+inline ComX cm_x(const RingParams& R, const CmProof& P, const u64* s /* 3 x d */, const std::vector<u64>& ro_a, const std::vector<u64>& ro_b) {      // cm.rs:537-575
+    const int d = R.d; const size_t L = P.dcom.fcoms.size(), kappa = P.kappa, nE = 1 + P.dcom.out.n_M; ComX X; u64 t[64], acc[64];
+    for (size_t l = 0; l < L; ++l) for (size_t i = 0; i < kappa; ++i) { const FComs& C = P.dcom.fcoms[l];
+        r_mul(R, acc, s, C.C_Mf.data() + i * d); r_mul(R, t, s + d, C.cm_mtau.data() + i * d); el_add(R, acc, acc, t);
+        r_mul(R, t, s + 2 * d, C.cm_f.data() + i * d); el_add(R, acc, acc, t); el_add(R, acc, acc, P.comh.data() + (l * kappa + i) * d);
+        X.cm_g.insert(X.cm_g.end(), acc, acc + d); }
+    for (size_t i = 0; i < ro_a.size(); ++i) { X.ro.push_back(ro_a[i]); X.ro.push_back(ro_b[i]); }
+    for (size_t l = 0; l < L; ++l) for (size_t i = 0; i < nE; ++i) for (int z = 0; z < 2; ++z) { const u64* e = P.evals[z].data() + ((l * nE + i) * 4) * d;
+        r_mul(R, acc, s, e); r_mul(R, t, s + d, e + d); el_add(R, acc, acc, t); r_mul(R, t, s + 2 * d, e + 2 * d); el_add(R, acc, acc, t); el_add(R, acc, acc, e + 3 * d);
+        X.vo.insert(X.vo.end(), acc, acc + d); }
+    return X;
+}
+// Cm::sumchecker (cm.rs:205-342)
+inline void cm_sumchecker(const RingParams& R, int nvars, const std::vector<RgInstance>& inst, const Dcom& dcom, const std::vector<std::vector<u64>>& h,
+                          const std::vector<u64>& t0, const std::vector<u64>& t1, const std::vector<SparseR>& M, PlusTranscript& T, PProof& pf, std::vector<u64>& evals, std::vector<u64>& ro) {
+    const int d = R.d; const Fp& F = R.F; const size_t L = inst.size(), Mlen = M.size();
+    const u64 rc = T.get_challenge();
+    std::vector<PMle> mles;
+    auto push = [&](std::vector<u64> ev) { PMle m; m.nv = nvars; m.ev = std::move(ev); mles.push_back(std::move(m)); };
+    { std::vector<u64> eq = eq_table_base(R, dcom.out.r.data(), nvars), e(eq.size() * d, 0); for (size_t i = 0; i < eq.size(); ++i) e[i * d] = eq[i]; push(std::move(e)); }
+    for (size_t i = 0; i < L; ++i) { const RgInstance& I = inst[i];
+        std::vector<u64> rtau(I.n * d, 0); for (size_t x = 0; x < I.n; ++x) rtau[x * d] = I.tau[x];
+        push(rtau); push(I.m_tau); push(I.f); push(h[i]);
+        for (auto& m : M) { push(sp_mul_vec(R, m, rtau)); push(sp_mul_vec(R, m, I.m_tau)); push(sp_mul_vec(R, m, I.f)); push(sp_mul_vec(R, m, h[i])); } }
+    push(t0); push(t1);
+    std::vector<u64> rcps; u64 rcp = 1;
+    for (size_t i = 0; i < L * (4 + 4 * Mlen); ++i) { rcps.push_back(rcp); rcp = F.mul(rcp, rc); }
+    rcps.push_back(rcp); rcp = F.mul(rcp, rc); rcps.push_back(rcp);
+    const size_t nvals = mles.size();
+    CombFn comb = [&](const u64* vals, u64* out) {      // cm.rs:285-307
+        u64 tot[64], in[64], t[64]; memset(tot, 0, 8 * d);
+        for (size_t l = 0; l < L; ++l) { const size_t l_idx = 1 + l * (4 + 4 * Mlen); memset(in, 0, 8 * d);
+            for (size_t q = 0; q < 4 + 4 * Mlen; ++q) { r_scale(R, t, vals + (l_idx + q) * d, rcps[l_idx + q - 1]); el_add(R, in, in, t); }
+            r_mul(R, t, vals, in); el_add(R, tot, tot, t);
+            r_mul(R, t, vals + l_idx * d, vals + (nvals - 2) * d); r_scale(R, t, t, rcps[nvals - 3]); el_add(R, tot, tot, t);
+            r_mul(R, t, vals + l_idx * d, vals + (nvals - 1) * d); r_scale(R, t, t, rcps[nvals - 2]); el_add(R, tot, tot, t); }
+        memcpy(out, tot, 8 * d);
+    };
+    pf = p_prove(R, T, mles, nvars, 2, comb, ro);
+    evals.assign(L * (1 + Mlen) * 4 * d, 0);
+    for (size_t l = 0; l < L; ++l) for (size_t i = 0; i <= Mlen; ++i) for (int q = 0; q < 4; ++q)
+        pm_evaluate(R, mles[1 + l * (4 + 4 * Mlen) + 4 * i + q], ro.data(), nvars, evals.data() + ((l * (1 + Mlen) + i) * 4 + q) * d);
+    T.absorb_slice(evals.data(), evals.size() / d);      // absorb_evaluations, cm.rs:581-588
+}
+// Cm::prove (cm.rs:57-203)
+inline void cm_prove(const RingParams& R, int nvars, const std::vector<RgInstance>& inst, const DecompParameters& dp, const std::vector<SparseR>& M, PlusTranscript& T, Com& com, CmProof& P) {
+    const int d = R.d, k = dp.k; const size_t L = inst.size(), n = inst[0].tau.size(), kappa = inst[0].kappa, N = (size_t)1 << nvars;
+    P.kappa = kappa; P.dcom = range_check(R, nvars, inst, dp, M, T);
+    std::vector<u64> s(3 * d), sp((size_t)k * d * d);
+    for (int i = 0; i < 3; ++i) short_challenge128(R, T, s.data() + i * d);
+    for (int i = 0; i < k * d; ++i) short_challenge128(R, T, sp.data() + (size_t)i * d);
+    std::vector<std::vector<u64>> h(L, std::vector<u64>(N * d, 0)); u64 t[64];
+    for (size_t l = 0; l < L; ++l)
+        #pragma omp parallel for schedule(static) private(t)
+        for (long x = 0; x < (long)n; ++x) for (int kk = 0; kk < k; ++kk) for (int c = 0; c < d; ++c) {
+            r_mul(R, t, inst[l].M_f[kk].data() + ((size_t)x * d + c) * d, sp.data() + ((size_t)kk * d + c) * d); el_add(R, h[l].data() + (size_t)x * d, h[l].data() + (size_t)x * d, t); }
+    P.comh.assign(L * kappa * d, 0);
+    for (size_t l = 0; l < L; ++l) for (int kk = 0; kk < k; ++kk) for (size_t r = 0; r < kappa; ++r) for (int c = 0; c < d; ++c) {
+        r_mul(R, t, inst[l].comM_f[kk].data() + (r * d + c) * d, sp.data() + ((size_t)kk * d + c) * d); el_add(R, P.comh.data() + (l * kappa + r) * d, P.comh.data() + (l * kappa + r) * d, t); }
+    T.absorb_slice(P.comh.data(), L * kappa);
+    const int log_kappa = ceil_log2(kappa);
+    std::vector<u64> c0 = T.get_challenges(log_kappa), c1 = T.get_challenges(log_kappa);
+    std::vector<u64> t0 = calculate_t_z(R, c0, sp, dp.l), t1 = calculate_t_z(R, c1, sp, dp.l);
+    if (t0.size() > n * d) throw std::runtime_error("t0 too large!");
+    t0.resize(n * d, 0); t1.resize(n * d, 0);
+    std::vector<u64> ro_a, ro_b;
+    cm_sumchecker(R, nvars, inst, P.dcom, h, t0, t1, M, T, P.pf[0], P.evals[0], ro_a);
+    cm_sumchecker(R, nvars, inst, P.dcom, h, t0, t1, M, T, P.pf[1], P.evals[1], ro_b);
+    com.g.assign(L * n * d, 0);
+    for (size_t l = 0; l < L; ++l)
+        #pragma omp parallel for schedule(static)
+        for (long x = 0; x < (long)n; ++x) { u64 a[64], u[64], cst[64]; const RgInstance& I = inst[l];
+            r_const(R, cst, I.tau[x]); r_mul(R, a, s.data(), cst); r_mul(R, u, s.data() + d, I.m_tau.data() + (size_t)x * d); el_add(R, a, a, u);
+            r_mul(R, u, s.data() + 2 * d, I.f.data() + (size_t)x * d); el_add(R, a, a, u); el_add(R, a, a, h[l].data() + (size_t)x * d);
+            memcpy(com.g.data() + (l * n + x) * d, a, 8 * d); }
+    com.x = cm_x(R, P, s.data(), ro_a, ro_b);
+}
+// CmProof::verify (cm.rs:349-535): returns false where the reference returns Err / panics on a failed check
+inline bool cm_verify(const RingParams& R, const CmProof& P, const std::vector<SparseR>& M, PlusTranscript& T, ComX& out) {
+    const int d = R.d, k = P.dcom.dp.k, nvars = P.dcom.out.nvars; const Fp& F = R.F; const size_t L = P.dcom.evals.size(), kappa = P.kappa, Mlen = M.size(), nE = 1 + Mlen;
+    if ((size_t)P.dcom.out.n_M != Mlen) return false;
+    if (!range_check_verify(R, P.dcom, T)) return false;
+    std::vector<u64> s(3 * d), sp((size_t)k * d * d);
+    for (int i = 0; i < 3; ++i) short_challenge128(R, T, s.data() + i * d);
+    for (int i = 0; i < k * d; ++i) short_challenge128(R, T, sp.data() + (size_t)i * d);
+    T.absorb_slice(P.comh.data(), L * kappa);
+    const int log_kappa = ceil_log2(kappa);
+    std::vector<u64> c0 = T.get_challenges(log_kappa), c1 = T.get_challenges(log_kappa);
+    u64 t[64];
+    std::vector<u64> u(L * nE * d, 0);      // u[l][ni] = sum over the k sets of instance l and their d columns of e * s'
+    for (size_t l = 0; l < L; ++l) for (size_t ni = 0; ni < nE; ++ni) for (int q = 0; q < k * d; ++q) {
+        const u64* e = P.dcom.out.e.data() + ((ni * P.dcom.out.n_mat + l * k) * (size_t)P.dcom.out.ncols + q) * d;
+        r_mul(R, t, e, sp.data() + (size_t)q * d); el_add(R, u.data() + (l * nE + ni) * d, u.data() + (l * nE + ni) * d, t); }
+    std::vector<u64> tc0 = tensor(R, c0.data(), log_kappa), tc1 = tensor(R, c1.data(), log_kappa), tcch0(L * d, 0), tcch1(L * d, 0);
+    for (size_t l = 0; l < L; ++l) for (size_t i = 0; i < std::min(tc0.size(), kappa); ++i) {
+        r_scale(R, t, P.comh.data() + (l * kappa + i) * d, tc0[i]); el_add(R, tcch0.data() + l * d, tcch0.data() + l * d, t);
+        r_scale(R, t, P.comh.data() + (l * kappa + i) * d, tc1[i]); el_add(R, tcch1.data() + l * d, tcch1.data() + l * d, t); }
+    std::vector<u64> ro[2];
+    for (int z = 0; z < 2; ++z) {
+        const u64 rc = T.get_challenge(); const size_t z_idx = L * (4 + 4 * Mlen);
+        std::vector<u64> claimed(d, 0);
+        auto add_scaled = [&](std::vector<u64>& acc, const u64* e, u64 c) { r_scale(R, t, e, c); el_add(R, acc.data(), acc.data(), t); };
+        for (size_t l = 0; l < L; ++l) { const DcomEvals& E = P.dcom.evals[l]; const size_t l_idx = l * (4 + 4 * Mlen); u64 cst[64];
+            for (size_t i = 0; i < nE; ++i) { const size_t idx = l_idx + 4 * i;
+                r_const(R, cst, E.a[i]); add_scaled(claimed, cst, F.pow(rc, idx)); add_scaled(claimed, E.b.data() + i * d, F.pow(rc, idx + 1));
+                add_scaled(claimed, E.c.data() + i * d, F.pow(rc, idx + 2)); add_scaled(claimed, u.data() + (l * nE + i) * d, F.pow(rc, idx + 3)); }
+            add_scaled(claimed, tcch0.data() + l * d, F.pow(rc, z_idx)); add_scaled(claimed, tcch1.data() + l * d, F.pow(rc, z_idx + 1)); }
+        PSubClaim sc = p_verify(R, T, nvars, 2, claimed.data(), P.pf[z]);
+        if (!sc.ok) return false;
+        ro[z] = sc.point;
+        u64 t0_ro[64], t1_ro[64];
+        { PMle m; m.nv = nvars; m.ev = calculate_t_z(R, c0, sp, P.dcom.dp.l); if (m.ev.size() > ((size_t)d << nvars)) return false; pm_evaluate(R, std::move(m), ro[z].data(), nvars, t0_ro); }
+        { PMle m; m.nv = nvars; m.ev = calculate_t_z(R, c1, sp, P.dcom.dp.l); pm_evaluate(R, std::move(m), ro[z].data(), nvars, t1_ro); }
+        if (P.evals[z].size() != L * nE * 4 * d) return false;
+        T.absorb_slice(P.evals[z].data(), P.evals[z].size() / d);
+        const u64 eq = eq_eval_base(R, P.dcom.out.r.data(), ro[z].data(), nvars);
+        std::vector<u64> ev(d, 0);
+        for (size_t l = 0; l < L; ++l) { const size_t l_idx = l * (4 + 4 * Mlen); std::vector<u64> in(d, 0); const u64* el = P.evals[z].data() + (l * nE * 4) * d;
+            for (size_t q = 0; q < 4 * nE; ++q) add_scaled(in, el + q * d, F.pow(rc, l_idx + q));
+            add_scaled(ev, in.data(), eq);
+            u64 pr[64]; r_mul(R, pr, t0_ro, el); add_scaled(ev, pr, F.pow(rc, z_idx)); r_mul(R, pr, t1_ro, el); add_scaled(ev, pr, F.pow(rc, z_idx + 1)); }
+        if (memcmp(ev.data(), sc.expected.data(), 8 * d) != 0) return false;      // assert_eq!(expected_eval, eval)
+    }
+    out = cm_x(R, P, s.data(), ro[0], ro[1]);
+    return true;
+}
+// CmProof image: the Dcom image, comh[L x kappa x d], two sumcheck proofs [nvars x 3 x d], two evaluation blocks [L x (1+n_M) x 4 x d]
+inline std::vector<u64> cm_proof_words(const RingParams& R, const CmProof& P) {
+    std::vector<u64> w = dcom_words(R, P.dcom, P.kappa);
+    for (auto* v : {&P.comh, &P.pf[0].msgs, &P.pf[1].msgs, &P.evals[0], &P.evals[1]}) w.insert(w.end(), v->begin(), v->end());
+    return w;
+}
+inline void cm_proof_parse(const RingParams& R, const u64* w, size_t len, CmProof& P) {
+    const size_t d = R.d; dcom_parse(R, w, len, P.dcom, P.kappa);
+    const size_t L = P.dcom.evals.size(), nE = 1 + P.dcom.out.n_M, nv = P.dcom.out.nvars, off = dcom_words(R, P.dcom, P.kappa).size();
+    const size_t n1 = L * P.kappa * d, n2 = nv * 3 * d, n3 = L * nE * 4 * d;
+    if (len < off + n1 + 2 * n2 + 2 * n3) throw std::runtime_error("cm proof image truncated");
+    const u64* p = w + off; P.comh.assign(p, p + n1); p += n1;
+    for (int z = 0; z < 2; ++z) { P.pf[z].nvars = (int)nv; P.pf[z].degree = 2; P.pf[z].msgs.assign(p, p + n2); p += n2; }
+    for (int z = 0; z < 2; ++z) { P.evals[z].assign(p, p + n3); p += n3; }
+}
+// ComX image: cm_g[L x kappa x d] ro[nvars x 2] vo[L x (1+n_M) x 2 x d]
+inline std::vector<u64> comx_words(const ComX& X) { std::vector<u64> w = X.cm_g; w.insert(w.end(), X.ro.begin(), X.ro.end()); w.insert(w.end(), X.vo.begin(), X.vo.end()); return w; }
+
 } }  // namespace lfo::plus

@@ -322,6 +322,11 @@ class Oracle:
         L.lfo_plus_range_check.restype = C.c_long
         L.lfo_plus_range_check.argtypes = [C.c_int, C.c_int, C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, C.c_int, C.c_int, C.POINTER(Csr), C.c_int, u64p, C.c_size_t, u64p, C.c_size_t]
         L.lfo_plus_range_check_verify.argtypes = [C.c_int, u64p, C.c_size_t, u64p, C.c_size_t]
+        L.lfo_plus_cm_prove.restype = C.c_long
+        L.lfo_plus_cm_prove.argtypes = [C.c_int, C.c_int, C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, C.c_int, C.c_int, C.POINTER(Csr), C.c_int, u64p, C.c_size_t,
+                                        u64p, C.c_size_t, u64p, C.c_size_t, u64p]
+        L.lfo_plus_cm_verify.argtypes = [C.c_int, u64p, C.c_size_t, C.POINTER(Csr), C.c_int, u64p, C.c_size_t, u64p, C.c_size_t]
+        L.lfo_plus_mat_vec.argtypes = [C.c_int, u64p, C.c_size_t, C.c_size_t, u64p, u64p]
         L.lfo_plus_tensor.argtypes = [C.c_int, u64p, C.c_int, u64p]
         L.lfo_plus_ring_mul.argtypes = [C.c_int, u64p, u64p, u64p]
         self._plus_ready = True
@@ -382,6 +387,41 @@ class Oracle:
         if rc < 0:
             raise OracleError(rc, self.err())
         return bool(rc)
+
+    @staticmethod
+    def plus_comx_words(nvars, L, kappa, n_M, d=16):
+        return L * kappa * d + 2 * nvars + L * (1 + n_M) * 2 * d
+
+    def plus_cm_prove(self, ring, nvars, fs, A, b, k, l, M=(), seed=None, want_g=True):
+        """Cm::prove on from_f instances: returns (CmProof image, ComX image, g[L, n, d] or None)."""
+        self._plus_setup()
+        fs, A = np.ascontiguousarray(fs), np.ascontiguousarray(A)
+        ma = make_csr_array(list(M))
+        sd, sp, sn = self._seed(seed)
+        comx = np.zeros(self.plus_comx_words(nvars, fs.shape[0], A.shape[0], len(M)), dtype=np.uint64)
+        g = np.zeros_like(fs) if want_g else None
+        proof = self._plus_call(lambda out, cap: self.lib.lfo_plus_cm_prove(ring, nvars, fs.shape[0], ptr(fs), fs.shape[1], ptr(A), A.shape[0], b, k, l, ma, len(M), sp, sn,
+                                                                             ptr(out), cap, ptr(comx), comx.size, ptr(g)))
+        return proof, comx, g
+
+    def plus_cm_verify(self, ring, words, M=(), seed=None, nvars=None, L=1, kappa=1):
+        """CmProof::verify: (accepted, ComX image or None)"""
+        self._plus_setup()
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        ma = make_csr_array(list(M))
+        sd, sp, sn = self._seed(seed)
+        comx = np.zeros(self.plus_comx_words(nvars, L, kappa, len(M)), dtype=np.uint64) if nvars else None
+        rc = self.lib.lfo_plus_cm_verify(ring, ptr(words), words.size, ma, len(M), sp, sn, ptr(comx), comx.size if comx is not None else 0)
+        if rc < 0:
+            raise OracleError(rc, self.err())
+        return bool(rc), (comx if rc else None)
+
+    def plus_mat_vec(self, ring, A, x):
+        self._plus_setup()
+        A, x = np.ascontiguousarray(A), np.ascontiguousarray(x)
+        out = np.zeros((A.shape[0], A.shape[2]), dtype=np.uint64)
+        self.check(self.lib.lfo_plus_mat_vec(ring, ptr(A), A.shape[0], A.shape[1], ptr(x), ptr(out)))
+        return out
 
     def plus_tensor(self, ring, r):
         self._plus_setup()

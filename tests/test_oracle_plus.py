@@ -94,3 +94,25 @@ def test_range_check_random_two_instances(oracle):
     assert oracle.plus_range_check_verify(RING, dcom)
     bad = oracle.plus_range_check(RING, 15, fs, A, 8, k, l, [pc.random_ring_sparse(n, n, 2, 12)])      # ring-valued M: the psi tests of e[1] / c[1] fail
     assert not oracle.plus_range_check_verify(RING, bad)
+
+
+@pytest.mark.parametrize("kappa,with_M,L", [(2, True, 1), (1, False, 1), (2, True, 2)])
+def test_commitment_transformation(oracle, kappa, with_M, L):      # cm.rs:621-665 test_com (kappa = 2, M = identity with a 2) and variations
+    n, k, l, nvars = 1 << 15, 2, pc.frog_l(), 15
+    fs, A = pc.range_check_inputs(n, kappa, seed=21 + kappa, L=L)
+    if L == 1:
+        fs = pc.reference_range_check_f(n)
+    M = []
+    if with_M:
+        m = pc.identity(n); m["val"] = m["val"].copy(); m["val"][0, 0] = 2; M = [m]
+    proof, comx, g = oracle.plus_cm_prove(RING, nvars, fs, A, 8, k, l, M)
+    ok, comx_v = oracle.plus_cm_verify(RING, proof, M, nvars=nvars, L=L, kappa=kappa)
+    assert ok and np.array_equal(comx, comx_v)      # prover and verifier derive the same ComX
+    for pos in (proof.size - 1, proof.size - 2 * L * (1 + len(M)) * 4 * 16 - 5):      # an evaluation of the second sumcheck, a message of it
+        t = proof.copy(); t[pos] = (int(t[pos]) + 1) % pc.P_FROG
+        assert not oracle.plus_cm_verify(RING, t, M)[0]
+    assert not oracle.plus_cm_verify(RING, proof, M, seed=[5])[0]
+    # g = s0 tau + s1 m_tau + s2 f + h is a commitment opening: A g = cm_g (the folded commitment of ComX), by linearity of A
+    cmg = comx[: L * kappa * 16].reshape(L, kappa, 16)
+    for li in range(L):
+        assert np.array_equal(oracle.plus_mat_vec(RING, A, g[li]), cmg[li])
