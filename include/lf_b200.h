@@ -319,6 +319,16 @@ lf_status lf_plus_range_check(lf_ctx* ctx, lf_transcript* t, int32_t nvars, lf_p
                               const lf_csr* M, int32_t n_M, uint64_t* out, uint64_t out_cap, uint64_t* out_len);
 /* Dcom::verify                               rgchk.rs:190-246 (host).  LF_OK / LF_ERR_SUMCHECK_FAILED / LF_ERR_RECOMPOSED (a psi check) */
 lf_status lf_plus_range_check_verify(lf_transcript* t, const uint64_t* words, uint64_t len);
+/* Cm::prove                                  cm.rs:57-203: range check, h = M_f s', comh, the two degree-2 sumchecks over
+ * [eq | tau, m_tau, f, h | M_i-images | t(0), t(1)] and g = s0 tau + s1 m_tau + s2 f + h.  Images:
+ *   CmProof (cm.rs:31-37):  the Dcom image | comh[L][kappa][16] | sumcheck messages [2][nvars][3][16] | evaluations [2][L][1 + n_M][4][16]
+ *   ComX    (cm.rs:45-50):  cm_g[L][kappa][16] | ro[nvars][2] | vo[L][1 + n_M][2][16]          (lf_plus_comx_words words)
+ * g_host (L x n x 16 words, Com::g) may be NULL.                                                                                 */
+uint64_t lf_plus_comx_words(int32_t nvars, int32_t L, uint64_t kappa, int32_t n_M);
+lf_status lf_plus_cm_prove(lf_ctx* ctx, lf_transcript* t, int32_t nvars, lf_plus_rg* const* inst, int32_t L, const lf_csr* M, int32_t n_M,
+                           uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* comx, uint64_t* g_host);
+/* CmProof::verify                            cm.rs:349-535 (host; only the number of matrices is read from M there).  comx_out may be NULL */
+lf_status lf_plus_cm_verify(lf_transcript* t, const uint64_t* proof, uint64_t len, int32_t n_M, uint64_t* comx_out);
 /* utils.rs:74-86 tensor(r) (host): out has 2^n entries                                                                         */
 lf_status lf_plus_tensor(const uint64_t* r, int32_t n, uint64_t* out);
 

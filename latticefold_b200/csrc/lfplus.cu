@@ -241,6 +241,188 @@ void verify_set_image(Tr& T, const SetImage& s, std::vector<u64>* point_out = nu
 // ct(psi * a) with psi = sum_{0<i<d/2} i (X^-i + X^i): the constant coefficient of the negacyclic product
 // (psi_i = i, psi_{16-i} = -i, X^16 = -1  =>  ct = sum_i i (a_i - a_{16-i}))
 u64 ct_psi(const u64* a) { u64 acc = 0; for (int i = 1; i < PD / 2; ++i) acc = Fm::add(acc, Fm::hmul((u64)i, Fm::sub(a[i], a[PD - i]))); return acc; }
+// ---------------------------------------------------------------- commitment transformation (cm.rs): host pieces
+void hring_mul(u64* out, const u64* a, const u64* b) {      // negacyclic product of two canonical elements
+    u64 w[PD] = {0};
+    for (int i = 0; i < PD; ++i) { if (!a[i]) continue;
+        for (int j = 0; j < PD; ++j) { if (!b[j]) continue; const u64 pr = Fm::hmul(a[i], b[j]); const int k = i + j; if (k >= PD) w[k - PD] = Fm::sub(w[k - PD], pr); else w[k] = Fm::add(w[k], pr); } }
+    std::memcpy(out, w, sizeof w);
+}
+void hring_add(u64* out, const u64* a, const u64* b) { for (int i = 0; i < PD; ++i) out[i] = Fm::add(a[i], b[i]); }
+void hring_axpy(u64* acc, const u64* a, u64 c) { for (int i = 0; i < PD; ++i) if (a[i]) acc[i] = Fm::add(acc[i], Fm::hmul(a[i], c)); }      // acc += c a
+int plus_ceil_log2(size_t x) { int l = 0; while (((size_t)1 << l) < x) ++l; return l; }
+std::vector<u64> tensor_host(const std::vector<u64>& r) {      // utils.rs:74-86
+    std::vector<u64> res(1, 1);
+    for (u64 ri : r) { std::vector<u64> nx; nx.reserve(res.size() * 2); for (u64 a : res) { nx.push_back(Fm::hmul(a, Fm::sub(1, ri))); nx.push_back(Fm::hmul(a, ri)); } res.swap(nx); }
+    return res;
+}
+// short_challenge(128, transcript) (utils.rs:88-103): 16 bytes -> (byte mod 256) - 128, the decode of the Frog challenge set
+void short_challenge(Tr& T, u64* out) { T.get_short_challenge(out); }
+int to_small(u64 c) { return c > Fm::P / 2 ? -(int)(Fm::P - c) : (int)c; }
+struct CmChallenges { std::vector<u64> s /* 3 x 16 */, sp /* k*16 x 16 */; };
+CmChallenges draw_cm_challenges(Tr& T, int k) { CmChallenges c; c.s.resize(3 * PD); c.sp.resize((size_t)k * PD * PD); for (int i = 0; i < 3; ++i) short_challenge(T, &c.s[i * PD]); for (int i = 0; i < k * PD; ++i) short_challenge(T, &c.sp[(size_t)i * PD]); return c; }
+// ComX (cm.rs:537-575): cm_g[L][kappa], ro[nvars][2], vo[L][1 + n_M][2]
+std::vector<u64> comx_words(const u64* s, size_t L, size_t kappa, size_t nE, const u64* const* fcoms /* L pointers: cm_f | C_Mf | cm_mtau */, const u64* comh, const std::vector<u64>* evals /* [2] */, const std::vector<u64>* ro /* [2] */) {
+    std::vector<u64> w; u64 acc[PD], t[PD];
+    for (size_t l = 0; l < L; ++l) for (size_t i = 0; i < kappa; ++i) { const u64* cm_f = fcoms[l] + i * PD; const u64* C_Mf = fcoms[l] + (kappa + i) * PD; const u64* cm_mtau = fcoms[l] + (2 * kappa + i) * PD;
+        hring_mul(acc, s, C_Mf); hring_mul(t, s + PD, cm_mtau); hring_add(acc, acc, t); hring_mul(t, s + 2 * PD, cm_f); hring_add(acc, acc, t); hring_add(acc, acc, comh + (l * kappa + i) * PD);
+        w.insert(w.end(), acc, acc + PD); }
+    for (size_t i = 0; i < ro[0].size(); ++i) { w.push_back(ro[0][i]); w.push_back(ro[1][i]); }
+    for (size_t l = 0; l < L; ++l) for (size_t i = 0; i < nE; ++i) for (int z = 0; z < 2; ++z) { const u64* e = evals[z].data() + ((l * nE + i) * 4) * PD;
+        hring_mul(acc, s, e); hring_mul(t, s + PD, e + PD); hring_add(acc, acc, t); hring_mul(t, s + 2 * PD, e + 2 * PD); hring_add(acc, acc, t); hring_add(acc, acc, e + 3 * PD);
+        w.insert(w.end(), acc, acc + PD); }
+    return w;
+}
+struct DevCsr { u64 *row_ptr = nullptr, *col = nullptr, *val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0; void free(Eng& E) { E.dfree(row_ptr); E.dfree(col); E.dfree(val); row_ptr = col = val = nullptr; } };
+DevCsr upload_csr(Eng& E, const lf_csr& m) {      // validated by upload_by_columns before
+    DevCsr S; S.nrows = m.nrows; S.ncols = m.ncols; S.nnz = m.row_ptr[m.nrows];
+    S.row_ptr = E.dalloc<u64>(m.nrows + 1); S.col = E.dalloc<u64>(std::max<size_t>(S.nnz, 1)); S.val = E.dalloc<u64>(std::max<size_t>(S.nnz, 1) * PD);
+    LF_CUDA(cudaMemcpyAsync(S.row_ptr, m.row_ptr, (m.nrows + 1) * 8, cudaMemcpyHostToDevice, E.st()));
+    if (S.nnz) { LF_CUDA(cudaMemcpyAsync(S.col, m.col, S.nnz * 8, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemcpyAsync(S.val, m.val, S.nnz * PD * 8, cudaMemcpyHostToDevice, E.st())); }
+    E.sync(); return S;
+}
+
+// dense ring-valued MLE (len elements, zero tail) at a base-field point, by successive halving
+void mle_eval_dense(std::vector<u64> ev, int nv, const std::vector<u64>& point, u64* out) {
+    size_t len = ev.size() / PD;
+    for (int i = 0; i < nv; ++i) { const size_t nl = (len + 1) / 2; std::vector<u64> nx(std::max<size_t>(nl, 1) * PD, 0);
+        for (size_t b = 0; b < nl; ++b) for (int c = 0; c < PD; ++c) { const u64 a = ev[(2 * b) * PD + c], hi = 2 * b + 1 < len ? ev[(2 * b + 1) * PD + c] : 0; nx[b * PD + c] = Fm::add(a, Fm::hmul(Fm::sub(hi, a), point[i])); }
+        ev.swap(nx); len = std::max<size_t>(nl, 1); }
+    std::memcpy(out, ev.data(), 8 * PD);
+}
+// Rg::range_check (rgchk.rs:75-187).  Leaves eq(r, .) and the w_i on the device (R) for the commitment transformation that follows it in Cm::prove.
+std::vector<u64> range_check_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* inst, int L, const std::vector<DevSparse>& Ms, SetCheckResult& R) {
+        const lf_plus_rg& I0 = *inst[0];
+        for (int i = 0; i < L; ++i) if (!inst[i] || inst[i]->n != I0.n || inst[i]->k != I0.k || inst[i]->kappa != I0.kappa || inst[i]->l != I0.l || inst[i]->b != I0.b) throw LfException(LF_ERR_INVALID_ARG, "range check: instances of different shapes");
+        // sets: the k matrices M_f of every instance, then every instance's m_tau (rgchk.rs:80-89)
+        std::vector<DevSet> mats, vecs;
+        for (int i = 0; i < L; ++i) for (int kk = 0; kk < I0.k; ++kk) { DevSet s; s.codes = inst[i]->codes + (size_t)kk * PD * inst[i]->code_pitch; s.code_pitch = inst[i]->code_pitch; s.nrows = I0.n; s.ncols = PD; mats.push_back(s); }
+        for (int i = 0; i < L; ++i) { DevSet s; s.codes = inst[i]->mtau_codes; s.code_pitch = inst[i]->code_pitch; s.nrows = I0.n; s.ncols = 1; vecs.push_back(s); }
+        R = set_check_core(E, T, nvars, mats, vecs, Ms);
+        // evaluations at r (rgchk.rs:101-171): v = c[0] = MLE(f)(r) coefficient-wise, a[0] = MLE(tau)(r), and through w_i = M_i^T eq(r, .) the M_i-images
+        const size_t nE = 1 + Ms.size(), n = I0.n; const SmallArgs sm = small_consts();
+        std::vector<u64> img = {(u64)L, (u64)I0.k, (u64)I0.l, (u64)I0.kappa, I0.b}; { auto w = R.words(); img.insert(img.end(), w.begin(), w.end()); }
+        u64* cp = E.dalloc<u64>(2); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
+        std::vector<std::vector<u64>> av(L), cv(L);
+        for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
+            std::vector<u64> v(PD), a(nE), b(nE * PD), cc(nE * PD), tmp(PD);
+            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+              E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, 1), 256, 0, E.st()>>>(R.d_eq_r, cp, nullptr, I.f, partial); }); finish_wsum(E, partial, ch, 1, 0, v.data()); }
+            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+              E.launch("k_plus_wsum_scalar_small", [&] { k_plus_wsum_scalar_small<<<dim3(ch, 1), 256, 0, E.st()>>>(R.d_eq_r, I.tau, n, sm, partial); }); finish_wsum(E, partial, ch, 1, 1, tmp.data()); a[0] = tmp[0]; }
+            std::memcpy(b.data(), R.b.data() + (size_t)li * PD, 8 * PD); std::memcpy(cc.data(), v.data(), 8 * PD);
+            for (size_t mi = 0; mi < Ms.size(); ++mi) { const u64* W = R.d_w[mi];
+                { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+                  E.launch("k_plus_wsum_ring_small", [&] { k_plus_wsum_ring_small<<<dim3(ch, 1), 256, 0, E.st()>>>(W, I.tau, n, sm, partial); }); finish_wsum(E, partial, ch, 1, 0, tmp.data()); a[1 + mi] = tmp[0]; }
+                { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+                  E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, 1), 256, 0, E.st()>>>(W, I.mtau_codes, I.code_pitch, n, partial); }); finish_wsum(E, partial, ch, 1, 0, &b[(1 + mi) * PD]); }
+                { const unsigned ch = chunks_for(n, 128); u64* partial = E.partial_dev((size_t)ch * PD);
+                  E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(W, cp, nullptr, I.f, partial); }); finish_wsum(E, partial, ch, 1, 2, &cc[(1 + mi) * PD]); }
+            }
+            for (auto* x : {&v, &a, &b, &cc, }) img.insert(img.end(), x->begin(), x->end());
+            img.insert(img.end(), I.fcoms.begin(), I.fcoms.end());
+            av[li] = a; cv[li] = cc;
+        }
+        E.dfree(cp);
+        for (int li = 0; li < L; ++li) { for (u64 a : av[li]) absorb_field(T, a); T.absorb_slice(cv[li].data(), nE); }      // rgchk.rs:338-343
+        return img;
+}
+// Cm::prove (cm.rs:57-203).  proof image = Dcom image | comh | two sumcheck proofs | two evaluation blocks
+void cm_prove_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* inst, int L, const lf_csr* Mh, int n_M, std::vector<u64>& proof, std::vector<u64>& comx, u64* g_host) {
+    const lf_plus_rg& I0 = *inst[0]; const size_t n = I0.n, kappa = I0.kappa, N = (size_t)1 << nvars, nE = 1 + (size_t)n_M; const int k = I0.k, l = I0.l, kd = k * PD;
+    std::vector<DevSparse> Ms; std::vector<DevCsr> Mr; SetCheckResult R; std::vector<void*> blocks;
+    struct Cleanup { Eng& E; std::vector<DevSparse>& a; std::vector<DevCsr>& b; SetCheckResult& r; std::vector<void*>& blk; ~Cleanup() { for (auto& s : a) s.free(E); for (auto& s : b) s.free(E); r.free(E); for (void* p : blk) E.dfree(p); } } cl{E, Ms, Mr, R, blocks};
+    auto alloc = [&](size_t words) { u64* p = E.dalloc<u64>(words); blocks.push_back(p); return p; };
+    for (int i = 0; i < n_M; ++i) { Ms.push_back(upload_by_columns(E, Mh[i])); Mr.push_back(upload_csr(E, Mh[i])); }
+    proof = range_check_core(E, T, nvars, inst, L, Ms, R);
+    const CmChallenges ch = draw_cm_challenges(T, k);
+    std::vector<short> sp16((size_t)kd * PD); for (size_t i = 0; i < sp16.size(); ++i) sp16[i] = (short)to_small(ch.sp[i]);
+    short* d_sp = (short*)alloc((sp16.size() * 2 + 7) / 8); E.h2d(d_sp, sp16.data(), sp16.size() * 2);
+    // h_l = sum_kk M_f[kk] s'_kk (device), comh_l = sum_kk comM_f[kk] s'_kk (kappa elements, host)
+    std::vector<u64*> d_h(L);
+    for (int li = 0; li < L; ++li) { d_h[li] = alloc(n * PD);
+        E.launch("k_plus_h", [&] { k_plus_h<<<Eng::blocks_for(n, 128), 128, (size_t)kd * PD * 2, E.st()>>>(inst[li]->codes, inst[li]->code_pitch, n, kd, d_sp, d_h[li]); }); }
+    std::vector<u64> comh((size_t)L * kappa * PD, 0); u64 t[PD];
+    for (int li = 0; li < L; ++li) for (int kk = 0; kk < k; ++kk) for (size_t r = 0; r < kappa; ++r) for (int c = 0; c < PD; ++c) {
+        hring_mul(t, &inst[li]->comM[(((size_t)kk * kappa + r) * PD + c) * PD], &ch.sp[((size_t)kk * PD + c) * PD]); hring_add(&comh[(li * kappa + r) * PD], &comh[(li * kappa + r) * PD], t); }
+    T.absorb_slice(comh.data(), (size_t)L * kappa);
+    const int log_kappa = plus_ceil_log2(kappa);
+    std::vector<u64> c0(log_kappa), c1(log_kappa); for (auto& x : c0) x = challenge(T); for (auto& x : c1) x = challenge(T);
+    const std::vector<u64> tc0 = tensor_host(c0), tc1 = tensor_host(c1);
+    const size_t nt = tc0.size() * kd * l * PD;
+    if (nt > n) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "cm: t(z) longer than the witness (cm.rs:150-161)");
+    // scalar tables eq(r, .) | S = sum_l tau_l (kept; every sumcheck folds copies), ring tables G | U (rebuilt per sumcheck)
+    const SmallArgs sm = small_consts();
+    u64* sc0 = alloc(2 * N); LF_CUDA(cudaMemcpyAsync(sc0, R.d_eq_r, N * 8, cudaMemcpyDeviceToDevice, E.st())); LF_CUDA(cudaMemsetAsync(sc0 + N, 0, N * 8, E.st()));
+    { TauList tl; if (L > 64) throw LfException(LF_ERR_UNSUPPORTED, "cm: more than 64 instances"); tl.n = L; for (int li = 0; li < L; ++li) tl.p[li] = inst[li]->tau;
+      E.launch("k_plus_tau_sum", [&] { k_plus_tau_sum<<<Eng::blocks_for(n, 256), 256, 0, E.st()>>>(tl, n, sm, sc0 + N); }); }
+    u64 *GU = alloc(2 * N * PD), *GUn = alloc(N * PD), *scn = alloc(N), *scm = alloc(N / 2 + 1), *GUm = alloc(N * PD / 2 + PD), *Z = n_M ? alloc(n * PD) : nullptr, *d_scal = alloc(tc0.size() * l);
+    u64* eq_ro = alloc(N); u64* cp = alloc(2); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
+    std::vector<u64> msgs[2], evals[2], ro[2];
+    for (int z = 0; z < 2; ++z) {      // Cm::sumchecker (cm.rs:205-342), twice
+        const u64 rc = challenge(T);
+        std::vector<u64> rcps; { u64 p = 1; for (size_t i = 0; i < (size_t)L * (4 + 4 * n_M) + 2; ++i) { rcps.push_back(p); p = Fm::hmul(p, rc); } }
+        const size_t zi = (size_t)L * (4 + 4 * n_M);
+        LF_CUDA(cudaMemsetAsync(GU, 0, 2 * N * PD * 8, E.st()));
+        for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li]; const size_t base = (size_t)li * (4 + 4 * n_M);
+            Lin4 w{Fm::to_mont(rcps[base]), rcps[base + 1], Fm::to_mont(rcps[base + 2]), Fm::to_mont(rcps[base + 3])};
+            E.launch("k_plus_lin4", [&] { k_plus_lin4<<<Eng::blocks_for(n * PD, 256), 256, 0, E.st()>>>(I.tau, I.mtau_codes, I.f, d_h[li], n, w, li > 0 ? 1 : 0, GU); });
+            for (int mi = 0; mi < n_M; ++mi) { const size_t idx = base + 4 + 4 * mi;      // M_i (rc^a tau + rc^b m_tau + rc^c f + rc^d h): one sparse product per (instance, matrix)
+                Lin4 wz{Fm::to_mont(rcps[idx]), rcps[idx + 1], Fm::to_mont(rcps[idx + 2]), Fm::to_mont(rcps[idx + 3])};
+                E.launch("k_plus_lin4", [&] { k_plus_lin4<<<Eng::blocks_for(n * PD, 256), 256, 0, E.st()>>>(I.tau, I.mtau_codes, I.f, d_h[li], n, wz, 0, Z); });
+                E.launch("k_plus_spmv_acc", [&] { k_plus_spmv_acc<<<Eng::blocks_for(Mr[mi].nrows, 128), 128, 0, E.st()>>>(Mr[mi].row_ptr, Mr[mi].col, Mr[mi].val, Mr[mi].nrows, Z, Fm::r2(), GU); }); }
+        }
+        std::vector<u64> scal(tc0.size() * l);
+        for (size_t i = 0; i < tc0.size(); ++i) { u64 dpw = 1; const u64 base = Fm::add(Fm::hmul(rcps[zi], tc0[i]), Fm::hmul(rcps[zi + 1], tc1[i]));
+            for (int a = 0; a < l; ++a) { scal[i * l + a] = Fm::to_mont(Fm::hmul(base, dpw)); dpw = Fm::hmul(dpw, PD / 2); } }
+        E.h2d(d_scal, scal.data(), scal.size() * 8);
+        E.launch("k_plus_tz", [&] { k_plus_tz<<<Eng::blocks_for(nt, 128), 128, 0, E.st()>>>(d_scal, d_sp, kd, l, nt, GU + N * PD); });
+        // MLSumcheck::prove_as_subprotocol, degree 2
+        absorb_field(T, (u64)nvars); absorb_field(T, 2);
+        msgs[z].assign((size_t)nvars * 3 * PD, 0);
+        const u64 *sc_cur = sc0, *gu_cur = GU; u64 *sc_a = scn, *sc_b = scm, *gu_a = GUn, *gu_b = GUm; size_t len = N; u64 r_prev = 0;
+        for (int i = 0; i < nvars; ++i) {
+            if (i > 0) { const size_t n_out = len / 2; const u64 rm = Fm::to_mont(r_prev);
+                E.launch("k_plus_fold", [&] { k_plus_fold<<<dim3(Eng::blocks_for(n_out, 256), 2), 256, 0, E.st()>>>(sc_cur, len, sc_a, n_out, rm); });
+                E.launch("k_plus_fold", [&] { k_plus_fold_ring<<<dim3(Eng::blocks_for(n_out * PD, 256), 2), 256, 0, E.st()>>>(gu_cur, len, gu_a, n_out, rm); });
+                sc_cur = sc_a; gu_cur = gu_a; std::swap(sc_a, sc_b); std::swap(gu_a, gu_b); len = n_out; }
+            const size_t n_pairs = len / 2; const unsigned nblk = (unsigned)std::min<size_t>(std::max<size_t>((n_pairs * PD + 255) / 256, 1), 148 * 16);
+            u64* partial = E.partial_dev((size_t)nblk * 3 * PD); u64* d_out = E.small_dev(3 * PD);
+            E.launch("k_plus_cm_round", [&] { k_plus_cm_round<<<nblk, 256, 0, E.st()>>>(sc_cur, len, gu_cur, gu_cur + len * PD, n_pairs, partial); });
+            E.reduce_partials(partial, (int)nblk, 3 * PD, d_out);
+            u64* msg = msgs[z].data() + (size_t)i * 3 * PD; E.download_words(d_out, 3 * PD, msg);
+            T.absorb_slice(msg, 3);
+            r_prev = challenge(T); absorb_field(T, r_prev); ro[z].push_back(r_prev);
+        }
+        // evaluations of the individual tables at ro (cm.rs:315-337), through eq(ro, .) and w_i = M_i^T eq(ro, .)
+        eq_table(E, ro[z], eq_ro, N);
+        evals[z].assign((size_t)L * nE * 4 * PD, 0);
+        std::vector<u64*> d_w; for (int mi = 0; mi < n_M; ++mi) { u64* wv = alloc(std::max<size_t>(Ms[mi].ncols, 1) * PD);
+            E.launch("k_plus_mt_eq", [&] { k_plus_mt_eq<<<Eng::blocks_for(Ms[mi].ncols, 128), 128, 0, E.st()>>>(eq_ro, Ms[mi].col_ptr, Ms[mi].erow, Ms[mi].val, Ms[mi].ncols, wv); }); d_w.push_back(wv); }
+        for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
+            for (size_t e = 0; e < nE; ++e) { const bool ring = e > 0; const u64* W = ring ? d_w[e - 1] : eq_ro; u64* out = evals[z].data() + ((li * nE + e) * 4) * PD; const unsigned c256 = chunks_for(n, 256), c128 = chunks_for(n, 128);
+                { u64* partial = E.partial_dev((size_t)c256 * PD);
+                  if (ring) E.launch("k_plus_wsum_ring_small", [&] { k_plus_wsum_ring_small<<<dim3(c256, 1), 256, 0, E.st()>>>(W, I.tau, n, sm, partial); });
+                  else E.launch("k_plus_wsum_scalar_small", [&] { k_plus_wsum_scalar_small<<<dim3(c256, 1), 256, 0, E.st()>>>(W, I.tau, n, sm, partial); });
+                  finish_wsum(E, partial, c256, 1, ring ? 0 : 1, out); }
+                { DevSet S; S.codes = I.mtau_codes; S.code_pitch = I.code_pitch; S.nrows = n; S.ncols = 1; wsum_set(E, S, W, ring, out + PD); }
+                for (int q = 0; q < 2; ++q) { const u64* src = q == 0 ? I.f : d_h[li]; const unsigned chn = ring ? c128 : c256; u64* partial = E.partial_dev((size_t)chn * PD);
+                  if (ring) E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(chn, 1), 128, 0, E.st()>>>(W, cp, nullptr, src, partial); });
+                  else E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(chn, 1), 256, 0, E.st()>>>(W, cp, nullptr, src, partial); });
+                  finish_wsum(E, partial, chn, 1, ring ? 2 : 0, out + (2 + q) * PD); }
+            } }
+        T.absorb_slice(evals[z].data(), evals[z].size() / PD);      // absorb_evaluations (cm.rs:581-588)
+    }
+    // g_l = s0 tau + s1 m_tau + s2 f + h (cm.rs:165-182)
+    if (g_host) { GArgs ga; for (int o = 0; o < PD; ++o) { ga.s0[o] = (short)to_small(ch.s[o]); ga.s1[o] = (short)to_small(ch.s[PD + o]); ga.s2m[o] = Fm::to_mont(ch.s[2 * PD + o]); }
+        u64* d_g = alloc(n * PD);
+        for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
+            E.launch("k_plus_g", [&] { k_plus_g<<<Eng::blocks_for(n, 128), 128, 0, E.st()>>>(I.tau, I.mtau_codes, I.f, d_h[li], n, ga, d_g); });
+            LF_CUDA(cudaMemcpyAsync(g_host + (size_t)li * n * PD, d_g, n * PD * 8, cudaMemcpyDeviceToHost, E.st())); E.sync(); } }
+    for (auto* v : {&comh, &msgs[0], &msgs[1], &evals[0], &evals[1]}) proof.insert(proof.end(), v->begin(), v->end());
+    std::vector<const u64*> fc(L); for (int li = 0; li < L; ++li) fc[li] = inst[li]->fcoms.data();
+    comx = comx_words(ch.s.data(), L, kappa, nE, fc.data(), comh.data(), evals, ro);
+}
 }  // namespace
 
 extern "C" {
@@ -345,43 +527,11 @@ void lf_plus_rg_free(lf_ctx* c, lf_plus_rg* I) { if (I && c) { Eng E(c); E.dfree
 lf_status lf_plus_range_check(lf_ctx* c, lf_transcript* t, int32_t nvars, lf_plus_rg* const* inst, int32_t L, const lf_csr* M, int32_t n_M, uint64_t* out, uint64_t out_cap, uint64_t* out_len) {
     return pguard(c, [&] {
         need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
-        if (L < 1 || !inst || n_M < 0 || (n_M && !M) || !out_len) throw LfException(LF_ERR_INVALID_ARG, "range check: null / empty arguments");
-        const lf_plus_rg& I0 = *inst[0];
-        for (int i = 0; i < L; ++i) if (!inst[i] || inst[i]->n != I0.n || inst[i]->k != I0.k || inst[i]->kappa != I0.kappa || inst[i]->l != I0.l || inst[i]->b != I0.b) throw LfException(LF_ERR_INVALID_ARG, "range check: instances of different shapes");
+        if (L < 1 || !inst || !inst[0] || n_M < 0 || (n_M && !M) || !out_len) throw LfException(LF_ERR_INVALID_ARG, "range check: null / empty arguments");
         std::vector<DevSparse> Ms; SetCheckResult R;
         struct Cleanup { Eng& E; std::vector<DevSparse>& a; SetCheckResult& r; ~Cleanup() { for (auto& s : a) s.free(E); r.free(E); } } cl{E, Ms, R};
         for (int i = 0; i < n_M; ++i) Ms.push_back(upload_by_columns(E, M[i]));
-        // sets: the k matrices M_f of every instance, then every instance's m_tau (rgchk.rs:80-89)
-        std::vector<DevSet> mats, vecs;
-        for (int i = 0; i < L; ++i) for (int kk = 0; kk < I0.k; ++kk) { DevSet s; s.codes = inst[i]->codes + (size_t)kk * PD * inst[i]->code_pitch; s.code_pitch = inst[i]->code_pitch; s.nrows = I0.n; s.ncols = PD; mats.push_back(s); }
-        for (int i = 0; i < L; ++i) { DevSet s; s.codes = inst[i]->mtau_codes; s.code_pitch = inst[i]->code_pitch; s.nrows = I0.n; s.ncols = 1; vecs.push_back(s); }
-        R = set_check_core(E, T, nvars, mats, vecs, Ms);
-        // evaluations at r (rgchk.rs:101-171): v = c[0] = MLE(f)(r) coefficient-wise, a[0] = MLE(tau)(r), and through w_i = M_i^T eq(r, .) the M_i-images
-        const size_t nE = 1 + Ms.size(), n = I0.n; const SmallArgs sm = small_consts();
-        std::vector<u64> img = {(u64)L, (u64)I0.k, (u64)I0.l, (u64)I0.kappa, I0.b}; { auto w = R.words(); img.insert(img.end(), w.begin(), w.end()); }
-        u64* cp = E.dalloc<u64>(2); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
-        std::vector<std::vector<u64>> av(L), cv(L);
-        for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
-            std::vector<u64> v(PD), a(nE), b(nE * PD), cc(nE * PD), tmp(PD);
-            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-              E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, 1), 256, 0, E.st()>>>(R.d_eq_r, cp, nullptr, I.f, partial); }); finish_wsum(E, partial, ch, 1, 0, v.data()); }
-            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-              E.launch("k_plus_wsum_scalar_small", [&] { k_plus_wsum_scalar_small<<<dim3(ch, 1), 256, 0, E.st()>>>(R.d_eq_r, I.tau, n, sm, partial); }); finish_wsum(E, partial, ch, 1, 1, tmp.data()); a[0] = tmp[0]; }
-            std::memcpy(b.data(), R.b.data() + (size_t)li * PD, 8 * PD); std::memcpy(cc.data(), v.data(), 8 * PD);
-            for (size_t mi = 0; mi < Ms.size(); ++mi) { const u64* W = R.d_w[mi];
-                { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-                  E.launch("k_plus_wsum_ring_small", [&] { k_plus_wsum_ring_small<<<dim3(ch, 1), 256, 0, E.st()>>>(W, I.tau, n, sm, partial); }); finish_wsum(E, partial, ch, 1, 0, tmp.data()); a[1 + mi] = tmp[0]; }
-                { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-                  E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, 1), 256, 0, E.st()>>>(W, I.mtau_codes, I.code_pitch, n, partial); }); finish_wsum(E, partial, ch, 1, 0, &b[(1 + mi) * PD]); }
-                { const unsigned ch = chunks_for(n, 128); u64* partial = E.partial_dev((size_t)ch * PD);
-                  E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(W, cp, nullptr, I.f, partial); }); finish_wsum(E, partial, ch, 1, 2, &cc[(1 + mi) * PD]); }
-            }
-            for (auto* x : {&v, &a, &b, &cc, }) img.insert(img.end(), x->begin(), x->end());
-            img.insert(img.end(), I.fcoms.begin(), I.fcoms.end());
-            av[li] = a; cv[li] = cc;
-        }
-        E.dfree(cp);
-        for (int li = 0; li < L; ++li) { for (u64 a : av[li]) absorb_field(T, a); T.absorb_slice(cv[li].data(), nE); }      // rgchk.rs:338-343
+        const std::vector<u64> img = range_check_core(E, T, nvars, inst, L, Ms, R);
         *out_len = img.size();
         if (!out || out_cap < img.size()) throw LfException(LF_ERR_INVALID_ARG, "range check: output buffer too small");
         std::memcpy(out, img.data(), img.size() * 8);
@@ -408,6 +558,83 @@ lf_status lf_plus_range_check_verify(lf_transcript* t, const uint64_t* w, uint64
                 if (ct_psi(uc) != (ni == 0 ? v[j] : c[ni * PD + j])) throw LfException(LF_ERR_RECOMPOSED, "range check: ct(psi sum d'^i u_i) != v (RangeCheckError::PsiCheckVU)");
             }
         }
+    });
+}
+uint64_t lf_plus_comx_words(int32_t nvars, int32_t L, uint64_t kappa, int32_t n_M) { return (uint64_t)L * kappa * PD + 2 * (uint64_t)nvars + (uint64_t)L * (1 + n_M) * 2 * PD; }
+lf_status lf_plus_cm_prove(lf_ctx* c, lf_transcript* t, int32_t nvars, lf_plus_rg* const* inst, int32_t L, const lf_csr* M, int32_t n_M,
+                           uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* comx, uint64_t* g_host) {
+    return pguard(c, [&] {
+        need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (L < 1 || !inst || !inst[0] || n_M < 0 || (n_M && !M) || !proof_len) throw LfException(LF_ERR_INVALID_ARG, "cm: null / empty arguments");
+        std::vector<u64> pw, xw; cm_prove_core(E, T, nvars, inst, L, M, n_M, pw, xw, g_host);
+        *proof_len = pw.size();
+        if (!proof || proof_cap < pw.size()) throw LfException(LF_ERR_INVALID_ARG, "cm: proof buffer too small");
+        std::memcpy(proof, pw.data(), pw.size() * 8); if (comx) std::memcpy(comx, xw.data(), xw.size() * 8);
+    });
+}
+// CmProof::verify (cm.rs:349-535), host.  comx_out (lf_plus_comx_words) receives the ComX the verifier derives
+lf_status lf_plus_cm_verify(lf_transcript* t, const uint64_t* w, uint64_t len, int32_t n_M, uint64_t* comx_out) {
+    return pguard(nullptr, [&] {
+        Tr& T = tr_of(t);
+        if (!w || len < 10) throw LfException(LF_ERR_INCORRECT_LENGTH, "cm proof image too short");
+        const size_t L = w[0], k = w[1], l = w[2], kappa = w[3];
+        if (L < 1 || L > 64 || k < 1 || k > 16 || l < 1 || l > 64 || kappa < 1 || kappa > 4096) throw LfException(LF_ERR_INVALID_ARG, "cm proof image: implausible header");
+        const SetImage s = parse_set_image(w + 5, len - 5);
+        if (s.n_M != n_M) throw LfException(LF_ERR_INVALID_ARG, "cm proof image: number of matrices differs");
+        const size_t nE = 1 + s.n_M, per = PD + nE + 2 * nE * PD + 3 * kappa * PD, dlen = 5 + s.words + L * per, nv = s.nvars;
+        const size_t n1 = L * kappa * PD, n2 = nv * 3 * PD, n3 = L * nE * 4 * PD;
+        if (len < dlen + n1 + 2 * n2 + 2 * n3) throw LfException(LF_ERR_INCORRECT_LENGTH, "cm proof image truncated");
+        check_canonical(w + dlen, n1 + 2 * n2 + 2 * n3, "cm proof image");
+        lf_transcript tt{LF_RING_FROG, &T};
+        const lf_status rs = lf_plus_range_check_verify(&tt, w, dlen); if (rs != LF_OK) throw LfException(rs, "cm: range check rejected");
+        const u64* comh = w + dlen; const u64* msgs[2] = {comh + n1, comh + n1 + n2}; const u64* ev[2] = {comh + n1 + 2 * n2, comh + n1 + 2 * n2 + n3};
+        const CmChallenges ch = draw_cm_challenges(T, (int)k);
+        T.absorb_slice(comh, L * kappa);
+        const int log_kappa = plus_ceil_log2(kappa);
+        std::vector<u64> c0(log_kappa), c1(log_kappa); for (auto& x : c0) x = challenge(T); for (auto& x : c1) x = challenge(T);
+        const std::vector<u64> tc0 = tensor_host(c0), tc1 = tensor_host(c1);
+        // u[l][ni] = sum over instance l's k sets and their d columns of e * s' (cm.rs:386-404); tensor(c) . comh (cm.rs:406-430)
+        std::vector<u64> u(L * nE * PD, 0), tcch0(L * PD, 0), tcch1(L * PD, 0); u64 t[PD];
+        for (size_t li = 0; li < L; ++li) for (size_t ni = 0; ni < nE; ++ni) for (size_t q = 0; q < k * PD; ++q) {
+            hring_mul(t, s.e + ((ni * s.n_mat + li * k) * (size_t)s.ncols + q) * PD, &ch.sp[q * PD]); hring_add(&u[(li * nE + ni) * PD], &u[(li * nE + ni) * PD], t); }
+        for (size_t li = 0; li < L; ++li) for (size_t i = 0; i < std::min(tc0.size(), kappa); ++i) { hring_axpy(&tcch0[li * PD], comh + (li * kappa + i) * PD, tc0[i]); hring_axpy(&tcch1[li * PD], comh + (li * kappa + i) * PD, tc1[i]); }
+        // t(z) as dense vectors (cm.rs:590-601), evaluated at each sumcheck's point below
+        auto t_z = [&](const std::vector<u64>& tc) { std::vector<u64> out(tc.size() * k * PD * l * PD * PD, 0); size_t idx = 0;
+            for (u64 tci : tc) for (size_t j = 0; j < k * PD; ++j) { u64 dpw = 1; for (size_t a = 0; a < l; ++a) { const u64 sc = Fm::hmul(tci, dpw); dpw = Fm::hmul(dpw, PD / 2);
+                for (int b = 0; b < PD; ++b, ++idx) for (int o = 0; o < PD; ++o) { const u64 v = ch.sp[j * PD + ((o - b) & (PD - 1))]; out[idx * PD + o] = Fm::hmul(sc, o >= b ? v : Fm::neg(v)); } } }
+            return out; };
+        const std::vector<u64> t0 = t_z(tc0), t1 = t_z(tc1);
+        if (t0.size() / PD > ((size_t)1 << nv)) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "cm: t(z) longer than 2^nvars");
+        const u64* dcom_evals = w + 5 + s.words; std::vector<u64> ro[2]; std::vector<u64> evv[2];
+        for (int z = 0; z < 2; ++z) {
+            const u64 rc = challenge(T); const size_t zi = L * (4 + 4 * (size_t)s.n_M);
+            std::vector<u64> rcps; { u64 p = 1; for (size_t i = 0; i < zi + 2; ++i) { rcps.push_back(p); p = Fm::hmul(p, rc); } }
+            u64 claimed[PD] = {0};
+            for (size_t li = 0; li < L; ++li) { const u64* p = dcom_evals + li * per; const u64 *a = p + PD, *b = a + nE, *cc = b + nE * PD; const size_t base = li * (4 + 4 * (size_t)s.n_M);
+                for (size_t i = 0; i < nE; ++i) { const size_t idx = base + 4 * i;
+                    claimed[0] = Fm::add(claimed[0], Fm::hmul(a[i], rcps[idx])); hring_axpy(claimed, b + i * PD, rcps[idx + 1]); hring_axpy(claimed, cc + i * PD, rcps[idx + 2]); hring_axpy(claimed, &u[(li * nE + i) * PD], rcps[idx + 3]); }
+                hring_axpy(claimed, &tcch0[li * PD], rcps[zi]); hring_axpy(claimed, &tcch1[li * PD], rcps[zi + 1]); }
+            // MLSumcheck::verify_as_subprotocol, degree 2
+            absorb_field(T, (u64)nv); absorb_field(T, 2);
+            for (size_t i = 0; i < nv; ++i) { T.absorb_slice(msgs[z] + i * 3 * PD, 3); const u64 r = challenge(T); ro[z].push_back(r); absorb_field(T, r); }
+            u64 expected[PD]; std::memcpy(expected, claimed, sizeof expected);
+            for (size_t i = 0; i < nv; ++i) { const u64* msg = msgs[z] + i * 3 * PD;
+                for (int cf = 0; cf < PD; ++cf) if (Fm::add(msg[cf], msg[PD + cf]) != expected[cf]) throw LfException(LF_ERR_SUMCHECK_FAILED, "cm: sumcheck round sum mismatch");
+                u64 lag[3]; for (int a = 0; a < 3; ++a) { u64 num = 1, den = 1; for (int b = 0; b < 3; ++b) if (b != a) { num = Fm::hmul(num, Fm::sub(ro[z][i], (u64)b)); den = Fm::hmul(den, a > b ? (u64)(a - b) : Fm::P - (u64)(b - a)); } lag[a] = Fm::hmul(num, Fm::hpow(den, Fm::P - 2)); }
+                for (int cf = 0; cf < PD; ++cf) { u64 v = 0; for (int a = 0; a < 3; ++a) v = Fm::add(v, Fm::hmul(msg[a * PD + cf], lag[a])); expected[cf] = v; } }
+            u64 t0_ro[PD], t1_ro[PD]; mle_eval_dense(t0, (int)nv, ro[z], t0_ro); mle_eval_dense(t1, (int)nv, ro[z], t1_ro);
+            T.absorb_slice(ev[z], L * nE * 4);
+            u64 eq = 1; for (size_t i = 0; i < nv; ++i) { const u64 xy = Fm::hmul(s.r[i], ro[z][i]); eq = Fm::hmul(eq, Fm::add(Fm::sub(Fm::sub(Fm::add(xy, xy), s.r[i]), ro[z][i]), 1)); }
+            u64 evl[PD] = {0};
+            for (size_t li = 0; li < L; ++li) { const u64* el = ev[z] + li * nE * 4 * PD; const size_t base = li * (4 + 4 * (size_t)s.n_M); u64 in[PD] = {0}, pr[PD];
+                for (size_t q = 0; q < 4 * nE; ++q) hring_axpy(in, el + q * PD, rcps[base + q]);
+                hring_axpy(evl, in, eq);
+                hring_mul(pr, t0_ro, el); hring_axpy(evl, pr, rcps[zi]); hring_mul(pr, t1_ro, el); hring_axpy(evl, pr, rcps[zi + 1]); }
+            if (std::memcmp(evl, expected, sizeof evl) != 0) throw LfException(LF_ERR_SUMCHECK_FAILED, "cm: evaluation claim mismatch (cm.rs:521)");
+            evv[z].assign(ev[z], ev[z] + n3);
+        }
+        if (comx_out) { std::vector<const u64*> fc(L); for (size_t li = 0; li < L; ++li) fc[li] = dcom_evals + li * per + PD + nE + 2 * nE * PD;
+            const std::vector<u64> xw = comx_words(ch.s.data(), L, kappa, nE, fc.data(), comh, evv, ro); std::memcpy(comx_out, xw.data(), xw.size() * 8); }
     });
 }
 lf_status lf_plus_tensor(const uint64_t* r, int32_t n, uint64_t* out) {

@@ -267,4 +267,135 @@ __global__ void k_plus_digit_codes(const u64* __restrict__ f, size_t n, long lon
     }
 }
 
+// ---------------------------------------------------------------- commitment transformation (cm.rs)
+LF_HD u64 small_to_field(int v) { return v >= 0 ? (u64)v : Fm::P - (u64)(-v); }
+// h[x] = sum_kk M_f[kk][x] . s'_kk = sum_{kk, c} X^code s'[kk][c]  (cm.rs:83-103): rotations of the short challenges, exact in 32-bit integers
+__global__ void __launch_bounds__(128) k_plus_h(const unsigned char* __restrict__ codes, size_t code_pitch, size_t nrows, int kd /* k * 16 */, const short* __restrict__ sp /* kd x 16 */, u64* __restrict__ h) {
+    extern __shared__ short sps[];
+    for (int i = threadIdx.x; i < kd * PD; i += blockDim.x) sps[i] = sp[i];
+    __syncthreads();
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nrows) return;
+    int acc[PD];
+#pragma unroll
+    for (int o = 0; o < PD; ++o) acc[o] = 0;
+    for (int q = 0; q < kd; ++q) {
+        const unsigned cd = codes[(size_t)q * code_pitch + x];
+        if (cd >= PD) continue;
+        const short* sq = sps + q * PD;
+#pragma unroll
+        for (int o = 0; o < PD; ++o) { const int v = sq[(o - cd) & (PD - 1)]; acc[o] += (unsigned)o >= cd ? v : -v; }
+    }
+#pragma unroll
+    for (int o = 0; o < PD; ++o) h[x * PD + o] = small_to_field(acc[o]);
+}
+// U = rho0 t0 + rho1 t1 with t(z) = tensor(c_z) (x) s' (x) (1, d', ..) (x) (1, X, ..) (cm.rs:590-601): entry ((i kd + j) l + a) 16 + b is
+// scal[i][a] * (s'_j X^b), scal[i][a] = (rho0 tensor(c0)_i + rho1 tensor(c1)_i) d'^a in Montgomery form
+__global__ void k_plus_tz(const u64* __restrict__ scal, const short* __restrict__ sp, int kd, int l, size_t nt, u64* __restrict__ U) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nt) return;
+    const unsigned b = idx % PD; const int a = (int)((idx / PD) % l); const int j = (int)((idx / PD / l) % kd); const size_t i = idx / PD / l / kd;
+    const u64 sc = scal[i * l + a]; const short* sj = sp + j * PD;
+#pragma unroll
+    for (int o = 0; o < PD; ++o) { const int v = sj[(o - b) & (PD - 1)]; U[idx * PD + o] = Fm::mul(sc, small_to_field((unsigned)o >= b ? v : -v)); }
+}
+// out[x] (+)= ra tau[x] + rb m_tau[x] + rc f[x] + rd h[x] as ring elements (the rc-weighted sum of one instance's four tables, cm.rs:285-300)
+struct Lin4 { u64 ra_m, rb, rc_m, rd_m; };      // ra, rc, rd in Montgomery form, rb canonical
+__global__ void k_plus_lin4(const signed char* __restrict__ tau, const unsigned char* __restrict__ mcode, const u64* __restrict__ f, const u64* __restrict__ h, size_t n, Lin4 w, int accumulate, u64* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * PD) return;
+    const size_t x = i / PD; const unsigned o = (unsigned)(i % PD);
+    u64 v = Fm::add(Fm::mul(w.rc_m, f[i]), Fm::mul(w.rd_m, h[i]));
+    if (o == 0) v = Fm::add(v, Fm::mul(w.ra_m, small_to_field(tau[x])));
+    if (o == mcode[x]) v = Fm::add(v, w.rb);
+    out[i] = accumulate ? Fm::add(out[i], v) : v;
+}
+// G[y] += sum_e M[y][col_e] * Z[col_e] (row-major CSR, general ring products; M's coefficients are lifted to Montgomery form so the products are canonical)
+__global__ void __launch_bounds__(128) k_plus_spmv_acc(const u64* __restrict__ row_ptr, const u64* __restrict__ col, const u64* __restrict__ val, size_t nrows, const u64* __restrict__ Z, u64 r2, u64* __restrict__ G) {
+    const size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= nrows) return;
+    u64 acc[PD];
+#pragma unroll
+    for (int c = 0; c < PD; ++c) acc[c] = 0;
+    for (u64 e = row_ptr[y]; e < row_ptr[y + 1]; ++e) {
+        u64 v[PD];
+#pragma unroll
+        for (int j = 0; j < PD; ++j) v[j] = Z[col[e] * PD + j];
+#pragma unroll 1
+        for (int i = 0; i < PD; ++i) {
+            const u64 mi = val[e * PD + i];
+            if (mi) { const u64 mm = Fm::mul(mi, r2);
+#pragma unroll
+                for (int j = 0; j < PD; ++j) acc[j] = Fm::add(acc[j], Fm::mul(mm, v[j])); }
+            const u64 top = v[PD - 1];
+#pragma unroll
+            for (int j = PD - 1; j > 0; --j) v[j] = v[j - 1];
+            v[0] = Fm::neg(top);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < PD; ++c) G[y * PD + c] = Fm::add(G[y * PD + c], acc[c]);
+}
+// one round of the cm sumcheck (cm.rs:285-307 collapsed): h(X)[o] = sum_b eq(X) G(X)[o] + S(X) U(X)[o], X = 0, 1, 2; thread = (pair, coefficient)
+__global__ void __launch_bounds__(256) k_plus_cm_round(const u64* __restrict__ sc /* eq | S, stride */, size_t stride, const u64* __restrict__ G, const u64* __restrict__ U, size_t n_pairs, u64* __restrict__ partial) {
+    u64 acc[3] = {0, 0, 0};
+    const unsigned o = threadIdx.x & (PD - 1);
+    for (size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; b < n_pairs; b += ((size_t)gridDim.x * blockDim.x) >> 4) {
+        const u64 e0 = sc[2 * b], e1 = sc[2 * b + 1], s0 = sc[stride + 2 * b], s1 = sc[stride + 2 * b + 1];
+        const u64 g0 = G[(2 * b) * PD + o], g1 = G[(2 * b + 1) * PD + o], u0 = U[(2 * b) * PD + o], u1 = U[(2 * b + 1) * PD + o];
+        acc[0] = Fm::add(acc[0], Fm::add(Fm::mul(e0, g0), Fm::mul(s0, u0)));
+        acc[1] = Fm::add(acc[1], Fm::add(Fm::mul(e1, g1), Fm::mul(s1, u1)));
+        const u64 e2 = Fm::add(e1, Fm::sub(e1, e0)), s2 = Fm::add(s1, Fm::sub(s1, s0)), g2 = Fm::add(g1, Fm::sub(g1, g0)), u2 = Fm::add(u1, Fm::sub(u1, u0));
+        acc[2] = Fm::add(acc[2], Fm::add(Fm::mul(e2, g2), Fm::mul(s2, u2)));
+    }
+    __shared__ u64 sh[8][3][PD];
+#pragma unroll
+    for (int X = 0; X < 3; ++X) { u64 v = acc[X]; v = Fm::add(v, __shfl_xor_sync(0xffffffffu, v, 16)); if ((threadIdx.x & 31) < PD) sh[threadIdx.x >> 5][X][o] = v; }
+    __syncthreads();
+    if (threadIdx.x < 3 * PD) { const int X = threadIdx.x / PD, oo = threadIdx.x % PD; u64 v = 0; for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v = Fm::add(v, sh[wv][X][oo]); partial[(size_t)blockIdx.x * 3 * PD + threadIdx.x] = v; }
+}
+// fix_variables on ring-valued tables (coefficient-wise): out[t][b][o] = in[t][2b][o] + r (in[t][2b+1][o] - in[t][2b][o])
+__global__ void k_plus_fold_ring(const u64* __restrict__ in, size_t in_len, u64* __restrict__ out, size_t n_out, u64 r) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; const size_t t = blockIdx.y;
+    if (i >= n_out * PD) return;
+    const size_t b = i / PD, o = i % PD; const u64* base = in + t * in_len * PD;
+    const u64 a = base[(2 * b) * PD + o], c = base[(2 * b + 1) * PD + o];
+    out[t * n_out * PD + i] = Fm::add(a, Fm::mul(r, Fm::sub(c, a)));
+}
+// g[x] = s0 tau[x] + s1 m_tau[x] + s2 f[x] + h[x] (cm.rs:165-182): s small (|.| <= 128); s2 f is the only real ring product
+struct GArgs { short s0[PD], s1[PD]; u64 s2m[PD]; };      // s2 in Montgomery form
+__global__ void __launch_bounds__(128) k_plus_g(const signed char* __restrict__ tau, const unsigned char* __restrict__ mcode, const u64* __restrict__ f, const u64* __restrict__ h, size_t n, GArgs a, u64* __restrict__ g) {
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    u64 acc[PD], v[PD];
+    const int t = tau[x]; const unsigned cd = mcode[x];
+#pragma unroll
+    for (int o = 0; o < PD; ++o) { const int s1v = a.s1[(o - cd) & (PD - 1)]; acc[o] = Fm::add(h[x * PD + o], small_to_field(a.s0[o] * t + ((unsigned)o >= cd ? s1v : -s1v))); v[o] = f[x * PD + o]; }
+#pragma unroll 1
+    for (int i = 0; i < PD; ++i) {      // + s2_i (X^i f)
+        const u64 si = a.s2m[i];
+        if (si) {
+#pragma unroll
+            for (int j = 0; j < PD; ++j) acc[j] = Fm::add(acc[j], Fm::mul(si, v[j])); }
+        const u64 top = v[PD - 1];
+#pragma unroll
+        for (int j = PD - 1; j > 0; --j) v[j] = v[j - 1];
+        v[0] = Fm::neg(top);
+    }
+#pragma unroll
+    for (int o = 0; o < PD; ++o) g[x * PD + o] = acc[o];
+}
+// S[x] = sum_l tau_l[x] in Montgomery form (the scalar factor of the t(z) terms, cm.rs:303-304)
+struct TauList { const signed char* p[64]; int n; };
+__global__ void k_plus_tau_sum(TauList tl, size_t n, SmallArgs sm, u64* __restrict__ S) {
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    u64 v = 0;
+    for (int l = 0; l < tl.n; ++l) { const int t = tl.p[l][x]; u64 s = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if ((t & 15) == k) s = sm.v[k];
+        v = Fm::add(v, s); }
+    S[x] = v;
+}
+
 } }  // namespace lf::plus

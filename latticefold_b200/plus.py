@@ -14,7 +14,8 @@ from .api import Csr, LfError, Transcript, lib, ptr, u64p, vp
 RING = synth.RING_FROG
 D = 16
 SYMBOLS = """lf_transcript_get_challenge_base lf_plus_set_check lf_plus_set_check_verify lf_plus_mat_create lf_plus_mat_free
-lf_plus_rg_from_f lf_plus_rg_read lf_plus_rg_free lf_plus_range_check lf_plus_range_check_verify lf_plus_tensor""".split()
+lf_plus_rg_from_f lf_plus_rg_read lf_plus_rg_free lf_plus_range_check lf_plus_range_check_verify lf_plus_tensor
+lf_plus_comx_words lf_plus_cm_prove lf_plus_cm_verify""".split()
 
 
 class PlusSet(C.Structure):      # lf_plus_set
@@ -39,6 +40,10 @@ def _L():
         L.lf_plus_range_check.argtypes = [vp, vp, C.c_int32, C.POINTER(vp), C.c_int32, C.POINTER(Csr), C.c_int32, u64p, C.c_uint64, u64p]
         L.lf_plus_range_check_verify.argtypes = [vp, u64p, C.c_uint64]
         L.lf_plus_tensor.argtypes = [u64p, C.c_int32, u64p]
+        L.lf_plus_comx_words.restype = C.c_uint64
+        L.lf_plus_comx_words.argtypes = [C.c_int32, C.c_int32, C.c_uint64, C.c_int32]
+        L.lf_plus_cm_prove.argtypes = [vp, vp, C.c_int32, C.POINTER(vp), C.c_int32, C.POINTER(Csr), C.c_int32, u64p, C.c_uint64, u64p, u64p, u64p]
+        L.lf_plus_cm_verify.argtypes = [vp, u64p, C.c_uint64, C.c_int32, u64p]
         _ready = True
     return L
 
@@ -166,6 +171,32 @@ def range_check_verify(words, transcript):      # Dcom::verify, rgchk.rs:190-246
     if rc in (0, -10, -11):
         return rc == 0
     raise LfError(rc, "range-check image rejected as malformed")
+
+
+class Cm:
+    """cm.rs:22-25: the commitment transformation over an `Rg`."""
+
+    def __init__(self, rg):
+        self.rg = rg
+
+    def prove(self, M, transcript, want_g=True, g_out=None):      # cm.rs:57-203 -> (CmProof image, ComX image, g[L, n, 16] or None)
+        L_, rg = _L(), self.rg
+        hs = (vp * len(rg.instances))(*[i.h for i in rg.instances])
+        ma = _csr_array(list(M))
+        i0 = rg.instances[0]
+        comx = np.zeros(int(L_.lf_plus_comx_words(rg.nvars, len(rg.instances), i0.kappa, len(M))), dtype=np.uint64)
+        g = g_out if g_out is not None else (np.zeros((len(rg.instances), i0.n, D), dtype=np.uint64) if want_g else None)
+        proof = _grow(rg.ctx, lambda o, cap, n: L_.lf_plus_cm_prove(rg.ctx.h, transcript.h, rg.nvars, hs, len(rg.instances), ma, len(M), o, cap, n, ptr(comx), ptr(g)))
+        return proof, comx, g
+
+
+def cm_verify(words, n_M, transcript, nvars=None, L=1, kappa=1):      # CmProof::verify, cm.rs:349-535 -> (accepted, ComX image)
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    comx = np.zeros(int(_L().lf_plus_comx_words(nvars, L, kappa, n_M)), dtype=np.uint64) if nvars else None
+    rc = _L().lf_plus_cm_verify(transcript.h, ptr(words), words.size, n_M, ptr(comx))
+    if rc in (0, -10, -11):
+        return rc == 0, (comx if rc == 0 else None)
+    raise LfError(rc, "cm proof image rejected as malformed")
 
 
 def tensor(r):      # utils.rs:74-86

@@ -111,3 +111,41 @@ def test_range_check_at_benchmark_size(ctx):
     assert plus.range_check_verify(dcom, seeded())
     t = dcom.copy(); t[40] = (int(t[40]) + 1) % pc.P_FROG
     assert not plus.range_check_verify(t, seeded())
+
+
+@pytest.mark.parametrize("kappa,with_M,L", [(2, True, 1), (1, False, 1), (2, True, 2), (4, False, 1)])
+def test_commitment_transformation_bit_exact(ctx, oracle, kappa, with_M, L):      # cm.rs:621-665 (test_com) and variations
+    n, k, l, nvars = 1 << (16 if kappa == 4 else 15), 2, pc.frog_l(), 16 if kappa == 4 else 15
+    fs, A = pc.range_check_inputs(n, kappa, seed=21 + kappa, L=L)
+    if L == 1 and kappa == 2:
+        fs = pc.reference_range_check_f(n)
+    M = []
+    if with_M:
+        m = pc.identity(n); m["val"] = m["val"].copy(); m["val"][0, 0] = 2
+        M = [m] if L == 1 else [m, pc.random_ring_sparse(n, n, 2, 31, constant=True)]
+    Ad = plus.Matrix(ctx, A)
+    inst = [plus.RgInstance.from_f(ctx, fs[i], Ad, 8, k, l) for i in range(L)]
+    tp = seeded([8, 1])
+    proof, comx, g = plus.Cm(plus.Rg(ctx, nvars, inst)).prove(M, tp)
+    oproof, ocomx, og = oracle.plus_cm_prove(RING, nvars, fs, A, 8, k, l, M, seed=[8, 1])
+    assert proof.shape == oproof.shape and np.array_equal(proof, oproof)
+    assert np.array_equal(comx, ocomx) and np.array_equal(g, og)
+    tv = seeded([8, 1])
+    ok, comx_v = plus.cm_verify(proof, len(M), tv, nvars=nvars, L=L, kappa=kappa)
+    assert ok and np.array_equal(comx_v, comx)
+    assert tp.get_challenge() == tv.get_challenge()      # prover and verifier leave the transcript in the same state
+    assert oracle.plus_cm_verify(RING, proof, M, seed=[8, 1])[0]
+    cmg = comx[: L * kappa * 16].reshape(L, kappa, 16)
+    for li in range(L):
+        assert np.array_equal(oracle.plus_mat_vec(RING, A, g[li]), cmg[li])      # A g = cm_g: g opens the folded commitment
+
+
+def test_commitment_transformation_at_benchmark_size(ctx, oracle):
+    """benches/utils/mod.rs commitment_transform rows use n = 2^16, k = 2, kappa = 2: acceptance by both verifiers and A g = cm_g."""
+    n, kappa, k, l, nvars = 1 << 16, 2, 2, pc.frog_l(), 16
+    fs, A = pc.range_check_inputs(n, kappa, seed=5, L=1)
+    inst = [plus.RgInstance.from_f(ctx, fs[0], plus.Matrix(ctx, A), 8, k, l)]
+    proof, comx, g = plus.Cm(plus.Rg(ctx, nvars, inst)).prove([], seeded())
+    assert plus.cm_verify(proof, 0, seeded(), nvars=nvars, L=1, kappa=kappa)[0]
+    assert oracle.plus_cm_verify(RING, proof, [])[0]
+    assert np.array_equal(oracle.plus_mat_vec(RING, A, g[0]), comx[: kappa * 16].reshape(kappa, 16))

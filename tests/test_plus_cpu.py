@@ -71,3 +71,23 @@ def test_provers_fail_loudly_without_gpu():
     import latticefold_b200 as lf
     with pytest.raises(lf.LfError):
         lf.Context(RING)
+
+
+@pytest.mark.parametrize("kappa,with_M,L", [(2, True, 1), (1, False, 1), (2, True, 2)])
+def test_product_verifier_on_oracle_cm(oracle, kappa, with_M, L):      # cm.rs:621-665 (test_com) and variations: oracle prover -> product verifier
+    n, k, l, nvars = 1 << 15, 2, pc.frog_l(), 15
+    fs, A = pc.range_check_inputs(n, kappa, seed=21 + kappa, L=L)
+    if L == 1:
+        fs = pc.reference_range_check_f(n)
+    M = []
+    if with_M:
+        m = pc.identity(n); m["val"] = m["val"].copy(); m["val"][0, 0] = 2; M = [m]
+    proof, comx, _ = oracle.plus_cm_prove(RING, nvars, fs, A, 8, k, l, M, seed=[6], want_g=False)
+    ok, comx_v = plus.cm_verify(proof, len(M), seeded([6]), nvars=nvars, L=L, kappa=kappa)
+    assert ok and np.array_equal(comx_v, comx)
+    for pos in (proof.size - 1, proof.size - 2 * L * (1 + len(M)) * 4 * 16 - 5, 40):
+        t = proof.copy(); t[pos] = (int(t[pos]) + 1) % pc.P_FROG
+        assert not plus.cm_verify(t, len(M), seeded([6]))[0]
+    assert not plus.cm_verify(proof, len(M), seeded(None))[0]
+    with pytest.raises(plus.LfError):
+        plus.cm_verify(proof[:-3], len(M), seeded([6]))
