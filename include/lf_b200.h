@@ -329,6 +329,17 @@ lf_status lf_plus_cm_prove(lf_ctx* ctx, lf_transcript* t, int32_t nvars, lf_plus
                            uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* comx, uint64_t* g_host);
 /* CmProof::verify                            cm.rs:349-535 (host; only the number of matrices is read from M there).  comx_out may be NULL */
 lf_status lf_plus_cm_verify(lf_transcript* t, const uint64_t* proof, uint64_t len, int32_t n_M, uint64_t* comx_out);
+/* Mlin::mlin                                 mlin.rs:41-106: from_f on each of the L witnesses (fs: L x n x 16), Cm::prove, and the sums
+ * over the instances.  linb2x (LinB2X) = cm_g[kappa][16] | ro[nvars][2] | vo[1 + n_M][2][16]; g_host (n x 16, LinB2::g) may be NULL     */
+lf_status lf_plus_mlin(lf_ctx* ctx, lf_transcript* t, const lf_plus_mat* A, const uint64_t* fs, int32_t L, uint64_t n, uint64_t b, int32_t k, int32_t l,
+                       const lf_csr* M, int32_t n_M, uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* linb2x, uint64_t* g_host);
+/* Decomp::decompose                          decomp.rs:32-99: F = decompose_to_vec(f, B, 2), C_i = A F_i, v_i = evaluations of F_i and of
+ * every M_j F_i at the two points r_pairs (nvars x 2 field elements).  proof (DecompProof) = C0[kappa][16] | C1 | v0[1 + n_M][2][16] | v1;
+ * F_host (2 x n x 16) may be NULL.  LF_ERR_DOES_NOT_FIT when a coefficient needs more than two digits                                   */
+lf_status lf_plus_decompose(lf_ctx* ctx, const lf_plus_mat* A, const uint64_t* f, uint64_t n, const uint64_t* r_pairs, const lf_csr* M, int32_t n_M,
+                            uint64_t B, uint64_t* proof, uint64_t* F_host);
+/* DecompProof::verify                        decomp.rs:102-126 (host): LF_OK / LF_ERR_RECOMPOSED                                         */
+lf_status lf_plus_decompose_verify(const uint64_t* proof, uint64_t kappa, int32_t n_M, const uint64_t* cm_f, const uint64_t* v, uint64_t B);
 /* utils.rs:74-86 tensor(r) (host): out has 2^n entries                                                                         */
 lf_status lf_plus_tensor(const uint64_t* r, int32_t n, uint64_t* out);
 

@@ -328,7 +328,7 @@ std::vector<u64> range_check_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* i
         return img;
 }
 // Cm::prove (cm.rs:57-203).  proof image = Dcom image | comh | two sumcheck proofs | two evaluation blocks
-void cm_prove_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* inst, int L, const lf_csr* Mh, int n_M, std::vector<u64>& proof, std::vector<u64>& comx, u64* g_host) {
+void cm_prove_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* inst, int L, const lf_csr* Mh, int n_M, std::vector<u64>& proof, std::vector<u64>& comx, u64* g_host, bool sum_g = false) {
     const lf_plus_rg& I0 = *inst[0]; const size_t n = I0.n, kappa = I0.kappa, N = (size_t)1 << nvars, nE = 1 + (size_t)n_M; const int k = I0.k, l = I0.l, kd = k * PD;
     std::vector<DevSparse> Ms; std::vector<DevCsr> Mr; SetCheckResult R; std::vector<void*> blocks;
     struct Cleanup { Eng& E; std::vector<DevSparse>& a; std::vector<DevCsr>& b; SetCheckResult& r; std::vector<void*>& blk; ~Cleanup() { for (auto& s : a) s.free(E); for (auto& s : b) s.free(E); r.free(E); for (void* p : blk) E.dfree(p); } } cl{E, Ms, Mr, R, blocks};
@@ -417,52 +417,15 @@ void cm_prove_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* inst, int L, con
     if (g_host) { GArgs ga; for (int o = 0; o < PD; ++o) { ga.s0[o] = (short)to_small(ch.s[o]); ga.s1[o] = (short)to_small(ch.s[PD + o]); ga.s2m[o] = Fm::to_mont(ch.s[2 * PD + o]); }
         u64* d_g = alloc(n * PD);
         for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
-            E.launch("k_plus_g", [&] { k_plus_g<<<Eng::blocks_for(n, 128), 128, 0, E.st()>>>(I.tau, I.mtau_codes, I.f, d_h[li], n, ga, d_g); });
-            LF_CUDA(cudaMemcpyAsync(g_host + (size_t)li * n * PD, d_g, n * PD * 8, cudaMemcpyDeviceToHost, E.st())); E.sync(); } }
+            E.launch("k_plus_g", [&] { k_plus_g<<<Eng::blocks_for(n, 128), 128, 0, E.st()>>>(I.tau, I.mtau_codes, I.f, d_h[li], n, ga, sum_g && li > 0 ? 1 : 0, d_g); });
+            if (!sum_g || li == L - 1) { LF_CUDA(cudaMemcpyAsync(g_host + (sum_g ? 0 : (size_t)li * n * PD), d_g, n * PD * 8, cudaMemcpyDeviceToHost, E.st())); E.sync(); } } }
     for (auto* v : {&comh, &msgs[0], &msgs[1], &evals[0], &evals[1]}) proof.insert(proof.end(), v->begin(), v->end());
     std::vector<const u64*> fc(L); for (int li = 0; li < L; ++li) fc[li] = inst[li]->fcoms.data();
     comx = comx_words(ch.s.data(), L, kappa, nE, fc.data(), comh.data(), evals, ro);
 }
-}  // namespace
-
-extern "C" {
-
-void lf_transcript_get_challenge_base(lf_transcript* t, uint64_t* out1) { pguard(nullptr, [&] { *out1 = challenge(tr_of(t)); }); }
-
-lf_status lf_plus_set_check(lf_ctx* c, lf_transcript* t, int32_t nvars, const lf_plus_set* sets, int32_t n_sets, const lf_csr* M, int32_t n_M, uint64_t* out, uint64_t out_cap, uint64_t* out_len) {
-    return pguard(c, [&] {
-        need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
-        if (n_sets < 1 || !sets || n_M < 0 || (n_M && !M) || !out_len) throw LfException(LF_ERR_INVALID_ARG, "set check: null / empty arguments");
-        std::vector<DevSparse> store; store.reserve((size_t)n_sets + n_M); std::vector<DevSet> mats, vecs; std::vector<DevSparse> Ms; SetCheckResult R;
-        struct Cleanup { Eng& E; std::vector<DevSparse>& a; std::vector<DevSparse>& b; SetCheckResult& r; ~Cleanup() { for (auto& s : a) s.free(E); for (auto& s : b) s.free(E); r.free(E); } } cl{E, store, Ms, R};
-        for (int i = 0; i < n_sets; ++i) {
-            store.push_back(sets[i].kind == 0 ? upload_by_columns(E, sets[i].m) : upload_dense_vector(E, sets[i].v, sets[i].n));
-            DevSet s; s.gen = &store.back(); s.nrows = store.back().nrows; s.ncols = store.back().ncols; (sets[i].kind == 0 ? mats : vecs).push_back(s);
-        }
-        for (int i = 0; i < n_M; ++i) Ms.push_back(upload_by_columns(E, M[i]));
-        R = set_check_core(E, T, nvars, mats, vecs, Ms);
-        const std::vector<u64> w = R.words(); *out_len = w.size();
-        if (!out || out_cap < w.size()) throw LfException(LF_ERR_INVALID_ARG, "set check: output buffer too small");
-        std::memcpy(out, w.data(), w.size() * 8);
-    });
-}
-lf_status lf_plus_set_check_verify(lf_transcript* t, const uint64_t* words, uint64_t len) {
-    return pguard(nullptr, [&] { Tr& T = tr_of(t); verify_set_image(T, parse_set_image(words, len)); });
-}
-
-lf_status lf_plus_mat_create(lf_ctx* c, uint64_t kappa, uint64_t n, const uint64_t* host, lf_plus_mat** out) {
-    *out = nullptr;
-    return pguard(c, [&] { need_frog(c); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
-        if (!host || !kappa || !n) throw LfException(LF_ERR_INVALID_ARG, "matrix: null / empty"); check_canonical(host, kappa * n * PD, "matrix");
-        std::unique_ptr<lf_plus_mat> A(new lf_plus_mat); A->kappa = kappa; A->n = n; LF_CUDA(cudaMalloc(&A->d, kappa * n * PD * 8));
-        LF_CUDA(cudaMemcpyAsync(A->d, host, kappa * n * PD * 8, cudaMemcpyHostToDevice, E.st())); E.sync(); *out = A.release(); });
-}
-void lf_plus_mat_free(lf_ctx* c, lf_plus_mat* a) { if (a) { if (c) cudaStreamSynchronize(c->stream); cudaFree(a->d); delete a; } }
-
-lf_status lf_plus_rg_from_f(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, uint64_t n, uint64_t b, int32_t k, int32_t l, lf_plus_rg** out) {
-    *out = nullptr;
-    return pguard(c, [&] {
-        need_frog(c); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+// RgInstance::from_f (rgchk.rs:259-336)
+lf_plus_rg* rg_from_f_core(Eng& E, lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, uint64_t n, uint64_t b, int32_t k, int32_t l) {
+    {
         const bool tm = std::getenv("LF_PLUS_TIMING") != nullptr; auto t_last = std::chrono::steady_clock::now();      // diagnostic: phase times on stderr
         auto mark = [&](const char* what) { if (!tm) return; E.sync(); auto now = std::chrono::steady_clock::now(); std::fprintf(stderr, "from_f %-16s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count()); t_last = now; };
         if (!A || !f || n != A->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "from_f: witness length differs from the matrix width");
@@ -515,8 +478,48 @@ lf_status lf_plus_rg_from_f(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, 
         }
         E.sync(); E.dfree(cp);
         mark("commitments");
-        g.p = nullptr; *out = I.release();
+        g.p = nullptr; return I.release();
+    }
+}
+}  // namespace
+
+extern "C" {
+
+void lf_transcript_get_challenge_base(lf_transcript* t, uint64_t* out1) { pguard(nullptr, [&] { *out1 = challenge(tr_of(t)); }); }
+
+lf_status lf_plus_set_check(lf_ctx* c, lf_transcript* t, int32_t nvars, const lf_plus_set* sets, int32_t n_sets, const lf_csr* M, int32_t n_M, uint64_t* out, uint64_t out_cap, uint64_t* out_len) {
+    return pguard(c, [&] {
+        need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (n_sets < 1 || !sets || n_M < 0 || (n_M && !M) || !out_len) throw LfException(LF_ERR_INVALID_ARG, "set check: null / empty arguments");
+        std::vector<DevSparse> store; store.reserve((size_t)n_sets + n_M); std::vector<DevSet> mats, vecs; std::vector<DevSparse> Ms; SetCheckResult R;
+        struct Cleanup { Eng& E; std::vector<DevSparse>& a; std::vector<DevSparse>& b; SetCheckResult& r; ~Cleanup() { for (auto& s : a) s.free(E); for (auto& s : b) s.free(E); r.free(E); } } cl{E, store, Ms, R};
+        for (int i = 0; i < n_sets; ++i) {
+            store.push_back(sets[i].kind == 0 ? upload_by_columns(E, sets[i].m) : upload_dense_vector(E, sets[i].v, sets[i].n));
+            DevSet s; s.gen = &store.back(); s.nrows = store.back().nrows; s.ncols = store.back().ncols; (sets[i].kind == 0 ? mats : vecs).push_back(s);
+        }
+        for (int i = 0; i < n_M; ++i) Ms.push_back(upload_by_columns(E, M[i]));
+        R = set_check_core(E, T, nvars, mats, vecs, Ms);
+        const std::vector<u64> w = R.words(); *out_len = w.size();
+        if (!out || out_cap < w.size()) throw LfException(LF_ERR_INVALID_ARG, "set check: output buffer too small");
+        std::memcpy(out, w.data(), w.size() * 8);
     });
+}
+lf_status lf_plus_set_check_verify(lf_transcript* t, const uint64_t* words, uint64_t len) {
+    return pguard(nullptr, [&] { Tr& T = tr_of(t); verify_set_image(T, parse_set_image(words, len)); });
+}
+
+lf_status lf_plus_mat_create(lf_ctx* c, uint64_t kappa, uint64_t n, const uint64_t* host, lf_plus_mat** out) {
+    *out = nullptr;
+    return pguard(c, [&] { need_frog(c); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (!host || !kappa || !n) throw LfException(LF_ERR_INVALID_ARG, "matrix: null / empty"); check_canonical(host, kappa * n * PD, "matrix");
+        std::unique_ptr<lf_plus_mat> A(new lf_plus_mat); A->kappa = kappa; A->n = n; LF_CUDA(cudaMalloc(&A->d, kappa * n * PD * 8));
+        LF_CUDA(cudaMemcpyAsync(A->d, host, kappa * n * PD * 8, cudaMemcpyHostToDevice, E.st())); E.sync(); *out = A.release(); });
+}
+void lf_plus_mat_free(lf_ctx* c, lf_plus_mat* a) { if (a) { if (c) cudaStreamSynchronize(c->stream); cudaFree(a->d); delete a; } }
+
+lf_status lf_plus_rg_from_f(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, uint64_t n, uint64_t b, int32_t k, int32_t l, lf_plus_rg** out) {
+    *out = nullptr;
+    return pguard(c, [&] { need_frog(c); LF_CUDA(cudaSetDevice(c->device)); Eng E(c); *out = rg_from_f_core(E, c, A, f, n, b, k, l); });
 }
 lf_status lf_plus_rg_read(const lf_plus_rg* I, uint64_t* tau, uint64_t* fcoms, uint64_t* comM) {
     return pguard(nullptr, [&] { if (!I) throw LfException(LF_ERR_INVALID_ARG, "null instance");
@@ -635,6 +638,72 @@ lf_status lf_plus_cm_verify(lf_transcript* t, const uint64_t* w, uint64_t len, i
         }
         if (comx_out) { std::vector<const u64*> fc(L); for (size_t li = 0; li < L; ++li) fc[li] = dcom_evals + li * per + PD + nE + 2 * nE * PD;
             const std::vector<u64> xw = comx_words(ch.s.data(), L, kappa, nE, fc.data(), comh, evv, ro); std::memcpy(comx_out, xw.data(), xw.size() * 8); }
+    });
+}
+// Mlin::mlin (mlin.rs:41-106): from_f on every witness, Cm::prove, the sums over the instances.  linb2x = cm_g[kappa][16] | ro[nvars][2] | vo[1 + n_M][2][16]
+lf_status lf_plus_mlin(lf_ctx* c, lf_transcript* t, const lf_plus_mat* A, const uint64_t* fs, int32_t L, uint64_t n, uint64_t b, int32_t k, int32_t l, const lf_csr* M, int32_t n_M,
+                       uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* linb2x, uint64_t* g_host) {
+    return pguard(c, [&] {
+        need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (L < 1 || L > 64 || !fs || !A || n_M < 0 || (n_M && !M) || !proof_len || !linb2x) throw LfException(LF_ERR_INVALID_ARG, "mlin: null / empty arguments");
+        std::vector<lf_plus_rg*> inst; struct Cleanup { lf_ctx* c; std::vector<lf_plus_rg*>& v; ~Cleanup() { for (auto* p : v) lf_plus_rg_free(c, p); } } cl{c, inst};
+        for (int i = 0; i < L; ++i) inst.push_back(rg_from_f_core(E, c, A, fs + (size_t)i * n * PD, n, b, k, l));
+        const int nvars = plus_ceil_log2(n); const size_t kappa = A->kappa, nE = 1 + (size_t)n_M;
+        std::vector<u64> pw, xw; cm_prove_core(E, T, nvars, inst.data(), L, M, n_M, pw, xw, g_host, true);
+        // LinB2X: sums of the per-instance cm_g and vo, ro as it is
+        const u64 *cmg = xw.data(), *ro = cmg + (size_t)L * kappa * PD, *vo = ro + 2 * (size_t)nvars;
+        std::vector<u64> x(kappa * PD + 2 * (size_t)nvars + nE * 2 * PD, 0);
+        for (int li = 0; li < L; ++li) { for (size_t i = 0; i < kappa * PD; ++i) x[i] = Fm::add(x[i], cmg[(size_t)li * kappa * PD + i]);
+            for (size_t i = 0; i < nE * 2 * PD; ++i) x[kappa * PD + 2 * (size_t)nvars + i] = Fm::add(x[kappa * PD + 2 * (size_t)nvars + i], vo[(size_t)li * nE * 2 * PD + i]); }
+        std::memcpy(&x[kappa * PD], ro, 2 * (size_t)nvars * 8);
+        *proof_len = pw.size();
+        if (!proof || proof_cap < pw.size()) throw LfException(LF_ERR_INVALID_ARG, "mlin: proof buffer too small");
+        std::memcpy(proof, pw.data(), pw.size() * 8); std::memcpy(linb2x, x.data(), x.size() * 8);
+    });
+}
+// Decomp::decompose (decomp.rs:32-99).  r_pairs: nvars x 2 field elements (the points are constants of R on every path of the reference).
+// proof = C0[kappa][16] | C1 | v0[1 + n_M][2][16] | v1; F_host (2 x n x 16: the two LinB witnesses) may be NULL
+lf_status lf_plus_decompose(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, uint64_t n, const uint64_t* r_pairs, const lf_csr* M, int32_t n_M, uint64_t B, uint64_t* proof, uint64_t* F_host) {
+    return pguard(c, [&] {
+        need_frog(c); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (!A || !f || !r_pairs || !proof || n_M < 0 || (n_M && !M)) throw LfException(LF_ERR_INVALID_ARG, "decompose: null arguments");
+        if (n != A->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "decompose: witness length differs from the matrix width");
+        if (B < 2 || B >> 40) throw LfException(LF_ERR_INVALID_ARG, "decompose: base out of range");
+        const int nvars = plus_ceil_log2(n); const size_t N = (size_t)1 << nvars, kappa = A->kappa, nE = 1 + (size_t)n_M; check_canonical(r_pairs, 2 * (size_t)nvars, "decompose point");
+        std::vector<DevSparse> Ms; std::vector<void*> blocks;
+        struct Cleanup { Eng& E; std::vector<DevSparse>& a; std::vector<void*>& blk; ~Cleanup() { for (auto& s : a) s.free(E); for (void* p : blk) E.dfree(p); } } cl{E, Ms, blocks};
+        auto alloc = [&](size_t words) { u64* p = E.dalloc<u64>(words); blocks.push_back(p); return p; };
+        for (int i = 0; i < n_M; ++i) { Ms.push_back(upload_by_columns(E, M[i])); if (Ms.back().ncols != n || Ms.back().nrows > N) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "decompose: M_i does not match the witness"); }
+        u64 *d_f = alloc(n * PD), *F = alloc(2 * n * PD), *eq = alloc(2 * N), *cp = alloc(2); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
+        LF_CUDA(cudaMemcpyAsync(d_f, f, n * PD * 8, cudaMemcpyHostToDevice, E.st()));
+        E.launch("k_plus_split2", [&] { k_plus_split2<<<Eng::blocks_for(n * PD, 256), 256, 0, E.st()>>>(d_f, n * PD, (long long)B, F, F + n * PD, c->d_err); });
+        { int h = 0; LF_CUDA(cudaMemcpyAsync(&h, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, E.st())); E.sync();
+          if (h) { LF_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), E.st())); if (h == 3) throw LfException(LF_ERR_INVALID_ARG, "decompose: non-canonical field element"); throw LfException(LF_ERR_DOES_NOT_FIT, "decompose: a coefficient needs more than two digits in base B"); } }
+        std::vector<u64> pt[2]; for (int i = 0; i < nvars; ++i) { pt[0].push_back(r_pairs[2 * i]); pt[1].push_back(r_pairs[2 * i + 1]); }
+        eq_table(E, pt[0], eq, N); eq_table(E, pt[1], eq + N, N);
+        std::vector<u64*> w[2]; for (int q = 0; q < 2; ++q) for (auto& m : Ms) { u64* wv = alloc(n * PD);
+            E.launch("k_plus_mt_eq", [&] { k_plus_mt_eq<<<Eng::blocks_for(m.ncols, 128), 128, 0, E.st()>>>(eq + q * N, m.col_ptr, m.erow, m.val, m.ncols, wv); }); w[q].push_back(wv); }
+        u64 *C = proof, *v = proof + 2 * kappa * PD;
+        for (int z = 0; z < 2; ++z) { const u64* Fz = F + (size_t)z * n * PD;
+            for (size_t r = 0; r < kappa; ++r) { const unsigned ch = chunks_for(n, 128); u64* partial = E.partial_dev((size_t)ch * PD);      // C_z = A F_z
+                E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(A->d + r * n * PD, cp, nullptr, Fz, partial); }); finish_wsum(E, partial, ch, 1, 2, C + ((size_t)z * kappa + r) * PD); }
+            for (size_t e = 0; e < nE; ++e) for (int q = 0; q < 2; ++q) { u64* out = v + (((size_t)z * nE + e) * 2 + q) * PD;      // (MLE(.)(r_a), MLE(.)(r_b)) of F_z and of every M_j F_z
+                if (e == 0) { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+                    E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, 1), 256, 0, E.st()>>>(eq + q * N, cp, nullptr, Fz, partial); }); finish_wsum(E, partial, ch, 1, 0, out); }
+                else { const unsigned ch = chunks_for(n, 128); u64* partial = E.partial_dev((size_t)ch * PD);
+                    E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(w[q][e - 1], cp, nullptr, Fz, partial); }); finish_wsum(E, partial, ch, 1, 2, out); } }
+        }
+        if (F_host) { LF_CUDA(cudaMemcpyAsync(F_host, F, 2 * n * PD * 8, cudaMemcpyDeviceToHost, E.st())); E.sync(); }
+    });
+}
+// DecompProof::verify (decomp.rs:102-126), host: recompose([C0, C1], B) = cm_f and the same for every evaluation pair.  LF_ERR_RECOMPOSED on mismatch
+lf_status lf_plus_decompose_verify(const uint64_t* proof, uint64_t kappa, int32_t n_M, const uint64_t* cm_f, const uint64_t* v, uint64_t B) {
+    return pguard(nullptr, [&] {
+        if (!proof || !cm_f || !v || n_M < 0 || !kappa) throw LfException(LF_ERR_INVALID_ARG, "decompose verify: null arguments");
+        const size_t nc = kappa * PD, nv = (size_t)(1 + n_M) * 2 * PD; const u64 Bm = B % Fm::P;
+        check_canonical(proof, 2 * nc + 2 * nv, "decomposition proof"); check_canonical(cm_f, nc, "cm_f"); check_canonical(v, nv, "v");
+        for (size_t i = 0; i < nc; ++i) if (Fm::add(proof[i], Fm::hmul(proof[nc + i], Bm)) != cm_f[i]) throw LfException(LF_ERR_RECOMPOSED, "decompose verify: commitments do not recompose");
+        for (size_t i = 0; i < nv; ++i) if (Fm::add(proof[2 * nc + i], Fm::hmul(proof[2 * nc + nv + i], Bm)) != v[i]) throw LfException(LF_ERR_RECOMPOSED, "decompose verify: evaluations do not recompose");
     });
 }
 lf_status lf_plus_tensor(const uint64_t* r, int32_t n, uint64_t* out) {

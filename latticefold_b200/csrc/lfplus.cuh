@@ -364,7 +364,7 @@ __global__ void k_plus_fold_ring(const u64* __restrict__ in, size_t in_len, u64*
 }
 // g[x] = s0 tau[x] + s1 m_tau[x] + s2 f[x] + h[x] (cm.rs:165-182): s small (|.| <= 128); s2 f is the only real ring product
 struct GArgs { short s0[PD], s1[PD]; u64 s2m[PD]; };      // s2 in Montgomery form
-__global__ void __launch_bounds__(128) k_plus_g(const signed char* __restrict__ tau, const unsigned char* __restrict__ mcode, const u64* __restrict__ f, const u64* __restrict__ h, size_t n, GArgs a, u64* __restrict__ g) {
+__global__ void __launch_bounds__(128) k_plus_g(const signed char* __restrict__ tau, const unsigned char* __restrict__ mcode, const u64* __restrict__ f, const u64* __restrict__ h, size_t n, GArgs a, int accumulate, u64* __restrict__ g) {
     const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n) return;
     u64 acc[PD], v[PD];
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(128) k_plus_g(const signed char* __restrict__ 
         v[0] = Fm::neg(top);
     }
 #pragma unroll
-    for (int o = 0; o < PD; ++o) g[x * PD + o] = acc[o];
+    for (int o = 0; o < PD; ++o) g[x * PD + o] = accumulate ? Fm::add(g[x * PD + o], acc[o]) : acc[o];      // (Mlin::mlin sums the instances' g, mlin.rs:97-103)
 }
 // S[x] = sum_l tau_l[x] in Montgomery form (the scalar factor of the t(z) terms, cm.rs:303-304)
 struct TauList { const signed char* p[64]; int n; };
@@ -396,6 +396,18 @@ __global__ void k_plus_tau_sum(TauList tl, size_t n, SmallArgs sm, u64* __restri
         for (int k = 0; k < 16; ++k) if ((t & 15) == k) s = sm.v[k];
         v = Fm::add(v, s); }
     S[x] = v;
+}
+
+// Decomp::decompose (decomp.rs:37-40): every coefficient of f -> two balanced base-B digits, F0 and F1 as canonical field elements
+__global__ void k_plus_split2(const u64* __restrict__ f, size_t words, long long B, u64* __restrict__ F0, u64* __restrict__ F1, int* __restrict__ err) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= words) return;
+    const u64 v = f[i];
+    if (v >= Fm::P) { atomicExch(err, 3); return; }
+    const bool negv = v > (Fm::P - 1) / 2; const u64 mag = negv ? Fm::P - v : v;
+    int64_t dg[2];
+    if (!balanced_digits(negv ? -(int64_t)mag : (int64_t)mag, B, 2, dg)) { atomicExch(err, 1); return; }
+    F0[i] = dg[0] < 0 ? Fm::P - (u64)(-dg[0]) : (u64)dg[0]; F1[i] = dg[1] < 0 ? Fm::P - (u64)(-dg[1]) : (u64)dg[1];
 }
 
 } }  // namespace lf::plus

@@ -15,7 +15,7 @@ RING = synth.RING_FROG
 D = 16
 SYMBOLS = """lf_transcript_get_challenge_base lf_plus_set_check lf_plus_set_check_verify lf_plus_mat_create lf_plus_mat_free
 lf_plus_rg_from_f lf_plus_rg_read lf_plus_rg_free lf_plus_range_check lf_plus_range_check_verify lf_plus_tensor
-lf_plus_comx_words lf_plus_cm_prove lf_plus_cm_verify""".split()
+lf_plus_comx_words lf_plus_cm_prove lf_plus_cm_verify lf_plus_mlin lf_plus_decompose lf_plus_decompose_verify""".split()
 
 
 class PlusSet(C.Structure):      # lf_plus_set
@@ -44,6 +44,9 @@ def _L():
         L.lf_plus_comx_words.argtypes = [C.c_int32, C.c_int32, C.c_uint64, C.c_int32]
         L.lf_plus_cm_prove.argtypes = [vp, vp, C.c_int32, C.POINTER(vp), C.c_int32, C.POINTER(Csr), C.c_int32, u64p, C.c_uint64, u64p, u64p, u64p]
         L.lf_plus_cm_verify.argtypes = [vp, u64p, C.c_uint64, C.c_int32, u64p]
+        L.lf_plus_mlin.argtypes = [vp, vp, vp, u64p, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(Csr), C.c_int32, u64p, C.c_uint64, u64p, u64p, u64p]
+        L.lf_plus_decompose.argtypes = [vp, vp, u64p, C.c_uint64, u64p, C.POINTER(Csr), C.c_int32, C.c_uint64, u64p, u64p]
+        L.lf_plus_decompose_verify.argtypes = [u64p, C.c_uint64, C.c_int32, u64p, u64p, C.c_uint64]
         _ready = True
     return L
 
@@ -197,6 +200,40 @@ def cm_verify(words, n_M, transcript, nvars=None, L=1, kappa=1):      # CmProof:
     if rc in (0, -10, -11):
         return rc == 0, (comx if rc == 0 else None)
     raise LfError(rc, "cm proof image rejected as malformed")
+
+
+class Mlin:
+    """mlin.rs:15-19: L witnesses `fs` (L x n x 16) folded by Cm::prove; `mlin` returns (CmProof image, LinB2X dict, g[n, 16])."""
+
+    def __init__(self, ctx, fs, b, k, l):
+        self.ctx, self.fs, self.b, self.k, self.l = ctx, np.ascontiguousarray(fs, dtype=np.uint64), b, k, l
+
+    def mlin(self, A, M, transcript, want_g=True):      # mlin.rs:41-106
+        L_ = _L()
+        Lc, n, d = self.fs.shape; nE, nv = 1 + len(M), int(n - 1).bit_length()
+        ma = _csr_array(list(M))
+        x = np.zeros(A.kappa * d + 2 * nv + nE * 2 * d, dtype=np.uint64)
+        g = np.zeros((n, d), dtype=np.uint64) if want_g else None
+        proof = _grow(self.ctx, lambda o, cap, ln: L_.lf_plus_mlin(self.ctx.h, transcript.h, A.h, ptr(self.fs), Lc, n, self.b, self.k, self.l, ma, len(M), o, cap, ln, ptr(x), ptr(g)))
+        kd = A.kappa * d
+        return proof, dict(cm_g=x[:kd].reshape(A.kappa, d).copy(), ro=x[kd: kd + 2 * nv].reshape(nv, 2).copy(), vo=x[kd + 2 * nv:].reshape(nE, 2, d).copy()), g
+
+
+def decompose(ctx, A, f, r_pairs, M, B, want_F=True):      # Decomp::decompose, decomp.rs:32-99 -> (DecompProof words, F[2, n, 16])
+    f, r_pairs = np.ascontiguousarray(f, dtype=np.uint64), np.ascontiguousarray(r_pairs, dtype=np.uint64)
+    n, d = f.shape
+    ma = _csr_array(list(M))
+    proof = np.zeros(2 * A.kappa * d + 2 * (1 + len(M)) * 2 * d, dtype=np.uint64)
+    F = np.zeros((2, n, d), dtype=np.uint64) if want_F else None
+    ctx.check(_L().lf_plus_decompose(ctx.h, A.h, ptr(f), n, ptr(r_pairs), ma, len(M), B, ptr(proof), ptr(F)))
+    return proof, F
+
+
+def decompose_verify(proof, kappa, n_M, cm_f, v, B):      # DecompProof::verify, decomp.rs:102-126
+    rc = _L().lf_plus_decompose_verify(ptr(np.ascontiguousarray(proof, dtype=np.uint64)), kappa, n_M, ptr(np.ascontiguousarray(cm_f, dtype=np.uint64)), ptr(np.ascontiguousarray(v, dtype=np.uint64)), B)
+    if rc in (0, -11):
+        return rc == 0
+    raise LfError(rc, "decomposition proof rejected as malformed")
 
 
 def tensor(r):      # utils.rs:74-86

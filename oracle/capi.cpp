@@ -328,4 +328,33 @@ int lfo_plus_mat_vec(int id, const u64* A, size_t kappa, size_t n, const u64* x,
     return guard([&] { const RingParams& R = ring(id); auto y = plus::mat_mul_vec(R, Vec(A, A + kappa * n * R.d), kappa, n, Vec(x, x + n * R.d)); memcpy(out, y.data(), 8 * y.size()); });
 }
 
+
+// Mlin::mlin: linb2x = cm_g[kappa x d] ro[nvars x 2] vo[(1+n_M) x 2 x d]; g[n x d]; returns the CmProof image length
+long lfo_plus_mlin(int id, int L, const u64* f, size_t n, const u64* A, size_t kappa, u64 b, int k, int l, const lfo_csr* M, int n_M, const u64* seed, size_t n_seed,
+                   u64* proof, size_t cap, u64* linb2x, u64* g) {
+    long nw = -1; int rc = guard([&] { const RingParams& R = ring(id); const size_t d = R.d; plus::DecompParameters dp{b, k, l};
+        std::vector<Vec> fs; for (int i = 0; i < L; ++i) fs.emplace_back(f + (size_t)i * n * d, f + (size_t)(i + 1) * n * d);
+        std::vector<plus::SparseR> Ms; for (int i = 0; i < n_M; ++i) Ms.push_back(sparse_of(R, M[i]));
+        auto T = plus_transcript(R, seed, n_seed); plus::CmProof P;
+        plus::LinB2 o = plus::mlin(R, fs, Vec(A, A + kappa * n * d), kappa, dp, Ms, T, P);
+        auto w = plus::cm_proof_words(R, P); nw = (long)w.size(); if (w.size() <= cap) memcpy(proof, w.data(), 8 * w.size());
+        if (linb2x) { u64* p = linb2x; for (auto* v : {&o.cm_g, &o.ro, &o.vo}) { memcpy(p, v->data(), 8 * v->size()); p += v->size(); } }
+        if (g) memcpy(g, o.g.data(), 8 * o.g.size()); });
+    return rc ? rc : nw;
+}
+// Decomp::decompose: proof = C0 C1 [kappa x d each] v0 v1 [(1+n_M) x 2 x d each]; F = 2 x n x d (optional)
+int lfo_plus_decompose(int id, const u64* f, size_t n, const u64* r_pairs, const lfo_csr* M, int n_M, const u64* A, size_t kappa, u64 B, u64* proof, u64* F) {
+    return guard([&] { const RingParams& R = ring(id); const size_t d = R.d; int nv = plus::ceil_log2(n);
+        std::vector<plus::SparseR> Ms; for (int i = 0; i < n_M; ++i) Ms.push_back(sparse_of(R, M[i]));
+        Vec Fs[2]; plus::DecompProof P = plus::decompose(R, Vec(f, f + n * d), Vec(r_pairs, r_pairs + 2 * nv), Ms, Vec(A, A + kappa * n * d), kappa, B, Fs);
+        u64* p = proof; for (auto* v : {&P.C[0], &P.C[1], &P.v[0], &P.v[1]}) { memcpy(p, v->data(), 8 * v->size()); p += v->size(); }
+        if (F) { memcpy(F, Fs[0].data(), 8 * n * d); memcpy(F + n * d, Fs[1].data(), 8 * n * d); } });
+}
+int lfo_plus_decompose_verify(int id, const u64* proof, size_t kappa, int n_M, const u64* cm_f, const u64* v, u64 B) {
+    int ok = 0; int rc = guard([&] { const RingParams& R = ring(id); const size_t d = R.d, nc = kappa * d, nv = (size_t)(1 + n_M) * 2 * d; plus::DecompProof P;
+        P.C[0].assign(proof, proof + nc); P.C[1].assign(proof + nc, proof + 2 * nc); P.v[0].assign(proof + 2 * nc, proof + 2 * nc + nv); P.v[1].assign(proof + 2 * nc + nv, proof + 2 * nc + 2 * nv);
+        ok = plus::decompose_verify(R, P, Vec(cm_f, cm_f + nc), Vec(v, v + nv), B) ? 1 : 0; });
+    return rc ? rc : ok;
+}
+
 }  // extern "C"

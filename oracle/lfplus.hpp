@@ -10,6 +10,9 @@
 //   crates/latticefold-plus/src/rgchk.rs:75-187       Rg::range_check
 //   crates/latticefold-plus/src/rgchk.rs:190-246      Dcom::verify
 //   crates/latticefold-plus/src/rgchk.rs:259-336      RgInstance::from_f (double commitment)
+//   crates/latticefold-plus/src/cm.rs:57-601          Cm::prove, sumchecker, CmProof::verify, ComX, calculate_t_z
+//   crates/latticefold-plus/src/mlin.rs:41-106        Mlin::mlin
+//   crates/latticefold-plus/src/decomp.rs:32-127      Decomp::decompose, DecompProof::verify
 //   crates/latticefold/src/utils/sumcheck.rs:53-104, sumcheck/prover.rs:56-162, sumcheck/verifier.rs:92-254 (generic over R: OverField)
 // Third-party pieces restated from their published definition (stark-rings @ 886a89f, not in the tree):
 //   exp(a) = sgn(a) X^a = X^(a mod d) for |a| < d/2, psi = sum_{0<i<d/2} i (X^{-i} + X^i), ct = constant coefficient
@@ -590,5 +593,42 @@ inline void cm_proof_parse(const RingParams& R, const u64* w, size_t len, CmProo
 }
 // ComX image: cm_g[L x kappa x d] ro[nvars x 2] vo[L x (1+n_M) x 2 x d]
 inline std::vector<u64> comx_words(const ComX& X) { std::vector<u64> w = X.cm_g; w.insert(w.end(), X.ro.begin(), X.ro.end()); w.insert(w.end(), X.vo.begin(), X.vo.end()); return w; }
+
+// ---------------------------------------------------------------- mlin.rs / decomp.rs
+struct LinB2 { std::vector<u64> g /* n x d */, cm_g /* kappa x d */, ro /* nvars x 2 */, vo /* (1+n_M) x 2 x d */; };
+// Mlin::mlin (mlin.rs:41-106): from_f on every f, Cm::prove, then the sums over the instances
+inline LinB2 mlin(const RingParams& R, const std::vector<std::vector<u64>>& fs, const std::vector<u64>& A, size_t kappa, const DecompParameters& dp, const std::vector<SparseR>& M, PlusTranscript& T, CmProof& P) {
+    const int d = R.d; const size_t n = fs[0].size() / d, L = fs.size(), nE = 1 + M.size();
+    std::vector<RgInstance> inst; for (auto& f : fs) inst.push_back(rg_from_f(R, f, A, kappa, dp));
+    Com com; cm_prove(R, ceil_log2(n), inst, dp, M, T, com, P);
+    LinB2 o; o.cm_g.assign(kappa * d, 0); o.vo.assign(nE * 2 * d, 0); o.g.assign(n * d, 0); o.ro = com.x.ro;
+    for (size_t l = 0; l < L; ++l) {
+        for (size_t i = 0; i < kappa * d; ++i) o.cm_g[i] = R.F.add(o.cm_g[i], com.x.cm_g[l * kappa * d + i]);
+        for (size_t i = 0; i < nE * 2 * d; ++i) o.vo[i] = R.F.add(o.vo[i], com.x.vo[l * nE * 2 * d + i]);
+        for (size_t i = 0; i < n * d; ++i) o.g[i] = R.F.add(o.g[i], com.g[l * n * d + i]); }
+    return o;
+}
+struct DecompProof { std::vector<u64> C[2] /* kappa x d */, v[2] /* (1+n_M) x 2 x d */; };
+// Decomp::decompose (decomp.rs:32-99): F = decompose_to_vec(f, B, 2); v_i over [F_i, M_j F_i] at the two points; C_i = A F_i.  r: nvars x 2 (constants of R)
+inline DecompProof decompose(const RingParams& R, const std::vector<u64>& f, const std::vector<u64>& r, const std::vector<SparseR>& M, const std::vector<u64>& A, size_t kappa, u128 B, std::vector<u64> F[2]) {
+    const int d = R.d; const size_t n = f.size() / d; const int nvars = ceil_log2(n); DecompProof P; i128 dg[2];
+    F[0].assign(n * d, 0); F[1].assign(n * d, 0);
+    for (size_t i = 0; i < n * d; ++i) { decompose_balanced(R.F, f[i], B, 2, dg); F[0][i] = R.F.from_i128(dg[0]); F[1][i] = R.F.from_i128(dg[1]); }
+    std::vector<u64> ra(nvars), rb(nvars); for (int i = 0; i < nvars; ++i) { ra[i] = r[2 * i]; rb[i] = r[2 * i + 1]; }
+    for (int z = 0; z < 2; ++z) {
+        auto two = [&](const std::vector<u64>& tbl) { u64 o[64]; PMle m; m.nv = nvars; m.ev = tbl; pm_evaluate(R, m, ra.data(), nvars, o); P.v[z].insert(P.v[z].end(), o, o + d); pm_evaluate(R, std::move(m), rb.data(), nvars, o); P.v[z].insert(P.v[z].end(), o, o + d); };
+        two(F[z]); for (auto& m : M) two(sp_mul_vec(R, m, F[z]));
+        P.C[z] = mat_mul_vec(R, A, kappa, n, F[z]);
+    }
+    return P;
+}
+// DecompProof::verify (decomp.rs:102-126): recompose([C0, C1], B) = cm_f and recompose of the evaluation pairs = v
+inline bool decompose_verify(const RingParams& R, const DecompProof& P, const std::vector<u64>& cm_f, const std::vector<u64>& v, u128 B) {
+    const u64 Bm = (u64)(B % R.F.p);
+    if (P.C[0].size() != cm_f.size() || P.v[0].size() != v.size()) return false;
+    for (size_t i = 0; i < cm_f.size(); ++i) if (R.F.add(P.C[0][i], R.F.mul(P.C[1][i], Bm)) != cm_f[i]) return false;
+    for (size_t i = 0; i < v.size(); ++i) if (R.F.add(P.v[0][i], R.F.mul(P.v[1][i], Bm)) != v[i]) return false;
+    return true;
+}
 
 } }  // namespace lfo::plus

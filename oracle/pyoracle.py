@@ -326,6 +326,10 @@ class Oracle:
         L.lfo_plus_cm_prove.argtypes = [C.c_int, C.c_int, C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, C.c_int, C.c_int, C.POINTER(Csr), C.c_int, u64p, C.c_size_t,
                                         u64p, C.c_size_t, u64p, C.c_size_t, u64p]
         L.lfo_plus_cm_verify.argtypes = [C.c_int, u64p, C.c_size_t, C.POINTER(Csr), C.c_int, u64p, C.c_size_t, u64p, C.c_size_t]
+        L.lfo_plus_mlin.restype = C.c_long
+        L.lfo_plus_mlin.argtypes = [C.c_int, C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, C.c_int, C.c_int, C.POINTER(Csr), C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, u64p, u64p]
+        L.lfo_plus_decompose.argtypes = [C.c_int, u64p, C.c_size_t, u64p, C.POINTER(Csr), C.c_int, u64p, C.c_size_t, C.c_uint64, u64p, u64p]
+        L.lfo_plus_decompose_verify.argtypes = [C.c_int, u64p, C.c_size_t, C.c_int, u64p, u64p, C.c_uint64]
         L.lfo_plus_mat_vec.argtypes = [C.c_int, u64p, C.c_size_t, C.c_size_t, u64p, u64p]
         L.lfo_plus_tensor.argtypes = [C.c_int, u64p, C.c_int, u64p]
         L.lfo_plus_ring_mul.argtypes = [C.c_int, u64p, u64p, u64p]
@@ -415,6 +419,33 @@ class Oracle:
         if rc < 0:
             raise OracleError(rc, self.err())
         return bool(rc), (comx if rc else None)
+
+    def plus_mlin(self, ring, fs, A, b, k, l, M=(), seed=None):
+        """Mlin::mlin: (CmProof image, dict(cm_g[kappa, d], ro[nvars, 2], vo[1 + n_M, 2, d]), g[n, d])"""
+        self._plus_setup()
+        fs, A = np.ascontiguousarray(fs), np.ascontiguousarray(A)
+        Lc, n, d = fs.shape; kappa, nE, nv = A.shape[0], 1 + len(M), int(n - 1).bit_length()
+        ma = make_csr_array(list(M)); sd, sp, sn = self._seed(seed)
+        x = np.zeros(kappa * d + 2 * nv + nE * 2 * d, dtype=np.uint64); g = np.zeros((n, d), dtype=np.uint64)
+        proof = self._plus_call(lambda out, cap: self.lib.lfo_plus_mlin(ring, Lc, ptr(fs), n, ptr(A), kappa, b, k, l, ma, len(M), sp, sn, ptr(out), cap, ptr(x), ptr(g)))
+        return proof, dict(cm_g=x[: kappa * d].reshape(kappa, d).copy(), ro=x[kappa * d: kappa * d + 2 * nv].reshape(nv, 2).copy(), vo=x[kappa * d + 2 * nv:].reshape(nE, 2, d).copy()), g
+
+    def plus_decompose(self, ring, f, r_pairs, A, B, M=()):
+        """Decomp::decompose: (proof words = C0 | C1 | v0 | v1, F[2, n, d])"""
+        self._plus_setup()
+        f, A, r_pairs = np.ascontiguousarray(f), np.ascontiguousarray(A), np.ascontiguousarray(r_pairs, dtype=np.uint64)
+        n, d = f.shape; kappa, nE = A.shape[0], 1 + len(M)
+        ma = make_csr_array(list(M))
+        proof = np.zeros(2 * kappa * d + 2 * nE * 2 * d, dtype=np.uint64); F = np.zeros((2, n, d), dtype=np.uint64)
+        self.check(self.lib.lfo_plus_decompose(ring, ptr(f), n, ptr(r_pairs), ma, len(M), ptr(A), kappa, B, ptr(proof), ptr(F)))
+        return proof, F
+
+    def plus_decompose_verify(self, ring, proof, kappa, n_M, cm_f, v, B):
+        self._plus_setup()
+        rc = self.lib.lfo_plus_decompose_verify(ring, ptr(np.ascontiguousarray(proof)), kappa, n_M, ptr(np.ascontiguousarray(cm_f)), ptr(np.ascontiguousarray(v)), B)
+        if rc < 0:
+            raise OracleError(rc, self.err())
+        return bool(rc)
 
     def plus_mat_vec(self, ring, A, x):
         self._plus_setup()

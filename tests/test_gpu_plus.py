@@ -149,3 +149,24 @@ def test_commitment_transformation_at_benchmark_size(ctx, oracle):
     assert plus.cm_verify(proof, 0, seeded(), nvars=nvars, L=1, kappa=kappa)[0]
     assert oracle.plus_cm_verify(RING, proof, [])[0]
     assert np.array_equal(oracle.plus_mat_vec(RING, A, g[0]), comx[: kappa * 16].reshape(kappa, 16))
+
+
+@pytest.mark.parametrize("L,n_M", [(2, 2), (3, 0)])
+def test_mlin_and_decompose_bit_exact(ctx, oracle, L, n_M):      # mlin.rs:41-106, decomp.rs:32-127 (the data flow of test_decomp_g from the folded instances on)
+    n, kappa, k, l = 1 << 15, 2, 2, pc.frog_l()
+    fs, A = pc.range_check_inputs(n, kappa, seed=50 + L, L=L)
+    m = pc.identity(n); m["val"] = m["val"].copy(); m["val"][0, 0] = 2
+    M = [m, pc.random_ring_sparse(n, n, 2, 51, constant=True)][:n_M]
+    Ad = plus.Matrix(ctx, A)
+    proof, x, g = plus.Mlin(ctx, fs, 8, k, l).mlin(Ad, M, seeded([3]))
+    oproof, ox, og = oracle.plus_mlin(RING, fs, A, 8, k, l, M, seed=[3])
+    assert np.array_equal(proof, oproof) and np.array_equal(g, og) and all(np.array_equal(x[key], ox[key]) for key in ("cm_g", "ro", "vo"))
+    assert plus.cm_verify(proof, len(M), seeded([3]))[0]
+    for B in (int(pc.P_FROG ** 0.5) + 2, 1 << 12):      # decomp.rs:190-193, and a base that makes both digits non-trivial
+        dproof, F = plus.decompose(ctx, Ad, g, x["ro"], M, B)
+        odproof, oF = oracle.plus_decompose(RING, g, x["ro"], A, B, M)
+        assert np.array_equal(dproof, odproof) and np.array_equal(F, oF)
+        assert plus.decompose_verify(dproof, kappa, len(M), x["cm_g"], x["vo"], B) and oracle.plus_decompose_verify(RING, dproof, kappa, len(M), x["cm_g"], x["vo"], B)
+    with pytest.raises(lf.LfError) as e:      # two digits in base 4 cannot hold g
+        plus.decompose(ctx, Ad, g, x["ro"], M, 4)
+    assert e.value.code == -9

@@ -116,3 +116,31 @@ def test_commitment_transformation(oracle, kappa, with_M, L):      # cm.rs:621-6
     cmg = comx[: L * kappa * 16].reshape(L, kappa, 16)
     for li in range(L):
         assert np.array_equal(oracle.plus_mat_vec(RING, A, g[li]), cmg[li])
+
+
+def mlin_inputs(n, kappa, L, seed):
+    fs, A = pc.range_check_inputs(n, kappa, seed=seed, L=L)
+    m = pc.identity(n); m["val"] = m["val"].copy(); m["val"][0, 0] = 2
+    return fs, A, [m, pc.random_ring_sparse(n, n, 2, seed + 1, constant=True)]
+
+
+def test_mlin_then_decompose(oracle):      # the data flow of decomp.rs:189-268 (test_decomp_g) from the folded instances on: mlin -> CmProof::verify -> decompose -> DecompProof::verify
+    n, kappa, k, l, L = 1 << 15, 2, 2, pc.frog_l(), 2
+    fs, A, M = mlin_inputs(n, kappa, L, 41)
+    proof, x, g = oracle.plus_mlin(RING, fs, A, 8, k, l, M)
+    ok, comx = oracle.plus_cm_verify(RING, proof, M, nvars=15, L=L, kappa=kappa)
+    assert ok
+    cmg = comx[: L * kappa * 16].reshape(L, kappa, 16)      # LinB2X sums the per-instance ComX
+    assert [[int(v) for v in row] for row in x["cm_g"]] == [[sum(int(cmg[li, r, c]) for li in range(L)) % pc.P_FROG for c in range(16)] for r in range(kappa)]
+    assert np.array_equal(oracle.plus_mat_vec(RING, A, g), x["cm_g"])
+    B = int(pc.P_FROG ** 0.5) + 2      # decomp.rs:190-193
+    for Bv in (B, 1 << 12):
+        dproof, F = oracle.plus_decompose(RING, g, x["ro"], A, Bv, M)
+        assert oracle.plus_decompose_verify(RING, dproof, kappa, len(M), x["cm_g"], x["vo"], Bv)
+        t = dproof.copy(); t[3] = (int(t[3]) + 1) % pc.P_FROG
+        assert not oracle.plus_decompose_verify(RING, t, kappa, len(M), x["cm_g"], x["vo"], Bv)
+        t = dproof.copy(); t[-1] = (int(t[-1]) + 1) % pc.P_FROG
+        assert not oracle.plus_decompose_verify(RING, t, kappa, len(M), x["cm_g"], x["vo"], Bv)
+        # F0 + B F1 = g, digits inside the balanced range
+        rec = (F[0].astype(object) + Bv * F[1].astype(object)) % pc.P_FROG
+        assert np.array_equal(rec.astype(np.uint64), g)

@@ -91,3 +91,18 @@ def test_product_verifier_on_oracle_cm(oracle, kappa, with_M, L):      # cm.rs:6
     assert not plus.cm_verify(proof, len(M), seeded(None))[0]
     with pytest.raises(plus.LfError):
         plus.cm_verify(proof[:-3], len(M), seeded([6]))
+
+
+def test_product_decompose_verify_on_oracle_proof(oracle):
+    n, kappa, k, l, L = 1 << 15, 2, 2, pc.frog_l(), 2
+    fs, A = pc.range_check_inputs(n, kappa, seed=41, L=L)
+    m = pc.identity(n); m["val"] = m["val"].copy(); m["val"][0, 0] = 2
+    M = [m]
+    proof, x, g = oracle.plus_mlin(RING, fs, A, 8, k, l, M)
+    B = 1 << 12      # both digits non-trivial (with the reference's B = sqrt(q) the high digit of g is zero)
+    dproof, _ = oracle.plus_decompose(RING, g, x["ro"], A, B, M)
+    assert plus.decompose_verify(dproof, kappa, len(M), x["cm_g"], x["vo"], B)
+    for pos in (0, dproof.size - 1, 2 * kappa * 16 + 3):
+        t = dproof.copy(); t[pos] = (int(t[pos]) + 1) % pc.P_FROG
+        assert not plus.decompose_verify(t, kappa, len(M), x["cm_g"], x["vo"], B)
+    assert not plus.decompose_verify(dproof, kappa, len(M), x["cm_g"], x["vo"], B + 1)
