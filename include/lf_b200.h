@@ -329,6 +329,12 @@ lf_status lf_plus_cm_prove(lf_ctx* ctx, lf_transcript* t, int32_t nvars, lf_plus
                            uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* comx, uint64_t* g_host);
 /* CmProof::verify                            cm.rs:349-535 (host; only the number of matrices is read from M there).  comx_out may be NULL */
 lf_status lf_plus_cm_verify(lf_transcript* t, const uint64_t* proof, uint64_t len, int32_t n_M, uint64_t* comx_out);
+/* ComR1CS::linearize                         r1cs.rs:72-134: g* = A|B|C f, the degree-3 sumcheck of eq(r, x) (ga gb - gc) over ring-valued tables
+ * (real negacyclic products) and the evaluations at its point.  image = [nvars] ro[nvars] messages[nvars][4][16] v[16] va vb vc;
+ * the LinB the reference returns is (f, cm_f, r = (ro, ro), v = the four evaluations twice)                                             */
+lf_status lf_plus_r1cs_linearize(lf_ctx* ctx, lf_transcript* t, const lf_csr* abc /* A, B, C */, const uint64_t* f, uint64_t n, uint64_t* out, uint64_t out_cap, uint64_t* out_len);
+/* ComR1CSProof::verify                       r1cs.rs:136-162 (host)                                                                    */
+lf_status lf_plus_r1cs_linearize_verify(lf_transcript* t, const uint64_t* words, uint64_t len);
 /* Mlin::mlin                                 mlin.rs:41-106: from_f on each of the L witnesses (fs: L x n x 16), Cm::prove, and the sums
  * over the instances.  linb2x (LinB2X) = cm_g[kappa][16] | ro[nvars][2] | vo[1 + n_M][2][16]; g_host (n x 16, LinB2::g) may be NULL     */
 lf_status lf_plus_mlin(lf_ctx* ctx, lf_transcript* t, const lf_plus_mat* A, const uint64_t* fs, int32_t L, uint64_t n, uint64_t b, int32_t k, int32_t l,

@@ -481,6 +481,59 @@ lf_plus_rg* rg_from_f_core(Eng& E, lf_ctx* c, const lf_plus_mat* A, const uint64
         g.p = nullptr; return I.release();
     }
 }
+
+// MLSumcheck::verify_as_subprotocol (sumcheck.rs:84-104, verifier.rs:92-123) on ring-valued messages with base-field challenges
+void sumcheck_verify_host(Tr& T, size_t nv, int deg, const u64* claimed, const u64* msgs, std::vector<u64>& point, u64* expected) {
+    const int ne = deg + 1;
+    absorb_field(T, (u64)nv); absorb_field(T, (u64)deg); point.clear();
+    for (size_t i = 0; i < nv; ++i) { T.absorb_slice(msgs + i * ne * PD, ne); const u64 r = challenge(T); point.push_back(r); absorb_field(T, r); }
+    std::memcpy(expected, claimed, 8 * PD);
+    for (size_t i = 0; i < nv; ++i) { const u64* msg = msgs + i * ne * PD;
+        for (int c = 0; c < PD; ++c) if (Fm::add(msg[c], msg[PD + c]) != expected[c]) throw LfException(LF_ERR_SUMCHECK_FAILED, "sumcheck round sum mismatch (SumCheckError::SumCheckFailed)");
+        u64 lag[8];
+        for (int a = 0; a < ne; ++a) { u64 num = 1, den = 1; for (int b = 0; b < ne; ++b) if (b != a) { num = Fm::hmul(num, Fm::sub(point[i], (u64)b)); den = Fm::hmul(den, a > b ? (u64)(a - b) : Fm::P - (u64)(b - a)); } lag[a] = Fm::hmul(num, Fm::hpow(den, Fm::P - 2)); }
+        for (int c = 0; c < PD; ++c) { u64 v = 0; for (int a = 0; a < ne; ++a) v = Fm::add(v, Fm::hmul(msg[a * PD + c], lag[a])); expected[c] = v; } }
+}
+// ComR1CS::linearize (r1cs.rs:72-134).  image: [nvars] ro[nvars] messages[nvars][4][16] v | va | vb | vc
+std::vector<u64> r1cs_linearize_core(Eng& E, Tr& T, const lf_csr* abc, const u64* f, size_t n) {
+    const int nvars = plus_ceil_log2(n); const size_t N = (size_t)1 << nvars;
+    std::vector<void*> blocks; std::vector<DevCsr> Mr;
+    struct Cleanup { Eng& E; std::vector<DevCsr>& b; std::vector<void*>& blk; ~Cleanup() { for (auto& s : b) s.free(E); for (void* p : blk) E.dfree(p); } } cl{E, Mr, blocks};
+    auto alloc = [&](size_t words) { u64* p = E.dalloc<u64>(words); blocks.push_back(p); return p; };
+    check_canonical(f, n * PD, "linearize witness");
+    for (int i = 0; i < 3; ++i) { DevSparse tmp = upload_by_columns(E, abc[i]); tmp.free(E);      // (validates the arrays)
+        if (abc[i].ncols != n || abc[i].nrows > N) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "linearize: R1CS matrix does not match the witness"); Mr.push_back(upload_csr(E, abc[i])); }
+    u64 *d_f = alloc(n * PD), *G = alloc(3 * N * PD), *Gn = alloc(3 * N * PD / 2), *Gm = alloc(3 * N * PD / 4 + PD), *eq = alloc(N), *eqn = alloc(N / 2 + 1), *eqm = alloc(N / 4 + 1), *cp = alloc(2);
+    LF_CUDA(cudaMemcpyAsync(d_f, f, n * PD * 8, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemsetAsync(G, 0, 3 * N * PD * 8, E.st()));
+    for (int i = 0; i < 3; ++i) E.launch("k_plus_spmv_acc", [&] { k_plus_spmv_acc<<<Eng::blocks_for(Mr[i].nrows, 128), 128, 0, E.st()>>>(Mr[i].row_ptr, Mr[i].col, Mr[i].val, Mr[i].nrows, d_f, Fm::r2(), G + (size_t)i * N * PD); });
+    std::vector<u64> r(nvars); for (auto& x : r) x = challenge(T);
+    eq_table(E, r, eq, N);
+    std::vector<u64> img = {(u64)nvars}, ro, msgs((size_t)nvars * 4 * PD);
+    absorb_field(T, (u64)nvars); absorb_field(T, 3);
+    const u64 *g_cur = G, *e_cur = eq; u64 *g_a = Gn, *g_b = Gm, *e_a = eqn, *e_b = eqm; size_t len = N; u64 r_prev = 0;
+    for (int i = 0; i < nvars; ++i) {
+        if (i > 0) { const size_t n_out = len / 2; const u64 rm = Fm::to_mont(r_prev);
+            E.launch("k_plus_fold", [&] { k_plus_fold<<<dim3(Eng::blocks_for(n_out, 256), 1), 256, 0, E.st()>>>(e_cur, len, e_a, n_out, rm); });
+            E.launch("k_plus_fold", [&] { k_plus_fold_ring<<<dim3(Eng::blocks_for(n_out * PD, 256), 3), 256, 0, E.st()>>>(g_cur, len, g_a, n_out, rm); });
+            e_cur = e_a; g_cur = g_a; std::swap(e_a, e_b); std::swap(g_a, g_b); len = n_out; }
+        const size_t n_pairs = len / 2; const unsigned nblk = (unsigned)std::min<size_t>(std::max<size_t>((n_pairs * PD + 255) / 256, 1), 148 * 8);
+        u64* partial = E.partial_dev((size_t)nblk * 4 * PD); u64* d_out = E.small_dev(4 * PD);
+        E.launch("k_plus_r1cs_round", [&] { k_plus_r1cs_round<<<nblk, 256, 0, E.st()>>>(e_cur, g_cur, len, n_pairs, Fm::r2(), partial); });
+        E.reduce_partials(partial, (int)nblk, 4 * PD, d_out);
+        u64* msg = msgs.data() + (size_t)i * 4 * PD; E.download_words(d_out, 4 * PD, msg);
+        T.absorb_slice(msg, 4);
+        r_prev = challenge(T); absorb_field(T, r_prev); ro.push_back(r_prev);
+    }
+    // v = MLE(f)(ro), va, vb, vc = MLE(A|B|C f)(ro)
+    eq_table(E, ro, eq, N); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
+    u64* cpN = alloc(2); const u64 cphN[2] = {0, N}; E.h2d(cpN, cphN, 16);
+    std::vector<u64> v4(4 * PD);
+    for (int q = 0; q < 4; ++q) { const size_t cnt = q == 0 ? n : N; const unsigned ch = chunks_for(cnt, 256); u64* partial = E.partial_dev((size_t)ch * PD);
+        E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, 1), 256, 0, E.st()>>>(eq, q == 0 ? cp : cpN, nullptr, q == 0 ? d_f : G + (size_t)(q - 1) * N * PD, partial); }); finish_wsum(E, partial, ch, 1, 0, &v4[q * PD]); }
+    T.absorb_slice(v4.data(), 4);
+    for (auto* x : {&ro, &msgs, &v4}) img.insert(img.end(), x->begin(), x->end());
+    return img;
+}
 }  // namespace
 
 extern "C" {
@@ -705,6 +758,29 @@ lf_status lf_plus_decompose_verify(const uint64_t* proof, uint64_t kappa, int32_
         for (size_t i = 0; i < nc; ++i) if (Fm::add(proof[i], Fm::hmul(proof[nc + i], Bm)) != cm_f[i]) throw LfException(LF_ERR_RECOMPOSED, "decompose verify: commitments do not recompose");
         for (size_t i = 0; i < nv; ++i) if (Fm::add(proof[2 * nc + i], Fm::hmul(proof[2 * nc + nv + i], Bm)) != v[i]) throw LfException(LF_ERR_RECOMPOSED, "decompose verify: evaluations do not recompose");
     });
+}
+// ComR1CS::linearize (r1cs.rs:72-134) on the R1CS matrices abc[3] = A, B, C (n columns) and the committed witness f (n x 16)
+lf_status lf_plus_r1cs_linearize(lf_ctx* c, lf_transcript* t, const lf_csr* abc, const uint64_t* f, uint64_t n, uint64_t* out, uint64_t out_cap, uint64_t* out_len) {
+    return pguard(c, [&] { need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (!abc || !f || !out_len || n < 2) throw LfException(LF_ERR_INVALID_ARG, "linearize: null / empty arguments");
+        const std::vector<u64> img = r1cs_linearize_core(E, T, abc, f, n); *out_len = img.size();
+        if (!out || out_cap < img.size()) throw LfException(LF_ERR_INVALID_ARG, "linearize: output buffer too small");
+        std::memcpy(out, img.data(), img.size() * 8); });
+}
+// ComR1CSProof::verify (r1cs.rs:136-162), host
+lf_status lf_plus_r1cs_linearize_verify(lf_transcript* t, const uint64_t* w, uint64_t len) {
+    return pguard(nullptr, [&] { Tr& T = tr_of(t);
+        if (!w || len < 1 || w[0] < 1 || w[0] > 40) throw LfException(LF_ERR_INCORRECT_LENGTH, "linearization image: bad header");
+        const size_t nv = w[0]; if (len < 1 + nv + nv * 4 * PD + 4 * PD) throw LfException(LF_ERR_INCORRECT_LENGTH, "linearization image truncated");
+        check_canonical(w + 1, nv + nv * 4 * PD + 4 * PD, "linearization image");
+        const u64 *msgs = w + 1 + nv, *v4 = msgs + nv * 4 * PD;
+        std::vector<u64> r(nv); for (auto& x : r) x = challenge(T);
+        std::vector<u64> point; u64 zero[PD] = {0}, expected[PD];
+        sumcheck_verify_host(T, nv, 3, zero, msgs, point, expected);
+        T.absorb_slice(v4, 4);
+        u64 e = 1; for (size_t i = 0; i < nv; ++i) { const u64 xy = Fm::hmul(r[i], point[i]); e = Fm::hmul(e, Fm::add(Fm::sub(Fm::sub(Fm::add(xy, xy), r[i]), point[i]), 1)); }
+        u64 pr[PD]; hring_mul(pr, v4 + PD, v4 + 2 * PD);
+        for (int c = 0; c < PD; ++c) if (Fm::hmul(Fm::sub(pr[c], v4[3 * PD + c]), e) != expected[c]) throw LfException(LF_ERR_SUMCHECK_FAILED, "linearization: evaluation claim mismatch (r1cs.rs:159)"); });
 }
 lf_status lf_plus_tensor(const uint64_t* r, int32_t n, uint64_t* out) {
     return pguard(nullptr, [&] { if (!r || !out || n < 0 || n > 30) throw LfException(LF_ERR_INVALID_ARG, "tensor: bad arguments"); check_canonical(r, n, "tensor");

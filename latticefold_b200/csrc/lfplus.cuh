@@ -410,4 +410,37 @@ __global__ void k_plus_split2(const u64* __restrict__ f, size_t words, long long
     F0[i] = dg[0] < 0 ? Fm::P - (u64)(-dg[0]) : (u64)dg[0]; F1[i] = dg[1] < 0 ? Fm::P - (u64)(-dg[1]) : (u64)dg[1];
 }
 
+// one round of the R1CS linearization sumcheck (r1cs.rs:92: eq (ga gb - gc), degree 3) on ring-valued tables: the only LatticeFold+ sumcheck with
+// real ring products.  16 lanes per pair, lane k owns coefficient k; ga(X) (lifted to Montgomery form) and gb(X) are exchanged through shared
+// memory and lane k forms coefficient k of the negacyclic product.  partial[block][4][16]
+__global__ void __launch_bounds__(256) k_plus_r1cs_round(const u64* __restrict__ eq, const u64* __restrict__ G /* [3][len][16] */, size_t len, size_t n_pairs, u64 r2, u64* __restrict__ partial) {
+    __shared__ u64 sa[16][PD], sb[16][PD];      // per pair slot of the block
+    const unsigned k = threadIdx.x & (PD - 1), slot = threadIdx.x >> 4;
+    u64 acc[4] = {0, 0, 0, 0};
+    const size_t pairs_per_pass = ((size_t)gridDim.x * blockDim.x) >> 4;
+    for (size_t b0 = 0; b0 < n_pairs; b0 += pairs_per_pass) {
+        const size_t b = b0 + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4); const bool live = b < n_pairs;
+        u64 a = 0, da = 0, bb = 0, db = 0, c = 0, dc = 0, e = 0, de = 0;
+        if (live) { const u64 a1 = G[(2 * b + 1) * PD + k], b1 = G[(len + 2 * b + 1) * PD + k], c1 = G[(2 * len + 2 * b + 1) * PD + k], e1 = eq[2 * b + 1];
+            a = G[(2 * b) * PD + k]; bb = G[(len + 2 * b) * PD + k]; c = G[(2 * len + 2 * b) * PD + k]; e = eq[2 * b];
+            da = Fm::sub(a1, a); db = Fm::sub(b1, bb); dc = Fm::sub(c1, c); de = Fm::sub(e1, e); }
+#pragma unroll 1
+        for (int X = 0; X < 4; ++X) {
+            __syncwarp();
+            sa[slot][k] = Fm::mul(a, r2); sb[slot][k] = bb;
+            __syncwarp();
+            u64 p = 0;
+#pragma unroll
+            for (int i = 0; i < PD; ++i) { const u64 pr = Fm::mul(sa[slot][i], sb[slot][(k - i) & (PD - 1)]); p = (unsigned)i <= k ? Fm::add(p, pr) : Fm::sub(p, pr); }
+            if (live) acc[X] = Fm::add(acc[X], Fm::mul(e, Fm::sub(p, c)));
+            a = Fm::add(a, da); bb = Fm::add(bb, db); c = Fm::add(c, dc); e = Fm::add(e, de);
+        }
+    }
+    __shared__ u64 sh[8][4][PD];
+#pragma unroll
+    for (int X = 0; X < 4; ++X) { u64 v = acc[X]; v = Fm::add(v, __shfl_xor_sync(0xffffffffu, v, 16)); if ((threadIdx.x & 31) < PD) sh[threadIdx.x >> 5][X][k] = v; }
+    __syncthreads();
+    if (threadIdx.x < 4 * PD) { const int X = threadIdx.x / PD, kk = threadIdx.x % PD; u64 v = 0; for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v = Fm::add(v, sh[wv][X][kk]); partial[(size_t)blockIdx.x * 4 * PD + threadIdx.x] = v; }
+}
+
 } }  // namespace lf::plus

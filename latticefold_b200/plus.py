@@ -15,7 +15,8 @@ RING = synth.RING_FROG
 D = 16
 SYMBOLS = """lf_transcript_get_challenge_base lf_plus_set_check lf_plus_set_check_verify lf_plus_mat_create lf_plus_mat_free
 lf_plus_rg_from_f lf_plus_rg_read lf_plus_rg_free lf_plus_range_check lf_plus_range_check_verify lf_plus_tensor
-lf_plus_comx_words lf_plus_cm_prove lf_plus_cm_verify lf_plus_mlin lf_plus_decompose lf_plus_decompose_verify""".split()
+lf_plus_comx_words lf_plus_cm_prove lf_plus_cm_verify lf_plus_mlin lf_plus_decompose lf_plus_decompose_verify
+lf_plus_r1cs_linearize lf_plus_r1cs_linearize_verify""".split()
 
 
 class PlusSet(C.Structure):      # lf_plus_set
@@ -47,6 +48,8 @@ def _L():
         L.lf_plus_mlin.argtypes = [vp, vp, vp, u64p, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(Csr), C.c_int32, u64p, C.c_uint64, u64p, u64p, u64p]
         L.lf_plus_decompose.argtypes = [vp, vp, u64p, C.c_uint64, u64p, C.POINTER(Csr), C.c_int32, C.c_uint64, u64p, u64p]
         L.lf_plus_decompose_verify.argtypes = [u64p, C.c_uint64, C.c_int32, u64p, u64p, C.c_uint64]
+        L.lf_plus_r1cs_linearize.argtypes = [vp, vp, C.POINTER(Csr), u64p, C.c_uint64, u64p, C.c_uint64, u64p]
+        L.lf_plus_r1cs_linearize_verify.argtypes = [vp, u64p, C.c_uint64]
         _ready = True
     return L
 
@@ -202,6 +205,31 @@ def cm_verify(words, n_M, transcript, nvars=None, L=1, kappa=1):      # CmProof:
     raise LfError(rc, "cm proof image rejected as malformed")
 
 
+class ComR1CS:
+    """r1cs.rs:19-35: R1CS matrices (A, B, C as csr dicts over the committed, decomposed witness) and the witness f (n x 16)."""
+
+    def __init__(self, ctx, abc, f):
+        self.ctx, self.abc, self.f = ctx, list(abc), np.ascontiguousarray(f, dtype=np.uint64)
+
+    def matrices(self):
+        return self.abc
+
+    def linearize(self, transcript):      # r1cs.rs:72-134 -> (LinB dict(f, r, v), proof image)
+        ma = _csr_array(self.abc)
+        img = _grow(self.ctx, lambda o, cap, n: _L().lf_plus_r1cs_linearize(self.ctx.h, transcript.h, ma, ptr(self.f), self.f.shape[0], o, cap, n))
+        nv = int(img[0])
+        ro, v4 = img[1: 1 + nv], img[-4 * D:].reshape(4, D)
+        return dict(f=self.f, r=np.stack([ro, ro], axis=1), v=np.stack([v4, v4], axis=1)), img
+
+
+def r1cs_linearize_verify(words, transcript):      # ComR1CSProof::verify, r1cs.rs:136-162
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    rc = _L().lf_plus_r1cs_linearize_verify(transcript.h, ptr(words), words.size)
+    if rc in (0, -10):
+        return rc == 0
+    raise LfError(rc, "linearization image rejected as malformed")
+
+
 class Mlin:
     """mlin.rs:15-19: L witnesses `fs` (L x n x 16) folded by Cm::prove; `mlin` returns (CmProof image, LinB2X dict, g[n, 16])."""
 
@@ -234,6 +262,35 @@ def decompose_verify(proof, kappa, n_M, cm_f, v, B):      # DecompProof::verify,
     if rc in (0, -11):
         return rc == 0
     raise LfError(rc, "decomposition proof rejected as malformed")
+
+
+class PlusProver:
+    """plus.rs:15-24, 48-118: the accumulating LatticeFold+ prover.  Host orchestration as in the reference; every step it calls runs on the device."""
+
+    def __init__(self, ctx, A, M, b, k, l, B, transcript):      # PlusProver::init
+        self.ctx, self.A, self.M, self.b, self.k, self.l, self.B, self.transcript, self.acc = ctx, A, list(M), b, k, l, B, transcript, []
+
+    def prove(self, comps):      # plus.rs:80-117 -> PlusProof dict(linb2x, lproof, cmproof, dproof)
+        lproof = []
+        for comp in comps:
+            linb, lp = comp.linearize(self.transcript)
+            lproof.append(lp); self.acc.append(linb["f"])
+        cmproof, x, g = Mlin(self.ctx, np.stack(self.acc), self.b, self.k, self.l).mlin(self.A, self.M, self.transcript)
+        dproof, F = decompose(self.ctx, self.A, g, x["ro"], self.M, self.B)
+        self.acc = [F[0], F[1]]      # keep only the accumulated instance
+        return dict(linb2x=x, lproof=lproof, cmproof=cmproof, dproof=dproof)
+
+
+class PlusVerifier:
+    """plus.rs:26-33, 120-145"""
+
+    def __init__(self, kappa, n_M, B, transcript):
+        self.kappa, self.n_M, self.B, self.transcript = kappa, n_M, B, transcript
+
+    def verify(self, proof):
+        ok = all(r1cs_linearize_verify(lp, self.transcript) for lp in proof["lproof"])
+        ok = ok and cm_verify(proof["cmproof"], self.n_M, self.transcript)[0]
+        return ok and decompose_verify(proof["dproof"], self.kappa, self.n_M, proof["linb2x"]["cm_g"], proof["linb2x"]["vo"], self.B)
 
 
 def tensor(r):      # utils.rs:74-86

@@ -357,4 +357,35 @@ int lfo_plus_decompose_verify(int id, const u64* proof, size_t kappa, int n_M, c
     return rc ? rc : ok;
 }
 
+
+// ComR1CS::linearize on (A, B, C, f): image [nvars] r msgs v|va|vb|vc (the LinB it returns is f with r = (ro, ro), v = the four evaluations twice)
+long lfo_plus_r1cs_linearize(int id, const lfo_csr* abc, const u64* f, size_t n, void* tr, u64* out, size_t cap) {
+    long nw = -1; int rc = guard([&] { const RingParams& R = ring(id); plus::SparseR M[3]; for (int i = 0; i < 3; ++i) M[i] = sparse_of(R, abc[i]);
+        auto w = plus::r1cs_lin_words(plus::r1cs_linearize(R, M, Vec(f, f + n * R.d), *(plus::PlusTranscript*)tr)); nw = (long)w.size(); if (w.size() <= cap) memcpy(out, w.data(), 8 * w.size()); });
+    return rc ? rc : nw;
+}
+int lfo_plus_r1cs_linearize_verify(int id, const u64* words, size_t len, void* tr) {
+    int ok = 0; int rc = guard([&] { const RingParams& R = ring(id); plus::R1csLinProof P; plus::r1cs_lin_parse(R, words, len, P); ok = plus::r1cs_linearize_verify(R, P, *(plus::PlusTranscript*)tr) ? 1 : 0; });
+    return rc ? rc : ok;
+}
+// stateful LatticeFold+ transcript for multi-protocol flows (plus.rs): create / absorb base elements / free; the other lfo_plus_*_t entry points take it
+void* lfo_plus_tr_new(int id, const u64* seed, size_t n_seed) { void* p = nullptr; guard([&] { p = new plus::PlusTranscript(plus_transcript(ring(id), seed, n_seed)); }); return p; }
+void lfo_plus_tr_free(void* t) { delete (plus::PlusTranscript*)t; }
+u64 lfo_plus_tr_challenge(void* t) { return ((plus::PlusTranscript*)t)->get_challenge(); }
+long lfo_plus_mlin_t(int id, int L, const u64* f, size_t n, const u64* A, size_t kappa, u64 b, int k, int l, const lfo_csr* M, int n_M, void* tr, u64* proof, size_t cap, u64* linb2x, u64* g) {
+    long nw = -1; int rc = guard([&] { const RingParams& R = ring(id); const size_t d = R.d; plus::DecompParameters dp{b, k, l};
+        std::vector<Vec> fs; for (int i = 0; i < L; ++i) fs.emplace_back(f + (size_t)i * n * d, f + (size_t)(i + 1) * n * d);
+        std::vector<plus::SparseR> Ms; for (int i = 0; i < n_M; ++i) Ms.push_back(sparse_of(R, M[i]));
+        plus::CmProof P; plus::LinB2 o = plus::mlin(R, fs, Vec(A, A + kappa * n * d), kappa, dp, Ms, *(plus::PlusTranscript*)tr, P);
+        auto w = plus::cm_proof_words(R, P); nw = (long)w.size(); if (w.size() <= cap) memcpy(proof, w.data(), 8 * w.size());
+        if (linb2x) { u64* p = linb2x; for (auto* v : {&o.cm_g, &o.ro, &o.vo}) { memcpy(p, v->data(), 8 * v->size()); p += v->size(); } }
+        if (g) memcpy(g, o.g.data(), 8 * o.g.size()); });
+    return rc ? rc : nw;
+}
+int lfo_plus_cm_verify_t(int id, const u64* words, size_t len, int n_M, void* tr) {
+    int ok = 0; int rc = guard([&] { const RingParams& R = ring(id); plus::CmProof P; plus::cm_proof_parse(R, words, len, P);
+        std::vector<plus::SparseR> Ms(n_M); plus::ComX X; ok = plus::cm_verify(R, P, Ms, *(plus::PlusTranscript*)tr, X) ? 1 : 0; });
+    return rc ? rc : ok;
+}
+
 }  // extern "C"

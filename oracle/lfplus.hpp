@@ -11,6 +11,7 @@
 //   crates/latticefold-plus/src/rgchk.rs:190-246      Dcom::verify
 //   crates/latticefold-plus/src/rgchk.rs:259-336      RgInstance::from_f (double commitment)
 //   crates/latticefold-plus/src/cm.rs:57-601          Cm::prove, sumchecker, CmProof::verify, ComX, calculate_t_z
+//   crates/latticefold-plus/src/r1cs.rs:72-165        ComR1CS::linearize, ComR1CSProof::verify
 //   crates/latticefold-plus/src/mlin.rs:41-106        Mlin::mlin
 //   crates/latticefold-plus/src/decomp.rs:32-127      Decomp::decompose, DecompProof::verify
 //   crates/latticefold/src/utils/sumcheck.rs:53-104, sumcheck/prover.rs:56-162, sumcheck/verifier.rs:92-254 (generic over R: OverField)
@@ -593,6 +594,43 @@ inline void cm_proof_parse(const RingParams& R, const u64* w, size_t len, CmProo
 }
 // ComX image: cm_g[L x kappa x d] ro[nvars x 2] vo[L x (1+n_M) x 2 x d]
 inline std::vector<u64> comx_words(const ComX& X) { std::vector<u64> w = X.cm_g; w.insert(w.end(), X.ro.begin(), X.ro.end()); w.insert(w.end(), X.vo.begin(), X.vo.end()); return w; }
+
+// ---------------------------------------------------------------- r1cs.rs: linearization of a committed R1CS
+struct R1csLinProof { int nvars = 0; PProof pf; std::vector<u64> r /* nvars */, v4 /* v, va, vb, vc: 4 x d */; };
+// ComR1CS::linearize (r1cs.rs:72-134): sumcheck of eq(r, x) (ga(x) gb(x) - gc(x)) with g* = A|B|C f as ring-valued MLEs (real ring products)
+inline R1csLinProof r1cs_linearize(const RingParams& R, const SparseR Mabc[3], const std::vector<u64>& f, PlusTranscript& T) {
+    const int d = R.d; const size_t n = f.size() / d; const int nvars = ceil_log2(n);
+    std::vector<u64> g[3]; for (int i = 0; i < 3; ++i) g[i] = sp_mul_vec(R, Mabc[i], f);
+    std::vector<u64> r = T.get_challenges(nvars);
+    std::vector<PMle> mles; auto push = [&](std::vector<u64> ev) { PMle m; m.nv = nvars; m.ev = std::move(ev); mles.push_back(std::move(m)); };
+    { std::vector<u64> eq = eq_table_base(R, r.data(), nvars), e(eq.size() * d, 0); for (size_t i = 0; i < eq.size(); ++i) e[i * d] = eq[i]; push(std::move(e)); }
+    for (int i = 0; i < 3; ++i) push(g[i]);
+    CombFn comb = [&](const u64* vals, u64* out) { u64 t[64]; r_mul(R, t, vals + d, vals + 2 * d); el_sub(R, t, t, vals + 3 * d); r_mul(R, out, vals, t); };      // r1cs.rs:92
+    R1csLinProof P; P.nvars = nvars;
+    P.pf = p_prove(R, T, mles, nvars, 3, comb, P.r);
+    P.v4.assign(4 * d, 0);
+    { PMle m; m.nv = nvars; m.ev = f; pm_evaluate(R, std::move(m), P.r.data(), nvars, P.v4.data()); }
+    for (int i = 0; i < 3; ++i) pm_evaluate(R, mles[1 + i], P.r.data(), nvars, P.v4.data() + (size_t)(1 + i) * d);
+    T.absorb_slice(P.v4.data(), 4);
+    return P;
+}
+// ComR1CSProof::verify (r1cs.rs:136-162)
+inline bool r1cs_linearize_verify(const RingParams& R, const R1csLinProof& P, PlusTranscript& T) {
+    const int d = R.d; std::vector<u64> r = T.get_challenges(P.nvars), zero(d, 0);
+    PSubClaim sc = p_verify(R, T, P.nvars, 3, zero.data(), P.pf);
+    if (!sc.ok) return false;
+    T.absorb_slice(P.v4.data(), 4);
+    const u64 e = eq_eval_base(R, r.data(), sc.point.data(), P.nvars);
+    u64 t[64]; r_mul(R, t, P.v4.data() + d, P.v4.data() + 2 * d); el_sub(R, t, t, P.v4.data() + 3 * d); r_scale(R, t, t, e);
+    return memcmp(t, sc.expected.data(), 8 * d) == 0;
+}
+// image: [nvars] r[nvars] messages[nvars x 4 x d] v|va|vb|vc [4 x d]
+inline std::vector<u64> r1cs_lin_words(const R1csLinProof& P) { std::vector<u64> w = {(u64)P.nvars}; for (auto* v : {&P.r, &P.pf.msgs, &P.v4}) w.insert(w.end(), v->begin(), v->end()); return w; }
+inline void r1cs_lin_parse(const RingParams& R, const u64* w, size_t len, R1csLinProof& P) {
+    const size_t d = R.d; if (len < 1 || w[0] > 40) throw std::runtime_error("linearization image: bad header");
+    P.nvars = (int)w[0]; const size_t nv = P.nvars; if (len < 1 + nv + nv * 4 * d + 4 * d) throw std::runtime_error("linearization image truncated");
+    const u64* p = w + 1; P.r.assign(p, p + nv); p += nv; P.pf.nvars = P.nvars; P.pf.degree = 3; P.pf.msgs.assign(p, p + nv * 4 * d); p += nv * 4 * d; P.v4.assign(p, p + 4 * d);
+}
 
 // ---------------------------------------------------------------- mlin.rs / decomp.rs
 struct LinB2 { std::vector<u64> g /* n x d */, cm_g /* kappa x d */, ro /* nvars x 2 */, vo /* (1+n_M) x 2 x d */; };

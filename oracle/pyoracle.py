@@ -330,6 +330,17 @@ class Oracle:
         L.lfo_plus_mlin.argtypes = [C.c_int, C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, C.c_int, C.c_int, C.POINTER(Csr), C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, u64p, u64p]
         L.lfo_plus_decompose.argtypes = [C.c_int, u64p, C.c_size_t, u64p, C.POINTER(Csr), C.c_int, u64p, C.c_size_t, C.c_uint64, u64p, u64p]
         L.lfo_plus_decompose_verify.argtypes = [C.c_int, u64p, C.c_size_t, C.c_int, u64p, u64p, C.c_uint64]
+        L.lfo_plus_r1cs_linearize.restype = C.c_long
+        L.lfo_plus_r1cs_linearize.argtypes = [C.c_int, C.POINTER(Csr), u64p, C.c_size_t, C.c_void_p, u64p, C.c_size_t]
+        L.lfo_plus_r1cs_linearize_verify.argtypes = [C.c_int, u64p, C.c_size_t, C.c_void_p]
+        L.lfo_plus_tr_new.restype = C.c_void_p
+        L.lfo_plus_tr_new.argtypes = [C.c_int, u64p, C.c_size_t]
+        L.lfo_plus_tr_free.argtypes = [C.c_void_p]
+        L.lfo_plus_tr_challenge.restype = C.c_uint64
+        L.lfo_plus_tr_challenge.argtypes = [C.c_void_p]
+        L.lfo_plus_mlin_t.restype = C.c_long
+        L.lfo_plus_mlin_t.argtypes = [C.c_int, C.c_int, u64p, C.c_size_t, u64p, C.c_size_t, C.c_uint64, C.c_int, C.c_int, C.POINTER(Csr), C.c_int, C.c_void_p, u64p, C.c_size_t, u64p, u64p]
+        L.lfo_plus_cm_verify_t.argtypes = [C.c_int, u64p, C.c_size_t, C.c_int, C.c_void_p]
         L.lfo_plus_mat_vec.argtypes = [C.c_int, u64p, C.c_size_t, C.c_size_t, u64p, u64p]
         L.lfo_plus_tensor.argtypes = [C.c_int, u64p, C.c_int, u64p]
         L.lfo_plus_ring_mul.argtypes = [C.c_int, u64p, u64p, u64p]
@@ -443,6 +454,51 @@ class Oracle:
     def plus_decompose_verify(self, ring, proof, kappa, n_M, cm_f, v, B):
         self._plus_setup()
         rc = self.lib.lfo_plus_decompose_verify(ring, ptr(np.ascontiguousarray(proof)), kappa, n_M, ptr(np.ascontiguousarray(cm_f)), ptr(np.ascontiguousarray(v)), B)
+        if rc < 0:
+            raise OracleError(rc, self.err())
+        return bool(rc)
+
+    # ---- stateful LatticeFold+ transcript and the entry points that take it (the flow of plus.rs)
+    def plus_transcript(self, ring, seed=None):
+        self._plus_setup()
+        sd, sp, sn = self._seed(seed)
+        return self.lib.lfo_plus_tr_new(ring, sp, sn)
+
+    def plus_transcript_free(self, tr):
+        self.lib.lfo_plus_tr_free(tr)
+
+    def plus_transcript_challenge(self, tr):
+        return int(self.lib.lfo_plus_tr_challenge(tr))
+
+    def plus_r1cs_linearize(self, ring, abc, f, tr):
+        """ComR1CS::linearize: (LinB dict(f, r, v), proof image)"""
+        self._plus_setup()
+        f = np.ascontiguousarray(f); ma = make_csr_array(list(abc)); d = f.shape[1]
+        img = self._plus_call(lambda out, cap: self.lib.lfo_plus_r1cs_linearize(ring, ma, ptr(f), f.shape[0], tr, ptr(out), cap))
+        nv = int(img[0]); ro, v4 = img[1: 1 + nv], img[-4 * d:].reshape(4, d)
+        return dict(f=f, r=np.stack([ro, ro], axis=1), v=np.stack([v4, v4], axis=1)), img
+
+    def plus_r1cs_linearize_verify(self, ring, words, tr):
+        self._plus_setup()
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        rc = self.lib.lfo_plus_r1cs_linearize_verify(ring, ptr(words), words.size, tr)
+        if rc < 0:
+            raise OracleError(rc, self.err())
+        return bool(rc)
+
+    def plus_mlin_t(self, ring, fs, A, b, k, l, M, tr):
+        self._plus_setup()
+        fs, A = np.ascontiguousarray(fs), np.ascontiguousarray(A)
+        Lc, n, d = fs.shape; kappa, nE, nv = A.shape[0], 1 + len(M), int(n - 1).bit_length()
+        ma = make_csr_array(list(M))
+        x = np.zeros(kappa * d + 2 * nv + nE * 2 * d, dtype=np.uint64); g = np.zeros((n, d), dtype=np.uint64)
+        proof = self._plus_call(lambda out, cap: self.lib.lfo_plus_mlin_t(ring, Lc, ptr(fs), n, ptr(A), kappa, b, k, l, ma, len(M), tr, ptr(out), cap, ptr(x), ptr(g)))
+        return proof, dict(cm_g=x[: kappa * d].reshape(kappa, d).copy(), ro=x[kappa * d: kappa * d + 2 * nv].reshape(nv, 2).copy(), vo=x[kappa * d + 2 * nv:].reshape(nE, 2, d).copy()), g
+
+    def plus_cm_verify_t(self, ring, words, n_M, tr):
+        self._plus_setup()
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        rc = self.lib.lfo_plus_cm_verify_t(ring, ptr(words), words.size, n_M, tr)
         if rc < 0:
             raise OracleError(rc, self.err())
         return bool(rc)

@@ -119,3 +119,41 @@ def reference_range_check_f(n, d=D):      # rgchk.rs:354-361: f = [2 + 5X, 4 + X
 def frog_l(d=D, p=P_FROG):      # rgchk.rs:367-369: ceil(ln q / ln(d/2))
     import math
     return math.ceil(math.log(float(p)) / math.log(d / 2))
+
+
+def r1cs_instance(n, seed, p=P_FROG, d=D):
+    """A satisfied R1CS over the committed witness (r1cs.rs / plus.rs tests use decomposed identity systems): A = B = C = a 0/1 selection
+    matrix with one entry scaled by 2 in A and C, and a 0/1 witness, so that (A f) * (B f) = C f holds as ring elements."""
+    rng = np.random.default_rng(seed)
+    f = np.zeros((n, d), dtype=np.uint64)
+    f[:, 0] = rng.integers(0, 2, size=n).astype(np.uint64)
+    f[0, 0] = 1
+    perm = rng.permutation(n)
+    ent = {(i, int(perm[i])): monomial(0, d) for i in range(n)}
+    A = csr_from_entries(n, n, ent, d)
+    two = dict(ent); two[(0, int(perm[0]))] = monomial(0, d) * np.uint64(2)
+    A2 = csr_from_entries(n, n, two, d)
+    return [A2, A, A2], f
+
+
+class OraclePlus:
+    """the flow of plus.rs (PlusProver::prove / PlusVerifier::verify) on the CPU oracle's entry points"""
+
+    def __init__(self, orc, A, M, b, k, l, B, seed=None):
+        self.o, self.A, self.M, self.b, self.k, self.l, self.B = orc, A, list(M), b, k, l, B
+        self.tp, self.tv, self.acc = orc.plus_transcript(RING_FROG, seed), orc.plus_transcript(RING_FROG, seed), []
+
+    def prove(self, comps):      # comps: list of (abc, f)
+        lproof = []
+        for abc, f in comps:
+            linb, lp = self.o.plus_r1cs_linearize(RING_FROG, abc, f, self.tp)
+            lproof.append(lp); self.acc.append(linb["f"])
+        cmproof, x, g = self.o.plus_mlin_t(RING_FROG, np.stack(self.acc), self.A, self.b, self.k, self.l, self.M, self.tp)
+        dproof, F = self.o.plus_decompose(RING_FROG, g, x["ro"], self.A, self.B, self.M)
+        self.acc = [F[0], F[1]]
+        return dict(linb2x=x, lproof=lproof, cmproof=cmproof, dproof=dproof)
+
+    def verify(self, proof):
+        ok = all(self.o.plus_r1cs_linearize_verify(RING_FROG, lp, self.tv) for lp in proof["lproof"])
+        ok = ok and self.o.plus_cm_verify_t(RING_FROG, proof["cmproof"], len(self.M), self.tv)
+        return ok and self.o.plus_decompose_verify(RING_FROG, proof["dproof"], self.A.shape[0], len(self.M), proof["linb2x"]["cm_g"], proof["linb2x"]["vo"], self.B)

@@ -170,3 +170,39 @@ def test_mlin_and_decompose_bit_exact(ctx, oracle, L, n_M):      # mlin.rs:41-10
     with pytest.raises(lf.LfError) as e:      # two digits in base 4 cannot hold g
         plus.decompose(ctx, Ad, g, x["ro"], M, 4)
     assert e.value.code == -9
+
+
+@pytest.mark.parametrize("n", [1 << 7, 1 << 12, 96])
+def test_r1cs_linearize_bit_exact(ctx, oracle, n):      # r1cs.rs:207-232; n = 96: a witness shorter than 2^nvars
+    abc, f = pc.r1cs_instance(n, n + 1)
+    tp = seeded([4])
+    linb, lp = plus.ComR1CS(ctx, abc, f).linearize(tp)
+    to = oracle.plus_transcript(RING, [4])
+    olinb, olp = oracle.plus_r1cs_linearize(RING, abc, f, to)
+    assert np.array_equal(lp, olp) and np.array_equal(linb["r"], olinb["r"]) and np.array_equal(linb["v"], olinb["v"])
+    assert plus.r1cs_linearize_verify(lp, seeded([4])) and oracle.plus_r1cs_linearize_verify(RING, lp, oracle.plus_transcript(RING, [4]))
+    assert tp.get_challenge() == oracle.plus_transcript_challenge(to)
+    # general ring-valued matrices and witness (no relation holds: the proof must be rejected, but the images still agree)
+    rng = np.random.default_rng(n)
+    g = rng.integers(0, pc.P_FROG, size=f.shape, dtype=np.uint64)
+    abc2 = [pc.random_ring_sparse(n, n, 2, s) for s in (1, 2, 3)]
+    _, lp2 = plus.ComR1CS(ctx, abc2, g).linearize(seeded())
+    _, olp2 = oracle.plus_r1cs_linearize(RING, abc2, g, oracle.plus_transcript(RING))
+    assert np.array_equal(lp2, olp2) and not plus.r1cs_linearize_verify(lp2, seeded())
+
+
+def test_plus_prover_three_folds_bit_exact(ctx, oracle):      # plus.rs:216-272 (test_prove_multi: k = 4, n = 2^16, three folds of the accumulator with a fresh instance)
+    n, kappa, k, l, B = 1 << 16, 2, 4, pc.frog_l(), 3000
+    _, A = pc.range_check_inputs(n, kappa, seed=61)
+    abc, f0 = pc.r1cs_instance(n, 5)
+    oflow = pc.OraclePlus(oracle, A, abc, 8, k, l, B)
+    prover = plus.PlusProver(ctx, plus.Matrix(ctx, A), abc, 8, k, l, B, seeded())
+    verifier = plus.PlusVerifier(kappa, len(abc), B, seeded())
+    for fold in range(3):
+        proof = prover.prove([plus.ComR1CS(ctx, abc, f0)])
+        want = oflow.prove([(abc, f0)])
+        assert np.array_equal(proof["cmproof"], want["cmproof"]) and np.array_equal(proof["dproof"], want["dproof"]), fold
+        assert all(np.array_equal(a, b) for a, b in zip(proof["lproof"], want["lproof"]))
+        assert all(np.array_equal(proof["linb2x"][key], want["linb2x"][key]) for key in ("cm_g", "ro", "vo"))
+        assert all(np.array_equal(a, b) for a, b in zip(prover.acc, oflow.acc))      # the accumulated witnesses
+        assert verifier.verify(proof) and oflow.verify(proof)

@@ -144,3 +144,29 @@ def test_mlin_then_decompose(oracle):      # the data flow of decomp.rs:189-268 
         # F0 + B F1 = g, digits inside the balanced range
         rec = (F[0].astype(object) + Bv * F[1].astype(object)) % pc.P_FROG
         assert np.array_equal(rec.astype(np.uint64), g)
+
+
+def test_r1cs_linearize(oracle):      # r1cs.rs:207-232 (test_linearization): prove -> verify; an unsatisfied system is rejected
+    n = 1 << 7
+    abc, f = pc.r1cs_instance(n, 3)
+    tp, tv = oracle.plus_transcript(RING), oracle.plus_transcript(RING)
+    linb, lp = oracle.plus_r1cs_linearize(RING, abc, f, tp)
+    assert oracle.plus_r1cs_linearize_verify(RING, lp, tv)
+    assert oracle.plus_transcript_challenge(tp) == oracle.plus_transcript_challenge(tv)
+    bad = f.copy(); bad[0, 0] = 3      # (2 * 3) * 3 != 2 * 3
+    _, lp2 = oracle.plus_r1cs_linearize(RING, abc, bad, oracle.plus_transcript(RING))
+    assert not oracle.plus_r1cs_linearize_verify(RING, lp2, oracle.plus_transcript(RING))
+
+
+def test_plus_prover_fold_two_instances(oracle):      # plus.rs:161-214 (test_prove): two committed R1CS instances folded into one accumulator
+    n, kappa, k, l = 1 << 15, 2, 2, pc.frog_l()
+    _, A = pc.range_check_inputs(n, kappa, seed=61)
+    abc, f0 = pc.r1cs_instance(n, 5)
+    f1 = f0.copy(); f1[1:, 0] = 1 - f1[1:, 0]
+    flow = pc.OraclePlus(oracle, A, abc, 8, k, l, 1 << 11)
+    p1 = flow.prove([(abc, f0), (abc, f1)])
+    assert flow.verify(p1)
+    t = dict(p1); t["dproof"] = p1["dproof"].copy(); t["dproof"][0] ^= np.uint64(1)
+    flow2 = pc.OraclePlus(oracle, A, abc, 8, k, l, 1 << 11)
+    flow2.prove([(abc, f0), (abc, f1)])
+    assert not flow2.verify(t)

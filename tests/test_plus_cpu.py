@@ -106,3 +106,14 @@ def test_product_decompose_verify_on_oracle_proof(oracle):
         t = dproof.copy(); t[pos] = (int(t[pos]) + 1) % pc.P_FROG
         assert not plus.decompose_verify(t, kappa, len(M), x["cm_g"], x["vo"], B)
     assert not plus.decompose_verify(dproof, kappa, len(M), x["cm_g"], x["vo"], B + 1)
+
+
+def test_product_linearize_verify_on_oracle_proof(oracle):
+    abc, f = pc.r1cs_instance(1 << 7, 3)
+    linb, lp = oracle.plus_r1cs_linearize(RING, abc, f, oracle.plus_transcript(RING, [2]))
+    assert plus.r1cs_linearize_verify(lp, seeded([2])) and not plus.r1cs_linearize_verify(lp, seeded(None))
+    t = lp.copy(); t[-1] = (int(t[-1]) + 1) % pc.P_FROG
+    assert not plus.r1cs_linearize_verify(t, seeded([2]))
+    bad = f.copy(); bad[0, 0] = 3
+    _, lp2 = oracle.plus_r1cs_linearize(RING, abc, bad, oracle.plus_transcript(RING, [2]))
+    assert not plus.r1cs_linearize_verify(lp2, seeded([2]))
