@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, dest="cpu_budget_s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
-    ap.add_argument("--plus-op", default="rgchk", choices=["rgchk", "cm"], dest="plus_op", help="--config plus: range check (benches/rgchk.rs) or commitment transformation (benches/cm.rs)")
+    ap.add_argument("--plus-op", default="rgchk", choices=["rgchk", "cm", "fold"], dest="plus_op", help="--config plus: range check (benches/rgchk.rs), commitment transformation (benches/cm.rs) or a whole PlusProver::prove (benches/e2e.rs)")
     ap.add_argument("--plus-instances", type=int, default=None, dest="plus_instances", help="--config plus: number of RgInstances (the folding arity L of benches/utils/mod.rs)")
     ap.add_argument("--full-step", action="store_true", dest="full_step", help="--config c3: time a whole NIFSProver::prove step instead of commit + linearization")
     args = ap.parse_args()

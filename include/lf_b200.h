@@ -346,6 +346,11 @@ lf_status lf_plus_decompose(lf_ctx* ctx, const lf_plus_mat* A, const uint64_t* f
                             uint64_t B, uint64_t* proof, uint64_t* F_host);
 /* DecompProof::verify                        decomp.rs:102-126 (host): LF_OK / LF_ERR_RECOMPOSED                                         */
 lf_status lf_plus_decompose_verify(const uint64_t* proof, uint64_t kappa, int32_t n_M, const uint64_t* cm_f, const uint64_t* v, uint64_t B);
+/* Static matrices (the M of PlusProver::init, the R1CS matrices): lf_plus_csr_pin keeps a validated, device-resident copy; every lf_plus_*
+ * entry point that is later handed the same host arrays uses it instead of uploading again.  The arrays must stay alive and unchanged until
+ * lf_plus_csr_unpin (or the context is destroyed).                                                                                      */
+lf_status lf_plus_csr_pin(lf_ctx* ctx, const lf_csr* m);
+lf_status lf_plus_csr_unpin(lf_ctx* ctx, const lf_csr* m);
 /* utils.rs:74-86 tensor(r) (host): out has 2^n entries                                                                         */
 lf_status lf_plus_tensor(const uint64_t* r, int32_t n, uint64_t* out);
 

@@ -4,6 +4,7 @@
 #include "ring_ops.cuh"
 
 using namespace lf;
+namespace lf { void plus_forget_ctx(lf_ctx* c); }      // lfplus.cu: drops the pinned-matrix records of a context that is going away
 
 namespace {
 thread_local std::string g_create_err;
@@ -48,6 +49,7 @@ lf_status lf_ctx_create(int32_t ring_id, int32_t device, lf_ctx** out) {
 }
 void lf_ctx_destroy(lf_ctx* c) {
     if (!c) return;
+    lf::plus_forget_ctx(c);
     cudaSetDevice(c->device); cudaStreamSynchronize(c->stream);
     for (int r = 0; r < 8; ++r) if (c->xg.peer_region[r]) cudaIpcCloseMemHandle(c->xg.peer_region[r]);
     if (c->xg.region) cudaFree(c->xg.region);

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <numeric>
 #include <chrono>
+#include <mutex>
 #include <cstdio>
 
 using namespace lf;
@@ -38,11 +39,11 @@ void absorb_field(Tr& T, u64 c) { u64 el[PD] = {0}; el[0] = c; T.absorb_base(el,
 
 // a sparse matrix / dense vector of ring elements grouped by columns on the device
 struct DevSparse {
-    u64* col_ptr = nullptr; u32 *erow = nullptr, *ecol = nullptr; u64* val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0;
-    void free(Eng& E) { E.dfree(col_ptr); E.dfree(erow); E.dfree(ecol); E.dfree(val); col_ptr = nullptr; erow = ecol = nullptr; val = nullptr; }
+    u64* col_ptr = nullptr; u32 *erow = nullptr, *ecol = nullptr; u64* val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0; bool borrowed = false;      // borrowed: a pinned matrix's resident copy
+    void free(Eng& E) { if (borrowed) return; E.dfree(col_ptr); E.dfree(erow); E.dfree(ecol); E.dfree(val); col_ptr = nullptr; erow = ecol = nullptr; val = nullptr; }
 };
 void check_canonical(const u64* v, size_t n, const char* what) { for (size_t i = 0; i < n; ++i) if (v[i] >= Fm::P) throw LfException(LF_ERR_INVALID_ARG, std::string(what) + ": non-canonical field element"); }
-DevSparse upload_by_columns(Eng& E, const lf_csr& m) {
+DevSparse upload_by_columns_raw(Eng& E, const lf_csr& m) {
     if (!m.row_ptr || (m.row_ptr[m.nrows] && (!m.col || !m.val))) throw LfException(LF_ERR_INVALID_ARG, "sparse matrix: null arrays");
     const size_t nnz = m.row_ptr[m.nrows];
     if (m.nrows >> 32 || m.ncols >> 32) throw LfException(LF_ERR_UNSUPPORTED, "sparse matrix: more than 2^32 rows / columns");
@@ -273,14 +274,27 @@ std::vector<u64> comx_words(const u64* s, size_t L, size_t kappa, size_t nE, con
         w.insert(w.end(), acc, acc + PD); }
     return w;
 }
-struct DevCsr { u64 *row_ptr = nullptr, *col = nullptr, *val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0; void free(Eng& E) { E.dfree(row_ptr); E.dfree(col); E.dfree(val); row_ptr = col = val = nullptr; } };
-DevCsr upload_csr(Eng& E, const lf_csr& m) {      // validated by upload_by_columns before
+struct DevCsr { u64 *row_ptr = nullptr, *col = nullptr, *val = nullptr; size_t nrows = 0, ncols = 0, nnz = 0; bool borrowed = false; void free(Eng& E) { if (borrowed) return; E.dfree(row_ptr); E.dfree(col); E.dfree(val); row_ptr = col = val = nullptr; } };
+DevCsr upload_csr_raw(Eng& E, const lf_csr& m) {      // validated by upload_by_columns before
     DevCsr S; S.nrows = m.nrows; S.ncols = m.ncols; S.nnz = m.row_ptr[m.nrows];
     S.row_ptr = E.dalloc<u64>(m.nrows + 1); S.col = E.dalloc<u64>(std::max<size_t>(S.nnz, 1)); S.val = E.dalloc<u64>(std::max<size_t>(S.nnz, 1) * PD);
     LF_CUDA(cudaMemcpyAsync(S.row_ptr, m.row_ptr, (m.nrows + 1) * 8, cudaMemcpyHostToDevice, E.st()));
     if (S.nnz) { LF_CUDA(cudaMemcpyAsync(S.col, m.col, S.nnz * 8, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemcpyAsync(S.val, m.val, S.nnz * PD * 8, cudaMemcpyHostToDevice, E.st())); }
     E.sync(); return S;
 }
+
+// Pinned matrices (lf_plus_csr_pin): the static matrices of a protocol run (PlusProver::init holds A and M in the reference as well) keep a resident
+// copy in both orders; the entry points recognise them by their host arrays and skip validation, sorting and the copies.
+struct Pinned { lf_ctx* ctx; const u64 *row_ptr, *col, *val; u64 nrows, ncols; DevSparse by_col; DevCsr by_row; };
+std::vector<Pinned>& pinned_list() { static std::vector<Pinned> v; return v; }
+std::mutex& pinned_mutex() { static std::mutex m; return m; }
+const Pinned* find_pinned(lf_ctx* c, const lf_csr& m) {
+    std::lock_guard<std::mutex> g(pinned_mutex());
+    for (auto& p : pinned_list()) if (p.ctx == c && p.row_ptr == m.row_ptr && p.col == m.col && p.val == m.val && p.nrows == m.nrows && p.ncols == m.ncols) return &p;
+    return nullptr;
+}
+DevSparse upload_by_columns(Eng& E, const lf_csr& m) { if (const Pinned* p = find_pinned(E.c, m)) { DevSparse s = p->by_col; s.borrowed = true; return s; } return upload_by_columns_raw(E, m); }
+DevCsr upload_csr(Eng& E, const lf_csr& m) { if (const Pinned* p = find_pinned(E.c, m)) { DevCsr s = p->by_row; s.borrowed = true; return s; } return upload_csr_raw(E, m); }
 
 // dense ring-valued MLE (len elements, zero tail) at a base-field point, by successive halving
 void mle_eval_dense(std::vector<u64> ev, int nv, const std::vector<u64>& point, u64* out) {
@@ -501,7 +515,7 @@ std::vector<u64> r1cs_linearize_core(Eng& E, Tr& T, const lf_csr* abc, const u64
     struct Cleanup { Eng& E; std::vector<DevCsr>& b; std::vector<void*>& blk; ~Cleanup() { for (auto& s : b) s.free(E); for (void* p : blk) E.dfree(p); } } cl{E, Mr, blocks};
     auto alloc = [&](size_t words) { u64* p = E.dalloc<u64>(words); blocks.push_back(p); return p; };
     check_canonical(f, n * PD, "linearize witness");
-    for (int i = 0; i < 3; ++i) { DevSparse tmp = upload_by_columns(E, abc[i]); tmp.free(E);      // (validates the arrays)
+    for (int i = 0; i < 3; ++i) { if (!find_pinned(E.c, abc[i])) { DevSparse tmp = upload_by_columns_raw(E, abc[i]); tmp.free(E); }      // (validates the arrays of a matrix seen for the first time)
         if (abc[i].ncols != n || abc[i].nrows > N) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "linearize: R1CS matrix does not match the witness"); Mr.push_back(upload_csr(E, abc[i])); }
     u64 *d_f = alloc(n * PD), *G = alloc(3 * N * PD), *Gn = alloc(3 * N * PD / 2), *Gm = alloc(3 * N * PD / 4 + PD), *eq = alloc(N), *eqn = alloc(N / 2 + 1), *eqm = alloc(N / 4 + 1), *cp = alloc(2);
     LF_CUDA(cudaMemcpyAsync(d_f, f, n * PD * 8, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemsetAsync(G, 0, 3 * N * PD * 8, E.st()));
@@ -535,6 +549,11 @@ std::vector<u64> r1cs_linearize_core(Eng& E, Tr& T, const lf_csr* abc, const u64
     return img;
 }
 }  // namespace
+
+namespace lf { void plus_forget_ctx(lf_ctx* c) {      // the resident copies are blocks of the context and are released with it
+    std::lock_guard<std::mutex> g(pinned_mutex()); auto& v = pinned_list();
+    for (size_t i = v.size(); i-- > 0;) if (v[i].ctx == c) v.erase(v.begin() + i);
+} }
 
 extern "C" {
 
@@ -781,6 +800,18 @@ lf_status lf_plus_r1cs_linearize_verify(lf_transcript* t, const uint64_t* w, uin
         u64 e = 1; for (size_t i = 0; i < nv; ++i) { const u64 xy = Fm::hmul(r[i], point[i]); e = Fm::hmul(e, Fm::add(Fm::sub(Fm::sub(Fm::add(xy, xy), r[i]), point[i]), 1)); }
         u64 pr[PD]; hring_mul(pr, v4 + PD, v4 + 2 * PD);
         for (int c = 0; c < PD; ++c) if (Fm::hmul(Fm::sub(pr[c], v4[3 * PD + c]), e) != expected[c]) throw LfException(LF_ERR_SUMCHECK_FAILED, "linearization: evaluation claim mismatch (r1cs.rs:159)"); });
+}
+// keep a resident copy of a static matrix; the host arrays must stay alive and unchanged until lf_plus_csr_unpin
+lf_status lf_plus_csr_pin(lf_ctx* c, const lf_csr* m) {
+    return pguard(c, [&] { need_frog(c); if (!m) throw LfException(LF_ERR_INVALID_ARG, "pin: null matrix"); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (find_pinned(c, *m)) return;
+        Pinned p{c, m->row_ptr, m->col, m->val, m->nrows, m->ncols, upload_by_columns_raw(E, *m), upload_csr_raw(E, *m)};
+        std::lock_guard<std::mutex> g(pinned_mutex()); pinned_list().push_back(p); });
+}
+lf_status lf_plus_csr_unpin(lf_ctx* c, const lf_csr* m) {
+    return pguard(c, [&] { if (!c || !m) throw LfException(LF_ERR_INVALID_ARG, "unpin: null argument"); Eng E(c); E.sync();
+        std::lock_guard<std::mutex> g(pinned_mutex()); auto& v = pinned_list();
+        for (size_t i = 0; i < v.size(); ++i) if (v[i].ctx == c && v[i].row_ptr == m->row_ptr && v[i].col == m->col && v[i].val == m->val) { v[i].by_col.free(E); v[i].by_row.free(E); v.erase(v.begin() + i); return; } });
 }
 lf_status lf_plus_tensor(const uint64_t* r, int32_t n, uint64_t* out) {
     return pguard(nullptr, [&] { if (!r || !out || n < 0 || n > 30) throw LfException(LF_ERR_INVALID_ARG, "tensor: bad arguments"); check_canonical(r, n, "tensor");

@@ -16,7 +16,7 @@ D = 16
 SYMBOLS = """lf_transcript_get_challenge_base lf_plus_set_check lf_plus_set_check_verify lf_plus_mat_create lf_plus_mat_free
 lf_plus_rg_from_f lf_plus_rg_read lf_plus_rg_free lf_plus_range_check lf_plus_range_check_verify lf_plus_tensor
 lf_plus_comx_words lf_plus_cm_prove lf_plus_cm_verify lf_plus_mlin lf_plus_decompose lf_plus_decompose_verify
-lf_plus_r1cs_linearize lf_plus_r1cs_linearize_verify""".split()
+lf_plus_r1cs_linearize lf_plus_r1cs_linearize_verify lf_plus_csr_pin lf_plus_csr_unpin""".split()
 
 
 class PlusSet(C.Structure):      # lf_plus_set
@@ -50,6 +50,7 @@ def _L():
         L.lf_plus_decompose_verify.argtypes = [u64p, C.c_uint64, C.c_int32, u64p, u64p, C.c_uint64]
         L.lf_plus_r1cs_linearize.argtypes = [vp, vp, C.POINTER(Csr), u64p, C.c_uint64, u64p, C.c_uint64, u64p]
         L.lf_plus_r1cs_linearize_verify.argtypes = [vp, u64p, C.c_uint64]
+        L.lf_plus_csr_pin.argtypes = L.lf_plus_csr_unpin.argtypes = [vp, C.POINTER(Csr)]
         _ready = True
     return L
 
@@ -264,11 +265,33 @@ def decompose_verify(proof, kappa, n_M, cm_f, v, B):      # DecompProof::verify,
     raise LfError(rc, "decomposition proof rejected as malformed")
 
 
+class PinnedMatrices:
+    """lf_plus_csr_pin for a list of csr dicts: resident copies of the static matrices for as long as this object lives."""
+
+    def __init__(self, ctx, mats):
+        self.ctx, self.mats, self.arr = ctx, list(mats), _csr_array(list(mats))
+        for i in range(len(self.mats)):
+            ctx.check(_L().lf_plus_csr_pin(ctx.h, C.byref(self.arr[i])))
+
+    def close(self):
+        if self.arr is not None and self.ctx.h:
+            for i in range(len(self.mats)):
+                _L().lf_plus_csr_unpin(self.ctx.h, C.byref(self.arr[i]))
+        self.arr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PlusProver:
     """plus.rs:15-24, 48-118: the accumulating LatticeFold+ prover.  Host orchestration as in the reference; every step it calls runs on the device."""
 
     def __init__(self, ctx, A, M, b, k, l, B, transcript):      # PlusProver::init
         self.ctx, self.A, self.M, self.b, self.k, self.l, self.B, self.transcript, self.acc = ctx, A, list(M), b, k, l, B, transcript, []
+        self.pinned = PinnedMatrices(ctx, self.M)      # the reference's prover owns M as well
 
     def prove(self, comps):      # plus.rs:80-117 -> PlusProof dict(linb2x, lproof, cmproof, dproof)
         lproof = []
