@@ -31,7 +31,8 @@ template <class Fn> lf_status pguard(lf_ctx* ctx, Fn&& fn) {
     catch (const std::exception& e) { if (ctx) ctx->err = e.what(); g_plus_err = e.what(); return LF_ERR_INVALID_ARG; }
 }
 Tr& tr_of(lf_transcript* t) { if (!t || t->ring != LF_RING_FROG) throw LfException(LF_ERR_INVALID_ARG, "LatticeFold+ entry points need a transcript of LF_RING_FROG"); return *(Tr*)t->impl; }
-void need_frog(lf_ctx* c) { if (!c || c->ring != LF_RING_FROG) throw LfException(LF_ERR_UNSUPPORTED, "LatticeFold+ entry points run on the Frog ring (X^16 + 1) only"); }
+void need_frog(lf_ctx* c) { if (!c || c->ring != LF_RING_FROG) throw LfException(LF_ERR_UNSUPPORTED, "LatticeFold+ entry points run on the Frog ring (X^16 + 1) only");
+                           if (c->world > 1) throw LfException(LF_ERR_UNSUPPORTED, "LatticeFold+ entry points do not shard: run replicas (one context per GPU, each on its own instances)"); }
 
 // transcript surface of latticefold-plus/src/transcript.rs
 u64 challenge(Tr& T) { u64 c; T.squeeze_base(&c, 1); T.absorb_base(&c, 1); return c; }
