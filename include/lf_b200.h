@@ -299,6 +299,7 @@ lf_status lf_ntt_negacyclic_mul_host(lf_ctx* ctx, const lf_ntt_plan* plan, const
 typedef struct { int32_t kind; int32_t pad; lf_csr m; const uint64_t* v; uint64_t n; } lf_plus_set; /* MonomialSet  setchk.rs:17-21: kind 0 = Matrix(m), 1 = Vector(v, n elements) */
 typedef struct lf_plus_mat lf_plus_mat;   /* Matrix<R> kappa x n, coefficient form, device resident (the matrix A of from_f)  */
 typedef struct lf_plus_rg lf_plus_rg;     /* RgInstance<R>                            rgchk.rs:41-48                          */
+typedef struct lf_plus_vec lf_plus_vec;   /* Vec<R>, n x 16 coefficients, device resident (the witness of a LinB, lin.rs:38-42) */
 /* Transcript::get_challenge of latticefold-plus/src/transcript.rs:46-55 (extension degree 1)                                  */
 void lf_transcript_get_challenge_base(lf_transcript* t, uint64_t* out1);
 /* In::set_check                              setchk.rs:59-262.  LF_ERR_INVALID_ARG when out_cap is too small (*out_len = needed) */
@@ -346,6 +347,17 @@ lf_status lf_plus_decompose(lf_ctx* ctx, const lf_plus_mat* A, const uint64_t* f
                             uint64_t B, uint64_t* proof, uint64_t* F_host);
 /* DecompProof::verify                        decomp.rs:102-126 (host): LF_OK / LF_ERR_RECOMPOSED                                         */
 lf_status lf_plus_decompose_verify(const uint64_t* proof, uint64_t kappa, int32_t n_M, const uint64_t* cm_f, const uint64_t* v, uint64_t B);
+/* Device-resident witnesses for the flow of PlusProver::prove (plus.rs:80-117): a LinB's f is uploaded once, mlin leaves g on the device,
+ * decompose leaves the two digit vectors (the next accumulator) there; the *_v entry points are the ones above on such vectors.          */
+lf_status lf_plus_vec_upload(lf_ctx* ctx, const uint64_t* host, uint64_t n, lf_plus_vec** out);
+lf_status lf_plus_vec_download(lf_ctx* ctx, const lf_plus_vec* v, uint64_t* host);
+uint64_t lf_plus_vec_len(const lf_plus_vec* v);
+void lf_plus_vec_free(lf_ctx* ctx, lf_plus_vec* v);
+lf_status lf_plus_r1cs_linearize_v(lf_ctx* ctx, lf_transcript* t, const lf_csr* abc, const lf_plus_vec* f, uint64_t* out, uint64_t out_cap, uint64_t* out_len);
+lf_status lf_plus_mlin_v(lf_ctx* ctx, lf_transcript* t, const lf_plus_mat* A, const lf_plus_vec* const* fs, int32_t L, uint64_t b, int32_t k, int32_t l,
+                         const lf_csr* M, int32_t n_M, uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* linb2x, lf_plus_vec** g_out);
+lf_status lf_plus_decompose_v(lf_ctx* ctx, const lf_plus_mat* A, const lf_plus_vec* f, const uint64_t* r_pairs, const lf_csr* M, int32_t n_M, uint64_t B,
+                              uint64_t* proof, lf_plus_vec** F0, lf_plus_vec** F1);
 /* Static matrices (the M of PlusProver::init, the R1CS matrices): lf_plus_csr_pin keeps a validated, device-resident copy; every lf_plus_*
  * entry point that is later handed the same host arrays uses it instead of uploading again.  The arrays must stay alive and unchanged until
  * lf_plus_csr_unpin (or the context is destroyed).                                                                                      */

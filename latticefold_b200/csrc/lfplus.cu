@@ -12,6 +12,7 @@ using namespace lf;
 using namespace lf::plus;
 
 struct lf_plus_mat { u64* d = nullptr; size_t kappa = 0, n = 0; };
+struct lf_plus_vec { u64* d = nullptr; size_t n = 0; };      // Vec<R> on the device: n x 16 canonical words (a block of the context's cache)
 struct lf_plus_rg {
     size_t n = 0, kappa = 0, code_pitch = 0; int k = 0, l = 0; u64 b = 0;
     unsigned char* codes = nullptr;        // [k * 16 columns][code_pitch]: exponents of M_f[kk][.][c]
@@ -77,7 +78,9 @@ DevSparse upload_dense_vector(Eng& E, const u64* v, size_t n) {
 // one monomial set as the device sees it: exponent codes (the range check's own M_f / m_tau) or general entries (anything the caller passes)
 struct DevSet { const unsigned char* codes = nullptr; size_t code_pitch = 0; const DevSparse* gen = nullptr; size_t nrows = 0, ncols = 0; };
 
-unsigned chunks_for(size_t n, int tpb) { return (unsigned)std::min<size_t>(std::max<size_t>((n + tpb - 1) / tpb, 1), 148 * 4); }
+// blocks along the rows for a weighted-sum launch of `ncols` columns: about four waves of blocks in all, so that a thread of a many-column launch
+// (the double commitment: k * 16 columns) sums several rows before the block reduction instead of one
+unsigned chunks_for(size_t n, int tpb, size_t ncols = 1) { return (unsigned)std::min<size_t>(std::max<size_t>((n + tpb - 1) / tpb, 1), std::max<size_t>(148 * 4 / std::max<size_t>(ncols, 1), 1)); }
 
 // out = sum over block partials -> host, `cols` ring elements; scale: 0 as is, 1 from Montgomery, 2 times 2^64 (canonical x canonical products)
 void finish_wsum(Eng& E, u64* partial, unsigned chunks, size_t cols, int scale, u64* out_host) {
@@ -90,13 +93,13 @@ void finish_wsum(Eng& E, u64* partial, unsigned chunks, size_t cols, int scale, 
 // sum_x W[x] entry(x, col) for every column of a set; W scalar (Montgomery eq table) or ring-valued (canonical, 16 words per x)
 void wsum_set(Eng& E, const DevSet& S, const u64* W, bool ring_w, u64* out_host) {
     if (S.codes) {
-        const unsigned ch = chunks_for(S.nrows, 256); u64* partial = E.partial_dev((size_t)ch * S.ncols * PD);
+        const unsigned ch = chunks_for(S.nrows, 256, S.ncols); u64* partial = E.partial_dev((size_t)ch * S.ncols * PD);
         if (ring_w) E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, (unsigned)S.ncols), 256, 0, E.st()>>>(W, S.codes, S.code_pitch, S.nrows, partial); });
         else E.launch("k_plus_wsum_scalar_mono", [&] { k_plus_wsum_scalar_mono<<<dim3(ch, (unsigned)S.ncols), 256, 0, E.st()>>>(W, S.codes, S.code_pitch, S.nrows, partial); });
         finish_wsum(E, partial, ch, S.ncols, ring_w ? 0 : 1, out_host);
     } else {
         const DevSparse& G = *S.gen; const int tpb = ring_w ? 128 : 256;
-        const unsigned ch = chunks_for(std::max<size_t>(G.nnz / std::max<size_t>(G.ncols, 1), 1), tpb); u64* partial = E.partial_dev((size_t)ch * G.ncols * PD);
+        const unsigned ch = chunks_for(std::max<size_t>(G.nnz / std::max<size_t>(G.ncols, 1), 1), tpb, G.ncols); u64* partial = E.partial_dev((size_t)ch * G.ncols * PD);
         if (ring_w) E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, (unsigned)G.ncols), 128, 0, E.st()>>>(W, G.col_ptr, G.erow, G.val, partial); });
         else E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, (unsigned)G.ncols), 256, 0, E.st()>>>(W, G.col_ptr, G.erow, G.val, partial); });
         finish_wsum(E, partial, ch, G.ncols, ring_w ? 2 : 0, out_host);
@@ -343,7 +346,7 @@ std::vector<u64> range_check_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* i
         return img;
 }
 // Cm::prove (cm.rs:57-203).  proof image = Dcom image | comh | two sumcheck proofs | two evaluation blocks
-void cm_prove_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* inst, int L, const lf_csr* Mh, int n_M, std::vector<u64>& proof, std::vector<u64>& comx, u64* g_host, bool sum_g = false) {
+void cm_prove_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* inst, int L, const lf_csr* Mh, int n_M, std::vector<u64>& proof, std::vector<u64>& comx, u64* g_host, bool sum_g = false, u64* g_dev = nullptr) {
     const lf_plus_rg& I0 = *inst[0]; const size_t n = I0.n, kappa = I0.kappa, N = (size_t)1 << nvars, nE = 1 + (size_t)n_M; const int k = I0.k, l = I0.l, kd = k * PD;
     std::vector<DevSparse> Ms; std::vector<DevCsr> Mr; SetCheckResult R; std::vector<void*> blocks;
     struct Cleanup { Eng& E; std::vector<DevSparse>& a; std::vector<DevCsr>& b; SetCheckResult& r; std::vector<void*>& blk; ~Cleanup() { for (auto& s : a) s.free(E); for (auto& s : b) s.free(E); r.free(E); for (void* p : blk) E.dfree(p); } } cl{E, Ms, Mr, R, blocks};
@@ -429,17 +432,17 @@ void cm_prove_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* inst, int L, con
         T.absorb_slice(evals[z].data(), evals[z].size() / PD);      // absorb_evaluations (cm.rs:581-588)
     }
     // g_l = s0 tau + s1 m_tau + s2 f + h (cm.rs:165-182)
-    if (g_host) { GArgs ga; for (int o = 0; o < PD; ++o) { ga.s0[o] = (short)to_small(ch.s[o]); ga.s1[o] = (short)to_small(ch.s[PD + o]); ga.s2m[o] = Fm::to_mont(ch.s[2 * PD + o]); }
-        u64* d_g = alloc(n * PD);
+    if (g_host || g_dev) { GArgs ga; for (int o = 0; o < PD; ++o) { ga.s0[o] = (short)to_small(ch.s[o]); ga.s1[o] = (short)to_small(ch.s[PD + o]); ga.s2m[o] = Fm::to_mont(ch.s[2 * PD + o]); }
+        u64* d_g = g_dev ? g_dev : alloc(n * PD);      // (g_dev: the summed g stays on the device, Mlin::mlin)
         for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
             E.launch("k_plus_g", [&] { k_plus_g<<<Eng::blocks_for(n, 128), 128, 0, E.st()>>>(I.tau, I.mtau_codes, I.f, d_h[li], n, ga, sum_g && li > 0 ? 1 : 0, d_g); });
-            if (!sum_g || li == L - 1) { LF_CUDA(cudaMemcpyAsync(g_host + (sum_g ? 0 : (size_t)li * n * PD), d_g, n * PD * 8, cudaMemcpyDeviceToHost, E.st())); E.sync(); } } }
+            if (g_host && (!sum_g || li == L - 1)) { LF_CUDA(cudaMemcpyAsync(g_host + (sum_g ? 0 : (size_t)li * n * PD), d_g, n * PD * 8, cudaMemcpyDeviceToHost, E.st())); E.sync(); } } }
     for (auto* v : {&comh, &msgs[0], &msgs[1], &evals[0], &evals[1]}) proof.insert(proof.end(), v->begin(), v->end());
     std::vector<const u64*> fc(L); for (int li = 0; li < L; ++li) fc[li] = inst[li]->fcoms.data();
     comx = comx_words(ch.s.data(), L, kappa, nE, fc.data(), comh.data(), evals, ro);
 }
 // RgInstance::from_f (rgchk.rs:259-336)
-lf_plus_rg* rg_from_f_core(Eng& E, lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, uint64_t n, uint64_t b, int32_t k, int32_t l) {
+lf_plus_rg* rg_from_f_core(Eng& E, lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, uint64_t n, uint64_t b, int32_t k, int32_t l, bool f_on_device = false) {
     {
         const bool tm = std::getenv("LF_PLUS_TIMING") != nullptr; auto t_last = std::chrono::steady_clock::now();      // diagnostic: phase times on stderr
         auto mark = [&](const char* what) { if (!tm) return; E.sync(); auto now = std::chrono::steady_clock::now(); std::fprintf(stderr, "from_f %-16s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count()); t_last = now; };
@@ -452,7 +455,7 @@ lf_plus_rg* rg_from_f_core(Eng& E, lf_ctx* c, const lf_plus_mat* A, const uint64
         struct Guard { Eng& E; lf_plus_rg* p; ~Guard() { if (p) { E.dfree(p->codes); E.dfree(p->mtau_codes); E.dfree(p->tau); E.dfree(p->f); } } } g{E, I.get()};
         I->f = E.dalloc<u64>(n * PD); I->codes = E.dalloc<unsigned char>((size_t)k * PD * I->code_pitch); I->mtau_codes = E.dalloc<unsigned char>(I->code_pitch); I->tau = E.dalloc<signed char>(n);
         mark("validate+alloc");
-        LF_CUDA(cudaMemcpyAsync(I->f, f, n * PD * 8, cudaMemcpyHostToDevice, E.st()));
+        LF_CUDA(cudaMemcpyAsync(I->f, f, n * PD * 8, f_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, E.st()));
         mark("h2d");
         // D_f = decompose_to_vec(cf(f), b, k), M_f = exp(D_f) as exponent codes
         E.launch("k_plus_digit_codes", [&] { k_plus_digit_codes<<<Eng::blocks_for(n * PD, 256), 256, 0, E.st()>>>(I->f, n, (long long)b, k, I->codes, I->code_pitch, c->d_err); });
@@ -464,7 +467,7 @@ lf_plus_rg* rg_from_f_core(Eng& E, lf_ctx* c, const lf_plus_mat* A, const uint64
         // comM_f[kk] = A * M_f[kk]: rotations only.  com = hconcat: row r, column kk * d + c
         I->comM.assign((size_t)k * kappa * PD * PD, 0); std::vector<u64> com(kappa * (size_t)k * PD * PD);
         for (size_t r = 0; r < kappa; ++r) {
-            const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * k * PD * PD);
+            const unsigned ch = chunks_for(n, 256, (size_t)k * PD); u64* partial = E.partial_dev((size_t)ch * k * PD * PD);
             E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, (unsigned)(k * PD)), 256, 0, E.st()>>>(A->d + r * n * PD, I->codes, I->code_pitch, n, partial); });
             finish_wsum(E, partial, ch, (size_t)k * PD, 0, com.data() + r * k * PD * PD);
             for (int kk = 0; kk < k; ++kk) std::memcpy(&I->comM[(((size_t)kk * kappa + r) * PD) * PD], &com[(r * k + kk) * PD * PD], 8 * PD * PD);
@@ -510,16 +513,16 @@ void sumcheck_verify_host(Tr& T, size_t nv, int deg, const u64* claimed, const u
         for (int c = 0; c < PD; ++c) { u64 v = 0; for (int a = 0; a < ne; ++a) v = Fm::add(v, Fm::hmul(msg[a * PD + c], lag[a])); expected[c] = v; } }
 }
 // ComR1CS::linearize (r1cs.rs:72-134).  image: [nvars] ro[nvars] messages[nvars][4][16] v | va | vb | vc
-std::vector<u64> r1cs_linearize_core(Eng& E, Tr& T, const lf_csr* abc, const u64* f, size_t n) {
+std::vector<u64> r1cs_linearize_core(Eng& E, Tr& T, const lf_csr* abc, const u64* f, size_t n, bool f_on_device = false) {
     const int nvars = plus_ceil_log2(n); const size_t N = (size_t)1 << nvars;
     std::vector<void*> blocks; std::vector<DevCsr> Mr;
     struct Cleanup { Eng& E; std::vector<DevCsr>& b; std::vector<void*>& blk; ~Cleanup() { for (auto& s : b) s.free(E); for (void* p : blk) E.dfree(p); } } cl{E, Mr, blocks};
     auto alloc = [&](size_t words) { u64* p = E.dalloc<u64>(words); blocks.push_back(p); return p; };
-    check_canonical(f, n * PD, "linearize witness");
+    if (!f_on_device) check_canonical(f, n * PD, "linearize witness");
     for (int i = 0; i < 3; ++i) { if (!find_pinned(E.c, abc[i])) { DevSparse tmp = upload_by_columns_raw(E, abc[i]); tmp.free(E); }      // (validates the arrays of a matrix seen for the first time)
         if (abc[i].ncols != n || abc[i].nrows > N) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "linearize: R1CS matrix does not match the witness"); Mr.push_back(upload_csr(E, abc[i])); }
     u64 *d_f = alloc(n * PD), *G = alloc(3 * N * PD), *Gn = alloc(3 * N * PD / 2), *Gm = alloc(3 * N * PD / 4 + PD), *eq = alloc(N), *eqn = alloc(N / 2 + 1), *eqm = alloc(N / 4 + 1), *cp = alloc(2);
-    LF_CUDA(cudaMemcpyAsync(d_f, f, n * PD * 8, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemsetAsync(G, 0, 3 * N * PD * 8, E.st()));
+    LF_CUDA(cudaMemcpyAsync(d_f, f, n * PD * 8, f_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemsetAsync(G, 0, 3 * N * PD * 8, E.st()));
     for (int i = 0; i < 3; ++i) E.launch("k_plus_spmv_acc", [&] { k_plus_spmv_acc<<<Eng::blocks_for(Mr[i].nrows, 128), 128, 0, E.st()>>>(Mr[i].row_ptr, Mr[i].col, Mr[i].val, Mr[i].nrows, d_f, Fm::r2(), G + (size_t)i * N * PD); });
     std::vector<u64> r(nvars); for (auto& x : r) x = challenge(T);
     eq_table(E, r, eq, N);
@@ -714,15 +717,14 @@ lf_status lf_plus_cm_verify(lf_transcript* t, const uint64_t* w, uint64_t len, i
     });
 }
 // Mlin::mlin (mlin.rs:41-106): from_f on every witness, Cm::prove, the sums over the instances.  linb2x = cm_g[kappa][16] | ro[nvars][2] | vo[1 + n_M][2][16]
-lf_status lf_plus_mlin(lf_ctx* c, lf_transcript* t, const lf_plus_mat* A, const uint64_t* fs, int32_t L, uint64_t n, uint64_t b, int32_t k, int32_t l, const lf_csr* M, int32_t n_M,
-                       uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* linb2x, uint64_t* g_host) {
-    return pguard(c, [&] {
+static void mlin_core(lf_ctx* c, lf_transcript* t, const lf_plus_mat* A, const uint64_t* const* srcs, bool on_device, int32_t L, uint64_t n, uint64_t b, int32_t k, int32_t l, const lf_csr* M, int32_t n_M,
+                      uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* linb2x, uint64_t* g_host, uint64_t* g_dev) {
         need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
-        if (L < 1 || L > 64 || !fs || !A || n_M < 0 || (n_M && !M) || !proof_len || !linb2x) throw LfException(LF_ERR_INVALID_ARG, "mlin: null / empty arguments");
+        if (L < 1 || L > 64 || !srcs || !A || n_M < 0 || (n_M && !M) || !proof_len || !linb2x) throw LfException(LF_ERR_INVALID_ARG, "mlin: null / empty arguments");
         std::vector<lf_plus_rg*> inst; struct Cleanup { lf_ctx* c; std::vector<lf_plus_rg*>& v; ~Cleanup() { for (auto* p : v) lf_plus_rg_free(c, p); } } cl{c, inst};
-        for (int i = 0; i < L; ++i) inst.push_back(rg_from_f_core(E, c, A, fs + (size_t)i * n * PD, n, b, k, l));
+        for (int i = 0; i < L; ++i) inst.push_back(rg_from_f_core(E, c, A, srcs[i], n, b, k, l, on_device));
         const int nvars = plus_ceil_log2(n); const size_t kappa = A->kappa, nE = 1 + (size_t)n_M;
-        std::vector<u64> pw, xw; cm_prove_core(E, T, nvars, inst.data(), L, M, n_M, pw, xw, g_host, true);
+        std::vector<u64> pw, xw; cm_prove_core(E, T, nvars, inst.data(), L, M, n_M, pw, xw, g_host, true, g_dev);
         // LinB2X: sums of the per-instance cm_g and vo, ro as it is
         const u64 *cmg = xw.data(), *ro = cmg + (size_t)L * kappa * PD, *vo = ro + 2 * (size_t)nvars;
         std::vector<u64> x(kappa * PD + 2 * (size_t)nvars + nE * 2 * PD, 0);
@@ -732,12 +734,27 @@ lf_status lf_plus_mlin(lf_ctx* c, lf_transcript* t, const lf_plus_mat* A, const 
         *proof_len = pw.size();
         if (!proof || proof_cap < pw.size()) throw LfException(LF_ERR_INVALID_ARG, "mlin: proof buffer too small");
         std::memcpy(proof, pw.data(), pw.size() * 8); std::memcpy(linb2x, x.data(), x.size() * 8);
-    });
+}
+lf_status lf_plus_mlin(lf_ctx* c, lf_transcript* t, const lf_plus_mat* A, const uint64_t* fs, int32_t L, uint64_t n, uint64_t b, int32_t k, int32_t l, const lf_csr* M, int32_t n_M,
+                       uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* linb2x, uint64_t* g_host) {
+    return pguard(c, [&] { if (!fs || L < 1 || L > 64) throw LfException(LF_ERR_INVALID_ARG, "mlin: null / empty arguments");
+        std::vector<const uint64_t*> srcs(L); for (int i = 0; i < L; ++i) srcs[i] = fs + (size_t)i * n * PD;
+        mlin_core(c, t, A, srcs.data(), false, L, n, b, k, l, M, n_M, proof, proof_cap, proof_len, linb2x, g_host, nullptr); });
+}
+// the same on device-resident witnesses (lf_plus_vec): g stays on the device as a new vector
+lf_status lf_plus_mlin_v(lf_ctx* c, lf_transcript* t, const lf_plus_mat* A, const lf_plus_vec* const* fs, int32_t L, uint64_t b, int32_t k, int32_t l, const lf_csr* M, int32_t n_M,
+                         uint64_t* proof, uint64_t proof_cap, uint64_t* proof_len, uint64_t* linb2x, lf_plus_vec** g_out) {
+    if (g_out) *g_out = nullptr;
+    return pguard(c, [&] { need_frog(c); if (!fs || L < 1 || L > 64 || !fs[0] || !g_out) throw LfException(LF_ERR_INVALID_ARG, "mlin: null / empty arguments");
+        const size_t n = fs[0]->n; std::vector<const uint64_t*> srcs(L); for (int i = 0; i < L; ++i) { if (!fs[i] || fs[i]->n != n) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "mlin: witnesses of different lengths"); srcs[i] = fs[i]->d; }
+        Eng E(c); std::unique_ptr<lf_plus_vec> g(new lf_plus_vec); g->n = n; g->d = E.dalloc<u64>(n * PD);
+        try { mlin_core(c, t, A, srcs.data(), true, L, n, b, k, l, M, n_M, proof, proof_cap, proof_len, linb2x, nullptr, g->d); } catch (...) { E.dfree(g->d); throw; }
+        *g_out = g.release(); });
 }
 // Decomp::decompose (decomp.rs:32-99).  r_pairs: nvars x 2 field elements (the points are constants of R on every path of the reference).
 // proof = C0[kappa][16] | C1 | v0[1 + n_M][2][16] | v1; F_host (2 x n x 16: the two LinB witnesses) may be NULL
-lf_status lf_plus_decompose(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, uint64_t n, const uint64_t* r_pairs, const lf_csr* M, int32_t n_M, uint64_t B, uint64_t* proof, uint64_t* F_host) {
-    return pguard(c, [&] {
+static void decompose_core(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, bool on_device, uint64_t n, const uint64_t* r_pairs, const lf_csr* M, int32_t n_M, uint64_t B, uint64_t* proof, uint64_t* F_host, u64* F_dev0, u64* F_dev1) {
+    {
         need_frog(c); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
         if (!A || !f || !r_pairs || !proof || n_M < 0 || (n_M && !M)) throw LfException(LF_ERR_INVALID_ARG, "decompose: null arguments");
         if (n != A->n) throw LfException(LF_ERR_WRONG_WITNESS_LEN, "decompose: witness length differs from the matrix width");
@@ -748,7 +765,7 @@ lf_status lf_plus_decompose(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, 
         auto alloc = [&](size_t words) { u64* p = E.dalloc<u64>(words); blocks.push_back(p); return p; };
         for (int i = 0; i < n_M; ++i) { Ms.push_back(upload_by_columns(E, M[i])); if (Ms.back().ncols != n || Ms.back().nrows > N) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "decompose: M_i does not match the witness"); }
         u64 *d_f = alloc(n * PD), *F = alloc(2 * n * PD), *eq = alloc(2 * N), *cp = alloc(2); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
-        LF_CUDA(cudaMemcpyAsync(d_f, f, n * PD * 8, cudaMemcpyHostToDevice, E.st()));
+        LF_CUDA(cudaMemcpyAsync(d_f, f, n * PD * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, E.st()));
         E.launch("k_plus_split2", [&] { k_plus_split2<<<Eng::blocks_for(n * PD, 256), 256, 0, E.st()>>>(d_f, n * PD, (long long)B, F, F + n * PD, c->d_err); });
         { int h = 0; LF_CUDA(cudaMemcpyAsync(&h, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, E.st())); E.sync();
           if (h) { LF_CUDA(cudaMemsetAsync(c->d_err, 0, sizeof(int), E.st())); if (h == 3) throw LfException(LF_ERR_INVALID_ARG, "decompose: non-canonical field element"); throw LfException(LF_ERR_DOES_NOT_FIT, "decompose: a coefficient needs more than two digits in base B"); } }
@@ -767,7 +784,20 @@ lf_status lf_plus_decompose(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, 
                     E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(w[q][e - 1], cp, nullptr, Fz, partial); }); finish_wsum(E, partial, ch, 1, 2, out); } }
         }
         if (F_host) { LF_CUDA(cudaMemcpyAsync(F_host, F, 2 * n * PD * 8, cudaMemcpyDeviceToHost, E.st())); E.sync(); }
-    });
+        if (F_dev0) LF_CUDA(cudaMemcpyAsync(F_dev0, F, n * PD * 8, cudaMemcpyDeviceToDevice, E.st()));
+        if (F_dev1) LF_CUDA(cudaMemcpyAsync(F_dev1, F + n * PD, n * PD * 8, cudaMemcpyDeviceToDevice, E.st()));
+    }
+}
+lf_status lf_plus_decompose(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, uint64_t n, const uint64_t* r_pairs, const lf_csr* M, int32_t n_M, uint64_t B, uint64_t* proof, uint64_t* F_host) {
+    return pguard(c, [&] { decompose_core(c, A, f, false, n, r_pairs, M, n_M, B, proof, F_host, nullptr, nullptr); });
+}
+// the same on a device-resident witness: the two digit vectors (the next accumulator, plus.rs:111-114) stay on the device
+lf_status lf_plus_decompose_v(lf_ctx* c, const lf_plus_mat* A, const lf_plus_vec* f, const uint64_t* r_pairs, const lf_csr* M, int32_t n_M, uint64_t B, uint64_t* proof, lf_plus_vec** F0, lf_plus_vec** F1) {
+    if (F0) *F0 = nullptr; if (F1) *F1 = nullptr;
+    return pguard(c, [&] { need_frog(c); if (!f || !F0 || !F1) throw LfException(LF_ERR_INVALID_ARG, "decompose: null arguments");
+        Eng E(c); std::unique_ptr<lf_plus_vec> a(new lf_plus_vec), b(new lf_plus_vec); a->n = b->n = f->n; a->d = E.dalloc<u64>(f->n * PD); b->d = E.dalloc<u64>(f->n * PD);
+        try { decompose_core(c, A, f->d, true, f->n, r_pairs, M, n_M, B, proof, nullptr, a->d, b->d); } catch (...) { E.dfree(a->d); E.dfree(b->d); throw; }
+        *F0 = a.release(); *F1 = b.release(); });
 }
 // DecompProof::verify (decomp.rs:102-126), host: recompose([C0, C1], B) = cm_f and the same for every evaluation pair.  LF_ERR_RECOMPOSED on mismatch
 lf_status lf_plus_decompose_verify(const uint64_t* proof, uint64_t kappa, int32_t n_M, const uint64_t* cm_f, const uint64_t* v, uint64_t B) {
@@ -784,6 +814,26 @@ lf_status lf_plus_r1cs_linearize(lf_ctx* c, lf_transcript* t, const lf_csr* abc,
     return pguard(c, [&] { need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
         if (!abc || !f || !out_len || n < 2) throw LfException(LF_ERR_INVALID_ARG, "linearize: null / empty arguments");
         const std::vector<u64> img = r1cs_linearize_core(E, T, abc, f, n); *out_len = img.size();
+        if (!out || out_cap < img.size()) throw LfException(LF_ERR_INVALID_ARG, "linearize: output buffer too small");
+        std::memcpy(out, img.data(), img.size() * 8); });
+}
+// Vec<R> resident on the device (the LinB witnesses that travel between the sub-protocols of PlusProver::prove)
+lf_status lf_plus_vec_upload(lf_ctx* c, const uint64_t* host, uint64_t n, lf_plus_vec** out) {
+    *out = nullptr;
+    return pguard(c, [&] { need_frog(c); if (!host || !n) throw LfException(LF_ERR_INVALID_ARG, "vector: null / empty"); check_canonical(host, n * PD, "vector"); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        std::unique_ptr<lf_plus_vec> v(new lf_plus_vec); v->n = n; v->d = E.dalloc<u64>(n * PD);
+        LF_CUDA(cudaMemcpyAsync(v->d, host, n * PD * 8, cudaMemcpyHostToDevice, E.st())); E.sync(); *out = v.release(); });
+}
+lf_status lf_plus_vec_download(lf_ctx* c, const lf_plus_vec* v, uint64_t* host) {
+    return pguard(c, [&] { if (!v || !host) throw LfException(LF_ERR_INVALID_ARG, "vector: null"); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        LF_CUDA(cudaMemcpyAsync(host, v->d, v->n * PD * 8, cudaMemcpyDeviceToHost, E.st())); E.sync(); });
+}
+uint64_t lf_plus_vec_len(const lf_plus_vec* v) { return v ? v->n : 0; }
+void lf_plus_vec_free(lf_ctx* c, lf_plus_vec* v) { if (v && c) { Eng E(c); E.dfree(v->d); delete v; } }
+lf_status lf_plus_r1cs_linearize_v(lf_ctx* c, lf_transcript* t, const lf_csr* abc, const lf_plus_vec* f, uint64_t* out, uint64_t out_cap, uint64_t* out_len) {
+    return pguard(c, [&] { need_frog(c); Tr& T = tr_of(t); LF_CUDA(cudaSetDevice(c->device)); Eng E(c);
+        if (!abc || !f || !out_len || f->n < 2) throw LfException(LF_ERR_INVALID_ARG, "linearize: null / empty arguments");
+        const std::vector<u64> img = r1cs_linearize_core(E, T, abc, f->d, f->n, true); *out_len = img.size();
         if (!out || out_cap < img.size()) throw LfException(LF_ERR_INVALID_ARG, "linearize: output buffer too small");
         std::memcpy(out, img.data(), img.size() * 8); });
 }

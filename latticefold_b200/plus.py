@@ -16,7 +16,8 @@ D = 16
 SYMBOLS = """lf_transcript_get_challenge_base lf_plus_set_check lf_plus_set_check_verify lf_plus_mat_create lf_plus_mat_free
 lf_plus_rg_from_f lf_plus_rg_read lf_plus_rg_free lf_plus_range_check lf_plus_range_check_verify lf_plus_tensor
 lf_plus_comx_words lf_plus_cm_prove lf_plus_cm_verify lf_plus_mlin lf_plus_decompose lf_plus_decompose_verify
-lf_plus_r1cs_linearize lf_plus_r1cs_linearize_verify lf_plus_csr_pin lf_plus_csr_unpin""".split()
+lf_plus_r1cs_linearize lf_plus_r1cs_linearize_verify lf_plus_csr_pin lf_plus_csr_unpin
+lf_plus_vec_upload lf_plus_vec_download lf_plus_vec_len lf_plus_vec_free lf_plus_r1cs_linearize_v lf_plus_mlin_v lf_plus_decompose_v""".split()
 
 
 class PlusSet(C.Structure):      # lf_plus_set
@@ -51,6 +52,14 @@ def _L():
         L.lf_plus_r1cs_linearize.argtypes = [vp, vp, C.POINTER(Csr), u64p, C.c_uint64, u64p, C.c_uint64, u64p]
         L.lf_plus_r1cs_linearize_verify.argtypes = [vp, u64p, C.c_uint64]
         L.lf_plus_csr_pin.argtypes = L.lf_plus_csr_unpin.argtypes = [vp, C.POINTER(Csr)]
+        L.lf_plus_vec_upload.argtypes = [vp, u64p, C.c_uint64, C.POINTER(vp)]
+        L.lf_plus_vec_download.argtypes = [vp, vp, u64p]
+        L.lf_plus_vec_len.restype = C.c_uint64
+        L.lf_plus_vec_len.argtypes = [vp]
+        L.lf_plus_vec_free.argtypes = [vp, vp]
+        L.lf_plus_r1cs_linearize_v.argtypes = [vp, vp, C.POINTER(Csr), vp, u64p, C.c_uint64, u64p]
+        L.lf_plus_mlin_v.argtypes = [vp, vp, vp, C.POINTER(vp), C.c_int32, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(Csr), C.c_int32, u64p, C.c_uint64, u64p, u64p, C.POINTER(vp)]
+        L.lf_plus_decompose_v.argtypes = [vp, vp, vp, u64p, C.POINTER(Csr), C.c_int32, C.c_uint64, u64p, C.POINTER(vp), C.POINTER(vp)]
         _ready = True
     return L
 
@@ -206,11 +215,49 @@ def cm_verify(words, n_M, transcript, nvars=None, L=1, kappa=1):      # CmProof:
     raise LfError(rc, "cm proof image rejected as malformed")
 
 
+class Vec:
+    """Vec<R> resident on the device (n x 16 coefficients): the witness of a LinB between the sub-protocols of PlusProver::prove."""
+
+    def __init__(self, ctx, host=None, handle=None):
+        self.ctx, self.h = ctx, handle
+        if handle is None:
+            host = np.ascontiguousarray(host, dtype=np.uint64)
+            self.h = vp()
+            ctx.check(_L().lf_plus_vec_upload(ctx.h, ptr(host), host.shape[0], C.byref(self.h)))
+
+    def __len__(self):
+        return int(_L().lf_plus_vec_len(self.h))
+
+    def download(self):
+        out = np.zeros((len(self), D), dtype=np.uint64)
+        self.ctx.check(_L().lf_plus_vec_download(self.ctx.h, self.h, ptr(out)))
+        return out
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                _L().lf_plus_vec_free(self.ctx.h, self.h)
+        except Exception:
+            pass
+
+
 class ComR1CS:
     """r1cs.rs:19-35: R1CS matrices (A, B, C as csr dicts over the committed, decomposed witness) and the witness f (n x 16)."""
 
     def __init__(self, ctx, abc, f):
         self.ctx, self.abc, self.f = ctx, list(abc), np.ascontiguousarray(f, dtype=np.uint64)
+        self._vec = None
+
+    def vec(self):      # the witness on the device, uploaded once
+        if self._vec is None:
+            self._vec = Vec(self.ctx, self.f)
+        return self._vec
+
+    def linearize_resident(self, transcript):      # the same proof from the resident witness -> (Vec, proof image)
+        ma = _csr_array(self.abc)
+        v = self.vec()
+        img = _grow(self.ctx, lambda o, cap, n: _L().lf_plus_r1cs_linearize_v(self.ctx.h, transcript.h, ma, v.h, o, cap, n))
+        return v, img
 
     def matrices(self):
         return self.abc
@@ -293,15 +340,26 @@ class PlusProver:
         self.ctx, self.A, self.M, self.b, self.k, self.l, self.B, self.transcript, self.acc = ctx, A, list(M), b, k, l, B, transcript, []
         self.pinned = PinnedMatrices(ctx, self.M)      # the reference's prover owns M as well
 
-    def prove(self, comps):      # plus.rs:80-117 -> PlusProof dict(linb2x, lproof, cmproof, dproof)
-        lproof = []
+    def prove(self, comps):      # plus.rs:80-117 -> PlusProof dict(linb2x, lproof, cmproof, dproof); the witnesses stay on the device between the steps
+        L_ = _L(); lproof = []
         for comp in comps:
-            linb, lp = comp.linearize(self.transcript)
-            lproof.append(lp); self.acc.append(linb["f"])
-        cmproof, x, g = Mlin(self.ctx, np.stack(self.acc), self.b, self.k, self.l).mlin(self.A, self.M, self.transcript)
-        dproof, F = decompose(self.ctx, self.A, g, x["ro"], self.M, self.B)
-        self.acc = [F[0], F[1]]      # keep only the accumulated instance
-        return dict(linb2x=x, lproof=lproof, cmproof=cmproof, dproof=dproof)
+            v, lp = comp.linearize_resident(self.transcript)
+            lproof.append(lp); self.acc.append(v)
+        n, nE = len(self.acc[0]), 1 + len(self.M); nv = int(n - 1).bit_length()
+        ma = _csr_array(self.M)
+        hs = (vp * len(self.acc))(*[v.h for v in self.acc])
+        x = np.zeros(self.A.kappa * D + 2 * nv + nE * 2 * D, dtype=np.uint64); gh = vp()
+        cmproof = _grow(self.ctx, lambda o, cap, ln: L_.lf_plus_mlin_v(self.ctx.h, self.transcript.h, self.A.h, hs, len(self.acc), self.b, self.k, self.l, ma, len(self.M), o, cap, ln, ptr(x), C.byref(gh)))
+        g = Vec(self.ctx, handle=gh); kd = self.A.kappa * D
+        linb2x = dict(cm_g=x[:kd].reshape(self.A.kappa, D).copy(), ro=x[kd: kd + 2 * nv].reshape(nv, 2).copy(), vo=x[kd + 2 * nv:].reshape(nE, 2, D).copy())
+        dproof = np.zeros(2 * kd + 2 * nE * 2 * D, dtype=np.uint64); f0, f1 = vp(), vp()
+        ro = np.ascontiguousarray(linb2x["ro"])
+        self.ctx.check(L_.lf_plus_decompose_v(self.ctx.h, self.A.h, g.h, ptr(ro), ma, len(self.M), self.B, ptr(dproof), C.byref(f0), C.byref(f1)))
+        self.acc = [Vec(self.ctx, handle=f0), Vec(self.ctx, handle=f1)]      # keep only the accumulated instance
+        return dict(linb2x=linb2x, lproof=lproof, cmproof=cmproof, dproof=dproof)
+
+    def acc_download(self):
+        return [v.download() for v in self.acc]
 
 
 class PlusVerifier:

@@ -204,5 +204,5 @@ def test_plus_prover_three_folds_bit_exact(ctx, oracle):      # plus.rs:216-272 
         assert np.array_equal(proof["cmproof"], want["cmproof"]) and np.array_equal(proof["dproof"], want["dproof"]), fold
         assert all(np.array_equal(a, b) for a, b in zip(proof["lproof"], want["lproof"]))
         assert all(np.array_equal(proof["linb2x"][key], want["linb2x"][key]) for key in ("cm_g", "ro", "vo"))
-        assert all(np.array_equal(a, b) for a, b in zip(prover.acc, oflow.acc))      # the accumulated witnesses
+        assert all(np.array_equal(a, b) for a, b in zip(prover.acc_download(), oflow.acc))      # the accumulated witnesses (device resident between the folds)
         assert verifier.verify(proof) and oflow.verify(proof)

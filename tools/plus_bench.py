@@ -70,6 +70,12 @@ def fold_bench(args, reference_arm):
     def step():
         return plus.PlusProver(ctx, Ad, abc, B, K, l, Bfold, plus.PoseidonTranscript()).prove(comps)
 
+    def step_e2e():
+        pr = plus.PlusProver(ctx, Ad, abc, B, K, l, Bfold, plus.PoseidonTranscript())
+        out = pr.prove([plus.ComR1CS(ctx, abc, f) for f in fs])
+        pr.acc_download()
+        return out
+
     for _ in range(max(args.warmup, 3)):
         step()
     l0 = ctx.launches(); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -79,6 +85,10 @@ def fold_bench(args, reference_arm):
             proof = step()
         b.record(stream); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / args.steps; launches = (ctx.launches() - l0) // args.steps
+    step_e2e(); torch.cuda.synchronize(); a.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    b.record(stream); torch.cuda.synchronize(); ms_e2e = a.elapsed_time(b) / args.steps
     ctx.profile(True); step(); rep = ctx.profile_report(); ctx.profile(False)
     kern = sorted(rep.items(), key=lambda kv: -kv[1][1])
     ok = plus.PlusVerifier(KAPPA, len(abc), Bfold, plus.PoseidonTranscript()).verify(proof)
@@ -98,8 +108,8 @@ def fold_bench(args, reference_arm):
     v = L * n / (ms * 1e-3)
     print(json.dumps(dict(metric=METRIC_FOLD, value=v, unit="elements/s", n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                           dtype="u64 (mod 15912092521325583641, Montgomery on the device)", data="synthetic", config=cfg, clocks=cs.summary(), gpu_launches=int(launches),
-                          value_note="every step starts from host witnesses and returns the proof and the two accumulated witnesses to the host: value and e2e are the same measurement",
-                          e2e=dict(value=v, unit="elements/s", ms_per_step=ms, h2d_bytes_per_step=int(2 * sum(f.nbytes for f in fs) + fs[0].nbytes), d2h_bytes_per_step=int(3 * fs[0].nbytes)),
+                          value_note="value: the instances' witnesses resident on the device (uploaded once), the accumulated witnesses stay there; e2e: fresh ComR1CS objects per step (witness upload inside) and the two accumulated witnesses read back",
+                          e2e=dict(value=L * n / (ms_e2e * 1e-3), unit="elements/s", ms_per_step=ms_e2e, h2d_bytes_per_step=int(sum(f.nbytes for f in fs)), d2h_bytes_per_step=int(2 * fs[0].nbytes)),
                           roofline=dict(bound="latency", kernel=kern[0][0], note="host-paced sumcheck rounds (L + 3 sumchecks per step); per-kernel device time below",
                                         kernels=[dict(kernel=k_, launches=c, total_ms=round(t, 4)) for k_, (c, t) in kern if t >= 0.05]),
                           cpu_baseline=cpu, verify=verify, verified=verify["verified"])))
