@@ -312,6 +312,44 @@ def decompose_verify(proof, kappa, n_M, cm_f, v, B):      # DecompProof::verify,
     raise LfError(rc, "decomposition proof rejected as malformed")
 
 
+def estimate_bound(sop, L, d, k):      # utils.rs:105-115
+    a = sop * L
+    c = d // 2 + d * k + 1
+    return int(np.ceil((a + np.sqrt(float(a * a + 4 * a * c))) / 2.0))
+
+
+def sparse_gadget_decompose(M, b, k, p=15912092521325583641):
+    """SparseMatrix::gadget_decompose(b, k): column j becomes the k columns j k + t with entries M[i][j] b^t, so that the result times
+    gadget_decompose(z, b, k) equals M z (stark-rings-linalg; the digit order is the one of Vec::gadget_decompose: digit t of element j at j k + t)."""
+    nnz = M["col"].size
+    col = (M["col"].astype(np.uint64)[:, None] * np.uint64(k) + np.arange(k, dtype=np.uint64)[None, :]).reshape(-1)
+    pw = [pow(b, t, p) for t in range(k)]
+    val = np.zeros((nnz, k, D), dtype=np.uint64)
+    src = M["val"].astype(object)
+    for t in range(k):
+        val[:, t, :] = ((src * pw[t]) % p).astype(np.uint64)
+    row_ptr = (M["row_ptr"].astype(np.uint64) * np.uint64(k)).astype(np.uint64)
+    return dict(nrows=M["nrows"], ncols=M["ncols"] * k, row_ptr=np.ascontiguousarray(row_ptr), col=np.ascontiguousarray(col), val=np.ascontiguousarray(val.reshape(nnz * k, D)))
+
+
+def pad_rows(M, n):      # SparseMatrix::pad_rows: empty rows up to n
+    if M["nrows"] >= n:
+        return M
+    rp = np.concatenate([M["row_ptr"], np.full(n - M["nrows"], M["row_ptr"][-1], dtype=np.uint64)])
+    return dict(M, nrows=n, row_ptr=np.ascontiguousarray(rp))
+
+
+def r1cs_decomposed_square(abc, n, b, k):      # r1cs.rs:171-185: n x m -> n x n with m k = n
+    return [pad_rows(sparse_gadget_decompose(M, b, k), n) for M in abc]
+
+
+def com_r1cs_new(ctx, abc, z, b, k):
+    """ComR1CS::new (r1cs.rs:46-58): f = gadget_decompose(z, b, k) on the device; the commitment cm_f = A f is RgInstance::from_f's, not needed here."""
+    from .api import FORM_COEFF
+    f = ctx.gadget_decompose(ctx.upload(np.ascontiguousarray(z, dtype=np.uint64), FORM_COEFF), b, k).download()
+    return ComR1CS(ctx, abc, f)
+
+
 class PinnedMatrices:
     """lf_plus_csr_pin for a list of csr dicts: resident copies of the static matrices for as long as this object lives."""
 

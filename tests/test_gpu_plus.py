@@ -206,3 +206,31 @@ def test_plus_prover_three_folds_bit_exact(ctx, oracle):      # plus.rs:216-272 
         assert all(np.array_equal(proof["linb2x"][key], want["linb2x"][key]) for key in ("cm_g", "ro", "vo"))
         assert all(np.array_equal(a, b) for a, b in zip(prover.acc_download(), oflow.acc))      # the accumulated witnesses (device resident between the folds)
         assert verifier.verify(proof) and oflow.verify(proof)
+
+
+def test_plus_prove_reference_setup(ctx, oracle):      # plus.rs:161-214 (test_prove) with the reference's own construction of the instances
+    d, n, k, kappa, L = 16, 1 << 15, 2, 2, 3
+    B = plus.estimate_bound(d * 128, L, d, k) + 1      # utils.rs:105-115
+    assert B == 6186
+    m, l = n // k, pc.frog_l()
+    rng = np.random.default_rng(9)
+    zs = [np.zeros((m, d), dtype=np.uint64) for _ in range(2)]
+    for z in zs:
+        z[:, 0] = rng.integers(0, 2, size=m).astype(np.uint64)
+    abc = plus.r1cs_decomposed_square([pc.identity(m)] * 3, n, B, k)      # r1cs.rs:171-185
+    assert abc[0]["nrows"] == n and abc[0]["ncols"] == n
+    comps = [plus.com_r1cs_new(ctx, abc, z, B, k) for z in zs]
+    for c_, z in zip(comps, zs):
+        assert np.array_equal(c_.f, oracle.gadget_decompose(RING, z, B, k))      # ComR1CS::new's f
+        # (A f) o (B f) = C f row by row: the decomposed system holds the relation of the original one (check_relation)
+        zf = np.zeros((n, d), dtype=np.uint64); zf[:m] = z      # identity rows recompose z
+        assert np.array_equal(c_.f[0::k][:, 0], z[:, 0])
+    _, A = pc.range_check_inputs(n, kappa, seed=3)
+    prover = plus.PlusProver(ctx, plus.Matrix(ctx, A), abc, 8, k, l, B, seeded())
+    proof = prover.prove(comps)
+    assert plus.PlusVerifier(kappa, 3, B, seeded()).verify(proof)
+    oflow = pc.OraclePlus(oracle, A, abc, 8, k, l, B)
+    want = oflow.prove([(abc, c_.f) for c_ in comps])
+    assert np.array_equal(proof["cmproof"], want["cmproof"]) and np.array_equal(proof["dproof"], want["dproof"]) and oflow.verify(proof)
+    t = dict(proof); t["lproof"] = [proof["lproof"][1], proof["lproof"][0]]
+    assert not plus.PlusVerifier(kappa, 3, B, seeded()).verify(t)
