@@ -82,29 +82,56 @@ struct DevSet { const unsigned char* codes = nullptr; size_t code_pitch = 0; con
 // (the double commitment: k * 16 columns) sums several rows before the block reduction instead of one
 unsigned chunks_for(size_t n, int tpb, size_t ncols = 1) { return (unsigned)std::min<size_t>(std::max<size_t>((n + tpb - 1) / tpb, 1), std::max<size_t>(148 * 4 / std::max<size_t>(ncols, 1), 1)); }
 
-// out = sum over block partials -> host, `cols` ring elements; scale: 0 as is, 1 from Montgomery, 2 times 2^64 (canonical x canonical products)
-void finish_wsum(Eng& E, u64* partial, unsigned chunks, size_t cols, int scale, u64* out_host) {
-    u64* d_out = E.small_dev(cols * PD);
-    E.reduce_partials(partial, (int)chunks, cols * PD, d_out);
-    E.download_words(d_out, cols * PD, out_host);
-    if (scale == 1) for (size_t i = 0; i < cols * PD; ++i) out_host[i] = Fm::from_mont(out_host[i]);
-    if (scale == 2) for (size_t i = 0; i < cols * PD; ++i) out_host[i] = Fm::to_mont(out_host[i]);
-}
-// sum_x W[x] entry(x, col) for every column of a set; W scalar (Montgomery eq table) or ring-valued (canonical, 16 words per x)
-void wsum_set(Eng& E, const DevSet& S, const u64* W, bool ring_w, u64* out_host) {
-    if (S.codes) {
-        const unsigned ch = chunks_for(S.nrows, 256, S.ncols); u64* partial = E.partial_dev((size_t)ch * S.ncols * PD);
-        if (ring_w) E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, (unsigned)S.ncols), 256, 0, E.st()>>>(W, S.codes, S.code_pitch, S.nrows, partial); });
-        else E.launch("k_plus_wsum_scalar_mono", [&] { k_plus_wsum_scalar_mono<<<dim3(ch, (unsigned)S.ncols), 256, 0, E.st()>>>(W, S.codes, S.code_pitch, S.nrows, partial); });
-        finish_wsum(E, partial, ch, S.ncols, ring_w ? 0 : 1, out_host);
-    } else {
-        const DevSparse& G = *S.gen; const int tpb = ring_w ? 128 : 256;
-        const unsigned ch = chunks_for(std::max<size_t>(G.nnz / std::max<size_t>(G.ncols, 1), 1), tpb, G.ncols); u64* partial = E.partial_dev((size_t)ch * G.ncols * PD);
-        if (ring_w) E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, (unsigned)G.ncols), 128, 0, E.st()>>>(W, G.col_ptr, G.erow, G.val, partial); });
-        else E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, (unsigned)G.ncols), 256, 0, E.st()>>>(W, G.col_ptr, G.erow, G.val, partial); });
-        finish_wsum(E, partial, ch, G.ncols, ring_w ? 2 : 0, out_host);
+// Weighted sums  out[col] = sum_x W[x] (*) entry(x, col)  are queued and flushed together: every launch writes its block partials into one
+// shared [chunk][columns of all jobs][16] buffer, then ONE reduction and ONE read-back serve them all (a range check has ~30 of them, a
+// commitment transformation ~100; issued one by one each costs a reduction launch and a stream synchronisation).
+enum WKind { W_SCALAR_MONO, W_SCALAR_GENERAL, W_SCALAR_SMALL, W_RING_MONO, W_RING_GENERAL, W_RING_SMALL };
+struct WJob { WKind kind; const u64* W; size_t nrows, cols; u64* out;
+              const unsigned char* codes = nullptr; size_t code_pitch = 0;                       // *_MONO
+              const u64* col_ptr = nullptr; const u32* erow = nullptr; const u64* val = nullptr;  // *_GENERAL (erow == nullptr: dense, entry e in row e)
+              const signed char* tau = nullptr; };                                               // *_SMALL
+struct WsumBatch {
+    Eng& E; std::vector<WJob> jobs; size_t total_cols = 0;
+    explicit WsumBatch(Eng& e) : E(e) {}
+    void add(const WJob& j) { jobs.push_back(j); total_cols += j.cols; }
+    void mono(const u64* W, bool ring_w, const unsigned char* codes, size_t pitch, size_t nrows, size_t cols, u64* out) { WJob j{ring_w ? W_RING_MONO : W_SCALAR_MONO, W, nrows, cols, out}; j.codes = codes; j.code_pitch = pitch; add(j); }
+    void general(const u64* W, bool ring_w, const u64* col_ptr, const u32* erow, const u64* val, size_t rows_per_col, size_t cols, u64* out) { WJob j{ring_w ? W_RING_GENERAL : W_SCALAR_GENERAL, W, rows_per_col, cols, out}; j.col_ptr = col_ptr; j.erow = erow; j.val = val; add(j); }
+    void small(const u64* W, bool ring_w, const signed char* tau, size_t nrows, u64* out) { WJob j{ring_w ? W_RING_SMALL : W_SCALAR_SMALL, W, nrows, 1, out}; j.tau = tau; add(j); }
+    // scale of a result: scalar weights are Montgomery (x mono / small entries: result Montgomery; x canonical entries: canonical); ring weights are
+    // canonical (x canonical general entries: the products come out times 2^-64)
+    static int scale_of(WKind k) { return k == W_SCALAR_MONO || k == W_SCALAR_SMALL ? 1 : k == W_RING_GENERAL ? 2 : 0; }
+    void flush() {
+        if (jobs.empty()) return;
+        size_t max_rows = 1; for (auto& j : jobs) max_rows = std::max(max_rows, j.nrows);
+        const unsigned ch = (unsigned)std::min<size_t>(std::max<size_t>((max_rows + 1023) / 1024, 8), std::max<size_t>(148 * 4 / std::max<size_t>(total_cols / jobs.size(), 1), 8));
+        u64* partial = E.partial_dev((size_t)ch * total_cols * PD); const SmallArgs sm = small_consts_cached();
+        size_t off = 0;
+        for (auto& j : jobs) { const POut po{partial, (unsigned)total_cols, (unsigned)off}; const dim3 g(ch, (unsigned)j.cols);
+            switch (j.kind) {
+                case W_SCALAR_MONO: E.launch("k_plus_wsum_scalar_mono", [&] { k_plus_wsum_scalar_mono<<<g, 256, 0, E.st()>>>(j.W, j.codes, j.code_pitch, j.nrows, po); }); break;
+                case W_RING_MONO: E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<g, 256, 0, E.st()>>>(j.W, j.codes, j.code_pitch, j.nrows, po); }); break;
+                case W_SCALAR_GENERAL: E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<g, 256, 0, E.st()>>>(j.W, j.col_ptr, j.erow, j.val, po); }); break;
+                case W_RING_GENERAL: E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<g, 128, 0, E.st()>>>(j.W, j.col_ptr, j.erow, j.val, po); }); break;
+                case W_SCALAR_SMALL: E.launch("k_plus_wsum_scalar_small", [&] { k_plus_wsum_scalar_small<<<g, 256, 0, E.st()>>>(j.W, j.tau, j.nrows, sm, po); }); break;
+                case W_RING_SMALL: E.launch("k_plus_wsum_ring_small", [&] { k_plus_wsum_ring_small<<<g, 256, 0, E.st()>>>(j.W, j.tau, j.nrows, sm, po); }); break;
+            }
+            off += j.cols; }
+        u64* d_out = E.small_dev(total_cols * PD);
+        E.reduce_partials(partial, (int)ch, total_cols * PD, d_out);
+        std::vector<u64> host(total_cols * PD); E.download_words(d_out, total_cols * PD, host.data());
+        off = 0;
+        for (auto& j : jobs) { const int sc = scale_of(j.kind); const u64* src = host.data() + off * PD;
+            for (size_t i = 0; i < j.cols * PD; ++i) j.out[i] = sc == 1 ? Fm::from_mont(src[i]) : sc == 2 ? Fm::to_mont(src[i]) : src[i];
+            off += j.cols; }
+        jobs.clear(); total_cols = 0;
     }
-}
+    static const SmallArgs& small_consts_cached() { static const SmallArgs s = [] { SmallArgs x; for (int t = -8; t < 8; ++t) x.v[t & 15] = Fm::to_mont(t < 0 ? Fm::P - (u64)(-t) : (u64)t); return x; }(); return s; }
+    // every column of a set: monomial codes or general entries
+    void set(const DevSet& S, const u64* W, bool ring_w, u64* out) {
+        if (S.codes) mono(W, ring_w, S.codes, S.code_pitch, S.nrows, S.ncols, out);
+        else general(W, ring_w, S.gen->col_ptr, S.gen->erow, S.gen->val, std::max<size_t>(S.gen->nnz / std::max<size_t>(S.gen->ncols, 1), 1), S.gen->ncols, out);
+    }
+};
 SmallArgs small_consts() { SmallArgs s; for (int t = -8; t < 8; ++t) s.v[t & 15] = Fm::to_mont(t < 0 ? Fm::P - (u64)(-t) : (u64)t); return s; }
 void eq_table(Eng& E, const std::vector<u64>& c, u64* d_out, size_t N) {
     if (c.size() > 40) throw LfException(LF_ERR_UNSUPPORTED, "more than 40 variables");
@@ -187,11 +214,12 @@ SetCheckResult set_check_core(Eng& E, Tr& T, int nvars, const std::vector<DevSet
     for (auto& m : M) { u64* wv = E.dalloc<u64>(std::max<size_t>(m.ncols, 1) * PD);
         E.launch("k_plus_mt_eq", [&] { k_plus_mt_eq<<<Eng::blocks_for(m.ncols, 128), 128, 0, E.st()>>>(R.d_eq_r, m.col_ptr, m.erow, m.val, m.ncols, wv); });
         R.d_w.push_back(wv); }
-    R.e.assign((1 + M.size()) * nM * ncols * PD, 0);
+    R.e.assign((1 + M.size()) * nM * ncols * PD, 0); R.b.assign(nV * PD, 0);
+    WsumBatch wb(E);
     for (size_t mi = 0; mi <= M.size(); ++mi) for (size_t i = 0; i < nM; ++i)
-        wsum_set(E, mats[i], mi == 0 ? R.d_eq_r : R.d_w[mi - 1], mi != 0, R.e.data() + (mi * nM + i) * ncols * PD);
-    R.b.assign(nV * PD, 0);
-    for (size_t i = 0; i < nV; ++i) wsum_set(E, vecs[i], R.d_eq_r, false, R.b.data() + i * PD);
+        wb.set(mats[i], mi == 0 ? R.d_eq_r : R.d_w[mi - 1], mi != 0, R.e.data() + (mi * nM + i) * ncols * PD);
+    for (size_t i = 0; i < nV; ++i) wb.set(vecs[i], R.d_eq_r, false, R.b.data() + i * PD);
+    wb.flush();
     T.absorb_slice(R.e.data(), R.e.size() / PD); T.absorb_slice(R.b.data(), R.b.size() / PD);      // absorb_evaluations, setchk.rs:346-356
     return R;
 }
@@ -318,30 +346,25 @@ std::vector<u64> range_check_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* i
         for (int i = 0; i < L; ++i) { DevSet s; s.codes = inst[i]->mtau_codes; s.code_pitch = inst[i]->code_pitch; s.nrows = I0.n; s.ncols = 1; vecs.push_back(s); }
         R = set_check_core(E, T, nvars, mats, vecs, Ms);
         // evaluations at r (rgchk.rs:101-171): v = c[0] = MLE(f)(r) coefficient-wise, a[0] = MLE(tau)(r), and through w_i = M_i^T eq(r, .) the M_i-images
-        const size_t nE = 1 + Ms.size(), n = I0.n; const SmallArgs sm = small_consts();
+        const size_t nE = 1 + Ms.size(), n = I0.n;
         std::vector<u64> img = {(u64)L, (u64)I0.k, (u64)I0.l, (u64)I0.kappa, I0.b}; { auto w = R.words(); img.insert(img.end(), w.begin(), w.end()); }
         u64* cp = E.dalloc<u64>(2); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
-        std::vector<std::vector<u64>> av(L), cv(L);
+        std::vector<std::vector<u64>> vv(L, std::vector<u64>(PD)), ar(L, std::vector<u64>(nE * PD)), bv(L, std::vector<u64>(nE * PD)), cv(L, std::vector<u64>(nE * PD)), av(L, std::vector<u64>(nE));
+        WsumBatch wb(E);
         for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
-            std::vector<u64> v(PD), a(nE), b(nE * PD), cc(nE * PD), tmp(PD);
-            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-              E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, 1), 256, 0, E.st()>>>(R.d_eq_r, cp, nullptr, I.f, partial); }); finish_wsum(E, partial, ch, 1, 0, v.data()); }
-            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-              E.launch("k_plus_wsum_scalar_small", [&] { k_plus_wsum_scalar_small<<<dim3(ch, 1), 256, 0, E.st()>>>(R.d_eq_r, I.tau, n, sm, partial); }); finish_wsum(E, partial, ch, 1, 1, tmp.data()); a[0] = tmp[0]; }
-            std::memcpy(b.data(), R.b.data() + (size_t)li * PD, 8 * PD); std::memcpy(cc.data(), v.data(), 8 * PD);
+            wb.general(R.d_eq_r, false, cp, nullptr, I.f, n, 1, vv[li].data());                       // v = c[0] = MLE(f)(r), coefficient-wise
+            wb.small(R.d_eq_r, false, I.tau, n, ar[li].data());                                       // a[0] = MLE(tau)(r)
             for (size_t mi = 0; mi < Ms.size(); ++mi) { const u64* W = R.d_w[mi];
-                { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-                  E.launch("k_plus_wsum_ring_small", [&] { k_plus_wsum_ring_small<<<dim3(ch, 1), 256, 0, E.st()>>>(W, I.tau, n, sm, partial); }); finish_wsum(E, partial, ch, 1, 0, tmp.data()); a[1 + mi] = tmp[0]; }
-                { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-                  E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, 1), 256, 0, E.st()>>>(W, I.mtau_codes, I.code_pitch, n, partial); }); finish_wsum(E, partial, ch, 1, 0, &b[(1 + mi) * PD]); }
-                { const unsigned ch = chunks_for(n, 128); u64* partial = E.partial_dev((size_t)ch * PD);
-                  E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(W, cp, nullptr, I.f, partial); }); finish_wsum(E, partial, ch, 1, 2, &cc[(1 + mi) * PD]); }
-            }
-            for (auto* x : {&v, &a, &b, &cc, }) img.insert(img.end(), x->begin(), x->end());
-            img.insert(img.end(), I.fcoms.begin(), I.fcoms.end());
-            av[li] = a; cv[li] = cc;
+                wb.small(W, true, I.tau, n, ar[li].data() + (1 + mi) * PD);                           // a[1 + i] = ct(MLE(M_i tau)(r))
+                wb.mono(W, true, I.mtau_codes, I.code_pitch, n, 1, bv[li].data() + (1 + mi) * PD);     // b[1 + i] = MLE(M_i m_tau)(r)
+                wb.general(W, true, cp, nullptr, I.f, n, 1, cv[li].data() + (1 + mi) * PD); }          // c[1 + i] = MLE(M_i f)(r)
         }
-        E.dfree(cp);
+        wb.flush(); E.dfree(cp);
+        for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
+            std::memcpy(bv[li].data(), R.b.data() + (size_t)li * PD, 8 * PD); std::memcpy(cv[li].data(), vv[li].data(), 8 * PD);
+            for (size_t e = 0; e < nE; ++e) av[li][e] = ar[li][e * PD];
+            for (auto* x : {&vv[li], &av[li], &bv[li], &cv[li]}) img.insert(img.end(), x->begin(), x->end());
+            img.insert(img.end(), I.fcoms.begin(), I.fcoms.end()); }
         for (int li = 0; li < L; ++li) { for (u64 a : av[li]) absorb_field(T, a); T.absorb_slice(cv[li].data(), nE); }      // rgchk.rs:338-343
         return img;
 }
@@ -370,7 +393,7 @@ void cm_prove_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* inst, int L, con
     const size_t nt = tc0.size() * kd * l * PD;
     if (nt > n) throw LfException(LF_ERR_INVALID_SIZE_BOUNDS, "cm: t(z) longer than the witness (cm.rs:150-161)");
     // scalar tables eq(r, .) | S = sum_l tau_l (kept; every sumcheck folds copies), ring tables G | U (rebuilt per sumcheck)
-    const SmallArgs sm = small_consts();
+    const SmallArgs sm = WsumBatch::small_consts_cached();
     u64* sc0 = alloc(2 * N); LF_CUDA(cudaMemcpyAsync(sc0, R.d_eq_r, N * 8, cudaMemcpyDeviceToDevice, E.st())); LF_CUDA(cudaMemsetAsync(sc0 + N, 0, N * 8, E.st()));
     { TauList tl; if (L > 64) throw LfException(LF_ERR_UNSUPPORTED, "cm: more than 64 instances"); tl.n = L; for (int li = 0; li < L; ++li) tl.p[li] = inst[li]->tau;
       E.launch("k_plus_tau_sum", [&] { k_plus_tau_sum<<<Eng::blocks_for(n, 256), 256, 0, E.st()>>>(tl, n, sm, sc0 + N); }); }
@@ -417,18 +440,12 @@ void cm_prove_core(Eng& E, Tr& T, int nvars, lf_plus_rg* const* inst, int L, con
         evals[z].assign((size_t)L * nE * 4 * PD, 0);
         std::vector<u64*> d_w; for (int mi = 0; mi < n_M; ++mi) { u64* wv = alloc(std::max<size_t>(Ms[mi].ncols, 1) * PD);
             E.launch("k_plus_mt_eq", [&] { k_plus_mt_eq<<<Eng::blocks_for(Ms[mi].ncols, 128), 128, 0, E.st()>>>(eq_ro, Ms[mi].col_ptr, Ms[mi].erow, Ms[mi].val, Ms[mi].ncols, wv); }); d_w.push_back(wv); }
-        for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
-            for (size_t e = 0; e < nE; ++e) { const bool ring = e > 0; const u64* W = ring ? d_w[e - 1] : eq_ro; u64* out = evals[z].data() + ((li * nE + e) * 4) * PD; const unsigned c256 = chunks_for(n, 256), c128 = chunks_for(n, 128);
-                { u64* partial = E.partial_dev((size_t)c256 * PD);
-                  if (ring) E.launch("k_plus_wsum_ring_small", [&] { k_plus_wsum_ring_small<<<dim3(c256, 1), 256, 0, E.st()>>>(W, I.tau, n, sm, partial); });
-                  else E.launch("k_plus_wsum_scalar_small", [&] { k_plus_wsum_scalar_small<<<dim3(c256, 1), 256, 0, E.st()>>>(W, I.tau, n, sm, partial); });
-                  finish_wsum(E, partial, c256, 1, ring ? 0 : 1, out); }
-                { DevSet S; S.codes = I.mtau_codes; S.code_pitch = I.code_pitch; S.nrows = n; S.ncols = 1; wsum_set(E, S, W, ring, out + PD); }
-                for (int q = 0; q < 2; ++q) { const u64* src = q == 0 ? I.f : d_h[li]; const unsigned chn = ring ? c128 : c256; u64* partial = E.partial_dev((size_t)chn * PD);
-                  if (ring) E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(chn, 1), 128, 0, E.st()>>>(W, cp, nullptr, src, partial); });
-                  else E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(chn, 1), 256, 0, E.st()>>>(W, cp, nullptr, src, partial); });
-                  finish_wsum(E, partial, chn, 1, ring ? 2 : 0, out + (2 + q) * PD); }
-            } }
+        { WsumBatch wb(E);
+          for (int li = 0; li < L; ++li) { const lf_plus_rg& I = *inst[li];
+            for (size_t e = 0; e < nE; ++e) { const bool ring = e > 0; const u64* W = ring ? d_w[e - 1] : eq_ro; u64* out = evals[z].data() + ((li * nE + e) * 4) * PD;
+                wb.small(W, ring, I.tau, n, out); wb.mono(W, ring, I.mtau_codes, I.code_pitch, n, 1, out + PD);
+                wb.general(W, ring, cp, nullptr, I.f, n, 1, out + 2 * PD); wb.general(W, ring, cp, nullptr, d_h[li], n, 1, out + 3 * PD); } }
+          wb.flush(); }
         T.absorb_slice(evals[z].data(), evals[z].size() / PD);      // absorb_evaluations (cm.rs:581-588)
     }
     // g_l = s0 tau + s1 m_tau + s2 f + h (cm.rs:165-182)
@@ -466,12 +483,10 @@ lf_plus_rg* rg_from_f_core(Eng& E, lf_ctx* c, const lf_plus_mat* A, const uint64
         mark("digits");
         // comM_f[kk] = A * M_f[kk]: rotations only.  com = hconcat: row r, column kk * d + c
         I->comM.assign((size_t)k * kappa * PD * PD, 0); std::vector<u64> com(kappa * (size_t)k * PD * PD);
-        for (size_t r = 0; r < kappa; ++r) {
-            const unsigned ch = chunks_for(n, 256, (size_t)k * PD); u64* partial = E.partial_dev((size_t)ch * k * PD * PD);
-            E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, (unsigned)(k * PD)), 256, 0, E.st()>>>(A->d + r * n * PD, I->codes, I->code_pitch, n, partial); });
-            finish_wsum(E, partial, ch, (size_t)k * PD, 0, com.data() + r * k * PD * PD);
-            for (int kk = 0; kk < k; ++kk) std::memcpy(&I->comM[(((size_t)kk * kappa + r) * PD) * PD], &com[(r * k + kk) * PD * PD], 8 * PD * PD);
-        }
+        { WsumBatch wb(E);
+          for (size_t r = 0; r < kappa; ++r) wb.mono(A->d + r * n * PD, true, I->codes, I->code_pitch, n, (size_t)k * PD, com.data() + r * k * PD * PD);
+          wb.flush(); }
+        for (size_t r = 0; r < kappa; ++r) for (int kk = 0; kk < k; ++kk) std::memcpy(&I->comM[(((size_t)kk * kappa + r) * PD) * PD], &com[(r * k + kk) * PD * PD], 8 * PD * PD);
         mark("A*M_f");
         // tau = split(com, n, d/2, l) (utils.rs:12-43): l balanced base-(d/2) digits of every coefficient, digit-major per entry; host work on kappa * k * d elements
         I->tau_host.assign(n, 0); std::vector<signed char> tau8(n, 0); std::vector<unsigned char> mt(I->code_pitch, 0);      // exp(0) = X^0
@@ -484,16 +499,12 @@ lf_plus_rg* rg_from_f_core(Eng& E, lf_ctx* c, const lf_plus_mat* A, const uint64
         LF_CUDA(cudaMemcpyAsync(I->tau, tau8.data(), n, cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemcpyAsync(I->mtau_codes, mt.data(), I->code_pitch, cudaMemcpyHostToDevice, E.st()));
         mark("split");
         // cm_f = A f, C_Mf = A tau, cm_mtau = A m_tau (rgchk.rs:322-327)
-        I->fcoms.assign(3 * kappa * PD, 0); const SmallArgs sm = small_consts();
+        I->fcoms.assign(3 * kappa * PD, 0);
         u64* cp = E.dalloc<u64>(2); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
-        for (size_t r = 0; r < kappa; ++r) { const u64* Ar = A->d + r * n * PD;
-            { const unsigned ch = chunks_for(n, 128); u64* partial = E.partial_dev((size_t)ch * PD);
-              E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(Ar, cp, nullptr, I->f, partial); }); finish_wsum(E, partial, ch, 1, 2, &I->fcoms[r * PD]); }
-            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-              E.launch("k_plus_wsum_ring_small", [&] { k_plus_wsum_ring_small<<<dim3(ch, 1), 256, 0, E.st()>>>(Ar, I->tau, n, sm, partial); }); finish_wsum(E, partial, ch, 1, 0, &I->fcoms[(kappa + r) * PD]); }
-            { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-              E.launch("k_plus_wsum_ring_mono", [&] { k_plus_wsum_ring_mono<<<dim3(ch, 1), 256, 0, E.st()>>>(Ar, I->mtau_codes, I->code_pitch, n, partial); }); finish_wsum(E, partial, ch, 1, 0, &I->fcoms[(2 * kappa + r) * PD]); }
-        }
+        { WsumBatch wb(E);
+          for (size_t r = 0; r < kappa; ++r) { const u64* Ar = A->d + r * n * PD;
+            wb.general(Ar, true, cp, nullptr, I->f, n, 1, &I->fcoms[r * PD]); wb.small(Ar, true, I->tau, n, &I->fcoms[(kappa + r) * PD]); wb.mono(Ar, true, I->mtau_codes, I->code_pitch, n, 1, &I->fcoms[(2 * kappa + r) * PD]); }
+          wb.flush(); }
         E.sync(); E.dfree(cp);
         mark("commitments");
         g.p = nullptr; return I.release();
@@ -546,8 +557,7 @@ std::vector<u64> r1cs_linearize_core(Eng& E, Tr& T, const lf_csr* abc, const u64
     eq_table(E, ro, eq, N); const u64 cph[2] = {0, n}; E.h2d(cp, cph, 16);
     u64* cpN = alloc(2); const u64 cphN[2] = {0, N}; E.h2d(cpN, cphN, 16);
     std::vector<u64> v4(4 * PD);
-    for (int q = 0; q < 4; ++q) { const size_t cnt = q == 0 ? n : N; const unsigned ch = chunks_for(cnt, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-        E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, 1), 256, 0, E.st()>>>(eq, q == 0 ? cp : cpN, nullptr, q == 0 ? d_f : G + (size_t)(q - 1) * N * PD, partial); }); finish_wsum(E, partial, ch, 1, 0, &v4[q * PD]); }
+    { WsumBatch wb(E); for (int q = 0; q < 4; ++q) wb.general(eq, false, q == 0 ? cp : cpN, nullptr, q == 0 ? d_f : G + (size_t)(q - 1) * N * PD, q == 0 ? n : N, 1, &v4[q * PD]); wb.flush(); }
     T.absorb_slice(v4.data(), 4);
     for (auto* x : {&ro, &msgs, &v4}) img.insert(img.end(), x->begin(), x->end());
     return img;
@@ -774,15 +784,12 @@ static void decompose_core(lf_ctx* c, const lf_plus_mat* A, const uint64_t* f, b
         std::vector<u64*> w[2]; for (int q = 0; q < 2; ++q) for (auto& m : Ms) { u64* wv = alloc(n * PD);
             E.launch("k_plus_mt_eq", [&] { k_plus_mt_eq<<<Eng::blocks_for(m.ncols, 128), 128, 0, E.st()>>>(eq + q * N, m.col_ptr, m.erow, m.val, m.ncols, wv); }); w[q].push_back(wv); }
         u64 *C = proof, *v = proof + 2 * kappa * PD;
-        for (int z = 0; z < 2; ++z) { const u64* Fz = F + (size_t)z * n * PD;
-            for (size_t r = 0; r < kappa; ++r) { const unsigned ch = chunks_for(n, 128); u64* partial = E.partial_dev((size_t)ch * PD);      // C_z = A F_z
-                E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(A->d + r * n * PD, cp, nullptr, Fz, partial); }); finish_wsum(E, partial, ch, 1, 2, C + ((size_t)z * kappa + r) * PD); }
-            for (size_t e = 0; e < nE; ++e) for (int q = 0; q < 2; ++q) { u64* out = v + (((size_t)z * nE + e) * 2 + q) * PD;      // (MLE(.)(r_a), MLE(.)(r_b)) of F_z and of every M_j F_z
-                if (e == 0) { const unsigned ch = chunks_for(n, 256); u64* partial = E.partial_dev((size_t)ch * PD);
-                    E.launch("k_plus_wsum_scalar_general", [&] { k_plus_wsum_scalar_general<<<dim3(ch, 1), 256, 0, E.st()>>>(eq + q * N, cp, nullptr, Fz, partial); }); finish_wsum(E, partial, ch, 1, 0, out); }
-                else { const unsigned ch = chunks_for(n, 128); u64* partial = E.partial_dev((size_t)ch * PD);
-                    E.launch("k_plus_wsum_ring_general", [&] { k_plus_wsum_ring_general<<<dim3(ch, 1), 128, 0, E.st()>>>(w[q][e - 1], cp, nullptr, Fz, partial); }); finish_wsum(E, partial, ch, 1, 2, out); } }
-        }
+        { WsumBatch wb(E);
+          for (int z = 0; z < 2; ++z) { const u64* Fz = F + (size_t)z * n * PD;
+            for (size_t r = 0; r < kappa; ++r) wb.general(A->d + r * n * PD, true, cp, nullptr, Fz, n, 1, C + ((size_t)z * kappa + r) * PD);      // C_z = A F_z
+            for (size_t e = 0; e < nE; ++e) for (int q = 0; q < 2; ++q)      // (MLE(.)(r_a), MLE(.)(r_b)) of F_z and of every M_j F_z
+                wb.general(e == 0 ? eq + q * N : w[q][e - 1], e != 0, cp, nullptr, Fz, n, 1, v + (((size_t)z * nE + e) * 2 + q) * PD); }
+          wb.flush(); }
         if (F_host) { LF_CUDA(cudaMemcpyAsync(F_host, F, 2 * n * PD * 8, cudaMemcpyDeviceToHost, E.st())); E.sync(); }
         if (F_dev0) LF_CUDA(cudaMemcpyAsync(F_dev0, F, n * PD * 8, cudaMemcpyDeviceToDevice, E.st()));
         if (F_dev1) LF_CUDA(cudaMemcpyAsync(F_dev1, F + n * PD, n * PD * 8, cudaMemcpyDeviceToDevice, E.st()));

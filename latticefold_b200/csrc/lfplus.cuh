@@ -121,7 +121,9 @@ __global__ void k_plus_fold(const u64* __restrict__ in, size_t in_stride, u64* _
 }
 
 // ---- weighted sums  out[col] = sum_x W[x] (*) entry(x, col)  with block partials  partial[chunk][col][16]
-template <class Body> __device__ __forceinline__ void wsum_finish(u64 (&acc)[PD], u64* __restrict__ partial, int ncols) {
+// where a weighted-sum launch puts its block partials: several launches share one [chunk][stride_cols][16] buffer (one reduction, one read-back for all)
+struct POut { u64* p; unsigned stride_cols, col_off; };
+template <class Body> __device__ __forceinline__ void wsum_finish(u64 (&acc)[PD], const POut po) {
     __shared__ u64 sh[8][PD];
 #pragma unroll
     for (int c = 0; c < PD; ++c) {
@@ -130,10 +132,10 @@ template <class Body> __device__ __forceinline__ void wsum_finish(u64 (&acc)[PD]
         if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][c] = v;
     }
     __syncthreads();
-    if (threadIdx.x < PD) { u64 v = 0; for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v = Fm::add(v, sh[wv][threadIdx.x]); partial[((size_t)blockIdx.x * ncols + blockIdx.y) * PD + threadIdx.x] = v; }
+    if (threadIdx.x < PD) { u64 v = 0; for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v = Fm::add(v, sh[wv][threadIdx.x]); po.p[((size_t)blockIdx.x * po.stride_cols + po.col_off + blockIdx.y) * PD + threadIdx.x] = v; }
 }
 // scalar weights (eq(r, .), Montgomery), monomial entries: coefficient `code` of the result collects the weights      setchk.rs:199-214, 251-257
-__global__ void __launch_bounds__(256) k_plus_wsum_scalar_mono(const u64* __restrict__ W, const unsigned char* __restrict__ codes, size_t code_pitch, size_t nrows, u64* __restrict__ partial) {
+__global__ void __launch_bounds__(256) k_plus_wsum_scalar_mono(const u64* __restrict__ W, const unsigned char* __restrict__ codes, size_t code_pitch, size_t nrows, const POut po) {
     u64 acc[PD];
 #pragma unroll
     for (int c = 0; c < PD; ++c) acc[c] = 0;
@@ -143,10 +145,10 @@ __global__ void __launch_bounds__(256) k_plus_wsum_scalar_mono(const u64* __rest
 #pragma unroll
         for (int c = 0; c < PD; ++c) acc[c] = Fm::add(acc[c], cd == c ? wv : 0);
     }
-    wsum_finish<void>(acc, partial, gridDim.y);
+    wsum_finish<void>(acc, po);
 }
 // scalar weights, general entries grouped by column (col_ptr / row / val); row == nullptr: a dense vector, entry e sits in row e
-__global__ void __launch_bounds__(256) k_plus_wsum_scalar_general(const u64* __restrict__ W, const u64* __restrict__ col_ptr, const u32* __restrict__ erow, const u64* __restrict__ val, u64* __restrict__ partial) {
+__global__ void __launch_bounds__(256) k_plus_wsum_scalar_general(const u64* __restrict__ W, const u64* __restrict__ col_ptr, const u32* __restrict__ erow, const u64* __restrict__ val, const POut po) {
     u64 acc[PD];
 #pragma unroll
     for (int c = 0; c < PD; ++c) acc[c] = 0;
@@ -156,10 +158,10 @@ __global__ void __launch_bounds__(256) k_plus_wsum_scalar_general(const u64* __r
 #pragma unroll
         for (int c = 0; c < PD; ++c) acc[c] = Fm::add(acc[c], Fm::mul(wv, val[e * PD + c]));
     }
-    wsum_finish<void>(acc, partial, gridDim.y);
+    wsum_finish<void>(acc, po);
 }
 // ring-valued weights W[x] (16 words each), monomial entries: W[x] X^code is a negacyclic rotation                  rgchk.rs:297-304 (A * M_f), setchk.rs:217-240
-__global__ void __launch_bounds__(256) k_plus_wsum_ring_mono(const u64* __restrict__ W, const unsigned char* __restrict__ codes, size_t code_pitch, size_t nrows, u64* __restrict__ partial) {
+__global__ void __launch_bounds__(256) k_plus_wsum_ring_mono(const u64* __restrict__ W, const unsigned char* __restrict__ codes, size_t code_pitch, size_t nrows, const POut po) {
     u64 acc[PD];
 #pragma unroll
     for (int c = 0; c < PD; ++c) acc[c] = 0;
@@ -174,10 +176,10 @@ __global__ void __launch_bounds__(256) k_plus_wsum_ring_mono(const u64* __restri
             acc[o] = (unsigned)o >= cd ? Fm::add(acc[o], v) : Fm::sub(acc[o], v);
         }
     }
-    wsum_finish<void>(acc, partial, gridDim.y);
+    wsum_finish<void>(acc, po);
 }
 // ring-valued weights, general entries: negacyclic products (both operands canonical: the sum comes out times 2^-64)   rgchk.rs:322 (A f), 167-172 (M f)
-__global__ void __launch_bounds__(128) k_plus_wsum_ring_general(const u64* __restrict__ W, const u64* __restrict__ col_ptr, const u32* __restrict__ erow, const u64* __restrict__ val, u64* __restrict__ partial) {
+__global__ void __launch_bounds__(128) k_plus_wsum_ring_general(const u64* __restrict__ W, const u64* __restrict__ col_ptr, const u32* __restrict__ erow, const u64* __restrict__ val, const POut po) {
     u64 acc[PD];
 #pragma unroll
     for (int c = 0; c < PD; ++c) acc[c] = 0;
@@ -200,11 +202,11 @@ __global__ void __launch_bounds__(128) k_plus_wsum_ring_general(const u64* __res
             v[0] = Fm::neg(top);
         }
     }
-    wsum_finish<void>(acc, partial, gridDim.y);
+    wsum_finish<void>(acc, po);
 }
 // ring-valued weights, small signed scalar entries (tau, |tau| < 8) given as Montgomery constants by value: W[x] * tau[x]   rgchk.rs:323-325 (A tau), 146-156
 struct SmallArgs { u64 v[16]; };      // Montgomery form of -8 .. 7 at index (t & 15)
-__global__ void __launch_bounds__(256) k_plus_wsum_ring_small(const u64* __restrict__ W, const signed char* __restrict__ tau, size_t nrows, SmallArgs sm, u64* __restrict__ partial) {
+__global__ void __launch_bounds__(256) k_plus_wsum_ring_small(const u64* __restrict__ W, const signed char* __restrict__ tau, size_t nrows, SmallArgs sm, const POut po) {
     u64 acc[PD];
 #pragma unroll
     for (int c = 0; c < PD; ++c) acc[c] = 0;
@@ -218,10 +220,10 @@ __global__ void __launch_bounds__(256) k_plus_wsum_ring_small(const u64* __restr
 #pragma unroll
         for (int c = 0; c < PD; ++c) acc[c] = Fm::add(acc[c], Fm::mul(s, wx[c]));
     }
-    wsum_finish<void>(acc, partial, gridDim.y);
+    wsum_finish<void>(acc, po);
 }
 // scalar weights, small scalar entries: sum_x W[x] tau[x] (coefficient 0 of the partial; Montgomery)                 rgchk.rs:131-135
-__global__ void __launch_bounds__(256) k_plus_wsum_scalar_small(const u64* __restrict__ W, const signed char* __restrict__ tau, size_t nrows, SmallArgs sm, u64* __restrict__ partial) {
+__global__ void __launch_bounds__(256) k_plus_wsum_scalar_small(const u64* __restrict__ W, const signed char* __restrict__ tau, size_t nrows, SmallArgs sm, const POut po) {
     u64 acc[PD];
 #pragma unroll
     for (int c = 0; c < PD; ++c) acc[c] = 0;
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(256) k_plus_wsum_scalar_small(const u64* __res
         for (int k = 0; k < 16; ++k) if ((t & 15) == k) s = sm.v[k];
         acc[0] = Fm::add(acc[0], Fm::mul(s, W[x]));
     }
-    wsum_finish<void>(acc, partial, gridDim.y);
+    wsum_finish<void>(acc, po);
 }
 // w = M^T eq(r, .) for a sparse matrix of ring elements held by columns: thread x sums its column                      setchk.rs:217-240 regrouped
 __global__ void k_plus_mt_eq(const u64* __restrict__ eq, const u64* __restrict__ col_ptr, const u32* __restrict__ erow, const u64* __restrict__ val, size_t ncols, u64* __restrict__ w) {
