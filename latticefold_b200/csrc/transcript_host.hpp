@@ -126,6 +126,14 @@ template <class Rg> class Transcript {
     // (REDC = two multiplies instead of a 128-by-64-bit division per reduction: 20.8 -> ~5 us per permutation); absorb / squeeze convert.
     // Matrix entries carry R^2 so that a lazily accumulated row (sum m s R^3, 192 bits) comes back to Montgomery form with two REDC steps.
     static constexpr bool MONT = !LAZY && F::P > (1ull << 32);
+    // 31-bit field (BabyBear): a dot product of 24 lanes runs on 32 x 16-bit partial products in plain 64-bit sums (no carry chains, vectorisable),
+    // the matrix entries split into their low and high 16 bits: sum a m = sum a m_lo + 2^16 sum a m_hi, both sums < 2^52
+    static constexpr bool SMALLP = F::P < (1ull << 32);
+    static inline u64 dot_small(const u64* row, const u64* v, int n) {
+        u64 s0 = 0, s1 = 0;
+        for (int j = 0; j < n; ++j) { const u64 a = (u32)v[j], m = row[j]; s0 += a * (m & 0xFFFFu); s1 += a * (m >> 16); }
+        return (s0 % F::P + ((s1 % F::P) << 16)) % F::P;
+    }
     static constexpr u64 NINV = ~poseidon_inv64(F::P) + 1;
     static inline u64 redc(u64 lo, u64 hi) {                // (hi:lo) / 2^64 mod p for hi < p; branch-free (the conditions are coin flips)
         const u64 m = lo * NINV; const u64 mph = (u64)(((u128)m * F::P) >> 64);
@@ -143,6 +151,7 @@ template <class Rg> class Transcript {
             u64 r = t0 + t1; r += (0 - (u64)(r < t1)) & 0xFFFFFFFFull;
             return r;
         } else if constexpr (MONT) return redc(lo, hi);
+        else if constexpr (F::P < (1ull << 32)) return lo % F::P;      // 31-bit field: every product and multiply-add of the sponge fits one word (hi == 0); a constant-divisor remainder, no 128-bit division
         else return F::reduce128(lo, hi);
     }
     static inline u64 wmul(u64 a, u64 b) { u128 x = (u128)a * b; return wred((u64)x, (u64)(x >> 64)); }
@@ -180,10 +189,14 @@ template <class Rg> class Transcript {
         if (ifma) { poseidon_ifma_dense(mi, st_); return; }
         u64 nx[W];
         for (int i = 0; i < W; ++i) {
-            Acc3 acc; const u64* row = m + i * W;
+            const u64* row = m + i * W;
+            if constexpr (SMALLP) nx[i] = dot_small(row, st_, W);
+            else {
+                Acc3 acc;
 #pragma GCC unroll 24
-            for (int j = 0; j < W; ++j) acc.mac(row[j], st_[j]);
-            nx[i] = acc.reduce();
+                for (int j = 0; j < W; ++j) acc.mac(row[j], st_[j]);
+                nx[i] = acc.reduce();
+            }
         }
         std::memcpy(st_, nx, sizeof st_);
     }
@@ -217,16 +230,19 @@ template <class Rg> class Transcript {
             const u64 a = wadd(st_[0], t.sp_c0[pr]);
             const u64 a2 = wmul(a, a), a3 = wmul(a2, a), a4 = wmul(a2, a2), x0 = wmul(a4, a3);     // depth 3: a^4 and a^3 in parallel
             const u64* row = t.sp_row0[pr]; const u64* col = t.sp_col0[pr];
-            Acc3 acc;                                      // lane 0 last: the other 23 products do not wait for the S-box
+            Acc3 acc; u64 small_dot = 0;                   // lane 0 last: the other 23 products do not wait for the S-box
+            if constexpr (SMALLP) small_dot = dot_small(row + 1, st_ + 1, W - 1);
+            else {
 #pragma GCC unroll 23
-            for (int j = 1; j < W; ++j) acc.mac(row[j], st_[j]);
-            acc.mac(row[0], x0);
+                for (int j = 1; j < W; ++j) acc.mac(row[j], st_[j]);
+                acc.mac(row[0], x0);
+            }
 #pragma GCC unroll 23
             for (int i = 1; i < W; ++i) {
                 if constexpr (MONT) st_[i] = madd(st_[i], wmul(col[i], x0));
                 else { u128 x = (u128)col[i] * x0 + st_[i]; st_[i] = wred((u64)x, (u64)(x >> 64)); }
             }
-            st_[0] = acc.reduce();
+            if constexpr (SMALLP) st_[0] = (small_dot + (row[0] * x0) % F::P) % F::P; else st_[0] = acc.reduce();
         }
         for (; r < RF + RP; ++r) {
             sbox_layer(&t.ark[r * W]);

@@ -46,6 +46,24 @@ def test_product_transcript_matches_oracle_on_long_schedule(oracle):
         assert np.array_equal(a.get_short_challenge(), b.get_short_challenge())
 
 
+@pytest.mark.parametrize("ring", [synth.RING_BABYBEAR, synth.RING_FROG])
+def test_product_transcript_other_rings_match_oracle(oracle, ring):
+    """the BabyBear sponge (one-word remainders, split-multiplier dot products) and the Frog sponge (Montgomery form, branch-free reductions)
+    against the oracle's canonical arithmetic: random and edge lanes, many rate boundaries"""
+    R = synth.RINGS[ring]; p, d = R["p"], R["d"]
+    a, b = lf.Transcript(ring), oracle.transcript(ring)
+    els = synth.uniform_field(p, 23 * d, 11).reshape(23, d)
+    edge = np.array([0, 1, 2, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, 1 << 16, (1 << 16) - 1, min(p - 1, (1 << 31) - 1)], dtype=np.uint64)
+    for step in range(5):
+        a.absorb(els[step * 4:(step + 1) * 4 + step]); b.absorb(els[step * 4:(step + 1) * 4 + step])
+        v = np.resize(np.roll(edge, step), 20 * 2 + step + 1); a.absorb_base(v); b.absorb_base(v)
+        for _ in range(step + 2):
+            assert np.array_equal(a.get_challenge(), b.get_challenge())
+        assert np.array_equal(a.get_short_challenge(), b.get_short_challenge())
+    v = np.full(20 * 4 + 3, p - 1, dtype=np.uint64); a.absorb_base(v); b.absorb_base(v)
+    assert np.array_equal(a.get_challenge(), b.get_challenge())
+
+
 def test_product_transcript_extreme_lanes_match_oracle(oracle):
     """lanes at the edges of the field (0, 1, 2^32 +- 1, p - 2^32, p - 1): the product's Poseidon keeps lazily reduced
     representatives inside a round, the oracle reduces canonically after every operation"""
