@@ -186,6 +186,9 @@ SetCheckResult set_check_core(Eng& E, Tr& T, int nvars, const std::vector<DevSet
     const int n_active = have_rc ? (int)groups.size() : 1;
     Group* d_groups = E.dalloc<Group>(groups.size()); u64* d_w = E.dalloc<u64>(w.size());
     E.h2d(d_groups, groups.data(), groups.size() * sizeof(Group)); E.h2d(d_w, w.data(), w.size() * 8);
+    // flattened (group, column) list of the active groups for the short-table form of the round kernel
+    std::vector<ColDesc> cols; for (int g = 0; g < n_active; ++g) for (int j = 0; j < groups[g].ncols; ++j) cols.push_back(ColDesc{groups[g].base + 2 * j, groups[g].base + 2 * groups[g].ncols});
+    ColDesc* d_cols = E.dalloc<ColDesc>(cols.size()); E.h2d(d_cols, cols.data(), cols.size() * sizeof(ColDesc));
 
     SetCheckResult R; R.nvars = nvars; R.n_mat = (int)nM; R.ncols = (int)ncols; R.n_vec = (int)nV; R.n_M = (int)M.size();
     // MLSumcheck::prove_as_subprotocol (sumcheck.rs:53-80), degree 3
@@ -200,15 +203,18 @@ SetCheckResult set_check_core(Eng& E, Tr& T, int nvars, const std::vector<DevSet
         }
         const size_t n_pairs = len / 2; const unsigned nblk = (unsigned)std::min<size_t>(std::max<size_t>((n_pairs + 255) / 256, 1), 148 * 16);      // one pair per thread up to 2^19 pairs: the per-pair chain is long, occupancy hides it
         u64* partial = E.partial_dev((size_t)nblk * 4); u64* d_out = E.small_dev(4);
-        E.launch("k_plus_round", [&] { k_plus_round<<<nblk, 256, 0, E.st()>>>(cur, len, n_pairs, d_groups, n_active, d_w, partial); });
-        E.reduce_partials(partial, (int)nblk, 4, d_out);
+        const bool short_tables = n_pairs < 8192;      // a warp per pair: 8 pairs per block
+        const unsigned nblk_c = (unsigned)((n_pairs + 7) / 8);
+        if (short_tables) { partial = E.partial_dev((size_t)nblk_c * 4); E.launch("k_plus_round", [&] { k_plus_round_cols<<<nblk_c, 256, 0, E.st()>>>(cur, len, n_pairs, d_cols, (int)cols.size(), d_w, partial); }); }
+        else E.launch("k_plus_round", [&] { k_plus_round<<<nblk, 256, 0, E.st()>>>(cur, len, n_pairs, d_groups, n_active, d_w, partial); });
+        E.reduce_partials(partial, (int)(short_tables ? nblk_c : nblk), 4, d_out);
         u64 h[4]; E.download_words(d_out, 4, h);
         u64* msg = R.msgs.data() + (size_t)i * 4 * PD;
         for (int X = 0; X < 4; ++X) msg[X * PD] = Fm::from_mont(h[X]);      // constants of R
         T.absorb_slice(msg, 4);
         r_prev = challenge(T); absorb_field(T, r_prev); R.r.push_back(r_prev);
     }
-    E.dfree(Tb); E.dfree(Tn); E.dfree(d_groups); E.dfree(d_w);
+    E.dfree(Tb); E.dfree(Tn); E.dfree(d_groups); E.dfree(d_w); E.dfree(d_cols);
     // Step 3 (setchk.rs:199-257): e[0] = MLE(column)(r), e[1 + i] = MLE(M_i column)(r) = sum_x (M_i^T eq(r, .))[x] column[x], b = MLE(vector)(r)
     R.d_eq_r = E.dalloc<u64>(N); eq_table(E, R.r, R.d_eq_r, N);
     for (auto& m : M) { u64* wv = E.dalloc<u64>(std::max<size_t>(m.ncols, 1) * PD);
