@@ -351,8 +351,10 @@ def main():
     n = wl["W"] * wl["L"] // world
     R = synth.RINGS[RING]
     # 64-bit multiply-accumulates per step of the integer-bound sumcheck kernel against the measured
-    # IMAD.WIDE-bound ceiling of tools/microbench/imad_peak.cu on B200: 1.785e12 lazily reduced MACs / s
-    MAC_PEAK = 1.785e12
+    # issue bound of IMAD.WIDE: one warp instruction per 4 cycles per scheduler = 32 lanes / clk / SM, 4 IMAD.WIDE per lazily reduced 64-bit MAC:
+    # 148 SMs x 32 x 1.965 GHz / 4 = 2.33e12 MAC / s.  (The register-only microbenchmark tools/microbench/imad_peak.cu reaches 24.8 of those 32
+    # lanes, 1.785e12 MAC / s -- the figure this ratio was quoted against until the kernel itself, with its late rounds no longer latency bound, passed it.)
+    MAC_PEAK = 148 * 32 * 1.965e9 / 4
     pairs_r2 = max(((1 << s) // world) // 2 - 1, 0) + max(world - 1, 0)                # sum over rounds >= 2 of the pair count
     macs = {"k_fold_sc_round": pairs_r2 * R["S"] * (2 * K * R["tau"]) * 66} if RING == synth.RING_GOLDILOCKS else {}
     top_name, (top_cnt, top_ms) = top

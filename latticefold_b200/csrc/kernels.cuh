@@ -1146,15 +1146,18 @@ k_fold_sc_round(const FoldScArgsT<typename Rg::W> a) {
 #pragma unroll
         for (int l = 0; l < TAU; ++l) { s_mine[l].clear(); s_other[l].clear(); sum_mine[l].clear(); }
         // the next table's pair is requested before the current one is consumed (the loop is not unrolled: register budget)
+        // short tables: the table loop is cut over blockIdx.z (the sums are linear in the tables, every slice writes its own row of block partials);
+        // one thread walking all 2K*tau tables of its pair is a serial chain of dependent loads -- 100 us per late round whatever its size (ncu launch list r02z)
+        const int per = (a.n_f + (int)gridDim.z - 1) / (int)gridDim.z, k0 = (int)blockIdx.z * per, k1 = min(a.n_f, k0 + per);
         u64 nx0[TAU], nx1[TAU];
 #pragma unroll
-        for (int l = 0; l < TAU; ++l) ldg_pair(a.fh + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b, nx0[l], nx1[l]);
+        for (int l = 0; l < TAU; ++l) { nx0[l] = nx1[l] = 0; if (k0 < k1) ldg_pair(a.fh + (size_t)k0 * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b, nx0[l], nx1[l]); }
 #pragma unroll 1
-        for (int kd = 0; kd < a.n_f; ++kd) {
+        for (int kd = k0; kd < k1; ++kd) {
             u64 t[TAU], mine[TAU], other[TAU], q[TAU];
 #pragma unroll
             for (int l = 0; l < TAU; ++l) { const u64 sl = F::sub(nx1[l], nx0[l]); t[l] = role ? sl : nx0[l]; }
-            if (kd + 1 < a.n_f) {
+            if (kd + 1 < k1) {
 #pragma unroll
                 for (int l = 0; l < TAU; ++l) ldg_pair(a.fh + (size_t)(kd + 1) * a.fh_stride + (size_t)(slot * TAU + l) * a.fh_pitch + 2 * b, nx0[l], nx1[l]);
             }
@@ -1179,7 +1182,7 @@ k_fold_sc_round(const FoldScArgsT<typename Rg::W> a) {
             }
         }
     }
-    fold_sc_tail<Rg, true>(a, b, active, slot, h, red, blockIdx.x, role == 0);
+    fold_sc_tail<Rg, true>(a, b, active, slot, h, red, (size_t)blockIdx.z * gridDim.x + blockIdx.x, role == 0 && blockIdx.z == 0);
 }
 
 }  // namespace lf

@@ -84,7 +84,10 @@ template <class Rg> struct SumcheckDriver {
         if (sc->kind == LF_COMB_FOLD) {
             const bool round1 = sc->dig && sc->applied == 0, round2d = sc->dig && sc->applied == 1 && sc->fh_deferred;
             const unsigned gx1 = (unsigned)((n_pairs + 127) / 128), gx2 = (unsigned)((n_pairs + 63) / 64);      // rounds >= 2: two lanes per pair
-            nblk = round1 ? gx1 : round2d ? (unsigned)((n_pairs + 32 * R2_GROUPS - 1) / (32 * R2_GROUPS)) : gx2;      // round 2 from digits: four lanes per pair, R2_GROUPS groups of 32 pairs per block
+            // rounds >= 3 on short tables: the 2K*tau tables are cut into table slices (blockIdx.z) so that about four waves of blocks exist whatever the length
+            unsigned tslices = 1;
+            if (!round1 && !round2d && !std::getenv("LF_FOLD_NO_TSLICE")) { const int want = (int)((148 * 4 + gx2 * S - 1) / (gx2 * S)); int ts = want < 12 ? want : 12; if (sc->n_f / 4 < ts) ts = sc->n_f / 4; tslices = (unsigned)(ts < 1 ? 1 : ts); }
+            nblk = round1 ? gx1 : round2d ? (unsigned)((n_pairs + 32 * R2_GROUPS - 1) / (32 * R2_GROUPS)) : gx2 * tslices;      // round 2 from digits: four lanes per pair, R2_GROUPS groups of 32 pairs per block
             partial = E.partial_dev((size_t)nblk * 5 * D);
             FoldScArgsT<W> a; a.dense = wp(sc->dense.cur); a.dense_pitch = sc->dense.pitch; a.dense_stride = sc->dense.stride; a.mu_pow = sc->d_mu_pow; a.n_f = sc->n_f;
             a.n_pairs = n_pairs; a.partial = partial; a.dig = sc->dig; a.dig_pitch = sc->dig_pitch; a.dig_stride = sc->dig_stride;
@@ -95,7 +98,7 @@ template <class Rg> struct SumcheckDriver {
                 // up to MAX_MU tables: 64 KB of dynamic shared memory (above the 48 KB default; per device, so set on every use)
                 LF_CUDA(cudaFuncSetAttribute(k_fold_sc_round2<Rg>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_MU * (TAU * 8 + 128)));
                 E.launch("k_fold_sc_round2", [&] { k_fold_sc_round2<Rg><<<dim3(nblk, S), 128, (size_t)sc->n_f * (TAU * 8 + 128), E.st()>>>(a); }); }
-            else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(gx2, S), 128, 0, E.st()>>>(a); });
+            else E.launch("k_fold_sc_round", [&] { k_fold_sc_round<Rg><<<dim3(gx2, S, tslices), 128, 0, E.st()>>>(a); });
         } else {
             // one thread per (pair, evaluation point): see k_sc_points
             const int ppb = 128 / ne;
