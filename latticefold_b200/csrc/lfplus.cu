@@ -45,6 +45,14 @@ struct DevSparse {
     void free(Eng& E) { if (borrowed) return; E.dfree(col_ptr); E.dfree(erow); E.dfree(ecol); E.dfree(val); col_ptr = nullptr; erow = ecol = nullptr; val = nullptr; }
 };
 void check_canonical(const u64* v, size_t n, const char* what) { for (size_t i = 0; i < n; ++i) if (v[i] >= Fm::P) throw LfException(LF_ERR_INVALID_ARG, std::string(what) + ": non-canonical field element"); }
+void validate_csr(const lf_csr& m) {      // the checks of upload_by_columns without the upload
+    if (!m.row_ptr || (m.row_ptr[m.nrows] && (!m.col || !m.val))) throw LfException(LF_ERR_INVALID_ARG, "sparse matrix: null arrays");
+    const size_t nnz = m.row_ptr[m.nrows];
+    if (m.nrows >> 32 || m.ncols >> 32) throw LfException(LF_ERR_UNSUPPORTED, "sparse matrix: more than 2^32 rows / columns");
+    for (size_t r = 0; r < m.nrows; ++r) if (m.row_ptr[r + 1] < m.row_ptr[r] || m.row_ptr[r + 1] > nnz) throw LfException(LF_ERR_INVALID_ARG, "sparse matrix: row_ptr not monotone");
+    for (size_t e = 0; e < nnz; ++e) if (m.col[e] >= m.ncols) throw LfException(LF_ERR_INVALID_ARG, "sparse matrix: column index out of range");
+    check_canonical(m.val, nnz * PD, "sparse matrix");
+}
 DevSparse upload_by_columns_raw(Eng& E, const lf_csr& m) {
     if (!m.row_ptr || (m.row_ptr[m.nrows] && (!m.col || !m.val))) throw LfException(LF_ERR_INVALID_ARG, "sparse matrix: null arrays");
     const size_t nnz = m.row_ptr[m.nrows];
@@ -326,13 +334,13 @@ DevCsr upload_csr_raw(Eng& E, const lf_csr& m) {      // validated by upload_by_
 struct Pinned { lf_ctx* ctx; const u64 *row_ptr, *col, *val; u64 nrows, ncols; DevSparse by_col; DevCsr by_row; };
 std::vector<Pinned>& pinned_list() { static std::vector<Pinned> v; return v; }
 std::mutex& pinned_mutex() { static std::mutex m; return m; }
-const Pinned* find_pinned(lf_ctx* c, const lf_csr& m) {
+bool find_pinned(lf_ctx* c, const lf_csr& m, Pinned* out = nullptr) {      // (a copy under the lock: another context's pin may grow the list)
     std::lock_guard<std::mutex> g(pinned_mutex());
-    for (auto& p : pinned_list()) if (p.ctx == c && p.row_ptr == m.row_ptr && p.col == m.col && p.val == m.val && p.nrows == m.nrows && p.ncols == m.ncols) return &p;
-    return nullptr;
+    for (auto& p : pinned_list()) if (p.ctx == c && p.row_ptr == m.row_ptr && p.col == m.col && p.val == m.val && p.nrows == m.nrows && p.ncols == m.ncols) { if (out) *out = p; return true; }
+    return false;
 }
-DevSparse upload_by_columns(Eng& E, const lf_csr& m) { if (const Pinned* p = find_pinned(E.c, m)) { DevSparse s = p->by_col; s.borrowed = true; return s; } return upload_by_columns_raw(E, m); }
-DevCsr upload_csr(Eng& E, const lf_csr& m) { if (const Pinned* p = find_pinned(E.c, m)) { DevCsr s = p->by_row; s.borrowed = true; return s; } return upload_csr_raw(E, m); }
+DevSparse upload_by_columns(Eng& E, const lf_csr& m) { Pinned p; if (find_pinned(E.c, m, &p)) { DevSparse s = p.by_col; s.borrowed = true; return s; } return upload_by_columns_raw(E, m); }
+DevCsr upload_csr(Eng& E, const lf_csr& m) { Pinned p; if (find_pinned(E.c, m, &p)) { DevCsr s = p.by_row; s.borrowed = true; return s; } return upload_csr_raw(E, m); }
 
 // dense ring-valued MLE (len elements, zero tail) at a base-field point, by successive halving
 void mle_eval_dense(std::vector<u64> ev, int nv, const std::vector<u64>& point, u64* out) {
@@ -536,7 +544,7 @@ std::vector<u64> r1cs_linearize_core(Eng& E, Tr& T, const lf_csr* abc, const u64
     struct Cleanup { Eng& E; std::vector<DevCsr>& b; std::vector<void*>& blk; ~Cleanup() { for (auto& s : b) s.free(E); for (void* p : blk) E.dfree(p); } } cl{E, Mr, blocks};
     auto alloc = [&](size_t words) { u64* p = E.dalloc<u64>(words); blocks.push_back(p); return p; };
     if (!f_on_device) check_canonical(f, n * PD, "linearize witness");
-    for (int i = 0; i < 3; ++i) { if (!find_pinned(E.c, abc[i])) { DevSparse tmp = upload_by_columns_raw(E, abc[i]); tmp.free(E); }      // (validates the arrays of a matrix seen for the first time)
+    for (int i = 0; i < 3; ++i) { if (!find_pinned(E.c, abc[i])) validate_csr(abc[i]);      // (a pinned matrix was validated when it was pinned)
         if (abc[i].ncols != n || abc[i].nrows > N) throw LfException(LF_ERR_LENGTHS_NOT_EQUAL, "linearize: R1CS matrix does not match the witness"); Mr.push_back(upload_csr(E, abc[i])); }
     u64 *d_f = alloc(n * PD), *G = alloc(3 * N * PD), *Gn = alloc(3 * N * PD / 2), *Gm = alloc(3 * N * PD / 4 + PD), *eq = alloc(N), *eqn = alloc(N / 2 + 1), *eqm = alloc(N / 4 + 1), *cp = alloc(2);
     LF_CUDA(cudaMemcpyAsync(d_f, f, n * PD * 8, f_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, E.st())); LF_CUDA(cudaMemsetAsync(G, 0, 3 * N * PD * 8, E.st()));
@@ -586,6 +594,7 @@ lf_status lf_plus_set_check(lf_ctx* c, lf_transcript* t, int32_t nvars, const lf
         std::vector<DevSparse> store; store.reserve((size_t)n_sets + n_M); std::vector<DevSet> mats, vecs; std::vector<DevSparse> Ms; SetCheckResult R;
         struct Cleanup { Eng& E; std::vector<DevSparse>& a; std::vector<DevSparse>& b; SetCheckResult& r; ~Cleanup() { for (auto& s : a) s.free(E); for (auto& s : b) s.free(E); r.free(E); } } cl{E, store, Ms, R};
         for (int i = 0; i < n_sets; ++i) {
+            if (sets[i].kind != 0 && sets[i].kind != 1) throw LfException(LF_ERR_INVALID_ARG, "set check: unknown set kind");
             store.push_back(sets[i].kind == 0 ? upload_by_columns(E, sets[i].m) : upload_dense_vector(E, sets[i].v, sets[i].n));
             DevSet s; s.gen = &store.back(); s.nrows = store.back().nrows; s.ncols = store.back().ncols; (sets[i].kind == 0 ? mats : vecs).push_back(s);
         }
